@@ -1,0 +1,521 @@
+"""differential-equations_b200 -- host-side mirror of the reference's operator API over the B200 C ABI.
+
+The reference (Ryan-D-Gast/differential-equations v0.6.1) is a Rust crate; this image has no Rust toolchain, so
+the host layer above the C ABI (include/deb_ensemble.h, libdeb200.so) is written here in Python with the same
+names, argument meaning and error behaviour as the crate's builder API, so the parity tests read like the
+reference's own tests:
+
+    reference (Rust)                                            this module
+    ---------------------------------------------------------   -----------------------------------------------
+    ExplicitRungeKutta::dopri5().rtol(1e-8)                      ExplicitRungeKutta.dopri5().rtol(1e-8)
+      src/methods/erk/dormandprince/mod.rs:45-58, erk/mod.rs:164-228
+    ExplicitRungeKutta::rk4(h)  / euler(h) ...                   ExplicitRungeKutta.rk4(h) / .euler(h) ...
+      src/methods/erk/fixed/mod.rs:41-89
+    IVP::ode(&sys, t0, tf, y0).t_eval(pts).method(m).solve()     EnsembleIVP.ode(sys, t0, tf, y0s).t_eval(pts).method(m).solve()
+      src/ivp.rs:279,656,632,781
+    IVP::sde(&mut sde, t0, tf, y0)...                            EnsembleIVP.sde(sde, t0, tf, y0s, seed=...)...
+      src/ivp.rs:504,857
+    Solution{t, y, status, evals, steps}                         EnsembleSolution[i] -> Solution  (or raises the Error)
+      src/solution.rs:30-53, src/error.rs:13-41
+
+The one difference is the ensemble axis: `y0s` is an (N, dim) array of initial states and a system carries either
+one parameter set or an (N, n_params) array (a parameter sweep); `solve()` returns all N results at once.
+
+PyTorch is not needed by this module (ctypes + numpy); bench.py uses torch only for device buffers and streams.
+The CUDA extension is mandatory: importing works without it (so CPU-only tooling can read the constants), but
+any solve raises if libdeb200.so is missing or no GPU is present -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdeb200.so")
+
+# ---------------------------------------------------------------------------------------------- enums (deb_ensemble.h)
+DEB_EULER, DEB_MIDPOINT, DEB_HEUN, DEB_RALSTON, DEB_SSP_RK3, DEB_RK4, DEB_THREE_EIGHTHS = range(7)
+DEB_DOPRI5, DEB_DOP853 = 16, 17
+(DEB_SYS_EXPONENTIAL, DEB_SYS_LINEAR, DEB_SYS_HARMONIC, DEB_SYS_LOGISTIC, DEB_SYS_VAN_DER_POL, DEB_SYS_LORENZ,
+ DEB_SYS_BRUSSELATOR) = range(7)
+DEB_SDE_OU, DEB_SDE_GBM = 0, 1
+DEB_STATUS_COMPLETE, DEB_STATUS_MAX_STEPS, DEB_STATUS_STEP_SIZE, DEB_STATUS_STIFFNESS, DEB_STATUS_BAD_INPUT = range(5)
+DEB_MEM_HOST, DEB_MEM_DEVICE = 0, 1
+DEB_OK, DEB_ERR_BAD_ARG, DEB_ERR_NO_DEVICE, DEB_ERR_CUDA, DEB_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
+DEB_ABI_VERSION = 1
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+
+class ErkOptions(C.Structure):
+    _fields_ = [("rtol", C.c_double), ("atol", C.c_double), ("rtol_vec", _dp), ("atol_vec", _dp), ("h0", C.c_double),
+                ("h_min", C.c_double), ("h_max", C.c_double), ("max_steps", C.c_int64), ("safety_factor", C.c_double),
+                ("min_scale", C.c_double), ("max_scale", C.c_double)]
+
+
+class OdeProblem(C.Structure):
+    _fields_ = [("struct_size", C.c_size_t), ("system", C.c_int32), ("method", C.c_int32), ("dim", C.c_int32),
+                ("n_params", C.c_int32), ("n_traj", C.c_int64), ("y0", C.c_void_p), ("params", C.c_void_p),
+                ("params_shared", C.c_int32), ("n_eval", C.c_int32), ("t_eval", _dp), ("t0", C.c_double), ("tf", C.c_double),
+                ("opt", ErkOptions), ("device", C.c_int32), ("memspace", C.c_int32), ("stream", C.c_void_p)]
+
+
+class SdeProblem(C.Structure):
+    _fields_ = [("struct_size", C.c_size_t), ("system", C.c_int32), ("method", C.c_int32), ("dim", C.c_int32),
+                ("n_params", C.c_int32), ("n_traj", C.c_int64), ("y0", C.c_void_p), ("y0_shared", C.c_int32),
+                ("params_shared", C.c_int32), ("params", C.c_void_p), ("n_eval", C.c_int32), ("t_eval", _dp),
+                ("t0", C.c_double), ("tf", C.c_double), ("opt", ErkOptions), ("seed", C.c_uint64), ("path_offset", C.c_int64),
+                ("device", C.c_int32), ("memspace", C.c_int32), ("stream", C.c_void_p)]
+
+
+class Result(C.Structure):
+    _fields_ = [("struct_size", C.c_size_t), ("y_eval", C.c_void_p), ("n_emitted", C.c_void_p), ("t_final", C.c_void_p),
+                ("y_final", C.c_void_p), ("status", C.c_void_p), ("accepted", C.c_void_p), ("rejected", C.c_void_p),
+                ("evals", C.c_void_p), ("t_rows", _dp), ("n_rows", C.c_int32), ("kernel_ms", C.c_float),
+                ("total_ms", C.c_float)]
+
+
+class HeatProblem(C.Structure):
+    _fields_ = [("struct_size", C.c_size_t), ("n_nodes", C.c_int64), ("lo", C.c_double), ("hi", C.c_double),
+                ("alpha", C.c_double), ("bc_lower_kind", C.c_int32), ("bc_upper_kind", C.c_int32),
+                ("bc_lower_value", C.c_double), ("bc_upper_value", C.c_double), ("method", C.c_int32), ("h", C.c_double),
+                ("t0", C.c_double), ("tf", C.c_double), ("max_steps", C.c_int64), ("u0", C.c_void_p), ("u_final", C.c_void_p),
+                ("t_final", _dp), ("steps", C.POINTER(C.c_int64)), ("status", _ip), ("device", C.c_int32),
+                ("memspace", C.c_int32), ("stream", C.c_void_p)]
+
+
+# every symbol include/deb_ensemble.h declares (tests check that the library exports all of them)
+ABI_SYMBOLS = ["deb_abi_version", "deb_last_error", "deb_device_count", "deb_erk_options_default", "deb_solve_ode",
+               "deb_solve_sde", "deb_solve_heat_mol", "deb_heat_rhs", "deb_ensemble_stats", "deb_malloc", "deb_free", "deb_memcpy_h2d",
+               "deb_memcpy_d2h", "deb_synchronize", "deb_pow_device", "deb_fp64_issue_peak"]
+
+_lib = None
+
+
+class ExtensionMissing(RuntimeError):
+    pass
+
+
+def load_library() -> C.CDLL:
+    """dlopen libdeb200.so (built in-tree by __graft_entry__.build()).  Fails loudly if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ExtensionMissing(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU fallback for the ensemble kernels)")
+    lib = C.CDLL(LIB_PATH)
+    lib.deb_last_error.restype = C.c_char_p
+    lib.deb_solve_ode.argtypes = [C.POINTER(OdeProblem), C.POINTER(Result)]
+    lib.deb_solve_sde.argtypes = [C.POINTER(SdeProblem), C.POINTER(Result)]
+    lib.deb_solve_heat_mol.argtypes = [C.POINTER(HeatProblem)]
+    lib.deb_heat_rhs.argtypes = [C.POINTER(HeatProblem), C.c_void_p, C.c_void_p]
+    lib.deb_erk_options_default.argtypes = [C.POINTER(ErkOptions)]
+    lib.deb_erk_options_default.restype = None
+    lib.deb_ensemble_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                       C.c_int32, C.c_int32, C.c_void_p]
+    lib.deb_pow_device.argtypes = [_dp, C.c_double, C.c_int64, _dp, C.c_int32]
+    lib.deb_fp64_issue_peak.argtypes = [C.c_int32, C.c_int32, _dp, C.POINTER(C.c_float)]
+    lib.deb_malloc.argtypes = [C.c_int32, C.c_size_t, C.POINTER(C.c_void_p)]
+    lib.deb_free.argtypes = [C.c_int32, C.c_void_p]
+    lib.deb_memcpy_h2d.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.deb_memcpy_d2h.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.deb_synchronize.argtypes = [C.c_int32]
+    _lib = lib
+    return lib
+
+
+def _check(lib, rc: int, what: str):
+    if rc != DEB_OK:
+        msg = lib.deb_last_error().decode("utf-8", "replace")
+        if rc == DEB_ERR_NO_DEVICE:
+            raise RuntimeError(f"{what}: no CUDA device ({msg}); the product path has no CPU fallback")
+        if rc == DEB_ERR_BAD_ARG:
+            raise ValueError(f"{what}: {msg}")
+        raise RuntimeError(f"{what}: error {rc}: {msg}")
+
+
+# ---------------------------------------------------------------------------------------------- errors / status
+class Error(Exception):
+    """Mirror of `Error<T, Y>` (src/error.rs:13-41)."""
+
+
+class BadInput(Error):
+    pass
+
+
+class MaxSteps(Error):
+    def __init__(self, t, y):
+        super().__init__(f"MaxSteps {{ t: {t}, y: {y} }}")
+        self.t, self.y = t, y
+
+
+class StepSize(Error):
+    def __init__(self, t, y):
+        super().__init__(f"StepSize {{ t: {t}, y: {y} }}")
+        self.t, self.y = t, y
+
+
+class Stiffness(Error):
+    def __init__(self, t, y):
+        super().__init__(f"Stiffness {{ t: {t}, y: {y} }}")
+        self.t, self.y = t, y
+
+
+@dataclass
+class Evals:  # src/stats.rs:16
+    function: int = 0
+
+
+@dataclass
+class Steps:  # src/stats.rs:69
+    accepted: int = 0
+    rejected: int = 0
+
+
+@dataclass
+class Solution:
+    """Mirror of `Solution<T, Y>` (src/solution.rs:30-53) for one trajectory."""
+    t: np.ndarray
+    y: np.ndarray
+    status: str
+    evals: Evals
+    steps: Steps
+    t_final: float = math.nan
+    y_final: Optional[np.ndarray] = None
+
+
+# ---------------------------------------------------------------------------------------------- systems
+@dataclass
+class OdeSystem:
+    """A built-in `ODE` (src/ode/ode.rs:20-44): id + parameters (one set, or one row per trajectory)."""
+    system_id: int
+    dim: int
+    params: np.ndarray  # (n_params,) or (N, n_params)
+
+
+def ExponentialGrowth(k): return OdeSystem(DEB_SYS_EXPONENTIAL, 1, _params(k))            # tests/ode/systems.rs:8-16
+def LinearEquation(a, b): return OdeSystem(DEB_SYS_LINEAR, 1, _params(a, b))               # :20-29
+def HarmonicOscillator(k): return OdeSystem(DEB_SYS_HARMONIC, 2, _params(k))               # :33-43
+def LogisticEquation(k, m): return OdeSystem(DEB_SYS_LOGISTIC, 1, _params(k, m))           # :48-59
+def VanDerPolOscillator(mu): return OdeSystem(DEB_SYS_VAN_DER_POL, 2, _params(mu))         # :66-78
+def LorenzSystem(sigma, rho, beta): return OdeSystem(DEB_SYS_LORENZ, 3, _params(sigma, rho, beta))  # :85-101
+def BrusselatorSystem(a, b): return OdeSystem(DEB_SYS_BRUSSELATOR, 2, _params(a, b))       # :106-120
+
+
+@dataclass
+class SdeSystem:
+    system_id: int
+    params: np.ndarray
+
+
+def OrnsteinUhlenbeck(theta, mu, sigma): return SdeSystem(DEB_SDE_OU, _params(theta, mu, sigma))
+def GeometricBrownianMotion(mu, sigma): return SdeSystem(DEB_SDE_GBM, _params(mu, sigma))
+
+
+def _params(*cols) -> np.ndarray:
+    arrs = [np.asarray(c, dtype=np.float64) for c in cols]
+    if all(a.ndim == 0 for a in arrs):
+        return np.array([float(a) for a in arrs], dtype=np.float64)
+    n = max(a.shape[0] for a in arrs if a.ndim == 1)
+    out = np.empty((n, len(arrs)), dtype=np.float64)
+    for j, a in enumerate(arrs):
+        out[:, j] = a
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- method builder
+class ExplicitRungeKutta:
+    """Mirror of `ExplicitRungeKutta` constructors and setters (src/methods/erk/mod.rs:135-228)."""
+
+    def __init__(self, method_id: int, h0: float = 0.0):
+        self.method_id = method_id
+        self._rtol = 1.0e-6
+        self._atol = 1.0e-6
+        self._h0 = float(h0)
+        self._h_min = 0.0
+        self._h_max = math.inf
+        self._max_steps = 10_000
+        self._max_rejects = 100  # accepted for API parity; the Dormand-Prince stepper never reads it
+        self._safety_factor = 0.9
+        self._min_scale = 0.2
+        self._max_scale = 10.0
+
+    # constructors: dormandprince/mod.rs:45-58, fixed/mod.rs:41-89
+    @classmethod
+    def dopri5(cls): return cls(DEB_DOPRI5)
+    @classmethod
+    def dop853(cls): return cls(DEB_DOP853)
+    @classmethod
+    def euler(cls, h0): return cls(DEB_EULER, h0)
+    @classmethod
+    def midpoint(cls, h0): return cls(DEB_MIDPOINT, h0)
+    @classmethod
+    def heun(cls, h0): return cls(DEB_HEUN, h0)
+    @classmethod
+    def ralston(cls, h0): return cls(DEB_RALSTON, h0)
+    @classmethod
+    def ssp_rk3(cls, h0): return cls(DEB_SSP_RK3, h0)
+    @classmethod
+    def rk4(cls, h0): return cls(DEB_RK4, h0)
+    @classmethod
+    def three_eighths(cls, h0): return cls(DEB_THREE_EIGHTHS, h0)
+
+    def rtol(self, v): self._rtol = v; return self
+    def atol(self, v): self._atol = v; return self
+    def h0(self, v): self._h0 = float(v); return self
+    def h_min(self, v): self._h_min = float(v); return self
+    def h_max(self, v): self._h_max = float(v); return self
+    def max_steps(self, v): self._max_steps = int(v); return self
+    def max_rejects(self, v): self._max_rejects = int(v); return self
+    def safety_factor(self, v): self._safety_factor = float(v); return self
+    def min_scale(self, v): self._min_scale = float(v); return self
+    def max_scale(self, v): self._max_scale = float(v); return self
+
+    def fill_options(self, opt: ErkOptions, dim: int, keep: list):
+        def tol(v, name):
+            if np.ndim(v) == 0:
+                return float(v), None
+            arr = np.ascontiguousarray(v, dtype=np.float64)
+            if arr.shape != (dim,):
+                raise ValueError(f"{name} vector must have {dim} entries")
+            keep.append(arr)
+            return float(arr[0]), arr.ctypes.data_as(_dp)
+        opt.rtol, opt.rtol_vec = tol(self._rtol, "rtol")
+        opt.atol, opt.atol_vec = tol(self._atol, "atol")
+        opt.h0, opt.h_min, opt.h_max = self._h0, self._h_min, self._h_max
+        opt.max_steps = self._max_steps
+        opt.safety_factor, opt.min_scale, opt.max_scale = self._safety_factor, self._min_scale, self._max_scale
+
+
+# ---------------------------------------------------------------------------------------------- results
+_STATUS_NAME = {DEB_STATUS_COMPLETE: "Complete", DEB_STATUS_MAX_STEPS: "MaxSteps", DEB_STATUS_STEP_SIZE: "StepSize",
+                DEB_STATUS_STIFFNESS: "Stiffness", DEB_STATUS_BAD_INPUT: "BadInput"}
+
+
+class EnsembleSolution:
+    """All N results of one ensemble solve, as flat arrays plus a per-trajectory `Solution` view."""
+
+    def __init__(self, n, dim, t_rows, y_eval, n_emitted, t_final, y_final, status, accepted, rejected, evals, kernel_ms,
+                 total_ms):
+        self.n, self.dim = n, dim
+        self.t_rows = t_rows            # times of the rows a trajectory can emit, in integration order
+        self.y_eval = y_eval            # (N, n_eval, dim); rows >= n_emitted[i] are unspecified
+        self.n_emitted = n_emitted
+        self.t_final, self.y_final = t_final, y_final
+        self.status, self.accepted, self.rejected, self.evals = status, accepted, rejected, evals
+        self.kernel_ms, self.total_ms = kernel_ms, total_ms
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i) -> Solution:
+        """`Result<Solution, Error>` of trajectory i: returns the Solution or raises the reference's Error variant."""
+        st = int(self.status[i])
+        yf = self.y_final[i].copy()
+        tfin = float(self.t_final[i])
+        if st == DEB_STATUS_BAD_INPUT:
+            raise BadInput("Invalid input")
+        if st == DEB_STATUS_MAX_STEPS:
+            raise MaxSteps(tfin, yf)
+        if st == DEB_STATUS_STEP_SIZE:
+            raise StepSize(tfin, yf)
+        if st == DEB_STATUS_STIFFNESS:
+            raise Stiffness(tfin, yf)
+        m = int(self.n_emitted[i])
+        return Solution(t=self.t_rows[:m].copy(), y=self.y_eval[i, :m].copy(), status="Complete",
+                        evals=Evals(int(self.evals[i])), steps=Steps(int(self.accepted[i]), int(self.rejected[i])),
+                        t_final=tfin, y_final=yf)
+
+    def status_names(self) -> List[str]:
+        return [_STATUS_NAME[int(s)] for s in self.status]
+
+
+def alloc_result_arrays(n, n_eval, dim):
+    return dict(y_eval=np.full((n, max(n_eval, 0), dim), np.nan), n_emitted=np.zeros(n, np.int32), t_final=np.zeros(n),
+                y_final=np.zeros((n, dim)), status=np.full(n, -1, np.int32), accepted=np.zeros(n, np.int32),
+                rejected=np.zeros(n, np.int32), evals=np.zeros(n, np.int32))
+
+
+def bind_result(res: Result, arrs: dict, t_sorted: np.ndarray):
+    res.struct_size = C.sizeof(Result)
+    for k in ("y_eval", "n_emitted", "t_final", "y_final", "status", "accepted", "rejected", "evals"):
+        a = arrs.get(k)
+        setattr(res, k, a.ctypes.data if a is not None and a.size > 0 else None)
+    res.t_rows = t_sorted.ctypes.data_as(_dp) if t_sorted.size else None
+
+
+# ---------------------------------------------------------------------------------------------- the builder
+class EnsembleIVP:
+    """Mirror of the `IVP` builder (src/ivp.rs) for an ensemble of N problems sharing (t0, tf, method)."""
+
+    def __init__(self, kind, system, t0, tf, y0s, seed=0, path_offset=0):
+        self.kind, self.system = kind, system
+        self.t0, self.tf = float(t0), float(tf)
+        y0s = np.ascontiguousarray(y0s, dtype=np.float64)
+        if kind == "ode":
+            if y0s.ndim == 1:
+                y0s = y0s.reshape(1, -1) if system.dim > 1 or y0s.shape[0] == 1 else y0s.reshape(-1, 1)
+            if y0s.ndim != 2 or y0s.shape[1] != system.dim:
+                raise ValueError(f"y0 must have shape (N, {system.dim})")
+        else:
+            y0s = y0s.reshape(-1)
+        self.y0s = y0s
+        self._t_eval = np.zeros(0)
+        self._method: Optional[ExplicitRungeKutta] = None
+        self._device = 0
+        self.seed, self.path_offset = int(seed), int(path_offset)
+
+    @classmethod
+    def ode(cls, system: OdeSystem, t0, tf, y0s):  # IVP::ode, ivp.rs:279
+        return cls("ode", system, t0, tf, y0s)
+
+    @classmethod
+    def sde(cls, system: SdeSystem, t0, tf, y0s, seed=0, path_offset=0):  # IVP::sde, ivp.rs:504
+        return cls("sde", system, t0, tf, y0s, seed, path_offset)
+
+    def t_eval(self, pts: Sequence[float]):  # ivp.rs:656
+        self._t_eval = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1)
+        return self
+
+    def method(self, m: ExplicitRungeKutta):  # ivp.rs:632
+        self._method = m
+        return self
+
+    def rtol(self, v):  # ivp.rs:764 (ToleranceConfig forwarding)
+        self._method.rtol(v); return self
+
+    def atol(self, v):  # ivp.rs:771
+        self._method.atol(v); return self
+
+    def device(self, ordinal: int):
+        self._device = int(ordinal)
+        return self
+
+    def build_problem(self):
+        """Assemble the C-ABI problem/result structs for this builder (host buffers).  Returns
+        (problem, result, result_arrays, t_sorted, keepalive)."""
+        if self._method is None:
+            raise ValueError("method(...) must be set before solve()")
+        n = int(self.y0s.shape[0])
+        keep: list = []
+        n_eval = int(self._t_eval.size)
+        res = Result()
+        t_sorted = np.zeros(max(n_eval, 1))
+        if self.kind == "ode":
+            sysm = self.system
+            dim = sysm.dim
+            P = OdeProblem()
+            P.struct_size = C.sizeof(OdeProblem)
+            P.system, P.method, P.dim = sysm.system_id, self._method.method_id, dim
+            params = np.ascontiguousarray(sysm.params, dtype=np.float64)
+        else:
+            dim = 1
+            P = SdeProblem()
+            P.struct_size = C.sizeof(SdeProblem)
+            P.system, P.method, P.dim = self.system.system_id, self._method.method_id, 1
+            params = np.ascontiguousarray(self.system.params, dtype=np.float64)
+            P.y0_shared = 0
+            P.seed, P.path_offset = self.seed, self.path_offset
+        if params.ndim == 2 and params.shape[0] != n:
+            raise ValueError("params must have one row per trajectory")
+        P.params_shared = 1 if params.ndim == 1 else 0
+        P.n_params = params.shape[-1]
+        P.y0 = self.y0s.ctypes.data
+        P.n_traj = n
+        P.params = params.ctypes.data
+        P.n_eval = n_eval
+        P.t_eval = self._t_eval.ctypes.data_as(_dp) if n_eval else None
+        P.t0, P.tf = self.t0, self.tf
+        self._method.fill_options(P.opt, dim, keep)
+        P.device, P.memspace, P.stream = self._device, DEB_MEM_HOST, None
+        arrs = alloc_result_arrays(n, n_eval, dim)
+        bind_result(res, arrs, t_sorted)
+        keep += [params, self.y0s, self._t_eval]
+        return P, res, arrs, t_sorted, keep
+
+    def solve(self, lib=None) -> EnsembleSolution:  # ivp.rs:781 / :857
+        """Run the ensemble on the GPU through the C ABI (deb_solve_ode / deb_solve_sde)."""
+        lib = lib or load_library()
+        P, res, arrs, t_sorted, keep = self.build_problem()
+        if self.kind == "ode":
+            _check(lib, lib.deb_solve_ode(C.byref(P), C.byref(res)), "deb_solve_ode")
+        else:
+            _check(lib, lib.deb_solve_sde(C.byref(P), C.byref(res)), "deb_solve_sde")
+        rows = t_sorted[:res.n_rows].copy()
+        return self.wrap_result(arrs, rows, res)
+
+    def wrap_result(self, arrs, rows, res) -> EnsembleSolution:
+        n = int(self.y0s.shape[0])
+        dim = self.system.dim if self.kind == "ode" else 1
+        return EnsembleSolution(n, dim, rows, arrs["y_eval"], arrs["n_emitted"], arrs["t_final"], arrs["y_final"],
+                                arrs["status"], arrs["accepted"], arrs["rejected"], arrs["evals"], res.kernel_ms, res.total_ms)
+
+
+def _plan_rows(t_eval: np.ndarray, t0: float, tf: float) -> np.ndarray:
+    """Times of the rows TEvalSolout can emit (t_eval.rs:87-171): sorted by direction; points not after t0 are
+    consumed by the first solout call, which emits only a leading point equal to t0."""
+    if t_eval.size == 0:
+        return np.zeros(0)
+    fwd = tf >= t0
+    pts = np.sort(t_eval, kind="stable") if fwd else np.sort(t_eval, kind="stable")[::-1]
+    rows = []
+    for i, v in enumerate(pts):
+        if i == 0 and v == t0:
+            rows.append(v)
+        elif (v > t0) if fwd else (v < t0):
+            rows.append(v)
+    return np.asarray(rows, dtype=np.float64)
+
+
+# ---------------------------------------------------------------------------------------------- method of lines (heat)
+@dataclass
+class HeatSolution:
+    u: np.ndarray
+    t: float
+    steps: int
+    status: str
+
+
+def build_heat_problem(u0, lo, hi, alpha, method: ExplicitRungeKutta, t0, tf, bc_lower, bc_upper, device=0):
+    u0 = np.ascontiguousarray(u0, dtype=np.float64)
+    out = np.empty_like(u0)
+    P = HeatProblem()
+    P.struct_size = C.sizeof(HeatProblem)
+    P.n_nodes, P.lo, P.hi, P.alpha = u0.size, lo, hi, alpha
+    kinds = {"dirichlet": 0, "neumann": 1}
+    P.bc_lower_kind, P.bc_lower_value = kinds[bc_lower[0]], bc_lower[1]
+    P.bc_upper_kind, P.bc_upper_value = kinds[bc_upper[0]], bc_upper[1]
+    P.method, P.h, P.t0, P.tf, P.max_steps = method.method_id, method._h0, t0, tf, method._max_steps
+    P.u0, P.u_final = u0.ctypes.data, out.ctypes.data
+    tfin, steps, status = C.c_double(0), C.c_int64(0), C.c_int32(-1)
+    P.t_final, P.steps, P.status = C.pointer(tfin), C.pointer(steps), C.pointer(status)
+    P.device, P.memspace, P.stream = device, DEB_MEM_HOST, None
+    return P, out, (tfin, steps, status), [u0]
+
+
+def solve_heat_mol(u0, lo, hi, alpha, method: ExplicitRungeKutta, t0, tf, bc_lower=("dirichlet", 0.0),
+                   bc_upper=("dirichlet", 0.0), device=0, lib=None) -> HeatSolution:
+    """IVP::pde(&heat, t0, tf, u0).space(MethodOfLines::finite_difference(grid).boundary(bc)).method(rk4(h)).solve()
+    (src/ivp.rs:419,713; tests/pde/method_of_lines.rs:37-70) on one GPU."""
+    lib = lib or load_library()
+    P, out, (tfin, steps, status), keep = build_heat_problem(u0, lo, hi, alpha, method, t0, tf, bc_lower, bc_upper, device)
+    _check(lib, lib.deb_solve_heat_mol(C.byref(P)), "deb_solve_heat_mol")
+    return HeatSolution(out, tfin.value, steps.value, _STATUS_NAME.get(status.value, "?"))
+
+
+def heat_rhs(u, lo, hi, alpha, bc_lower=("dirichlet", 0.0), bc_upper=("dirichlet", 0.0), device=0, lib=None) -> np.ndarray:
+    """`MethodOfLines::finite_difference(grid).boundary(bc).discretize(&heat).diff(t, &y, &mut dydt)`
+    (tests/pde/method_of_lines.rs:73-157) evaluated on the GPU."""
+    lib = lib or load_library()
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    P, _out, _s, keep = build_heat_problem(u, lo, hi, alpha, ExplicitRungeKutta.euler(0.0), 0.0, 1.0, bc_lower, bc_upper, device)
+    du = np.empty_like(u)
+    _check(lib, lib.deb_heat_rhs(C.byref(P), u.ctypes.data, du.ctypes.data), "deb_heat_rhs")
+    return du

@@ -1,0 +1,802 @@
+// deb_api.cu -- implementation of the C ABI declared in include/deb_ensemble.h (libdeb200.so).
+//
+// Host side of the drop-in boundary: validates the problem like the reference's builder does, sorts/filters
+// t_eval like TEvalSolout::new (/root/reference/src/solout/t_eval.rs:154-171), stages buffers, picks the kernel
+// instantiation for (system, method) and launches it.  There is no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/deb_ensemble.h"
+#include "ens_stats.cuh"
+#include "erk_ensemble.cuh"
+#include "erk_fixed.cuh"
+#include "mol_heat.cuh"
+#include "sde_ensemble.cuh"
+#include "systems.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define DEB_CUDA(call)                                                                                  \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            char buf_[512];                                                                             \
+            snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? DEB_ERR_NO_DEVICE : DEB_ERR_CUDA, buf_); \
+        }                                                                                               \
+    } while (0)
+
+int select_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(DEB_ERR_NO_DEVICE, std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                                           "); the ensemble integrator has no CPU fallback");
+    if (device < 0 || device >= n) return fail(DEB_ERR_BAD_ARG, "device ordinal out of range");
+    DEB_CUDA(cudaSetDevice(device));
+    return DEB_OK;
+}
+
+struct DeviceInfo { int sms = 0; };
+int device_info(int device, DeviceInfo* di) {
+    static std::mutex mu;
+    static std::vector<DeviceInfo> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    if ((int)cache.size() <= device) cache.resize(device + 1);
+    if (cache[device].sms == 0) {
+        int sms = 0;
+        DEB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        cache[device].sms = sms;
+    }
+    *di = cache[device];
+    return DEB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ kernel table
+typedef int (*ode_launch_fn)(const deb::OdeKernelArgs&, int sms, cudaStream_t);
+
+template <class Sys, class Tab, int BLOCK, int MIN_BLOCKS>
+int launch_dp(const deb::OdeKernelArgs& a, int sms, cudaStream_t st) {
+    auto kern = deb::dp_ensemble_kernel<Sys, Tab, BLOCK, MIN_BLOCKS>;
+    int per_sm = 0;
+    DEB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, 0));
+    if (per_sm < 1) per_sm = 1;
+    // persistent grid: every resident CTA slot of every SM, but never more threads than trajectories
+    long long blocks = (long long)sms * per_sm;
+    const long long need = (a.n_traj + BLOCK - 1) / BLOCK;
+    if (blocks > need) blocks = need;
+    if (blocks < 1) blocks = 1;
+    kern<<<(unsigned)blocks, BLOCK, 0, st>>>(a);
+    DEB_CUDA(cudaGetLastError());
+    return DEB_OK;
+}
+
+template <class Sys, class Tab>
+int launch_fixed(const deb::OdeKernelArgs& a, int sms, cudaStream_t st) {
+    constexpr int BLOCK = 128;
+    auto kern = deb::fixed_ensemble_kernel<Sys, Tab, BLOCK>;
+    long long blocks = (a.n_traj + BLOCK - 1) / BLOCK;
+    const long long cap = (long long)sms * 16 * 8;  // grid-stride beyond a few waves
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    kern<<<(unsigned)blocks, BLOCK, 0, st>>>(a);
+    DEB_CUDA(cudaGetLastError());
+    return DEB_OK;
+}
+
+template <class Sys>
+ode_launch_fn pick_ode_method(int method) {
+    switch (method) {
+        case DEB_DOPRI5: return launch_dp<Sys, deb::TabDopri5, 128, 4>;
+        case DEB_DOP853: return launch_dp<Sys, deb::TabDop853, 128, 2>;
+        case DEB_EULER: return launch_fixed<Sys, deb::TabEuler>;
+        case DEB_MIDPOINT: return launch_fixed<Sys, deb::TabMidpoint>;
+        case DEB_HEUN: return launch_fixed<Sys, deb::TabHeun>;
+        case DEB_RALSTON: return launch_fixed<Sys, deb::TabRalston>;
+        case DEB_SSP_RK3: return launch_fixed<Sys, deb::TabSspRk3>;
+        case DEB_RK4: return launch_fixed<Sys, deb::TabRk4>;
+        case DEB_THREE_EIGHTHS: return launch_fixed<Sys, deb::TabThreeEighths>;
+    }
+    return nullptr;
+}
+
+ode_launch_fn pick_ode(int system, int method, int* dim, int* np) {
+#define DEB_SYS_CASE(ID, T) case ID: *dim = deb::T::DIM; *np = deb::T::NP; return pick_ode_method<deb::T>(method);
+    switch (system) {
+        DEB_SYS_CASE(DEB_SYS_EXPONENTIAL, SysExponential)
+        DEB_SYS_CASE(DEB_SYS_LINEAR, SysLinear)
+        DEB_SYS_CASE(DEB_SYS_HARMONIC, SysHarmonic)
+        DEB_SYS_CASE(DEB_SYS_LOGISTIC, SysLogistic)
+        DEB_SYS_CASE(DEB_SYS_VAN_DER_POL, SysVanDerPol)
+        DEB_SYS_CASE(DEB_SYS_LORENZ, SysLorenz)
+        DEB_SYS_CASE(DEB_SYS_BRUSSELATOR, SysBrusselator)
+    }
+#undef DEB_SYS_CASE
+    *dim = -1;
+    return nullptr;
+}
+
+typedef int (*sde_launch_fn)(const deb::SdeKernelArgs&, int sms, cudaStream_t);
+template <class Sde, class Tab>
+int launch_sde(const deb::SdeKernelArgs& a, int sms, cudaStream_t st) {
+    constexpr int BLOCK = 256;
+    auto kern = deb::sde_ensemble_kernel<Sde, Tab, BLOCK>;
+    long long blocks = (a.n_traj + BLOCK - 1) / BLOCK;
+    const long long cap = (long long)sms * 8 * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    kern<<<(unsigned)blocks, BLOCK, 0, st>>>(a);
+    DEB_CUDA(cudaGetLastError());
+    return DEB_OK;
+}
+template <class Sde>
+sde_launch_fn pick_sde_method(int method) {
+    switch (method) {
+        case DEB_EULER: return launch_sde<Sde, deb::TabEuler>;
+        case DEB_MIDPOINT: return launch_sde<Sde, deb::TabMidpoint>;
+        case DEB_HEUN: return launch_sde<Sde, deb::TabHeun>;
+        case DEB_RALSTON: return launch_sde<Sde, deb::TabRalston>;
+        case DEB_SSP_RK3: return launch_sde<Sde, deb::TabSspRk3>;
+        case DEB_RK4: return launch_sde<Sde, deb::TabRk4>;
+        case DEB_THREE_EIGHTHS: return launch_sde<Sde, deb::TabThreeEighths>;
+    }
+    return nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------ t_eval plan
+// TEvalSolout::new sorts the points by direction (stable; t_eval.rs:154-171).  The solout call that precedes the
+// loop (solve_ivp.rs:160) consumes every point that is not after t0: the first one is emitted iff it equals t0,
+// the others are skipped forever (t_eval.rs:121-129).  `rows` = the points a trajectory can still emit, in order.
+struct TEvalPlan {
+    std::vector<double> rows;
+    bool emit_t0 = false;
+};
+int plan_t_eval(const double* t_eval, int n_eval, double t0, double tf, TEvalPlan* plan) {
+    plan->rows.clear();
+    plan->emit_t0 = false;
+    if (n_eval <= 0) return DEB_OK;
+    if (!t_eval) return fail(DEB_ERR_BAD_ARG, "n_eval > 0 but t_eval is NULL");
+    std::vector<double> pts(t_eval, t_eval + n_eval);
+    for (double v : pts)
+        if (v != v) return fail(DEB_ERR_BAD_ARG, "t_eval contains NaN");
+    const bool fwd = (tf - t0) > 0.0 || !((tf - t0) < 0.0);
+    if (fwd) std::stable_sort(pts.begin(), pts.end(), [](double a, double b) { return a < b; });
+    else std::stable_sort(pts.begin(), pts.end(), [](double a, double b) { return a > b; });
+    for (int i = 0; i < n_eval; i++) {
+        const double v = pts[i];
+        if (i == 0 && v == t0) { plan->rows.push_back(v); plan->emit_t0 = true; continue; }
+        const bool after = fwd ? (v > t0) : (v < t0);
+        if (after) plan->rows.push_back(v);
+    }
+    return DEB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ staging
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 8); }
+    template <class T> T* as() { return (T*)p; }
+};
+
+struct ResultPtrs {
+    double* y_eval; int* n_emitted; double* t_final; double* y_final; int* status; int* accepted; int* rejected; int* evals;
+};
+
+// Allocates device mirrors for the requested outputs (HOST memspace) or passes device pointers through.
+struct ResultStage {
+    DevBuf y_eval, n_emitted, t_final, y_final, status, accepted, rejected, evals;
+    ResultPtrs dev{};
+    int setup(const deb_result* R, bool host, long long n, int n_eval, int dim) {
+        if (!host) {
+            dev = {R->y_eval, R->n_emitted, R->t_final, R->y_final, R->status, R->accepted, R->rejected, R->evals};
+            return DEB_OK;
+        }
+#define DEB_STAGE(field, T, count)                                         \
+    if (R->field) {                                                        \
+        DEB_CUDA(field.alloc(sizeof(T) * (size_t)(count)));                \
+        dev.field = field.as<T>();                                         \
+    }
+        DEB_STAGE(y_eval, double, (size_t)n * n_eval * dim)
+        DEB_STAGE(n_emitted, int, n)
+        DEB_STAGE(t_final, double, n)
+        DEB_STAGE(y_final, double, (size_t)n * dim)
+        DEB_STAGE(status, int, n)
+        DEB_STAGE(accepted, int, n)
+        DEB_STAGE(rejected, int, n)
+        DEB_STAGE(evals, int, n)
+#undef DEB_STAGE
+        return DEB_OK;
+    }
+    int copy_back(const deb_result* R, long long n, int n_eval, int dim, cudaStream_t st) {
+#define DEB_BACK(field, T, count) \
+    if (R->field) DEB_CUDA(cudaMemcpyAsync(R->field, dev.field, sizeof(T) * (size_t)(count), cudaMemcpyDeviceToHost, st));
+        DEB_BACK(y_eval, double, (size_t)n * n_eval * dim)
+        DEB_BACK(n_emitted, int, n)
+        DEB_BACK(t_final, double, n)
+        DEB_BACK(y_final, double, (size_t)n * dim)
+        DEB_BACK(status, int, n)
+        DEB_BACK(accepted, int, n)
+        DEB_BACK(rejected, int, n)
+        DEB_BACK(evals, int, n)
+#undef DEB_BACK
+        return DEB_OK;
+    }
+};
+
+int check_options(const deb_erk_options& o) {
+    if (o.max_steps < 0) return fail(DEB_ERR_BAD_ARG, "max_steps must be >= 0");
+    return DEB_OK;
+}
+
+void publish_rows(deb_result* R, const TEvalPlan& plan) {
+    R->n_rows = (int32_t)plan.rows.size();
+    if (R->t_rows)
+        for (size_t i = 0; i < plan.rows.size(); i++) R->t_rows[i] = plan.rows[i];
+}
+
+}  // namespace
+
+extern "C" int deb_abi_version(void) { return DEB_ABI_VERSION; }
+extern "C" const char* deb_last_error(void) { return g_err.c_str(); }
+
+extern "C" int deb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+extern "C" void deb_erk_options_default(deb_erk_options* o) {  // erk/mod.rs:135-144
+    if (!o) return;
+    o->rtol = 1.0e-6;
+    o->atol = 1.0e-6;
+    o->rtol_vec = nullptr;
+    o->atol_vec = nullptr;
+    o->h0 = 0.0;
+    o->h_min = 0.0;
+    o->h_max = INFINITY;
+    o->max_steps = 10000;
+    o->safety_factor = 0.9;
+    o->min_scale = 0.2;
+    o->max_scale = 10.0;
+}
+
+extern "C" int deb_solve_ode(const deb_ode_problem* P, deb_result* R) {
+    if (!P || !R) return fail(DEB_ERR_BAD_ARG, "NULL problem/result");
+    if (P->struct_size != sizeof(deb_ode_problem) || R->struct_size != sizeof(deb_result))
+        return fail(DEB_ERR_BAD_ARG, "struct_size mismatch (ABI version skew)");
+    int dim = 0, np = 0;
+    ode_launch_fn launch = pick_ode(P->system, P->method, &dim, &np);
+    if (dim < 0) return fail(DEB_ERR_BAD_ARG, "unknown system id");
+    if (!launch) return fail(DEB_ERR_UNSUPPORTED, "unknown or unsupported method id");
+    if (P->dim != dim || P->n_params != np) return fail(DEB_ERR_BAD_ARG, "dim / n_params do not match the system");
+    if (P->n_traj < 0) return fail(DEB_ERR_BAD_ARG, "n_traj < 0");
+    if (P->n_traj > 0 && (!P->y0 || (np > 0 && !P->params))) return fail(DEB_ERR_BAD_ARG, "NULL y0/params");
+    if (P->n_eval < 0) return fail(DEB_ERR_BAD_ARG, "n_eval < 0");
+    if (int rc = check_options(P->opt)) return rc;
+    TEvalPlan plan;
+    if (int rc = plan_t_eval(P->t_eval, P->n_eval, P->t0, P->tf, &plan)) return rc;
+    publish_rows(R, plan);
+    R->kernel_ms = 0.f;
+    R->total_ms = 0.f;
+    if (P->n_traj == 0) return DEB_OK;  // empty ensemble: nothing to do, and no device needed
+    if (int rc = select_device(P->device)) return rc;
+    DeviceInfo di;
+    if (int rc = device_info(P->device, &di)) return rc;
+    const bool host = (P->memspace == DEB_MEM_HOST);
+    cudaStream_t st = host ? (cudaStream_t)0 : (cudaStream_t)P->stream;
+    const long long n = P->n_traj;
+
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (host)
+        for (auto& e : ev) DEB_CUDA(cudaEventCreate(&e));
+    if (host) DEB_CUDA(cudaEventRecord(ev[0], st));
+
+    deb::OdeKernelArgs a;
+    memset(&a, 0, sizeof a);
+    DevBuf d_y0, d_params;
+    if (host) {
+        DEB_CUDA(d_y0.alloc(sizeof(double) * (size_t)n * dim));
+        DEB_CUDA(cudaMemcpyAsync(d_y0.p, P->y0, sizeof(double) * (size_t)n * dim, cudaMemcpyHostToDevice, st));
+        a.y0 = d_y0.as<double>();
+        if (np > 0) {
+            const size_t cnt = P->params_shared ? (size_t)np : (size_t)n * np;
+            DEB_CUDA(d_params.alloc(sizeof(double) * cnt));
+            DEB_CUDA(cudaMemcpyAsync(d_params.p, P->params, sizeof(double) * cnt, cudaMemcpyHostToDevice, st));
+            a.params = d_params.as<double>();
+        }
+    } else {
+        a.y0 = P->y0;
+        a.params = P->params;
+    }
+    a.params_stride = P->params_shared ? 0 : np;
+    a.n_traj = n;
+    a.t0 = P->t0;
+    a.tf = P->tf;
+    for (int c = 0; c < DEB_MAX_DIM; c++) {
+        a.rtol[c] = (P->opt.rtol_vec && c < dim) ? P->opt.rtol_vec[c] : P->opt.rtol;
+        a.atol[c] = (P->opt.atol_vec && c < dim) ? P->opt.atol_vec[c] : P->opt.atol;
+    }
+    a.h0 = P->opt.h0;
+    a.h_min = P->opt.h_min;
+    a.h_max = P->opt.h_max;
+    a.safety = P->opt.safety_factor;
+    a.min_scale = P->opt.min_scale;
+    a.max_scale = P->opt.max_scale;
+    a.max_steps = (int)std::min<int64_t>(P->opt.max_steps, 0x7fffffff / 16);
+    // small device scratch: [queue counter (8 B)] [rows]
+    const size_t small_bytes = 8 + sizeof(double) * plan.rows.size();
+    void* d_small = nullptr;
+    DEB_CUDA(cudaMallocAsync(&d_small, small_bytes, st));
+    struct SmallFree { void* p; cudaStream_t st; ~SmallFree() { if (p) cudaFreeAsync(p, st); } } small_free{d_small, st};
+    DEB_CUDA(cudaMemsetAsync(small_free.p, 0, 8, st));
+    if (!plan.rows.empty())
+        DEB_CUDA(cudaMemcpyAsync((char*)small_free.p + 8, plan.rows.data(), sizeof(double) * plan.rows.size(), cudaMemcpyHostToDevice, st));
+    a.queue = (unsigned long long*)small_free.p;
+    a.t_rows = (const double*)((char*)small_free.p + 8);
+    a.n_rows = (int)plan.rows.size();
+    a.row_stride = P->n_eval;
+    a.emit_t0 = plan.emit_t0 ? 1 : 0;
+
+    ResultStage rs;
+    if (int rc = rs.setup(R, host, n, P->n_eval, dim)) return rc;
+    a.y_eval = rs.dev.y_eval;
+    a.n_emitted = rs.dev.n_emitted;
+    a.t_final = rs.dev.t_final;
+    a.y_final = rs.dev.y_final;
+    a.status = rs.dev.status;
+    a.accepted = rs.dev.accepted;
+    a.rejected = rs.dev.rejected;
+    a.evals = rs.dev.evals;
+
+    if (host) DEB_CUDA(cudaEventRecord(ev[1], st));
+    if (int rc = launch(a, di.sms, st)) return rc;
+    if (host) {
+        DEB_CUDA(cudaEventRecord(ev[2], st));
+        if (int rc = rs.copy_back(R, n, P->n_eval, dim, st)) return rc;
+        DEB_CUDA(cudaEventRecord(ev[3], st));
+        DEB_CUDA(cudaStreamSynchronize(st));
+        DEB_CUDA(cudaEventElapsedTime(&R->kernel_ms, ev[1], ev[2]));
+        DEB_CUDA(cudaEventElapsedTime(&R->total_ms, ev[0], ev[3]));
+        for (auto& e : ev) cudaEventDestroy(e);
+    }
+    return DEB_OK;
+}
+
+extern "C" int deb_solve_sde(const deb_sde_problem* P, deb_result* R) {
+    if (!P || !R) return fail(DEB_ERR_BAD_ARG, "NULL problem/result");
+    if (P->struct_size != sizeof(deb_sde_problem) || R->struct_size != sizeof(deb_result))
+        return fail(DEB_ERR_BAD_ARG, "struct_size mismatch (ABI version skew)");
+    sde_launch_fn launch = nullptr;
+    int np = 0;
+    if (P->system == DEB_SDE_OU) { launch = pick_sde_method<deb::SdeOU>(P->method); np = deb::SdeOU::NP; }
+    else if (P->system == DEB_SDE_GBM) { launch = pick_sde_method<deb::SdeGBM>(P->method); np = deb::SdeGBM::NP; }
+    else return fail(DEB_ERR_BAD_ARG, "unknown SDE system id");
+    if (!launch) return fail(DEB_ERR_UNSUPPORTED, "SDE ensembles take a fixed-step method id");
+    if (P->dim != 1 || P->n_params != np) return fail(DEB_ERR_BAD_ARG, "dim / n_params do not match the SDE system");
+    if (P->n_traj < 0 || P->n_eval < 0) return fail(DEB_ERR_BAD_ARG, "negative size");
+    if (P->n_traj > 0 && (!P->y0 || !P->params)) return fail(DEB_ERR_BAD_ARG, "NULL y0/params");
+    if (int rc = check_options(P->opt)) return rc;
+    TEvalPlan plan;
+    if (int rc = plan_t_eval(P->t_eval, P->n_eval, P->t0, P->tf, &plan)) return rc;
+    publish_rows(R, plan);
+    R->kernel_ms = 0.f;
+    R->total_ms = 0.f;
+    if (P->n_traj == 0) return DEB_OK;
+    if (int rc = select_device(P->device)) return rc;
+    DeviceInfo di;
+    if (int rc = device_info(P->device, &di)) return rc;
+    const bool host = (P->memspace == DEB_MEM_HOST);
+    cudaStream_t st = host ? (cudaStream_t)0 : (cudaStream_t)P->stream;
+    const long long n = P->n_traj;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (host) {
+        for (auto& e : ev) DEB_CUDA(cudaEventCreate(&e));
+        DEB_CUDA(cudaEventRecord(ev[0], st));
+    }
+    deb::SdeKernelArgs a;
+    memset(&a, 0, sizeof a);
+    DevBuf d_y0, d_params;
+    const size_t y0_cnt = P->y0_shared ? 1 : (size_t)n;
+    const size_t p_cnt = P->params_shared ? (size_t)np : (size_t)n * np;
+    if (host) {
+        DEB_CUDA(d_y0.alloc(sizeof(double) * y0_cnt));
+        DEB_CUDA(cudaMemcpyAsync(d_y0.p, P->y0, sizeof(double) * y0_cnt, cudaMemcpyHostToDevice, st));
+        DEB_CUDA(d_params.alloc(sizeof(double) * p_cnt));
+        DEB_CUDA(cudaMemcpyAsync(d_params.p, P->params, sizeof(double) * p_cnt, cudaMemcpyHostToDevice, st));
+        a.y0 = d_y0.as<double>();
+        a.params = d_params.as<double>();
+    } else {
+        a.y0 = P->y0;
+        a.params = P->params;
+    }
+    a.y0_stride = P->y0_shared ? 0 : 1;
+    a.params_stride = P->params_shared ? 0 : np;
+    a.n_traj = n;
+    a.path_offset = P->path_offset;
+    a.seed = P->seed;
+    a.t0 = P->t0;
+    a.tf = P->tf;
+    a.h0 = P->opt.h0;
+    a.h_min = P->opt.h_min;
+    a.h_max = P->opt.h_max;
+    a.max_steps = (int)std::min<int64_t>(P->opt.max_steps, 0x7fffffff / 16);
+    void* d_rows = nullptr;
+    DEB_CUDA(cudaMallocAsync(&d_rows, 8 + sizeof(double) * plan.rows.size(), st));
+    struct SmallFree { void* p; cudaStream_t st; ~SmallFree() { if (p) cudaFreeAsync(p, st); } } small_free{d_rows, st};
+    if (!plan.rows.empty())
+        DEB_CUDA(cudaMemcpyAsync(d_rows, plan.rows.data(), sizeof(double) * plan.rows.size(), cudaMemcpyHostToDevice, st));
+    a.t_rows = (const double*)d_rows;
+    a.n_rows = (int)plan.rows.size();
+    a.row_stride = P->n_eval;
+    a.emit_t0 = plan.emit_t0 ? 1 : 0;
+    ResultStage rs;
+    if (int rc = rs.setup(R, host, n, P->n_eval, 1)) return rc;
+    a.y_eval = rs.dev.y_eval;
+    a.n_emitted = rs.dev.n_emitted;
+    a.t_final = rs.dev.t_final;
+    a.y_final = rs.dev.y_final;
+    a.status = rs.dev.status;
+    a.accepted = rs.dev.accepted;
+    a.rejected = rs.dev.rejected;
+    a.evals = rs.dev.evals;
+    if (host) DEB_CUDA(cudaEventRecord(ev[1], st));
+    if (int rc = launch(a, di.sms, st)) return rc;
+    if (host) {
+        DEB_CUDA(cudaEventRecord(ev[2], st));
+        if (int rc = rs.copy_back(R, n, P->n_eval, 1, st)) return rc;
+        DEB_CUDA(cudaEventRecord(ev[3], st));
+        DEB_CUDA(cudaStreamSynchronize(st));
+        DEB_CUDA(cudaEventElapsedTime(&R->kernel_ms, ev[1], ev[2]));
+        DEB_CUDA(cudaEventElapsedTime(&R->total_ms, ev[0], ev[3]));
+        for (auto& e : ev) cudaEventDestroy(e);
+    }
+    return DEB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ heat MoL
+namespace {
+
+template <class Tab, int STAGE>
+int heat_launch_stage(const deb::HeatArgs& a, bool pow2, cudaStream_t st) {
+    const long long pairs = (a.n + 1) / 2;
+    const unsigned blocks = (unsigned)((pairs + 255) / 256);
+    if (pow2) deb::heat_stage_kernel<Tab, STAGE, true><<<blocks, 256, 0, st>>>(a);
+    else deb::heat_stage_kernel<Tab, STAGE, false><<<blocks, 256, 0, st>>>(a);
+    DEB_CUDA(cudaGetLastError());
+    return DEB_OK;
+}
+
+// launches stages STAGE..S-1 (each writes ks[STAGE])
+template <class Tab, int STAGE>
+int heat_run_stages(deb::HeatArgs& a, double* const* ks, bool pow2, cudaStream_t st) {
+    if constexpr (STAGE < Tab::S) {
+        a.out_k = ks[STAGE];
+        if (int rc = heat_launch_stage<Tab, STAGE>(a, pow2, st)) return rc;
+        return heat_run_stages<Tab, STAGE + 1>(a, ks, pow2, st);
+    } else {
+        return DEB_OK;
+    }
+}
+
+// solve_ode loop (solve_ivp.rs:139-277) on the host around per-stage kernels; t and h are scalars.
+template <class Tab>
+int heat_solve(const deb_heat_problem* P, double* y_a, double* y_b, double* const* kbuf, double* knew, bool pow2,
+               cudaStream_t st, double* t_out, long long* steps_out, int* status_out, double** y_out) {
+    const double t0 = P->t0, tf = P->tf;
+    const double d = tf - t0;
+    const double dir = (d != d) ? d : copysign(1.0, d);
+    *t_out = t0; *steps_out = 0; *y_out = y_a;
+    if (!(dir == 1.0 || dir == -1.0) || tf == t0) { *status_out = DEB_STATUS_BAD_INPUT; return DEB_OK; }
+    double h = P->h;
+    if (h == 0.0) h = fabs(tf - t0) / 100.0;  // fixed/ordinary.rs:23-28
+    // validate_step_size_parameters (utils.rs:60-157) with h_min = 0, h_max = inf
+    const double sg = (h != h) ? h : copysign(1.0, h);
+    if (sg != dir || fabs(h) > fabs(tf - t0) || h == 0.0) { *status_out = DEB_STATUS_BAD_INPUT; return DEB_OK; }
+    deb::HeatArgs a;
+    memset(&a, 0, sizeof a);
+    a.n = P->n_nodes;
+    a.dx = (P->hi - P->lo) / (double)(P->n_nodes - 1);  // grid.rs:23-36
+    a.inv_dx = 1.0 / a.dx;
+    a.alpha = P->alpha;
+    a.bc_lo_kind = P->bc_lower_kind; a.bc_hi_kind = P->bc_upper_kind;
+    a.bc_lo_val = P->bc_lower_value; a.bc_hi_val = P->bc_upper_value;
+    double* y = y_a;
+    double* y_next = y_b;
+    double* k0 = kbuf[0];
+    double* k0_next = knew;
+    // init: dydt = f(t0, y0)
+    a.y = y; a.h = 0.0; a.out_k = k0;
+    if (int rc = heat_launch_stage<Tab, 0>(a, pow2, st)) return rc;
+    double t = t0;
+    long long steps = 0;
+    int status = DEB_STATUS_COMPLETE;
+    const double eps10 = 2.220446049250313e-16 * 10.0;
+    for (;;) {
+        if ((t + h - tf) * dir > 0.0) {
+            const double h_new = tf - t;
+            if (fabs(h_new) < eps10) break;
+            h = h_new;
+        }
+        if (steps >= P->max_steps) { status = DEB_STATUS_MAX_STEPS; break; }
+        steps += 1;
+        a.y = y; a.h = h;
+        double* ks[8];
+        ks[0] = k0;
+        for (int i = 1; i < Tab::S; i++) ks[i] = kbuf[i];
+        for (int i = 0; i < Tab::S; i++) a.k[i] = ks[i];
+        if (int rc = heat_run_stages<Tab, 1>(a, ks, pow2, st)) return rc;
+        a.out_y = y_next; a.out_k = k0_next;
+        if (int rc = heat_launch_stage<Tab, Tab::S>(a, pow2, st)) return rc;
+        t += h;
+        std::swap(y, y_next);
+        std::swap(k0, k0_next);
+        if (fabs(tf - t) <= eps10) break;
+    }
+    *t_out = t; *steps_out = steps; *status_out = status; *y_out = y;
+    return DEB_OK;
+}
+
+bool is_pow2(double x) {
+    if (!(x > 0.0) || isinf(x)) return false;
+    int e;
+    return frexp(x, &e) == 0.5 && e > -1000 && e < 1000;
+}
+
+}  // namespace
+
+extern "C" int deb_solve_heat_mol(const deb_heat_problem* P) {
+    if (!P) return fail(DEB_ERR_BAD_ARG, "NULL problem");
+    if (P->struct_size != sizeof(deb_heat_problem)) return fail(DEB_ERR_BAD_ARG, "struct_size mismatch (ABI version skew)");
+    if (P->n_nodes < 2) return fail(DEB_ERR_BAD_ARG, "StructuredGrid requires at least two nodes per axis");
+    if (P->lo == P->hi) return fail(DEB_ERR_BAD_ARG, "StructuredGrid endpoints must be distinct");
+    if (!P->u0 || !P->u_final) return fail(DEB_ERR_BAD_ARG, "NULL u0/u_final");
+    if ((P->bc_lower_kind | P->bc_upper_kind) & ~1) return fail(DEB_ERR_BAD_ARG, "boundary kind must be 0 (Dirichlet) or 1 (Neumann)");
+    if (int rc = select_device(P->device)) return rc;
+    const bool host = (P->memspace == DEB_MEM_HOST);
+    cudaStream_t st = host ? (cudaStream_t)0 : (cudaStream_t)P->stream;
+    const size_t bytes = sizeof(double) * (size_t)P->n_nodes;
+    int S = 0;
+    switch (P->method) {
+        case DEB_EULER: S = 1; break;
+        case DEB_MIDPOINT: case DEB_HEUN: case DEB_RALSTON: S = 2; break;
+        case DEB_SSP_RK3: S = 3; break;
+        case DEB_RK4: case DEB_THREE_EIGHTHS: S = 4; break;
+        default: return fail(DEB_ERR_UNSUPPORTED, "method of lines takes a fixed-step method id");
+    }
+    // work buffers: two state buffers (ping-pong), S stage buffers + one for the next k_1
+    DevBuf ya, yb, kk[9];
+    DEB_CUDA(ya.alloc(bytes));
+    DEB_CUDA(yb.alloc(bytes));
+    double* kbuf[8] = {nullptr};
+    for (int i = 0; i < S; i++) { DEB_CUDA(kk[i].alloc(bytes)); kbuf[i] = kk[i].as<double>(); }
+    DEB_CUDA(kk[8].alloc(bytes));
+    DEB_CUDA(cudaMemcpyAsync(ya.p, P->u0, bytes, host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
+    const double dx = (P->hi - P->lo) / (double)(P->n_nodes - 1);
+    const bool pow2 = is_pow2(dx);
+    double t = P->t0;
+    long long steps = 0;
+    int status = 0;
+    double* yout = nullptr;
+    int rc = DEB_OK;
+#define DEB_HEAT_CASE(ID, T) case ID: rc = heat_solve<deb::T>(P, ya.as<double>(), yb.as<double>(), kbuf, kk[8].as<double>(), pow2, st, &t, &steps, &status, &yout); break;
+    switch (P->method) {
+        DEB_HEAT_CASE(DEB_EULER, TabEuler)
+        DEB_HEAT_CASE(DEB_MIDPOINT, TabMidpoint)
+        DEB_HEAT_CASE(DEB_HEUN, TabHeun)
+        DEB_HEAT_CASE(DEB_RALSTON, TabRalston)
+        DEB_HEAT_CASE(DEB_SSP_RK3, TabSspRk3)
+        DEB_HEAT_CASE(DEB_RK4, TabRk4)
+        DEB_HEAT_CASE(DEB_THREE_EIGHTHS, TabThreeEighths)
+    }
+#undef DEB_HEAT_CASE
+    if (rc) return rc;
+    DEB_CUDA(cudaMemcpyAsync(P->u_final, yout, bytes, host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
+    DEB_CUDA(cudaStreamSynchronize(st));  // work buffers are freed on return
+    if (P->t_final) *P->t_final = t;
+    if (P->steps) *P->steps = steps;
+    if (P->status) *P->status = status;
+    return DEB_OK;
+}
+
+extern "C" int deb_heat_rhs(const deb_heat_problem* P, const double* u, double* du) {
+    if (!P || !u || !du) return fail(DEB_ERR_BAD_ARG, "NULL pointer");
+    if (P->struct_size != sizeof(deb_heat_problem)) return fail(DEB_ERR_BAD_ARG, "struct_size mismatch (ABI version skew)");
+    if (P->n_nodes < 2) return fail(DEB_ERR_BAD_ARG, "StructuredGrid requires at least two nodes per axis");
+    if (P->lo == P->hi) return fail(DEB_ERR_BAD_ARG, "StructuredGrid endpoints must be distinct");
+    if ((P->bc_lower_kind | P->bc_upper_kind) & ~1) return fail(DEB_ERR_BAD_ARG, "boundary kind must be 0 (Dirichlet) or 1 (Neumann)");
+    if (int rc = select_device(P->device)) return rc;
+    const bool host = (P->memspace == DEB_MEM_HOST);
+    cudaStream_t st = host ? (cudaStream_t)0 : (cudaStream_t)P->stream;
+    const size_t bytes = sizeof(double) * (size_t)P->n_nodes;
+    DevBuf d_u, d_du;
+    deb::HeatArgs a;
+    memset(&a, 0, sizeof a);
+    a.n = P->n_nodes;
+    a.dx = (P->hi - P->lo) / (double)(P->n_nodes - 1);
+    a.inv_dx = 1.0 / a.dx;
+    a.alpha = P->alpha;
+    a.bc_lo_kind = P->bc_lower_kind; a.bc_hi_kind = P->bc_upper_kind;
+    a.bc_lo_val = P->bc_lower_value; a.bc_hi_val = P->bc_upper_value;
+    if (host) {
+        DEB_CUDA(d_u.alloc(bytes));
+        DEB_CUDA(d_du.alloc(bytes));
+        DEB_CUDA(cudaMemcpyAsync(d_u.p, u, bytes, cudaMemcpyHostToDevice, st));
+        a.y = d_u.as<double>(); a.out_k = d_du.as<double>();
+    } else {
+        a.y = u; a.out_k = du;
+    }
+    const bool pow2 = is_pow2(a.dx);
+    if (int rc = heat_launch_stage<deb::TabEuler, 0>(a, pow2, st)) return rc;
+    if (host) {
+        DEB_CUDA(cudaMemcpyAsync(du, d_du.p, bytes, cudaMemcpyDeviceToHost, st));
+        DEB_CUDA(cudaStreamSynchronize(st));
+    }
+    return DEB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ statistics
+extern "C" int deb_ensemble_stats(const double* y_eval, const int32_t* n_emitted, int64_t n_traj, int32_t n_eval, int32_t dim, double* sums,
+                       int64_t* counts, int32_t device, int32_t memspace, void* stream) {
+    if (!y_eval || !n_emitted || !sums || !counts) return fail(DEB_ERR_BAD_ARG, "NULL pointer");
+    if (n_traj < 0 || n_eval <= 0 || dim <= 0) return fail(DEB_ERR_BAD_ARG, "bad sizes");
+    if (int rc = select_device(device)) return rc;
+    DeviceInfo di;
+    if (int rc = device_info(device, &di)) return rc;
+    const bool host = (memspace == DEB_MEM_HOST);
+    cudaStream_t st = host ? (cudaStream_t)0 : (cudaStream_t)stream;
+    const int ne = n_eval * dim;
+    int n_cta = di.sms * 4;
+    if ((long long)n_cta > n_traj) n_cta = (int)std::max<int64_t>(1, n_traj);
+    DevBuf d_y, d_ne, d_sums, d_counts;
+    const double* dy = y_eval;
+    const int* dn = n_emitted;
+    double* ds = sums;
+    long long* dc = (long long*)counts;
+    if (host) {
+        DEB_CUDA(d_y.alloc(sizeof(double) * (size_t)n_traj * ne));
+        DEB_CUDA(d_ne.alloc(sizeof(int) * (size_t)n_traj));
+        DEB_CUDA(d_sums.alloc(sizeof(double) * 2 * ne));
+        DEB_CUDA(d_counts.alloc(sizeof(long long) * n_eval));
+        DEB_CUDA(cudaMemcpyAsync(d_y.p, y_eval, sizeof(double) * (size_t)n_traj * ne, cudaMemcpyHostToDevice, st));
+        DEB_CUDA(cudaMemcpyAsync(d_ne.p, n_emitted, sizeof(int) * (size_t)n_traj, cudaMemcpyHostToDevice, st));
+        dy = d_y.as<double>(); dn = d_ne.as<int>(); ds = d_sums.as<double>(); dc = d_counts.as<long long>();
+    }
+    void* scratch = nullptr;
+    const size_t pbytes = sizeof(double) * 2 * (size_t)n_cta * ne;
+    const size_t cbytes = sizeof(long long) * (size_t)n_cta * n_eval;
+    DEB_CUDA(cudaMallocAsync(&scratch, pbytes + cbytes, st));
+    struct SmallFree { void* p; cudaStream_t st; ~SmallFree() { if (p) cudaFreeAsync(p, st); } } sf{scratch, st};
+    double* partial = (double*)scratch;
+    long long* pcount = (long long*)((char*)scratch + pbytes);
+    deb::stats_partial_kernel<<<n_cta, 256, 0, st>>>(dy, dn, n_traj, n_eval, dim, partial, pcount);
+    DEB_CUDA(cudaGetLastError());
+    deb::stats_final_kernel<<<(ne + 127) / 128, 128, 0, st>>>(partial, pcount, n_cta, n_eval, dim, ds, dc);
+    DEB_CUDA(cudaGetLastError());
+    if (host) {
+        DEB_CUDA(cudaMemcpyAsync(sums, ds, sizeof(double) * 2 * ne, cudaMemcpyDeviceToHost, st));
+        DEB_CUDA(cudaMemcpyAsync(counts, dc, sizeof(long long) * n_eval, cudaMemcpyDeviceToHost, st));
+        DEB_CUDA(cudaStreamSynchronize(st));
+    }
+    return DEB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ memory helpers
+extern "C" int deb_malloc(int32_t device, size_t bytes, void** ptr) {
+    if (!ptr) return fail(DEB_ERR_BAD_ARG, "NULL ptr");
+    if (int rc = select_device(device)) return rc;
+    DEB_CUDA(cudaMalloc(ptr, bytes ? bytes : 8));
+    return DEB_OK;
+}
+extern "C" int deb_free(int32_t device, void* ptr) {
+    if (int rc = select_device(device)) return rc;
+    DEB_CUDA(cudaFree(ptr));
+    return DEB_OK;
+}
+extern "C" int deb_memcpy_h2d(int32_t device, void* dst, const void* src, size_t bytes) {
+    if (int rc = select_device(device)) return rc;
+    DEB_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    return DEB_OK;
+}
+extern "C" int deb_memcpy_d2h(int32_t device, void* dst, const void* src, size_t bytes) {
+    if (int rc = select_device(device)) return rc;
+    DEB_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return DEB_OK;
+}
+extern "C" int deb_synchronize(int32_t device) {
+    if (int rc = select_device(device)) return rc;
+    DEB_CUDA(cudaDeviceSynchronize());
+    return DEB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ diagnostics
+namespace {
+__global__ void pow_kernel(const double* x, double y, long long n, double* out) {
+    __shared__ double s_powlog[384];
+    __shared__ unsigned long long s_exp[256];
+    deb::load_pow_tables(s_powlog, s_exp);
+    deb_pow_tables tb;
+    tb.powlog = s_powlog;
+    tb.exptab = s_exp;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = deb_pow_pos(x[i], y, tb);
+}
+
+// Register-only stream of independent DP operations: ILP chains per thread, `iters` rounds.
+template <bool FMA>
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* sink, int iters, double m, double c) {
+    double v[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = 1.0 + 1e-3 * (threadIdx.x + i);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (FMA) { v[i] = __fma_rn(v[i], m, c); v[i] = __fma_rn(v[i], m, c); }
+            else { v[i] = __dmul_rn(v[i], m); v[i] = __dadd_rn(v[i], c); }
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += v[i];
+    if (s == 123.456) sink[0] = s;
+}
+}  // namespace
+
+extern "C" int deb_pow_device(const double* x, double y, int64_t n, double* out, int32_t device) {
+    if (!x || !out || n < 0) return fail(DEB_ERR_BAD_ARG, "bad arguments");
+    if (n == 0) return DEB_OK;
+    if (int rc = select_device(device)) return rc;
+    DevBuf dx, dout;
+    DEB_CUDA(dx.alloc(sizeof(double) * (size_t)n));
+    DEB_CUDA(dout.alloc(sizeof(double) * (size_t)n));
+    DEB_CUDA(cudaMemcpy(dx.p, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+    pow_kernel<<<1184, 256>>>(dx.as<double>(), y, n, dout.as<double>());
+    DEB_CUDA(cudaGetLastError());
+    DEB_CUDA(cudaMemcpy(out, dout.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+    return DEB_OK;
+}
+
+extern "C" int deb_fp64_issue_peak(int32_t device, int32_t use_fma, double* dp_inst_per_s, float* ms_out) {
+    if (!dp_inst_per_s) return fail(DEB_ERR_BAD_ARG, "NULL output");
+    if (int rc = select_device(device)) return rc;
+    DeviceInfo di;
+    if (int rc = device_info(device, &di)) return rc;
+    DevBuf sink;
+    DEB_CUDA(sink.alloc(8));
+    const int iters = 20000, blocks = di.sms * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    DEB_CUDA(cudaEventCreate(&e0));
+    DEB_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        DEB_CUDA(cudaEventRecord(e0));
+        if (use_fma) fp64_peak_kernel<true><<<blocks, threads>>>(sink.as<double>(), iters, 0.9999999, 1e-7);
+        else fp64_peak_kernel<false><<<blocks, threads>>>(sink.as<double>(), iters, 0.9999999, 1e-7);
+        DEB_CUDA(cudaEventRecord(e1));
+        DEB_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        DEB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double insts = (double)blocks * threads * (double)iters * 16.0;  // 8 chains x 2 DP instructions per round
+    *dp_inst_per_s = insts / (best * 1e-3);
+    if (ms_out) *ms_out = best;
+    return DEB_OK;
+}
+

@@ -1,0 +1,53 @@
+// ens_stats.cuh -- per-t_eval ensemble sums {sum y, sum y^2} and counts: the only quantity that crosses GPUs
+// (all-reduced by the caller).  HBM-bound single pass over y_eval[n_traj][n_eval][dim]; deterministic
+// (per-CTA partials in a fixed order, then one ordered reduction), so repeated runs give identical bits.
+#pragma once
+#include <stdint.h>
+
+namespace deb {
+
+// Each CTA owns a contiguous slab of trajectories; thread e owns element e = r*dim + c of a trajectory's block
+// (consecutive threads read consecutive doubles).  partial[(cta*ne + e)*2 + {0,1}], pcount[cta*n_eval + r].
+__global__ void __launch_bounds__(256) stats_partial_kernel(const double* __restrict__ y_eval, const int* __restrict__ n_emitted,
+                                                           long long n_traj, int n_eval, int dim, double* partial,
+                                                           long long* pcount) {
+    const int ne = n_eval * dim;
+    const long long per = (n_traj + gridDim.x - 1) / gridDim.x;
+    const long long b = (long long)blockIdx.x * per;
+    const long long e_end = (b + per < n_traj) ? (b + per) : n_traj;
+    for (int e = threadIdx.x; e < ne; e += blockDim.x) {
+        const int r = e / dim;
+        double s = 0.0, s2 = 0.0;
+        long long cnt = 0;
+        for (long long i = b; i < e_end; i++) {
+            if (n_emitted[i] > r) {
+                const double v = y_eval[i * ne + e];
+                s += v;
+                s2 += v * v;
+                cnt += 1;
+            }
+        }
+        partial[((long long)blockIdx.x * ne + e) * 2 + 0] = s;
+        partial[((long long)blockIdx.x * ne + e) * 2 + 1] = s2;
+        if (e % dim == 0) pcount[(long long)blockIdx.x * n_eval + r] = cnt;
+    }
+}
+
+__global__ void stats_final_kernel(const double* partial, const long long* pcount, int n_cta, int n_eval, int dim, double* sums,
+                                   long long* counts) {
+    const int ne = n_eval * dim;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ne) return;
+    double s = 0.0, s2 = 0.0;
+    long long cnt = 0;
+    for (int c = 0; c < n_cta; c++) {
+        s += partial[((long long)c * ne + e) * 2 + 0];
+        s2 += partial[((long long)c * ne + e) * 2 + 1];
+        if (e % dim == 0) cnt += pcount[(long long)c * n_eval + e / dim];
+    }
+    sums[e * 2 + 0] = s;
+    sums[e * 2 + 1] = s2;
+    if (e % dim == 0) counts[e / dim] = cnt;
+}
+
+}  // namespace deb

@@ -1,0 +1,457 @@
+// erk_ensemble.cuh -- persistent ensemble kernels for the explicit Runge-Kutta hot path (sm_100a).
+//
+// One trajectory per thread.  The whole per-trajectory call chain of the reference,
+//     solve_ode loop            /root/reference/src/ode/solve_ivp.rs:139-277
+//     DormandPrince init/step   /root/reference/src/methods/erk/dormandprince/ordinary.rs:16-270
+//     initial step size         /root/reference/src/methods/h_init.rs:45-135
+//     step-size utilities       /root/reference/src/utils.rs:22-157
+//     State algebra             /root/reference/src/traits.rs:316-410
+//     TEvalSolout + dense output  src/solout/t_eval.rs:87-137, dormandprince/ordinary.rs:301-337
+// is fused into one kernel: state, the S stage vectors and the controller live in registers, the tableau is
+// immediates (erk_tableau.cuh), there is no per-step memory traffic.  A warp executes "one step attempt per lane
+// per iteration"; lanes that finished (or failed) are refilled from a global trajectory queue with one
+// warp-aggregated atomicAdd (__ballot_sync + __popc), so warps stay full although adaptive step counts diverge.
+//
+// Arithmetic contract: every + and * below is one separately rounded IEEE f64 operation in the association order
+// of the Rust source (this TU is compiled with -fmad=false; Rust never contracts), sqrt and / are IEEE-exact in
+// CUDA, max/min ignore NaN like f64::max/min, and powf is the bit-exact glibc port of glibc_pow.h.  Terms whose
+// tableau coefficient is zero are skipped (identical for finite stage values; see DESIGN.md for the NaN/-0 note).
+#pragma once
+#include <float.h>
+#include <stdint.h>
+
+#include "../../include/deb_ensemble.h"
+#include "erk_tableau.cuh"
+#include "glibc_pow.h"
+
+namespace deb {
+
+struct OdeKernelArgs {
+    const double* y0;       // [n_traj][DIM]
+    const double* params;   // [n_traj][NP] or [NP]
+    int params_stride;      // NP, or 0 when shared
+    long long n_traj;
+    double t0, tf;
+    double rtol[DEB_MAX_DIM], atol[DEB_MAX_DIM];  // Tolerance indexed per component (tolerance.rs:32-41)
+    double h0, h_min, h_max, safety, min_scale, max_scale;
+    int max_steps;
+    // t_eval: `rows` = the points that can ever be emitted, in integration order (host-filtered, see deb_api.cu)
+    const double* t_rows;   // device [n_rows]
+    int n_rows;
+    int row_stride;         // rows per trajectory in y_eval (= problem n_eval)
+    int emit_t0;            // rows[0] == t0: emitted by the solout call that precedes the loop (solve_ivp.rs:160)
+    double* y_eval;
+    int* n_emitted;
+    double* t_final;
+    double* y_final;
+    int* status;
+    int* accepted;
+    int* rejected;
+    int* evals;
+    unsigned long long* queue;  // next unclaimed trajectory index
+};
+
+__device__ __forceinline__ double d_signum(double x) { return (x != x) ? x : copysign(1.0, x); }  // f64::signum
+
+// utils.rs:22-33
+__device__ __forceinline__ double constrain_step_size(double h, double h_min, double h_max) {
+    const double sign = d_signum(h);
+    if (fabs(h) < h_min) return sign * h_min;
+    if (fabs(h) > h_max) return sign * h_max;
+    return h;
+}
+
+// utils.rs:60-157 -- true when every check passes
+__device__ __forceinline__ bool validate_step_size_parameters(double h0, double h_min, double h_max, double t0, double tf) {
+    if (tf == t0) return false;
+    const double sign = d_signum(tf - t0);
+    if (d_signum(h0) != sign) return false;
+    if (h_min < 0.0) return false;
+    if (h_max < 0.0) return false;
+    if (h_min > h_max) return false;
+    if (fabs(h0) < h_min) return false;
+    if (fabs(h0) > h_max) return false;
+    if (fabs(h0) > fabs(tf - t0)) return false;
+    if (h0 == 0.0) return false;
+    return true;
+}
+
+// InitialStepSize::<Ordinary>::compute, h_init.rs:45-135.  f0 = f(t0,y0) is returned in f0 (2 RHS evaluations).
+template <class Sys>
+__device__ __forceinline__ double initial_step_size(double t0, double tf, const double* y0, const double* p, int order,
+                                                 const double* rtol, const double* atol, double h_min, double h_max,
+                                                 const deb_pow_tables tb) {
+    constexpr int N = Sys::DIM;
+    const double posneg = d_signum(tf - t0);
+    double f0[N], f1[N], sk[N], y1[N];
+    Sys::rhs(t0, y0, f0, p);
+    double dnf = 0.0, dny = 0.0;
+#pragma unroll
+    for (int c = 0; c < N; c++) {
+        sk[c] = atol[c] + rtol[c] * fabs(y0[c]);
+        const double a = f0[c] / sk[c];
+        dnf = dnf + a * a;
+        const double b = y0[c] / sk[c];
+        dny = dny + b * b;
+    }
+    double h;
+    if (dnf <= 1.0e-10 || dny <= 1.0e-10) h = 1.0e-6;
+    else h = sqrt(dny / dnf) * 0.01;
+    h = fmin(h, h_max);
+    h = h * posneg;
+#pragma unroll
+    for (int c = 0; c < N; c++) y1[c] = y0[c] + h * f0[c];
+    Sys::rhs(t0 + h, y1, f1, p);
+    double der2 = 0.0;
+#pragma unroll
+    for (int c = 0; c < N; c++) {
+        const double d = (f1[c] - f0[c]) / sk[c];
+        der2 = der2 + d * d;
+    }
+    der2 = sqrt(der2) / fabs(h);
+    const double der12 = fmax(sqrt(dnf), der2);
+    double h1;
+    if (der12 <= 1.0e-15) h1 = fabs(h) * fmax(1.0e-3, 1.0e-6);  // precedence as written, h_init.rs:116-120
+    else h1 = deb_pow_pos(0.01 / der12, 1.0 / (double)order, tb);
+    const double interval = fabs(tf - t0);
+    h = fmin(fmax(fmin(fmin(fabs(h) * 100.0, h1), h_max), h_min), interval);
+    return h * posneg;
+}
+
+__device__ __forceinline__ void load_pow_tables(double* s_powlog, unsigned long long* s_exp) {
+    for (int i = threadIdx.x; i < 384; i += blockDim.x) s_powlog[i] = deb_c_powlog_tab[i];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_exp[i] = deb_c_exp_tab[i];
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Dormand-Prince family (DOPRI5, DOP853): adaptive step, embedded error norm, I-controller, dense output.
+// ------------------------------------------------------------------------------------------------------------
+template <class Sys, class Tab, int BLOCK, int MIN_BLOCKS>
+__global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const OdeKernelArgs a) {
+    constexpr int N = Sys::DIM, NP = Sys::NP, S = Tab::S, I = Tab::I, O = Tab::O;
+    constexpr unsigned FULL = 0xffffffffu;
+    __shared__ double s_powlog[384];
+    __shared__ unsigned long long s_exp[256];
+    load_pow_tables(s_powlog, s_exp);
+    deb_pow_tables tb;
+    tb.powlog = s_powlog;
+    tb.exptab = s_exp;
+
+    const unsigned lane = threadIdx.x & 31u;
+    const double t0 = a.t0, tf = a.tf;
+    const double dir = d_signum(tf - t0);
+    const double eps10 = DBL_EPSILON * 10.0;
+    const double neg_err_exp = -(1.0 / (double)O);  // -error_exponent, ordinary.rs:152-154
+    const double te_none = (dir > 0.0) ? (1.0 / 0.0) : -(1.0 / 0.0);
+
+    // per-lane trajectory state (registers)
+    bool active = false, exhausted = false;
+    long long traj = 0;
+    double t = 0.0, h = 0.0, h_prev = 0.0, te = te_none;
+    double y[N], k[S][N], p[NP > 0 ? NP : 1];
+    int acc = 0, rej = 0, evals_base = 0, stiff = 0, nonstiff = 0, idx = 0, n_emit = 0;
+    bool rejected_prev = false;
+
+    for (;;) {
+        // ---------------- refill idle lanes from the global queue (one atomic per warp)
+        const unsigned need = __ballot_sync(FULL, !active && !exhausted);
+        if (need) {
+            const int leader = __ffs(need) - 1;
+            unsigned long long base = 0;
+            if ((int)lane == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(need));
+            base = __shfl_sync(FULL, base, leader);
+            if (!active && !exhausted) {
+                traj = (long long)base + __popc(need & ((1u << lane) - 1u));
+                if (traj >= a.n_traj) {
+                    exhausted = true;
+                } else {
+                    // ---- init, dormandprince/ordinary.rs:16-61
+#pragma unroll
+                    for (int c = 0; c < N; c++) y[c] = a.y0[traj * N + c];
+#pragma unroll
+                    for (int q = 0; q < NP; q++) p[q] = a.params[traj * a.params_stride + q];
+                    double h0 = a.h0;
+                    evals_base = 1;
+                    if (h0 == 0.0) {
+                        h0 = initial_step_size<Sys>(t0, tf, y, p, O, a.rtol, a.atol, a.h_min, a.h_max, tb);
+                        evals_base = 3;
+                    }
+                    acc = 0; rej = 0; n_emit = 0; idx = 0;
+                    t = t0;
+                    if (!validate_step_size_parameters(h0, a.h_min, a.h_max, t0, tf)) {
+                        // Err(BadInput): no solution; report (t0, y0)
+                        if (a.status) a.status[traj] = DEB_STATUS_BAD_INPUT;
+                        if (a.t_final) a.t_final[traj] = t0;
+                        if (a.y_final) {
+#pragma unroll
+                            for (int c = 0; c < N; c++) a.y_final[traj * N + c] = y[c];
+                        }
+                        if (a.accepted) a.accepted[traj] = 0;
+                        if (a.rejected) a.rejected[traj] = 0;
+                        if (a.evals) a.evals[traj] = 0;
+                        if (a.n_emitted) a.n_emitted[traj] = 0;
+                    } else {
+                        h = h0;
+                        h_prev = 0.0;
+                        stiff = 0; nonstiff = 0;
+                        rejected_prev = false;
+                        Sys::rhs(t, y, k[0], p);
+                        // solout before the loop (solve_ivp.rs:160): emits rows[0] iff it equals t0
+                        if (a.emit_t0) {
+                            if (a.y_eval) {
+#pragma unroll
+                                for (int c = 0; c < N; c++) a.y_eval[(traj * a.row_stride) * N + c] = y[c];
+                            }
+                            n_emit = 1;
+                            idx = 1;
+                        }
+                        te = (idx < a.n_rows) ? a.t_rows[idx] : te_none;
+                        active = true;
+                    }
+                }
+            }
+        }
+        // leave when every lane has drained the queue and finished its last trajectory
+        if (!__any_sync(FULL, active || !exhausted)) break;
+        if (!active) continue;
+
+        // ---------------- solve_ode loop head, solve_ivp.rs:193-209
+        int fin = -1;  // >= 0: trajectory ends with this status
+        if ((t + h - tf) * dir > 0.0) {
+            const double h_new = tf - t;
+            if (fabs(h_new) < eps10) fin = DEB_STATUS_COMPLETE;
+            else h = h_new;
+        }
+        if (fin < 0) {
+            if (fabs(h) < fabs(h_prev) * 1e-14) fin = DEB_STATUS_STEP_SIZE;   // ordinary.rs:70
+            else if (acc + rej >= a.max_steps) fin = DEB_STATUS_MAX_STEPS;    // ordinary.rs:82 (steps counts rejected attempts too)
+        }
+        if (fin < 0) {
+            const int steps = acc + rej + 1;  // self.steps after the increment
+            // ---- stages, ordinary.rs:95-104
+            double ysti[N];
+#pragma unroll
+            for (int i = 1; i < S; i++) {
+                double ys[N];
+#pragma unroll
+                for (int c = 0; c < N; c++) ys[c] = y[c];
+#pragma unroll
+                for (int j = 0; j < i; j++) {
+                    const double aij = Tab::a(i, j);
+                    if (aij != 0.0) {
+                        const double ah = aij * h;
+#pragma unroll
+                        for (int c = 0; c < N; c++) ys[c] = ys[c] + ah * k[j][c];
+                    }
+                }
+                Sys::rhs(t + Tab::c(i) * h, ys, k[i], p);
+                if (i == S - 1) {
+#pragma unroll
+                    for (int c = 0; c < N; c++) ysti[c] = ys[c];
+                }
+            }
+            // ---- solution and error estimate, ordinary.rs:106-149
+            double yseg[N], ynew[N], es[N];
+#pragma unroll
+            for (int c = 0; c < N; c++) { yseg[c] = 0.0; es[c] = 0.0; }
+#pragma unroll
+            for (int i = 0; i < S; i++) {
+                if (Tab::b(i) != 0.0) {
+#pragma unroll
+                    for (int c = 0; c < N; c++) yseg[c] = __dadd_rn(yseg[c], Tab::b(i) * k[i][c]);
+                }
+                if (Tab::er(i) != 0.0) {
+#pragma unroll
+                    for (int c = 0; c < N; c++) es[c] = __dadd_rn(es[c], Tab::er(i) * k[i][c]);
+                }
+            }
+            const double t_new = t + h;
+            double err = 0.0, err2 = 0.0;
+            double sk[N];
+#pragma unroll
+            for (int c = 0; c < N; c++) {
+                ynew[c] = y[c] + h * yseg[c];
+                sk[c] = a.atol[c] + a.rtol[c] * fmax(fabs(y[c]), fabs(ynew[c]));  // traits.rs:587-595
+                const double e = es[c] / sk[c];
+                err = err + e * e;
+            }
+            if (Tab::HAS_BH) {  // DOP853 second estimator, ordinary.rs:135-143
+                double e2[N];
+#pragma unroll
+                for (int c = 0; c < N; c++) e2[c] = yseg[c];
+#pragma unroll
+                for (int i = 0; i < S; i++) {
+                    if (Tab::bh(i) != 0.0) {
+#pragma unroll
+                        for (int c = 0; c < N; c++) e2[c] = e2[c] + (-Tab::bh(i)) * k[i][c];
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < N; c++) {
+                    const double e = e2[c] / sk[c];
+                    err2 = err2 + e * e;
+                }
+            }
+            double deno = err + 0.01 * err2;
+            if (deno <= 0.0) deno = 1.0;
+            err = fabs(h) * err * sqrt(1.0 / (deno * (double)N));  // ordinary.rs:148
+            // ---- controller, ordinary.rs:151-157
+            double scale = a.safety * deb_pow_pos(err, neg_err_exp, tb);
+            scale = fmin(fmax(scale, a.min_scale), a.max_scale);
+
+            if (err <= 1.0) {
+                // ---- accepted, ordinary.rs:160-254
+                double dydt[N];
+                Sys::rhs(t_new, ynew, dydt, p);
+                if (steps % 100 == 0) {  // stiffness test, ordinary.rs:165-194
+                    double stdnum = 0.0, stden = 0.0;
+#pragma unroll
+                    for (int c = 0; c < N; c++) {
+                        const double d1 = yseg[c] - k[S - 1][c];
+                        stdnum = stdnum + d1 * d1;
+                        const double d2 = dydt[c] - ysti[c];  // (sic) derivative minus stage state, as in the reference
+                        stden = stden + d2 * d2;
+                    }
+                    if (stden > 0.0) {
+                        const double h_lamb = h * sqrt(stdnum / stden);
+                        if (h_lamb > 6.1) {
+                            nonstiff = 0;
+                            stiff += 1;
+                            if (stiff == 15) fin = DEB_STATUS_STIFFNESS;  // Err before any state update
+                        }
+                    } else {
+                        nonstiff += 1;
+                        if (nonstiff == 6) stiff = 0;
+                    }
+                }
+                if (fin < 0) {
+                    // ---- TEvalSolout (t_eval.rs:100-130) with the dense output built only when a point lies in the step
+                    const bool hit = (dir > 0.0) ? (te <= t_new) : (te >= t_new);
+                    if (hit) {
+                        double c1[N], c2[N], c3[N];
+#pragma unroll
+                        for (int c = 0; c < N; c++) {  // ordinary.rs:196-207
+                            c1[c] = ynew[c] - y[c];
+                            c2[c] = __dadd_rn(0.0, h * k[0][c]) - c1[c];
+                            c3[c] = (c1[c] + (-h) * dydt[c]) - c2[c];
+                        }
+                        double ch[(O > 4) ? (O - 4) : 1][N];  // cont[4..O-1]
+                        if (I > S) {
+                            // extra dense stages, ordinary.rs:210-225: k[S] = dydt, stages S+1..I-1
+                            double kx[(I > S) ? (I - S) : 1][N];
+#pragma unroll
+                            for (int c = 0; c < N; c++) kx[0][c] = dydt[c];
+#pragma unroll
+                            for (int i = S + 1; i < I; i++) {
+                                double ys[N];
+#pragma unroll
+                                for (int c = 0; c < N; c++) ys[c] = y[c];
+#pragma unroll
+                                for (int j = 0; j < i; j++) {
+                                    const double aij = Tab::a(i, j);
+                                    if (aij != 0.0) {
+                                        const double ah = aij * h;
+#pragma unroll
+                                        for (int c = 0; c < N; c++) ys[c] = ys[c] + ah * ((j < S) ? k[j][c] : kx[j - S][c]);
+                                    }
+                                }
+                                Sys::rhs(t + Tab::c(i) * h, ys, kx[i - S], p);
+                            }
+#pragma unroll
+                            for (int i = 4; i < O; i++) {  // ordinary.rs:228-234
+#pragma unroll
+                                for (int c = 0; c < N; c++) ch[i - 4][c] = 0.0;
+#pragma unroll
+                                for (int j = 0; j < I; j++) {
+                                    if (Tab::bi(i, j) != 0.0) {
+#pragma unroll
+                                        for (int c = 0; c < N; c++)
+                                            ch[i - 4][c] = __dadd_rn(ch[i - 4][c], Tab::bi(i, j) * ((j < S) ? k[j][c] : kx[j - S][c]));
+                                    }
+                                }
+#pragma unroll
+                                for (int c = 0; c < N; c++) ch[i - 4][c] = ch[i - 4][c] * h;
+                            }
+                        } else {
+                            // DOPRI5: bi rows 4.. are all zero => cont[4] = (+0) * h
+#pragma unroll
+                            for (int i = 4; i < O; i++) {
+#pragma unroll
+                                for (int c = 0; c < N; c++) ch[i - 4][c] = __dmul_rn(0.0, h);
+                            }
+                        }
+                        do {
+                            double row[N];
+                            if (te == t_new) {  // exact hit: the solver state itself (t_eval.rs:113-114)
+#pragma unroll
+                                for (int c = 0; c < N; c++) row[c] = ynew[c];
+                            } else {  // interpolate, ordinary.rs:301-337, factor order as written
+                                const double s = (te - t) / h;
+                                const double s1 = 1.0 - s;
+#pragma unroll
+                                for (int c = 0; c < N; c++) {
+                                    double accp = (O > 4) ? ch[O - 5][c] : c3[c];
+#pragma unroll
+                                    for (int i = O - 2; i >= 1; i--) {
+                                        double factor;
+                                        if (i >= 4) factor = (((O - 1) - i) % 2 == 1) ? s1 : s;
+                                        else factor = (i % 2 == 1) ? s1 : s;
+                                        const double ci = (i >= 4) ? ch[(i >= 4) ? (i - 4) : 0][c] : (i == 3 ? c3[c] : (i == 2 ? c2[c] : c1[c]));
+                                        accp = accp * factor + ci;
+                                    }
+                                    row[c] = y[c] + s * accp;
+                                }
+                            }
+                            if (a.y_eval) {
+                                double* dst = a.y_eval + ((size_t)traj * a.row_stride + n_emit) * N;
+#pragma unroll
+                                for (int c = 0; c < N; c++) dst[c] = row[c];
+                            }
+                            n_emit += 1;
+                            idx += 1;
+                            te = (idx < a.n_rows) ? a.t_rows[idx] : te_none;
+                        } while ((dir > 0.0) ? (te <= t_new) : (te >= t_new));
+                    }
+                    // ---- shift, ordinary.rs:237-254
+                    h_prev = h;
+                    t = t_new;
+#pragma unroll
+                    for (int c = 0; c < N; c++) { y[c] = ynew[c]; k[0][c] = dydt[c]; }
+                    if (rejected_prev) {
+                        rejected_prev = false;
+                        scale = fmin(scale, 1.0);
+                    }
+                    acc += 1;
+                }
+            } else {
+                rejected_prev = true;  // Status::RejectedStep
+                rej += 1;
+            }
+            if (fin < 0) {
+                // ---- step-size update, ordinary.rs:261-267 (filter = identity)
+                h = h * scale;
+                h = constrain_step_size(h, a.h_min, a.h_max);
+                // accepted: end-of-interval test, solve_ivp.rs:263
+                if (!rejected_prev && fabs(tf - t) <= eps10) fin = DEB_STATUS_COMPLETE;
+            }
+        }
+        if (fin >= 0) {
+            // ---------------- trajectory finished: Solution / Error fields
+            if (a.status) a.status[traj] = fin;
+            if (a.t_final) a.t_final[traj] = t;
+            if (a.y_final) {
+#pragma unroll
+                for (int c = 0; c < N; c++) a.y_final[traj * N + c] = y[c];
+            }
+            if (a.accepted) a.accepted[traj] = acc;
+            if (a.rejected) a.rejected[traj] = rej;
+            // Evals.function: 1 (+2 for the automatic h0) + (S-1) per attempt + 1 (+ I-S-1 dense stages) per accepted step
+            if (a.evals) a.evals[traj] = evals_base + (S - 1) * (acc + rej) + acc * (1 + ((I > S) ? (I - S - 1) : 0));
+            if (a.n_emitted) a.n_emitted[traj] = n_emit;
+            active = false;
+        }
+    }
+}
+
+}  // namespace deb

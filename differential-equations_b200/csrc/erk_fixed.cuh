@@ -1,0 +1,146 @@
+// erk_fixed.cuh -- fixed-step explicit Runge-Kutta ensembles (Euler, midpoint, Heun, Ralston, SSP-RK3, RK4, 3/8).
+//
+// Fuses, per trajectory (one per thread, state in registers):
+//     solve_ode loop               /root/reference/src/ode/solve_ivp.rs:139-277
+//     Fixed init/step              /root/reference/src/methods/erk/fixed/ordinary.rs:16-139
+//     cubic-Hermite dense output   /root/reference/src/interpolate.rs:40-60 (via fixed/ordinary.rs:206-216)
+//     TEvalSolout                  /root/reference/src/solout/t_eval.rs:87-137
+// All trajectories of an ensemble share t0, tf and h, so every lane takes the same number of steps: no queue and
+// no divergence; a plain grid-stride loop over trajectories is enough.
+// Note the association of the solution update here is y + sum_i (b_i*h)*k_i (fixed/ordinary.rs:98-102), which is
+// NOT the Dormand-Prince form y + h*(sum_i b_i*k_i).
+#pragma once
+#include "erk_ensemble.cuh"
+
+namespace deb {
+
+template <class Sys, class Tab, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) fixed_ensemble_kernel(const OdeKernelArgs a) {
+    constexpr int N = Sys::DIM, NP = Sys::NP, S = Tab::S;
+    const double t0 = a.t0, tf = a.tf;
+    const double dir = d_signum(tf - t0);
+    const double eps10 = DBL_EPSILON * 10.0;
+    const double te_none = (dir > 0.0) ? (1.0 / 0.0) : -(1.0 / 0.0);
+    const long long stride = (long long)gridDim.x * BLOCK;
+
+    for (long long traj = (long long)blockIdx.x * BLOCK + threadIdx.x; traj < a.n_traj; traj += stride) {
+        double y[N], dydt[N], k[S][N], p[NP > 0 ? NP : 1];
+#pragma unroll
+        for (int c = 0; c < N; c++) y[c] = a.y0[traj * N + c];
+#pragma unroll
+        for (int q = 0; q < NP; q++) p[q] = a.params[traj * a.params_stride + q];
+        int steps = 0, evals = 0, n_emit = 0, idx = 0;
+        int fin = -1;
+        double t = t0;
+        // ---- init, fixed/ordinary.rs:16-56
+        double h = a.h0;
+        if (h == 0.0) h = fabs(tf - t0) / 100.0;
+        if (!validate_step_size_parameters(h, a.h_min, a.h_max, t0, tf)) {
+            fin = DEB_STATUS_BAD_INPUT;
+        } else {
+            Sys::rhs(t, y, dydt, p);
+            evals = 1;
+            if (a.emit_t0) {
+                if (a.y_eval) {
+#pragma unroll
+                    for (int c = 0; c < N; c++) a.y_eval[(traj * a.row_stride) * N + c] = y[c];
+                }
+                n_emit = 1;
+                idx = 1;
+            }
+        }
+        double te = (idx < a.n_rows) ? a.t_rows[idx] : te_none;
+        while (fin < 0) {
+            // ---- loop head, solve_ivp.rs:193-209
+            if ((t + h - tf) * dir > 0.0) {
+                const double h_new = tf - t;
+                if (fabs(h_new) < eps10) { fin = DEB_STATUS_COMPLETE; break; }
+                h = h_new;
+            }
+            // ---- step, fixed/ordinary.rs:58-139
+            if (steps >= a.max_steps) { fin = DEB_STATUS_MAX_STEPS; break; }
+            steps += 1;
+#pragma unroll
+            for (int c = 0; c < N; c++) k[0][c] = dydt[c];
+#pragma unroll
+            for (int i = 1; i < S; i++) {
+                double ys[N];
+#pragma unroll
+                for (int c = 0; c < N; c++) ys[c] = y[c];
+#pragma unroll
+                for (int j = 0; j < i; j++) {
+                    const double aij = Tab::a(i, j);
+                    if (aij != 0.0) {
+                        const double ah = aij * h;
+#pragma unroll
+                        for (int c = 0; c < N; c++) ys[c] = ys[c] + ah * k[j][c];
+                    }
+                }
+                Sys::rhs(t + Tab::c(i) * h, ys, k[i], p);
+            }
+            double ynew[N], dnew[N];
+#pragma unroll
+            for (int c = 0; c < N; c++) ynew[c] = y[c];
+#pragma unroll
+            for (int i = 0; i < S; i++) {
+                if (Tab::b(i) != 0.0) {
+                    const double bh = Tab::b(i) * h;
+#pragma unroll
+                    for (int c = 0; c < N; c++) ynew[c] = ynew[c] + bh * k[i][c];
+                }
+            }
+            const double t_new = t + h;
+            Sys::rhs(t_new, ynew, dnew, p);
+            evals += S;  // S-1 stages + the new derivative (fsal = false)
+            // ---- TEvalSolout with cubic Hermite interpolation
+            while ((dir > 0.0) ? (te <= t_new) : (te >= t_new)) {
+                double row[N];
+                if (te == t_new) {
+#pragma unroll
+                    for (int c = 0; c < N; c++) row[c] = ynew[c];
+                } else {
+                    const double hh = t_new - t;
+                    const double s = (te - t) / hh;
+                    const double s2 = s * s, s3 = s2 * s;
+                    const double h00 = 2.0 * s3 - 3.0 * s2 + 1.0;
+                    const double h10 = s3 - 2.0 * s2 + s;
+                    const double h01 = -2.0 * s3 + 3.0 * s2;
+                    const double h11 = s3 - s2;
+                    const double w10 = h10 * hh, w11 = h11 * hh;
+#pragma unroll
+                    for (int c = 0; c < N; c++) {  // linear_combination: 0, then += term by term (traits.rs:357-370)
+                        double v = __dadd_rn(0.0, h00 * y[c]);
+                        v = v + w10 * dydt[c];
+                        v = v + h01 * ynew[c];
+                        v = v + w11 * dnew[c];
+                        row[c] = v;
+                    }
+                }
+                if (a.y_eval) {
+                    double* dst = a.y_eval + ((size_t)traj * a.row_stride + n_emit) * N;
+#pragma unroll
+                    for (int c = 0; c < N; c++) dst[c] = row[c];
+                }
+                n_emit += 1;
+                idx += 1;
+                te = (idx < a.n_rows) ? a.t_rows[idx] : te_none;
+            }
+            t = t_new;
+#pragma unroll
+            for (int c = 0; c < N; c++) { y[c] = ynew[c]; dydt[c] = dnew[c]; }
+            if (fabs(tf - t) <= eps10) fin = DEB_STATUS_COMPLETE;  // solve_ivp.rs:263
+        }
+        if (a.status) a.status[traj] = fin;
+        if (a.t_final) a.t_final[traj] = t;
+        if (a.y_final) {
+#pragma unroll
+            for (int c = 0; c < N; c++) a.y_final[traj * N + c] = y[c];
+        }
+        if (a.accepted) a.accepted[traj] = steps;
+        if (a.rejected) a.rejected[traj] = 0;
+        if (a.evals) a.evals[traj] = evals;
+        if (a.n_emitted) a.n_emitted[traj] = n_emit;
+    }
+}
+
+}  // namespace deb

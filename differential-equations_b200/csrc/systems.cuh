@@ -1,0 +1,69 @@
+// systems.cuh -- built-in right-hand sides (`ODE::diff`, /root/reference/src/ode/ode.rs:44) as device functors.
+//
+// A Rust closure cannot cross to the device, so the systems of the reference's own tests and benches are compiled
+// in.  Expression order follows /root/reference/tests/ode/systems.rs exactly (this TU is compiled with -fmad=false,
+// so `a*b+c` stays two separately rounded operations like in Rust).
+#pragma once
+
+namespace deb {
+
+struct SysExponential {  // systems.rs:12-16
+    static constexpr int DIM = 1, NP = 1;
+    __device__ __forceinline__ static void rhs(double, const double* y, double* d, const double* p) { d[0] = p[0] * y[0]; }
+};
+struct SysLinear {  // systems.rs:25-29
+    static constexpr int DIM = 1, NP = 2;
+    __device__ __forceinline__ static void rhs(double, const double* y, double* d, const double* p) { d[0] = p[0] + p[1] * y[0]; }
+};
+struct SysHarmonic {  // systems.rs:38-43
+    static constexpr int DIM = 2, NP = 1;
+    __device__ __forceinline__ static void rhs(double, const double* y, double* d, const double* p) {
+        d[0] = y[1];
+        d[1] = -p[0] * y[0];
+    }
+};
+struct SysLogistic {  // systems.rs:55-59
+    static constexpr int DIM = 1, NP = 2;
+    __device__ __forceinline__ static void rhs(double, const double* y, double* d, const double* p) {
+        d[0] = p[0] * y[0] * (1.0 - y[0] / p[1]);
+    }
+};
+struct SysVanDerPol {  // systems.rs:70-78
+    static constexpr int DIM = 2, NP = 1;
+    __device__ __forceinline__ static void rhs(double, const double* y, double* d, const double* p) {
+        const double y1 = y[0], y2 = y[1];
+        d[0] = y2;
+        d[1] = p[0] * (1.0 - y1 * y1) * y2 - y1;
+    }
+};
+struct SysLorenz {  // systems.rs:91-101
+    static constexpr int DIM = 3, NP = 3;
+    __device__ __forceinline__ static void rhs(double, const double* y, double* d, const double* p) {
+        const double x = y[0], yv = y[1], z = y[2];
+        d[0] = p[0] * (yv - x);
+        d[1] = x * (p[1] - z) - yv;
+        d[2] = x * yv - p[2] * z;
+    }
+};
+struct SysBrusselator {  // systems.rs:112-120
+    static constexpr int DIM = 2, NP = 2;
+    __device__ __forceinline__ static void rhs(double, const double* y, double* d, const double* p) {
+        const double y1 = y[0], y2 = y[1];
+        d[0] = p[0] + y1 * y1 * y2 - (p[1] + 1.0) * y1;
+        d[1] = p[1] * y1 - y1 * y1 * y2;
+    }
+};
+
+// Scalar SDEs (`SDE::drift` / `SDE::diffusion`, /root/reference/src/sde/sde.rs:16-52)
+struct SdeOU {  // examples/sde/03_ornstein_uhlenbeck/main.rs:42-49
+    static constexpr int NP = 3;
+    __device__ __forceinline__ static double drift(double, double y, const double* p) { return p[0] * (p[1] - y); }
+    __device__ __forceinline__ static double diffusion(double, double, const double* p) { return p[2]; }
+};
+struct SdeGBM {  // src/sde/solve_ivp.rs doc example: drift mu*y, diffusion sigma*y
+    static constexpr int NP = 2;
+    __device__ __forceinline__ static double drift(double, double y, const double* p) { return p[0] * y; }
+    __device__ __forceinline__ static double diffusion(double, double y, const double* p) { return p[1] * y; }
+};
+
+}  // namespace deb

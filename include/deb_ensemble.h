@@ -1,0 +1,247 @@
+/* deb_ensemble.h -- C ABI of the B200 ensemble integrator (libdeb200.so).
+ *
+ * The reference crate (Ryan-D-Gast/differential-equations, v0.6.1) has no FFI: its operator API is the Rust
+ * trait surface.  This header is the boundary a Rust shim (differential-equations_b200/rust/)
+ * binds with `extern "C"`; each entry point replaces the per-trajectory call chain named beside it for an
+ * ENSEMBLE of independent initial-value problems:
+ *
+ *   deb_solve_ode     <->  IVP::ode(&sys,t0,tf,y0).t_eval(pts).method(ExplicitRungeKutta::<m>()...).solve()
+ *                          src/ivp.rs:279,656,632,781 -> solve_ode src/ode/solve_ivp.rs:116-277
+ *                          -> init/step/interpolate src/methods/erk/dormandprince/ordinary.rs:16,63,301
+ *                             or src/methods/erk/fixed/ordinary.rs:16,58,169
+ *                          -> TEvalSolout::solout src/solout/t_eval.rs:87-137
+ *   deb_solve_sde     <->  IVP::sde(&mut sde,t0,tf,y0).t_eval(pts).method(ExplicitRungeKutta::euler(h)).solve()
+ *                          src/ivp.rs:504,857 -> solve_sde src/sde/solve_ivp.rs:135-287
+ *                          -> src/methods/erk/fixed/stochastic.rs:18,67,177 ; SDE::noise (src/sde/sde.rs:67)
+ *                             is replaced by counter-based Philox4x32-10 Wiener increments (documented below)
+ *   deb_solve_heat_mol <-> IVP::pde(..).space(MethodOfLines::finite_difference(grid).boundary(bc))
+ *                             .method(ExplicitRungeKutta::rk4(h)).solve()
+ *                          src/ivp.rs:419,713 ; RHS = SemiDiscretePde::diff src/pde/semi_discrete.rs:250-287
+ *   deb_ensemble_stats <-> (new) per-t_eval ensemble mean / variance sums, the only quantity that is
+ *                          all-reduced across GPUs.
+ *
+ * Conventions
+ *  - Plain C: pointers + sizes, no C++/torch types.  All structs start with `struct_size` (set it to
+ *    sizeof(the struct)) so fields can be appended compatibly.
+ *  - Every function returns 0 on success, a negative deb_error otherwise; deb_last_error() gives the text.
+ *    Numerical failures of a trajectory are NOT call failures: they are reported per trajectory in
+ *    `status[]` with the same meaning as the reference's `Error` variants (src/error.rs:13-41), and the
+ *    trajectory's (t,y) at failure is returned in t_final/y_final like `Error::MaxSteps{t,y}`.
+ *  - Buffers are caller-owned.  `memspace` says where ALL data pointers of a call live: DEB_MEM_HOST
+ *    (the library stages through pinned memory and copies both ways, synchronous call) or DEB_MEM_DEVICE
+ *    (pointers are device pointers on `device`; the call enqueues on `stream` and returns without
+ *    synchronising).
+ *  - There is NO CPU fallback: without a CUDA device every solve returns DEB_ERR_NO_DEVICE.
+ *  - Layout: trajectory i, component c of y0 / y_final lives at  ptr[i*dim + c]  ("array of states",
+ *    i.e. a Rust Vec<[f64; N]> reinterpreted), y_eval at ptr[(i*n_eval + r)*dim + c] for emitted row r.
+ */
+#ifndef DEB_ENSEMBLE_H
+#define DEB_ENSEMBLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DEB_ABI_VERSION 1
+#define DEB_MAX_DIM 16 /* widest state the register-resident kernels are instantiated for */
+
+typedef enum deb_error {
+    DEB_OK = 0,
+    DEB_ERR_BAD_ARG = -1,    /* malformed problem description (NULL pointer, dim mismatch, ...) */
+    DEB_ERR_NO_DEVICE = -2,  /* no CUDA device / extension not usable: the product path never falls back to a CPU */
+    DEB_ERR_CUDA = -3,       /* CUDA runtime error, text in deb_last_error() */
+    DEB_ERR_UNSUPPORTED = -4 /* valid request that this build has no kernel for (system x method x dim) */
+} deb_error;
+
+/* Explicit Runge-Kutta constructors of the reference that the kernels implement
+ * (src/methods/erk/fixed/mod.rs:41-89, src/methods/erk/dormandprince/mod.rs:45-58). */
+typedef enum deb_method {
+    DEB_EULER = 0,
+    DEB_MIDPOINT = 1,
+    DEB_HEUN = 2,
+    DEB_RALSTON = 3,
+    DEB_SSP_RK3 = 4,
+    DEB_RK4 = 5,
+    DEB_THREE_EIGHTHS = 6,
+    DEB_DOPRI5 = 16,
+    DEB_DOP853 = 17
+} deb_method;
+
+/* Built-in right-hand sides (`ODE::diff`, src/ode/ode.rs:44).  A Rust closure cannot cross to the device,
+ * so the systems of the reference's own tests/benches are compiled in, with the reference's expression
+ * order (tests/ode/systems.rs).  params are per trajectory (or shared, stride 0). */
+typedef enum deb_system {
+    DEB_SYS_EXPONENTIAL = 0, /* dim 1, params {k}:         y' = k*y                  systems.rs:12-16  */
+    DEB_SYS_LINEAR = 1,      /* dim 1, params {a,b}:       y' = a + b*y              systems.rs:25-29  */
+    DEB_SYS_HARMONIC = 2,    /* dim 2, params {k}:         y0' = y1; y1' = -k*y0     systems.rs:38-43  */
+    DEB_SYS_LOGISTIC = 3,    /* dim 1, params {k,m}:       y' = k*y*(1 - y/m)        systems.rs:55-59  */
+    DEB_SYS_VAN_DER_POL = 4, /* dim 2, params {mu}:        systems.rs:70-78                             */
+    DEB_SYS_LORENZ = 5,      /* dim 3, params {sigma,rho,beta}: systems.rs:91-101                       */
+    DEB_SYS_BRUSSELATOR = 6  /* dim 2, params {a,b}:       systems.rs:112-120                           */
+} deb_system;
+
+/* Built-in SDEs (`SDE::drift/diffusion`, src/sde/sde.rs:16-52), scalar state. */
+typedef enum deb_sde_system {
+    DEB_SDE_OU = 0, /* params {theta,mu,sigma}: drift theta*(mu-y), diffusion sigma   examples/sde/03_ornstein_uhlenbeck/main.rs:42-49 */
+    DEB_SDE_GBM = 1 /* params {mu,sigma}:       drift mu*y,         diffusion sigma*y src/sde/solve_ivp.rs doc example               */
+} deb_sde_system;
+
+/* Per-trajectory outcome, mirrors Status/Error of the reference (src/status.rs:26, src/error.rs:13-41). */
+typedef enum deb_status {
+    DEB_STATUS_COMPLETE = 0,
+    DEB_STATUS_MAX_STEPS = 1, /* Error::MaxSteps{t,y}   dormandprince/ordinary.rs:82-91 */
+    DEB_STATUS_STEP_SIZE = 2, /* Error::StepSize{t,y}   dormandprince/ordinary.rs:70-79 */
+    DEB_STATUS_STIFFNESS = 3, /* Error::Stiffness{t,y}  dormandprince/ordinary.rs:165-194 */
+    DEB_STATUS_BAD_INPUT = 4  /* Error::BadInput{..}    utils.rs:60-157, solve_ivp.rs:139-147 */
+} deb_status;
+
+typedef enum deb_memspace { DEB_MEM_HOST = 0, DEB_MEM_DEVICE = 1 } deb_memspace;
+
+/* Options of ExplicitRungeKutta (src/methods/erk/mod.rs:135-144 defaults, :164-228 setters). */
+typedef struct deb_erk_options {
+    double rtol;            /* scalar Tolerance; default 1e-6 */
+    double atol;            /* default 1e-6 */
+    const double* rtol_vec; /* Tolerance::Vector(dim) or NULL -- always HOST memory */
+    const double* atol_vec; /* idem */
+    double h0;              /* 0 = automatic (h_init.rs:45-135 for DP; |tf-t0|/100 for fixed step) */
+    double h_min;           /* default 0 */
+    double h_max;           /* default +inf */
+    int64_t max_steps;      /* default 10000; counts rejected attempts too */
+    double safety_factor;   /* default 0.9 */
+    double min_scale;       /* default 0.2 */
+    double max_scale;       /* default 10 */
+} deb_erk_options;
+
+typedef struct deb_ode_problem {
+    size_t struct_size;
+    int32_t system;       /* deb_system */
+    int32_t method;       /* deb_method */
+    int32_t dim;          /* must equal the system's dimension */
+    int32_t n_params;     /* must equal the system's parameter count */
+    int64_t n_traj;
+    const double* y0;     /* [n_traj][dim] */
+    const double* params; /* [n_traj][n_params], or [n_params] shared by all when params_shared != 0 */
+    int32_t params_shared;
+    int32_t n_eval;       /* number of t_eval points (0 = none) */
+    const double* t_eval; /* HOST memory always.  Sorted like TEvalSolout::new (t_eval.rs:154-165) */
+    double t0, tf;
+    deb_erk_options opt;
+    int32_t device;       /* CUDA ordinal */
+    int32_t memspace;     /* deb_memspace for y0, params and every result pointer */
+    void* stream;         /* cudaStream_t when memspace == DEB_MEM_DEVICE (NULL = default stream) */
+} deb_ode_problem;
+
+typedef struct deb_sde_problem {
+    size_t struct_size;
+    int32_t system;       /* deb_sde_system */
+    int32_t method;       /* fixed-step deb_method; DEB_EULER = Euler-Maruyama */
+    int32_t dim;          /* 1 */
+    int32_t n_params;
+    int64_t n_traj;
+    const double* y0;     /* [n_traj], or one value shared by all when y0_shared != 0 */
+    int32_t y0_shared;
+    int32_t params_shared;
+    const double* params;
+    int32_t n_eval;
+    const double* t_eval; /* HOST */
+    double t0, tf;
+    deb_erk_options opt;  /* h0, h_min, h_max, max_steps are used */
+    /* Wiener increments: dW(path p, step s, component c) = sqrt(h_s) * z, z = Box-Muller normal number
+     * (s*dim + c) of the Philox4x32-10 stream with key (seed lo32, seed hi32) and counter
+     * (pair index lo32, pair index hi32, path lo32, path hi32); see differential-equations_b200/csrc/philox.h. */
+    uint64_t seed;
+    int64_t path_offset;  /* global index of path 0 of this call (for sharding across devices) */
+    int32_t device;
+    int32_t memspace;
+    void* stream;
+} deb_sde_problem;
+
+/* Result buffers; any pointer may be NULL to skip that output. */
+typedef struct deb_result {
+    size_t struct_size;
+    double* y_eval;      /* [n_traj][n_eval][dim]: rows 0..n_emitted[i]-1 are valid */
+    int32_t* n_emitted;  /* [n_traj] number of t_eval rows recorded (Solution.t.len()) */
+    double* t_final;     /* [n_traj] t at completion / at the error */
+    double* y_final;     /* [n_traj][dim] */
+    int32_t* status;     /* [n_traj] deb_status */
+    int32_t* accepted;   /* [n_traj] Steps.accepted  (src/stats.rs:69) */
+    int32_t* rejected;   /* [n_traj] Steps.rejected */
+    int32_t* evals;      /* [n_traj] Evals.function  (src/stats.rs:16) */
+    /* filled by the library (HOST memory, always):
+     * TEvalSolout sorts the points by direction (t_eval.rs:154-171); the solout call before the loop consumes
+     * every point that is not after t0 (a leading point equal to t0 is emitted, the rest are skipped forever,
+     * t_eval.rs:121-129).  t_rows[0..n_rows) are the points that remain emittable, in integration order: row r of
+     * every trajectory is the state at t_rows[r] (Solution.t = t_rows[0..n_emitted[i])). */
+    double* t_rows;        /* [n_eval] caller-provided, may be NULL */
+    int32_t n_rows;
+    float kernel_ms;       /* device time of the integration kernel(s), DEB_MEM_HOST calls only */
+    float total_ms;        /* H2D + kernel + D2H, DEB_MEM_HOST calls only */
+} deb_result;
+
+/* Method-of-lines heat equation u_t = (alpha u_x)_x on a uniform 1-D grid, second-order finite differences,
+ * integrated with a fixed-step ERK method; one large state instead of an ensemble. */
+typedef struct deb_heat_problem {
+    size_t struct_size;
+    int64_t n_nodes;     /* grid nodes, StructuredGrid::uniform (src/pde/grid.rs:23-36): dx = (hi-lo)/(n-1) */
+    double lo, hi;
+    double alpha;        /* flux = alpha * grad u (examples/pde/01_heat_equation/main.rs:18-22) */
+    int32_t bc_lower_kind, bc_upper_kind; /* 0 = Dirichlet(value): node derivative is 0 (semi_discrete.rs:264-267); 1 = Neumann(gradient) */
+    double bc_lower_value, bc_upper_value;
+    int32_t method;      /* fixed-step deb_method (DEB_RK4) */
+    double h;            /* step size (rk4(h)) */
+    double t0, tf;
+    int64_t max_steps;   /* default 10000 */
+    const double* u0;    /* [n_nodes] */
+    double* u_final;     /* [n_nodes] */
+    double* t_final;     /* HOST, 1 value (may be NULL) */
+    int64_t* steps;      /* HOST, 1 value: accepted steps taken (may be NULL) */
+    int32_t* status;     /* HOST, 1 value (may be NULL) */
+    int32_t device;
+    int32_t memspace;
+    void* stream;
+} deb_heat_problem;
+
+int deb_abi_version(void);
+const char* deb_last_error(void);
+int deb_device_count(void);
+
+/* Fill with the reference defaults (erk/mod.rs:135-144). */
+void deb_erk_options_default(deb_erk_options* opt);
+
+int deb_solve_ode(const deb_ode_problem* problem, deb_result* result);
+int deb_solve_sde(const deb_sde_problem* problem, deb_result* result);
+int deb_solve_heat_mol(const deb_heat_problem* problem);
+/* One evaluation of the semi-discrete right-hand side (SemiDiscretePde::diff, src/pde/semi_discrete.rs:250-287)
+ * for the grid / boundary description in `problem` (its u0, u_final, method, h, t0, tf are ignored):
+ * du[i] = f(u)[i].  u/du live in problem->memspace.  Mirrors `system.diff(t, &y, &mut dydt)` of
+ * tests/pde/method_of_lines.rs:73-157. */
+int deb_heat_rhs(const deb_heat_problem* problem, const double* u, double* du);
+
+/* sums[(r*dim + c)*2 + {0,1}] = sum over trajectories with n_emitted > r of {y, y^2} at row r;
+ * counts[r] = number of contributing trajectories.  y_eval/n_emitted in `memspace`; sums/counts likewise. */
+int deb_ensemble_stats(const double* y_eval, const int32_t* n_emitted, int64_t n_traj, int32_t n_eval, int32_t dim,
+                       double* sums, int64_t* counts, int32_t device, int32_t memspace, void* stream);
+
+/* Device-memory helpers so that a caller without the CUDA runtime can keep an ensemble resident. */
+int deb_malloc(int32_t device, size_t bytes, void** ptr);
+int deb_free(int32_t device, void* ptr);
+int deb_memcpy_h2d(int32_t device, void* dst_dev, const void* src_host, size_t bytes);
+int deb_memcpy_d2h(int32_t device, void* dst_host, const void* src_dev, size_t bytes);
+int deb_synchronize(int32_t device);
+
+/* Diagnostics.
+ * deb_pow_device: out[i] = the controller's pow(x[i], y) evaluated on the device (HOST pointers); used to
+ *   prove the device port of glibc pow returns libm's bits.
+ * deb_fp64_issue_peak: runs a register-only stream of independent DADD/DMUL (no FMA fusion, like the
+ *   reference arithmetic) on every SM and reports DP instructions per second -- the roofline denominator
+ *   for the compute-bound ensemble kernels (MEASURED_PEAKS.json has no FP64 entry). */
+int deb_pow_device(const double* x, double y, int64_t n, double* out, int32_t device);
+int deb_fp64_issue_peak(int32_t device, int32_t use_fma, double* dp_inst_per_s, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEB_ENSEMBLE_H */

@@ -1,0 +1,737 @@
+// oracle.cpp -- CPU restatement of the reference's explicit-RK hot path.  TEST INFRASTRUCTURE ONLY.
+//
+// Nothing under differential-equations_b200/ may include, link or call this file.  It exists so that
+// tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs can check and time
+// the CUDA path against the reference's algorithm.
+//
+// PARITY STATUS: "parity unpinned" at the bit level.  The reference is a Rust crate; this image has no
+// Rust toolchain, so the crate itself cannot be run here.  The reference's own tests pin this path only
+// coarsely (tests/ode/accuracy.rs 1e-3..1e3, tests/ode/interpolation.rs 1e-3, tests/ode/from_fn.rs 1e-3,
+// tests/pde/method_of_lines.rs 5e-4 / 1e-12 KATs); tests/test_oracle_golden.py checks this file against
+// every one of those.  Everything beyond that is a line-by-line restatement, with the operation order of
+// the Rust source kept exactly (no FMA contraction: build with -ffp-contract=off; libm pow/sqrt).
+//
+// Each function cites the reference file:line it follows (paths relative to /root/reference/).
+#include <algorithm>
+#include <atomic>
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "../include/deb_ensemble.h"
+#include "erk_tableau_data.h"
+#include "philox_ref.h"
+
+namespace {
+
+// State vector of one trajectory: inline storage like the reference's `[f64; N]` / SVector states (no heap traffic).
+struct Vec {
+    double v[DEB_MAX_DIM];
+    int n = 0;
+    Vec() {}
+    Vec(const Vec& o) : n(o.n) { for (int i = 0; i < n; i++) v[i] = o.v[i]; }
+    Vec& operator=(const Vec& o) { n = o.n; for (int i = 0; i < n; i++) v[i] = o.v[i]; return *this; }
+    Vec(int n_, double fill) : n(n_) { for (int i = 0; i < n; i++) v[i] = fill; }
+    Vec(const double* b, const double* e) : n((int)(e - b)) { for (int i = 0; i < n; i++) v[i] = b[i]; }
+    size_t size() const { return (size_t)n; }
+    double& operator[](size_t i) { return v[i]; }
+    const double& operator[](size_t i) const { return v[i]; }
+    double* data() { return v; }
+    const double* data() const { return v; }
+    double* begin() { return v; }
+    double* end() { return v + n; }
+    void assign(int n_, double fill) { n = n_; for (int i = 0; i < n; i++) v[i] = fill; }
+};
+typedef std::vector<double> BigVec;  // method-of-lines state (2^24 nodes)
+typedef void (*rhs_fn)(double t, const double* y, double* dydt, const double* p);
+
+// ---------------------------------------------------------------- systems (tests/ode/systems.rs)
+void sys_exponential(double, const double* y, double* d, const double* p) { d[0] = p[0] * y[0]; }             // :12-16
+void sys_linear(double, const double* y, double* d, const double* p) { d[0] = p[0] + p[1] * y[0]; }           // :25-29
+void sys_harmonic(double, const double* y, double* d, const double* p) { d[0] = y[1]; d[1] = -p[0] * y[0]; }  // :38-43
+void sys_logistic(double, const double* y, double* d, const double* p) { d[0] = p[0] * y[0] * (1.0 - y[0] / p[1]); }  // :55-59
+void sys_vdp(double, const double* y, double* d, const double* p) {                                            // :70-78
+    double y1 = y[0], y2 = y[1];
+    d[0] = y2;
+    d[1] = p[0] * (1.0 - y1 * y1) * y2 - y1;
+}
+void sys_lorenz(double, const double* y, double* d, const double* p) {  // :91-101
+    double x = y[0], yv = y[1], z = y[2];
+    d[0] = p[0] * (yv - x);
+    d[1] = x * (p[1] - z) - yv;
+    d[2] = x * yv - p[2] * z;
+}
+void sys_brusselator(double, const double* y, double* d, const double* p) {  // :112-120
+    double y1 = y[0], y2 = y[1];
+    d[0] = p[0] + y1 * y1 * y2 - (p[1] + 1.0) * y1;
+    d[1] = p[1] * y1 - y1 * y1 * y2;
+}
+struct SysInfo { rhs_fn f; int dim, np; };
+bool get_system(int id, SysInfo* s) {
+    switch (id) {
+        case DEB_SYS_EXPONENTIAL: *s = {sys_exponential, 1, 1}; return true;
+        case DEB_SYS_LINEAR: *s = {sys_linear, 1, 2}; return true;
+        case DEB_SYS_HARMONIC: *s = {sys_harmonic, 2, 1}; return true;
+        case DEB_SYS_LOGISTIC: *s = {sys_logistic, 1, 2}; return true;
+        case DEB_SYS_VAN_DER_POL: *s = {sys_vdp, 2, 1}; return true;
+        case DEB_SYS_LORENZ: *s = {sys_lorenz, 3, 3}; return true;
+        case DEB_SYS_BRUSSELATOR: *s = {sys_brusselator, 2, 2}; return true;
+    }
+    return false;
+}
+
+// ---------------------------------------------------------------- tableau (src/tableau/mod.rs:39-46)
+struct Tableau {
+    int order, stages, dense;  // O, S, I
+    bool adaptive;
+    const double* c;   // [I]
+    const double* a;   // [I][I]
+    const double* b;   // [S]
+    const double* bh;  // [S] or null
+    const double* er;  // [S] or null
+    const double* bi;  // [I][I] or null
+};
+const double D5_C[7] = DEB_DOPRI5_C;  const double D5_A[7][7] = DEB_DOPRI5_A;  const double D5_B[7] = DEB_DOPRI5_B;
+const double D5_ER[7] = DEB_DOPRI5_ER; const double D5_BI[7][7] = DEB_DOPRI5_BI;
+const double D8_C[16] = DEB_DOP853_C; const double D8_A[16][16] = DEB_DOP853_A; const double D8_B[12] = DEB_DOP853_B;
+const double D8_BH[12] = DEB_DOP853_BH; const double D8_ER[12] = DEB_DOP853_ER; const double D8_BI[16][16] = DEB_DOP853_BI;
+const double RK4_C[4] = DEB_RK4_C; const double RK4_A[4][4] = DEB_RK4_A; const double RK4_B[4] = DEB_RK4_B;
+const double T38_C[4] = DEB_THREE_EIGHTHS_C; const double T38_A[4][4] = DEB_THREE_EIGHTHS_A; const double T38_B[4] = DEB_THREE_EIGHTHS_B;
+const double MID_C[2] = DEB_MIDPOINT_C; const double MID_A[2][2] = DEB_MIDPOINT_A; const double MID_B[2] = DEB_MIDPOINT_B;
+const double HEUN_C[2] = DEB_HEUN_C; const double HEUN_A[2][2] = DEB_HEUN_A; const double HEUN_B[2] = DEB_HEUN_B;
+const double RAL_C[2] = DEB_RALSTON_C; const double RAL_A[2][2] = DEB_RALSTON_A; const double RAL_B[2] = DEB_RALSTON_B;
+const double SSP_C[3] = DEB_SSP_RK3_C; const double SSP_A[3][3] = DEB_SSP_RK3_A; const double SSP_B[3] = DEB_SSP_RK3_B;
+const double EU_C[1] = DEB_EULER_C; const double EU_A[1][1] = DEB_EULER_A; const double EU_B[1] = DEB_EULER_B;
+
+bool get_tableau(int m, Tableau* t) {
+    switch (m) {  // (order, S, I): dormandprince/mod.rs:45-58, fixed/mod.rs:41-89
+        case DEB_DOPRI5: *t = {5, 7, 7, true, D5_C, &D5_A[0][0], D5_B, nullptr, D5_ER, &D5_BI[0][0]}; return true;
+        case DEB_DOP853: *t = {8, 12, 16, true, D8_C, &D8_A[0][0], D8_B, D8_BH, D8_ER, &D8_BI[0][0]}; return true;
+        case DEB_RK4: *t = {4, 4, 4, false, RK4_C, &RK4_A[0][0], RK4_B, nullptr, nullptr, nullptr}; return true;
+        case DEB_THREE_EIGHTHS: *t = {4, 4, 4, false, T38_C, &T38_A[0][0], T38_B, nullptr, nullptr, nullptr}; return true;
+        case DEB_MIDPOINT: *t = {2, 2, 2, false, MID_C, &MID_A[0][0], MID_B, nullptr, nullptr, nullptr}; return true;
+        case DEB_HEUN: *t = {2, 2, 2, false, HEUN_C, &HEUN_A[0][0], HEUN_B, nullptr, nullptr, nullptr}; return true;
+        case DEB_RALSTON: *t = {2, 2, 2, false, RAL_C, &RAL_A[0][0], RAL_B, nullptr, nullptr, nullptr}; return true;
+        case DEB_SSP_RK3: *t = {3, 3, 3, false, SSP_C, &SSP_A[0][0], SSP_B, nullptr, nullptr, nullptr}; return true;
+        case DEB_EULER: *t = {1, 1, 1, false, EU_C, &EU_A[0][0], EU_B, nullptr, nullptr, nullptr}; return true;
+    }
+    return false;
+}
+
+// ---------------------------------------------------------------- State ops (src/traits.rs)
+inline void add_scaled(Vec& s, double alpha, const Vec& o) {  // traits.rs:316-319  *val += alpha * other[i]
+    for (size_t i = 0; i < s.size(); i++) s[i] += alpha * o[i];
+}
+inline Vec plus_scaled(const Vec& s, double alpha, const Vec& o) {  // traits.rs:336-340
+    Vec out = s;
+    add_scaled(out, alpha, o);
+    return out;
+}
+inline Vec minus(const Vec& s, const Vec& o) { return plus_scaled(s, -1.0, o); }  // traits.rs:352-354
+inline void scale_by(Vec& s, double alpha) { for (double& v : s) v *= alpha; }     // traits.rs:323-326
+inline double diff_norm_squared(const Vec& a, const Vec& b) {                      // traits.rs:383-391
+    double sum = 0.0;
+    for (size_t i = 0; i < a.size(); i++) { double d = a[i] - b[i]; sum += d * d; }
+    return sum;
+}
+// Rust f64::max/min ignore a NaN operand; std::fmax/fmin have the same rule.
+inline double rmax(double a, double b) { return std::fmax(a, b); }
+inline double rmin(double a, double b) { return std::fmin(a, b); }
+inline double signum(double x) { return std::isnan(x) ? x : std::copysign(1.0, x); }  // f64::signum
+struct Tol { double s; const double* v; double operator[](size_t i) const { return v ? v[i] : s; } };  // tolerance.rs:32-41
+inline double error_norm(const Vec& y, const Vec& y_new, const Vec& err, const Tol& atol, const Tol& rtol) {  // traits.rs:394-410
+    double sum = 0.0;
+    for (size_t i = 0; i < y.size(); i++) {
+        double sk = atol[i] + rtol[i] * rmax(std::fabs(y[i]), std::fabs(y_new[i]));
+        double e = err[i] / sk;
+        sum += e * e;
+    }
+    return sum;
+}
+
+// ---------------------------------------------------------------- step-size utilities (src/utils.rs)
+inline double constrain_step_size(double h, double h_min, double h_max) {  // utils.rs:22-33
+    double sign = signum(h);
+    if (std::fabs(h) < h_min) return sign * h_min;
+    if (std::fabs(h) > h_max) return sign * h_max;
+    return h;
+}
+inline bool validate_step_size_parameters(double h0, double h_min, double h_max, double t0, double tf) {  // utils.rs:60-157
+    if (tf == t0) return false;
+    double sign = signum(tf - t0);
+    if (signum(h0) != sign) return false;
+    if (h_min < 0.0) return false;
+    if (h_max < 0.0) return false;
+    if (h_min > h_max) return false;
+    if (std::fabs(h0) < h_min) return false;
+    if (std::fabs(h0) > h_max) return false;
+    if (std::fabs(h0) > std::fabs(tf - t0)) return false;
+    if (h0 == 0.0) return false;
+    return true;
+}
+
+struct Problem {
+    rhs_fn f; const double* p; int n;
+    void diff(double t, const Vec& y, Vec& d) const { f(t, y.data(), d.data(), p); }
+};
+
+// InitialStepSize::<Ordinary>::compute, src/methods/h_init.rs:45-135
+double h_init(const Problem& ode, double t0, double tf, const Vec& y0, int order, const Tol& rtol, const Tol& atol,
+              double h_min, double h_max, int* evals) {
+    double posneg = signum(tf - t0);
+    int n = ode.n;
+    Vec f0(n, 0.0), f1(n, 0.0);
+    ode.diff(t0, y0, f0);
+    *evals += 1;
+    double dnf = 0.0, dny = 0.0;
+    Vec sk_vec(n, 0.0);
+    for (int i = 0; i < n; i++) {
+        double sk = atol[i] + rtol[i] * std::fabs(y0[i]);
+        sk_vec[i] = sk;
+        double a = f0[i] / sk; dnf += a * a;   // powi(2)
+        double b = y0[i] / sk; dny += b * b;
+    }
+    double h;
+    if (dnf <= 1.0e-10 || dny <= 1.0e-10) h = 1.0e-6;
+    else h = std::sqrt(dny / dnf) * 0.01;
+    h = rmin(h, h_max);
+    h *= posneg;
+    Vec y1 = plus_scaled(y0, h, f0);
+    ode.diff(t0 + h, y1, f1);
+    *evals += 1;
+    double der2 = 0.0;
+    for (int i = 0; i < n; i++) { double d = (f1[i] - f0[i]) / sk_vec[i]; der2 += d * d; }
+    der2 = std::sqrt(der2) / std::fabs(h);
+    double der12 = rmax(std::sqrt(dnf), der2);
+    double h1;
+    if (der12 <= 1.0e-15) h1 = std::fabs(h) * rmax(1.0e-3, 1.0e-6);  // precedence as written, h_init.rs:116-120
+    else h1 = std::pow(0.01 / der12, 1.0 / (double)order);
+    double interval = std::fabs(tf - t0);
+    h = rmin(rmax(rmin(rmin(std::fabs(h) * 100.0, h1), h_max), h_min), interval);
+    return h * posneg;
+}
+
+enum StepOutcome { STEP_OK = 0, STEP_ERR_MAX_STEPS, STEP_ERR_STEP_SIZE, STEP_ERR_STIFFNESS };
+
+// ExplicitRungeKutta<Ordinary, DormandPrince|Fixed> (src/methods/erk/mod.rs:32-110)
+struct Erk {
+    Tableau tb;
+    Tol rtol, atol;
+    double h0, h_min, h_max, safety, min_scale, max_scale;
+    int64_t max_steps;
+    // state
+    double t = 0, h = 0, t_prev = 0, h_prev = 0;
+    Vec y, dydt, y_prev, dydt_prev;
+    std::vector<Vec> k, cont;
+    int64_t steps = 0;
+    int stiffness_counter = 0, non_stiffness_counter = 0;
+    bool rejected = false;  // Status::RejectedStep
+
+    // ---- Dormand-Prince: init, dormandprince/ordinary.rs:16-61
+    bool dp_init(const Problem& ode, double t0, double tf, const Vec& y0, int* evals) {
+        if (h0 == 0.0) h0 = h_init(ode, t0, tf, y0, tb.order, rtol, atol, h_min, h_max, evals);
+        if (!validate_step_size_parameters(h0, h_min, h_max, t0, tf)) return false;
+        h = h0;
+        stiffness_counter = 0;
+        t = t0; y = y0;
+        int n = ode.n;
+        dydt.assign(n, 0.0); y_prev = y0; dydt_prev.assign(n, 0.0);
+        k.assign(tb.dense, Vec(n, 0.0));
+        cont.assign(tb.order, Vec(n, 0.0));
+        ode.diff(t, y, k[0]);
+        dydt = k[0];
+        *evals += 1;
+        t_prev = t; y_prev = y; dydt_prev = dydt;
+        rejected = false;
+        return true;
+    }
+
+    // ---- Dormand-Prince: step, dormandprince/ordinary.rs:63-270
+    StepOutcome dp_step(const Problem& ode, int* evals_out) {
+        int evals = 0;
+        const int S = tb.stages, I = tb.dense, n = ode.n;
+        if (std::fabs(h) < std::fabs(h_prev) * 1e-14) return STEP_ERR_STEP_SIZE;  // :70
+        if (steps >= max_steps) return STEP_ERR_MAX_STEPS;                        // :82
+        steps += 1;
+        Vec y_stage(n, 0.0);
+        for (int i = 1; i < S; i++) {  // :95-104
+            y_stage = y;
+            for (int j = 0; j < i; j++) add_scaled(y_stage, tb.a[i * I + j] * h, k[j]);
+            ode.diff(t + tb.c[i] * h, y_stage, k[i]);
+        }
+        Vec ysti = y_stage;
+        Vec yseg(n, 0.0);
+        for (int i = 0; i < S; i++) add_scaled(yseg, tb.b[i], k[i]);  // :110-113
+        Vec y_new = plus_scaled(y, h, yseg);                          // :116
+        double t_new = t + h;
+        evals += S - 1;
+        double err2 = 0.0;
+        Vec err_state(n, 0.0);
+        for (int j = 0; j < S; j++) add_scaled(err_state, tb.er[j], k[j]);  // :128-130
+        double err = error_norm(y, y_new, err_state, atol, rtol);
+        if (tb.bh) {  // :135-143
+            Vec err2_state = yseg;
+            for (int j = 0; j < S; j++) add_scaled(err2_state, -tb.bh[j], k[j]);
+            err2 = error_norm(y, y_new, err2_state, atol, rtol);
+        }
+        double deno = err + 0.01 * err2;
+        if (deno <= 0.0) deno = 1.0;
+        err = std::fabs(h) * err * std::sqrt(1.0 / (deno * (double)n));  // :148
+        double order = (double)tb.order;
+        double error_exponent = 1.0 / order;
+        double scale = safety * std::pow(err, -error_exponent);  // :154
+        scale = rmin(rmax(scale, min_scale), max_scale);          // :157
+        if (err <= 1.0) {
+            ode.diff(t_new, y_new, dydt);
+            evals += 1;
+            if (steps % 100 == 0) {  // :165-194
+                double stdnum = diff_norm_squared(yseg, k[S - 1]);
+                double stden = diff_norm_squared(dydt, ysti);
+                if (stden > 0.0) {
+                    double h_lamb = h * std::sqrt(stdnum / stden);
+                    if (h_lamb > 6.1) {
+                        non_stiffness_counter = 0;
+                        stiffness_counter += 1;
+                        if (stiffness_counter == 15) return STEP_ERR_STIFFNESS;
+                    }
+                } else {
+                    non_stiffness_counter += 1;
+                    if (non_stiffness_counter == 6) stiffness_counter = 0;
+                }
+            }
+            cont[0] = y;  // :196-207
+            Vec ydiff = minus(y_new, y);
+            cont[1] = ydiff;
+            Vec bspl(n, 0.0);
+            add_scaled(bspl, h, k[0]);
+            add_scaled(bspl, -1.0, ydiff);
+            cont[2] = bspl;
+            Vec cont3 = ydiff;
+            add_scaled(cont3, -h, dydt);
+            add_scaled(cont3, -1.0, bspl);
+            cont[3] = cont3;
+            if (tb.bi) {  // :210-235
+                if (I > S) {
+                    k[S] = dydt;
+                    for (int i = S + 1; i < I; i++) {
+                        Vec ys = y;
+                        for (int j = 0; j < i; j++) add_scaled(ys, tb.a[i * I + j] * h, k[j]);
+                        ode.diff(t + tb.c[i] * h, ys, k[i]);
+                        evals += 1;
+                    }
+                }
+                for (int i = 4; i < tb.order; i++) {
+                    std::fill(cont[i].begin(), cont[i].end(), 0.0);
+                    for (int j = 0; j < I; j++) add_scaled(cont[i], tb.bi[i * I + j], k[j]);
+                    scale_by(cont[i], h);
+                }
+            }
+            t_prev = t; y_prev = y; dydt_prev = k[0]; h_prev = h;  // :238-241
+            t = t_new; y = y_new; k[0] = dydt;
+            if (rejected) { rejected = false; scale = rmin(scale, 1.0); }  // :249-254
+        } else {
+            rejected = true;
+        }
+        h *= scale;                                   // :261
+        h = constrain_step_size(h, h_min, h_max);     // :264
+        *evals_out += evals;
+        return STEP_OK;
+    }
+
+    // ---- Dormand-Prince dense output, dormandprince/ordinary.rs:301-337 (factor order AS WRITTEN)
+    Vec dp_interpolate(double ti) const {
+        double s = (ti - t_prev) / h_prev;
+        double s1 = 1.0 - s;
+        int ilast = (int)cont.size() - 1;
+        Vec acc = cont[ilast];
+        for (int i = ilast - 1; i >= 1; i--) {
+            double factor;
+            if (i >= 4) factor = ((ilast - i) % 2 == 1) ? s1 : s;
+            else factor = (i % 2 == 1) ? s1 : s;
+            scale_by(acc, factor);
+            add_scaled(acc, 1.0, cont[i]);
+        }
+        return plus_scaled(cont[0], s, acc);
+    }
+
+    // ---- fixed step: init, fixed/ordinary.rs:16-56
+    bool fx_init(const Problem& ode, double t0, double tf, const Vec& y0, int* evals) {
+        if (h0 == 0.0) h0 = std::fabs(tf - t0) / 100.0;
+        if (!validate_step_size_parameters(h0, h_min, h_max, t0, tf)) return false;
+        h = h0;
+        t = t0; y = y0;
+        int n = ode.n;
+        dydt.assign(n, 0.0); y_prev = y0; dydt_prev.assign(n, 0.0);
+        k.assign(tb.dense, Vec(n, 0.0));
+        ode.diff(t, y, dydt);
+        *evals += 1;
+        t_prev = t; y_prev = y; dydt_prev = dydt;
+        return true;
+    }
+    // ---- fixed step: step, fixed/ordinary.rs:58-139 (fsal = false for every constructor, fixed/mod.rs:41-89)
+    StepOutcome fx_step(const Problem& ode, int* evals_out) {
+        const int S = tb.stages, I = tb.dense;
+        if (steps >= max_steps) return STEP_ERR_MAX_STEPS;
+        steps += 1;
+        k[0] = dydt;
+        for (int i = 1; i < S; i++) {
+            Vec ys = y;
+            for (int j = 0; j < i; j++) add_scaled(ys, tb.a[i * I + j] * h, k[j]);
+            ode.diff(t + tb.c[i] * h, ys, k[i]);
+        }
+        *evals_out += S - 1;
+        t_prev = t; y_prev = y; dydt_prev = k[0]; h_prev = h;
+        Vec y_next = y;
+        for (int i = 0; i < S; i++) add_scaled(y_next, tb.b[i] * h, k[i]);  // :98-102  (b_i*h)*k_i
+        t += h;
+        y = y_next;
+        ode.diff(t, y, dydt);
+        *evals_out += 1;
+        return STEP_OK;
+    }
+    // cubic Hermite, src/interpolate.rs:40-60 via fixed/ordinary.rs:206-216
+    Vec fx_interpolate(double ti) const {
+        double hh = t - t_prev;
+        double s = (ti - t_prev) / hh;
+        double s2 = s * s, s3 = s2 * s;
+        double h00 = 2.0 * s3 - 3.0 * s2 + 1.0;
+        double h10 = s3 - 2.0 * s2 + s;
+        double h01 = -2.0 * s3 + 3.0 * s2;
+        double h11 = s3 - s2;
+        Vec out(y.size(), 0.0);  // linear_combination: fill(0) then add_scaled each term, traits.rs:357-370
+        add_scaled(out, h00, y_prev);
+        add_scaled(out, h10 * hh, dydt_prev);
+        add_scaled(out, h01, y);
+        add_scaled(out, h11 * hh, dydt);
+        return out;
+    }
+};
+
+// TEvalSolout, src/solout/t_eval.rs:87-171
+struct TEval {
+    BigVec pts; size_t idx = 0; double dir;
+    TEval(const double* p, int n, double t0, double tf) : pts(p, p + n), dir(signum(tf - t0)) {
+        if (dir > 0.0) std::stable_sort(pts.begin(), pts.end(), [](double a, double b) { return a < b; });
+        else std::stable_sort(pts.begin(), pts.end(), [](double a, double b) { return a > b; });
+    }
+};
+
+struct Out {  // per-trajectory output slots
+    double* y_eval; int32_t* n_emitted; double* t_final; double* y_final;
+    int32_t* status; int32_t* accepted; int32_t* rejected; int32_t* evals;
+};
+
+template <class Interp>
+void solout_teval(TEval& te, double t_curr, double t_prev, const Vec& y_curr, Interp&& interp, double* y_eval, int n, int* n_emit) {
+    size_t idx = te.idx;
+    while (idx < te.pts.size()) {
+        double tv = te.pts[idx];
+        bool in_range = (te.dir > 0.0) ? ((tv == t_prev && idx == 0) || (tv > t_prev && tv <= t_curr))
+                                       : ((tv == t_prev && idx == 0) || (tv < t_prev && tv >= t_curr));
+        if (in_range) {
+            Vec yv = (tv == t_curr) ? y_curr : interp(tv);
+            if (y_eval) std::memcpy(y_eval + (size_t)(*n_emit) * n, yv.data(), sizeof(double) * n);
+            *n_emit += 1;
+            idx += 1;
+        } else {
+            if ((te.dir > 0.0 && tv > t_curr) || (te.dir < 0.0 && tv < t_curr)) break;
+            idx += 1;
+        }
+    }
+    te.idx = idx;
+}
+
+// solve_ode, src/ode/solve_ivp.rs:116-277, for one trajectory
+void solve_one(const deb_ode_problem* P, const SysInfo& si, const Tableau& tb, int64_t i, const Out& o) {
+    const int n = si.dim;
+    Problem ode{si.f, P->params_shared ? P->params : P->params + (size_t)i * si.np, n};
+    Vec y0(P->y0 + (size_t)i * n, P->y0 + (size_t)(i + 1) * n);
+    const double t0 = P->t0, tf = P->tf;
+    Erk m;
+    m.tb = tb;
+    m.rtol = {P->opt.rtol, P->opt.rtol_vec}; m.atol = {P->opt.atol, P->opt.atol_vec};
+    m.h0 = P->opt.h0; m.h_min = P->opt.h_min; m.h_max = P->opt.h_max; m.max_steps = P->opt.max_steps;
+    m.safety = P->opt.safety_factor; m.min_scale = P->opt.min_scale; m.max_scale = P->opt.max_scale;
+    int evals = 0, acc = 0, rej = 0, n_emit = 0;
+    int status = DEB_STATUS_COMPLETE;
+    double* ye = o.y_eval ? o.y_eval + (size_t)i * P->n_eval * n : nullptr;
+    auto finish = [&](int st, double t, const Vec& y) {
+        if (o.status) o.status[i] = st;
+        if (o.t_final) o.t_final[i] = t;
+        if (o.y_final) std::memcpy(o.y_final + (size_t)i * n, y.data(), sizeof(double) * n);
+        if (o.accepted) o.accepted[i] = acc;
+        if (o.rejected) o.rejected[i] = rej;
+        if (o.evals) o.evals[i] = evals;
+        if (o.n_emitted) o.n_emitted[i] = n_emit;
+    };
+    double dir = signum(tf - t0);
+    if (!(dir == 1.0 || dir == -1.0)) { finish(DEB_STATUS_BAD_INPUT, t0, y0); return; }  // :139-147
+    bool ok = tb.adaptive ? m.dp_init(ode, t0, tf, y0, &evals) : m.fx_init(ode, t0, tf, y0, &evals);
+    if (!ok) { evals = 0; finish(DEB_STATUS_BAD_INPUT, t0, y0); return; }
+    TEval te(P->t_eval, P->n_eval, t0, tf);
+    auto interp = [&](double tv) { return tb.adaptive ? m.dp_interpolate(tv) : m.fx_interpolate(tv); };
+    solout_teval(te, m.t, m.t_prev, m.y, interp, ye, n, &n_emit);  // :160
+    const double eps10 = DBL_EPSILON * 10.0;
+    for (;;) {
+        if ((m.t + m.h - tf) * dir > 0.0) {  // :193-209
+            double h_new = tf - m.t;
+            if (std::fabs(h_new) < eps10) { status = DEB_STATUS_COMPLETE; break; }
+            m.h = h_new;
+        }
+        StepOutcome so = tb.adaptive ? m.dp_step(ode, &evals) : m.fx_step(ode, &evals);
+        if (so != STEP_OK) {
+            status = so == STEP_ERR_MAX_STEPS ? DEB_STATUS_MAX_STEPS : so == STEP_ERR_STEP_SIZE ? DEB_STATUS_STEP_SIZE : DEB_STATUS_STIFFNESS;
+            break;
+        }
+        if (m.rejected) { rej += 1; continue; }  // :218-221
+        acc += 1;
+        solout_teval(te, m.t, m.t_prev, m.y, interp, ye, n, &n_emit);
+        if (std::fabs(tf - m.t) <= eps10) break;  // :263
+    }
+    finish(status, m.t, m.y);
+}
+
+// ---------------------------------------------------------------- SDE (fixed step), scalar built-ins
+struct SdeSys { int np; void (*drift)(double, double, double*, const double*); void (*diffusion)(double, double, double*, const double*); };
+void ou_drift(double, double y, double* d, const double* p) { *d = p[0] * (p[1] - y); }   // examples/sde/03_ornstein_uhlenbeck/main.rs:43-45
+void ou_diff(double, double, double* g, const double* p) { *g = p[2]; }                    // :47-49
+void gbm_drift(double, double y, double* d, const double* p) { *d = p[0] * y; }            // src/sde/solve_ivp.rs doc example
+void gbm_diff(double, double y, double* g, const double* p) { *g = p[1] * y; }
+bool get_sde(int id, SdeSys* s) {
+    if (id == DEB_SDE_OU) { *s = {3, ou_drift, ou_diff}; return true; }
+    if (id == DEB_SDE_GBM) { *s = {2, gbm_drift, gbm_diff}; return true; }
+    return false;
+}
+
+// solve_sde (src/sde/solve_ivp.rs:135-287) + ExplicitRungeKutta<Stochastic, Fixed> (fixed/stochastic.rs:18-146), scalar state.
+// SDE::noise is the library's Philox Wiener increment (see philox_ref.h).
+void solve_one_sde(const deb_sde_problem* P, const SdeSys& ss, const Tableau& tb, int64_t i, const Out& o) {
+    const double* p = P->params_shared ? P->params : P->params + (size_t)i * ss.np;
+    double y0 = P->y0_shared ? P->y0[0] : P->y0[i];
+    const double t0 = P->t0, tf = P->tf;
+    int evals = 0, acc = 0, n_emit = 0;
+    double* ye = o.y_eval ? o.y_eval + (size_t)i * P->n_eval : nullptr;
+    auto finish = [&](int st, double t, double y) {
+        if (o.status) o.status[i] = st;
+        if (o.t_final) o.t_final[i] = t;
+        if (o.y_final) o.y_final[i] = y;
+        if (o.accepted) o.accepted[i] = acc;
+        if (o.rejected) o.rejected[i] = 0;
+        if (o.evals) o.evals[i] = evals;
+        if (o.n_emitted) o.n_emitted[i] = n_emit;
+    };
+    double dir = signum(tf - t0);
+    if (!(dir == 1.0 || dir == -1.0)) { finish(DEB_STATUS_BAD_INPUT, t0, y0); return; }
+    // init, stochastic.rs:18-65
+    double h0 = P->opt.h0;
+    if (h0 == 0.0) h0 = std::fabs(tf - t0) / 100.0;
+    if (!validate_step_size_parameters(h0, P->opt.h_min, P->opt.h_max, t0, tf)) { finish(DEB_STATUS_BAD_INPUT, t0, y0); return; }
+    double h = h0, t = t0, y = y0, dydt = 0.0, g = 0.0;
+    int64_t steps = 0;
+    const int S = tb.stages, I = tb.dense;
+    double k[8];
+    ss.drift(t, y, &dydt, p);
+    ss.diffusion(t, y, &g, p);
+    evals += 2;
+    double t_prev = t, y_prev = y;
+    TEval te(P->t_eval, P->n_eval, t0, tf);
+    auto emit = [&](double t_curr, double tp, double y_curr) {
+        Vec yc(1, y_curr);
+        // linear interpolation, src/interpolate.rs:71-74 via stochastic.rs:177-190
+        auto interp = [&](double tv) { double s = (tv - tp) / (t_curr - tp); Vec out(1, 0.0); out[0] += (1.0 - s) * y_prev; out[0] += s * y_curr; return out; };
+        solout_teval(te, t_curr, tp, yc, interp, ye, 1, &n_emit);
+    };
+    emit(t, t_prev, y);
+    const double eps10 = DBL_EPSILON * 10.0;
+    const uint64_t path = (uint64_t)(P->path_offset + i);
+    int status = DEB_STATUS_COMPLETE;
+    for (;;) {
+        if ((t + h - tf) * dir > 0.0) {
+            double h_new = tf - t;
+            if (std::fabs(h_new) < eps10) break;
+            h = h_new;
+        }
+        // step, stochastic.rs:67-146
+        if (steps >= P->opt.max_steps) { status = DEB_STATUS_MAX_STEPS; break; }
+        steps += 1;
+        t_prev = t; y_prev = y;
+        k[0] = dydt;
+        for (int s = 1; s < S; s++) {
+            double ys = y;
+            for (int j = 0; j < s; j++) ys += (tb.a[s * I + j] * h) * k[j];
+            ss.drift(t + tb.c[s] * h, ys, &k[s], p);
+        }
+        evals += S - 1;
+        double drift_inc = 0.0;
+        for (int s = 0; s < S; s++) drift_inc += (tb.b[s] * h) * k[s];
+        ss.diffusion(t, y, &g, p);
+        evals += 1;
+        double dw = deb_ref::wiener_increment(P->seed, path, (uint64_t)(steps - 1), 0, 1, h);
+        double diff_inc = g * dw;  // component_multiply, linalg/util.rs:21
+        double y_next = y;         // plus_linear_combination, traits.rs:343-349
+        y_next += 1.0 * drift_inc;
+        y_next += 1.0 * diff_inc;
+        t += h;
+        y = y_next;
+        ss.drift(t, y, &dydt, p);
+        evals += 1;
+        acc += 1;
+        emit(t, t_prev, y);
+        if (std::fabs(tf - t) <= eps10) break;
+    }
+    finish(status, t, y);
+}
+
+template <class F>
+void parallel_for(int64_t n, int n_threads, F&& body) {
+    if (n_threads <= 1 || n < 2) { for (int64_t i = 0; i < n; i++) body(i); return; }
+    std::atomic<int64_t> next{0};
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(256, n / (n_threads * 8) + 1));
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; t++)
+        th.emplace_back([&] {
+            for (;;) {
+                int64_t b = next.fetch_add(chunk);
+                if (b >= n) break;
+                int64_t e = std::min(n, b + chunk);
+                for (int64_t i = b; i < e; i++) body(i);
+            }
+        });
+    for (auto& t : th) t.join();
+}
+
+}  // namespace
+
+extern "C" {
+
+int orc_hardware_threads(void) { return (int)std::thread::hardware_concurrency(); }
+
+// Same problem/result structs as the product ABI (host pointers only); n_threads <= 0 means all cores.
+int orc_solve_ode(const deb_ode_problem* P, deb_result* R, int n_threads) {
+    SysInfo si; Tableau tb;
+    if (!P || !R || !get_system(P->system, &si) || !get_tableau(P->method, &tb)) return DEB_ERR_BAD_ARG;
+    if (si.dim != P->dim || si.np != P->n_params) return DEB_ERR_BAD_ARG;
+    if (n_threads <= 0) n_threads = orc_hardware_threads();
+    Out o{R->y_eval, R->n_emitted, R->t_final, R->y_final, R->status, R->accepted, R->rejected, R->evals};
+    parallel_for(P->n_traj, n_threads, [&](int64_t i) { solve_one(P, si, tb, i, o); });
+    // sorted t_eval bookkeeping for the caller
+    return DEB_OK;
+}
+
+int orc_solve_sde(const deb_sde_problem* P, deb_result* R, int n_threads) {
+    SdeSys ss; Tableau tb;
+    if (!P || !R || !get_sde(P->system, &ss) || !get_tableau(P->method, &tb) || tb.adaptive) return DEB_ERR_BAD_ARG;
+    if (P->dim != 1 || ss.np != P->n_params) return DEB_ERR_BAD_ARG;
+    if (n_threads <= 0) n_threads = orc_hardware_threads();
+    Out o{R->y_eval, R->n_emitted, R->t_final, R->y_final, R->status, R->accepted, R->rejected, R->evals};
+    parallel_for(P->n_traj, n_threads, [&](int64_t i) { solve_one_sde(P, ss, tb, i, o); });
+    return DEB_OK;
+}
+
+// Wiener increment / normal exposed for the host-side stream regeneration tests.
+double orc_wiener_increment(uint64_t seed, uint64_t path, uint64_t step, int comp, int dim, double h) {
+    return deb_ref::wiener_increment(seed, path, step, comp, dim, h);
+}
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { deb_ref::philox4x32_10(ctr, key, out); }
+
+// libm pow over an array (what Rust's f64::powf calls): the truth the device pow port is compared with.
+void orc_pow_array(const double* x, double y, int64_t n, double* out) { for (int64_t i = 0; i < n; i++) out[i] = std::pow(x[i], y); }
+
+// Method-of-lines heat equation: SemiDiscretePde::diff (src/pde/semi_discrete.rs:250-287) with the FD flux of
+// :181-190 / :150-172 for a scalar field on a 1-D uniform grid, zero source, flux = alpha*grad_u, integrated by
+// the fixed-step ERK loop above (solve_ode + fixed/ordinary.rs).  Plain stencil loop, not the reference's generic
+// per-node machinery; arithmetic per node is the same expression sequence.
+// One evaluation of SemiDiscretePde::diff (semi_discrete.rs:250-287) for the heat problem P on state u.
+int orc_heat_rhs(const deb_heat_problem* P, const double* u, double* du) {
+    if (!P || P->n_nodes < 2) return DEB_ERR_BAD_ARG;
+    const int64_t N = P->n_nodes;
+    const double dx = (P->hi - P->lo) / (double)(N - 1);
+    for (int64_t i = 0; i < N; i++) {
+        bool lower = (i == 0), upper = (i == N - 1);
+        if ((lower && P->bc_lower_kind == 0) || (upper && P->bc_upper_kind == 0)) { du[i] = 0.0; continue; }
+        double gl = !lower ? (u[i] - u[i - 1]) / dx : P->bc_lower_value;
+        double gu = !upper ? (u[i + 1] - u[i]) / dx : P->bc_upper_value;
+        double fl = P->alpha * gl, fu = P->alpha * gu;
+        du[i] = 0.0 + (fu - fl) / dx;
+    }
+    return DEB_OK;
+}
+
+int orc_solve_heat_mol(const deb_heat_problem* P, int n_threads) {
+    Tableau tb;
+    if (!P || !get_tableau(P->method, &tb) || tb.adaptive || P->n_nodes < 2) return DEB_ERR_BAD_ARG;
+    if (n_threads <= 0) n_threads = orc_hardware_threads();
+    const int64_t N = P->n_nodes;
+    const double dx = (P->hi - P->lo) / (double)(N - 1);  // grid.rs:23-36
+    const double alpha = P->alpha;
+    auto rhs = [&](const double* u, double* du) {
+        parallel_for((N + 65535) / 65536, n_threads, [&](int64_t blk) {
+            int64_t b = blk * 65536, e = std::min(N, b + 65536);
+            for (int64_t i = b; i < e; i++) {
+                bool lower = (i == 0), upper = (i == N - 1);
+                if ((lower && P->bc_lower_kind == 0) || (upper && P->bc_upper_kind == 0)) { du[i] = 0.0; continue; }  // :264-267
+                double gl, gu;
+                if (!lower) gl = (u[i] - u[i - 1]) / dx; else gl = P->bc_lower_value;   // :150-172 (Neumann face: prescribed gradient)
+                if (!upper) gu = (u[i + 1] - u[i]) / dx; else gu = P->bc_upper_value;
+                double fl = alpha * gl, fu = alpha * gu;                                  // PDE::flux
+                du[i] = 0.0 + (fu - fl) / dx;                                             // add_scaled_difference :132-139
+            }
+        });
+    };
+    const double t0 = P->t0, tf = P->tf;
+    double dir = signum(tf - t0);
+    auto set = [&](int st, double t, int64_t steps) { if (P->status) *P->status = st; if (P->t_final) *P->t_final = t; if (P->steps) *P->steps = steps; };
+    if (!(dir == 1.0 || dir == -1.0)) { set(DEB_STATUS_BAD_INPUT, t0, 0); return DEB_OK; }
+    double h0 = P->h;
+    if (h0 == 0.0) h0 = std::fabs(tf - t0) / 100.0;
+    if (!validate_step_size_parameters(h0, 0.0, INFINITY, t0, tf)) { set(DEB_STATUS_BAD_INPUT, t0, 0); return DEB_OK; }
+    const int S = tb.stages, I = tb.dense;
+    BigVec y(P->u0, P->u0 + N), dydt(N), ys(N), ynext(N);
+    std::vector<BigVec> k(S, BigVec(N));
+    rhs(y.data(), dydt.data());
+    double t = t0, h = h0;
+    int64_t steps = 0;
+    int status = DEB_STATUS_COMPLETE;
+    const double eps10 = DBL_EPSILON * 10.0;
+    for (;;) {
+        if ((t + h - tf) * dir > 0.0) {
+            double h_new = tf - t;
+            if (std::fabs(h_new) < eps10) break;
+            h = h_new;
+        }
+        if (steps >= P->max_steps) { status = DEB_STATUS_MAX_STEPS; break; }
+        steps += 1;
+        k[0] = dydt;
+        for (int s = 1; s < S; s++) {
+            ys = y;
+            for (int j = 0; j < s; j++) {
+                double ah = tb.a[s * I + j] * h;
+                parallel_for((N + 65535) / 65536, n_threads, [&](int64_t blk) {
+                    int64_t b = blk * 65536, e = std::min(N, b + 65536);
+                    for (int64_t i = b; i < e; i++) ys[i] += ah * k[j][i];
+                });
+            }
+            rhs(ys.data(), k[s].data());
+        }
+        ynext = y;
+        for (int s = 0; s < S; s++) {
+            double bh = tb.b[s] * h;
+            parallel_for((N + 65535) / 65536, n_threads, [&](int64_t blk) {
+                int64_t b = blk * 65536, e = std::min(N, b + 65536);
+                for (int64_t i = b; i < e; i++) ynext[i] += bh * k[s][i];
+            });
+        }
+        t += h;
+        y.swap(ynext);
+        rhs(y.data(), dydt.data());
+        if (std::fabs(tf - t) <= eps10) break;
+    }
+    if (P->u_final) std::memcpy(P->u_final, y.data(), sizeof(double) * N);
+    set(status, t, steps);
+    return DEB_OK;
+}
+
+}  // extern "C"

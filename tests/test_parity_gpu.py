@@ -1,0 +1,350 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical seeded inputs.
+
+Bar (BASELINE.json north_star): adaptive DOPRI5/DOP853 -- per-trajectory final states within 1e-9 relative and
+accepted/rejected counts equal on >= 99.9% of trajectories.  Lorenz on t in [0,100] is chaotic, so that bar is only
+reachable bit-exactly: these tests assert BITWISE equality of every output (states, t_eval rows, counters, status).
+Fixed-step RK4 and SDE paths: 1e-12 relative (asserted bitwise where the arithmetic is IEEE-exact on both sides).
+"""
+import importlib
+
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+
+deb = importlib.import_module("differential-equations_b200")
+E = deb.ExplicitRungeKutta
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+def assert_same_solution(gpu, cpu, exact=True, rtol=0.0):
+    assert np.array_equal(gpu.status, cpu.status), "status differs"
+    assert np.array_equal(gpu.accepted, cpu.accepted), "accepted step counts differ"
+    assert np.array_equal(gpu.rejected, cpu.rejected), "rejected step counts differ"
+    assert np.array_equal(gpu.evals, cpu.evals), "function evaluation counts differ"
+    assert np.array_equal(gpu.n_emitted, cpu.n_emitted), "number of emitted t_eval rows differs"
+    assert np.array_equal(gpu.t_rows, cpu.t_rows)
+    mask = np.arange(gpu.y_eval.shape[1])[None, :] < gpu.n_emitted[:, None]
+    if exact:
+        assert np.array_equal(bits(gpu.t_final), bits(cpu.t_final)), "t_final differs bitwise"
+        assert np.array_equal(bits(gpu.y_final), bits(cpu.y_final)), "y_final differs bitwise"
+        assert np.array_equal(bits(gpu.y_eval)[mask], bits(cpu.y_eval)[mask]), "t_eval rows differ bitwise"
+    else:
+        np.testing.assert_allclose(gpu.t_final, cpu.t_final, rtol=rtol, atol=0)
+        np.testing.assert_allclose(gpu.y_final, cpu.y_final, rtol=rtol, atol=1e-300)
+        np.testing.assert_allclose(gpu.y_eval[mask], cpu.y_eval[mask], rtol=rtol, atol=1e-300)
+
+
+def lorenz():
+    return deb.LorenzSystem(10.0, 28.0, 8.0 / 3.0)
+
+
+# ------------------------------------------------------------------------------------------ the controller's pow
+@pytest.mark.parametrize("y", [-0.2, -0.125, 0.2, 0.125])
+def test_device_pow_is_libm_pow(y):
+    """The device port of glibc pow returns libm's bits (the reference's powf, ordinary.rs:154 / h_init.rs:124)."""
+    lib = deb.load_library()
+    rng = np.random.default_rng(7)
+    n = 1 << 22
+    x = np.concatenate([
+        np.exp(rng.uniform(-27.6, 27.6, n)),                               # [1e-12, 1e12] log-uniform
+        rng.integers(1, 0x7FEFFFFFFFFFFFFF, n, dtype=np.int64).view(np.float64),  # every positive finite exponent
+        1.0 + rng.uniform(-0.5, 0.5, n // 4) * 2.0 ** -rng.integers(0, 60, n // 4),  # near 1
+        rng.integers(1, 1 << 52, 4096, dtype=np.int64).view(np.float64),  # subnormals
+        np.array([0.0, np.inf, np.nan, 1.0, 5e-324, 2.2250738585072014e-308, 1.7976931348623157e308]),
+    ])
+    out = np.empty_like(x)
+    rc = lib.deb_pow_device(x.ctypes.data_as(deb._dp), y, x.size, out.ctypes.data_as(deb._dp), 0)
+    assert rc == 0, lib.deb_last_error()
+    ref = ob.libm_pow(x, y)
+    nan = np.isnan(ref)
+    assert np.array_equal(np.isnan(out), nan)
+    assert np.array_equal(bits(out)[~nan], bits(ref)[~nan]), f"{np.count_nonzero(bits(out)[~nan] != bits(ref)[~nan])} mismatches"
+
+
+# ------------------------------------------------------------------------------------------ config C1
+def test_c1_lorenz_dopri5_1024_bit_exact():
+    """Config C1: Lorenz DOPRI5 rtol=1e-8 (atol default 1e-6), t in [0,100], 1024 perturbed initial conditions, plus
+    the t_eval grid of C2 (100 points, the last equal to tf: exact-hit branch of t_eval.rs:113)."""
+    y0 = ob.lorenz_ensemble_y0(1024)
+    def prob():
+        return deb.EnsembleIVP.ode(lorenz(), 0.0, 100.0, y0).t_eval(np.arange(1.0, 101.0)).method(E.dopri5().rtol(1e-8))
+    gpu, cpu = prob().solve(), ob.oracle_solve(prob())
+    assert_same_solution(gpu, cpu)
+    assert (gpu.status == deb.DEB_STATUS_COMPLETE).sum() > 900
+    # the size-independent book-keeping identity: evals = 3 + 6*attempts + accepted
+    assert np.array_equal(gpu.evals, 3 + 6 * (gpu.accepted + gpu.rejected) + gpu.accepted)
+
+
+def test_lorenz_dopri5_queue_refill_more_trajectories_than_threads():
+    """More trajectories than resident threads with short, very unequal lifetimes: exercises the warp-aggregated
+    work-queue refill; results must not depend on which lane ran a trajectory."""
+    n = 200_000
+    y0 = ob.lorenz_ensemble_y0(n, seed=99)
+    tf = 0.6
+    def prob(sub=slice(None)):
+        return deb.EnsembleIVP.ode(lorenz(), 0.0, tf, y0[sub]).t_eval([0.1, 0.3, 0.6]).method(E.dopri5().rtol(1e-8))
+    gpu = prob().solve()
+    sub = slice(0, n, 37)
+    cpu = ob.oracle_solve(prob(sub))
+    for name in ("status", "accepted", "rejected", "evals", "n_emitted"):
+        assert np.array_equal(getattr(gpu, name)[sub], getattr(cpu, name)), name
+    assert np.array_equal(bits(gpu.y_final[sub]), bits(cpu.y_final))
+    assert np.array_equal(bits(gpu.y_eval[sub]), bits(cpu.y_eval))
+    assert (gpu.status == 0).all()
+
+
+def test_dopri5_all_builtin_systems_bit_exact():
+    rng = np.random.default_rng(3)
+    cases = [
+        (deb.ExponentialGrowth(1.0), 0.0, 10.0, 1.0 + rng.uniform(-0.1, 0.1, (64, 1))),
+        (deb.LinearEquation(1.0, 1.0), 0.0, 10.0, 1.0 + rng.uniform(-0.1, 0.1, (64, 1))),
+        (deb.HarmonicOscillator(1.0), 0.0, 10.0, np.array([1.0, 0.0]) + rng.uniform(-0.1, 0.1, (64, 2))),
+        (deb.LogisticEquation(1.0, 10.0), 0.0, 10.0, 0.1 + rng.uniform(0, 0.1, (64, 1))),
+        (deb.VanDerPolOscillator(rng.uniform(0.1, 5.0, 64)), 0.0, 10.0, np.tile([2.0, 0.0], (64, 1))),
+        (deb.BrusselatorSystem(1.0, 3.0), 0.0, 10.0, np.array([1.5, 3.0]) + rng.uniform(-0.1, 0.1, (64, 2))),
+    ]
+    for sysm, t0, tf, y0 in cases:
+        for m in (E.dopri5, E.dop853):
+            def prob():
+                return deb.EnsembleIVP.ode(sysm, t0, tf, y0).t_eval(np.linspace(t0, tf, 23)).method(m().rtol(1e-7).atol(1e-9))
+            assert_same_solution(prob().solve(), ob.oracle_solve(prob()))
+
+
+# ------------------------------------------------------------------------------------------ config C3 (reduced)
+def test_c3_van_der_pol_dop853_sweep_bit_exact():
+    """Config C3 at oracle-sized N: mu sweep in [0.1, 50], DOP853 rtol=atol=1e-8, y0=(2,0), t in [0,100]."""
+    n = 1536
+    mu = 0.1 + 49.9 * np.arange(n) / (n - 1)
+    y0 = np.tile([2.0, 0.0], (n, 1))
+    def prob():
+        return (deb.EnsembleIVP.ode(deb.VanDerPolOscillator(mu), 0.0, 100.0, y0).t_eval(np.arange(5.0, 101.0, 5.0))
+                .method(E.dop853().rtol(1e-8).atol(1e-8)))
+    gpu, cpu = prob().solve(), ob.oracle_solve(prob())
+    assert_same_solution(gpu, cpu)
+    assert (gpu.status == 0).all()
+    # evals = 3 + 11*attempts + 4*accepted for DOP853 (dense stages counted on every accepted step)
+    assert np.array_equal(gpu.evals, 3 + 11 * (gpu.accepted + gpu.rejected) + 4 * gpu.accepted)
+
+
+# ------------------------------------------------------------------------------------------ errors / edge cases
+def test_error_statuses_match_reference_semantics():
+    y0 = ob.lorenz_ensemble_y0(64)
+    # MaxSteps: atol=1e-8 needs > 10000 attempts
+    def p1():
+        return deb.EnsembleIVP.ode(lorenz(), 0.0, 100.0, y0).method(E.dopri5().rtol(1e-8).atol(1e-8))
+    g, c = p1().solve(), ob.oracle_solve(p1())
+    assert_same_solution(g, c)
+    assert (g.status == deb.DEB_STATUS_MAX_STEPS).any()
+    with pytest.raises(deb.MaxSteps):
+        g[int(np.argmax(g.status == deb.DEB_STATUS_MAX_STEPS))]
+    # BadInput: tf == t0 (tests/ode/errors.rs:87) and h0 larger than the interval (errors.rs:110)
+    def p2():
+        return deb.EnsembleIVP.ode(lorenz(), 1.0, 1.0, y0).method(E.dopri5())
+    g, c = p2().solve(), ob.oracle_solve(p2())
+    assert_same_solution(g, c)
+    assert (g.status == deb.DEB_STATUS_BAD_INPUT).all()
+    def p3():
+        return deb.EnsembleIVP.ode(lorenz(), 0.0, 1.0, y0).method(E.dopri5().h0(2.0))
+    g, c = p3().solve(), ob.oracle_solve(p3())
+    assert_same_solution(g, c)
+    assert (g.status == deb.DEB_STATUS_BAD_INPUT).all()
+    with pytest.raises(deb.BadInput):
+        g[0]
+    # StepSize: a blow-up (y' = y^2-like growth through the logistic equation with negative capacity)
+    def p4():
+        return deb.EnsembleIVP.ode(deb.LogisticEquation(1.0, -1.0), 0.0, 10.0, np.full((8, 1), 1.0)).method(E.dopri5())
+    g, c = p4().solve(), ob.oracle_solve(p4())
+    assert_same_solution(g, c)
+    assert set(g.status.tolist()) <= {deb.DEB_STATUS_STEP_SIZE, deb.DEB_STATUS_MAX_STEPS}
+
+
+def test_t_eval_ordering_filtering_and_backward_integration():
+    y0 = np.array([1.0, 0.0]) + np.linspace(0, 0.1, 32)[:, None]
+    pts = [3.0, 0.0, 11.0, -1.0, 0.5, 10.0, 0.5, 7.25]  # unsorted, duplicates, outside the interval, t0 and tf themselves
+    for m in (E.dopri5, E.dop853, lambda: E.rk4(0.01)):
+        def fwd():
+            return deb.EnsembleIVP.ode(deb.HarmonicOscillator(1.0), 0.0, 10.0, y0).t_eval(pts).method(m())
+        g, c = fwd().solve(), ob.oracle_solve(fwd())
+        assert_same_solution(g, c)
+        assert g.t_rows.tolist() == [0.5, 0.5, 3.0, 7.25, 10.0, 11.0]  # -1 and 0.0 (not first) are consumed at t0
+        def bwd():
+            return deb.EnsembleIVP.ode(deb.HarmonicOscillator(1.0), 10.0, 0.0, y0).t_eval(pts).method(m())
+        if m in (E.dopri5, E.dop853):  # (backward integration with a fixed step needs a negative h: below)
+            g, c = bwd().solve(), ob.oracle_solve(bwd())
+            assert_same_solution(g, c)
+            assert g.t_rows.tolist() == [7.25, 3.0, 0.5, 0.5, 0.0, -1.0]
+    def bwd_rk4():
+        return deb.EnsembleIVP.ode(deb.HarmonicOscillator(1.0), 10.0, 0.0, y0).t_eval(pts).method(E.rk4(-0.01))
+    assert_same_solution(bwd_rk4().solve(), ob.oracle_solve(bwd_rk4()))
+    # first point equal to t0 is emitted by the solout call before the loop
+    def t0_first():
+        return deb.EnsembleIVP.ode(deb.HarmonicOscillator(1.0), 0.0, 2.0, y0).t_eval([0.0, 1.0, 2.0]).method(E.dopri5())
+    g, c = t0_first().solve(), ob.oracle_solve(t0_first())
+    assert_same_solution(g, c)
+    assert np.array_equal(g.y_eval[:, 0, :], y0) and (g.n_emitted >= 2).all()
+
+
+def test_vector_tolerances_and_options_cross_the_abi():
+    y0 = ob.lorenz_ensemble_y0(64, seed=5)
+    def prob():
+        m = (E.dopri5().rtol([1e-7, 1e-8, 1e-6]).atol([1e-9, 1e-6, 1e-7]).h_max(0.05).h_min(1e-9).safety_factor(0.8)
+             .min_scale(0.3).max_scale(5.0).max_steps(5000).h0(1e-3))
+        return deb.EnsembleIVP.ode(lorenz(), 0.0, 20.0, y0).t_eval(np.linspace(0.5, 20, 40)).method(m)
+    assert_same_solution(prob().solve(), ob.oracle_solve(prob()))
+
+
+# ------------------------------------------------------------------------------------------ fixed step
+@pytest.mark.parametrize("ctor", ["euler", "midpoint", "heun", "ralston", "ssp_rk3", "rk4", "three_eighths"])
+def test_fixed_step_methods_bit_exact(ctor):
+    """Fixed-step ERK (bar: 1e-12; asserted bitwise -- both sides execute the same IEEE operations)."""
+    y0 = ob.lorenz_ensemble_y0(300, seed=11)
+    def prob():
+        return (deb.EnsembleIVP.ode(lorenz(), 0.0, 2.0, y0).t_eval([0.0, 0.333, 1.0, 1.5, 2.0])
+                .method(getattr(E, ctor)(1e-3)))
+    g, c = prob().solve(), ob.oracle_solve(prob())
+    assert_same_solution(g, c)
+    # t accumulates h (fixed/ordinary.rs:123): 2000 steps, or 2001 with a last sliver step, the same for all lanes
+    assert (g.status == 0).all() and g.accepted[0] in (2000, 2001) and (g.accepted == g.accepted[0]).all()
+
+
+def test_fixed_step_default_h_and_max_steps():
+    y0 = np.full((16, 1), 1.0)
+    def p1():  # h0 == 0 -> |tf-t0|/100 (fixed/ordinary.rs:23-28)
+        return deb.EnsembleIVP.ode(deb.ExponentialGrowth(1.0), 0.0, 1.0, y0).method(E.rk4(0.0))
+    g, c = p1().solve(), ob.oracle_solve(p1())
+    assert_same_solution(g, c)
+    assert (g.accepted == 100).all()
+    def p2():  # 20001 steps needed, default max_steps 10000 -> MaxSteps
+        return deb.EnsembleIVP.ode(deb.ExponentialGrowth(1.0), 0.0, 1.0, y0).method(E.euler(5e-5))
+    g, c = p2().solve(), ob.oracle_solve(p2())
+    assert_same_solution(g, c)
+    assert (g.status == deb.DEB_STATUS_MAX_STEPS).all() and (g.accepted == 10000).all()
+
+
+def test_reference_from_fn_euler_kat():
+    """tests/ode/from_fn.rs:4-18: Euler h=0.1 on y'=y over [0,1] gives 2.5937 +- 1e-3."""
+    s = deb.EnsembleIVP.ode(deb.ExponentialGrowth(1.0), 0.0, 1.0, [[1.0]]).method(E.euler(0.1)).solve()[0]
+    assert abs(s.y_final[0] - 2.5937) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------ SDE (config C4, reduced)
+@pytest.mark.parametrize("which", ["ou", "gbm"])
+def test_c4_euler_maruyama_matches_host_regenerated_philox(which):
+    n = 4096
+    if which == "ou":   # theta=0.5, mu=1.0, sigma=0.3, y0=5, t in [0,10], euler(0.01): 1001 steps
+        sysm, t0, tf, h, y0 = deb.OrnsteinUhlenbeck(0.5, 1.0, 0.3), 0.0, 10.0, 0.01, 5.0
+        nsteps = 1001
+    else:               # mu=0.1, sigma=0.2, y0=100, t in [0,1], euler(1e-3): 1000 steps
+        sysm, t0, tf, h, y0 = deb.GeometricBrownianMotion(0.1, 0.2), 0.0, 1.0, 1e-3, 100.0
+        nsteps = 1000
+    def prob():
+        return (deb.EnsembleIVP.sde(sysm, t0, tf, np.full(n, y0), seed=2026, path_offset=123456789)
+                .t_eval([tf / 3, tf / 2, tf]).method(E.euler(h)))
+    g, c = prob().solve(), ob.oracle_solve(prob())
+    assert_same_solution(g, c, exact=False, rtol=1e-12)
+    assert (g.accepted == nsteps).all() and (g.status == 0).all()
+    # paths differ from each other (the noise is per path) and have the right spread
+    assert np.unique(g.y_final).size == n
+
+
+def test_sde_rk4_drift_stages():
+    """examples/sde/03_ornstein_uhlenbeck/main.rs:66 drives the SDE with rk4(dt): RK drift stages + EM diffusion."""
+    n = 512
+    def prob():
+        return (deb.EnsembleIVP.sde(deb.OrnsteinUhlenbeck(0.5, 1.0, 0.3), 0.0, 10.0, np.full(n, 5.0), seed=42)
+                .t_eval([2.0, 5.0, 8.0]).method(E.rk4(0.01)))
+    assert_same_solution(prob().solve(), ob.oracle_solve(prob()), exact=False, rtol=1e-12)
+
+
+# ------------------------------------------------------------------------------------------ heat (config C5, reduced)
+@pytest.mark.parametrize("n,lo,hi", [(4097, 0.0, 4096.0), (4096, 0.0, 1.0), (41, 0.0, 1.0), (2, 0.0, 1.0), (65537, 0.0, 65536.0)])
+@pytest.mark.parametrize("bc", ["dirichlet", "neumann", "mixed"])
+def test_c5_heat_method_of_lines_rk4(n, lo, hi, bc):
+    """dx = 1 (power of two: multiplication path) and dx = 1/4095, 1/40 (IEEE division path); odd and even N."""
+    x = np.linspace(lo, hi, n)
+    u0 = np.sin(np.pi * (x - lo) / (hi - lo)) + 0.25 * np.cos(3 * np.pi * (x - lo) / (hi - lo))
+    dx = (hi - lo) / (n - 1)
+    alpha = 0.1
+    h = 0.2 * dx * dx / alpha
+    bcl, bcu = {"dirichlet": (("dirichlet", 0.0), ("dirichlet", 0.0)), "neumann": (("neumann", 0.3), ("neumann", -0.2)),
+                "mixed": (("dirichlet", 0.0), ("neumann", 0.1))}[bc]
+    for meth in (E.rk4(h), E.three_eighths(h), E.euler(h / 4)):
+        tf = 37.5 * h
+        g = deb.solve_heat_mol(u0, lo, hi, alpha, meth, 0.0, tf, bcl, bcu)
+        c = ob.oracle_heat(u0, lo, hi, alpha, meth, 0.0, tf, bcl, bcu)
+        assert g.status == c.status == "Complete" and g.steps == c.steps and g.t == c.t
+        assert np.array_equal(bits(g.u), bits(c.u)), f"max diff {np.abs(g.u - c.u).max()}"
+
+
+def test_heat_rhs_reference_kats():
+    """tests/pde/method_of_lines.rs:73-91 (Dirichlet rows exactly 0) and :143-157 (Neumann KAT)."""
+    du = deb.heat_rhs([2.0, 1.0, 0.0, -0.5, -1.0], 0.0, 1.0, 1.0, ("dirichlet", 2.0), ("dirichlet", -1.0))
+    assert du[0] == 0.0 and du[-1] == 0.0
+    du = deb.heat_rhs([0.0, 1.0, 0.0, -1.0, 0.0], 0.0, 1.0, 1.0)
+    assert du[0] == 0.0 and du[4] == 0.0 and abs(du[2]) < 1e-12
+    dx = 0.25
+    du = deb.heat_rhs([1.0, 2.0, 2.0, 2.0, 2.0], 0.0, 1.0, 1.0, ("neumann", 0.0), ("neumann", 0.0))
+    assert abs(du[0] - (1.0 / dx) / dx) < 1e-12
+    rng = np.random.default_rng(0)
+    for n in (2, 3, 64, 65, 1000, 4099):
+        u = rng.normal(size=n)
+        for bcl, bcu in ((("dirichlet", 0.0), ("neumann", 0.5)), (("neumann", -1.0), ("dirichlet", 0.0))):
+            assert np.array_equal(bits(deb.heat_rhs(u, -1.0, 2.0, 0.7, bcl, bcu)), bits(ob.oracle_heat_rhs(u, -1.0, 2.0, 0.7, bcl, bcu)))
+
+
+def test_heat_matches_analytic_mode():
+    """tests/pde/method_of_lines.rs:37-70: N=41, alpha=0.1, rk4(1e-4), t=0.02, tolerance 5e-4 against the analytic mode."""
+    x = np.linspace(0.0, 1.0, 41)
+    g = deb.solve_heat_mol(np.sin(np.pi * x), 0.0, 1.0, 0.1, E.rk4(1.0e-4), 0.0, 0.02)
+    expected = np.exp(-0.1 * np.pi ** 2 * 0.02) * np.sin(np.pi * x)
+    assert np.abs(g.u - expected).max() < 5.0e-4
+
+
+# ------------------------------------------------------------------------------------------ ensemble statistics
+def test_ensemble_stats_match_numpy():
+    import ctypes as C
+    lib = deb.load_library()
+    y0 = ob.lorenz_ensemble_y0(5000, seed=1)
+    g = deb.EnsembleIVP.ode(lorenz(), 0.0, 5.0, y0).t_eval(np.linspace(0.5, 5.0, 10)).method(E.dopri5().rtol(1e-8).max_steps(300)).solve()
+    assert (g.status != 0).any() and (g.status == 0).any()  # some trajectories stop early: ragged n_emitted
+    sums = np.zeros((10, 3, 2))
+    counts = np.zeros(10, np.int64)
+    rc = lib.deb_ensemble_stats(g.y_eval.ctypes.data, g.n_emitted.ctypes.data, 5000, 10, 3, sums.ctypes.data, counts.ctypes.data, 0,
+                                deb.DEB_MEM_HOST, None)
+    assert rc == 0, lib.deb_last_error()
+    mask = np.arange(10)[None, :] < g.n_emitted[:, None]
+    assert np.array_equal(counts, mask.sum(0))
+    ye = np.where(mask[:, :, None], g.y_eval, 0.0)
+    np.testing.assert_allclose(sums[:, :, 0], ye.sum(0), rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(sums[:, :, 1], (ye * ye).sum(0), rtol=1e-12)
+
+
+# ------------------------------------------------------------------------------------------ properties at scale
+def test_large_ensemble_properties_and_subset_parity():
+    """1M Lorenz trajectories (config C2 at 1/10 size): size-independent properties + a strided subset against the oracle."""
+    n = 1_000_000
+    y0 = ob.lorenz_ensemble_y0(n)
+    te = np.arange(1.0, 101.0)
+    g = deb.EnsembleIVP.ode(lorenz(), 0.0, 100.0, y0).t_eval(te).method(E.dopri5().rtol(1e-8)).solve()
+    ok = g.status == 0
+    assert ok.mean() > 0.9
+    assert np.array_equal(g.evals, 3 + 6 * (g.accepted + g.rejected) + g.accepted)
+    assert (g.accepted + g.rejected <= 10000).all()
+    assert ((g.status == deb.DEB_STATUS_MAX_STEPS) == (g.accepted + g.rejected == 10000) | (g.status == deb.DEB_STATUS_MAX_STEPS)).all()
+    assert (g.n_emitted[ok] == 100).all() and np.array_equal(bits(g.y_eval[ok, 99]), bits(g.y_final[ok]))  # exact hit at tf
+    assert np.isfinite(g.y_eval[ok]).all() and np.abs(g.y_eval[ok]).max() < 100.0  # on the attractor
+    # the first 1024 trajectories are config C1: identical results whatever the ensemble size (no cross-talk)
+    g1 = deb.EnsembleIVP.ode(lorenz(), 0.0, 100.0, y0[:1024]).t_eval(te).method(E.dopri5().rtol(1e-8)).solve()
+    assert np.array_equal(bits(g.y_eval[:1024]), bits(g1.y_eval)) and np.array_equal(g.accepted[:1024], g1.accepted)
+    sub = slice(0, n, 4001)
+    c = ob.oracle_solve(deb.EnsembleIVP.ode(lorenz(), 0.0, 100.0, y0[sub]).t_eval(te).method(E.dopri5().rtol(1e-8)))
+    assert np.array_equal(g.status[sub], c.status) and np.array_equal(g.accepted[sub], c.accepted)
+    assert np.array_equal(g.rejected[sub], c.rejected)
+    assert np.array_equal(bits(g.y_final[sub]), bits(c.y_final))
+    m = np.arange(100)[None, :] < c.n_emitted[:, None]
+    assert np.array_equal(bits(g.y_eval[sub])[m], bits(c.y_eval)[m])
