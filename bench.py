@@ -1,0 +1,351 @@
+#!/usr/bin/env python3
+"""bench.py -- accepted trajectory-steps/s of the Lorenz DOPRI5 f64 ensemble (BASELINE.json config[1]).
+
+    python bench.py --gpus N --steps K --warmup W           (N > 1: launched under torchrun, one rank per GPU)
+    python bench.py --impl reference ...                    (the reference algorithm's CPU path, all host threads)
+
+A "step" is one pass of the hot path over the whole ensemble: integrate every trajectory from t0 to tf with DOPRI5
+(t_eval at 100 points recorded to HBM), then reduce the per-t_eval ensemble statistics and all-reduce them.
+Workload: Lorenz sigma=10 rho=28 beta=8/3, y0 = (1,1,1)+U[-0.5,0.5)^3 from splitmix64(2026),
+t in [0,100], dopri5().rtol(1e-8) (atol 1e-6, max_steps 10000, automatic h0), t_eval = 1..100, 10 M trajectories in
+total, split evenly across the ranks ("strong" scaling: the metric names a 10 M ensemble at 1/2/4/8 GPUs).
+
+Printed JSON (one line, rank 0): see the contract in the task statement.  `value` is measured with inputs resident
+in HBM (CUDA events on the launch stream, max over ranks); `e2e` goes through the C ABI with pinned HOST buffers
+(H2D of y0/params and D2H of every result inside the timed region); `roofline` is the FP64 issue roofline of the
+integration kernel against the DADD/DMUL issue peak measured in this run; `cpu_baseline` is the CPU oracle
+(a C++ port of the reference algorithm; the Rust crate cannot be built in this image) on all host threads.
+"""
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "accepted traj-steps/sec, Lorenz DOPRI5 f64 10M ensemble"
+UNIT = "accepted traj-steps/s"
+N_EVAL = 100
+T0, TF = 0.0, 100.0
+# algorithmic DP operations (SURVEY.md 8d / DESIGN.md): 309 per step attempt + 38 per accepted step
+OPS_PER_ATTEMPT, OPS_PER_ACCEPT = 309, 38
+
+
+def lorenz_problem(deb, y0, device=0):
+    return (deb.EnsembleIVP.ode(deb.LorenzSystem(10.0, 28.0, 8.0 / 3.0), T0, TF, y0)
+            .t_eval(np.arange(1.0, N_EVAL + 1.0)).method(deb.ExplicitRungeKutta.dopri5().rtol(1e-8)).device(device))
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc = gpu_index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_rate(ob, deb, n_sample, threads):
+    y0 = ob.lorenz_ensemble_y0(n_sample)
+    t = time.perf_counter()
+    s = ob.oracle_solve(lorenz_problem(deb, y0), threads)
+    dt = time.perf_counter() - t
+    return float(s.accepted.sum()) / dt, dt, int(s.accepted.sum())
+
+
+def cpu_baseline(ob, deb, target_s=15.0):
+    threads = ob.load_oracle().orc_hardware_threads()
+    pilot = max(256, 32 * threads)
+    rate, dt, _ = cpu_rate(ob, deb, pilot, threads)
+    n = int(min(200_000, max(pilot, pilot * target_s / max(dt, 1e-3))))
+    rate, dt, acc = cpu_rate(ob, deb, n, threads)
+    return {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"first {n} trajectories of the same ensemble (same generator, same t_eval), {acc} accepted steps in {dt:.1f} s; "
+                      "C++ port of the reference algorithm (oracle/), g++ -O2 -ffp-contract=off, one std::thread per core"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path = the oracle port (no Rust toolchain here)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    deb = importlib.import_module("differential-equations_b200")
+    import oracle_binding as ob
+    threads = ob.load_oracle().orc_hardware_threads()
+    pilot = max(256, 32 * threads)
+    _, dt, _ = cpu_rate(ob, deb, pilot, threads)
+    total_steps = args.steps + args.warmup
+    n = int(min(200_000, max(pilot, pilot * (120.0 / total_steps) / max(dt, 1e-3))))  # whole run ~2 minutes
+    for _ in range(args.warmup):
+        cpu_rate(ob, deb, n, threads)
+    t = time.perf_counter()
+    acc = 0
+    for _ in range(args.steps):
+        _, _, a = cpu_rate(ob, deb, n, threads)
+        acc += a
+    dt = time.perf_counter() - t
+    value = acc / dt
+    sample = (f"each step = first {n} trajectories of the 10M ensemble (same generator, t_eval, options) through the C++ port of the "
+              f"reference algorithm (oracle/; the Rust crate cannot be built here), {threads} host threads")
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                      "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+                      "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                      "config": {"workload": f"Lorenz DOPRI5 f64 rtol=1e-8, t in [0,100], t_eval at 100 points; bounded sample of {n} trajectories per step"},
+                      "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+                      "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n-traj", type=int, default=10_000_000, help="total ensemble size (BASELINE config: 10M)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    deb = importlib.import_module("differential-equations_b200")
+    import oracle_binding as ob  # cpu_baseline leg + input generator only
+    lib = deb.load_library()  # raises if the extension is missing: no fallback
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the ensemble kernels have no CPU fallback")
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    # ---- shard: trajectories split evenly, rank r takes i = r, r+world, ... (interleaved)
+    n_total = args.n_traj
+    idx = np.arange(rank, n_total, world)
+    n = idx.size
+    # generate only this shard's initial conditions (u_k for k = 3i..3i+2)
+    k = (idx[:, None] * 3 + np.arange(3)[None, :]).reshape(-1).astype(np.uint64) + np.uint64(1)
+    with np.errstate(over="ignore"):
+        z = np.uint64(2026) + k * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    y0_host = (1.0 + ((z >> np.uint64(11)).astype(np.float64) * 2.0 ** -53 - 0.5)).reshape(n, 3)
+    del k, z
+    params_host = np.array([10.0, 28.0, 8.0 / 3.0])
+    t_eval = np.arange(1.0, N_EVAL + 1.0)
+
+    # ---- device-resident buffers (torch = allocator + stream plumbing)
+    d_y0 = torch.from_numpy(y0_host).to(dev)
+    d_params = torch.from_numpy(params_host).to(dev)
+    d_y_eval = torch.empty((n, N_EVAL, 3), dtype=torch.float64, device=dev)
+    d_n_emitted = torch.empty(n, dtype=torch.int32, device=dev)
+    d_t_final = torch.empty(n, dtype=torch.float64, device=dev)
+    d_y_final = torch.empty((n, 3), dtype=torch.float64, device=dev)
+    d_status = torch.empty(n, dtype=torch.int32, device=dev)
+    d_acc = torch.empty(n, dtype=torch.int32, device=dev)
+    d_rej = torch.empty(n, dtype=torch.int32, device=dev)
+    d_evals = torch.empty(n, dtype=torch.int32, device=dev)
+    d_sums = torch.zeros((N_EVAL, 3, 2), dtype=torch.float64, device=dev)
+    d_counts = torch.zeros(N_EVAL, dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    P = deb.OdeProblem()
+    P.struct_size = C.sizeof(deb.OdeProblem)
+    P.system, P.method, P.dim, P.n_params = deb.DEB_SYS_LORENZ, deb.DEB_DOPRI5, 3, 3
+    P.n_traj, P.y0, P.params, P.params_shared = n, d_y0.data_ptr(), d_params.data_ptr(), 1
+    P.n_eval, P.t_eval, P.t0, P.tf = N_EVAL, t_eval.ctypes.data_as(deb._dp), T0, TF
+    lib.deb_erk_options_default(C.byref(P.opt))
+    P.opt.rtol = 1e-8
+    P.device, P.memspace, P.stream = local_rank, deb.DEB_MEM_DEVICE, stream.cuda_stream
+    R = deb.Result()
+    R.struct_size = C.sizeof(deb.Result)
+    R.y_eval, R.n_emitted, R.t_final, R.y_final = d_y_eval.data_ptr(), d_n_emitted.data_ptr(), d_t_final.data_ptr(), d_y_final.data_ptr()
+    R.status, R.accepted, R.rejected, R.evals = d_status.data_ptr(), d_acc.data_ptr(), d_rej.data_ptr(), d_evals.data_ptr()
+
+    kernel_events = []
+
+    def step(timed):
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        rc = lib.deb_solve_ode(C.byref(P), C.byref(R))           # 1 launch: dp_ensemble_kernel<Lorenz, DOPRI5>
+        if rc != 0:
+            raise RuntimeError(lib.deb_last_error().decode())
+        e1.record(stream)
+        rc = lib.deb_ensemble_stats(d_y_eval.data_ptr(), d_n_emitted.data_ptr(), n, N_EVAL, 3, d_sums.data_ptr(), d_counts.data_ptr(),
+                                    local_rank, deb.DEB_MEM_DEVICE, stream.cuda_stream)  # 2 launches
+        if rc != 0:
+            raise RuntimeError(lib.deb_last_error().decode())
+        if dist is not None:  # the only cross-GPU traffic: 4.8 KB of sums + counts
+            dist.all_reduce(d_sums)
+            dist.all_reduce(d_counts)
+        if timed:
+            kernel_events.append((e0, e1))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step(False)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record(stream)
+    for _ in range(args.steps):
+        step(True)
+    t1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    elapsed_ms = t0.elapsed_time(t1)
+    kernel_ms = sum(a.elapsed_time(b) for a, b in kernel_events) / len(kernel_events)
+
+    acc_local = int(d_acc.sum(dtype=torch.int64).item())
+    rej_local = int(d_rej.sum(dtype=torch.int64).item())
+    n_complete = int((d_status == 0).sum().item())
+    red = torch.tensor([acc_local, rej_local, n_complete], dtype=torch.int64, device=dev)
+    tmax = torch.tensor([elapsed_ms, kernel_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(red)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    acc_total, rej_total, complete_total = (int(x) for x in red.tolist())
+    elapsed_ms, kernel_ms_max = tmax.tolist()
+    ms_per_step = elapsed_ms / args.steps
+    value = acc_total / (ms_per_step * 1e-3)
+
+    # ---- roofline of the integration kernel: algorithmic DP ops / kernel time vs the measured DP issue peak
+    peak = C.c_double(0)
+    pk_ms = C.c_float(0)
+    lib.deb_fp64_issue_peak(local_rank, 0, C.byref(peak), C.byref(pk_ms))
+    ops_local = OPS_PER_ATTEMPT * (acc_local + rej_local) + OPS_PER_ACCEPT * acc_local
+    achieved = ops_local / (kernel_ms * 1e-3) / 1e12
+    roofline = {"bound": "fp64", "achieved": achieved, "peak": peak.value / 1e12, "unit": "TFLOP/s",
+                "frac": achieved / (peak.value / 1e12), "traffic": None,
+                "kernel": "deb::dp_ensemble_kernel<SysLorenz, TabDopri5, 128, 4>", "kernel_ms": kernel_ms,
+                "peak_source": "measured in this run: register-only DADD/DMUL stream on all SMs (deb_fp64_issue_peak); "
+                               "MEASURED_PEAKS.json has no FP64 entry. The reference arithmetic forbids FMA fusion, so the bound is DP "
+                               "instruction issue (1 op per instruction), not the 2x DFMA figure",
+                "algorithmic_ops": f"{OPS_PER_ATTEMPT}*(accepted+rejected) + {OPS_PER_ACCEPT}*accepted DP ops per launch (rank 0: {ops_local})"}
+
+    # ---- e2e: the public C-ABI call with pinned HOST buffers; H2D + kernel + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        del d_y_eval  # make room: the HOST path stages its own device mirror of y_eval
+        torch.cuda.empty_cache()
+        pin = dict(pin_memory=True)
+        h_y0 = torch.from_numpy(y0_host).pin_memory()
+        h_params = torch.from_numpy(params_host).pin_memory()
+        h_y_eval = torch.empty((n, N_EVAL, 3), dtype=torch.float64, **pin)
+        h_n_emitted = torch.empty(n, dtype=torch.int32, **pin)
+        h_t_final = torch.empty(n, dtype=torch.float64, **pin)
+        h_y_final = torch.empty((n, 3), dtype=torch.float64, **pin)
+        h_i32 = [torch.empty(n, dtype=torch.int32, **pin) for _ in range(4)]
+        PH = deb.OdeProblem()
+        C.memmove(C.byref(PH), C.byref(P), C.sizeof(deb.OdeProblem))
+        PH.y0, PH.params, PH.memspace, PH.stream = h_y0.data_ptr(), h_params.data_ptr(), deb.DEB_MEM_HOST, None
+        RH = deb.Result()
+        RH.struct_size = C.sizeof(deb.Result)
+        RH.y_eval, RH.n_emitted, RH.t_final, RH.y_final = h_y_eval.data_ptr(), h_n_emitted.data_ptr(), h_t_final.data_ptr(), h_y_final.data_ptr()
+        RH.status, RH.accepted, RH.rejected, RH.evals = (t.data_ptr() for t in h_i32)
+        h2d = h_y0.numel() * 8 + h_params.numel() * 8
+        d2h = h_y_eval.numel() * 8 + h_t_final.numel() * 8 + h_y_final.numel() * 8 + 5 * n * 4
+
+        def e2e_step():
+            rc = lib.deb_solve_ode(C.byref(PH), C.byref(RH))
+            if rc != 0:
+                raise RuntimeError(lib.deb_last_error().decode())
+        e2e_step()  # warm-up (page-touch of the pinned buffers, allocator)
+        barrier()
+        w0 = time.perf_counter()
+        e_steps = max(1, min(args.steps, 2))
+        for _ in range(e_steps):
+            e2e_step()
+        barrier()
+        e_ms = (time.perf_counter() - w0) * 1e3 / e_steps
+        acc_e = torch.tensor([int(h_i32[1].sum(dtype=torch.int64).item())], dtype=torch.int64, device=dev)
+        e_t = torch.tensor([e_ms], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(acc_e)
+            dist.all_reduce(e_t, op=dist.ReduceOp.MAX)
+        e2e = {"value": int(acc_e.item()) / (e_t.item() * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": e_t.item(), "steps": e_steps,
+               "how": "deb_solve_ode(memspace=HOST) on pinned host buffers: H2D y0+params, kernel, D2H y_eval/finals/counters; wall clock, max over ranks"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(ob, deb)
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic",
+               "config": {"workload": "Lorenz (sigma=10,rho=28,beta=8/3) DOPRI5 f64 rtol=1e-8 atol=1e-6, t in [0,100], t_eval at 100 points, "
+                                      f"{n_total} trajectories total split evenly over {world} GPU(s) (BASELINE.json configs[1])",
+                          "n_traj_total": n_total, "n_traj_per_gpu": n, "t_eval_points": N_EVAL,
+                          "l2": "inputs and outputs larger than L2 (y0 240 MB, y_eval 24 GB per 10M); no reuse between steps",
+                          "accepted_steps": acc_total, "rejected_steps": rej_total, "complete_trajectories": complete_total},
+               "gpu_launches": 3 * args.steps,
+               "clocks": clocks, "roofline": roofline}
+        if e2e is not None:
+            out["e2e"] = e2e
+        if cpu is not None:
+            out["cpu_baseline"] = cpu
+        print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
