@@ -187,7 +187,6 @@ def main():
 
     # ---- device-resident buffers (torch = allocator + stream plumbing)
     d_y0 = torch.from_numpy(y0_host).to(dev)
-    d_params = torch.from_numpy(params_host).to(dev)
     d_y_eval = torch.empty((n, N_EVAL, 3), dtype=torch.float64, device=dev)
     d_n_emitted = torch.empty(n, dtype=torch.int32, device=dev)
     d_t_final = torch.empty(n, dtype=torch.float64, device=dev)
@@ -203,7 +202,7 @@ def main():
     P = deb.OdeProblem()
     P.struct_size = C.sizeof(deb.OdeProblem)
     P.system, P.method, P.dim, P.n_params = deb.DEB_SYS_LORENZ, deb.DEB_DOPRI5, 3, 3
-    P.n_traj, P.y0, P.params, P.params_shared = n, d_y0.data_ptr(), d_params.data_ptr(), 1
+    P.n_traj, P.y0, P.params, P.params_shared = n, d_y0.data_ptr(), params_host.ctypes.data, 1  # shared set: host pointer
     P.n_eval, P.t_eval, P.t0, P.tf = N_EVAL, t_eval.ctypes.data_as(deb._dp), T0, TF
     lib.deb_erk_options_default(C.byref(P.opt))
     P.opt.rtol = 1e-8

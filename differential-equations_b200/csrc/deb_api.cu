@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -69,9 +70,9 @@ int device_info(int device, DeviceInfo* di) {
 // ------------------------------------------------------------------------------------------------ kernel table
 typedef int (*ode_launch_fn)(const deb::OdeKernelArgs&, int sms, cudaStream_t);
 
-template <class Sys, class Tab, int BLOCK, int MIN_BLOCKS>
-int launch_dp(const deb::OdeKernelArgs& a, int sms, cudaStream_t st) {
-    auto kern = deb::dp_ensemble_kernel<Sys, Tab, BLOCK, MIN_BLOCKS>;
+template <class Sys, class Tab, int BLOCK, int MIN_BLOCKS, bool SHARED_P>
+int launch_dp_impl(const deb::OdeKernelArgs& a, int sms, cudaStream_t st) {
+    auto kern = deb::dp_ensemble_kernel<Sys, Tab, BLOCK, MIN_BLOCKS, SHARED_P>;
     int per_sm = 0;
     DEB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, 0));
     if (per_sm < 1) per_sm = 1;
@@ -83,6 +84,13 @@ int launch_dp(const deb::OdeKernelArgs& a, int sms, cudaStream_t st) {
     kern<<<(unsigned)blocks, BLOCK, 0, st>>>(a);
     DEB_CUDA(cudaGetLastError());
     return DEB_OK;
+}
+
+template <class Sys, class Tab, int BLOCK, int MIN_BLOCKS>
+int launch_dp(const deb::OdeKernelArgs& a, int sms, cudaStream_t st) {
+    // a.pc is filled by the caller iff the parameter set is shared (params_stride == 0) and lives on the host
+    if (a.params_stride == 0 && a.params == nullptr) return launch_dp_impl<Sys, Tab, BLOCK, MIN_BLOCKS, true>(a, sms, st);
+    return launch_dp_impl<Sys, Tab, BLOCK, MIN_BLOCKS, false>(a, sms, st);
 }
 
 template <class Sys, class Tab>
@@ -100,8 +108,21 @@ int launch_fixed(const deb::OdeKernelArgs& a, int sms, cudaStream_t st) {
 
 template <class Sys>
 ode_launch_fn pick_ode_method(int method) {
+    if (method == DEB_DOPRI5 && Sys::DIM == 3) {  // EXPERIMENT: launch-shape variants
+        const char* v = getenv("DEB_DP_VARIANT");
+        if (v) {
+            switch (atoi(v)) {
+                case 1: return launch_dp<Sys, deb::TabDopri5, 64, 9>;
+                case 2: return launch_dp<Sys, deb::TabDopri5, 64, 10>;
+                case 3: return launch_dp<Sys, deb::TabDopri5, 32, 19>;
+                case 4: return launch_dp<Sys, deb::TabDopri5, 32, 21>;
+                case 5: return launch_dp<Sys, deb::TabDopri5, 128, 5>;
+                case 6: return launch_dp<Sys, deb::TabDopri5, 128, 4>;
+            }
+        }
+    }
     switch (method) {
-        case DEB_DOPRI5: return launch_dp<Sys, deb::TabDopri5, 128, 4>;
+        case DEB_DOPRI5: return launch_dp<Sys, deb::TabDopri5, 256, 2>;  // 128 regs, no spills, 16 warps/SM (sweep: profiles/)
         case DEB_DOP853: return launch_dp<Sys, deb::TabDop853, 128, 2>;
         case DEB_EULER: return launch_fixed<Sys, deb::TabEuler>;
         case DEB_MIDPOINT: return launch_fixed<Sys, deb::TabMidpoint>;
@@ -313,14 +334,18 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P, deb_result* R) {
         DEB_CUDA(d_y0.alloc(sizeof(double) * (size_t)n * dim));
         DEB_CUDA(cudaMemcpyAsync(d_y0.p, P->y0, sizeof(double) * (size_t)n * dim, cudaMemcpyHostToDevice, st));
         a.y0 = d_y0.as<double>();
-        if (np > 0) {
-            const size_t cnt = P->params_shared ? (size_t)np : (size_t)n * np;
-            DEB_CUDA(d_params.alloc(sizeof(double) * cnt));
-            DEB_CUDA(cudaMemcpyAsync(d_params.p, P->params, sizeof(double) * cnt, cudaMemcpyHostToDevice, st));
-            a.params = d_params.as<double>();
-        }
     } else {
         a.y0 = P->y0;
+    }
+    if (np > 0 && P->params_shared) {
+        // one parameter set for the whole ensemble: HOST memory by contract, passed by value (constant bank)
+        for (int q = 0; q < np && q < 8; q++) a.pc[q] = P->params[q];
+        a.params = nullptr;
+    } else if (np > 0 && host) {
+        DEB_CUDA(d_params.alloc(sizeof(double) * (size_t)n * np));
+        DEB_CUDA(cudaMemcpyAsync(d_params.p, P->params, sizeof(double) * (size_t)n * np, cudaMemcpyHostToDevice, st));
+        a.params = d_params.as<double>();
+    } else {
         a.params = P->params;
     }
     a.params_stride = P->params_shared ? 0 : np;
@@ -411,17 +436,28 @@ extern "C" int deb_solve_sde(const deb_sde_problem* P, deb_result* R) {
     deb::SdeKernelArgs a;
     memset(&a, 0, sizeof a);
     DevBuf d_y0, d_params;
-    const size_t y0_cnt = P->y0_shared ? 1 : (size_t)n;
-    const size_t p_cnt = P->params_shared ? (size_t)np : (size_t)n * np;
-    if (host) {
-        DEB_CUDA(d_y0.alloc(sizeof(double) * y0_cnt));
-        DEB_CUDA(cudaMemcpyAsync(d_y0.p, P->y0, sizeof(double) * y0_cnt, cudaMemcpyHostToDevice, st));
-        DEB_CUDA(d_params.alloc(sizeof(double) * p_cnt));
-        DEB_CUDA(cudaMemcpyAsync(d_params.p, P->params, sizeof(double) * p_cnt, cudaMemcpyHostToDevice, st));
+    // y0: [n_traj] in `memspace`, or ONE value in HOST memory when y0_shared; params likewise (see the header)
+    double y0_one = 0.0;
+    if (P->y0_shared) {
+        y0_one = P->y0[0];
+        DEB_CUDA(d_y0.alloc(sizeof(double)));
+        DEB_CUDA(cudaMemcpyAsync(d_y0.p, &y0_one, sizeof(double), cudaMemcpyHostToDevice, st));
         a.y0 = d_y0.as<double>();
-        a.params = d_params.as<double>();
+    } else if (host) {
+        DEB_CUDA(d_y0.alloc(sizeof(double) * (size_t)n));
+        DEB_CUDA(cudaMemcpyAsync(d_y0.p, P->y0, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+        a.y0 = d_y0.as<double>();
     } else {
         a.y0 = P->y0;
+    }
+    if (P->params_shared) {
+        for (int q = 0; q < np && q < 8; q++) a.pc[q] = P->params[q];
+        a.params = nullptr;
+    } else if (host) {
+        DEB_CUDA(d_params.alloc(sizeof(double) * (size_t)n * np));
+        DEB_CUDA(cudaMemcpyAsync(d_params.p, P->params, sizeof(double) * (size_t)n * np, cudaMemcpyHostToDevice, st));
+        a.params = d_params.as<double>();
+    } else {
         a.params = P->params;
     }
     a.y0_stride = P->y0_shared ? 0 : 1;

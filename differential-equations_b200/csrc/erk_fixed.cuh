@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(BLOCK) fixed_ensemble_kernel(const OdeKernelAr
 #pragma unroll
         for (int c = 0; c < N; c++) y[c] = a.y0[traj * N + c];
 #pragma unroll
-        for (int q = 0; q < NP; q++) p[q] = a.params[traj * a.params_stride + q];
+        for (int q = 0; q < NP; q++) p[q] = a.params ? a.params[traj * a.params_stride + q] : a.pc[q];
         int steps = 0, evals = 0, n_emit = 0, idx = 0;
         int fin = -1;
         double t = t0;
@@ -71,12 +71,12 @@ __global__ void __launch_bounds__(BLOCK) fixed_ensemble_kernel(const OdeKernelAr
                 for (int j = 0; j < i; j++) {
                     const double aij = Tab::a(i, j);
                     if (aij != 0.0) {
-                        const double ah = aij * h;
+                        const double ah = Tab::av(i, j) * h;
 #pragma unroll
                         for (int c = 0; c < N; c++) ys[c] = ys[c] + ah * k[j][c];
                     }
                 }
-                Sys::rhs(t + Tab::c(i) * h, ys, k[i], p);
+                Sys::rhs(t + Tab::cv(i) * h, ys, k[i], p);
             }
             double ynew[N], dnew[N];
 #pragma unroll
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(BLOCK) fixed_ensemble_kernel(const OdeKernelAr
 #pragma unroll
             for (int i = 0; i < S; i++) {
                 if (Tab::b(i) != 0.0) {
-                    const double bh = Tab::b(i) * h;
+                    const double bh = Tab::bv(i) * h;
 #pragma unroll
                     for (int c = 0; c < N; c++) ynew[c] = ynew[c] + bh * k[i][c];
                 }

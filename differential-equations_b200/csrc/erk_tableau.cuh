@@ -10,53 +10,85 @@
 
 namespace deb {
 
-#define DEB_TAB_FN1(name, len, init) \
-    __host__ __device__ static constexpr double name(int i) { constexpr double v[len] = init; return v[i]; }
-#define DEB_TAB_FN2(name, len, init) \
-    __host__ __device__ static constexpr double name(int i, int j) { constexpr double v[len][len] = init; return v[i][j]; }
+// name(i[,j]): constexpr value, used ONLY for compile-time decisions (is this coefficient zero?).
+// name##v(i[,j]): the run-time operand, read from a __constant__ image of the same table.  With compile-time
+// indices it becomes a constant-bank operand of the DMUL/DADD itself (c[3][off]); a 64-bit immediate would instead
+// cost two UMOV issue slots per use (measured: 10% of all issued instructions in the first version of the kernel).
+#define DEB_TAB_FN1(name, len, init, cname)                                                                      \
+    __host__ __device__ static constexpr double name(int i) { constexpr double v[len] = init; return v[i]; }     \
+    __device__ __forceinline__ static double name##v(int i) { return cmem::cname[i]; }
+#define DEB_TAB_FN2(name, len, init, cname)                                                                                \
+    __host__ __device__ static constexpr double name(int i, int j) { constexpr double v[len][len] = init; return v[i][j]; } \
+    __device__ __forceinline__ static double name##v(int i, int j) { return cmem::cname[i][j]; }
+
+namespace cmem {
+__constant__ double d5_c[7] = DEB_DOPRI5_C;
+__constant__ double d5_a[7][7] = DEB_DOPRI5_A;
+__constant__ double d5_b[7] = DEB_DOPRI5_B;
+__constant__ double d5_er[7] = DEB_DOPRI5_ER;
+__constant__ double d5_bi[7][7] = DEB_DOPRI5_BI;
+__constant__ double d8_c[16] = DEB_DOP853_C;
+__constant__ double d8_a[16][16] = DEB_DOP853_A;
+__constant__ double d8_b[12] = DEB_DOP853_B;
+__constant__ double d8_bh[12] = DEB_DOP853_BH;
+__constant__ double d8_er[12] = DEB_DOP853_ER;
+__constant__ double d8_bi[16][16] = DEB_DOP853_BI;
+#define DEB_CMEM_FIXED(pfx, PFX, n)                  \
+    __constant__ double pfx##_c[n] = DEB_##PFX##_C;  \
+    __constant__ double pfx##_a[n][n] = DEB_##PFX##_A; \
+    __constant__ double pfx##_b[n] = DEB_##PFX##_B;
+DEB_CMEM_FIXED(euler, EULER, 1)
+DEB_CMEM_FIXED(midpoint, MIDPOINT, 2)
+DEB_CMEM_FIXED(heun, HEUN, 2)
+DEB_CMEM_FIXED(ralston, RALSTON, 2)
+DEB_CMEM_FIXED(ssp_rk3, SSP_RK3, 3)
+DEB_CMEM_FIXED(rk4, RK4, 4)
+DEB_CMEM_FIXED(three_eighths, THREE_EIGHTHS, 4)
+}  // namespace cmem
 
 // DOPRI5: /root/reference/src/tableau/dorman_prince.rs:37-117; (O,S,I) = (5,7,7) dormandprince/mod.rs:52-58
 struct TabDopri5 {
     static constexpr int O = 5, S = 7, I = 7;
     static constexpr bool ADAPTIVE = true, HAS_BH = false;
-    DEB_TAB_FN1(c, 7, DEB_DOPRI5_C)
-    DEB_TAB_FN2(a, 7, DEB_DOPRI5_A)
-    DEB_TAB_FN1(b, 7, DEB_DOPRI5_B)
-    DEB_TAB_FN1(er, 7, DEB_DOPRI5_ER)
+    DEB_TAB_FN1(c, 7, DEB_DOPRI5_C, d5_c)
+    DEB_TAB_FN2(a, 7, DEB_DOPRI5_A, d5_a)
+    DEB_TAB_FN1(b, 7, DEB_DOPRI5_B, d5_b)
+    DEB_TAB_FN1(er, 7, DEB_DOPRI5_ER, d5_er)
     __host__ __device__ static constexpr double bh(int) { return 0.0; }
+    __device__ __forceinline__ static double bhv(int) { return 0.0; }
     // The stepper reads bi[4][j] (dormandprince/ordinary.rs:229-233) but dopri5() filled row 0
     // (dorman_prince.rs:95-101): rows 4.. are zero, so cont[4] == 0.  Kept as in the reference.
-    DEB_TAB_FN2(bi, 7, DEB_DOPRI5_BI)
+    DEB_TAB_FN2(bi, 7, DEB_DOPRI5_BI, d5_bi)
 };
 
 // DOP853: /root/reference/src/tableau/dorman_prince.rs:155-381; (O,S,I) = (8,12,16) dormandprince/mod.rs:45-51
 struct TabDop853 {
     static constexpr int O = 8, S = 12, I = 16;
     static constexpr bool ADAPTIVE = true, HAS_BH = true;
-    DEB_TAB_FN1(c, 16, DEB_DOP853_C)
-    DEB_TAB_FN2(a, 16, DEB_DOP853_A)
-    DEB_TAB_FN1(b, 12, DEB_DOP853_B)
-    DEB_TAB_FN1(bh, 12, DEB_DOP853_BH)
-    DEB_TAB_FN1(er, 12, DEB_DOP853_ER)
-    DEB_TAB_FN2(bi, 16, DEB_DOP853_BI)
+    DEB_TAB_FN1(c, 16, DEB_DOP853_C, d8_c)
+    DEB_TAB_FN2(a, 16, DEB_DOP853_A, d8_a)
+    DEB_TAB_FN1(b, 12, DEB_DOP853_B, d8_b)
+    DEB_TAB_FN1(bh, 12, DEB_DOP853_BH, d8_bh)
+    DEB_TAB_FN1(er, 12, DEB_DOP853_ER, d8_er)
+    DEB_TAB_FN2(bi, 16, DEB_DOP853_BI, d8_bi)
 };
 
-#define DEB_FIXED_TAB(Name, PFX, order, stages)                      \
+#define DEB_FIXED_TAB(Name, PFX, pfx, order, stages)                 \
     struct Name {                                                    \
         static constexpr int O = order, S = stages, I = stages;      \
         static constexpr bool ADAPTIVE = false, HAS_BH = false;      \
-        DEB_TAB_FN1(c, stages, DEB_##PFX##_C)                        \
-        DEB_TAB_FN2(a, stages, DEB_##PFX##_A)                        \
-        DEB_TAB_FN1(b, stages, DEB_##PFX##_B)                        \
+        DEB_TAB_FN1(c, stages, DEB_##PFX##_C, pfx##_c)               \
+        DEB_TAB_FN2(a, stages, DEB_##PFX##_A, pfx##_a)               \
+        DEB_TAB_FN1(b, stages, DEB_##PFX##_B, pfx##_b)               \
     };
 
 // fixed-step constructors, /root/reference/src/methods/erk/fixed/mod.rs:41-89 (order, stages); fsal = false for all
-DEB_FIXED_TAB(TabEuler, EULER, 1, 1)
-DEB_FIXED_TAB(TabMidpoint, MIDPOINT, 2, 2)
-DEB_FIXED_TAB(TabHeun, HEUN, 2, 2)
-DEB_FIXED_TAB(TabRalston, RALSTON, 2, 2)
-DEB_FIXED_TAB(TabSspRk3, SSP_RK3, 3, 3)
-DEB_FIXED_TAB(TabRk4, RK4, 4, 4)
-DEB_FIXED_TAB(TabThreeEighths, THREE_EIGHTHS, 4, 4)
+DEB_FIXED_TAB(TabEuler, EULER, euler, 1, 1)
+DEB_FIXED_TAB(TabMidpoint, MIDPOINT, midpoint, 2, 2)
+DEB_FIXED_TAB(TabHeun, HEUN, heun, 2, 2)
+DEB_FIXED_TAB(TabRalston, RALSTON, ralston, 2, 2)
+DEB_FIXED_TAB(TabSspRk3, SSP_RK3, ssp_rk3, 3, 3)
+DEB_FIXED_TAB(TabRk4, RK4, rk4, 4, 4)
+DEB_FIXED_TAB(TabThreeEighths, THREE_EIGHTHS, three_eighths, 4, 4)
 
 }  // namespace deb

@@ -46,6 +46,8 @@ static inline double deb_as_f64_(uint64_t u) { double x; memcpy(&x, &u, 8); retu
 // shared memory once per CTA (lanes index them divergently, which constant memory serialises) and pass
 // the shared pointers in.
 #if defined(__CUDACC__)
+// scalar coefficients: constant-bank operands on the device (a 64-bit immediate costs two UMOV issue slots per use)
+__constant__ double deb_c_powk[17] = {DEB_POWLOG_LN2HI, DEB_POWLOG_LN2LO, DEB_POWLOG_A0, DEB_POWLOG_A1, DEB_POWLOG_A2, DEB_POWLOG_A3, DEB_POWLOG_A4, DEB_POWLOG_A5, DEB_POWLOG_A6, DEB_EXP_INVLN2N, DEB_EXP_SHIFT, DEB_EXP_NEGLN2HIN, DEB_EXP_NEGLN2LON, DEB_EXP_C2, DEB_EXP_C3, DEB_EXP_C4, DEB_EXP_C5};
 __constant__ double deb_c_powlog_tab[128 * 3] = DEB_POWLOG_TAB_INIT;
 __constant__ unsigned long long deb_c_exp_tab[128 * 2] = DEB_EXP_TAB_INIT;
 #endif
@@ -66,6 +68,44 @@ static inline deb_pow_tables deb_host_pow_tables() {
 #endif
 
 // pow(x, y) for x >= 0 (or NaN/inf), y "ordinary" (see header comment).
+#if defined(__CUDA_ARCH__)
+#define DEBK_POWLOG_LN2HI deb_c_powk[0]
+#define DEBK_POWLOG_LN2LO deb_c_powk[1]
+#define DEBK_POWLOG_A0 deb_c_powk[2]
+#define DEBK_POWLOG_A1 deb_c_powk[3]
+#define DEBK_POWLOG_A2 deb_c_powk[4]
+#define DEBK_POWLOG_A3 deb_c_powk[5]
+#define DEBK_POWLOG_A4 deb_c_powk[6]
+#define DEBK_POWLOG_A5 deb_c_powk[7]
+#define DEBK_POWLOG_A6 deb_c_powk[8]
+#define DEBK_EXP_INVLN2N deb_c_powk[9]
+#define DEBK_EXP_SHIFT deb_c_powk[10]
+#define DEBK_EXP_NEGLN2HIN deb_c_powk[11]
+#define DEBK_EXP_NEGLN2LON deb_c_powk[12]
+#define DEBK_EXP_C2 deb_c_powk[13]
+#define DEBK_EXP_C3 deb_c_powk[14]
+#define DEBK_EXP_C4 deb_c_powk[15]
+#define DEBK_EXP_C5 deb_c_powk[16]
+#else
+#define DEBK_POWLOG_LN2HI DEB_POWLOG_LN2HI
+#define DEBK_POWLOG_LN2LO DEB_POWLOG_LN2LO
+#define DEBK_POWLOG_A0 DEB_POWLOG_A0
+#define DEBK_POWLOG_A1 DEB_POWLOG_A1
+#define DEBK_POWLOG_A2 DEB_POWLOG_A2
+#define DEBK_POWLOG_A3 DEB_POWLOG_A3
+#define DEBK_POWLOG_A4 DEB_POWLOG_A4
+#define DEBK_POWLOG_A5 DEB_POWLOG_A5
+#define DEBK_POWLOG_A6 DEB_POWLOG_A6
+#define DEBK_EXP_INVLN2N DEB_EXP_INVLN2N
+#define DEBK_EXP_SHIFT DEB_EXP_SHIFT
+#define DEBK_EXP_NEGLN2HIN DEB_EXP_NEGLN2HIN
+#define DEBK_EXP_NEGLN2LON DEB_EXP_NEGLN2LON
+#define DEBK_EXP_C2 DEB_EXP_C2
+#define DEBK_EXP_C3 DEB_EXP_C3
+#define DEBK_EXP_C4 DEB_EXP_C4
+#define DEBK_EXP_C5 DEB_EXP_C5
+#endif
+
 DEB_HD double deb_pow_pos(double x, double y, const deb_pow_tables tb) {
     uint64_t ix = DEB_AS_U64(x);
     uint32_t topx = (uint32_t)(ix >> 52);
@@ -91,19 +131,19 @@ DEB_HD double deb_pow_pos(double x, double y, const deb_pow_tables tb) {
     double logc = tb.powlog[3 * i + 1];
     double logctail = tb.powlog[3 * i + 2];
 
-    double t1 = DEB_FMA(kd, DEB_POWLOG_LN2HI, logc);
-    double lo1 = DEB_FMA(kd, DEB_POWLOG_LN2LO, logctail);
+    double t1 = DEB_FMA(kd, DEBK_POWLOG_LN2HI, logc);
+    double lo1 = DEB_FMA(kd, DEBK_POWLOG_LN2LO, logctail);
     double r = DEB_FMA(z, invc, -1.0);
-    double ar = DEB_MUL(r, DEB_POWLOG_A0);
-    double p12 = DEB_FMA(r, DEB_POWLOG_A2, DEB_POWLOG_A1);
-    double p34 = DEB_FMA(r, DEB_POWLOG_A4, DEB_POWLOG_A3);
+    double ar = DEB_MUL(r, DEBK_POWLOG_A0);
+    double p12 = DEB_FMA(r, DEBK_POWLOG_A2, DEBK_POWLOG_A1);
+    double p34 = DEB_FMA(r, DEBK_POWLOG_A4, DEBK_POWLOG_A3);
     double t2 = DEB_ADD(r, t1);
     double lo2 = DEB_ADD(DEB_SUB(t1, t2), r);
     double ar2 = DEB_MUL(r, ar);
     double ar3 = DEB_MUL(r, ar2);
     double lo3 = DEB_FMA(ar, r, -ar2);
     double hi = DEB_ADD(t2, ar2);
-    double p56 = DEB_FMA(r, DEB_POWLOG_A6, DEB_POWLOG_A5);
+    double p56 = DEB_FMA(r, DEBK_POWLOG_A6, DEBK_POWLOG_A5);
     double lo4 = DEB_ADD(DEB_SUB(t2, hi), ar2);
     double q = DEB_FMA(p56, ar2, p34);
     double pp = DEB_FMA(ar2, q, p12);
@@ -126,20 +166,20 @@ DEB_HD double deb_pow_pos(double x, double y, const deb_pow_tables tb) {
         }
         big = true;  // 512 <= |y log x| < 1024: result may over/underflow, handled below
     }
-    double zs = DEB_FMA(ehi, DEB_EXP_INVLN2N, DEB_EXP_SHIFT);
+    double zs = DEB_FMA(ehi, DEBK_EXP_INVLN2N, DEBK_EXP_SHIFT);
     uint64_t ki = DEB_AS_U64(zs);
-    double kd2 = DEB_SUB(zs, DEB_EXP_SHIFT);
-    double r0 = DEB_FMA(kd2, DEB_EXP_NEGLN2HIN, ehi);
-    double r1 = DEB_FMA(kd2, DEB_EXP_NEGLN2LON, r0);
+    double kd2 = DEB_SUB(zs, DEBK_EXP_SHIFT);
+    double r0 = DEB_FMA(kd2, DEBK_EXP_NEGLN2HIN, ehi);
+    double r1 = DEB_FMA(kd2, DEBK_EXP_NEGLN2LON, r0);
     double rr = DEB_ADD(elo, r1);
     uint32_t idx = 2u * (uint32_t)(ki & 127);
     uint64_t top = ki << 45;
     double tail = DEB_AS_F64(tb.exptab[idx]);
     uint64_t sbits = tb.exptab[idx + 1] + top;
-    double c23 = DEB_FMA(rr, DEB_EXP_C3, DEB_EXP_C2);
+    double c23 = DEB_FMA(rr, DEBK_EXP_C3, DEBK_EXP_C2);
     double tr = DEB_ADD(rr, tail);
     double r2 = DEB_MUL(rr, rr);
-    double c45 = DEB_FMA(rr, DEB_EXP_C5, DEB_EXP_C4);
+    double c45 = DEB_FMA(rr, DEBK_EXP_C5, DEBK_EXP_C4);
     double s1 = DEB_FMA(c23, r2, tr);
     double r4 = DEB_MUL(r2, r2);
     double tm = DEB_FMA(c45, r4, s1);

@@ -49,11 +49,11 @@ __device__ __forceinline__ double combine1(const HeatArgs& a, long long i) {
     if (STAGE < Tab::S) {
 #pragma unroll
         for (int j = 0; j < ST; j++)
-            if (Tab::a(ST, j) != 0.0) w = w + (Tab::a(ST, j) * a.h) * a.k[j][i];
+            if (Tab::a(ST, j) != 0.0) w = w + (Tab::av(ST, j) * a.h) * a.k[j][i];
     } else {
 #pragma unroll
         for (int j = 0; j < Tab::S; j++)
-            if (Tab::b(j) != 0.0) w = w + (Tab::b(j) * a.h) * a.k[j][i];
+            if (Tab::b(j) != 0.0) w = w + (Tab::bv(j) * a.h) * a.k[j][i];
     }
     return w;
 }
@@ -66,7 +66,7 @@ __device__ __forceinline__ double2 combine2(const HeatArgs& a, long long i0) {
         for (int j = 0; j < ST; j++)
             if (Tab::a(ST, j) != 0.0) {
                 const double2 kk = *reinterpret_cast<const double2*>(a.k[j] + i0);
-                const double ah = Tab::a(ST, j) * a.h;
+                const double ah = Tab::av(ST, j) * a.h;
                 w.x = w.x + ah * kk.x;
                 w.y = w.y + ah * kk.y;
             }
@@ -75,7 +75,7 @@ __device__ __forceinline__ double2 combine2(const HeatArgs& a, long long i0) {
         for (int j = 0; j < Tab::S; j++)
             if (Tab::b(j) != 0.0) {
                 const double2 kk = *reinterpret_cast<const double2*>(a.k[j] + i0);
-                const double bh = Tab::b(j) * a.h;
+                const double bh = Tab::bv(j) * a.h;
                 w.x = w.x + bh * kk.x;
                 w.y = w.y + bh * kk.y;
             }

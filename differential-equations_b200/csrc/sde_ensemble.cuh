@@ -17,6 +17,7 @@ struct SdeKernelArgs {
     int y0_stride;       // 1, or 0 when one y0 is shared by all paths
     const double* params;
     int params_stride;   // NP, or 0 when shared
+    double pc[8];        // the shared parameter set by value (params == nullptr)
     long long n_traj;
     long long path_offset;
     unsigned long long seed;
@@ -46,7 +47,7 @@ __global__ void __launch_bounds__(BLOCK) sde_ensemble_kernel(const SdeKernelArgs
     for (long long traj = (long long)blockIdx.x * BLOCK + threadIdx.x; traj < a.n_traj; traj += stride) {
         double p[NP > 0 ? NP : 1];
 #pragma unroll
-        for (int q = 0; q < NP; q++) p[q] = a.params[traj * a.params_stride + q];
+        for (int q = 0; q < NP; q++) p[q] = a.params ? a.params[traj * a.params_stride + q] : a.pc[q];
         double y = a.y0[traj * a.y0_stride];
         const unsigned long long path = (unsigned long long)(a.path_offset + traj);
         int steps = 0, evals = 0, n_emit = 0, idx = 0, fin = -1;
@@ -84,14 +85,14 @@ __global__ void __launch_bounds__(BLOCK) sde_ensemble_kernel(const SdeKernelArgs
                 double ys = y;
 #pragma unroll
                 for (int j = 0; j < i; j++) {
-                    if (Tab::a(i, j) != 0.0) ys = ys + (Tab::a(i, j) * h) * k[j];
+                    if (Tab::a(i, j) != 0.0) ys = ys + (Tab::av(i, j) * h) * k[j];
                 }
-                k[i] = Sde::drift(t + Tab::c(i) * h, ys, p);
+                k[i] = Sde::drift(t + Tab::cv(i) * h, ys, p);
             }
             double drift_inc = 0.0;  // stochastic.rs:107-110
 #pragma unroll
             for (int i = 0; i < S; i++) {
-                if (Tab::b(i) != 0.0) drift_inc = __dadd_rn(drift_inc, (Tab::b(i) * h) * k[i]);
+                if (Tab::b(i) != 0.0) drift_inc = __dadd_rn(drift_inc, (Tab::bv(i) * h) * k[i]);
             }
             const double g = Sde::diffusion(t, y, p);  // stochastic.rs:113-115
             // noise(h, dw), stochastic.rs:118-119

@@ -123,7 +123,7 @@ typedef struct deb_ode_problem {
     int32_t n_params;     /* must equal the system's parameter count */
     int64_t n_traj;
     const double* y0;     /* [n_traj][dim] */
-    const double* params; /* [n_traj][n_params], or [n_params] shared by all when params_shared != 0 */
+    const double* params; /* [n_traj][n_params] in `memspace`; or, when params_shared != 0, ONE set [n_params] in HOST memory */
     int32_t params_shared;
     int32_t n_eval;       /* number of t_eval points (0 = none) */
     const double* t_eval; /* HOST memory always.  Sorted like TEvalSolout::new (t_eval.rs:154-165) */
@@ -141,10 +141,10 @@ typedef struct deb_sde_problem {
     int32_t dim;          /* 1 */
     int32_t n_params;
     int64_t n_traj;
-    const double* y0;     /* [n_traj], or one value shared by all when y0_shared != 0 */
+    const double* y0;     /* [n_traj] in `memspace`; or, when y0_shared != 0, ONE value in HOST memory */
     int32_t y0_shared;
     int32_t params_shared;
-    const double* params;
+    const double* params; /* [n_traj][n_params] in `memspace`; or ONE set in HOST memory when params_shared != 0 */
     int32_t n_eval;
     const double* t_eval; /* HOST */
     double t0, tf;
