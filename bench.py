@@ -171,17 +171,9 @@ def main():
 
     # ---- shard: trajectories split evenly, rank r takes i = r, r+world, ... (interleaved)
     n_total = args.n_traj
-    idx = np.arange(rank, n_total, world)
+    idx = deb.shard_indices(n_total, rank, world)
     n = idx.size
-    # generate only this shard's initial conditions (u_k for k = 3i..3i+2)
-    k = (idx[:, None] * 3 + np.arange(3)[None, :]).reshape(-1).astype(np.uint64) + np.uint64(1)
-    with np.errstate(over="ignore"):
-        z = np.uint64(2026) + k * np.uint64(0x9E3779B97F4A7C15)
-        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
-        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
-        z = z ^ (z >> np.uint64(31))
-    y0_host = (1.0 + ((z >> np.uint64(11)).astype(np.float64) * 2.0 ** -53 - 0.5)).reshape(n, 3)
-    del k, z
+    y0_host = deb.perturbed_ensemble([1.0, 1.0, 1.0], idx, seed=2026)  # only this shard's initial conditions
     params_host = np.array([10.0, 28.0, 8.0 / 3.0])
     t_eval = np.arange(1.0, N_EVAL + 1.0)
 
@@ -225,9 +217,7 @@ def main():
                                     local_rank, deb.DEB_MEM_DEVICE, stream.cuda_stream)  # 2 launches
         if rc != 0:
             raise RuntimeError(lib.deb_last_error().decode())
-        if dist is not None:  # the only cross-GPU traffic: 4.8 KB of sums + counts
-            dist.all_reduce(d_sums)
-            dist.all_reduce(d_counts)
+        deb.allreduce_ensemble_stats(d_sums, d_counts, dist)  # the only cross-GPU traffic: 4.8 KB of sums + counts
         if timed:
             kernel_events.append((e0, e1))
 

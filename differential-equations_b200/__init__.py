@@ -42,7 +42,7 @@ LIB_PATH = os.path.join(_HERE, "libdeb200.so")
 DEB_EULER, DEB_MIDPOINT, DEB_HEUN, DEB_RALSTON, DEB_SSP_RK3, DEB_RK4, DEB_THREE_EIGHTHS = range(7)
 DEB_DOPRI5, DEB_DOP853 = 16, 17
 (DEB_SYS_EXPONENTIAL, DEB_SYS_LINEAR, DEB_SYS_HARMONIC, DEB_SYS_LOGISTIC, DEB_SYS_VAN_DER_POL, DEB_SYS_LORENZ,
- DEB_SYS_BRUSSELATOR) = range(7)
+ DEB_SYS_BRUSSELATOR, DEB_SYS_ROBERTSON) = range(8)
 DEB_SDE_OU, DEB_SDE_GBM = 0, 1
 DEB_STATUS_COMPLETE, DEB_STATUS_MAX_STEPS, DEB_STATUS_STEP_SIZE, DEB_STATUS_STIFFNESS, DEB_STATUS_BAD_INPUT = range(5)
 DEB_MEM_HOST, DEB_MEM_DEVICE = 0, 1
@@ -207,6 +207,7 @@ def LogisticEquation(k, m): return OdeSystem(DEB_SYS_LOGISTIC, 1, _params(k, m))
 def VanDerPolOscillator(mu): return OdeSystem(DEB_SYS_VAN_DER_POL, 2, _params(mu))         # :66-78
 def LorenzSystem(sigma, rho, beta): return OdeSystem(DEB_SYS_LORENZ, 3, _params(sigma, rho, beta))  # :85-101
 def BrusselatorSystem(a, b): return OdeSystem(DEB_SYS_BRUSSELATOR, 2, _params(a, b))       # :106-120
+def RobertsonProblem(): return OdeSystem(DEB_SYS_ROBERTSON, 3, np.zeros(0))                  # :161-173
 
 
 @dataclass
@@ -519,3 +520,49 @@ def heat_rhs(u, lo, hi, alpha, bc_lower=("dirichlet", 0.0), bc_upper=("dirichlet
     du = np.empty_like(u)
     _check(lib, lib.deb_heat_rhs(C.byref(P), u.ctypes.data, du.ctypes.data), "deb_heat_rhs")
     return du
+
+
+# ---------------------------------------------------------------------------------------------- ensemble front end
+def splitmix64_uniform(seed: int, index: np.ndarray) -> np.ndarray:
+    """u_k = (splitmix64(seed + k*golden) >> 11) * 2^-53 - 0.5 for the (1-based) stream positions in `index`:
+    counter-based, so any shard of an ensemble can be generated without the rest."""
+    k = np.asarray(index, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed) + k * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(11)).astype(np.float64) * 2.0 ** -53 - 0.5
+
+
+def perturbed_ensemble(center, traj_index: np.ndarray, seed: int = 2026) -> np.ndarray:
+    """Initial states y0_i = center + (u_{d*i}, ..., u_{d*i+d-1}) for the global trajectory numbers `traj_index`
+    (perturbation uniform in [-0.5, 0.5)^d): the ensemble of configs C1/C2."""
+    center = np.asarray(center, dtype=np.float64)
+    d = center.size
+    idx = np.asarray(traj_index, dtype=np.uint64)
+    k = (idx[:, None] * np.uint64(d) + np.arange(d, dtype=np.uint64)[None, :]).reshape(-1) + np.uint64(1)
+    return center[None, :] + splitmix64_uniform(seed, k).reshape(idx.size, d)
+
+
+def shard_indices(n_total: int, rank: int, world: int) -> np.ndarray:
+    """Global trajectory numbers owned by `rank`: interleaved (i mod world == rank), so that a sorted parameter sweep
+    (config C3) is balanced across GPUs; trajectories are independent, there is no exchange during integration."""
+    return np.arange(rank, n_total, world, dtype=np.int64)
+
+
+def allreduce_ensemble_stats(sums, counts, dist=None):
+    """The only cross-GPU step: sum the per-t_eval {sum y, sum y^2} and counts over ranks (NCCL on GPUs, gloo in the
+    CPU tests).  `sums`/`counts` are torch tensors, reduced in place; a no-op for a single process."""
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(sums)
+        dist.all_reduce(counts)
+    return sums, counts
+
+
+def stats_to_mean_var(sums, counts):
+    """mean and (population) variance per t_eval row and component from the reduced sums."""
+    s = np.asarray(sums, dtype=np.float64)
+    c = np.maximum(np.asarray(counts, dtype=np.float64), 1.0)[:, None]
+    mean = s[:, :, 0] / c
+    return mean, s[:, :, 1] / c - mean * mean

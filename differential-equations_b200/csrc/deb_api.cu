@@ -145,6 +145,7 @@ ode_launch_fn pick_ode(int system, int method, int* dim, int* np) {
         DEB_SYS_CASE(DEB_SYS_VAN_DER_POL, SysVanDerPol)
         DEB_SYS_CASE(DEB_SYS_LORENZ, SysLorenz)
         DEB_SYS_CASE(DEB_SYS_BRUSSELATOR, SysBrusselator)
+        DEB_SYS_CASE(DEB_SYS_ROBERTSON, SysRobertson)
     }
 #undef DEB_SYS_CASE
     *dim = -1;

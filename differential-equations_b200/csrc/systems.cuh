@@ -54,6 +54,16 @@ struct SysBrusselator {  // systems.rs:112-120
     }
 };
 
+struct SysRobertson {  // systems.rs:161-173 (stiff; the reference tests DOP853/DOPRI5 on it with loose tolerances)
+    static constexpr int DIM = 3, NP = 0;
+    __device__ __forceinline__ static void rhs(double, const double* y, double* d, const double*) {
+        const double y1 = y[0], y2 = y[1], y3 = y[2];
+        d[0] = -0.04 * y1 + 1.0e4 * y2 * y3;
+        d[1] = 0.04 * y1 - 1.0e4 * y2 * y3 - 3.0e7 * y2 * y2;
+        d[2] = 3.0e7 * y2 * y2;
+    }
+};
+
 // Scalar SDEs (`SDE::drift` / `SDE::diffusion`, /root/reference/src/sde/sde.rs:16-52)
 struct SdeOU {  // examples/sde/03_ornstein_uhlenbeck/main.rs:42-49
     static constexpr int NP = 3;

@@ -80,7 +80,8 @@ typedef enum deb_system {
     DEB_SYS_LOGISTIC = 3,    /* dim 1, params {k,m}:       y' = k*y*(1 - y/m)        systems.rs:55-59  */
     DEB_SYS_VAN_DER_POL = 4, /* dim 2, params {mu}:        systems.rs:70-78                             */
     DEB_SYS_LORENZ = 5,      /* dim 3, params {sigma,rho,beta}: systems.rs:91-101                       */
-    DEB_SYS_BRUSSELATOR = 6  /* dim 2, params {a,b}:       systems.rs:112-120                           */
+    DEB_SYS_BRUSSELATOR = 6, /* dim 2, params {a,b}:       systems.rs:112-120                           */
+    DEB_SYS_ROBERTSON = 7    /* dim 3, no params (stiff):  systems.rs:161-173                           */
 } deb_system;
 
 /* Built-in SDEs (`SDE::drift/diffusion`, src/sde/sde.rs:16-52), scalar state. */

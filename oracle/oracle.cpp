@@ -69,6 +69,12 @@ void sys_brusselator(double, const double* y, double* d, const double* p) {  // 
     d[0] = p[0] + y1 * y1 * y2 - (p[1] + 1.0) * y1;
     d[1] = p[1] * y1 - y1 * y1 * y2;
 }
+void sys_robertson(double, const double* y, double* d, const double*) {  // :161-173
+    double y1 = y[0], y2 = y[1], y3 = y[2];
+    d[0] = -0.04 * y1 + 1.0e4 * y2 * y3;
+    d[1] = 0.04 * y1 - 1.0e4 * y2 * y3 - 3.0e7 * y2 * y2;
+    d[2] = 3.0e7 * y2 * y2;
+}
 struct SysInfo { rhs_fn f; int dim, np; };
 bool get_system(int id, SysInfo* s) {
     switch (id) {
@@ -79,6 +85,7 @@ bool get_system(int id, SysInfo* s) {
         case DEB_SYS_VAN_DER_POL: *s = {sys_vdp, 2, 1}; return true;
         case DEB_SYS_LORENZ: *s = {sys_lorenz, 3, 3}; return true;
         case DEB_SYS_BRUSSELATOR: *s = {sys_brusselator, 2, 2}; return true;
+        case DEB_SYS_ROBERTSON: *s = {sys_robertson, 3, 0}; return true;
     }
     return false;
 }

@@ -64,19 +64,13 @@ def oracle_heat(u0, lo, hi, alpha, method, t0, tf, bc_lower=("dirichlet", 0.0), 
 
 
 def splitmix64_uniform(seed: int, count: int) -> np.ndarray:
-    """u_k = (splitmix64(seed, k) >> 11) * 2^-53 - 0.5, the ensemble perturbation generator of SURVEY.md 8(d)."""
-    k = np.arange(1, count + 1, dtype=np.uint64)
-    with np.errstate(over="ignore"):
-        z = np.uint64(seed) + k * np.uint64(0x9E3779B97F4A7C15)
-        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
-        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
-        z = z ^ (z >> np.uint64(31))
-    return (z >> np.uint64(11)).astype(np.float64) * 2.0 ** -53 - 0.5
+    """u_k for k = 1..count (the package's counter-based generator)."""
+    return deb.splitmix64_uniform(seed, np.arange(1, count + 1, dtype=np.uint64))
 
 
 def lorenz_ensemble_y0(n: int, seed: int = 2026) -> np.ndarray:
     """y0_i = (1,1,1) + (u_{3i}, u_{3i+1}, u_{3i+2})  (config C1/C2)."""
-    return (1.0 + splitmix64_uniform(seed, 3 * n)).reshape(n, 3)
+    return deb.perturbed_ensemble([1.0, 1.0, 1.0], np.arange(n), seed)
 
 
 def oracle_heat_rhs(u, lo, hi, alpha, bc_lower=("dirichlet", 0.0), bc_upper=("dirichlet", 0.0)):

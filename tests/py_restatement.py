@@ -1,0 +1,394 @@
+"""A second, independent restatement of the reference's Dormand-Prince / fixed-step / Euler-Maruyama loops in
+plain Python floats (IEEE doubles, math.pow == libm pow), written from the Rust sources, NOT from oracle/oracle.cpp.
+
+TEST INFRASTRUCTURE.  Pure-Python loops: only for small cases.  Its purpose is to pin the C++ oracle: two
+independently written restatements must agree bit for bit (tests/test_oracle_golden.py), and both must reproduce the
+survey's probe values.
+
+Follows /root/reference/src/methods/erk/dormandprince/ordinary.rs:16-337, src/methods/h_init.rs:45-135,
+src/ode/solve_ivp.rs:139-277, src/solout/t_eval.rs:87-171, src/methods/erk/fixed/ordinary.rs:16-221,
+src/interpolate.rs:40-74.
+"""
+import math
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def load_tableaux():
+    """Parse the generated coefficient header (hex-float brace lists)."""
+    txt = open(os.path.join(ROOT, "oracle", "erk_tableau_data.h")).read().replace("\\\n", " ")
+    out = {}
+    for m in re.finditer(r"#define DEB_(\w+?)_(C|A|B|BH|ER|BI) (.*)", txt):
+        name, kind, body = m.group(1), m.group(2), m.group(3)
+        rows = re.findall(r"\{([^{}]*)\}", body)
+        vals = [[float.fromhex(x.strip()) for x in r.split(",")] for r in rows]
+        out.setdefault(name, {})[kind] = vals[0] if kind in ("C", "B", "BH", "ER") else vals
+    return out
+
+
+TAB = load_tableaux()
+EPS10 = 2.220446049250313e-16 * 10.0
+
+
+def signum(x):
+    return math.copysign(1.0, x)
+
+
+def rmax(a, b):  # f64::max ignores NaN
+    if a != a:
+        return b
+    if b != b:
+        return a
+    return max(a, b)
+
+
+def rmin(a, b):
+    if a != a:
+        return b
+    if b != b:
+        return a
+    return min(a, b)
+
+
+def powf(x, y):
+    if x == 0.0:
+        return math.inf if y < 0 else 0.0
+    try:
+        return math.pow(x, y)
+    except (OverflowError, ZeroDivisionError):
+        return math.inf
+    except ValueError:
+        return math.nan
+
+
+def h_init(f, t0, tf, y0, order, rtol, atol, h_min, h_max):
+    posneg = signum(tf - t0)
+    n = len(y0)
+    f0 = f(t0, y0)
+    dnf = dny = 0.0
+    sk = []
+    for i in range(n):
+        s = atol + rtol * abs(y0[i])
+        sk.append(s)
+        a = f0[i] / s
+        dnf += a * a
+        b = y0[i] / s
+        dny += b * b
+    h = 1.0e-6 if (dnf <= 1.0e-10 or dny <= 1.0e-10) else math.sqrt(dny / dnf) * 0.01
+    h = rmin(h, h_max)
+    h *= posneg
+    y1 = [y0[i] + h * f0[i] for i in range(n)]
+    f1 = f(t0 + h, y1)
+    der2 = 0.0
+    for i in range(n):
+        d = (f1[i] - f0[i]) / sk[i]
+        der2 += d * d
+    der2 = math.sqrt(der2) / abs(h)
+    der12 = rmax(math.sqrt(dnf), der2)
+    if der12 <= 1.0e-15:
+        h1 = abs(h) * rmax(1.0e-3, 1.0e-6)
+    else:
+        h1 = powf(0.01 / der12, 1.0 / float(order))
+    interval = abs(tf - t0)
+    h = rmin(rmax(rmin(rmin(abs(h) * 100.0, h1), h_max), h_min), interval)
+    return h * posneg
+
+
+def solve_dp(f, method, t0, tf, y0, rtol=1e-6, atol=1e-6, t_eval=(), h0=0.0, h_min=0.0, h_max=math.inf, max_steps=10000,
+             safety=0.9, min_scale=0.2, max_scale=10.0):
+    """Returns dict(status, t, y, accepted, rejected, evals, rows=[(t, y)])."""
+    T = TAB["DOPRI5" if method == "dopri5" else "DOP853"]
+    O, S, I = (5, 7, 7) if method == "dopri5" else (8, 12, 16)
+    c, A, b, er, bi = T["C"], T["A"], T["B"], T["ER"], T["BI"]
+    bh = T.get("BH")
+    n = len(y0)
+    evals = 0
+    if tf == t0:
+        return dict(status="BadInput")
+    dirn = signum(tf - t0)
+    if h0 == 0.0:
+        h0 = h_init(f, t0, tf, y0, O, rtol, atol, h_min, h_max)
+        evals += 2
+    if (signum(h0) != dirn or h_min < 0 or h_max < 0 or h_min > h_max or abs(h0) < h_min or abs(h0) > h_max
+            or abs(h0) > abs(tf - t0) or h0 == 0.0):
+        return dict(status="BadInput")
+    h, t, y = h0, t0, list(y0)
+    k = [[0.0] * n for _ in range(I)]
+    cont = [[0.0] * n for _ in range(O)]
+    k[0] = f(t, y)
+    evals += 1
+    t_prev, h_prev = t, 0.0
+    steps = stiff = nonstiff = acc = rej = 0
+    rejected = False
+    pts = sorted(t_eval) if dirn > 0 else sorted(t_eval, reverse=True)
+    rows = []
+    state = dict(idx=0)
+
+    def interpolate(ti):
+        s = (ti - t_prev) / h_prev
+        s1 = 1.0 - s
+        ilast = O - 1
+        accv = list(cont[ilast])
+        for i in range(ilast - 1, 0, -1):
+            if i >= 4:
+                factor = s1 if (ilast - i) % 2 == 1 else s
+            else:
+                factor = s1 if i % 2 == 1 else s
+            accv = [v * factor for v in accv]
+            accv = [accv[j] + 1.0 * cont[i][j] for j in range(n)]
+        return [cont[0][j] + s * accv[j] for j in range(n)]
+
+    def solout(t_curr, tp, y_curr):
+        idx = state["idx"]
+        while idx < len(pts):
+            te = pts[idx]
+            if dirn > 0:
+                in_range = (te == tp and idx == 0) or (te > tp and te <= t_curr)
+            else:
+                in_range = (te == tp and idx == 0) or (te < tp and te >= t_curr)
+            if in_range:
+                rows.append((te, list(y_curr) if te == t_curr else interpolate(te)))
+                idx += 1
+            else:
+                if (dirn > 0 and te > t_curr) or (dirn < 0 and te < t_curr):
+                    break
+                idx += 1
+        state["idx"] = idx
+
+    solout(t, t_prev, y)
+    status = "Complete"
+    while True:
+        if (t + h - tf) * dirn > 0.0:
+            h_new = tf - t
+            if abs(h_new) < EPS10:
+                break
+            h = h_new
+        if abs(h) < abs(h_prev) * 1e-14:
+            status = "StepSize"
+            break
+        if steps >= max_steps:
+            status = "MaxSteps"
+            break
+        steps += 1
+        ys = [0.0] * n
+        for i in range(1, S):
+            ys = list(y)
+            for j in range(i):
+                ah = A[i][j] * h
+                ys = [ys[q] + ah * k[j][q] for q in range(n)]
+            k[i] = f(t + c[i] * h, ys)
+        ysti = list(ys)
+        yseg = [0.0] * n
+        for i in range(S):
+            yseg = [yseg[q] + b[i] * k[i][q] for q in range(n)]
+        y_new = [y[q] + h * yseg[q] for q in range(n)]
+        t_new = t + h
+        step_evals = S - 1
+        es = [0.0] * n
+        for j in range(S):
+            es = [es[q] + er[j] * k[j][q] for q in range(n)]
+
+        def enorm(e):
+            tot = 0.0
+            for q in range(n):
+                sk = atol + rtol * rmax(abs(y[q]), abs(y_new[q]))
+                v = e[q] / sk
+                tot += v * v
+            return tot
+        err = enorm(es)
+        err2 = 0.0
+        if bh is not None:
+            e2 = list(yseg)
+            for j in range(S):
+                e2 = [e2[q] + (-bh[j]) * k[j][q] for q in range(n)]
+            err2 = enorm(e2)
+        deno = err + 0.01 * err2
+        if deno <= 0.0:
+            deno = 1.0
+        err = abs(h) * err * math.sqrt(1.0 / (deno * float(n)))
+        scale = safety * powf(err, -(1.0 / float(O)))
+        scale = rmin(rmax(scale, min_scale), max_scale)
+        if err <= 1.0:
+            dydt = f(t_new, y_new)
+            step_evals += 1
+            if steps % 100 == 0:
+                stdnum = 0.0
+                stden = 0.0
+                for q in range(n):
+                    d = yseg[q] - k[S - 1][q]
+                    stdnum += d * d
+                for q in range(n):
+                    d = dydt[q] - ysti[q]
+                    stden += d * d
+                if stden > 0.0:
+                    if h * math.sqrt(stdnum / stden) > 6.1:
+                        nonstiff = 0
+                        stiff += 1
+                        if stiff == 15:
+                            status = "Stiffness"
+                            break
+                else:
+                    nonstiff += 1
+                    if nonstiff == 6:
+                        stiff = 0
+            cont[0] = list(y)
+            ydiff = [y_new[q] + (-1.0) * y[q] for q in range(n)]
+            cont[1] = list(ydiff)
+            bspl = [0.0 + h * k[0][q] for q in range(n)]
+            bspl = [bspl[q] + (-1.0) * ydiff[q] for q in range(n)]
+            cont[2] = list(bspl)
+            c3 = [ydiff[q] + (-h) * dydt[q] for q in range(n)]
+            c3 = [c3[q] + (-1.0) * bspl[q] for q in range(n)]
+            cont[3] = c3
+            if I > S:
+                k[S] = list(dydt)
+                for i in range(S + 1, I):
+                    ys2 = list(y)
+                    for j in range(i):
+                        ah = A[i][j] * h
+                        ys2 = [ys2[q] + ah * k[j][q] for q in range(n)]
+                    k[i] = f(t + c[i] * h, ys2)
+                    step_evals += 1
+            for i in range(4, O):
+                ci = [0.0] * n
+                for j in range(I):
+                    ci = [ci[q] + bi[i][j] * k[j][q] for q in range(n)]
+                cont[i] = [v * h for v in ci]
+            t_prev, h_prev = t, h
+            t, y = t_new, y_new
+            k[0] = list(dydt)
+            if rejected:
+                rejected = False
+                scale = rmin(scale, 1.0)
+            accepted = True
+        else:
+            rejected = True
+            accepted = False
+        h *= scale
+        sg = signum(h)
+        if abs(h) < h_min:
+            h = sg * h_min
+        elif abs(h) > h_max:
+            h = sg * h_max
+        evals += step_evals
+        if not accepted:
+            rej += 1
+            continue
+        acc += 1
+        solout(t, t_prev, y)
+        if abs(tf - t) <= EPS10:
+            break
+    return dict(status=status, t=t, y=y, accepted=acc, rejected=rej, evals=evals, rows=rows)
+
+
+def solve_fixed(f, method, h0, t0, tf, y0, t_eval=(), max_steps=10000):
+    T = TAB[method.upper()]
+    c, A, b = T["C"], T["A"], T["B"]
+    S = len(b)
+    n = len(y0)
+    if tf == t0:
+        return dict(status="BadInput")
+    dirn = signum(tf - t0)
+    if h0 == 0.0:
+        h0 = abs(tf - t0) / 100.0
+    if signum(h0) != dirn or abs(h0) > abs(tf - t0):
+        return dict(status="BadInput")
+    h, t, y = h0, t0, list(y0)
+    dydt = f(t, y)
+    evals = 1
+    t_prev, y_prev, d_prev = t, list(y), list(dydt)
+    pts = sorted(t_eval) if dirn > 0 else sorted(t_eval, reverse=True)
+    rows = []
+    state = dict(idx=0)
+
+    def interpolate(ti):
+        hh = t - t_prev
+        s = (ti - t_prev) / hh
+        s2 = s * s
+        s3 = s2 * s
+        h00 = 2.0 * s3 - 3.0 * s2 + 1.0
+        h10 = s3 - 2.0 * s2 + s
+        h01 = -2.0 * s3 + 3.0 * s2
+        h11 = s3 - s2
+        out = [0.0] * n
+        out = [out[q] + h00 * y_prev[q] for q in range(n)]
+        out = [out[q] + (h10 * hh) * d_prev[q] for q in range(n)]
+        out = [out[q] + h01 * y[q] for q in range(n)]
+        out = [out[q] + (h11 * hh) * dydt[q] for q in range(n)]
+        return out
+
+    def solout(t_curr, tp, y_curr):
+        idx = state["idx"]
+        while idx < len(pts):
+            te = pts[idx]
+            if dirn > 0:
+                in_range = (te == tp and idx == 0) or (te > tp and te <= t_curr)
+            else:
+                in_range = (te == tp and idx == 0) or (te < tp and te >= t_curr)
+            if in_range:
+                rows.append((te, list(y_curr) if te == t_curr else interpolate(te)))
+                idx += 1
+            else:
+                if (dirn > 0 and te > t_curr) or (dirn < 0 and te < t_curr):
+                    break
+                idx += 1
+        state["idx"] = idx
+
+    solout(t, t_prev, y)
+    steps = 0
+    status = "Complete"
+    while True:
+        if (t + h - tf) * dirn > 0.0:
+            h_new = tf - t
+            if abs(h_new) < EPS10:
+                break
+            h = h_new
+        if steps >= max_steps:
+            status = "MaxSteps"
+            break
+        steps += 1
+        k = [list(dydt)] + [None] * (S - 1)
+        for i in range(1, S):
+            ys = list(y)
+            for j in range(i):
+                ah = A[i][j] * h
+                ys = [ys[q] + ah * k[j][q] for q in range(n)]
+            k[i] = f(t + c[i] * h, ys)
+        t_prev, y_prev, d_prev = t, list(y), list(k[0])
+        yn = list(y)
+        for i in range(S):
+            bh_ = b[i] * h
+            yn = [yn[q] + bh_ * k[i][q] for q in range(n)]
+        t += h
+        y = yn
+        dydt = f(t, y)
+        evals += S
+        solout(t, t_prev, y)
+        if abs(tf - t) <= EPS10:
+            break
+    return dict(status=status, t=t, y=y, accepted=steps, rejected=0, evals=evals, rows=rows)
+
+
+# right-hand sides, written from /root/reference/tests/ode/systems.rs
+def lorenz(sigma, rho, beta):
+    def f(t, y):
+        x, yv, z = y
+        return [sigma * (yv - x), x * (rho - z) - yv, x * yv - beta * z]
+    return f
+
+
+def van_der_pol(mu):
+    def f(t, y):
+        y1, y2 = y
+        return [y2, mu * (1.0 - y1 * y1) * y2 - y1]
+    return f
+
+
+def exponential(k):
+    return lambda t, y: [k * y[0]]
+
+
+def harmonic(k):
+    return lambda t, y: [y[1], -k * y[0]]

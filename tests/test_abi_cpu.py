@@ -1,0 +1,146 @@
+"""CPU tests (no GPU): the C-ABI library loads, exports every symbol include/deb_ensemble.h declares, agrees with the
+ctypes mirrors on struct layout, validates arguments, and -- without a CUDA device -- refuses to compute instead of
+falling back to a CPU path."""
+import ctypes as C
+import importlib
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+deb = importlib.import_module("differential-equations_b200")
+E = deb.ExplicitRungeKutta
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(deb.LIB_PATH):
+        sys.path.insert(0, ROOT)
+        import __graft_entry__ as g
+        g.build()
+    return deb.load_library()
+
+
+def header_functions():
+    txt = open(os.path.join(ROOT, "include", "deb_ensemble.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(deb_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    names = header_functions()
+    assert len(names) >= 15
+    assert sorted(names) == sorted(deb.ABI_SYMBOLS), "ABI_SYMBOLS must list exactly what the header declares"
+    for n in names:
+        getattr(lib, n)  # AttributeError if the symbol is not exported
+    assert lib.deb_abi_version() == deb.DEB_ABI_VERSION
+    # the symbols are plain C (no mangling) and nothing else leaks a torch/C++ type in its name
+    out = subprocess.run(["nm", "-D", "--defined-only", deb.LIB_PATH], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    assert set(names) <= exported
+
+
+def test_struct_layout_matches_header(lib):
+    src = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "deb_ensemble.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu\n", sizeof(deb_erk_options), sizeof(deb_ode_problem), sizeof(deb_sde_problem), sizeof(deb_result), sizeof(deb_heat_problem));
+  printf("%zu %zu %zu %zu\n", offsetof(deb_ode_problem, opt), offsetof(deb_ode_problem, device), offsetof(deb_result, n_rows), offsetof(deb_heat_problem, status));
+  printf("%zu %zu\n", offsetof(deb_sde_problem, seed), offsetof(deb_sde_problem, device));
+  return 0; }'''
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "s.c"), "w").write(src)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "s.c"), "-o", os.path.join(d, "s")], check=True)
+        out = subprocess.run([os.path.join(d, "s")], capture_output=True, text=True, check=True).stdout.split()
+    got = [int(x) for x in out]
+    want = [C.sizeof(deb.ErkOptions), C.sizeof(deb.OdeProblem), C.sizeof(deb.SdeProblem), C.sizeof(deb.Result), C.sizeof(deb.HeatProblem),
+            deb.OdeProblem.opt.offset, deb.OdeProblem.device.offset, deb.Result.n_rows.offset, deb.HeatProblem.status.offset,
+            deb.SdeProblem.seed.offset, deb.SdeProblem.device.offset]
+    assert got == want
+
+
+def test_defaults_match_reference(lib):
+    """erk/mod.rs:135-144."""
+    o = deb.ErkOptions()
+    lib.deb_erk_options_default(C.byref(o))
+    assert (o.rtol, o.atol, o.h0, o.h_min, o.max_steps, o.safety_factor, o.min_scale, o.max_scale) == (1e-6, 1e-6, 0.0, 0.0, 10000, 0.9, 0.2, 10.0)
+    assert o.h_max == float("inf") and not o.rtol_vec and not o.atol_vec
+    m = E.dopri5()
+    assert (m._rtol, m._atol, m._max_steps, m._max_rejects, m._safety_factor, m._min_scale, m._max_scale) == (1e-6, 1e-6, 10000, 100, 0.9, 0.2, 10.0)
+
+
+def test_argument_validation_needs_no_device(lib):
+    ivp = deb.EnsembleIVP.ode(deb.LorenzSystem(10.0, 28.0, 8.0 / 3.0), 0.0, 1.0, np.ones((4, 3))).t_eval([0.5]).method(E.dopri5())
+    P, R, arrs, ts, keep = ivp.build_problem()
+    P.struct_size = 8
+    assert lib.deb_solve_ode(C.byref(P), C.byref(R)) == deb.DEB_ERR_BAD_ARG and b"struct_size" in lib.deb_last_error()
+    P, R, arrs, ts, keep = ivp.build_problem()
+    P.system = 99
+    assert lib.deb_solve_ode(C.byref(P), C.byref(R)) == deb.DEB_ERR_BAD_ARG
+    P, R, arrs, ts, keep = ivp.build_problem()
+    P.method = 9
+    assert lib.deb_solve_ode(C.byref(P), C.byref(R)) == deb.DEB_ERR_UNSUPPORTED
+    P, R, arrs, ts, keep = ivp.build_problem()
+    P.dim = 2
+    assert lib.deb_solve_ode(C.byref(P), C.byref(R)) == deb.DEB_ERR_BAD_ARG
+    P, R, arrs, ts, keep = ivp.build_problem()
+    P.y0 = None
+    assert lib.deb_solve_ode(C.byref(P), C.byref(R)) == deb.DEB_ERR_BAD_ARG
+    bad = deb.EnsembleIVP.ode(deb.LorenzSystem(10.0, 28.0, 8.0 / 3.0), 0.0, 1.0, np.ones((4, 3))).t_eval([0.5, float("nan")]).method(E.dopri5())
+    P, R, arrs, ts, keep = bad.build_problem()
+    assert lib.deb_solve_ode(C.byref(P), C.byref(R)) == deb.DEB_ERR_BAD_ARG and b"NaN" in lib.deb_last_error()
+    assert lib.deb_solve_ode(None, None) == deb.DEB_ERR_BAD_ARG
+    with pytest.raises(ValueError):
+        deb.EnsembleIVP.ode(deb.LorenzSystem(10.0, 28.0, 8.0 / 3.0), 0.0, 1.0, np.ones((4, 2)))
+    with pytest.raises(ValueError):
+        deb.EnsembleIVP.ode(deb.VanDerPolOscillator(np.ones(3)), 0.0, 1.0, np.ones((4, 2))).method(E.dopri5()).build_problem()
+
+
+def test_empty_ensemble_and_t_eval_plan_without_device(lib):
+    """n_traj == 0 returns OK with the row plan filled in (no kernel, no device)."""
+    ivp = deb.EnsembleIVP.ode(deb.HarmonicOscillator(1.0), 0.0, 10.0, np.zeros((0, 2))).t_eval([3.0, 0.0, 11.0, -1.0, 0.5, 10.0, 0.5]).method(E.dopri5())
+    s = ivp.solve(lib)
+    assert len(s) == 0 and s.t_rows.tolist() == [0.5, 0.5, 3.0, 10.0, 11.0]
+    assert s.t_rows.tolist() == deb._plan_rows(ivp._t_eval, 0.0, 10.0).tolist()
+    back = deb.EnsembleIVP.ode(deb.HarmonicOscillator(1.0), 10.0, 0.0, np.zeros((0, 2))).t_eval([3.0, 10.0, 11.0, -1.0, 0.5]).method(E.dopri5())
+    # sorted descending: 11 lies before t0 and is skipped; 10.0 == t0 is then NOT the first point any more, so the
+    # reference never emits it (t_eval.rs:100-129)
+    assert back.solve(lib).t_rows.tolist() == [3.0, 0.5, -1.0]
+
+
+def test_no_cpu_fallback_without_a_device(lib):
+    """On a box without a GPU every compute entry point must fail loudly with DEB_ERR_NO_DEVICE."""
+    if lib.deb_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    ivp = deb.EnsembleIVP.ode(deb.LorenzSystem(10.0, 28.0, 8.0 / 3.0), 0.0, 1.0, np.ones((4, 3))).method(E.dopri5())
+    P, R, arrs, ts, keep = ivp.build_problem()
+    assert lib.deb_solve_ode(C.byref(P), C.byref(R)) == deb.DEB_ERR_NO_DEVICE
+    assert b"no CPU fallback" in lib.deb_last_error()
+    assert (arrs["status"] == -1).all()  # nothing was computed
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        ivp.solve(lib)
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        deb.EnsembleIVP.sde(deb.OrnsteinUhlenbeck(0.5, 1.0, 0.3), 0.0, 1.0, np.ones(4)).method(E.euler(0.01)).solve(lib)
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        deb.solve_heat_mol(np.ones(8), 0.0, 1.0, 0.1, E.rk4(1e-3), 0.0, 0.01, lib=lib)
+    v = C.c_double(0)
+    assert lib.deb_fp64_issue_peak(0, 0, C.byref(v), None) == deb.DEB_ERR_NO_DEVICE
+
+
+def test_product_never_references_the_oracle():
+    """The product path must not import, link or call anything under oracle/."""
+    pkg = os.path.join(ROOT, "differential-equations_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".rs", ".toml")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "liboracle" not in txt and "oracle_binding" not in txt and "orc_" not in txt and "oracle/" not in txt.replace("the oracle keeps its own copy: oracle/", ""), os.path.join(dirpath, f)
+    out = subprocess.run(["ldd", deb.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out

@@ -1,0 +1,126 @@
+"""CPU tests (no GPU) of host-side logic: tableau data, the Philox stream definition, the t_eval row plan, the
+splitmix ensemble generator, and the builder mirror."""
+import ctypes as C
+import importlib
+import math
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+import py_restatement as pr
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+deb = importlib.import_module("differential-equations_b200")
+E = deb.ExplicitRungeKutta
+
+
+def test_tableau_data_is_what_the_generator_extracts_from_the_reference():
+    if not os.path.isdir("/root/reference/src/tableau"):
+        pytest.skip("reference tree not present on this box")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_tableau.py")], capture_output=True, text=True, check=True).stdout
+    assert out == open(os.path.join(ROOT, "differential-equations_b200", "csrc", "erk_tableau_data.h")).read()
+    assert out == open(os.path.join(ROOT, "oracle", "erk_tableau_data.h")).read()
+
+
+def test_tableau_consistency_conditions():
+    """Row sums c_i = sum_j a_ij and sum b_i = 1 (to the precision of the reference's literals), DOPRI5 FSAL row,
+    the misplaced DOPRI5 dense row, literal spot checks."""
+    T = pr.TAB
+    for name, stages in (("DOPRI5", 7), ("DOP853", 12), ("RK4", 4), ("THREE_EIGHTHS", 4), ("MIDPOINT", 2), ("HEUN", 2), ("RALSTON", 2), ("SSP_RK3", 3), ("EULER", 1)):
+        t = T[name]
+        assert abs(sum(t["B"]) - 1.0) < 5e-15, name
+        for i in range(stages):
+            assert abs(sum(t["A"][i]) - t["C"][i]) < 2e-15, (name, i)
+    d5 = T["DOPRI5"]
+    assert d5["A"][6][:6] == d5["B"][:6] and d5["B"][6] == 0.0           # FSAL row
+    assert d5["C"][4] == 8.0 / 9.0 and d5["A"][3][1] == -56.0 / 15.0    # quotients evaluated in f64
+    assert any(v != 0.0 for v in d5["BI"][0]) and all(v == 0.0 for r in d5["BI"][4:] for v in r)  # cont[4] == 0 quirk
+    d8 = T["DOP853"]
+    assert d8["C"][1] == 5.260015195876773e-2 and d8["B"][0] == 5.4293734116568765e-2  # the reference's truncated literals
+    assert d8["C"][12] == 0.0 and d8["C"][13] == 0.1 and d8["BH"][8] == 7.338466882816118e-1
+    assert all(v == 0.0 for r in d8["BI"][:4] for v in r) and d8["BI"][7][15] == -1.4972683625798564e2
+    # extra dense stages: c_i = sum_j a_ij too (stage 12 is the derivative at the new point, c = 1 implied)
+    for i in (13, 14, 15):
+        assert abs(sum(d8["A"][i]) - d8["C"][i]) < 2e-15
+
+
+def test_philox4x32_10_known_answers():
+    """Random123 kat_vectors for philox4x32-10 (Salmon et al., SC'11)."""
+    lib = ob.load_oracle()
+    def run(ctr, key):
+        c = (C.c_uint32 * 4)(*ctr); k = (C.c_uint32 * 2)(*key); o = (C.c_uint32 * 4)()
+        lib.orc_philox4x32_10(c, k, o)
+        return [int(x) for x in o]
+    assert run([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert run([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert run([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_wiener_increment_definition_and_statistics():
+    """dW = sqrt(h) * z with z the documented Box-Muller mapping of the Philox words; regenerate in numpy."""
+    lib = ob.load_oracle()
+    def philox_np(pair, path, seed):
+        M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+        c = [np.uint64(pair & 0xffffffff), np.uint64(pair >> 32), np.uint64(path & 0xffffffff), np.uint64(path >> 32)]
+        k0, k1 = seed & 0xffffffff, seed >> 32
+        for _ in range(10):
+            p0, p1 = M0 * c[0], M1 * c[2]
+            c = [(p1 >> np.uint64(32)) ^ c[1] ^ np.uint64(k0), p1 & np.uint64(0xffffffff), (p0 >> np.uint64(32)) ^ c[3] ^ np.uint64(k1), p0 & np.uint64(0xffffffff)]
+            k0, k1 = (k0 + 0x9E3779B9) & 0xffffffff, (k1 + 0xBB67AE85) & 0xffffffff
+        return [int(x) for x in c]
+    seed, h = 2026, 0.01
+    for path, step in ((0, 0), (0, 1), (123456789, 6), (2 ** 33 + 5, 7), (99, 1000)):
+        w = philox_np(step >> 1, path, seed)
+        a = ((w[0] << 32) | w[1]) >> 11
+        b = ((w[2] << 32) | w[3]) >> 11
+        u1, u2 = (a + 1) * 2.0 ** -53, b * 2.0 ** -53
+        r, th = math.sqrt(-2.0 * math.log(u1)), 6.283185307179586 * u2
+        z = r * math.sin(th) if step & 1 else r * math.cos(th)
+        got = lib.orc_wiener_increment(seed, path, step, 0, 1, h)
+        assert got == math.sqrt(h) * z
+    zs = np.array([lib.orc_wiener_increment(7, p, s, 0, 1, 1.0) for p in range(200) for s in range(100)])
+    assert abs(zs.mean()) < 0.03 and abs(zs.std() - 1.0) < 0.03 and abs((zs ** 3).mean()) < 0.08
+
+
+def test_row_plan_equals_what_the_oracle_emits():
+    rng = np.random.default_rng(5)
+    for t0, tf in ((0.0, 10.0), (10.0, 0.0), (-3.0, 2.0)):
+        for _ in range(20):
+            pts = rng.choice([t0, tf, 0.5 * (t0 + tf), t0 - 1.0, tf + (tf - t0), t0 + 0.3 * (tf - t0)], size=rng.integers(1, 7)).tolist() + rng.uniform(min(t0, tf) - 2, max(t0, tf) + 2, 3).tolist()
+            ivp = deb.EnsembleIVP.ode(deb.HarmonicOscillator(1.0), t0, tf, [[1.0, 0.0]]).t_eval(pts).method(E.dopri5())
+            s = ob.oracle_solve(ivp)
+            m = int(s.n_emitted[0])
+            rows = deb._plan_rows(np.asarray(pts), t0, tf)
+            inside = [r for r in rows if (r <= tf if tf > t0 else r >= tf)]
+            assert m == len(inside) and np.isfinite(s.y_eval[0, :m]).all()
+            # emitted states agree with the closed form cos/sin to the solver tolerance
+            np.testing.assert_allclose(s.y_eval[0, :m, 0], np.cos(np.array(inside) - t0), atol=2e-4)
+
+
+def test_splitmix_generator_known_values():
+    u = ob.splitmix64_uniform(2026, 6)
+    assert ((u >= -0.5) & (u < 0.5)).all()
+    # reference implementation of splitmix64 in Python ints
+    def sm(seed, k):
+        z = (seed + k * 0x9E3779B97F4A7C15) & (2 ** 64 - 1)
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & (2 ** 64 - 1)
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & (2 ** 64 - 1)
+        return z ^ (z >> 31)
+    assert u.tolist() == [(sm(2026, k) >> 11) * 2.0 ** -53 - 0.5 for k in range(1, 7)]
+    y0 = ob.lorenz_ensemble_y0(10)
+    assert y0.shape == (10, 3) and np.array_equal(y0[3], 1.0 + ob.splitmix64_uniform(2026, 12)[9:12])
+
+
+def test_builder_mirror_semantics():
+    ivp = deb.EnsembleIVP.ode(deb.VanDerPolOscillator([0.5, 1.5]), 0.0, 1.0, [[2.0, 0.0], [2.0, 0.0]]).method(E.dop853()).rtol(1e-9).atol([1e-9, 1e-10])
+    P, R, arrs, ts, keep = ivp.build_problem()
+    assert P.params_shared == 0 and P.n_params == 1 and P.dim == 2 and P.n_traj == 2 and P.method == deb.DEB_DOP853
+    assert P.opt.rtol == 1e-9 and P.opt.atol_vec[1] == 1e-10 and not P.opt.rtol_vec
+    with pytest.raises(ValueError):
+        deb.EnsembleIVP.ode(deb.VanDerPolOscillator(1.0), 0.0, 1.0, [[2.0, 0.0]]).solve()  # no method
+    with pytest.raises(ValueError):
+        deb.EnsembleIVP.ode(deb.VanDerPolOscillator(1.0), 0.0, 1.0, [[2.0, 0.0]]).method(E.dopri5().rtol([1e-3])).build_problem()

@@ -1,0 +1,176 @@
+"""CPU tests (no GPU): pin the oracle (oracle/oracle.cpp) against every golden vector the reference's own tests hold
+for the explicit-RK path, against the survey's probe values, and against a second independent restatement.
+
+The reference is a Rust crate and cannot be run here (no toolchain): at the bit level parity is "unpinned" (see
+oracle/oracle.cpp header); these tests are everything that CAN be pinned."""
+import importlib
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+import py_restatement as pr
+
+deb = importlib.import_module("differential-equations_b200")
+E = deb.ExplicitRungeKutta
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+SYSTEMS = {"exponential": lambda p: deb.ExponentialGrowth(*p), "linear": lambda p: deb.LinearEquation(*p),
+           "harmonic": lambda p: deb.HarmonicOscillator(*p), "logistic": lambda p: deb.LogisticEquation(*p),
+           "robertson": lambda p: deb.RobertsonProblem()}
+
+
+def make_method(c):
+    if c["solver"] in ("dopri5", "dop853"):
+        m = getattr(E, c["solver"])()
+    else:
+        m = getattr(E, c["solver"])(c["h"])
+    if c["rtol"] is not None:
+        m.rtol(c["rtol"])
+    if c["atol"] is not None:
+        m.atol(c["atol"])
+    return m
+
+
+def test_reference_accuracy_goldens():
+    """tests/ode/accuracy.rs: final state vs SciPy DOP853 constants with the reference's own tolerances."""
+    cases = json.load(open(os.path.join(GOLDEN, "reference_accuracy.json")))["accuracy"]
+    assert len(cases) == 42
+    for c in cases:
+        ivp = deb.EnsembleIVP.ode(SYSTEMS[c["system"]](c["params"]), c["t0"], c["tf"], [c["y0"]]).method(make_method(c))
+        s = ob.oracle_solve(ivp)[0]  # the reference test unwrap()s: every case must solve
+        err = np.abs(s.y_final - np.array(c["expected"]))
+        assert (err < c["tolerance"]).all(), (c["case"], c["solver"], s.y_final, c["expected"])
+
+
+def test_reference_accuracy_tight():
+    """The same SciPy constants are good to ~1e-8 relative: DOP853 at rtol=atol=1e-12 must reproduce them that well
+    (much tighter than the reference's 1e-3), which pins tableau constants and controller far better."""
+    cases = [c for c in json.load(open(os.path.join(GOLDEN, "reference_accuracy.json")))["accuracy"]
+             if c["solver"] == "dop853" and c["system"] != "robertson"]
+    for c in cases:
+        ivp = deb.EnsembleIVP.ode(SYSTEMS[c["system"]](c["params"]), c["t0"], c["tf"], [c["y0"]]).method(make_method(c))
+        s = ob.oracle_solve(ivp)[0]
+        np.testing.assert_allclose(s.y_final, c["expected"], rtol=2e-8, atol=1e-8)
+
+
+def test_reference_interpolation_kat():
+    """tests/ode/interpolation.rs:35-79: y' = y, t_eval([0.5, 1.0, 1.69]); every solver within 1e-3 of e^t.  Only the
+    listed points come back, in order."""
+    for m in (E.dop853(), E.dopri5(), E.rk4(0.01)):  # the explicit-RK solvers of that test
+        s = ob.oracle_solve(deb.EnsembleIVP.ode(deb.ExponentialGrowth(1.0), 0.0, 2.0, [[1.0]]).t_eval([0.5, 1.0, 1.69]).method(m))[0]
+        assert s.t.tolist() == [0.5, 1.0, 1.69]
+        np.testing.assert_allclose(s.y[:, 0], np.exp([0.5, 1.0, 1.69]), atol=1e-3)
+
+
+def test_reference_from_fn_euler_kat():
+    """tests/ode/from_fn.rs:4-18."""
+    s = ob.oracle_solve(deb.EnsembleIVP.ode(deb.ExponentialGrowth(1.0), 0.0, 1.0, [[1.0]]).method(E.euler(0.1)))[0]
+    assert abs(s.y_final[0] - 2.5937) < 1e-3
+
+
+def test_reference_error_kats():
+    """tests/ode/errors.rs:87-130: tf == t0 and h0 > interval are BadInput."""
+    for ivp in (deb.EnsembleIVP.ode(deb.ExponentialGrowth(1.0), 0.0, 0.0, [[1.0]]).method(E.dopri5()),
+                deb.EnsembleIVP.ode(deb.ExponentialGrowth(1.0), 0.0, 1.0, [[1.0]]).method(E.dopri5().h0(10.0)),
+                deb.EnsembleIVP.ode(deb.ExponentialGrowth(1.0), 0.0, 1.0, [[1.0]]).method(E.rk4(10.0)),
+                deb.EnsembleIVP.ode(deb.ExponentialGrowth(1.0), 0.0, 1.0, [[1.0]]).method(E.rk4(-0.1)),
+                deb.EnsembleIVP.ode(deb.ExponentialGrowth(1.0), 0.0, 1.0, [[1.0]]).method(E.dopri5().h_min(1.0).h_max(0.5))):
+        with pytest.raises(deb.BadInput):
+            ob.oracle_solve(ivp)[0]
+
+
+def test_reference_pde_kats():
+    """tests/pde/method_of_lines.rs:37-157."""
+    x = np.linspace(0.0, 1.0, 41)
+    s = ob.oracle_heat(np.sin(np.pi * x), 0.0, 1.0, 0.1, E.rk4(1.0e-4), 0.0, 0.02)
+    assert np.abs(s.u - math.exp(-0.1 * math.pi ** 2 * 0.02) * np.sin(np.pi * x)).max() < 5.0e-4
+    du = ob.oracle_heat_rhs([2.0, 1.0, 0.0, -0.5, -1.0], 0.0, 1.0, 1.0, ("dirichlet", 2.0), ("dirichlet", -1.0))
+    assert du[0] == 0.0 and du[-1] == 0.0
+    du = ob.oracle_heat_rhs([0.0, 1.0, 0.0, -1.0, 0.0], 0.0, 1.0, 1.0)
+    assert du[0] == 0.0 and du[4] == 0.0 and abs(du[2]) < 1e-12
+    du = ob.oracle_heat_rhs([1.0, 2.0, 2.0, 2.0, 2.0], 0.0, 1.0, 1.0, ("neumann", 0.0), ("neumann", 0.0))
+    assert abs(du[0] - (1.0 / 0.25) / 0.25) < 1e-12
+
+
+def test_survey_probe_known_answers():
+    """SURVEY.md Appendix A (an independent Python restatement run by the surveyor; tentative known-answers)."""
+    lz = deb.LorenzSystem(10.0, 28.0, 8.0 / 3.0)
+    s = ob.oracle_solve(deb.EnsembleIVP.ode(lz, 0.0, 100.0, [[1.0, 1.0, 1.0]]).method(E.dopri5().rtol(1e-8)))
+    assert (int(s.accepted[0]), int(s.rejected[0]), int(s.evals[0])) == (6008, 411, 44525)
+    assert [v.hex() for v in s.y_final[0]] == ["-0x1.8c65ec78fb24fp+1", "-0x1.4d4949b09d281p+1", "0x1.5bf4de76ed043p+4"]
+    s = ob.oracle_solve(deb.EnsembleIVP.ode(lz, 0.0, 10.0, [[1.0, 1.0, 1.0]]).t_eval([1.0, 2.5, 10.0]).method(E.dopri5().rtol(1e-8)))
+    assert (int(s.accepted[0]), int(s.rejected[0]), int(s.evals[0])) == (504, 8, 3579)
+    assert [v.hex() for v in s.y_final[0]] == ["-0x1.39c5be73410dbp+2", "-0x1.df3a8c489ba9ep+1", "0x1.8b0d329428ea8p+4"]
+    assert s.y_eval[0, 0].tolist() == [-9.378567031548476, -8.357039113339846, 29.36231537793399]
+    assert s.y_eval[0, 1].tolist() == [-6.959579728354202, -7.272475545395783, 24.70312694098664]
+    assert np.array_equal(s.y_eval[0, 2], s.y_final[0])  # exact-hit branch
+    s = ob.oracle_solve(deb.EnsembleIVP.ode(lz, 0.0, 100.0, [[1.0, 1.0, 1.0]]).method(E.dopri5().rtol(1e-8).atol(1e-8)))
+    assert s.status[0] == deb.DEB_STATUS_MAX_STEPS  # 10343 attempts needed
+    s = ob.oracle_solve(deb.EnsembleIVP.ode(lz, 0.0, 100.0, [[1.0, 1.0, 1.0]]).method(E.dopri5().rtol(1e-8).atol(1e-8).max_steps(20000)))
+    assert (int(s.accepted[0]), int(s.rejected[0]), int(s.evals[0])) == (10126, 217, 72187)
+    s = ob.oracle_solve(deb.EnsembleIVP.ode(deb.VanDerPolOscillator(5.0), 0.0, 10.0, [[2.0, 0.0]]).method(E.dop853().rtol(1e-8).atol(1e-8)))
+    assert (int(s.accepted[0]), int(s.rejected[0]), int(s.evals[0])) == (83, 12, 1380)
+    assert s.y_final[0].tolist() == [-1.1587012635243283, 0.43046981176622706]
+    mu = np.array([0.1, 1.0, 5.0, 10.0, 20.0, 50.0])
+    s = ob.oracle_solve(deb.EnsembleIVP.ode(deb.VanDerPolOscillator(mu), 0.0, 100.0, np.tile([2.0, 0.0], (6, 1))).method(E.dop853().rtol(1e-8).atol(1e-8)))
+    assert (s.accepted + s.rejected).tolist() == [287, 767, 1078, 1069, 1073, 1813] and (s.status == 0).all()
+    # fixed-step schedules of the solve loop
+    for (tf, h, steps) in ((1.0, 1e-3, 1000), (10.0, 0.01, 1001), (100.0, 1.0, 100), (1.0, 0.01, 100)):
+        s = ob.oracle_solve(deb.EnsembleIVP.ode(deb.ExponentialGrowth(0.0), 0.0, tf, [[1.0]]).method(E.euler(h).max_steps(100000)))
+        assert int(s.accepted[0]) == steps
+    # dense-output quirks kept as written: DOPRI5 cont[4] == 0, DOP853 s/s1 order
+    e5 = ob.oracle_solve(deb.EnsembleIVP.ode(deb.ExponentialGrowth(1.0), 0.0, 2.0, [[1.0]]).t_eval([0.5]).method(E.dopri5()))
+    e8 = ob.oracle_solve(deb.EnsembleIVP.ode(deb.ExponentialGrowth(1.0), 0.0, 2.0, [[1.0]]).t_eval([0.5]).method(E.dop853()))
+    assert int(e5.accepted[0]) == 9 and int(e8.accepted[0]) == 3
+    assert abs((e5.y_eval[0, 0, 0] - math.exp(0.5)) - (-1.89e-5)) < 1e-7
+    assert abs((e8.y_eval[0, 0, 0] - math.exp(0.5)) - 3.76e-4) < 1e-6
+
+
+def _same_bits(a, b):
+    return np.array_equal(np.asarray(a, dtype=np.float64).view(np.uint64), np.asarray(b, dtype=np.float64).view(np.uint64))
+
+
+def test_oracle_equals_independent_python_restatement_bitwise():
+    """Two independently written restatements (C++ oracle, pure-Python tests/py_restatement.py) agree bit for bit on
+    states, dense output rows and counters."""
+    cases = [
+        ("dopri5", pr.lorenz(10.0, 28.0, 8.0 / 3.0), deb.LorenzSystem(10.0, 28.0, 8.0 / 3.0), [1.0, 1.0, 1.0], 0.0, 10.0, dict(rtol=1e-8, atol=1e-6)),
+        ("dopri5", pr.lorenz(10.0, 28.0, 8.0 / 3.0), deb.LorenzSystem(10.0, 28.0, 8.0 / 3.0), [0.7, 1.3, 1.1], 0.0, 12.0, dict(rtol=1e-6, atol=1e-9)),
+        ("dop853", pr.van_der_pol(5.0), deb.VanDerPolOscillator(5.0), [2.0, 0.0], 0.0, 10.0, dict(rtol=1e-8, atol=1e-8)),
+        ("dop853", pr.lorenz(10.0, 28.0, 8.0 / 3.0), deb.LorenzSystem(10.0, 28.0, 8.0 / 3.0), [1.0, 1.0, 1.0], 0.0, 8.0, dict(rtol=1e-9, atol=1e-9)),
+        ("dopri5", pr.harmonic(1.0), deb.HarmonicOscillator(1.0), [1.0, 0.0], 10.0, 0.0, dict(rtol=1e-7, atol=1e-7)),  # backward
+        ("dop853", pr.exponential(1.0), deb.ExponentialGrowth(1.0), [1.0], 0.0, 2.0, dict(rtol=1e-6, atol=1e-6)),
+    ]
+    for meth, f, sysm, y0, t0, tf, tol in cases:
+        te = list(np.linspace(t0, tf, 9)) + [0.5 * (t0 + tf) + 0.123]
+        p = pr.solve_dp(f, meth, t0, tf, y0, t_eval=te, **tol)
+        c = ob.oracle_solve(deb.EnsembleIVP.ode(sysm, t0, tf, [y0]).t_eval(te).method(getattr(E, meth)().rtol(tol["rtol"]).atol(tol["atol"])))
+        assert p["status"] == "Complete" and c.status[0] == 0
+        assert (p["accepted"], p["rejected"], p["evals"]) == (int(c.accepted[0]), int(c.rejected[0]), int(c.evals[0]))
+        assert _same_bits(p["y"], c.y_final[0]) and _same_bits([p["t"]], [c.t_final[0]])
+        assert len(p["rows"]) == int(c.n_emitted[0])
+        assert [r[0] for r in p["rows"]] == c.t_rows[:len(p["rows"])].tolist()
+        assert _same_bits([r[1] for r in p["rows"]], c.y_eval[0, :len(p["rows"])])
+    for meth in ("euler", "midpoint", "heun", "ralston", "ssp_rk3", "rk4", "three_eighths"):
+        p = pr.solve_fixed(pr.lorenz(10.0, 28.0, 8.0 / 3.0), meth, 0.01, 0.0, 1.0, [1.0, 1.0, 1.0], t_eval=[0.0, 0.255, 0.5, 1.0])
+        c = ob.oracle_solve(deb.EnsembleIVP.ode(deb.LorenzSystem(10.0, 28.0, 8.0 / 3.0), 0.0, 1.0, [[1.0, 1.0, 1.0]]).t_eval([0.0, 0.255, 0.5, 1.0]).method(getattr(E, meth)(0.01)))
+        assert (p["accepted"], p["evals"]) == (int(c.accepted[0]), int(c.evals[0]))
+        assert _same_bits(p["y"], c.y_final[0]) and _same_bits([r[1] for r in p["rows"]], c.y_eval[0, :len(p["rows"])])
+
+
+def test_oracle_properties():
+    """Book-keeping identities and ensemble invariances of the oracle itself."""
+    y0 = ob.lorenz_ensemble_y0(64)
+    lz = deb.LorenzSystem(10.0, 28.0, 8.0 / 3.0)
+    s = ob.oracle_solve(deb.EnsembleIVP.ode(lz, 0.0, 20.0, y0).t_eval(np.arange(1.0, 21.0)).method(E.dopri5().rtol(1e-8)))
+    assert np.array_equal(s.evals, 3 + 6 * (s.accepted + s.rejected) + s.accepted)
+    assert (s.n_emitted == 20).all() and _same_bits(s.y_eval[:, 19], s.y_final)
+    # thread count and ensemble position do not change a trajectory
+    s1 = ob.oracle_solve(deb.EnsembleIVP.ode(lz, 0.0, 20.0, y0[::-1].copy()).t_eval(np.arange(1.0, 21.0)).method(E.dopri5().rtol(1e-8)), n_threads=1)
+    assert _same_bits(s1.y_eval[::-1], s.y_eval) and np.array_equal(s1.accepted[::-1], s.accepted)
+    s8 = ob.oracle_solve(deb.EnsembleIVP.ode(deb.VanDerPolOscillator(1.0), 0.0, 10.0, np.tile([2.0, 0.0], (8, 1))).method(E.dop853()))
+    assert np.array_equal(s8.evals, 3 + 11 * (s8.accepted + s8.rejected) + 4 * s8.accepted)
