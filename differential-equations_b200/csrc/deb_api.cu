@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -320,37 +321,16 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P, deb_result* R) {
     DeviceInfo di;
     if (int rc = device_info(P->device, &di)) return rc;
     const bool host = (P->memspace == DEB_MEM_HOST);
-    cudaStream_t st = host ? (cudaStream_t)0 : (cudaStream_t)P->stream;
     const long long n = P->n_traj;
 
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    if (host)
-        for (auto& e : ev) DEB_CUDA(cudaEventCreate(&e));
-    if (host) DEB_CUDA(cudaEventRecord(ev[0], st));
-
+    // ---- kernel arguments common to every launch of this call
     deb::OdeKernelArgs a;
     memset(&a, 0, sizeof a);
-    DevBuf d_y0, d_params;
-    if (host) {
-        DEB_CUDA(d_y0.alloc(sizeof(double) * (size_t)n * dim));
-        DEB_CUDA(cudaMemcpyAsync(d_y0.p, P->y0, sizeof(double) * (size_t)n * dim, cudaMemcpyHostToDevice, st));
-        a.y0 = d_y0.as<double>();
-    } else {
-        a.y0 = P->y0;
-    }
     if (np > 0 && P->params_shared) {
         // one parameter set for the whole ensemble: HOST memory by contract, passed by value (constant bank)
         for (int q = 0; q < np && q < 8; q++) a.pc[q] = P->params[q];
-        a.params = nullptr;
-    } else if (np > 0 && host) {
-        DEB_CUDA(d_params.alloc(sizeof(double) * (size_t)n * np));
-        DEB_CUDA(cudaMemcpyAsync(d_params.p, P->params, sizeof(double) * (size_t)n * np, cudaMemcpyHostToDevice, st));
-        a.params = d_params.as<double>();
-    } else {
-        a.params = P->params;
     }
     a.params_stride = P->params_shared ? 0 : np;
-    a.n_traj = n;
     a.t0 = P->t0;
     a.tf = P->tf;
     for (int c = 0; c < DEB_MAX_DIM; c++) {
@@ -364,42 +344,125 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P, deb_result* R) {
     a.min_scale = P->opt.min_scale;
     a.max_scale = P->opt.max_scale;
     a.max_steps = (int)std::min<int64_t>(P->opt.max_steps, 0x7fffffff / 16);
-    // small device scratch: [queue counter (8 B)] [rows]
-    const size_t small_bytes = 8 + sizeof(double) * plan.rows.size();
-    void* d_small = nullptr;
-    DEB_CUDA(cudaMallocAsync(&d_small, small_bytes, st));
-    struct SmallFree { void* p; cudaStream_t st; ~SmallFree() { if (p) cudaFreeAsync(p, st); } } small_free{d_small, st};
-    DEB_CUDA(cudaMemsetAsync(small_free.p, 0, 8, st));
-    if (!plan.rows.empty())
-        DEB_CUDA(cudaMemcpyAsync((char*)small_free.p + 8, plan.rows.data(), sizeof(double) * plan.rows.size(), cudaMemcpyHostToDevice, st));
-    a.queue = (unsigned long long*)small_free.p;
-    a.t_rows = (const double*)((char*)small_free.p + 8);
     a.n_rows = (int)plan.rows.size();
     a.row_stride = P->n_eval;
     a.emit_t0 = plan.emit_t0 ? 1 : 0;
+    const bool per_traj_params = (np > 0 && !P->params_shared);
+    const size_t rows_bytes = sizeof(double) * plan.rows.size();
 
-    ResultStage rs;
-    if (int rc = rs.setup(R, host, n, P->n_eval, dim)) return rc;
-    a.y_eval = rs.dev.y_eval;
-    a.n_emitted = rs.dev.n_emitted;
-    a.t_final = rs.dev.t_final;
-    a.y_final = rs.dev.y_final;
-    a.status = rs.dev.status;
-    a.accepted = rs.dev.accepted;
-    a.rejected = rs.dev.rejected;
-    a.evals = rs.dev.evals;
-
-    if (host) DEB_CUDA(cudaEventRecord(ev[1], st));
-    if (int rc = launch(a, di.sms, st)) return rc;
-    if (host) {
-        DEB_CUDA(cudaEventRecord(ev[2], st));
-        if (int rc = rs.copy_back(R, n, P->n_eval, dim, st)) return rc;
-        DEB_CUDA(cudaEventRecord(ev[3], st));
-        DEB_CUDA(cudaStreamSynchronize(st));
-        DEB_CUDA(cudaEventElapsedTime(&R->kernel_ms, ev[1], ev[2]));
-        DEB_CUDA(cudaEventElapsedTime(&R->total_ms, ev[0], ev[3]));
-        for (auto& e : ev) cudaEventDestroy(e);
+    if (!host) {
+        // ---- DEVICE memspace: pointers are device pointers; enqueue on the caller's stream and return
+        cudaStream_t st = (cudaStream_t)P->stream;
+        void* d_small = nullptr;  // [queue counter (8 B)] [rows]
+        DEB_CUDA(cudaMallocAsync(&d_small, 8 + rows_bytes, st));
+        struct SmallFree { void* p; cudaStream_t st; ~SmallFree() { if (p) cudaFreeAsync(p, st); } } small_free{d_small, st};
+        DEB_CUDA(cudaMemsetAsync(d_small, 0, 8, st));
+        if (rows_bytes) DEB_CUDA(cudaMemcpyAsync((char*)d_small + 8, plan.rows.data(), rows_bytes, cudaMemcpyHostToDevice, st));
+        a.queue = (unsigned long long*)d_small;
+        a.t_rows = (const double*)((char*)d_small + 8);
+        a.y0 = P->y0;
+        a.params = per_traj_params ? P->params : nullptr;
+        a.n_traj = n;
+        a.y_eval = R->y_eval; a.n_emitted = R->n_emitted; a.t_final = R->t_final; a.y_final = R->y_final;
+        a.status = R->status; a.accepted = R->accepted; a.rejected = R->rejected; a.evals = R->evals;
+        return launch(a, di.sms, st);
     }
+
+    // ---- HOST memspace: pipelined chunks.  Two slots, each with its own stream and device buffers, run
+    //      H2D(y0) -> kernel -> D2H(results) for alternating chunks, so the result copy of one chunk (the bulk of the
+    //      PCIe traffic: n_eval*dim*8 B per trajectory) overlaps the integration of the next, and the tail of one
+    //      persistent kernel overlaps the start of the following one.  Device memory is 2 chunks, not the ensemble.
+    const auto wall0 = std::chrono::steady_clock::now();
+    long long CHUNK = 1ll << 21;  // 2 Mi trajectories: measured best for C2 (tail loss vs exposed last copy), profiles/
+    if (const char* e = getenv("DEB_HOST_CHUNK")) {  // tuning / test knob
+        const long long v = atoll(e);
+        if (v > 0) CHUNK = v;
+    }
+    // equal chunks of at most CHUNK trajectories
+    const long long n_chunks = (n + CHUNK - 1) / CHUNK;
+    const long long chunk = (n + n_chunks - 1) / n_chunks;
+    const int n_slots = (n > chunk) ? 2 : 1;
+    const int n_eval = P->n_eval;
+    struct Slot {
+        cudaStream_t st = nullptr;
+        cudaEvent_t k0 = nullptr, k1 = nullptr;
+        DevBuf y0, params, small, y_eval, n_emitted, t_final, y_final, status, accepted, rejected, evals;
+        bool used = false;
+        ~Slot() {
+            if (k0) cudaEventDestroy(k0);
+            if (k1) cudaEventDestroy(k1);
+            if (st) cudaStreamDestroy(st);
+        }
+    } slot[2];
+    for (int s = 0; s < n_slots; s++) {
+        Slot& S = slot[s];
+        DEB_CUDA(cudaStreamCreateWithFlags(&S.st, cudaStreamNonBlocking));
+        DEB_CUDA(cudaEventCreate(&S.k0));
+        DEB_CUDA(cudaEventCreate(&S.k1));
+        DEB_CUDA(S.y0.alloc(sizeof(double) * (size_t)chunk * dim));
+        if (per_traj_params) DEB_CUDA(S.params.alloc(sizeof(double) * (size_t)chunk * np));
+        DEB_CUDA(S.small.alloc(8 + rows_bytes));
+        if (rows_bytes) DEB_CUDA(cudaMemcpyAsync((char*)S.small.p + 8, plan.rows.data(), rows_bytes, cudaMemcpyHostToDevice, S.st));
+        if (R->y_eval) DEB_CUDA(S.y_eval.alloc(sizeof(double) * (size_t)chunk * n_eval * dim));
+        if (R->n_emitted) DEB_CUDA(S.n_emitted.alloc(sizeof(int) * (size_t)chunk));
+        if (R->t_final) DEB_CUDA(S.t_final.alloc(sizeof(double) * (size_t)chunk));
+        if (R->y_final) DEB_CUDA(S.y_final.alloc(sizeof(double) * (size_t)chunk * dim));
+        if (R->status) DEB_CUDA(S.status.alloc(sizeof(int) * (size_t)chunk));
+        if (R->accepted) DEB_CUDA(S.accepted.alloc(sizeof(int) * (size_t)chunk));
+        if (R->rejected) DEB_CUDA(S.rejected.alloc(sizeof(int) * (size_t)chunk));
+        if (R->evals) DEB_CUDA(S.evals.alloc(sizeof(int) * (size_t)chunk));
+    }
+    float kernel_ms = 0.f;
+    int ci = 0;
+    for (long long off = 0; off < n; off += chunk, ci++) {
+        Slot& S = slot[ci % n_slots];
+        const long long cnt = std::min(chunk, n - off);
+        if (S.used) {  // collect the kernel time of the chunk that used this slot before (its stream has passed k1)
+            DEB_CUDA(cudaEventSynchronize(S.k1));
+            float ms = 0.f;
+            DEB_CUDA(cudaEventElapsedTime(&ms, S.k0, S.k1));
+            kernel_ms += ms;
+        }
+        DEB_CUDA(cudaMemcpyAsync(S.y0.p, P->y0 + (size_t)off * dim, sizeof(double) * (size_t)cnt * dim, cudaMemcpyHostToDevice, S.st));
+        if (per_traj_params)
+            DEB_CUDA(cudaMemcpyAsync(S.params.p, P->params + (size_t)off * np, sizeof(double) * (size_t)cnt * np, cudaMemcpyHostToDevice, S.st));
+        DEB_CUDA(cudaMemsetAsync(S.small.p, 0, 8, S.st));
+        deb::OdeKernelArgs ac = a;
+        ac.queue = (unsigned long long*)S.small.p;
+        ac.t_rows = (const double*)((char*)S.small.p + 8);
+        ac.y0 = S.y0.as<double>();
+        ac.params = per_traj_params ? S.params.as<double>() : nullptr;
+        ac.n_traj = cnt;
+        ac.y_eval = S.y_eval.as<double>(); ac.n_emitted = S.n_emitted.as<int>(); ac.t_final = S.t_final.as<double>();
+        ac.y_final = S.y_final.as<double>(); ac.status = S.status.as<int>(); ac.accepted = S.accepted.as<int>();
+        ac.rejected = S.rejected.as<int>(); ac.evals = S.evals.as<int>();
+        DEB_CUDA(cudaEventRecord(S.k0, S.st));
+        if (int rc = launch(ac, di.sms, S.st)) return rc;
+        DEB_CUDA(cudaEventRecord(S.k1, S.st));
+        S.used = true;
+#define DEB_BACK(field, T, per)                                                                                   \
+    if (R->field)                                                                                                 \
+        DEB_CUDA(cudaMemcpyAsync(R->field + (size_t)off * (per), S.field.p, sizeof(T) * (size_t)cnt * (per), cudaMemcpyDeviceToHost, S.st));
+        DEB_BACK(y_eval, double, (size_t)n_eval * dim)
+        DEB_BACK(n_emitted, int, 1)
+        DEB_BACK(t_final, double, 1)
+        DEB_BACK(y_final, double, dim)
+        DEB_BACK(status, int, 1)
+        DEB_BACK(accepted, int, 1)
+        DEB_BACK(rejected, int, 1)
+        DEB_BACK(evals, int, 1)
+#undef DEB_BACK
+    }
+    for (int s = 0; s < n_slots; s++) {
+        DEB_CUDA(cudaStreamSynchronize(slot[s].st));
+        if (slot[s].used) {
+            float ms = 0.f;
+            DEB_CUDA(cudaEventElapsedTime(&ms, slot[s].k0, slot[s].k1));
+            kernel_ms += ms;
+        }
+    }
+    R->kernel_ms = kernel_ms;  // sum over chunks (chunks on the two streams overlap: can exceed the wall time)
+    R->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
     return DEB_OK;
 }
 

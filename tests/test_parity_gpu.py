@@ -350,3 +350,25 @@ def test_large_ensemble_properties_and_subset_parity():
     assert np.array_equal(bits(g.y_final[sub]), bits(c.y_final))
     m = np.arange(100)[None, :] < c.n_emitted[:, None]
     assert np.array_equal(bits(g.y_eval[sub])[m], bits(c.y_eval)[m])
+
+
+def test_host_path_chunk_pipeline_is_transparent(monkeypatch):
+    """The HOST-memspace call pipelines the ensemble in chunks over two streams; chunking must not change a bit,
+    including with per-trajectory parameters, a ragged last chunk and rows that stop early."""
+    n = 5003
+    mu = np.linspace(0.1, 8.0, n)
+    y0 = np.tile([2.0, 0.0], (n, 1)) + ob.splitmix64_uniform(3, 2 * n).reshape(n, 2) * 0.1
+    def prob():
+        return (deb.EnsembleIVP.ode(deb.VanDerPolOscillator(mu), 0.0, 12.0, y0).t_eval(np.linspace(0.0, 12.0, 7))
+                .method(E.dopri5().rtol(1e-7).max_steps(158)))
+    monkeypatch.setenv("DEB_HOST_CHUNK", "100000000")
+    one = prob().solve()
+    monkeypatch.setenv("DEB_HOST_CHUNK", "700")
+    many = prob().solve()
+    assert (one.status != 0).any() and (one.status == 0).any()
+    for name in ("status", "accepted", "rejected", "evals", "n_emitted"):
+        assert np.array_equal(getattr(one, name), getattr(many, name)), name
+    assert np.array_equal(bits(one.y_final), bits(many.y_final)) and np.array_equal(bits(one.t_final), bits(many.t_final))
+    m = np.arange(7)[None, :] < one.n_emitted[:, None]
+    assert np.array_equal(bits(one.y_eval)[m], bits(many.y_eval)[m])
+    assert_same_solution(many, ob.oracle_solve(prob()))

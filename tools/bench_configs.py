@@ -1,0 +1,156 @@
+#!/usr/bin/env python3
+"""Timings of the other BASELINE.json configurations (C3 Van der Pol/DOP853 sweep, C4 Euler-Maruyama, C5 heat MoL) on
+one B200, device-resident, with the roofline each kernel is bounded by.  Not the headline bench (that is bench.py /
+config C2); the numbers go to profiles/ and DESIGN.md.
+
+    python tools/bench_configs.py [--c3 N] [--c4 N] [--c5 LOG2N] [--reps R]
+"""
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+deb = importlib.import_module("differential-equations_b200")
+lib = deb.load_library()
+dev = torch.device("cuda", 0)
+stream = torch.cuda.current_stream(dev)
+
+
+def timed(fn, reps):
+    fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return min(ts), sum(ts) / len(ts)
+
+
+def result_buffers(n, n_eval, dim):
+    R = deb.Result()
+    R.struct_size = C.sizeof(deb.Result)
+    bufs = dict(y_eval=torch.empty((n, max(n_eval, 1), dim), dtype=torch.float64, device=dev), n_emitted=torch.empty(n, dtype=torch.int32, device=dev),
+                t_final=torch.empty(n, dtype=torch.float64, device=dev), y_final=torch.empty((n, dim), dtype=torch.float64, device=dev),
+                status=torch.empty(n, dtype=torch.int32, device=dev), accepted=torch.empty(n, dtype=torch.int32, device=dev),
+                rejected=torch.empty(n, dtype=torch.int32, device=dev), evals=torch.empty(n, dtype=torch.int32, device=dev))
+    for k, v in bufs.items():
+        setattr(R, k, v.data_ptr())
+    return R, bufs
+
+
+def fp64_peak():
+    v = C.c_double(0)
+    lib.deb_fp64_issue_peak(0, 0, C.byref(v), None)
+    return v.value
+
+
+def c3(n, reps):
+    """Van der Pol mu in [0.1, 50] sweep, DOP853 rtol=atol=1e-8, y0=(2,0), t in [0,100], final state + counters."""
+    mu = torch.from_numpy(0.1 + 49.9 * np.arange(n) / max(n - 1, 1)).to(dev)
+    y0 = torch.from_numpy(np.tile([2.0, 0.0], (n, 1))).to(dev)
+    te = np.array([100.0])
+    P = deb.OdeProblem()
+    P.struct_size = C.sizeof(deb.OdeProblem)
+    P.system, P.method, P.dim, P.n_params = deb.DEB_SYS_VAN_DER_POL, deb.DEB_DOP853, 2, 1
+    P.n_traj, P.y0, P.params, P.params_shared = n, y0.data_ptr(), mu.data_ptr(), 0
+    P.n_eval, P.t_eval, P.t0, P.tf = 1, te.ctypes.data_as(deb._dp), 0.0, 100.0
+    lib.deb_erk_options_default(C.byref(P.opt))
+    P.opt.rtol = P.opt.atol = 1e-8
+    P.device, P.memspace, P.stream = 0, deb.DEB_MEM_DEVICE, stream.cuda_stream
+    R, bufs = result_buffers(n, 1, 2)
+    def run():
+        assert lib.deb_solve_ode(C.byref(P), C.byref(R)) == 0, lib.deb_last_error()
+    best, avg = timed(run, reps)
+    acc = int(bufs["accepted"].sum(dtype=torch.int64)); rej = int(bufs["rejected"].sum(dtype=torch.int64))
+    ok = int((bufs["status"] == 0).sum())
+    ops = 474 * (acc + rej) + 374 * acc  # per attempt / per accepted step (dense stages + cont[4..7] + RHS)
+    pk = fp64_peak()
+    return {"config": "C3 Van der Pol mu-sweep DOP853", "n_traj": n, "ms": best, "ms_avg": avg, "accepted": acc, "rejected": rej, "complete": ok,
+            "accepted_steps_per_s": acc / (best * 1e-3), "roofline": {"bound": "fp64", "achieved_TFLOPs": ops / (best * 1e-3) / 1e12, "peak": pk / 1e12,
+                                                                    "frac": ops / (best * 1e-3) / pk,
+                                                                    "note": "algorithmic 474/attempt + 374/accepted counts the dense-output stages the reference always evaluates; "
+                                                                            "the kernel evaluates them only when a t_eval point lies in the step"}}
+
+
+def c4(n, which, reps):
+    if which == "ou":
+        sysid, params, t0, tf, h, y0v, nsteps = deb.DEB_SDE_OU, np.array([0.5, 1.0, 0.3]), 0.0, 10.0, 0.01, 5.0, 1001
+    else:
+        sysid, params, t0, tf, h, y0v, nsteps = deb.DEB_SDE_GBM, np.array([0.1, 0.2]), 0.0, 1.0, 1e-3, 100.0, 1000
+    y0 = np.array([y0v])
+    te = np.array([tf])
+    P = deb.SdeProblem()
+    P.struct_size = C.sizeof(deb.SdeProblem)
+    P.system, P.method, P.dim, P.n_params = sysid, deb.DEB_EULER, 1, params.size
+    P.n_traj, P.y0, P.y0_shared, P.params, P.params_shared = n, y0.ctypes.data, 1, params.ctypes.data, 1
+    P.n_eval, P.t_eval, P.t0, P.tf = 1, te.ctypes.data_as(deb._dp), t0, tf
+    lib.deb_erk_options_default(C.byref(P.opt))
+    P.opt.h0 = h
+    P.seed, P.path_offset = 2026, 0
+    P.device, P.memspace, P.stream = 0, deb.DEB_MEM_DEVICE, stream.cuda_stream
+    R, bufs = result_buffers(n, 1, 1)
+    def run():
+        assert lib.deb_solve_sde(C.byref(P), C.byref(R)) == 0, lib.deb_last_error()
+    best, avg = timed(run, reps)
+    steps = int(bufs["accepted"].sum(dtype=torch.int64))
+    yf = bufs["y_final"].reshape(-1)
+    mean, var = float(yf.mean()), float(yf.var())
+    if which == "ou":  # exact moments of the EM chain are close to the SDE's: mean 1 + 4 e^{-5}, var sigma^2/(2 theta)(1 - e^{-10})
+        exp_mean, exp_var = 1.0 + 4.0 * np.exp(-5.0), 0.09 / 1.0 * (1 - np.exp(-10.0))
+    else:
+        exp_mean, exp_var = 100.0 * np.exp(0.1), 100.0 ** 2 * np.exp(0.2) * (np.exp(0.04) - 1)
+    return {"config": f"C4 Euler-Maruyama {which.upper()}", "n_paths": n, "steps_per_path": nsteps, "ms": best, "ms_avg": avg,
+            "path_steps_per_s": steps / (best * 1e-3), "mean": mean, "var": var, "sde_mean": exp_mean, "sde_var": exp_var}
+
+
+def c5(log2n, reps):
+    n = 1 << log2n
+    x = np.arange(n, dtype=np.float64)
+    u0 = torch.from_numpy(np.sin(np.pi * x / (n - 1))).to(dev)
+    out = torch.empty_like(u0)
+    P = deb.HeatProblem()
+    P.struct_size = C.sizeof(deb.HeatProblem)
+    P.n_nodes, P.lo, P.hi, P.alpha = n, 0.0, float(n - 1), 0.1
+    P.bc_lower_kind = P.bc_upper_kind = 0
+    P.method, P.h, P.t0, P.tf, P.max_steps = deb.DEB_RK4, 1.0, 0.0, 100.0, 10000
+    P.u0, P.u_final = u0.data_ptr(), out.data_ptr()
+    steps, status, tfin = C.c_int64(0), C.c_int32(-1), C.c_double(0)
+    P.steps, P.status, P.t_final = C.pointer(steps), C.pointer(status), C.pointer(tfin)
+    P.device, P.memspace, P.stream = 0, deb.DEB_MEM_DEVICE, stream.cuda_stream
+    def run():
+        assert lib.deb_solve_heat_mol(C.byref(P)) == 0, lib.deb_last_error()
+    best, avg = timed(run, reps)
+    bytes_alg = 128.0 * n * steps.value + 3 * 8.0 * n  # 16 N doubles per RK4 step (+ init RHS, copy in/out)
+    hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    return {"config": "C5 heat MoL RK4", "n_nodes": n, "steps": steps.value, "status": status.value, "ms": best, "ms_avg": avg, "ms_per_step": best / max(steps.value, 1),
+            "node_steps_per_s": n * steps.value / (best * 1e-3),
+            "roofline": {"bound": "hbm", "achieved_GBs": bytes_alg / (best * 1e-3) / 1e9, "peak_GBs": hbm, "frac": bytes_alg / (best * 1e-3) / 1e9 / hbm,
+                         "note": "whole deb_solve_heat_mol call incl. buffer allocation, D2D copy in/out and 401 launches"}}
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--c3", type=int, default=4_000_000)
+    ap.add_argument("--c4", type=int, default=100_000_000)
+    ap.add_argument("--c5", type=int, default=24)
+    ap.add_argument("--reps", type=int, default=3)
+    a = ap.parse_args()
+    if a.c3:
+        print(json.dumps(c3(a.c3, a.reps)), flush=True)
+    if a.c4:
+        for w in ("ou", "gbm"):
+            print(json.dumps(c4(a.c4, w, a.reps)), flush=True)
+    if a.c5:
+        print(json.dumps(c5(a.c5, a.reps)), flush=True)
