@@ -107,10 +107,11 @@ def load_library() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("DEB200_LIB", LIB_PATH)  # (override used to A/B alternative builds of the same library)
+    if not os.path.exists(path):
         raise ExtensionMissing(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
                                "(there is no CPU fallback for the ensemble kernels)")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     lib.deb_last_error.restype = C.c_char_p
     lib.deb_solve_ode.argtypes = [C.POINTER(OdeProblem), C.POINTER(Result)]
     lib.deb_solve_sde.argtypes = [C.POINTER(SdeProblem), C.POINTER(Result)]

@@ -117,13 +117,13 @@ ode_launch_fn pick_ode_method(int method) {
                 case 2: return launch_dp<Sys, deb::TabDopri5, 64, 10>;
                 case 3: return launch_dp<Sys, deb::TabDopri5, 32, 19>;
                 case 4: return launch_dp<Sys, deb::TabDopri5, 32, 21>;
-                case 5: return launch_dp<Sys, deb::TabDopri5, 128, 5>;
+                case 5: return launch_dp<Sys, deb::TabDopri5, 256, 2>;
                 case 6: return launch_dp<Sys, deb::TabDopri5, 128, 4>;
             }
         }
     }
     switch (method) {
-        case DEB_DOPRI5: return launch_dp<Sys, deb::TabDopri5, 256, 2>;  // 128 regs, no spills, 16 warps/SM (sweep: profiles/)
+        case DEB_DOPRI5: return launch_dp<Sys, deb::TabDopri5, 128, 5>;  // 96 regs, no spills, 20 warps/SM (sweep: profiles/)
         case DEB_DOP853: return launch_dp<Sys, deb::TabDop853, 128, 2>;
         case DEB_EULER: return launch_fixed<Sys, deb::TabEuler>;
         case DEB_MIDPOINT: return launch_fixed<Sys, deb::TabMidpoint>;

@@ -128,19 +128,24 @@ __device__ __forceinline__ void load_pow_tables(double* s_powlog, unsigned long 
 // ------------------------------------------------------------------------------------------------------------
 // Dormand-Prince family (DOPRI5, DOP853): adaptive step, embedded error norm, I-controller, dense output.
 // ------------------------------------------------------------------------------------------------------------
-// Control-flow design: every lane of a warp executes the SAME instruction stream for the step attempt -- stages,
-// error norm, controller, the derivative at the new point -- whether it holds a live trajectory, is about to
-// reject, or is idle (idle lanes carry a benign dummy state; nothing they compute is committed).  Accept/reject,
-// the state shift and the step-size update are predicated selects.  Only three rare blocks diverge, and each is
-// closed by __syncwarp() so the warp is converged again before the next common instruction:
-//   (1) the stiffness test (every 100th step), (2) the t_eval emission (~1.6% of lane-steps), (3) trajectory
-//   finish + the refill from the global queue.
-// Deferred emission (methods whose dense output needs no extra stages, i.e. DOPRI5): with 32 lanes a warp would
-// enter the emission block in ~40% of its iterations with one or two lanes active (measured: 10% of all issued
-// instructions at 4% lane utilisation).  Instead a lane whose step contains a t_eval point parks the six vectors the
-// interpolant needs (t, h, y, y_new, k0, f(y_new)) in shared memory and keeps stepping; the warp interpolates and
-// stores for all parked lanes at once when 16 of them are waiting (or when a parked lane hits again / finishes).
-// The arithmetic is unchanged -- same operands, same operations, later.
+// Control-flow design.  The kernel alternates between a HOT LOOP and a SERVICE SECTION.
+//   Hot loop: one step attempt per lane per iteration.  Every lane of the warp executes the same instruction stream
+//   -- stages, error norm, controller, the derivative at the new point -- whether it holds a live trajectory, is about
+//   to reject, or is idle (idle lanes carry a benign dummy state; nothing they compute is committed).  Accept/reject,
+//   the state shift and the step-size update are predicated.  The loop runs until some lane needs service (one vote
+//   per iteration).  Only two short blocks diverge inside it: the stiffness test (every 100th step of a lane) and
+//   the parking of a t_eval hit (below).
+//   Service section (every ~50 iterations): flush parked t_eval rows, write out finished trajectories, refill idle
+//   lanes from the global queue with ONE warp-aggregated atomicAdd (__ballot_sync + __popc + __shfl_sync), leave
+//   when the queue is drained and no lane is live.  Keeping these rare blocks out of the hot loop also keeps their
+//   register shuffling (phi moves) out of it.
+// Parked emission (methods whose dense output needs no extra stages, i.e. DOPRI5): with 32 lanes, some lane has a
+//   t_eval point inside its step in ~40% of the iterations; interpolating on the spot ran ~170 instructions with one
+//   or two lanes active (measured: 10% of all issued instructions at 4% lane utilisation).  Instead the lane parks the
+//   vectors the interpolant needs (t, h, y, y_new, k0, f(y_new)) in shared memory and keeps stepping; the rows of all
+//   parked lanes are computed together in the service section.  A lane that hits again while parked does not commit
+//   its step, asks for service and redoes the attempt afterwards -- same inputs, same bits.  The arithmetic is
+//   unchanged: same operands, same operations, later.  DOP853 (3 extra dense stages) interpolates on the spot.
 // SHARED_P: every trajectory uses the same parameter set (passed by value in a.pc: no registers).
 template <class Sys, class Tab, int BLOCK, int MIN_BLOCKS, bool SHARED_P>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const OdeKernelArgs a) {
@@ -159,15 +164,16 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
     const double eps10 = DBL_EPSILON * 10.0;
     const double neg_err_exp = -(1.0 / (double)O);  // -error_exponent, ordinary.rs:152-154
     const double te_none = (dir > 0.0) ? (1.0 / 0.0) : -(1.0 / 0.0);
+    const int evals_base = (a.h0 == 0.0) ? 3 : 1;   // init: f(t0,y0) (+2 for the automatic initial step)
+    const bool bounded_h = (a.h_min > 0.0) || (a.h_max < 1.0 / 0.0);  // constrain_step_size can change h at all
 
     constexpr bool DEFER = (I == S);   // dense output needs no extra stages: emission can be parked
-    constexpr int FLUSH_AT = 16;       // parked lanes per warp that trigger a flush
     constexpr int NSTASH = 2 + 4 * N;  // t, h, y, y_new, k0, f(y_new)
     __shared__ double s_stash[DEFER ? (BLOCK / 32) : 1][DEFER ? NSTASH : 1][32];
     double (*stash)[32] = s_stash[DEFER ? (threadIdx.x >> 5) : 0];
     const bool want_rows = (a.y_eval != nullptr);
-    bool pending = false, finishing = false;  // parked emission; finished, waiting for its rows to be flushed
-    int pend_idx = 0, fin_status = 0;
+    bool pending = false;  // this lane has a parked step
+    int pend_idx = 0;      // first row of the parked step
 
     // per-lane trajectory state (registers); starts as the idle dummy
     bool active = false, exhausted = false;
@@ -175,8 +181,9 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
     double t = t0, h = 0.0, h_prev = 0.0, te = te_none;
     double y[N], k[S][N], p_reg[(NP > 0 && !SHARED_P) ? NP : 1];
     const double* p = SHARED_P ? a.pc : p_reg;
-    int acc = 0, rej = 0, evals_base = 0, stiff = 0, nonstiff = 0;
-    int idx = 0;  // next t_eval row == number of rows emitted so far (rows are pre-filtered: every consumed point is emitted)
+    int acc = 0, rej = 0, stiff = 0, nonstiff = 0;
+    int idx = 0;   // next t_eval row == rows emitted so far (rows are pre-filtered: every consumed point is emitted)
+    int fin = -1;  // >= 0: the trajectory has ended with this status and waits for the service section
     bool rejected_prev = false;
 #pragma unroll
     for (int c = 0; c < N; c++) { y[c] = 1.0; k[0][c] = 0.0; }
@@ -186,9 +193,77 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
     }
 
     for (;;) {
-        // ---------------- refill idle lanes from the global queue (one atomic per warp)
-        const unsigned need = __ballot_sync(FULL, !active && !exhausted);
-        if (need) {  // warp-uniform
+        // =====================================================================================================
+        // SERVICE SECTION
+        // =====================================================================================================
+        if (DEFER) {
+            // ---- flush parked rows
+            if (pending) {
+                const double ts = stash[0][lane], hs = stash[1][lane];
+                double ys[N], yn[N], c1[N], c2[N], c3[N];
+#pragma unroll
+                for (int c = 0; c < N; c++) {  // ordinary.rs:196-207
+                    ys[c] = stash[2 + c][lane];
+                    yn[c] = stash[2 + N + c][lane];
+                    const double k0s = stash[2 + 2 * N + c][lane], dys = stash[2 + 3 * N + c][lane];
+                    c1[c] = yn[c] - ys[c];
+                    c2[c] = __dadd_rn(0.0, hs * k0s) - c1[c];
+                    c3[c] = (c1[c] + (-hs) * dys) - c2[c];
+                }
+                const double c4 = __dmul_rn(0.0, hs);  // bi rows 4.. are all zero => cont[4] = (+0) * h
+                const double tn = ts + hs;
+                // the parked step covers rows [pend_idx, idx): idx was advanced past the step when the lane parked
+                for (int r = pend_idx; r < idx; r++) {
+                    const double ter = a.t_rows[r];
+                    double row[N];
+                    if (ter == tn) {  // exact hit: the solver state itself (t_eval.rs:113-114)
+#pragma unroll
+                        for (int c = 0; c < N; c++) row[c] = yn[c];
+                    } else {  // interpolate, ordinary.rs:301-337 with O = 5
+                        const double sx = (ter - ts) / hs;
+                        const double s1 = 1.0 - sx;
+#pragma unroll
+                        for (int c = 0; c < N; c++) {
+                            double accp = c4 * s1 + c3[c];
+                            accp = accp * sx + c2[c];
+                            accp = accp * s1 + c1[c];
+                            row[c] = ys[c] + sx * accp;
+                        }
+                    }
+                    double* dst = a.y_eval + ((size_t)traj * a.row_stride + r) * N;
+#pragma unroll
+                    for (int c = 0; c < N; c++) dst[c] = row[c];
+                }
+                pending = false;
+            }
+            __syncwarp();
+        }
+        // ---- finished trajectories: Solution / Error fields
+        if (active && fin >= 0) {
+            if (a.status) a.status[traj] = fin;
+            if (a.t_final) a.t_final[traj] = t;
+            if (a.y_final) {
+#pragma unroll
+                for (int c = 0; c < N; c++) a.y_final[traj * N + c] = y[c];
+            }
+            if (a.accepted) a.accepted[traj] = acc;
+            if (a.rejected) a.rejected[traj] = rej;
+            // Evals.function: 1 (+2 for the automatic h0) + (S-1) per attempt + 1 (+ I-S-1 dense stages) per accepted step
+            if (a.evals) a.evals[traj] = evals_base + (S - 1) * (acc + rej) + acc * (1 + ((I > S) ? (I - S - 1) : 0));
+            if (a.n_emitted) a.n_emitted[traj] = idx;
+            active = false;
+            // idle dummy state: finite, never committed
+            t = t0; h = 0.0; h_prev = 0.0; te = te_none;
+#pragma unroll
+            for (int c = 0; c < N; c++) { y[c] = 1.0; k[0][c] = 0.0; }
+        }
+        fin = -1;
+        __syncwarp();
+        // ---- refill idle lanes from the global queue (one atomic per warp); BadInput trajectories are written
+        //      out at once and the lane asks again
+        for (;;) {
+            const unsigned need = __ballot_sync(FULL, !active && !exhausted);
+            if (need == 0u) break;
             const int leader = __ffs(need) - 1;
             unsigned long long base = 0;
             if ((int)lane == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(need));
@@ -207,13 +282,9 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
                         for (int q = 0; q < NP; q++) p_reg[q] = a.params[traj * a.params_stride + q];
                     }
                     double h0 = a.h0;
-                    evals_base = 1;
-                    if (h0 == 0.0) {
-                        h0 = initial_step_size<Sys>(t0, tf, y0v, p, O, a.rtol, a.atol, a.h_min, a.h_max, tb);
-                        evals_base = 3;
-                    }
+                    if (h0 == 0.0) h0 = initial_step_size<Sys>(t0, tf, y0v, p, O, a.rtol, a.atol, a.h_min, a.h_max, tb);
                     if (!validate_step_size_parameters(h0, a.h_min, a.h_max, t0, tf)) {
-                        // Err(BadInput): no solution; report (t0, y0).  The lane stays idle and asks again.
+                        // Err(BadInput): no solution; report (t0, y0)
                         if (a.status) a.status[traj] = DEB_STATUS_BAD_INPUT;
                         if (a.t_final) a.t_final[traj] = t0;
                         if (a.y_final) {
@@ -249,323 +320,268 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
             }
             __syncwarp();
         }
-        // leave when every lane has drained the queue and finished its last trajectory
-        if (!__any_sync(FULL, active || !exhausted)) break;
+        // ---- leave when the queue is drained and no lane holds a live trajectory
+        if (!__any_sync(FULL, active)) break;
 
-        // ---------------- solve_ode loop head, solve_ivp.rs:193-209; step guards, ordinary.rs:70-92
-        int fin = -1;  // >= 0: the trajectory ends with this status
-        {
-            const double h_new = tf - t;
-            if ((t + h - tf) * dir > 0.0) {
-                if (fabs(h_new) < eps10) fin = DEB_STATUS_COMPLETE;
-                else h = h_new;
-            }
-            if (fin < 0) {
-                if (fabs(h) < fabs(h_prev) * 1e-14) fin = DEB_STATUS_STEP_SIZE;
-                else if (acc + rej >= a.max_steps) fin = DEB_STATUS_MAX_STEPS;  // steps counts rejected attempts too
-            }
-        }
-        const bool stepping = active && !finishing && fin < 0;
-        const int steps = acc + rej + 1;  // self.steps after the increment
-
-        // ---- stages, ordinary.rs:95-104 (all lanes)
-#pragma unroll
-        for (int i = 1; i < S; i++) {
-            double ys[N];
-#pragma unroll
-            for (int c = 0; c < N; c++) ys[c] = y[c];
-#pragma unroll
-            for (int j = 0; j < i; j++) {
-                if (Tab::a(i, j) != 0.0) {
-                    const double ah = Tab::av(i, j) * h;
-#pragma unroll
-                    for (int c = 0; c < N; c++) ys[c] = ys[c] + ah * k[j][c];
+        // =====================================================================================================
+        // HOT LOOP: one step attempt per lane per iteration, until some lane needs service
+        // =====================================================================================================
+        bool service;
+        do {
+            // ---- solve_ode loop head, solve_ivp.rs:193-209; step guards, ordinary.rs:70-92
+            {
+                const double h_new = tf - t;
+                if ((t + h - tf) * dir > 0.0) {
+                    if (fabs(h_new) < eps10) fin = DEB_STATUS_COMPLETE;
+                    else h = h_new;
+                }
+                if (fin < 0) {
+                    if (fabs(h) < fabs(h_prev) * 1e-14) fin = DEB_STATUS_STEP_SIZE;
+                    else if (acc + rej >= a.max_steps) fin = DEB_STATUS_MAX_STEPS;  // steps counts rejected attempts too
                 }
             }
-            Sys::rhs(t + Tab::cv(i) * h, ys, k[i], p);
-        }
-        // ---- solution and error estimate, ordinary.rs:106-149
-        double yseg[N], ynew[N], es[N];
+            const bool stepping = active && fin < 0;
+            const int steps = acc + rej + 1;  // self.steps after the increment
+
+            // ---- stages, ordinary.rs:95-104 (all lanes)
 #pragma unroll
-        for (int c = 0; c < N; c++) { yseg[c] = 0.0; es[c] = 0.0; }
+            for (int i = 1; i < S; i++) {
+                double ys[N];
 #pragma unroll
-        for (int i = 0; i < S; i++) {
-            if (Tab::b(i) != 0.0) {
+                for (int c = 0; c < N; c++) ys[c] = y[c];
 #pragma unroll
-                for (int c = 0; c < N; c++) yseg[c] = __dadd_rn(yseg[c], Tab::bv(i) * k[i][c]);
+                for (int j = 0; j < i; j++) {
+                    if (Tab::a(i, j) != 0.0) {
+                        const double ah = Tab::av(i, j) * h;
+#pragma unroll
+                        for (int c = 0; c < N; c++) ys[c] = ys[c] + ah * k[j][c];
+                    }
+                }
+                Sys::rhs(t + Tab::cv(i) * h, ys, k[i], p);
             }
-            if (Tab::er(i) != 0.0) {
+            // ---- solution and error estimate, ordinary.rs:106-149
+            double yseg[N], ynew[N], es[N];
 #pragma unroll
-                for (int c = 0; c < N; c++) es[c] = __dadd_rn(es[c], Tab::erv(i) * k[i][c]);
-            }
-        }
-        const double t_new = t + h;
-        double err = 0.0, err2 = 0.0;
-        double sk[N];
-#pragma unroll
-        for (int c = 0; c < N; c++) {
-            ynew[c] = y[c] + h * yseg[c];
-            sk[c] = a.atol[c] + a.rtol[c] * fmax(fabs(y[c]), fabs(ynew[c]));  // traits.rs:587-595
-            const double e = es[c] / sk[c];
-            err = err + e * e;
-        }
-        if (Tab::HAS_BH) {  // DOP853 second estimator, ordinary.rs:135-143
-            double e2[N];
-#pragma unroll
-            for (int c = 0; c < N; c++) e2[c] = yseg[c];
+            for (int c = 0; c < N; c++) { yseg[c] = 0.0; es[c] = 0.0; }
 #pragma unroll
             for (int i = 0; i < S; i++) {
-                if (Tab::bh(i) != 0.0) {
+                if (Tab::b(i) != 0.0) {
 #pragma unroll
-                    for (int c = 0; c < N; c++) e2[c] = e2[c] + (-Tab::bhv(i)) * k[i][c];
+                    for (int c = 0; c < N; c++) yseg[c] = __dadd_rn(yseg[c], Tab::bv(i) * k[i][c]);
+                }
+                if (Tab::er(i) != 0.0) {
+#pragma unroll
+                    for (int c = 0; c < N; c++) es[c] = __dadd_rn(es[c], Tab::erv(i) * k[i][c]);
                 }
             }
+            const double t_new = t + h;
+            double err = 0.0, err2 = 0.0;
+            double sk[N];
 #pragma unroll
             for (int c = 0; c < N; c++) {
-                const double e = e2[c] / sk[c];
-                err2 = err2 + e * e;
+                ynew[c] = y[c] + h * yseg[c];
+                sk[c] = a.atol[c] + a.rtol[c] * fmax(fabs(y[c]), fabs(ynew[c]));  // traits.rs:587-595
+                const double e = es[c] / sk[c];
+                err = err + e * e;
             }
-        }
-        double deno = err + 0.01 * err2;
-        if (deno <= 0.0) deno = 1.0;
-        err = fabs(h) * err * sqrt(1.0 / (deno * (double)N));  // ordinary.rs:148
-        // ---- controller, ordinary.rs:151-157
-        double scale = a.safety * deb_pow_pos(err, neg_err_exp, tb);
-        scale = fmin(fmax(scale, a.min_scale), a.max_scale);
-
-        // ---- derivative at the new point (ordinary.rs:162; evaluated by every lane, committed only on accept)
-        const bool accept = stepping && (err <= 1.0);
-        double dydt[N];
-        Sys::rhs(t_new, ynew, dydt, p);
-
-        if (accept && (steps % 100 == 0)) {  // stiffness test, ordinary.rs:165-194
-            // ysti = the argument of the last stage; rebuilt here (same operations, same bits) instead of being kept
-            // alive in registers through 99 steps out of 100
-            double ysti[N];
+            if (Tab::HAS_BH) {  // DOP853 second estimator, ordinary.rs:135-143
+                double e2[N];
 #pragma unroll
-            for (int c = 0; c < N; c++) ysti[c] = y[c];
+                for (int c = 0; c < N; c++) e2[c] = yseg[c];
 #pragma unroll
-            for (int j = 0; j < S - 1; j++) {
-                if (Tab::a(S - 1, j) != 0.0) {
-                    const double ah = Tab::av(S - 1, j) * h;
+                for (int i = 0; i < S; i++) {
+                    if (Tab::bh(i) != 0.0) {
 #pragma unroll
-                    for (int c = 0; c < N; c++) ysti[c] = ysti[c] + ah * k[j][c];
+                        for (int c = 0; c < N; c++) e2[c] = e2[c] + (-Tab::bhv(i)) * k[i][c];
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < N; c++) {
+                    const double e = e2[c] / sk[c];
+                    err2 = err2 + e * e;
                 }
             }
-            double stdnum = 0.0, stden = 0.0;
+            double deno = err + 0.01 * err2;
+            if (deno <= 0.0) deno = 1.0;
+            err = fabs(h) * err * sqrt(1.0 / (deno * (double)N));  // ordinary.rs:148
+            // ---- controller, ordinary.rs:151-157
+            double scale = a.safety * deb_pow_pos(err, neg_err_exp, tb);
+            // scale.max(min_scale).min(max_scale) (ordinary.rs:157) with f64::max/min NaN rules: a NaN scale becomes
+            // min_scale.  Written as ordered compares + selects (the options are never NaN): 6 instructions, not 16.
+            scale = (scale >= a.min_scale) ? scale : a.min_scale;
+            scale = (scale <= a.max_scale) ? scale : a.max_scale;
+
+            // ---- derivative at the new point (ordinary.rs:162; evaluated by every lane, committed only on accept)
+            const bool accept = stepping && (err <= 1.0);
+            double dydt[N];
+            Sys::rhs(t_new, ynew, dydt, p);
+
+            if (accept && (steps % 100 == 0)) {  // stiffness test, ordinary.rs:165-194
+                // ysti = the argument of the last stage; rebuilt here (same operations, same bits) instead of being
+                // kept alive in registers through 99 steps out of 100
+                double ysti[N];
 #pragma unroll
-            for (int c = 0; c < N; c++) {
-                const double d1 = yseg[c] - k[S - 1][c];
-                stdnum = stdnum + d1 * d1;
-                const double d2 = dydt[c] - ysti[c];  // (sic) derivative minus stage state, as in the reference
-                stden = stden + d2 * d2;
-            }
-            if (stden > 0.0) {
-                const double h_lamb = h * sqrt(stdnum / stden);
-                if (h_lamb > 6.1) {
-                    nonstiff = 0;
-                    stiff += 1;
-                    if (stiff == 15) fin = DEB_STATUS_STIFFNESS;  // Err before any state update
+                for (int c = 0; c < N; c++) ysti[c] = y[c];
+#pragma unroll
+                for (int j = 0; j < S - 1; j++) {
+                    if (Tab::a(S - 1, j) != 0.0) {
+                        const double ah = Tab::av(S - 1, j) * h;
+#pragma unroll
+                        for (int c = 0; c < N; c++) ysti[c] = ysti[c] + ah * k[j][c];
+                    }
                 }
+                double stdnum = 0.0, stden = 0.0;
+#pragma unroll
+                for (int c = 0; c < N; c++) {
+                    const double d1 = yseg[c] - k[S - 1][c];
+                    stdnum = stdnum + d1 * d1;
+                    const double d2 = dydt[c] - ysti[c];  // (sic) derivative minus stage state, as in the reference
+                    stden = stden + d2 * d2;
+                }
+                if (stden > 0.0) {
+                    const double h_lamb = h * sqrt(stdnum / stden);
+                    if (h_lamb > 6.1) {
+                        nonstiff = 0;
+                        stiff += 1;
+                        if (stiff == 15) fin = DEB_STATUS_STIFFNESS;  // Err before any state update
+                    }
+                } else {
+                    nonstiff += 1;
+                    if (nonstiff == 6) stiff = 0;
+                }
+            }
+            __syncwarp();
+
+            // ---- TEvalSolout (t_eval.rs:100-130): does a t_eval point lie in this step?  (te - t_new == 0 iff te == t_new)
+            const bool hit = accept && fin < 0 && ((te - t_new) * dir <= 0.0);
+            bool blocked = false;
+            if (DEFER) {
+                blocked = hit && pending;  // slot occupied: do not commit, get the slot flushed, redo this attempt
+                if (hit && !blocked) {
+                    if (want_rows) {  // park the step
+                        stash[0][lane] = t;
+                        stash[1][lane] = h;
+#pragma unroll
+                        for (int c = 0; c < N; c++) {
+                            stash[2 + c][lane] = y[c];
+                            stash[2 + N + c][lane] = ynew[c];
+                            stash[2 + 2 * N + c][lane] = k[0][c];
+                            stash[2 + 3 * N + c][lane] = dydt[c];
+                        }
+                        pend_idx = idx;
+                        pending = true;
+                    }
+                    do {
+                        idx += 1;
+                        te = (idx < a.n_rows) ? a.t_rows[idx] : te_none;
+                    } while ((te - t_new) * dir <= 0.0);
+                }
+                __syncwarp();
             } else {
-                nonstiff += 1;
-                if (nonstiff == 6) stiff = 0;
-            }
-        }
-        __syncwarp();
-        const bool commit = accept && fin < 0;
-
-        // ---- TEvalSolout (t_eval.rs:100-130); the dense output is built only when a point lies in the step
-        const bool hit = commit && ((dir > 0.0) ? (te <= t_new) : (te >= t_new));
-        if (DEFER) {
-            // -- flush parked rows: enough lanes waiting, or a parked lane needs its slot again / has finished
-            const unsigned pmask = __ballot_sync(FULL, pending);
-            const bool force = __any_sync(FULL, pending && (hit || finishing));
-            if (pmask != 0u && (force || __popc(pmask) >= FLUSH_AT)) {  // warp-uniform
-                if (pending) {
-                    const double ts = stash[0][lane], hs = stash[1][lane];
-                    double ys[N], yn[N], c1[N], c2[N], c3[N];
+                if (hit) {
+                    double c1[N], c2[N], c3[N];
 #pragma unroll
                     for (int c = 0; c < N; c++) {  // ordinary.rs:196-207
-                        ys[c] = stash[2 + c][lane];
-                        yn[c] = stash[2 + N + c][lane];
-                        const double k0s = stash[2 + 2 * N + c][lane], dys = stash[2 + 3 * N + c][lane];
-                        c1[c] = yn[c] - ys[c];
-                        c2[c] = __dadd_rn(0.0, hs * k0s) - c1[c];
-                        c3[c] = (c1[c] + (-hs) * dys) - c2[c];
+                        c1[c] = ynew[c] - y[c];
+                        c2[c] = __dadd_rn(0.0, h * k[0][c]) - c1[c];
+                        c3[c] = (c1[c] + (-h) * dydt[c]) - c2[c];
                     }
-                    const double c4 = __dmul_rn(0.0, hs);  // bi rows 4.. are all zero => cont[4] = (+0) * h
-                    const double tn = ts + hs;
-                    // the parked step covers rows [pend_idx, idx): idx was advanced past the step when the lane parked
-                    for (int r = pend_idx; r < idx; r++) {
-                        const double ter = a.t_rows[r];
-                        double row[N];
-                        if (ter == tn) {  // exact hit: the solver state itself (t_eval.rs:113-114)
+                    double ch[(O > 4) ? (O - 4) : 1][N];  // cont[4..O-1]
+                    {
+                        // extra dense stages, ordinary.rs:210-225: k[S] = dydt, stages S+1..I-1
+                        double kx[(I > S) ? (I - S) : 1][N];
 #pragma unroll
-                            for (int c = 0; c < N; c++) row[c] = yn[c];
-                        } else {  // interpolate, ordinary.rs:301-337 with O = 5
-                            const double sx = (ter - ts) / hs;
+                        for (int c = 0; c < N; c++) kx[0][c] = dydt[c];
+#pragma unroll
+                        for (int i = S + 1; i < I; i++) {
+                            double ys[N];
+#pragma unroll
+                            for (int c = 0; c < N; c++) ys[c] = y[c];
+#pragma unroll
+                            for (int j = 0; j < i; j++) {
+                                if (Tab::a(i, j) != 0.0) {
+                                    const double ah = Tab::av(i, j) * h;
+#pragma unroll
+                                    for (int c = 0; c < N; c++) ys[c] = ys[c] + ah * ((j < S) ? k[j][c] : kx[j - S][c]);
+                                }
+                            }
+                            Sys::rhs(t + Tab::cv(i) * h, ys, kx[i - S], p);
+                        }
+#pragma unroll
+                        for (int i = 4; i < O; i++) {  // ordinary.rs:228-234
+#pragma unroll
+                            for (int c = 0; c < N; c++) ch[i - 4][c] = 0.0;
+#pragma unroll
+                            for (int j = 0; j < I; j++) {
+                                if (Tab::bi(i, j) != 0.0) {
+#pragma unroll
+                                    for (int c = 0; c < N; c++)
+                                        ch[i - 4][c] = __dadd_rn(ch[i - 4][c], Tab::biv(i, j) * ((j < S) ? k[j][c] : kx[j - S][c]));
+                                }
+                            }
+#pragma unroll
+                            for (int c = 0; c < N; c++) ch[i - 4][c] = ch[i - 4][c] * h;
+                        }
+                    }
+                    do {
+                        double row[N];
+                        if (te == t_new) {  // exact hit: the solver state itself (t_eval.rs:113-114)
+#pragma unroll
+                            for (int c = 0; c < N; c++) row[c] = ynew[c];
+                        } else {  // interpolate, ordinary.rs:301-337, factor order as written
+                            const double sx = (te - t) / h;
                             const double s1 = 1.0 - sx;
 #pragma unroll
                             for (int c = 0; c < N; c++) {
-                                double accp = c4 * s1 + c3[c];
-                                accp = accp * sx + c2[c];
-                                accp = accp * s1 + c1[c];
-                                row[c] = ys[c] + sx * accp;
+                                double accp = (O > 4) ? ch[O - 5][c] : c3[c];
+#pragma unroll
+                                for (int i = O - 2; i >= 1; i--) {
+                                    double factor;
+                                    if (i >= 4) factor = (((O - 1) - i) % 2 == 1) ? s1 : sx;
+                                    else factor = (i % 2 == 1) ? s1 : sx;
+                                    const double ci = (i >= 4) ? ch[(i >= 4) ? (i - 4) : 0][c] : (i == 3 ? c3[c] : (i == 2 ? c2[c] : c1[c]));
+                                    accp = accp * factor + ci;
+                                }
+                                row[c] = y[c] + sx * accp;
                             }
                         }
-                        double* dst = a.y_eval + ((size_t)traj * a.row_stride + r) * N;
+                        if (want_rows) {
+                            double* dst = a.y_eval + ((size_t)traj * a.row_stride + idx) * N;
 #pragma unroll
-                        for (int c = 0; c < N; c++) dst[c] = row[c];
-                    }
-                    pending = false;
+                            for (int c = 0; c < N; c++) dst[c] = row[c];
+                        }
+                        idx += 1;
+                        te = (idx < a.n_rows) ? a.t_rows[idx] : te_none;
+                    } while ((te - t_new) * dir <= 0.0);
                 }
                 __syncwarp();
             }
-            // -- park this step's rows
-            if (hit) {
-                if (want_rows) {
-                    stash[0][lane] = t;
-                    stash[1][lane] = h;
-#pragma unroll
-                    for (int c = 0; c < N; c++) {
-                        stash[2 + c][lane] = y[c];
-                        stash[2 + N + c][lane] = ynew[c];
-                        stash[2 + 2 * N + c][lane] = k[0][c];
-                        stash[2 + 3 * N + c][lane] = dydt[c];
-                    }
-                    pend_idx = idx;
-                    pending = true;
-                }
-                do {
-                    idx += 1;
-                    te = (idx < a.n_rows) ? a.t_rows[idx] : te_none;
-                } while ((dir > 0.0) ? (te <= t_new) : (te >= t_new));
-            }
-            __syncwarp();
-        } else if (hit) {
-            double c1[N], c2[N], c3[N];
-#pragma unroll
-            for (int c = 0; c < N; c++) {  // ordinary.rs:196-207
-                c1[c] = ynew[c] - y[c];
-                c2[c] = __dadd_rn(0.0, h * k[0][c]) - c1[c];
-                c3[c] = (c1[c] + (-h) * dydt[c]) - c2[c];
-            }
-            double ch[(O > 4) ? (O - 4) : 1][N];  // cont[4..O-1]
-            {
-                // extra dense stages, ordinary.rs:210-225: k[S] = dydt, stages S+1..I-1
-                double kx[(I > S) ? (I - S) : 1][N];
-#pragma unroll
-                for (int c = 0; c < N; c++) kx[0][c] = dydt[c];
-#pragma unroll
-                for (int i = S + 1; i < I; i++) {
-                    double ys[N];
-#pragma unroll
-                    for (int c = 0; c < N; c++) ys[c] = y[c];
-#pragma unroll
-                    for (int j = 0; j < i; j++) {
-                        if (Tab::a(i, j) != 0.0) {
-                            const double ah = Tab::av(i, j) * h;
-#pragma unroll
-                            for (int c = 0; c < N; c++) ys[c] = ys[c] + ah * ((j < S) ? k[j][c] : kx[j - S][c]);
-                        }
-                    }
-                    Sys::rhs(t + Tab::cv(i) * h, ys, kx[i - S], p);
-                }
-#pragma unroll
-                for (int i = 4; i < O; i++) {  // ordinary.rs:228-234
-#pragma unroll
-                    for (int c = 0; c < N; c++) ch[i - 4][c] = 0.0;
-#pragma unroll
-                    for (int j = 0; j < I; j++) {
-                        if (Tab::bi(i, j) != 0.0) {
-#pragma unroll
-                            for (int c = 0; c < N; c++)
-                                ch[i - 4][c] = __dadd_rn(ch[i - 4][c], Tab::biv(i, j) * ((j < S) ? k[j][c] : kx[j - S][c]));
-                        }
-                    }
-#pragma unroll
-                    for (int c = 0; c < N; c++) ch[i - 4][c] = ch[i - 4][c] * h;
-                }
-            }
-            do {
-                double row[N];
-                if (te == t_new) {  // exact hit: the solver state itself (t_eval.rs:113-114)
-#pragma unroll
-                    for (int c = 0; c < N; c++) row[c] = ynew[c];
-                } else {  // interpolate, ordinary.rs:301-337, factor order as written
-                    const double sx = (te - t) / h;
-                    const double s1 = 1.0 - sx;
-#pragma unroll
-                    for (int c = 0; c < N; c++) {
-                        double accp = (O > 4) ? ch[O - 5][c] : c3[c];
-#pragma unroll
-                        for (int i = O - 2; i >= 1; i--) {
-                            double factor;
-                            if (i >= 4) factor = (((O - 1) - i) % 2 == 1) ? s1 : sx;
-                            else factor = (i % 2 == 1) ? s1 : sx;
-                            const double ci = (i >= 4) ? ch[(i >= 4) ? (i - 4) : 0][c] : (i == 3 ? c3[c] : (i == 2 ? c2[c] : c1[c]));
-                            accp = accp * factor + ci;
-                        }
-                        row[c] = y[c] + sx * accp;
-                    }
-                }
-                if (want_rows) {
-                    double* dst = a.y_eval + ((size_t)traj * a.row_stride + idx) * N;
-#pragma unroll
-                    for (int c = 0; c < N; c++) dst[c] = row[c];
-                }
-                idx += 1;
-                te = (idx < a.n_rows) ? a.t_rows[idx] : te_none;
-            } while ((dir > 0.0) ? (te <= t_new) : (te >= t_new));
-        }
-        __syncwarp();
 
-        // ---- accept: shift (ordinary.rs:237-254) / reject (ordinary.rs:255-258), as predicated updates
-        if (commit) {
-            h_prev = h;
-            t = t_new;
+            // ---- accept: shift (ordinary.rs:237-254) / reject (ordinary.rs:255-258), as predicated updates
+            const bool commit = accept && fin < 0 && !blocked;
+            const bool reject = stepping && fin < 0 && !accept;
+            if (commit) {
+                h_prev = h;
+                t = t_new;
 #pragma unroll
-            for (int c = 0; c < N; c++) { y[c] = ynew[c]; k[0][c] = dydt[c]; }
-            if (rejected_prev) scale = fmin(scale, 1.0);
-            rejected_prev = false;
-            acc += 1;
-        } else if (stepping && fin < 0) {
-            rejected_prev = true;  // Status::RejectedStep
-            rej += 1;
-        }
-        if (stepping && fin < 0) {
-            // ---- step-size update, ordinary.rs:261-267 (filter = identity)
-            h = h * scale;
-            h = constrain_step_size(h, a.h_min, a.h_max);
-            // accepted: end-of-interval test, solve_ivp.rs:263
-            if (commit && fabs(tf - t) <= eps10) fin = DEB_STATUS_COMPLETE;
-        }
-        // ---------------- trajectory end: a lane first becomes `finishing` (it stops stepping); one iteration later,
-        // when its parked rows have been flushed, it writes the Solution / Error fields and asks for new work
-        if (active && finishing) {
-            if (a.status) a.status[traj] = fin_status;
-            if (a.t_final) a.t_final[traj] = t;
-            if (a.y_final) {
-#pragma unroll
-                for (int c = 0; c < N; c++) a.y_final[traj * N + c] = y[c];
+                for (int c = 0; c < N; c++) { y[c] = ynew[c]; k[0][c] = dydt[c]; }
+                if (rejected_prev) scale = (scale <= 1.0) ? scale : 1.0;  // scale.min(1), scale is not NaN here
+                rejected_prev = false;
+                acc += 1;
             }
-            if (a.accepted) a.accepted[traj] = acc;
-            if (a.rejected) a.rejected[traj] = rej;
-            // Evals.function: 1 (+2 for the automatic h0) + (S-1) per attempt + 1 (+ I-S-1 dense stages) per accepted step
-            if (a.evals) a.evals[traj] = evals_base + (S - 1) * (acc + rej) + acc * (1 + ((I > S) ? (I - S - 1) : 0));
-            if (a.n_emitted) a.n_emitted[traj] = idx;
-            active = false;
-            finishing = false;
-            // idle dummy state: finite, never committed
-            t = t0; h = 0.0; h_prev = 0.0; te = te_none;
-#pragma unroll
-            for (int c = 0; c < N; c++) { y[c] = 1.0; k[0][c] = 0.0; }
-        } else if (active && fin >= 0) {
-            finishing = true;
-            fin_status = fin;
-        }
-        __syncwarp();
+            if (reject) {
+                rejected_prev = true;  // Status::RejectedStep
+                rej += 1;
+            }
+            if (commit || reject) {
+                // ---- step-size update, ordinary.rs:261-267 (filter = identity)
+                h = h * scale;
+                if (bounded_h) h = constrain_step_size(h, a.h_min, a.h_max);  // identity for h_min = 0, h_max = inf
+                // accepted: end-of-interval test, solve_ivp.rs:263
+                if (commit && fabs(tf - t) <= eps10) fin = DEB_STATUS_COMPLETE;
+            }
+            service = (active && fin >= 0) || blocked;
+        } while (!__any_sync(FULL, service));
     }
 }
 
