@@ -91,7 +91,7 @@ class HeatProblem(C.Structure):
 
 
 # every symbol include/deb_ensemble.h declares (tests check that the library exports all of them)
-ABI_SYMBOLS = ["deb_abi_version", "deb_last_error", "deb_device_count", "deb_erk_options_default", "deb_solve_ode",
+ABI_SYMBOLS = ["deb_abi_version", "deb_last_error", "deb_device_count", "deb_erk_options_default", "deb_define_ode", "deb_solve_ode",
                "deb_solve_sde", "deb_solve_heat_mol", "deb_heat_rhs", "deb_ensemble_stats", "deb_malloc", "deb_free", "deb_memcpy_h2d",
                "deb_memcpy_d2h", "deb_synchronize", "deb_pow_device", "deb_fp64_issue_peak"]
 
@@ -116,6 +116,7 @@ def load_library() -> C.CDLL:
     lib.deb_solve_ode.argtypes = [C.POINTER(OdeProblem), C.POINTER(Result)]
     lib.deb_solve_sde.argtypes = [C.POINTER(SdeProblem), C.POINTER(Result)]
     lib.deb_solve_heat_mol.argtypes = [C.POINTER(HeatProblem)]
+    lib.deb_define_ode.argtypes = [C.c_int32, C.c_int32, C.c_char_p, _ip]
     lib.deb_heat_rhs.argtypes = [C.POINTER(HeatProblem), C.c_void_p, C.c_void_p]
     lib.deb_erk_options_default.argtypes = [C.POINTER(ErkOptions)]
     lib.deb_erk_options_default.restype = None
@@ -209,6 +210,19 @@ def VanDerPolOscillator(mu): return OdeSystem(DEB_SYS_VAN_DER_POL, 2, _params(mu
 def LorenzSystem(sigma, rho, beta): return OdeSystem(DEB_SYS_LORENZ, 3, _params(sigma, rho, beta))  # :85-101
 def BrusselatorSystem(a, b): return OdeSystem(DEB_SYS_BRUSSELATOR, 2, _params(a, b))       # :106-120
 def RobertsonProblem(): return OdeSystem(DEB_SYS_ROBERTSON, 3, np.zeros(0))                  # :161-173
+
+
+def ode_from_source(dim: int, diff_body: str, params=(), lib=None) -> OdeSystem:
+    """`IVP::ode_from_fn(|t, y, dydt| ..)` (src/ivp.rs:291-317) for the device: the body of
+    `void diff(double t, const double* y, double* dydt, const double* p)` as CUDA C++ text, compiled at first use
+    (NVRTC).  `params`: one parameter set, or an (N, n_params) array for a sweep."""
+    lib = lib or load_library()
+    prm = np.ascontiguousarray(params, dtype=np.float64)
+    if prm.ndim == 0:
+        prm = prm.reshape(1)
+    sid = C.c_int32(-1)
+    _check(lib, lib.deb_define_ode(int(dim), int(prm.shape[-1]), diff_body.encode(), C.byref(sid)), "deb_define_ode")
+    return OdeSystem(sid.value, int(dim), prm)
 
 
 @dataclass

@@ -4,12 +4,17 @@
 // t_eval like TEvalSolout::new (/root/reference/src/solout/t_eval.rs:154-171), stages buffers, picks the kernel
 // instantiation for (system, method) and launches it.  There is no CPU fallback anywhere in this file.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <functional>
+#include <map>
+#include <memory>
 #include <chrono>
 #include <mutex>
 #include <string>
@@ -180,6 +185,171 @@ sde_launch_fn pick_sde_method(int method) {
     return nullptr;
 }
 
+// ------------------------------------------------------------------------------------------------ user systems (NVRTC)
+// A Rust `impl ODE for MySystem { fn diff(&self, t, y, dydt) }` (/root/reference/src/ode/ode.rs:20-44) cannot cross to
+// the device as a closure.  The device-side equivalent: the caller hands over the BODY of diff as CUDA C++ text
+// (deb_define_ode); the same kernel templates that serve the built-in systems are instantiated for it with NVRTC
+// (sm_100a, --fmad=false) the first time a method is used, and cached.
+#include "embedded_sources.inc"
+
+struct NvrtcApi {
+    void* handle = nullptr;
+    nvrtcResult (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+    nvrtcResult (*DestroyProgram)(nvrtcProgram*) = nullptr;
+    nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char* const*) = nullptr;
+    nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
+    nvrtcResult (*GetProgramLog)(nvrtcProgram, char*) = nullptr;
+    nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t*) = nullptr;
+    nvrtcResult (*GetCUBIN)(nvrtcProgram, char*) = nullptr;
+    nvrtcResult (*AddNameExpression)(nvrtcProgram, const char*) = nullptr;
+    nvrtcResult (*GetLoweredName)(nvrtcProgram, const char*, const char**) = nullptr;
+    const char* (*GetErrorString)(nvrtcResult) = nullptr;
+};
+
+const NvrtcApi* nvrtc_api() {
+    static NvrtcApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so"};
+        for (const char* n : names) {
+            api.handle = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+            if (api.handle) break;
+        }
+        if (!api.handle) return;
+#define DEB_SYM(field, sym) *(void**)(&api.field) = dlsym(api.handle, sym)
+        DEB_SYM(CreateProgram, "nvrtcCreateProgram");
+        DEB_SYM(DestroyProgram, "nvrtcDestroyProgram");
+        DEB_SYM(CompileProgram, "nvrtcCompileProgram");
+        DEB_SYM(GetProgramLogSize, "nvrtcGetProgramLogSize");
+        DEB_SYM(GetProgramLog, "nvrtcGetProgramLog");
+        DEB_SYM(GetCUBINSize, "nvrtcGetCUBINSize");
+        DEB_SYM(GetCUBIN, "nvrtcGetCUBIN");
+        DEB_SYM(AddNameExpression, "nvrtcAddNameExpression");
+        DEB_SYM(GetLoweredName, "nvrtcGetLoweredName");
+        DEB_SYM(GetErrorString, "nvrtcGetErrorString");
+#undef DEB_SYM
+        if (!api.CreateProgram || !api.CompileProgram || !api.GetCUBIN || !api.GetLoweredName) {
+            dlclose(api.handle);
+            api.handle = nullptr;
+        }
+    });
+    return api.handle ? &api : nullptr;
+}
+
+struct UserKernel {
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t kernel = nullptr;
+    bool adaptive = false;
+    int block = 128;
+};
+struct UserSystem {
+    int dim = 0, np = 0;
+    std::string body;
+    std::map<std::pair<int, int>, UserKernel> kernels;  // (device, method) -> compiled kernel
+};
+std::mutex g_user_mu;
+std::vector<std::unique_ptr<UserSystem>> g_user_systems;
+const int USER_SYSTEM_BASE = 1000;
+
+const char* method_tab_name(int method, bool* adaptive) {
+    *adaptive = false;
+    switch (method) {
+        case DEB_DOPRI5: *adaptive = true; return "deb::TabDopri5";
+        case DEB_DOP853: *adaptive = true; return "deb::TabDop853";
+        case DEB_EULER: return "deb::TabEuler";
+        case DEB_MIDPOINT: return "deb::TabMidpoint";
+        case DEB_HEUN: return "deb::TabHeun";
+        case DEB_RALSTON: return "deb::TabRalston";
+        case DEB_SSP_RK3: return "deb::TabSspRk3";
+        case DEB_RK4: return "deb::TabRk4";
+        case DEB_THREE_EIGHTHS: return "deb::TabThreeEighths";
+    }
+    return nullptr;
+}
+
+// Compile (once per device/method) the ensemble kernel for a user system.  Caller holds g_user_mu.
+int user_kernel(UserSystem& us, int device, int method, UserKernel** out) {
+    auto it = us.kernels.find({device, method});
+    if (it != us.kernels.end()) { *out = &it->second; return DEB_OK; }
+    bool adaptive = false;
+    const char* tab = method_tab_name(method, &adaptive);
+    if (!tab) return fail(DEB_ERR_UNSUPPORTED, "unknown or unsupported method id");
+    const NvrtcApi* rt = nvrtc_api();
+    if (!rt) return fail(DEB_ERR_UNSUPPORTED, "libnvrtc not found: user-defined systems need the NVRTC runtime compiler");
+    // occupancy hint: stage vectors live in registers, wider systems get the whole register file of fewer CTAs
+    const int min_blocks = adaptive ? (us.dim <= 3 ? (method == DEB_DOPRI5 ? 4 : 2) : (us.dim <= 6 ? 2 : 1)) : 1;
+    char expr[256];
+    if (adaptive) snprintf(expr, sizeof expr, "deb::dp_ensemble_kernel<deb::UserSys, %s, 128, %d, false>", tab, min_blocks);
+    else snprintf(expr, sizeof expr, "deb::fixed_ensemble_kernel<deb::UserSys, %s, 128>", tab);
+    std::string src;
+    src += "#include \"erk_fixed.cuh\"\n";
+    src += "namespace deb {\nstruct UserSys {\n";
+    src += "    static constexpr int DIM = " + std::to_string(us.dim) + ", NP = " + std::to_string(us.np) + ";\n";
+    src += "    __device__ __forceinline__ static void rhs(double t, const double* y, double* dydt, const double* p) {\n";
+    src += "        (void)t; (void)y; (void)p;\n";
+    src += us.body;
+    src += "\n    }\n};\n}  // namespace deb\n";
+    // headers: the embedded kernel sources + minimal stand-ins for the C headers NVRTC does not ship
+    std::vector<const char*> hdr_names, hdr_text;
+    for (const auto& e : deb_embedded_sources) { hdr_names.push_back(e.name); hdr_text.push_back(e.text); }
+    static const char* k_stdint =
+        "#pragma once\ntypedef signed char int8_t; typedef unsigned char uint8_t; typedef short int16_t; typedef unsigned short uint16_t;\n"
+        "typedef int int32_t; typedef unsigned int uint32_t; typedef long long int64_t; typedef unsigned long long uint64_t;\n";
+    static const char* k_float = "#pragma once\n#define DBL_EPSILON 2.2204460492503131e-16\n";
+    static const char* k_abi =
+        "#pragma once\n#define DEB_MAX_DIM 16\n"
+        "enum { DEB_STATUS_COMPLETE = 0, DEB_STATUS_MAX_STEPS = 1, DEB_STATUS_STEP_SIZE = 2, DEB_STATUS_STIFFNESS = 3, DEB_STATUS_BAD_INPUT = 4 };\n";
+    hdr_names.push_back("stdint.h"); hdr_text.push_back(k_stdint);
+    hdr_names.push_back("float.h"); hdr_text.push_back(k_float);
+    hdr_names.push_back("../../include/deb_ensemble.h"); hdr_text.push_back(k_abi);
+    nvrtcProgram prog = nullptr;
+    nvrtcResult r = rt->CreateProgram(&prog, src.c_str(), "deb_user_system.cu", (int)hdr_names.size(), hdr_text.data(), hdr_names.data());
+    if (r != NVRTC_SUCCESS) return fail(DEB_ERR_CUDA, std::string("nvrtcCreateProgram: ") + rt->GetErrorString(r));
+    struct ProgGuard { const NvrtcApi* rt; nvrtcProgram* p; ~ProgGuard() { if (*p) rt->DestroyProgram(p); } } guard{rt, &prog};
+    rt->AddNameExpression(prog, expr);
+    const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "--fmad=false", "-lineinfo"};
+    r = rt->CompileProgram(prog, 4, opts);
+    if (r != NVRTC_SUCCESS) {
+        size_t n = 0;
+        rt->GetProgramLogSize(prog, &n);
+        std::string log(n, '\0');
+        if (n) rt->GetProgramLog(prog, &log[0]);
+        return fail(DEB_ERR_BAD_ARG, "the right-hand side did not compile (NVRTC):\n" + log);
+    }
+    const char* lowered = nullptr;
+    r = rt->GetLoweredName(prog, expr, &lowered);
+    if (r != NVRTC_SUCCESS || !lowered) return fail(DEB_ERR_CUDA, "nvrtcGetLoweredName failed");
+    size_t nbin = 0;
+    rt->GetCUBINSize(prog, &nbin);
+    std::vector<char> cubin(nbin);
+    if (rt->GetCUBIN(prog, cubin.data()) != NVRTC_SUCCESS) return fail(DEB_ERR_CUDA, "nvrtcGetCUBIN failed");
+    UserKernel uk;
+    uk.adaptive = adaptive;
+    DEB_CUDA(cudaLibraryLoadData(&uk.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+    DEB_CUDA(cudaLibraryGetKernel(&uk.kernel, uk.lib, lowered));
+    auto ins = us.kernels.emplace(std::make_pair(device, method), uk);
+    *out = &ins.first->second;
+    return DEB_OK;
+}
+
+int launch_user(const UserKernel& uk, const deb::OdeKernelArgs& a, int sms, cudaStream_t st) {
+    long long blocks;
+    if (uk.adaptive) {
+        int per_sm = 0;
+        DEB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)uk.kernel, uk.block, 0));
+        if (per_sm < 1) per_sm = 1;
+        blocks = (long long)sms * per_sm;
+    } else {
+        blocks = (long long)sms * 16 * 8;
+    }
+    const long long need = (a.n_traj + uk.block - 1) / uk.block;
+    if (blocks > need) blocks = need;
+    if (blocks < 1) blocks = 1;
+    void* args[] = {(void*)&a};
+    DEB_CUDA(cudaLaunchKernel((const void*)uk.kernel, dim3((unsigned)blocks), dim3(uk.block), args, 0, st));
+    return DEB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ t_eval plan
 // TEvalSolout::new sorts the points by direction (stable; t_eval.rs:154-171).  The solout call that precedes the
 // loop (solve_ivp.rs:160) consumes every point that is not after t0: the first one is emitted iff it equals t0,
@@ -303,9 +473,23 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P, deb_result* R) {
     if (P->struct_size != sizeof(deb_ode_problem) || R->struct_size != sizeof(deb_result))
         return fail(DEB_ERR_BAD_ARG, "struct_size mismatch (ABI version skew)");
     int dim = 0, np = 0;
-    ode_launch_fn launch = pick_ode(P->system, P->method, &dim, &np);
-    if (dim < 0) return fail(DEB_ERR_BAD_ARG, "unknown system id");
-    if (!launch) return fail(DEB_ERR_UNSUPPORTED, "unknown or unsupported method id");
+    std::function<int(const deb::OdeKernelArgs&, int, cudaStream_t)> launch;
+    UserSystem* user = nullptr;
+    if (P->system >= USER_SYSTEM_BASE) {
+        std::lock_guard<std::mutex> lk(g_user_mu);
+        const size_t k = (size_t)(P->system - USER_SYSTEM_BASE);
+        if (k >= g_user_systems.size()) return fail(DEB_ERR_BAD_ARG, "unknown system id");
+        user = g_user_systems[k].get();
+        dim = user->dim;
+        np = user->np;
+        bool adaptive;
+        if (!method_tab_name(P->method, &adaptive)) return fail(DEB_ERR_UNSUPPORTED, "unknown or unsupported method id");
+    } else {
+        ode_launch_fn builtin = pick_ode(P->system, P->method, &dim, &np);
+        if (dim < 0) return fail(DEB_ERR_BAD_ARG, "unknown system id");
+        if (!builtin) return fail(DEB_ERR_UNSUPPORTED, "unknown or unsupported method id");
+        launch = builtin;
+    }
     if (P->dim != dim || P->n_params != np) return fail(DEB_ERR_BAD_ARG, "dim / n_params do not match the system");
     if (P->n_traj < 0) return fail(DEB_ERR_BAD_ARG, "n_traj < 0");
     if (P->n_traj > 0 && (!P->y0 || (np > 0 && !P->params))) return fail(DEB_ERR_BAD_ARG, "NULL y0/params");
@@ -320,16 +504,29 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P, deb_result* R) {
     if (int rc = select_device(P->device)) return rc;
     DeviceInfo di;
     if (int rc = device_info(P->device, &di)) return rc;
+    if (user) {  // user-defined right-hand side: compile (first use) and bind the run-time kernel
+        std::lock_guard<std::mutex> lk(g_user_mu);
+        UserKernel* uk = nullptr;
+        if (int rc = user_kernel(*user, P->device, P->method, &uk)) return rc;
+        const UserKernel ukc = *uk;
+        launch = [ukc](const deb::OdeKernelArgs& ka, int sms, cudaStream_t s2) { return launch_user(ukc, ka, sms, s2); };
+    }
     const bool host = (P->memspace == DEB_MEM_HOST);
     const long long n = P->n_traj;
 
     // ---- kernel arguments common to every launch of this call
     deb::OdeKernelArgs a;
     memset(&a, 0, sizeof a);
+    DevBuf d_shared_params;  // user kernels are built with SHARED_P = false: a shared set is read through the pointer (stride 0)
     if (np > 0 && P->params_shared) {
         // one parameter set for the whole ensemble: HOST memory by contract, passed by value (constant bank)
         for (int q = 0; q < np && q < 8; q++) a.pc[q] = P->params[q];
+        if (user || np > 8) {
+            DEB_CUDA(d_shared_params.alloc(sizeof(double) * np));
+            DEB_CUDA(cudaMemcpy(d_shared_params.p, P->params, sizeof(double) * np, cudaMemcpyHostToDevice));
+        }
     }
+    const double* shared_params_dev = d_shared_params.as<double>();
     a.params_stride = P->params_shared ? 0 : np;
     a.t0 = P->t0;
     a.tf = P->tf;
@@ -361,7 +558,7 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P, deb_result* R) {
         a.queue = (unsigned long long*)d_small;
         a.t_rows = (const double*)((char*)d_small + 8);
         a.y0 = P->y0;
-        a.params = per_traj_params ? P->params : nullptr;
+        a.params = per_traj_params ? P->params : shared_params_dev;
         a.n_traj = n;
         a.y_eval = R->y_eval; a.n_emitted = R->n_emitted; a.t_final = R->t_final; a.y_final = R->y_final;
         a.status = R->status; a.accepted = R->accepted; a.rejected = R->rejected; a.evals = R->evals;
@@ -431,7 +628,7 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P, deb_result* R) {
         ac.queue = (unsigned long long*)S.small.p;
         ac.t_rows = (const double*)((char*)S.small.p + 8);
         ac.y0 = S.y0.as<double>();
-        ac.params = per_traj_params ? S.params.as<double>() : nullptr;
+        ac.params = per_traj_params ? S.params.as<double>() : shared_params_dev;
         ac.n_traj = cnt;
         ac.y_eval = S.y_eval.as<double>(); ac.n_emitted = S.n_emitted.as<int>(); ac.t_final = S.t_final.as<double>();
         ac.y_final = S.y_final.as<double>(); ac.status = S.status.as<int>(); ac.accepted = S.accepted.as<int>();
@@ -463,6 +660,20 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P, deb_result* R) {
     }
     R->kernel_ms = kernel_ms;  // sum over chunks (chunks on the two streams overlap: can exceed the wall time)
     R->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+    return DEB_OK;
+}
+
+extern "C" int deb_define_ode(int32_t dim, int32_t n_params, const char* diff_body, int32_t* system_id) {
+    if (!diff_body || !system_id) return fail(DEB_ERR_BAD_ARG, "NULL argument");
+    if (dim < 1 || dim > DEB_MAX_DIM) return fail(DEB_ERR_BAD_ARG, "dim must be in 1..DEB_MAX_DIM");
+    if (n_params < 0 || n_params > 64) return fail(DEB_ERR_BAD_ARG, "n_params must be in 0..64");
+    std::lock_guard<std::mutex> lk(g_user_mu);
+    std::unique_ptr<UserSystem> us(new UserSystem);
+    us->dim = dim;
+    us->np = n_params;
+    us->body = diff_body;
+    g_user_systems.push_back(std::move(us));
+    *system_id = USER_SYSTEM_BASE + (int32_t)g_user_systems.size() - 1;
     return DEB_OK;
 }
 

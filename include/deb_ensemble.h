@@ -212,6 +212,15 @@ int deb_device_count(void);
 /* Fill with the reference defaults (erk/mod.rs:135-144). */
 void deb_erk_options_default(deb_erk_options* opt);
 
+/* User-defined right-hand side: the device-side equivalent of `impl ODE for S { fn diff(&self, t, y, dydt) }`
+ * (src/ode/ode.rs:20-44).  `diff_body` is the BODY of
+ *     void diff(double t, const double* y, double* dydt, const double* p)
+ * as CUDA C++ text (p = the trajectory's parameters; write every dydt[0..dim)).  It is compiled at first use with
+ * NVRTC for sm_100a with --fmad=false (a*b+c stays two roundings, like Rust) into the same kernel templates that
+ * serve the built-in systems, and cached.  Returns a system id (>= 1000) to put in deb_ode_problem.system.
+ * A body that does not compile makes the first deb_solve_ode return DEB_ERR_BAD_ARG with the compiler log. */
+int deb_define_ode(int32_t dim, int32_t n_params, const char* diff_body, int32_t* system_id);
+
 int deb_solve_ode(const deb_ode_problem* problem, deb_result* result);
 int deb_solve_sde(const deb_sde_problem* problem, deb_result* result);
 int deb_solve_heat_mol(const deb_heat_problem* problem);

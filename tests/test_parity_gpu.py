@@ -372,3 +372,85 @@ def test_host_path_chunk_pipeline_is_transparent(monkeypatch):
     m = np.arange(7)[None, :] < one.n_emitted[:, None]
     assert np.array_equal(bits(one.y_eval)[m], bits(many.y_eval)[m])
     assert_same_solution(many, ob.oracle_solve(prob()))
+
+
+# ------------------------------------------------------------------------------------------ user-defined RHS (NVRTC)
+LORENZ_SRC = """
+    const double x = y[0], yv = y[1], z = y[2];
+    dydt[0] = p[0] * (yv - x);
+    dydt[1] = x * (p[1] - z) - yv;
+    dydt[2] = x * yv - p[2] * z;
+"""
+# tests/ode/systems.rs:122-158 (powi(2) = x*x, powi(3) = x*x*x)
+CR3BP_SRC = """
+    const double mu = p[0];
+    const double rx = y[0], ry = y[1], rz = y[2], vx = y[3], vy = y[4], vz = y[5];
+    const double a1 = rx + mu, a2 = rx - 1.0 + mu;
+    const double r13 = sqrt(a1 * a1 + ry * ry + rz * rz);
+    const double r23 = sqrt(a2 * a2 + ry * ry + rz * rz);
+    const double r13c = r13 * r13 * r13, r23c = r23 * r23 * r23;
+    dydt[0] = vx;
+    dydt[1] = vy;
+    dydt[2] = vz;
+    dydt[3] = rx + 2.0 * vy - (1.0 - mu) * (rx + mu) / r13c - mu * (rx - 1.0 + mu) / r23c;
+    dydt[4] = ry - 2.0 * vx - (1.0 - mu) * ry / r13c - mu * ry / r23c;
+    dydt[5] = -(1.0 - mu) * rz / r13c - mu * rz / r23c;
+"""
+
+
+def cr3bp_py(mu):
+    import math
+    def f(t, y):
+        rx, ry, rz, vx, vy, vz = y
+        a1, a2 = rx + mu, rx - 1.0 + mu
+        r13 = math.sqrt(a1 * a1 + ry * ry + rz * rz)
+        r23 = math.sqrt(a2 * a2 + ry * ry + rz * rz)
+        r13c, r23c = r13 * r13 * r13, r23 * r23 * r23
+        return [vx, vy, vz,
+                rx + 2.0 * vy - (1.0 - mu) * (rx + mu) / r13c - mu * (rx - 1.0 + mu) / r23c,
+                ry - 2.0 * vx - (1.0 - mu) * ry / r13c - mu * ry / r23c,
+                -(1.0 - mu) * rz / r13c - mu * rz / r23c]
+    return f
+
+
+def test_user_defined_rhs_equals_builtin_bitwise():
+    """deb_define_ode: the Lorenz system written as source text goes through the same kernel template (compiled by NVRTC)
+    and must reproduce the built-in system -- hence the oracle -- bit for bit, for adaptive and fixed-step methods,
+    shared and per-trajectory parameters."""
+    y0 = ob.lorenz_ensemble_y0(3000, seed=21)
+    te = np.linspace(0.0, 8.0, 17)
+    user = deb.ode_from_source(3, LORENZ_SRC, [10.0, 28.0, 8.0 / 3.0])
+    for m in (lambda: E.dopri5().rtol(1e-8), lambda: E.dop853().rtol(1e-9).atol(1e-9), lambda: E.rk4(0.005)):
+        u = deb.EnsembleIVP.ode(user, 0.0, 8.0, y0).t_eval(te).method(m()).solve()
+        b = deb.EnsembleIVP.ode(lorenz(), 0.0, 8.0, y0).t_eval(te).method(m()).solve()
+        assert_same_solution(u, b)
+    rho = np.linspace(20.0, 35.0, 3000)
+    prm = np.stack([np.full(3000, 10.0), rho, np.full(3000, 8.0 / 3.0)], axis=1)
+    u = deb.EnsembleIVP.ode(deb.ode_from_source(3, LORENZ_SRC, prm), 0.0, 5.0, y0).t_eval(te).method(E.dopri5().rtol(1e-8)).solve()
+    c = ob.oracle_solve(deb.EnsembleIVP.ode(deb.LorenzSystem(10.0, rho, 8.0 / 3.0), 0.0, 5.0, y0).t_eval(te).method(E.dopri5().rtol(1e-8)))
+    assert_same_solution(u, c)
+
+
+def test_user_defined_six_dimensional_system_vs_python_restatement():
+    """A system that is NOT built in (CR3BP, dim 6, tests/ode/systems.rs:122-158), against the independent pure-Python
+    restatement of the DOPRI5 / DOP853 loops: bitwise states, dense rows and counters."""
+    import py_restatement as pr
+    mu = 0.012150585609624
+    y0 = np.array([1.021881345465263, 0.0, -0.182000000000000, 0.0, -0.102950816739606, 0.0])
+    y0s = y0[None, :] + ob.splitmix64_uniform(8, 6 * 40).reshape(40, 6) * 1e-3
+    te = [0.5, 1.0, 1.5110806241094467]
+    user = deb.ode_from_source(6, CR3BP_SRC, [mu])
+    for meth in ("dopri5", "dop853"):
+        g = deb.EnsembleIVP.ode(user, 0.0, 1.5110806241094467, y0s).t_eval(te).method(getattr(E, meth)().rtol(1e-9).atol(1e-9)).solve()
+        assert (g.status == 0).all()
+        for i in (0, 7, 39):
+            p = pr.solve_dp(cr3bp_py(mu), meth, 0.0, 1.5110806241094467, list(y0s[i]), rtol=1e-9, atol=1e-9, t_eval=te)
+            assert (p["accepted"], p["rejected"], p["evals"]) == (int(g.accepted[i]), int(g.rejected[i]), int(g.evals[i]))
+            assert np.array_equal(bits(p["y"]), bits(g.y_final[i]))
+            assert np.array_equal(bits([r[1] for r in p["rows"]]), bits(g.y_eval[i, :len(p["rows"])]))
+
+
+def test_user_defined_rhs_compile_error_is_reported():
+    bad = deb.ode_from_source(1, "dydt[0] = undefined_symbol * y[0];", [1.0])
+    with pytest.raises(ValueError, match="did not compile"):
+        deb.EnsembleIVP.ode(bad, 0.0, 1.0, [[1.0]]).method(E.dopri5()).solve()
