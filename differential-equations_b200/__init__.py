@@ -40,14 +40,14 @@ LIB_PATH = os.path.join(_HERE, "libdeb200.so")
 
 # ---------------------------------------------------------------------------------------------- enums (deb_ensemble.h)
 DEB_EULER, DEB_MIDPOINT, DEB_HEUN, DEB_RALSTON, DEB_SSP_RK3, DEB_RK4, DEB_THREE_EIGHTHS = range(7)
-DEB_DOPRI5, DEB_DOP853 = 16, 17
+DEB_DOPRI5, DEB_DOP853, DEB_RKF45, DEB_CASH_KARP = 16, 17, 18, 19
 (DEB_SYS_EXPONENTIAL, DEB_SYS_LINEAR, DEB_SYS_HARMONIC, DEB_SYS_LOGISTIC, DEB_SYS_VAN_DER_POL, DEB_SYS_LORENZ,
  DEB_SYS_BRUSSELATOR, DEB_SYS_ROBERTSON) = range(8)
 DEB_SDE_OU, DEB_SDE_GBM = 0, 1
 DEB_STATUS_COMPLETE, DEB_STATUS_MAX_STEPS, DEB_STATUS_STEP_SIZE, DEB_STATUS_STIFFNESS, DEB_STATUS_BAD_INPUT = range(5)
 DEB_MEM_HOST, DEB_MEM_DEVICE = 0, 1
 DEB_OK, DEB_ERR_BAD_ARG, DEB_ERR_NO_DEVICE, DEB_ERR_CUDA, DEB_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
-DEB_ABI_VERSION = 1
+DEB_ABI_VERSION = 2
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -56,7 +56,7 @@ _ip = C.POINTER(C.c_int32)
 class ErkOptions(C.Structure):
     _fields_ = [("rtol", C.c_double), ("atol", C.c_double), ("rtol_vec", _dp), ("atol_vec", _dp), ("h0", C.c_double),
                 ("h_min", C.c_double), ("h_max", C.c_double), ("max_steps", C.c_int64), ("safety_factor", C.c_double),
-                ("min_scale", C.c_double), ("max_scale", C.c_double)]
+                ("min_scale", C.c_double), ("max_scale", C.c_double), ("max_rejects", C.c_int64)]
 
 
 class OdeProblem(C.Structure):
@@ -258,7 +258,7 @@ class ExplicitRungeKutta:
         self._h_min = 0.0
         self._h_max = math.inf
         self._max_steps = 10_000
-        self._max_rejects = 100  # accepted for API parity; the Dormand-Prince stepper never reads it
+        self._max_rejects = 100  # read by the adaptive family (rkf45, cash_karp) only
         self._safety_factor = 0.9
         self._min_scale = 0.2
         self._max_scale = 10.0
@@ -268,6 +268,10 @@ class ExplicitRungeKutta:
     def dopri5(cls): return cls(DEB_DOPRI5)
     @classmethod
     def dop853(cls): return cls(DEB_DOP853)
+    @classmethod
+    def rkf45(cls): return cls(DEB_RKF45)          # adaptive/mod.rs:47-53
+    @classmethod
+    def cash_karp(cls): return cls(DEB_CASH_KARP)  # adaptive/mod.rs:54-60
     @classmethod
     def euler(cls, h0): return cls(DEB_EULER, h0)
     @classmethod
@@ -308,6 +312,7 @@ class ExplicitRungeKutta:
         opt.h0, opt.h_min, opt.h_max = self._h0, self._h_min, self._h_max
         opt.max_steps = self._max_steps
         opt.safety_factor, opt.min_scale, opt.max_scale = self._safety_factor, self._min_scale, self._max_scale
+        opt.max_rejects = self._max_rejects
 
 
 # ---------------------------------------------------------------------------------------------- results

@@ -130,6 +130,8 @@ ode_launch_fn pick_ode_method(int method) {
     switch (method) {
         case DEB_DOPRI5: return launch_dp<Sys, deb::TabDopri5, 128, 5>;  // 96 regs, no spills, 20 warps/SM (sweep: profiles/)
         case DEB_DOP853: return launch_dp<Sys, deb::TabDop853, 128, 2>;
+        case DEB_RKF45: return launch_dp<Sys, deb::TabRkf45, 128, 4>;
+        case DEB_CASH_KARP: return launch_dp<Sys, deb::TabCashKarp, 128, 4>;
         case DEB_EULER: return launch_fixed<Sys, deb::TabEuler>;
         case DEB_MIDPOINT: return launch_fixed<Sys, deb::TabMidpoint>;
         case DEB_HEUN: return launch_fixed<Sys, deb::TabHeun>;
@@ -256,6 +258,8 @@ const char* method_tab_name(int method, bool* adaptive) {
     switch (method) {
         case DEB_DOPRI5: *adaptive = true; return "deb::TabDopri5";
         case DEB_DOP853: *adaptive = true; return "deb::TabDop853";
+        case DEB_RKF45: *adaptive = true; return "deb::TabRkf45";
+        case DEB_CASH_KARP: *adaptive = true; return "deb::TabCashKarp";
         case DEB_EULER: return "deb::TabEuler";
         case DEB_MIDPOINT: return "deb::TabMidpoint";
         case DEB_HEUN: return "deb::TabHeun";
@@ -466,6 +470,7 @@ extern "C" void deb_erk_options_default(deb_erk_options* o) {  // erk/mod.rs:135
     o->safety_factor = 0.9;
     o->min_scale = 0.2;
     o->max_scale = 10.0;
+    o->max_rejects = 100;
 }
 
 extern "C" int deb_solve_ode(const deb_ode_problem* P, deb_result* R) {
@@ -541,6 +546,7 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P, deb_result* R) {
     a.min_scale = P->opt.min_scale;
     a.max_scale = P->opt.max_scale;
     a.max_steps = (int)std::min<int64_t>(P->opt.max_steps, 0x7fffffff / 16);
+    a.max_rejects = (int)std::min<int64_t>(std::max<int64_t>(P->opt.max_rejects, 0), 0x7fffffff);
     a.n_rows = (int)plan.rows.size();
     a.row_stride = P->n_eval;
     a.emit_t0 = plan.emit_t0 ? 1 : 0;

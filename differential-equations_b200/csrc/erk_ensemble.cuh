@@ -36,6 +36,7 @@ struct OdeKernelArgs {
     double rtol[DEB_MAX_DIM], atol[DEB_MAX_DIM];  // Tolerance indexed per component (tolerance.rs:32-41)
     double h0, h_min, h_max, safety, min_scale, max_scale;
     int max_steps;
+    int max_rejects;        // adaptive family only (adaptive/ordinary.rs:185-197)
     // t_eval: `rows` = the points that can ever be emitted, in integration order (host-filtered, see deb_api.cu)
     const double* t_rows;   // device [n_rows]
     int n_rows;
@@ -164,7 +165,8 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
     const double eps10 = DBL_EPSILON * 10.0;
     const double neg_err_exp = -(1.0 / (double)O);  // -error_exponent, ordinary.rs:152-154
     const double te_none = (dir > 0.0) ? (1.0 / 0.0) : -(1.0 / 0.0);
-    const int evals_base = (a.h0 == 0.0) ? 3 : 1;   // init: f(t0,y0) (+2 for the automatic initial step)
+    // init: f(t0,y0) (+2 for the automatic initial step; the adaptive family counts those two twice, adaptive/ordinary.rs:24-29)
+    const int evals_base = (a.h0 == 0.0) ? (Tab::DP ? 3 : 5) : 1;
     const bool bounded_h = (a.h_min > 0.0) || (a.h_max < 1.0 / 0.0);  // constrain_step_size can change h at all
 
     constexpr bool DEFER = (I == S);   // dense output needs no extra stages: emission can be parked
@@ -212,6 +214,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
                 }
                 const double c4 = __dmul_rn(0.0, hs);  // bi rows 4.. are all zero => cont[4] = (+0) * h
                 const double tn = ts + hs;
+                const double hh = tn - ts;  // cubic Hermite (adaptive family): t1 - t0, interpolate.rs:53
                 // the parked step covers rows [pend_idx, idx): idx was advanced past the step when the lane parked
                 for (int r = pend_idx; r < idx; r++) {
                     const double ter = a.t_rows[r];
@@ -219,7 +222,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
                     if (ter == tn) {  // exact hit: the solver state itself (t_eval.rs:113-114)
 #pragma unroll
                         for (int c = 0; c < N; c++) row[c] = yn[c];
-                    } else {  // interpolate, ordinary.rs:301-337 with O = 5
+                    } else if (Tab::DP) {  // interpolate, ordinary.rs:301-337 with O = 5
                         const double sx = (ter - ts) / hs;
                         const double s1 = 1.0 - sx;
 #pragma unroll
@@ -228,6 +231,22 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
                             accp = accp * sx + c2[c];
                             accp = accp * s1 + c1[c];
                             row[c] = ys[c] + sx * accp;
+                        }
+                    } else {  // cubic Hermite on (t_prev, t, y_prev, y, dydt_prev, dydt): interpolate.rs:40-60 via adaptive/ordinary.rs:282-295
+                        const double sx = (ter - ts) / hh;
+                        const double s2 = sx * sx, s3 = s2 * sx;
+                        const double h00 = 2.0 * s3 - 3.0 * s2 + 1.0;
+                        const double h10 = s3 - 2.0 * s2 + sx;
+                        const double h01 = -2.0 * s3 + 3.0 * s2;
+                        const double h11 = s3 - s2;
+                        const double w10 = h10 * hh, w11 = h11 * hh;
+#pragma unroll
+                        for (int c = 0; c < N; c++) {
+                            double v = __dadd_rn(0.0, h00 * ys[c]);
+                            v = v + w10 * stash[2 + 2 * N + c][lane];
+                            v = v + h01 * yn[c];
+                            v = v + w11 * stash[2 + 3 * N + c][lane];
+                            row[c] = v;
                         }
                     }
                     double* dst = a.y_eval + ((size_t)traj * a.row_stride + r) * N;
@@ -359,51 +378,80 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
                 }
                 Sys::rhs(t + Tab::cv(i) * h, ys, k[i], p);
             }
-            // ---- solution and error estimate, ordinary.rs:106-149
-            double yseg[N], ynew[N], es[N];
-#pragma unroll
-            for (int c = 0; c < N; c++) { yseg[c] = 0.0; es[c] = 0.0; }
-#pragma unroll
-            for (int i = 0; i < S; i++) {
-                if (Tab::b(i) != 0.0) {
-#pragma unroll
-                    for (int c = 0; c < N; c++) yseg[c] = __dadd_rn(yseg[c], Tab::bv(i) * k[i][c]);
-                }
-                if (Tab::er(i) != 0.0) {
-#pragma unroll
-                    for (int c = 0; c < N; c++) es[c] = __dadd_rn(es[c], Tab::erv(i) * k[i][c]);
-                }
-            }
+            // ---- solution and error estimate
+            double yseg[N], ynew[N];
             const double t_new = t + h;
-            double err = 0.0, err2 = 0.0;
-            double sk[N];
+            double err = 0.0;
+            if (Tab::DP) {  // dormandprince/ordinary.rs:106-149
+                double es[N];
 #pragma unroll
-            for (int c = 0; c < N; c++) {
-                ynew[c] = y[c] + h * yseg[c];
-                sk[c] = a.atol[c] + a.rtol[c] * fmax(fabs(y[c]), fabs(ynew[c]));  // traits.rs:587-595
-                const double e = es[c] / sk[c];
-                err = err + e * e;
-            }
-            if (Tab::HAS_BH) {  // DOP853 second estimator, ordinary.rs:135-143
-                double e2[N];
-#pragma unroll
-                for (int c = 0; c < N; c++) e2[c] = yseg[c];
+                for (int c = 0; c < N; c++) { yseg[c] = 0.0; es[c] = 0.0; }
 #pragma unroll
                 for (int i = 0; i < S; i++) {
-                    if (Tab::bh(i) != 0.0) {
+                    if (Tab::b(i) != 0.0) {
 #pragma unroll
-                        for (int c = 0; c < N; c++) e2[c] = e2[c] + (-Tab::bhv(i)) * k[i][c];
+                        for (int c = 0; c < N; c++) yseg[c] = __dadd_rn(yseg[c], Tab::bv(i) * k[i][c]);
+                    }
+                    if (Tab::er(i) != 0.0) {
+#pragma unroll
+                        for (int c = 0; c < N; c++) es[c] = __dadd_rn(es[c], Tab::erv(i) * k[i][c]);
+                    }
+                }
+                double err2 = 0.0;
+                double sk[N];
+#pragma unroll
+                for (int c = 0; c < N; c++) {
+                    ynew[c] = y[c] + h * yseg[c];
+                    sk[c] = a.atol[c] + a.rtol[c] * fmax(fabs(y[c]), fabs(ynew[c]));  // traits.rs:587-595
+                    const double e = es[c] / sk[c];
+                    err = err + e * e;
+                }
+                if (Tab::HAS_BH) {  // DOP853 second estimator, ordinary.rs:135-143
+                    double e2[N];
+#pragma unroll
+                    for (int c = 0; c < N; c++) e2[c] = yseg[c];
+#pragma unroll
+                    for (int i = 0; i < S; i++) {
+                        if (Tab::bh(i) != 0.0) {
+#pragma unroll
+                            for (int c = 0; c < N; c++) e2[c] = e2[c] + (-Tab::bhv(i)) * k[i][c];
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < N; c++) {
+                        const double e = e2[c] / sk[c];
+                        err2 = err2 + e * e;
+                    }
+                }
+                double deno = err + 0.01 * err2;
+                if (deno <= 0.0) deno = 1.0;
+                err = fabs(h) * err * sqrt(1.0 / (deno * (double)N));  // ordinary.rs:148
+            } else {  // adaptive/ordinary.rs:107-126: y_high, y_low, infinity norm of (y_high - y_low)/sk
+                double ylow[N];
+#pragma unroll
+                for (int c = 0; c < N; c++) { ynew[c] = y[c]; ylow[c] = y[c]; yseg[c] = 0.0; }
+#pragma unroll
+                for (int i = 0; i < S; i++) {
+                    if (Tab::b(i) != 0.0) {
+                        const double bw = Tab::bv(i) * h;
+#pragma unroll
+                        for (int c = 0; c < N; c++) ynew[c] = ynew[c] + bw * k[i][c];
                     }
                 }
 #pragma unroll
-                for (int c = 0; c < N; c++) {
-                    const double e = e2[c] / sk[c];
-                    err2 = err2 + e * e;
+                for (int i = 0; i < S; i++) {
+                    if (Tab::bh(i) != 0.0) {
+                        const double bw = Tab::bhv(i) * h;
+#pragma unroll
+                        for (int c = 0; c < N; c++) ylow[c] = ylow[c] + bw * k[i][c];
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < N; c++) {  // error_norm_inf, traits.rs:413-434 (f64::max ignores a NaN term, as fmax does)
+                    const double sk = a.atol[c] + a.rtol[c] * fmax(fabs(y[c]), fabs(ynew[c]));
+                    err = fmax(err, fabs((ynew[c] - ylow[c]) / sk));
                 }
             }
-            double deno = err + 0.01 * err2;
-            if (deno <= 0.0) deno = 1.0;
-            err = fabs(h) * err * sqrt(1.0 / (deno * (double)N));  // ordinary.rs:148
             // ---- controller, ordinary.rs:151-157
             double scale = a.safety * deb_pow_pos(err, neg_err_exp, tb);
             // scale.max(min_scale).min(max_scale) (ordinary.rs:157) with f64::max/min NaN rules: a NaN scale becomes
@@ -416,7 +464,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
             double dydt[N];
             Sys::rhs(t_new, ynew, dydt, p);
 
-            if (accept && (steps % 100 == 0)) {  // stiffness test, ordinary.rs:165-194
+            if (Tab::DP && accept && (steps % 100 == 0)) {  // stiffness test, ordinary.rs:165-194
                 // ysti = the argument of the last stage; rebuilt here (same operations, same bits) instead of being
                 // kept alive in registers through 99 steps out of 100
                 double ysti[N];
@@ -565,15 +613,22 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
                 t = t_new;
 #pragma unroll
                 for (int c = 0; c < N; c++) { y[c] = ynew[c]; k[0][c] = dydt[c]; }
-                if (rejected_prev) scale = (scale <= 1.0) ? scale : 1.0;  // scale.min(1), scale is not NaN here
+                if (rejected_prev) {
+                    scale = (scale <= 1.0) ? scale : 1.0;  // scale.min(1), scale is not NaN here
+                    if (!Tab::DP) stiff = 0;               // adaptive/ordinary.rs:137-143
+                }
                 rejected_prev = false;
                 acc += 1;
             }
             if (reject) {
                 rejected_prev = true;  // Status::RejectedStep
-                rej += 1;
+                if (!Tab::DP) {        // adaptive/ordinary.rs:182-197: max_rejects consecutive rejections => Err(Stiffness)
+                    stiff += 1;
+                    if (stiff >= a.max_rejects) fin = DEB_STATUS_STIFFNESS;  // Err: the attempt is not counted
+                }
+                if (fin < 0) rej += 1;
             }
-            if (commit || reject) {
+            if ((commit || reject) && fin < 0) {
                 // ---- step-size update, ordinary.rs:261-267 (filter = identity)
                 h = h * scale;
                 if (bounded_h) h = constrain_step_size(h, a.h_min, a.h_max);  // identity for h_min = 0, h_max = inf

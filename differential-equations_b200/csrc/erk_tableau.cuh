@@ -33,6 +33,14 @@ __constant__ double d8_b[12] = DEB_DOP853_B;
 __constant__ double d8_bh[12] = DEB_DOP853_BH;
 __constant__ double d8_er[12] = DEB_DOP853_ER;
 __constant__ double d8_bi[16][16] = DEB_DOP853_BI;
+__constant__ double rkf45_c[6] = DEB_RKF45_C;
+__constant__ double rkf45_a[6][6] = DEB_RKF45_A;
+__constant__ double rkf45_b[6] = DEB_RKF45_B;
+__constant__ double rkf45_bh[6] = DEB_RKF45_BH;
+__constant__ double ck_c[6] = DEB_CASH_KARP_C;
+__constant__ double ck_a[6][6] = DEB_CASH_KARP_A;
+__constant__ double ck_b[6] = DEB_CASH_KARP_B;
+__constant__ double ck_bh[6] = DEB_CASH_KARP_BH;
 #define DEB_CMEM_FIXED(pfx, PFX, n)                  \
     __constant__ double pfx##_c[n] = DEB_##PFX##_C;  \
     __constant__ double pfx##_a[n][n] = DEB_##PFX##_A; \
@@ -49,7 +57,7 @@ DEB_CMEM_FIXED(three_eighths, THREE_EIGHTHS, 4)
 // DOPRI5: /root/reference/src/tableau/dorman_prince.rs:37-117; (O,S,I) = (5,7,7) dormandprince/mod.rs:52-58
 struct TabDopri5 {
     static constexpr int O = 5, S = 7, I = 7;
-    static constexpr bool ADAPTIVE = true, HAS_BH = false;
+    static constexpr bool ADAPTIVE = true, HAS_BH = false, DP = true;
     DEB_TAB_FN1(c, 7, DEB_DOPRI5_C, d5_c)
     DEB_TAB_FN2(a, 7, DEB_DOPRI5_A, d5_a)
     DEB_TAB_FN1(b, 7, DEB_DOPRI5_B, d5_b)
@@ -64,7 +72,7 @@ struct TabDopri5 {
 // DOP853: /root/reference/src/tableau/dorman_prince.rs:155-381; (O,S,I) = (8,12,16) dormandprince/mod.rs:45-51
 struct TabDop853 {
     static constexpr int O = 8, S = 12, I = 16;
-    static constexpr bool ADAPTIVE = true, HAS_BH = true;
+    static constexpr bool ADAPTIVE = true, HAS_BH = true, DP = true;
     DEB_TAB_FN1(c, 16, DEB_DOP853_C, d8_c)
     DEB_TAB_FN2(a, 16, DEB_DOP853_A, d8_a)
     DEB_TAB_FN1(b, 12, DEB_DOP853_B, d8_b)
@@ -72,6 +80,24 @@ struct TabDop853 {
     DEB_TAB_FN1(er, 12, DEB_DOP853_ER, d8_er)
     DEB_TAB_FN2(bi, 16, DEB_DOP853_BI, d8_bi)
 };
+
+// Generic adaptive family (/root/reference/src/methods/erk/adaptive/mod.rs:47-60): error = y_high - y_low with the
+// embedded weights bh, infinity-norm error, `max_rejects` stiffness rule, cubic-Hermite dense output (bi = None), no FSAL.
+#define DEB_ADAPTIVE_TAB(Name, PFX, pfx)                                               \
+    struct Name {                                                                      \
+        static constexpr int O = 5, S = 6, I = 6;                                      \
+        static constexpr bool ADAPTIVE = true, HAS_BH = true, DP = false;              \
+        DEB_TAB_FN1(c, 6, DEB_##PFX##_C, pfx##_c)                                      \
+        DEB_TAB_FN2(a, 6, DEB_##PFX##_A, pfx##_a)                                      \
+        DEB_TAB_FN1(b, 6, DEB_##PFX##_B, pfx##_b)                                      \
+        DEB_TAB_FN1(bh, 6, DEB_##PFX##_BH, pfx##_bh)                                   \
+        __host__ __device__ static constexpr double er(int) { return 0.0; }            \
+        __device__ __forceinline__ static double erv(int) { return 0.0; }              \
+        __host__ __device__ static constexpr double bi(int, int) { return 0.0; }       \
+        __device__ __forceinline__ static double biv(int, int) { return 0.0; }         \
+    };
+DEB_ADAPTIVE_TAB(TabRkf45, RKF45, rkf45)        // runge_kutta.rs:335
+DEB_ADAPTIVE_TAB(TabCashKarp, CASH_KARP, ck)    // runge_kutta.rs:420
 
 #define DEB_FIXED_TAB(Name, PFX, pfx, order, stages)                 \
     struct Name {                                                    \

@@ -3,7 +3,7 @@
 //! for N independent problems, executed by the sm_100a kernels behind `include/deb_ensemble.h`.
 //!
 //! SOURCE ONLY: never compiled (no Rust toolchain in the build image).  The `#[repr(C)]` structs below are a
-//! field-for-field transcription of `include/deb_ensemble.h` (ABI version 1); `tests/test_abi_cpu.py` checks the
+//! field-for-field transcription of `include/deb_ensemble.h` (ABI version 2); `tests/test_abi_cpu.py` checks the
 //! same layout for the Python mirror against the compiled header.
 #![allow(non_camel_case_types)]
 
@@ -18,7 +18,7 @@ use differential_equations::{
 };
 
 // ------------------------------------------------------------------------------------------------ raw ABI
-pub const DEB_ABI_VERSION: i32 = 1;
+pub const DEB_ABI_VERSION: i32 = 2;
 
 #[repr(C)]
 #[derive(Clone, Copy)]
@@ -34,6 +34,7 @@ pub struct deb_erk_options {
     pub safety_factor: f64,
     pub min_scale: f64,
     pub max_scale: f64,
+    pub max_rejects: i64,
 }
 
 #[repr(C)]
@@ -133,6 +134,8 @@ impl Method {
     pub fn three_eighths(h: f64) -> Self { Self::new(6, h) }
     pub fn dopri5() -> Self { Self::new(16, 0.0) }
     pub fn dop853() -> Self { Self::new(17, 0.0) }
+    pub fn rkf45() -> Self { Self::new(18, 0.0) }
+    pub fn cash_karp() -> Self { Self::new(19, 0.0) }
     pub fn rtol(mut self, v: f64) -> Self { self.opt.rtol = v; self.rtol_vec = None; self }
     pub fn atol(mut self, v: f64) -> Self { self.opt.atol = v; self.atol_vec = None; self }
     pub fn rtol_vec(mut self, v: Vec<f64>) -> Self { self.rtol_vec = Some(v); self }
@@ -144,6 +147,7 @@ impl Method {
     pub fn safety_factor(mut self, v: f64) -> Self { self.opt.safety_factor = v; self }
     pub fn min_scale(mut self, v: f64) -> Self { self.opt.min_scale = v; self }
     pub fn max_scale(mut self, v: f64) -> Self { self.opt.max_scale = v; self }
+    pub fn max_rejects(mut self, v: usize) -> Self { self.opt.max_rejects = v as i64; self }
 }
 
 /// N independent IVPs sharing (t0, tf, method): the ensemble analogue of `IVP` (`src/ivp.rs`).

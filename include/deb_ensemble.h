@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define DEB_ABI_VERSION 1
+#define DEB_ABI_VERSION 2
 #define DEB_MAX_DIM 16 /* widest state the register-resident kernels are instantiated for */
 
 typedef enum deb_error {
@@ -57,7 +57,7 @@ typedef enum deb_error {
 } deb_error;
 
 /* Explicit Runge-Kutta constructors of the reference that the kernels implement
- * (src/methods/erk/fixed/mod.rs:41-89, src/methods/erk/dormandprince/mod.rs:45-58). */
+ * (src/methods/erk/fixed/mod.rs:41-89, src/methods/erk/dormandprince/mod.rs:45-58, src/methods/erk/adaptive/mod.rs:47-60). */
 typedef enum deb_method {
     DEB_EULER = 0,
     DEB_MIDPOINT = 1,
@@ -67,7 +67,10 @@ typedef enum deb_method {
     DEB_RK4 = 5,
     DEB_THREE_EIGHTHS = 6,
     DEB_DOPRI5 = 16,
-    DEB_DOP853 = 17
+    DEB_DOP853 = 17,
+    /* adaptive family with y_high - y_low error estimate (src/methods/erk/adaptive/mod.rs:47-60) */
+    DEB_RKF45 = 18,
+    DEB_CASH_KARP = 19
 } deb_method;
 
 /* Built-in right-hand sides (`ODE::diff`, src/ode/ode.rs:44).  A Rust closure cannot cross to the device,
@@ -114,6 +117,8 @@ typedef struct deb_erk_options {
     double safety_factor;   /* default 0.9 */
     double min_scale;       /* default 0.2 */
     double max_scale;       /* default 10 */
+    int64_t max_rejects;    /* default 100: consecutive rejections before Error::Stiffness in the adaptive family
+                               (adaptive/ordinary.rs:185-197); the Dormand-Prince stepper never reads it */
 } deb_erk_options;
 
 typedef struct deb_ode_problem {

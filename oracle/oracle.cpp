@@ -93,7 +93,8 @@ bool get_system(int id, SysInfo* s) {
 // ---------------------------------------------------------------- tableau (src/tableau/mod.rs:39-46)
 struct Tableau {
     int order, stages, dense;  // O, S, I
-    bool adaptive;
+    bool adaptive;     // has an error estimate + step-size controller
+    bool dp = false;   // Dormand-Prince family (dormandprince/ordinary.rs) vs generic adaptive family (adaptive/ordinary.rs)
     const double* c;   // [I]
     const double* a;   // [I][I]
     const double* b;   // [S]
@@ -111,19 +112,24 @@ const double MID_C[2] = DEB_MIDPOINT_C; const double MID_A[2][2] = DEB_MIDPOINT_
 const double HEUN_C[2] = DEB_HEUN_C; const double HEUN_A[2][2] = DEB_HEUN_A; const double HEUN_B[2] = DEB_HEUN_B;
 const double RAL_C[2] = DEB_RALSTON_C; const double RAL_A[2][2] = DEB_RALSTON_A; const double RAL_B[2] = DEB_RALSTON_B;
 const double SSP_C[3] = DEB_SSP_RK3_C; const double SSP_A[3][3] = DEB_SSP_RK3_A; const double SSP_B[3] = DEB_SSP_RK3_B;
+const double F45_C[6] = DEB_RKF45_C; const double F45_A[6][6] = DEB_RKF45_A; const double F45_B[6] = DEB_RKF45_B; const double F45_BH[6] = DEB_RKF45_BH;
+const double CK_C[6] = DEB_CASH_KARP_C; const double CK_A[6][6] = DEB_CASH_KARP_A; const double CK_B[6] = DEB_CASH_KARP_B; const double CK_BH[6] = DEB_CASH_KARP_BH;
 const double EU_C[1] = DEB_EULER_C; const double EU_A[1][1] = DEB_EULER_A; const double EU_B[1] = DEB_EULER_B;
 
 bool get_tableau(int m, Tableau* t) {
     switch (m) {  // (order, S, I): dormandprince/mod.rs:45-58, fixed/mod.rs:41-89
-        case DEB_DOPRI5: *t = {5, 7, 7, true, D5_C, &D5_A[0][0], D5_B, nullptr, D5_ER, &D5_BI[0][0]}; return true;
-        case DEB_DOP853: *t = {8, 12, 16, true, D8_C, &D8_A[0][0], D8_B, D8_BH, D8_ER, &D8_BI[0][0]}; return true;
-        case DEB_RK4: *t = {4, 4, 4, false, RK4_C, &RK4_A[0][0], RK4_B, nullptr, nullptr, nullptr}; return true;
-        case DEB_THREE_EIGHTHS: *t = {4, 4, 4, false, T38_C, &T38_A[0][0], T38_B, nullptr, nullptr, nullptr}; return true;
-        case DEB_MIDPOINT: *t = {2, 2, 2, false, MID_C, &MID_A[0][0], MID_B, nullptr, nullptr, nullptr}; return true;
-        case DEB_HEUN: *t = {2, 2, 2, false, HEUN_C, &HEUN_A[0][0], HEUN_B, nullptr, nullptr, nullptr}; return true;
-        case DEB_RALSTON: *t = {2, 2, 2, false, RAL_C, &RAL_A[0][0], RAL_B, nullptr, nullptr, nullptr}; return true;
-        case DEB_SSP_RK3: *t = {3, 3, 3, false, SSP_C, &SSP_A[0][0], SSP_B, nullptr, nullptr, nullptr}; return true;
-        case DEB_EULER: *t = {1, 1, 1, false, EU_C, &EU_A[0][0], EU_B, nullptr, nullptr, nullptr}; return true;
+        case DEB_DOPRI5: *t = {5, 7, 7, true, true, D5_C, &D5_A[0][0], D5_B, nullptr, D5_ER, &D5_BI[0][0]}; return true;
+        case DEB_DOP853: *t = {8, 12, 16, true, true, D8_C, &D8_A[0][0], D8_B, D8_BH, D8_ER, &D8_BI[0][0]}; return true;
+        // adaptive family, adaptive/mod.rs:47-60: (order, S, I) = (5, 6, 6), fsal = false, bi = None
+        case DEB_RKF45: *t = {5, 6, 6, true, false, F45_C, &F45_A[0][0], F45_B, F45_BH, nullptr, nullptr}; return true;
+        case DEB_CASH_KARP: *t = {5, 6, 6, true, false, CK_C, &CK_A[0][0], CK_B, CK_BH, nullptr, nullptr}; return true;
+        case DEB_RK4: *t = {4, 4, 4, false, false, RK4_C, &RK4_A[0][0], RK4_B, nullptr, nullptr, nullptr}; return true;
+        case DEB_THREE_EIGHTHS: *t = {4, 4, 4, false, false, T38_C, &T38_A[0][0], T38_B, nullptr, nullptr, nullptr}; return true;
+        case DEB_MIDPOINT: *t = {2, 2, 2, false, false, MID_C, &MID_A[0][0], MID_B, nullptr, nullptr, nullptr}; return true;
+        case DEB_HEUN: *t = {2, 2, 2, false, false, HEUN_C, &HEUN_A[0][0], HEUN_B, nullptr, nullptr, nullptr}; return true;
+        case DEB_RALSTON: *t = {2, 2, 2, false, false, RAL_C, &RAL_A[0][0], RAL_B, nullptr, nullptr, nullptr}; return true;
+        case DEB_SSP_RK3: *t = {3, 3, 3, false, false, SSP_C, &SSP_A[0][0], SSP_B, nullptr, nullptr, nullptr}; return true;
+        case DEB_EULER: *t = {1, 1, 1, false, false, EU_C, &EU_A[0][0], EU_B, nullptr, nullptr, nullptr}; return true;
     }
     return false;
 }
@@ -157,6 +163,15 @@ inline double error_norm(const Vec& y, const Vec& y_new, const Vec& err, const T
         sum += e * e;
     }
     return sum;
+}
+
+inline double error_norm_inf(const Vec& y, const Vec& y_new, const Vec& err, const Tol& atol, const Tol& rtol) {  // traits.rs:413-434
+    double mx = 0.0;
+    for (size_t i = 0; i < y.size(); i++) {
+        double sk = atol[i] + rtol[i] * rmax(std::fabs(y[i]), std::fabs(y_new[i]));
+        mx = rmax(mx, std::fabs(err[i] / sk));
+    }
+    return mx;
 }
 
 // ---------------------------------------------------------------- step-size utilities (src/utils.rs)
@@ -364,6 +379,66 @@ struct Erk {
         return plus_scaled(cont[0], s, acc);
     }
 
+    // ---- adaptive family (RKF45, Cash-Karp): init, adaptive/ordinary.rs:16-61
+    int64_t max_rejects = 100;
+    bool ad_init(const Problem& ode, double t0, double tf, const Vec& y0, int* evals) {
+        if (h0 == 0.0) {
+            h0 = h_init(ode, t0, tf, y0, tb.order, rtol, atol, h_min, h_max, evals);
+            *evals += 2;  // (sic) counted twice: compute() already added its two evaluations (:24-29)
+        }
+        if (!validate_step_size_parameters(h0, h_min, h_max, t0, tf)) return false;
+        h = h0;
+        stiffness_counter = 0;
+        t = t0; y = y0;
+        int n = ode.n;
+        dydt.assign(n, 0.0); y_prev = y0; dydt_prev.assign(n, 0.0);
+        k.assign(tb.dense, Vec(n, 0.0));
+        ode.diff(t, y, dydt);
+        *evals += 1;
+        t_prev = t; y_prev = y; dydt_prev = dydt;
+        rejected = false;
+        return true;
+    }
+    // ---- adaptive family: step, adaptive/ordinary.rs:63-211 (bi = None, fsal = false for RKF45 / Cash-Karp)
+    StepOutcome ad_step(const Problem& ode, int* evals_out) {
+        int evals = 0;
+        const int S = tb.stages, I = tb.dense;
+        if (std::fabs(h) < std::fabs(h_prev) * 1e-14) return STEP_ERR_STEP_SIZE;
+        if (steps >= max_steps) return STEP_ERR_MAX_STEPS;
+        steps += 1;
+        k[0] = dydt;
+        for (int i = 1; i < S; i++) {
+            Vec ys = y;
+            for (int j = 0; j < i; j++) add_scaled(ys, tb.a[i * I + j] * h, k[j]);
+            ode.diff(t + tb.c[i] * h, ys, k[i]);
+        }
+        evals += S - 1;
+        Vec y_high = y;
+        for (int i = 0; i < S; i++) add_scaled(y_high, tb.b[i] * h, k[i]);
+        Vec y_low = y;
+        for (int i = 0; i < S; i++) add_scaled(y_low, tb.bh[i] * h, k[i]);
+        Vec err = minus(y_high, y_low);
+        double err_norm = error_norm_inf(y, y_high, err, atol, rtol);
+        double scale = safety * std::pow(err_norm, -(1.0 / (double)tb.order));
+        scale = rmin(rmax(scale, min_scale), max_scale);
+        if (err_norm <= 1.0) {
+            t_prev = t; y_prev = y; dydt_prev = k[0]; h_prev = h;
+            if (rejected) { stiffness_counter = 0; rejected = false; scale = rmin(scale, 1.0); }
+            t += h;
+            y = y_high;
+            ode.diff(t, y, dydt);
+            evals += 1;
+        } else {
+            rejected = true;
+            stiffness_counter += 1;
+            if (stiffness_counter >= max_rejects) return STEP_ERR_STIFFNESS;  // Err: this attempt's evals are dropped
+        }
+        h *= scale;
+        h = constrain_step_size(h, h_min, h_max);
+        *evals_out += evals;
+        return STEP_OK;
+    }
+
     // ---- fixed step: init, fixed/ordinary.rs:16-56
     bool fx_init(const Problem& ode, double t0, double tf, const Vec& y0, int* evals) {
         if (h0 == 0.0) h0 = std::fabs(tf - t0) / 100.0;
@@ -462,6 +537,7 @@ void solve_one(const deb_ode_problem* P, const SysInfo& si, const Tableau& tb, i
     m.rtol = {P->opt.rtol, P->opt.rtol_vec}; m.atol = {P->opt.atol, P->opt.atol_vec};
     m.h0 = P->opt.h0; m.h_min = P->opt.h_min; m.h_max = P->opt.h_max; m.max_steps = P->opt.max_steps;
     m.safety = P->opt.safety_factor; m.min_scale = P->opt.min_scale; m.max_scale = P->opt.max_scale;
+    m.max_rejects = P->opt.max_rejects;
     int evals = 0, acc = 0, rej = 0, n_emit = 0;
     int status = DEB_STATUS_COMPLETE;
     double* ye = o.y_eval ? o.y_eval + (size_t)i * P->n_eval * n : nullptr;
@@ -476,10 +552,11 @@ void solve_one(const deb_ode_problem* P, const SysInfo& si, const Tableau& tb, i
     };
     double dir = signum(tf - t0);
     if (!(dir == 1.0 || dir == -1.0)) { finish(DEB_STATUS_BAD_INPUT, t0, y0); return; }  // :139-147
-    bool ok = tb.adaptive ? m.dp_init(ode, t0, tf, y0, &evals) : m.fx_init(ode, t0, tf, y0, &evals);
+    bool ok = tb.dp ? m.dp_init(ode, t0, tf, y0, &evals) : tb.adaptive ? m.ad_init(ode, t0, tf, y0, &evals) : m.fx_init(ode, t0, tf, y0, &evals);
     if (!ok) { evals = 0; finish(DEB_STATUS_BAD_INPUT, t0, y0); return; }
     TEval te(P->t_eval, P->n_eval, t0, tf);
-    auto interp = [&](double tv) { return tb.adaptive ? m.dp_interpolate(tv) : m.fx_interpolate(tv); };
+    // adaptive family without bi: cubic Hermite on (t_prev, t, y_prev, y, dydt_prev, dydt), adaptive/ordinary.rs:282-295
+    auto interp = [&](double tv) { return tb.dp ? m.dp_interpolate(tv) : m.fx_interpolate(tv); };
     solout_teval(te, m.t, m.t_prev, m.y, interp, ye, n, &n_emit);  // :160
     const double eps10 = DBL_EPSILON * 10.0;
     for (;;) {
@@ -488,7 +565,7 @@ void solve_one(const deb_ode_problem* P, const SysInfo& si, const Tableau& tb, i
             if (std::fabs(h_new) < eps10) { status = DEB_STATUS_COMPLETE; break; }
             m.h = h_new;
         }
-        StepOutcome so = tb.adaptive ? m.dp_step(ode, &evals) : m.fx_step(ode, &evals);
+        StepOutcome so = tb.dp ? m.dp_step(ode, &evals) : tb.adaptive ? m.ad_step(ode, &evals) : m.fx_step(ode, &evals);
         if (so != STEP_OK) {
             status = so == STEP_ERR_MAX_STEPS ? DEB_STATUS_MAX_STEPS : so == STEP_ERR_STEP_SIZE ? DEB_STATUS_STEP_SIZE : DEB_STATUS_STIFFNESS;
             break;

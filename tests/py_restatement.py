@@ -392,3 +392,137 @@ def exponential(k):
 
 def harmonic(k):
     return lambda t, y: [y[1], -k * y[0]]
+
+
+def solve_adaptive(f, method, t0, tf, y0, rtol=1e-6, atol=1e-6, t_eval=(), h0=0.0, h_min=0.0, h_max=math.inf, max_steps=10000,
+                   max_rejects=100, safety=0.9, min_scale=0.2, max_scale=10.0):
+    """Generic adaptive family (RKF45, Cash-Karp): /root/reference/src/methods/erk/adaptive/ordinary.rs:16-211, cubic
+    Hermite dense output (:282-295), driven by src/ode/solve_ivp.rs:139-277."""
+    T = TAB[method.upper()]
+    c, A, b, bh = T["C"], T["A"], T["B"], T["BH"]
+    S, O = len(b), 5
+    n = len(y0)
+    evals = 0
+    if tf == t0:
+        return dict(status="BadInput")
+    dirn = signum(tf - t0)
+    if h0 == 0.0:
+        h0 = h_init(f, t0, tf, y0, O, rtol, atol, h_min, h_max)
+        evals += 4  # (sic) 2 inside compute() + 2 again in init()
+    if (signum(h0) != dirn or h_min < 0 or h_max < 0 or h_min > h_max or abs(h0) < h_min or abs(h0) > h_max
+            or abs(h0) > abs(tf - t0) or h0 == 0.0):
+        return dict(status="BadInput")
+    h, t, y = h0, t0, list(y0)
+    dydt = f(t, y)
+    evals += 1
+    t_prev, y_prev, d_prev, h_prev = t, list(y), list(dydt), 0.0
+    steps = stiff = acc = rej = 0
+    rejected = False
+    pts = sorted(t_eval) if dirn > 0 else sorted(t_eval, reverse=True)
+    rows = []
+    state = dict(idx=0)
+
+    def interpolate(ti):
+        hh = t - t_prev
+        s = (ti - t_prev) / hh
+        s2 = s * s
+        s3 = s2 * s
+        h00 = 2.0 * s3 - 3.0 * s2 + 1.0
+        h10 = s3 - 2.0 * s2 + s
+        h01 = -2.0 * s3 + 3.0 * s2
+        h11 = s3 - s2
+        out = [0.0] * n
+        out = [out[q] + h00 * y_prev[q] for q in range(n)]
+        out = [out[q] + (h10 * hh) * d_prev[q] for q in range(n)]
+        out = [out[q] + h01 * y[q] for q in range(n)]
+        out = [out[q] + (h11 * hh) * dydt[q] for q in range(n)]
+        return out
+
+    def solout(t_curr, tp, y_curr):
+        idx = state["idx"]
+        while idx < len(pts):
+            te = pts[idx]
+            if dirn > 0:
+                in_range = (te == tp and idx == 0) or (te > tp and te <= t_curr)
+            else:
+                in_range = (te == tp and idx == 0) or (te < tp and te >= t_curr)
+            if in_range:
+                rows.append((te, list(y_curr) if te == t_curr else interpolate(te)))
+                idx += 1
+            else:
+                if (dirn > 0 and te > t_curr) or (dirn < 0 and te < t_curr):
+                    break
+                idx += 1
+        state["idx"] = idx
+
+    solout(t, t_prev, y)
+    status = "Complete"
+    while True:
+        if (t + h - tf) * dirn > 0.0:
+            h_new = tf - t
+            if abs(h_new) < EPS10:
+                break
+            h = h_new
+        if abs(h) < abs(h_prev) * 1e-14:
+            status = "StepSize"
+            break
+        if steps >= max_steps:
+            status = "MaxSteps"
+            break
+        steps += 1
+        k = [list(dydt)] + [None] * (S - 1)
+        for i in range(1, S):
+            ys = list(y)
+            for j in range(i):
+                ah = A[i][j] * h
+                ys = [ys[q] + ah * k[j][q] for q in range(n)]
+            k[i] = f(t + c[i] * h, ys)
+        step_evals = S - 1
+        y_high = list(y)
+        for i in range(S):
+            w = b[i] * h
+            y_high = [y_high[q] + w * k[i][q] for q in range(n)]
+        y_low = list(y)
+        for i in range(S):
+            w = bh[i] * h
+            y_low = [y_low[q] + w * k[i][q] for q in range(n)]
+        err = [y_high[q] + (-1.0) * y_low[q] for q in range(n)]
+        err_norm = 0.0
+        for q in range(n):
+            sk = atol + rtol * rmax(abs(y[q]), abs(y_high[q]))
+            err_norm = rmax(err_norm, abs(err[q] / sk))
+        scale = safety * powf(err_norm, -(1.0 / float(O)))
+        scale = rmin(rmax(scale, min_scale), max_scale)
+        if err_norm <= 1.0:
+            t_prev, y_prev, d_prev, h_prev = t, list(y), list(k[0]), h
+            if rejected:
+                stiff = 0
+                rejected = False
+                scale = rmin(scale, 1.0)
+            t += h
+            y = y_high
+            dydt = f(t, y)
+            step_evals += 1
+            accepted = True
+        else:
+            rejected = True
+            stiff += 1
+            if stiff >= max_rejects:
+                status = "Stiffness"
+                break
+            accepted = False
+        h *= scale
+        sg = signum(h)
+        if abs(h) < h_min:
+            h = sg * h_min
+        elif abs(h) > h_max:
+            h = sg * h_max
+        evals += step_evals
+        if not accepted:
+            rej += 1
+            continue
+        acc += 1
+        solout(t, t_prev, y)
+        if abs(tf - t) <= EPS10:
+            break
+    return dict(status=status, t=t, y=y, accepted=acc, rejected=rej, evals=evals, rows=rows)

@@ -71,7 +71,7 @@ def test_defaults_match_reference(lib):
     o = deb.ErkOptions()
     lib.deb_erk_options_default(C.byref(o))
     assert (o.rtol, o.atol, o.h0, o.h_min, o.max_steps, o.safety_factor, o.min_scale, o.max_scale) == (1e-6, 1e-6, 0.0, 0.0, 10000, 0.9, 0.2, 10.0)
-    assert o.h_max == float("inf") and not o.rtol_vec and not o.atol_vec
+    assert o.h_max == float("inf") and not o.rtol_vec and not o.atol_vec and o.max_rejects == 100
     m = E.dopri5()
     assert (m._rtol, m._atol, m._max_steps, m._max_rejects, m._safety_factor, m._min_scale, m._max_scale) == (1e-6, 1e-6, 10000, 100, 0.9, 0.2, 10.0)
 

@@ -24,7 +24,7 @@ SYSTEMS = {"exponential": lambda p: deb.ExponentialGrowth(*p), "linear": lambda 
 
 
 def make_method(c):
-    if c["solver"] in ("dopri5", "dop853"):
+    if c["solver"] in ("dopri5", "dop853", "rkf45", "cash_karp"):
         m = getattr(E, c["solver"])()
     else:
         m = getattr(E, c["solver"])(c["h"])
@@ -38,7 +38,7 @@ def make_method(c):
 def test_reference_accuracy_goldens():
     """tests/ode/accuracy.rs: final state vs SciPy DOP853 constants with the reference's own tolerances."""
     cases = json.load(open(os.path.join(GOLDEN, "reference_accuracy.json")))["accuracy"]
-    assert len(cases) == 42
+    assert len(cases) == 52
     for c in cases:
         ivp = deb.EnsembleIVP.ode(SYSTEMS[c["system"]](c["params"]), c["t0"], c["tf"], [c["y0"]]).method(make_method(c))
         s = ob.oracle_solve(ivp)[0]  # the reference test unwrap()s: every case must solve
@@ -174,3 +174,28 @@ def test_oracle_properties():
     assert _same_bits(s1.y_eval[::-1], s.y_eval) and np.array_equal(s1.accepted[::-1], s.accepted)
     s8 = ob.oracle_solve(deb.EnsembleIVP.ode(deb.VanDerPolOscillator(1.0), 0.0, 10.0, np.tile([2.0, 0.0], (8, 1))).method(E.dop853()))
     assert np.array_equal(s8.evals, 3 + 11 * (s8.accepted + s8.rejected) + 4 * s8.accepted)
+
+
+def test_adaptive_family_restatements_agree_bitwise():
+    """RKF45 / Cash-Karp (adaptive/ordinary.rs): the C++ oracle and the independent pure-Python restatement agree bit
+    for bit, including the doubled h_init evaluation count and the max_rejects rule."""
+    lz = pr.lorenz(10.0, 28.0, 8.0 / 3.0)
+    for meth in ("rkf45", "cash_karp"):
+        cases = ((lz, deb.LorenzSystem(10.0, 28.0, 8.0 / 3.0), 0.0, 10.0, [1.0, 1.0, 1.0], dict(rtol=1e-7, atol=1e-8)),
+                 (lz, deb.LorenzSystem(10.0, 28.0, 8.0 / 3.0), 0.0, 6.0, [0.3, -1.0, 20.0], dict(rtol=1e-6, atol=1e-6)),
+                 (pr.harmonic(1.0), deb.HarmonicOscillator(1.0), 10.0, 0.0, [1.0, 0.0], dict(rtol=1e-8, atol=1e-8)))  # backward
+        for (f, sysm, t0, tf, y0, tol) in cases:
+            te = list(np.linspace(t0, tf, 7)) + [0.5 * (t0 + tf) + 0.0123]
+            p = pr.solve_adaptive(f, meth, t0, tf, y0, t_eval=te, **tol)
+            c = ob.oracle_solve(deb.EnsembleIVP.ode(sysm, t0, tf, [y0]).t_eval(te)
+                                .method(getattr(E, meth)().rtol(tol["rtol"]).atol(tol["atol"])))
+            assert p["status"] == "Complete" and c.status[0] == 0
+            assert (p["accepted"], p["rejected"], p["evals"]) == (int(c.accepted[0]), int(c.rejected[0]), int(c.evals[0]))
+            assert p["evals"] == 5 + 5 * (p["accepted"] + p["rejected"]) + p["accepted"]
+            assert _same_bits(p["y"], c.y_final[0]) and _same_bits([r[1] for r in p["rows"]], c.y_eval[0, :len(p["rows"])])
+        rob = lambda t, y: [-0.04 * y[0] + 1.0e4 * y[1] * y[2], 0.04 * y[0] - 1.0e4 * y[1] * y[2] - 3.0e7 * y[1] * y[1], 3.0e7 * y[1] * y[1]]
+        p = pr.solve_adaptive(rob, meth, 0.0, 40.0, [1.0, 0.0, 0.0], h0=0.5, max_rejects=3)
+        c = ob.oracle_solve(deb.EnsembleIVP.ode(deb.RobertsonProblem(), 0.0, 40.0, [[1.0, 0.0, 0.0]]).method(getattr(E, meth)().h0(0.5).max_rejects(3)))
+        assert p["status"] == "Stiffness" and c.status[0] == deb.DEB_STATUS_STIFFNESS
+        assert (p["accepted"], p["rejected"], p["evals"]) == (int(c.accepted[0]), int(c.rejected[0]), int(c.evals[0]))
+        assert _same_bits(p["y"], c.y_final[0]) and p["t"] == c.t_final[0]

@@ -454,3 +454,34 @@ def test_user_defined_rhs_compile_error_is_reported():
     bad = deb.ode_from_source(1, "dydt[0] = undefined_symbol * y[0];", [1.0])
     with pytest.raises(ValueError, match="did not compile"):
         deb.EnsembleIVP.ode(bad, 0.0, 1.0, [[1.0]]).method(E.dopri5()).solve()
+
+
+# ------------------------------------------------------------------------------------------ adaptive family
+@pytest.mark.parametrize("ctor", ["rkf45", "cash_karp"])
+def test_adaptive_family_bit_exact(ctor):
+    """RKF45 / Cash-Karp (src/methods/erk/adaptive/ordinary.rs): y_high - y_low error in the infinity norm,
+    max_rejects stiffness rule, cubic-Hermite dense output, the doubled h_init evaluation count."""
+    y0 = ob.lorenz_ensemble_y0(2000, seed=31)
+    te = np.linspace(0.0, 10.0, 21)
+    def prob():
+        return deb.EnsembleIVP.ode(lorenz(), 0.0, 10.0, y0).t_eval(te).method(getattr(E, ctor)().rtol(1e-7).atol(1e-8))
+    g, c = prob().solve(), ob.oracle_solve(prob())
+    assert_same_solution(g, c)
+    assert (g.status == 0).all()
+    assert np.array_equal(g.evals, 5 + 5 * (g.accepted + g.rejected) + g.accepted)
+    # parameter sweep, backward time, vector tolerances, explicit h0 (no h_init: evals base 1)
+    mu = np.linspace(0.1, 6.0, 500)
+    def p2():
+        return (deb.EnsembleIVP.ode(deb.VanDerPolOscillator(mu), 10.0, 0.0, np.tile([2.0, 0.0], (500, 1))).t_eval([7.5, 2.5, 0.0])
+                .method(getattr(E, ctor)().rtol([1e-6, 1e-7]).atol([1e-8, 1e-9]).h0(-1e-3)))
+    g, c = p2().solve(), ob.oracle_solve(p2())
+    assert_same_solution(g, c)
+    assert np.array_equal(g.evals, 1 + 5 * (g.accepted + g.rejected) + g.accepted)
+    # the max_rejects rule: a stiff problem with a tiny max_rejects ends in Err(Stiffness), the rejected attempt uncounted
+    def p3():
+        return deb.EnsembleIVP.ode(deb.RobertsonProblem(), 0.0, 40.0, np.tile([1.0, 0.0, 0.0], (16, 1))).method(getattr(E, ctor)().h0(0.5).max_rejects(3))
+    g, c = p3().solve(), ob.oracle_solve(p3())
+    assert_same_solution(g, c)
+    assert (g.status == deb.DEB_STATUS_STIFFNESS).all()
+    with pytest.raises(deb.Stiffness):
+        g[0]
