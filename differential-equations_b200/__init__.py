@@ -46,8 +46,9 @@ DEB_DOPRI5, DEB_DOP853, DEB_RKF45, DEB_CASH_KARP = 16, 17, 18, 19
 DEB_SDE_OU, DEB_SDE_GBM = 0, 1
 DEB_STATUS_COMPLETE, DEB_STATUS_MAX_STEPS, DEB_STATUS_STEP_SIZE, DEB_STATUS_STIFFNESS, DEB_STATUS_BAD_INPUT = range(5)
 DEB_MEM_HOST, DEB_MEM_DEVICE = 0, 1
+DEB_SOLOUT_T_EVAL, DEB_SOLOUT_EVEN = 0, 1
 DEB_OK, DEB_ERR_BAD_ARG, DEB_ERR_NO_DEVICE, DEB_ERR_CUDA, DEB_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
-DEB_ABI_VERSION = 2
+DEB_ABI_VERSION = 3
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -63,7 +64,8 @@ class OdeProblem(C.Structure):
     _fields_ = [("struct_size", C.c_size_t), ("system", C.c_int32), ("method", C.c_int32), ("dim", C.c_int32),
                 ("n_params", C.c_int32), ("n_traj", C.c_int64), ("y0", C.c_void_p), ("params", C.c_void_p),
                 ("params_shared", C.c_int32), ("n_eval", C.c_int32), ("t_eval", _dp), ("t0", C.c_double), ("tf", C.c_double),
-                ("opt", ErkOptions), ("device", C.c_int32), ("memspace", C.c_int32), ("stream", C.c_void_p)]
+                ("opt", ErkOptions), ("device", C.c_int32), ("memspace", C.c_int32), ("stream", C.c_void_p),
+                ("solout", C.c_int32), ("reserved0", C.c_int32), ("even_dt", C.c_double)]
 
 
 class SdeProblem(C.Structure):
@@ -332,6 +334,7 @@ class EnsembleSolution:
         self.t_final, self.y_final = t_final, y_final
         self.status, self.accepted, self.rejected, self.evals = status, accepted, rejected, evals
         self.kernel_ms, self.total_ms = kernel_ms, total_ms
+        self.even_tf = None
 
     def __len__(self):
         return self.n
@@ -350,9 +353,22 @@ class EnsembleSolution:
         if st == DEB_STATUS_STIFFNESS:
             raise Stiffness(tfin, yf)
         m = int(self.n_emitted[i])
-        return Solution(t=self.t_rows[:m].copy(), y=self.y_eval[i, :m].copy(), status="Complete",
+        ts = self.row_times(i)
+        return Solution(t=ts, y=self.y_eval[i, :m].copy(), status="Complete",
                         evals=Evals(int(self.evals[i])), steps=Steps(int(self.accepted[i]), int(self.rejected[i])),
                         t_final=tfin, y_final=yf)
+
+    def row_times(self, i) -> np.ndarray:
+        """Solution.t of trajectory i."""
+        m = int(self.n_emitted[i])
+        ts = np.empty(m)
+        k = min(m, self.t_rows.size)
+        ts[:k] = self.t_rows[:k]
+        if self.even_tf is not None and m > 0 and self.t_final[i] == self.even_tf:
+            ts[m - 1] = self.even_tf  # even.rs:166-188: the last point is replaced by / completed with (tf, y(tf))
+        elif m > k:
+            ts[k:] = np.nan
+        return ts
 
     def status_names(self) -> List[str]:
         return [_STATUS_NAME[int(s)] for s in self.status]
@@ -389,6 +405,7 @@ class EnsembleIVP:
             y0s = y0s.reshape(-1)
         self.y0s = y0s
         self._t_eval = np.zeros(0)
+        self._even_dt = 0.0
         self._method: Optional[ExplicitRungeKutta] = None
         self._device = 0
         self.seed, self.path_offset = int(seed), int(path_offset)
@@ -403,6 +420,16 @@ class EnsembleIVP:
 
     def t_eval(self, pts: Sequence[float]):  # ivp.rs:656
         self._t_eval = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1)
+        return self
+
+    def even(self, dt: float):  # ivp.rs:643
+        """Evenly spaced output t0, t0+dt, ... (EvenSolout, src/solout/even.rs), plus the final state at tf."""
+        if self.kind != "ode":
+            raise ValueError("even(dt) is implemented for ODE ensembles")
+        if not (dt > 0.0):
+            raise ValueError("dt must be positive")
+        self._even_dt = float(dt)
+        self._t_eval = np.zeros(0)
         return self
 
     def method(self, m: ExplicitRungeKutta):  # ivp.rs:632
@@ -427,6 +454,8 @@ class EnsembleIVP:
         n = int(self.y0s.shape[0])
         keep: list = []
         n_eval = int(self._t_eval.size)
+        if self._even_dt > 0.0:
+            n_eval = int(math.floor(abs(self.tf - self.t0) / self._even_dt)) + 3  # row capacity per trajectory
         res = Result()
         t_sorted = np.zeros(max(n_eval, 1))
         if self.kind == "ode":
@@ -452,8 +481,10 @@ class EnsembleIVP:
         P.n_traj = n
         P.params = params.ctypes.data
         P.n_eval = n_eval
-        P.t_eval = self._t_eval.ctypes.data_as(_dp) if n_eval else None
+        P.t_eval = self._t_eval.ctypes.data_as(_dp) if self._t_eval.size else None
         P.t0, P.tf = self.t0, self.tf
+        if self.kind == "ode" and self._even_dt > 0.0:
+            P.solout, P.even_dt = DEB_SOLOUT_EVEN, self._even_dt
         self._method.fill_options(P.opt, dim, keep)
         P.device, P.memspace, P.stream = self._device, DEB_MEM_HOST, None
         arrs = alloc_result_arrays(n, n_eval, dim)
@@ -472,11 +503,25 @@ class EnsembleIVP:
         rows = t_sorted[:res.n_rows].copy()
         return self.wrap_result(arrs, rows, res)
 
+
     def wrap_result(self, arrs, rows, res) -> EnsembleSolution:
         n = int(self.y0s.shape[0])
         dim = self.system.dim if self.kind == "ode" else 1
-        return EnsembleSolution(n, dim, rows, arrs["y_eval"], arrs["n_emitted"], arrs["t_final"], arrs["y_final"],
-                                arrs["status"], arrs["accepted"], arrs["rejected"], arrs["evals"], res.kernel_ms, res.total_ms)
+        sol = EnsembleSolution(n, dim, rows, arrs["y_eval"], arrs["n_emitted"], arrs["t_final"], arrs["y_final"],
+                               arrs["status"], arrs["accepted"], arrs["rejected"], arrs["evals"], res.kernel_ms, res.total_ms)
+        if self._even_dt > 0.0:
+            sol.even_tf = self.tf  # EvenSolout: a trajectory that lands exactly on tf has its last row at tf
+        return sol
+
+
+def _even_rows(t0: float, tf: float, dt: float) -> np.ndarray:
+    """The points EvenSolout visits: t0, then repeatedly + dt*direction (accumulated), while not past tf."""
+    d = math.copysign(1.0, tf - t0)
+    rows, ti = [], t0
+    while (ti <= tf) if d > 0 else (ti >= tf):
+        rows.append(ti)
+        ti += dt * d
+    return np.asarray(rows, dtype=np.float64)
 
 
 def _plan_rows(t_eval: np.ndarray, t0: float, tf: float) -> np.ndarray:

@@ -440,10 +440,11 @@ int check_options(const deb_erk_options& o) {
     return DEB_OK;
 }
 
-void publish_rows(deb_result* R, const TEvalPlan& plan) {
-    R->n_rows = (int32_t)plan.rows.size();
+void publish_rows(deb_result* R, const TEvalPlan& plan, bool even = false) {
+    const size_t n = plan.rows.size() - (even ? 1 : 0);  // the EvenSolout tf sentinel is not a row time
+    R->n_rows = (int32_t)n;
     if (R->t_rows)
-        for (size_t i = 0; i < plan.rows.size(); i++) R->t_rows[i] = plan.rows[i];
+        for (size_t i = 0; i < n; i++) R->t_rows[i] = plan.rows[i];
 }
 
 }  // namespace
@@ -501,8 +502,24 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P, deb_result* R) {
     if (P->n_eval < 0) return fail(DEB_ERR_BAD_ARG, "n_eval < 0");
     if (int rc = check_options(P->opt)) return rc;
     TEvalPlan plan;
-    if (int rc = plan_t_eval(P->t_eval, P->n_eval, P->t0, P->tf, &plan)) return rc;
-    publish_rows(R, plan);
+    const bool even = (P->solout == DEB_SOLOUT_EVEN);
+    if (P->solout != DEB_SOLOUT_T_EVAL && !even) return fail(DEB_ERR_BAD_ARG, "unknown solout mode");
+    if (even) {
+        // EvenSolout::solout (even.rs:69-199): t0 is emitted by the call before the loop, then last + dt*direction,
+        // accumulated, while the point is not past tf
+        if (!(P->even_dt > 0.0) || !(P->tf != P->t0)) return fail(DEB_ERR_BAD_ARG, "even(dt): dt must be > 0 and tf != t0");
+        const double d = (P->tf > P->t0) ? 1.0 : -1.0;
+        if (fabs(P->tf - P->t0) / P->even_dt > 1.0e8) return fail(DEB_ERR_BAD_ARG, "even(dt): more than 1e8 output points");
+        for (double ti = P->t0; (d > 0.0) ? (ti <= P->tf) : (ti >= P->tf); ti += P->even_dt * d) plan.rows.push_back(ti);
+        if (!R->y_eval) return fail(DEB_ERR_BAD_ARG, "even(dt) needs a y_eval buffer");
+        plan.emit_t0 = true;
+        plan.rows.push_back(P->tf);  // sentinel: reaching it triggers the final-point rule in the kernels (not a row time)
+        if ((size_t)P->n_eval < plan.rows.size())
+            return fail(DEB_ERR_BAD_ARG, "even(dt): n_eval (row capacity) must be at least floor(|tf-t0|/dt) + 2");
+    } else if (int rc = plan_t_eval(P->t_eval, P->n_eval, P->t0, P->tf, &plan)) {
+        return rc;
+    }
+    publish_rows(R, plan, even);
     R->kernel_ms = 0.f;
     R->total_ms = 0.f;
     if (P->n_traj == 0) return DEB_OK;  // empty ensemble: nothing to do, and no device needed
@@ -550,6 +567,8 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P, deb_result* R) {
     a.n_rows = (int)plan.rows.size();
     a.row_stride = P->n_eval;
     a.emit_t0 = plan.emit_t0 ? 1 : 0;
+    a.even = even ? 1 : 0;
+    a.even_tol = fabs(P->even_dt) * 1e-12 + 2.220446049250313e-16 * 10.0;
     const bool per_traj_params = (np > 0 && !P->params_shared);
     const size_t rows_bytes = sizeof(double) * plan.rows.size();
 

@@ -42,6 +42,9 @@ struct OdeKernelArgs {
     int n_rows;
     int row_stride;         // rows per trajectory in y_eval (= problem n_eval)
     int emit_t0;            // rows[0] == t0: emitted by the solout call that precedes the loop (solve_ivp.rs:160)
+    int even;               // EvenSolout (src/solout/even.rs): rows are t0 + k*dt, always interpolated; the LAST entry of
+                            // t_rows is a sentinel equal to tf that triggers the final-point rule (even.rs:166-188)
+    double even_tol;        // |dt|*1e-12 + 10 eps (even.rs:92-93)
     double* y_eval;
     int* n_emitted;
     double* t_final;
@@ -217,9 +220,24 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
                 const double hh = tn - ts;  // cubic Hermite (adaptive family): t1 - t0, interpolate.rs:53
                 // the parked step covers rows [pend_idx, idx): idx was advanced past the step when the lane parked
                 for (int r = pend_idx; r < idx; r++) {
+                    if (a.even && r == a.n_rows - 1) {  // the tf sentinel: even.rs:166-188, only when the step landed exactly on tf
+                        int w = -1;
+                        if (tn == a.tf) {
+                            const double t_last = a.t_rows[r - 1];  // r >= 1: row 0 (t0) was emitted at init
+                            if (fabs(t_last - a.tf) <= a.even_tol) w = r - 1;  // pop + push(tf, y): replace the near-duplicate
+                            else w = r;                                       // push(tf, y)
+                        }
+                        if (w >= 0) {
+                            double* dst = a.y_eval + ((size_t)traj * a.row_stride + w) * N;
+#pragma unroll
+                            for (int c = 0; c < N; c++) dst[c] = yn[c];
+                        }
+                        idx = w + 1 > r ? r + 1 : r;  // rows emitted so far: the sentinel slot counts only if it was written
+                        break;
+                    }
                     const double ter = a.t_rows[r];
                     double row[N];
-                    if (ter == tn) {  // exact hit: the solver state itself (t_eval.rs:113-114)
+                    if (ter == tn && !a.even) {  // exact hit: the solver state itself (t_eval.rs:113-114); EvenSolout always interpolates
 #pragma unroll
                         for (int c = 0; c < N; c++) row[c] = yn[c];
                     } else if (Tab::DP) {  // interpolate, ordinary.rs:301-337 with O = 5
@@ -519,10 +537,10 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
                         pend_idx = idx;
                         pending = true;
                     }
-                    do {
+                    while ((te - t_new) * dir <= 0.0) {
                         idx += 1;
                         te = (idx < a.n_rows) ? a.t_rows[idx] : te_none;
-                    } while ((te - t_new) * dir <= 0.0);
+                    }
                 }
                 __syncwarp();
             } else {
@@ -571,9 +589,24 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
                             for (int c = 0; c < N; c++) ch[i - 4][c] = ch[i - 4][c] * h;
                         }
                     }
-                    do {
+                    while ((te - t_new) * dir <= 0.0) {
+                        if (a.even && idx == a.n_rows - 1) {  // the tf sentinel: final-point rule, even.rs:166-188
+                            int w = -1;
+                            if (t_new == tf) {
+                                const double t_last = a.t_rows[idx - 1];
+                                w = (fabs(t_last - tf) <= a.even_tol) ? idx - 1 : idx;
+                            }
+                            if (w >= 0 && want_rows) {
+                                double* dst = a.y_eval + ((size_t)traj * a.row_stride + w) * N;
+#pragma unroll
+                                for (int c = 0; c < N; c++) dst[c] = ynew[c];
+                            }
+                            if (w == idx) idx += 1;
+                            te = te_none;
+                            break;
+                        }
                         double row[N];
-                        if (te == t_new) {  // exact hit: the solver state itself (t_eval.rs:113-114)
+                        if (te == t_new && !a.even) {  // exact hit: the solver state itself (t_eval.rs:113-114)
 #pragma unroll
                             for (int c = 0; c < N; c++) row[c] = ynew[c];
                         } else {  // interpolate, ordinary.rs:301-337, factor order as written
@@ -600,7 +633,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
                         }
                         idx += 1;
                         te = (idx < a.n_rows) ? a.t_rows[idx] : te_none;
-                    } while ((te - t_new) * dir <= 0.0);
+                    }
                 }
                 __syncwarp();
             }

@@ -94,8 +94,23 @@ __global__ void __launch_bounds__(BLOCK) fixed_ensemble_kernel(const OdeKernelAr
             evals += S;  // S-1 stages + the new derivative (fsal = false)
             // ---- TEvalSolout with cubic Hermite interpolation
             while ((dir > 0.0) ? (te <= t_new) : (te >= t_new)) {
+                if (a.even && idx == a.n_rows - 1) {  // the tf sentinel: EvenSolout final-point rule, even.rs:166-188
+                    int w = -1;
+                    if (t_new == tf) {
+                        const double t_last = a.t_rows[idx - 1];
+                        w = (fabs(t_last - tf) <= a.even_tol) ? idx - 1 : idx;
+                    }
+                    if (w >= 0 && a.y_eval) {
+                        double* dst = a.y_eval + ((size_t)traj * a.row_stride + w) * N;
+#pragma unroll
+                        for (int c = 0; c < N; c++) dst[c] = ynew[c];
+                    }
+                    if (w == idx) { idx += 1; n_emit += 1; }
+                    te = te_none;
+                    break;
+                }
                 double row[N];
-                if (te == t_new) {
+                if (te == t_new && !a.even) {
 #pragma unroll
                     for (int c = 0; c < N; c++) row[c] = ynew[c];
                 } else {

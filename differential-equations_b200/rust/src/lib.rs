@@ -3,7 +3,7 @@
 //! for N independent problems, executed by the sm_100a kernels behind `include/deb_ensemble.h`.
 //!
 //! SOURCE ONLY: never compiled (no Rust toolchain in the build image).  The `#[repr(C)]` structs below are a
-//! field-for-field transcription of `include/deb_ensemble.h` (ABI version 2); `tests/test_abi_cpu.py` checks the
+//! field-for-field transcription of `include/deb_ensemble.h` (ABI version 3); `tests/test_abi_cpu.py` checks the
 //! same layout for the Python mirror against the compiled header.
 #![allow(non_camel_case_types)]
 
@@ -18,7 +18,7 @@ use differential_equations::{
 };
 
 // ------------------------------------------------------------------------------------------------ raw ABI
-pub const DEB_ABI_VERSION: i32 = 2;
+pub const DEB_ABI_VERSION: i32 = 3;
 
 #[repr(C)]
 #[derive(Clone, Copy)]
@@ -56,6 +56,9 @@ pub struct deb_ode_problem {
     pub device: i32,
     pub memspace: i32,
     pub stream: *mut c_void,
+    pub solout: i32, // 0 = t_eval, 1 = even(dt)
+    pub reserved0: i32,
+    pub even_dt: f64,
 }
 
 #[repr(C)]
@@ -209,6 +212,9 @@ impl<const N: usize> EnsembleIVP<N> {
             device: self.device,
             memspace: 0, // DEB_MEM_HOST
             stream: std::ptr::null_mut(),
+            solout: 0,
+            reserved0: 0,
+            even_dt: 0.0,
         };
         let mut result = deb_result {
             struct_size: std::mem::size_of::<deb_result>(),

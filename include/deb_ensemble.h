@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define DEB_ABI_VERSION 2
+#define DEB_ABI_VERSION 3
 #define DEB_MAX_DIM 16 /* widest state the register-resident kernels are instantiated for */
 
 typedef enum deb_error {
@@ -104,6 +104,13 @@ typedef enum deb_status {
 
 typedef enum deb_memspace { DEB_MEM_HOST = 0, DEB_MEM_DEVICE = 1 } deb_memspace;
 
+/* Output recorder (`Solout`, src/solout/): which rows go to y_eval. */
+typedef enum deb_solout {
+    DEB_SOLOUT_T_EVAL = 0, /* IVP::t_eval(points): TEvalSolout, src/solout/t_eval.rs:87-171 */
+    DEB_SOLOUT_EVEN = 1    /* IVP::even(dt): EvenSolout, src/solout/even.rs:69-199 -- t0, t0+dt, t0+2dt, ... (accumulated),
+                              every point interpolated, plus the exact final state when a step lands on tf */
+} deb_solout;
+
 /* Options of ExplicitRungeKutta (src/methods/erk/mod.rs:135-144 defaults, :164-228 setters). */
 typedef struct deb_erk_options {
     double rtol;            /* scalar Tolerance; default 1e-6 */
@@ -138,6 +145,11 @@ typedef struct deb_ode_problem {
     int32_t device;       /* CUDA ordinal */
     int32_t memspace;     /* deb_memspace for y0, params and every result pointer */
     void* stream;         /* cudaStream_t when memspace == DEB_MEM_DEVICE (NULL = default stream) */
+    int32_t solout;       /* deb_solout; 0 = t_eval */
+    int32_t reserved0;
+    double even_dt;       /* DEB_SOLOUT_EVEN: the spacing dt > 0.  t_eval is ignored; n_eval is the row capacity of y_eval per
+                             trajectory and must be at least floor(|tf-t0|/dt) + 2.  t_rows receives t0 + k*dt; a trajectory
+                             whose t_final == tf has its last row at tf (even.rs:166-188) */
 } deb_ode_problem;
 
 typedef struct deb_sde_problem {

@@ -526,6 +526,61 @@ void solout_teval(TEval& te, double t_curr, double t_prev, const Vec& y_curr, In
     te.idx = idx;
 }
 
+// EvenSolout, src/solout/even.rs:60-217 (rows are appended to y_eval; *n_emit counts them, the last one may be replaced)
+struct Even {
+    double dt, t0, tf, dir;
+    bool has_last = false;
+    double last = 0.0;
+    Even(double dt_, double t0_, double tf_) : dt(dt_), t0(t0_), tf(tf_), dir(signum(tf_ - t0_)) {}
+};
+template <class Interp>
+void solout_even(Even& ev, double t_curr, double t_prev, const Vec& y_curr, const Vec& y_prev, Interp&& interp, double* y_eval, int n, int* n_emit) {
+    auto push = [&](const Vec& v) { if (y_eval) std::memcpy(y_eval + (size_t)(*n_emit) * n, v.data(), sizeof(double) * n); *n_emit += 1; };
+    const double offset = std::fmod(ev.t0, ev.dt);
+    const double tol = std::fabs(ev.dt) * 1e-12 + DBL_EPSILON * 10.0;
+    double start_t;
+    if (ev.has_last) {
+        start_t = ev.last + ev.dt * ev.dir;
+    } else {
+        if (std::fabs(t_prev - ev.t0) < DBL_EPSILON) {
+            push(y_prev);
+            ev.last = ev.t0; ev.has_last = true;
+            start_t = ev.t0 + ev.dt * ev.dir;
+        } else {
+            double rem = std::fmod(t_prev - offset, ev.dt);
+            if (ev.dir > 0.0) start_t = (std::fabs(rem) < DBL_EPSILON) ? t_prev : t_prev + (ev.dt - rem);
+            else start_t = (std::fabs(rem) < DBL_EPSILON) ? t_prev : t_prev - rem;
+        }
+    }
+    double ti = start_t;
+    while ((ev.dir > 0.0 && ti <= t_curr) || (ev.dir < 0.0 && ti >= t_curr)) {
+        if ((ev.dir > 0.0 && ti >= t_prev && ti <= t_curr) || (ev.dir < 0.0 && ti <= t_prev && ti >= t_curr)) {
+            if (ev.has_last && std::fabs(ti - ev.last) <= tol) {
+                // near-duplicate: skip
+            } else {
+                push(interp(ti));
+                ev.last = ti; ev.has_last = true;
+            }
+        }
+        ti += ev.dt * ev.dir;
+    }
+    if (t_curr == ev.tf) {  // even.rs:166-188
+        if (ev.has_last) {
+            if (std::fabs(ev.last - ev.tf) <= tol) {
+                *n_emit -= 1;  // solution.pop()
+                push(y_curr);
+                ev.last = ev.tf;
+            } else if (ev.last != ev.tf) {
+                push(y_curr);
+                ev.last = ev.tf;
+            }
+        } else {
+            push(y_curr);
+            ev.last = ev.tf; ev.has_last = true;
+        }
+    }
+}
+
 // solve_ode, src/ode/solve_ivp.rs:116-277, for one trajectory
 void solve_one(const deb_ode_problem* P, const SysInfo& si, const Tableau& tb, int64_t i, const Out& o) {
     const int n = si.dim;
@@ -554,10 +609,16 @@ void solve_one(const deb_ode_problem* P, const SysInfo& si, const Tableau& tb, i
     if (!(dir == 1.0 || dir == -1.0)) { finish(DEB_STATUS_BAD_INPUT, t0, y0); return; }  // :139-147
     bool ok = tb.dp ? m.dp_init(ode, t0, tf, y0, &evals) : tb.adaptive ? m.ad_init(ode, t0, tf, y0, &evals) : m.fx_init(ode, t0, tf, y0, &evals);
     if (!ok) { evals = 0; finish(DEB_STATUS_BAD_INPUT, t0, y0); return; }
-    TEval te(P->t_eval, P->n_eval, t0, tf);
+    const bool even = (P->solout == DEB_SOLOUT_EVEN);
+    TEval te(even ? nullptr : P->t_eval, even ? 0 : P->n_eval, t0, tf);
+    Even ev(P->even_dt, t0, tf);
     // adaptive family without bi: cubic Hermite on (t_prev, t, y_prev, y, dydt_prev, dydt), adaptive/ordinary.rs:282-295
     auto interp = [&](double tv) { return tb.dp ? m.dp_interpolate(tv) : m.fx_interpolate(tv); };
-    solout_teval(te, m.t, m.t_prev, m.y, interp, ye, n, &n_emit);  // :160
+    auto record = [&]() {
+        if (even) solout_even(ev, m.t, m.t_prev, m.y, m.y_prev, interp, ye, n, &n_emit);
+        else solout_teval(te, m.t, m.t_prev, m.y, interp, ye, n, &n_emit);
+    };
+    record();  // :160
     const double eps10 = DBL_EPSILON * 10.0;
     for (;;) {
         if ((m.t + m.h - tf) * dir > 0.0) {  // :193-209
@@ -572,7 +633,7 @@ void solve_one(const deb_ode_problem* P, const SysInfo& si, const Tableau& tb, i
         }
         if (m.rejected) { rej += 1; continue; }  // :218-221
         acc += 1;
-        solout_teval(te, m.t, m.t_prev, m.y, interp, ye, n, &n_emit);
+        record();
         if (std::fabs(tf - m.t) <= eps10) break;  // :263
     }
     finish(status, m.t, m.y);

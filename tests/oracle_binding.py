@@ -50,7 +50,7 @@ def oracle_solve(ivp, n_threads=0):
     rc = fn(C.byref(P), C.byref(res), int(n_threads))
     if rc != 0:
         raise ValueError(f"oracle rejected the problem (rc={rc})")
-    rows = deb._plan_rows(ivp._t_eval, ivp.t0, ivp.tf)
+    rows = deb._plan_rows(ivp._t_eval, ivp.t0, ivp.tf) if ivp._even_dt <= 0.0 else deb._even_rows(ivp.t0, ivp.tf, ivp._even_dt)
     return ivp.wrap_result(arrs, rows, res)
 
 

@@ -96,7 +96,52 @@ def h_init(f, t0, tf, y0, order, rtol, atol, h_min, h_max):
     return h * posneg
 
 
-def solve_dp(f, method, t0, tf, y0, rtol=1e-6, atol=1e-6, t_eval=(), h0=0.0, h_min=0.0, h_max=math.inf, max_steps=10000,
+def make_even_solout(dt, t0, tf, rows, interpolate):
+    """EvenSolout::solout, /root/reference/src/solout/even.rs:69-199.  `interpolate(ti)` is the method's dense output."""
+    dirn = signum(tf - t0)
+    st = dict(last=None)
+    tol = abs(dt) * 1e-12 + 2.220446049250313e-16 * 10.0
+
+    def solout(t_curr, t_prev, y_curr, y_prev):
+        offset = math.fmod(t0, dt)
+        if st["last"] is not None:
+            start_t = st["last"] + dt * dirn
+        else:
+            if abs(t_prev - t0) < 2.220446049250313e-16:
+                rows.append((t0, list(y_prev)))
+                st["last"] = t0
+                start_t = t0 + dt * dirn
+            else:
+                rem = math.fmod(t_prev - offset, dt)
+                if dirn > 0:
+                    start_t = t_prev if abs(rem) < 2.220446049250313e-16 else t_prev + (dt - rem)
+                else:
+                    start_t = t_prev if abs(rem) < 2.220446049250313e-16 else t_prev - rem
+        ti = start_t
+        while (dirn > 0 and ti <= t_curr) or (dirn < 0 and ti >= t_curr):
+            if (dirn > 0 and t_prev <= ti <= t_curr) or (dirn < 0 and t_prev >= ti >= t_curr):
+                if st["last"] is not None and abs(ti - st["last"]) <= tol:
+                    pass
+                else:
+                    rows.append((ti, interpolate(ti)))
+                    st["last"] = ti
+            ti += dt * dirn
+        if t_curr == tf:
+            if st["last"] is not None:
+                if abs(st["last"] - tf) <= tol:
+                    rows.pop()
+                    rows.append((tf, list(y_curr)))
+                    st["last"] = tf
+                elif st["last"] != tf:
+                    rows.append((tf, list(y_curr)))
+                    st["last"] = tf
+            else:
+                rows.append((tf, list(y_curr)))
+                st["last"] = tf
+    return solout
+
+
+def solve_dp(f, method, t0, tf, y0, rtol=1e-6, atol=1e-6, t_eval=(), even=None, h0=0.0, h_min=0.0, h_max=math.inf, max_steps=10000,
              safety=0.9, min_scale=0.2, max_scale=10.0):
     """Returns dict(status, t, y, accepted, rejected, evals, rows=[(t, y)])."""
     T = TAB["DOPRI5" if method == "dopri5" else "DOP853"]
@@ -157,6 +202,10 @@ def solve_dp(f, method, t0, tf, y0, rtol=1e-6, atol=1e-6, t_eval=(), h0=0.0, h_m
                 idx += 1
         state["idx"] = idx
 
+    y_before = list(y)
+    if even is not None:
+        even_solout = make_even_solout(even, t0, tf, rows, interpolate)
+        solout = lambda tc, tp, yc: even_solout(tc, tp, yc, y_before)
     solout(t, t_prev, y)
     status = "Complete"
     while True:

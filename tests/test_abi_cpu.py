@@ -53,6 +53,7 @@ def test_struct_layout_matches_header(lib):
 int main(void) {
   printf("%zu %zu %zu %zu %zu\n", sizeof(deb_erk_options), sizeof(deb_ode_problem), sizeof(deb_sde_problem), sizeof(deb_result), sizeof(deb_heat_problem));
   printf("%zu %zu %zu %zu\n", offsetof(deb_ode_problem, opt), offsetof(deb_ode_problem, device), offsetof(deb_result, n_rows), offsetof(deb_heat_problem, status));
+  printf("%zu\n", offsetof(deb_ode_problem, even_dt));
   printf("%zu %zu\n", offsetof(deb_sde_problem, seed), offsetof(deb_sde_problem, device));
   return 0; }'''
     with tempfile.TemporaryDirectory() as d:
@@ -63,6 +64,7 @@ int main(void) {
     want = [C.sizeof(deb.ErkOptions), C.sizeof(deb.OdeProblem), C.sizeof(deb.SdeProblem), C.sizeof(deb.Result), C.sizeof(deb.HeatProblem),
             deb.OdeProblem.opt.offset, deb.OdeProblem.device.offset, deb.Result.n_rows.offset, deb.HeatProblem.status.offset,
             deb.SdeProblem.seed.offset, deb.SdeProblem.device.offset]
+    want.insert(9, deb.OdeProblem.even_dt.offset)
     assert got == want
 
 

@@ -199,3 +199,16 @@ def test_adaptive_family_restatements_agree_bitwise():
         assert p["status"] == "Stiffness" and c.status[0] == deb.DEB_STATUS_STIFFNESS
         assert (p["accepted"], p["rejected"], p["evals"]) == (int(c.accepted[0]), int(c.rejected[0]), int(c.evals[0]))
         assert _same_bits(p["y"], c.y_final[0]) and p["t"] == c.t_final[0]
+
+
+def test_even_solout_restatements_agree_bitwise():
+    """EvenSolout (src/solout/even.rs:69-199): C++ oracle vs the independent Python restatement, bit for bit; and the
+    documented output shape (t0 first, tf last, spacing dt)."""
+    for meth, dt, tf in (("dopri5", 0.3, 2.0), ("dop853", 0.5, 2.0), ("dopri5", 0.25, 10.0), ("dop853", 0.7, 5.0)):
+        p = pr.solve_dp(pr.lorenz(10.0, 28.0, 8.0 / 3.0), meth, 0.0, tf, [1.0, 1.0, 1.0], rtol=1e-8, atol=1e-8, even=dt)
+        c = ob.oracle_solve(deb.EnsembleIVP.ode(deb.LorenzSystem(10.0, 28.0, 8.0 / 3.0), 0.0, tf, [[1.0, 1.0, 1.0]]).even(dt)
+                            .method(getattr(E, meth)().rtol(1e-8).atol(1e-8)))
+        sol = c[0]
+        assert [r[0] for r in p["rows"]] == sol.t.tolist()
+        assert _same_bits([r[1] for r in p["rows"]], sol.y)
+        assert sol.t[0] == 0.0 and sol.t[-1] == tf and np.allclose(np.diff(sol.t[:-1]), dt)

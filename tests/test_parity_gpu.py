@@ -485,3 +485,26 @@ def test_adaptive_family_bit_exact(ctor):
     assert (g.status == deb.DEB_STATUS_STIFFNESS).all()
     with pytest.raises(deb.Stiffness):
         g[0]
+
+
+# ------------------------------------------------------------------------------------------ EvenSolout
+@pytest.mark.parametrize("meth", ["dopri5", "dop853", "rkf45", "rk4"])
+def test_even_solout_bit_exact(meth):
+    """IVP::even(dt) (src/solout/even.rs): t0, t0+dt, ... accumulated, every point interpolated (no exact-hit shortcut),
+    and the final-point rule at tf (replace a near-duplicate / append)."""
+    y0 = ob.lorenz_ensemble_y0(1500, seed=41)
+    for dt, tf in ((0.3, 2.0), (0.5, 2.0), (0.25, 6.0), (7.0, 3.0)):  # append tf / replace at tf / many rows / dt > interval
+        def prob():
+            m = getattr(E, meth)(0.01) if meth == "rk4" else getattr(E, meth)().rtol(1e-8).atol(1e-8)
+            return deb.EnsembleIVP.ode(lorenz(), 0.0, tf, y0).even(dt).method(m)
+        g, c = prob().solve(), ob.oracle_solve(prob())
+        assert_same_solution(g, c)
+        assert (g.status == 0).all()
+        s = g[7]
+        assert s.t[0] == 0.0 and s.t[-1] == tf and len(s.t) == len(s.y)
+    # backward integration and a trajectory that stops early (MaxSteps): rows up to the failure only
+    def back():
+        m = E.dopri5().max_steps(60) if meth != "rk4" else E.rk4(-0.01).max_steps(150)
+        return deb.EnsembleIVP.ode(deb.HarmonicOscillator(1.0), 3.0, 0.0, np.tile([1.0, 0.0], (64, 1)) + np.linspace(0, 0.2, 64)[:, None]).even(0.4).method(m)
+    g, c = back().solve(), ob.oracle_solve(back())
+    assert_same_solution(g, c)
