@@ -261,8 +261,11 @@ def main():
     ops_local = OPS_PER_ATTEMPT * (acc_local + rej_local) + OPS_PER_ACCEPT * acc_local
     achieved = ops_local / (kernel_ms * 1e-3) / 1e12
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak.value / 1e12, "unit": "TFLOP/s",
-                "frac": achieved / (peak.value / 1e12), "traffic": None,
-                "kernel": "deb::dp_ensemble_kernel<SysLorenz, TabDopri5, 128, 4>", "kernel_ms": kernel_ms,
+                "frac": achieved / (peak.value / 1e12),
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on the full 10 M config (profiles/r01_dram_traffic_10M.csv):
+                # 7.60 GB + 31.64 GB; algorithmic 0.24 GB in + 24.5 GB out (24-byte rows are written as partial sectors)
+                "traffic": (39.24e9 * n / 10_000_000) if n_total == 10_000_000 else None, "traffic_unit": "bytes per launch (ncu, r01)",
+                "kernel": "deb::dp_ensemble_kernel<SysLorenz, TabDopri5, 128, 5, shared-params>", "kernel_ms": kernel_ms,
                 "peak_source": "measured in this run: register-only DADD/DMUL stream on all SMs (deb_fp64_issue_peak); "
                                "MEASURED_PEAKS.json has no FP64 entry. The reference arithmetic forbids FMA fusion, so the bound is DP "
                                "instruction issue (1 op per instruction), not the 2x DFMA figure",

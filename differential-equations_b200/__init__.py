@@ -41,6 +41,7 @@ LIB_PATH = os.path.join(_HERE, "libdeb200.so")
 # ---------------------------------------------------------------------------------------------- enums (deb_ensemble.h)
 DEB_EULER, DEB_MIDPOINT, DEB_HEUN, DEB_RALSTON, DEB_SSP_RK3, DEB_RK4, DEB_THREE_EIGHTHS = range(7)
 DEB_DOPRI5, DEB_DOP853, DEB_RKF45, DEB_CASH_KARP = 16, 17, 18, 19
+DEB_MILSTEIN = 32
 (DEB_SYS_EXPONENTIAL, DEB_SYS_LINEAR, DEB_SYS_HARMONIC, DEB_SYS_LOGISTIC, DEB_SYS_VAN_DER_POL, DEB_SYS_LORENZ,
  DEB_SYS_BRUSSELATOR, DEB_SYS_ROBERTSON) = range(8)
 DEB_SDE_OU, DEB_SDE_GBM = 0, 1
@@ -315,6 +316,18 @@ class ExplicitRungeKutta:
         opt.max_steps = self._max_steps
         opt.safety_factor, opt.min_scale, opt.max_scale = self._safety_factor, self._min_scale, self._max_scale
         opt.max_rejects = self._max_rejects
+
+
+class Milstein(ExplicitRungeKutta):
+    """Mirror of `Milstein::new(h0)` (src/methods/milstein.rs:37-68): derivative-free Milstein for SDE ensembles;
+    settings h_min, h_max, max_steps."""
+
+    def __init__(self, h0: float):
+        super().__init__(DEB_MILSTEIN, h0)
+
+    @classmethod
+    def new(cls, h0):
+        return cls(h0)
 
 
 # ---------------------------------------------------------------------------------------------- results

@@ -161,10 +161,10 @@ ode_launch_fn pick_ode(int system, int method, int* dim, int* np) {
 }
 
 typedef int (*sde_launch_fn)(const deb::SdeKernelArgs&, int sms, cudaStream_t);
-template <class Sde, class Tab>
+template <class Sde, class Tab, bool MILSTEIN = false>
 int launch_sde(const deb::SdeKernelArgs& a, int sms, cudaStream_t st) {
     constexpr int BLOCK = 256;
-    auto kern = deb::sde_ensemble_kernel<Sde, Tab, BLOCK>;
+    auto kern = deb::sde_ensemble_kernel<Sde, Tab, BLOCK, MILSTEIN>;
     long long blocks = (a.n_traj + BLOCK - 1) / BLOCK;
     const long long cap = (long long)sms * 8 * 16;
     if (blocks > cap) blocks = cap;
@@ -183,6 +183,7 @@ sde_launch_fn pick_sde_method(int method) {
         case DEB_SSP_RK3: return launch_sde<Sde, deb::TabSspRk3>;
         case DEB_RK4: return launch_sde<Sde, deb::TabRk4>;
         case DEB_THREE_EIGHTHS: return launch_sde<Sde, deb::TabThreeEighths>;
+        case DEB_MILSTEIN: return launch_sde<Sde, deb::TabEuler, true>;
     }
     return nullptr;
 }
@@ -711,7 +712,7 @@ extern "C" int deb_solve_sde(const deb_sde_problem* P, deb_result* R) {
     if (P->system == DEB_SDE_OU) { launch = pick_sde_method<deb::SdeOU>(P->method); np = deb::SdeOU::NP; }
     else if (P->system == DEB_SDE_GBM) { launch = pick_sde_method<deb::SdeGBM>(P->method); np = deb::SdeGBM::NP; }
     else return fail(DEB_ERR_BAD_ARG, "unknown SDE system id");
-    if (!launch) return fail(DEB_ERR_UNSUPPORTED, "SDE ensembles take a fixed-step method id");
+    if (!launch) return fail(DEB_ERR_UNSUPPORTED, "SDE ensembles take a fixed-step method id or DEB_MILSTEIN");
     if (P->dim != 1 || P->n_params != np) return fail(DEB_ERR_BAD_ARG, "dim / n_params do not match the SDE system");
     if (P->n_traj < 0 || P->n_eval < 0) return fail(DEB_ERR_BAD_ARG, "negative size");
     if (P->n_traj > 0 && (!P->y0 || !P->params)) return fail(DEB_ERR_BAD_ARG, "NULL y0/params");
@@ -1019,9 +1020,10 @@ extern "C" int deb_ensemble_stats(const double* y_eval, const int32_t* n_emitted
     struct SmallFree { void* p; cudaStream_t st; ~SmallFree() { if (p) cudaFreeAsync(p, st); } } sf{scratch, st};
     double* partial = (double*)scratch;
     long long* pcount = (long long*)((char*)scratch + pbytes);
-    deb::stats_partial_kernel<<<n_cta, 256, 0, st>>>(dy, dn, n_traj, n_eval, dim, partial, pcount);
+    const int pthreads = std::min(512, ((ne + 31) / 32) * 32);
+    deb::stats_partial_kernel<<<n_cta, pthreads, 0, st>>>(dy, dn, n_traj, n_eval, dim, partial, pcount);
     DEB_CUDA(cudaGetLastError());
-    deb::stats_final_kernel<<<(ne + 127) / 128, 128, 0, st>>>(partial, pcount, n_cta, n_eval, dim, ds, dc);
+    deb::stats_final_kernel<<<(ne * 32 + 127) / 128, 128, 0, st>>>(partial, pcount, n_cta, n_eval, dim, ds, dc);
     DEB_CUDA(cudaGetLastError());
     if (host) {
         DEB_CUDA(cudaMemcpyAsync(sums, ds, sizeof(double) * 2 * ne, cudaMemcpyDeviceToHost, st));

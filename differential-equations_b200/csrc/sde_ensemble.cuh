@@ -35,7 +35,9 @@ struct SdeKernelArgs {
     int* evals;
 };
 
-template <class Sde, class Tab, int BLOCK>
+// MILSTEIN: derivative-free Milstein step (/root/reference/src/methods/milstein.rs:107-180) instead of the stochastic ERK step
+// (Tab is then unused).
+template <class Sde, class Tab, int BLOCK, bool MILSTEIN = false>
 __global__ void __launch_bounds__(BLOCK) sde_ensemble_kernel(const SdeKernelArgs a) {
     constexpr int NP = Sde::NP, S = Tab::S;
     const double t0 = a.t0, tf = a.tf;
@@ -59,7 +61,7 @@ __global__ void __launch_bounds__(BLOCK) sde_ensemble_kernel(const SdeKernelArgs
             fin = DEB_STATUS_BAD_INPUT;
         } else {
             dydt = Sde::drift(t, y, p);
-            evals = 2;  // drift + diffusion (the initial diffusion value is not used)
+            evals = MILSTEIN ? 1 : 2;  // ERK: drift + diffusion (the initial diffusion value is not used); Milstein: drift only
             if (a.emit_t0) {
                 if (a.y_eval) a.y_eval[traj * a.row_stride] = y;
                 n_emit = 1;
@@ -78,6 +80,20 @@ __global__ void __launch_bounds__(BLOCK) sde_ensemble_kernel(const SdeKernelArgs
             if (steps >= a.max_steps) { fin = DEB_STATUS_MAX_STEPS; break; }  // stochastic.rs:74-83
             const unsigned long long q = (unsigned long long)steps;       // normal index of this step (dim = 1)
             steps += 1;
+            if (h != h_cached) { h_cached = h; sqrt_h = sqrt(h); }
+            double z;
+            if ((q & 1ull) == 0) normal_pair(a.seed, path, q >> 1, &z, &z_odd);
+            else z = z_odd;
+            const double dw = sqrt_h * z;  // noise(h, dw)
+            double y_next;
+            if (MILSTEIN) {
+                const double g = Sde::diffusion(t, y, p);
+                const double g_aux = Sde::diffusion(t, y + sqrt_h * g, p);  // b(t_n, y_n + b sqrt(h))
+                const double factor = 1.0 / (2.0 * sqrt_h);
+                const double milstein_term = ((g_aux - g) * (dw * dw - h)) * factor;  // milstein.rs:148-156
+                y_next = ((y + dydt * h) + g * dw) + milstein_term;                   // milstein.rs:158-170
+                evals += 3;  // diffusion, auxiliary diffusion, new drift
+            } else {
             double k[S];
             k[0] = dydt;
 #pragma unroll
@@ -95,16 +111,11 @@ __global__ void __launch_bounds__(BLOCK) sde_ensemble_kernel(const SdeKernelArgs
                 if (Tab::b(i) != 0.0) drift_inc = __dadd_rn(drift_inc, (Tab::bv(i) * h) * k[i]);
             }
             const double g = Sde::diffusion(t, y, p);  // stochastic.rs:113-115
-            // noise(h, dw), stochastic.rs:118-119
-            double z;
-            if ((q & 1ull) == 0) normal_pair(a.seed, path, q >> 1, &z, &z_odd);
-            else z = z_odd;
-            if (h != h_cached) { h_cached = h; sqrt_h = sqrt(h); }
-            const double dw = sqrt_h * z;
-            const double y_next = (y + drift_inc) + g * dw;  // stochastic.rs:122-128 (coefficients 1.0)
+            y_next = (y + drift_inc) + g * dw;         // stochastic.rs:122-128 (coefficients 1.0); dw = noise(h), :118-119
+            evals += S + 1;  // S-1 drift stages + diffusion + new drift
+            }
             const double t_new = t + h;
             const double d_new = Sde::drift(t_new, y_next, p);
-            evals += S + 1;  // S-1 drift stages + diffusion + new drift
             while ((dir > 0.0) ? (te <= t_new) : (te >= t_new)) {
                 double row;
                 if (te == t_new) row = y_next;

@@ -70,7 +70,9 @@ typedef enum deb_method {
     DEB_DOP853 = 17,
     /* adaptive family with y_high - y_low error estimate (src/methods/erk/adaptive/mod.rs:47-60) */
     DEB_RKF45 = 18,
-    DEB_CASH_KARP = 19
+    DEB_CASH_KARP = 19,
+    /* SDE only: derivative-free Milstein, Milstein::new(h) (src/methods/milstein.rs:37-180) */
+    DEB_MILSTEIN = 32
 } deb_method;
 
 /* Built-in right-hand sides (`ODE::diff`, src/ode/ode.rs:44).  A Rust closure cannot cross to the device,

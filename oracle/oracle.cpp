@@ -677,10 +677,15 @@ void solve_one_sde(const deb_sde_problem* P, const SdeSys& ss, const Tableau& tb
     double h = h0, t = t0, y = y0, dydt = 0.0, g = 0.0;
     int64_t steps = 0;
     const int S = tb.stages, I = tb.dense;
+    const bool milstein = (P->method == DEB_MILSTEIN);
     double k[8];
     ss.drift(t, y, &dydt, p);
-    ss.diffusion(t, y, &g, p);
-    evals += 2;
+    if (milstein) {
+        evals += 1;  // Milstein::init evaluates the drift only, milstein.rs:88-100
+    } else {
+        ss.diffusion(t, y, &g, p);
+        evals += 2;
+    }
     double t_prev = t, y_prev = y;
     TEval te(P->t_eval, P->n_eval, t0, tf);
     auto emit = [&](double t_curr, double tp, double y_curr) {
@@ -703,6 +708,37 @@ void solve_one_sde(const deb_sde_problem* P, const SdeSys& ss, const Tableau& tb
         if (steps >= P->opt.max_steps) { status = DEB_STATUS_MAX_STEPS; break; }
         steps += 1;
         t_prev = t; y_prev = y;
+        if (milstein) {  // Milstein::step, milstein.rs:107-180 (scalar state)
+            ss.diffusion(t, y, &g, p);
+            evals += 1;
+            double dw = deb_ref::wiener_increment(P->seed, path, (uint64_t)(steps - 1), 0, 1, h);
+            double sqrt_h = std::sqrt(h);
+            double y_aux = y;
+            y_aux += sqrt_h * g;
+            double g_aux = 0.0;
+            ss.diffusion(t, y_aux, &g_aux, p);
+            evals += 1;
+            double dw_sq = dw * dw;
+            double factor = 1.0 / (2.0 * sqrt_h);
+            double diff = g_aux - g;
+            double dws_minus_h = dw_sq - h;
+            double milstein_term = diff * dws_minus_h * factor;
+            double drift_inc = dydt;
+            drift_inc *= h;
+            double diff_inc = g * dw;
+            double y_next = y;
+            y_next += 1.0 * drift_inc;
+            y_next += 1.0 * diff_inc;
+            y_next += 1.0 * milstein_term;
+            t += h;
+            y = y_next;
+            ss.drift(t, y, &dydt, p);
+            evals += 1;
+            acc += 1;
+            emit(t, t_prev, y);
+            if (std::fabs(tf - t) <= eps10) break;
+            continue;
+        }
         k[0] = dydt;
         for (int s = 1; s < S; s++) {
             double ys = y;
@@ -768,7 +804,9 @@ int orc_solve_ode(const deb_ode_problem* P, deb_result* R, int n_threads) {
 
 int orc_solve_sde(const deb_sde_problem* P, deb_result* R, int n_threads) {
     SdeSys ss; Tableau tb;
-    if (!P || !R || !get_sde(P->system, &ss) || !get_tableau(P->method, &tb) || tb.adaptive) return DEB_ERR_BAD_ARG;
+    const bool milstein = P && P->method == DEB_MILSTEIN;
+    if (milstein) get_tableau(DEB_EULER, &tb);
+    if (!P || !R || !get_sde(P->system, &ss) || (!milstein && (!get_tableau(P->method, &tb) || tb.adaptive))) return DEB_ERR_BAD_ARG;
     if (P->dim != 1 || ss.np != P->n_params) return DEB_ERR_BAD_ARG;
     if (n_threads <= 0) n_threads = orc_hardware_threads();
     Out o{R->y_eval, R->n_emitted, R->t_final, R->y_final, R->status, R->accepted, R->rejected, R->evals};

@@ -508,3 +508,20 @@ def test_even_solout_bit_exact(meth):
         return deb.EnsembleIVP.ode(deb.HarmonicOscillator(1.0), 3.0, 0.0, np.tile([1.0, 0.0], (64, 1)) + np.linspace(0, 0.2, 64)[:, None]).even(0.4).method(m)
     g, c = back().solve(), ob.oracle_solve(back())
     assert_same_solution(g, c)
+
+
+def test_milstein_matches_host_regenerated_philox():
+    """Milstein::new(h) (src/methods/milstein.rs:107-180), derivative-free correction, on GBM (multiplicative noise, where
+    the correction is non-zero) and OU (additive noise: the correction vanishes identically)."""
+    n = 4096
+    for sysm, y0, tf, h in ((deb.GeometricBrownianMotion(0.1, 0.2), 100.0, 1.0, 1e-3), (deb.OrnsteinUhlenbeck(0.5, 1.0, 0.3), 5.0, 2.0, 0.01)):
+        def prob(meth):
+            return deb.EnsembleIVP.sde(sysm, 0.0, tf, np.full(n, y0), seed=7, path_offset=10 ** 10).t_eval([tf / 3, tf]).method(meth)
+        g, c = prob(deb.Milstein.new(h)).solve(), ob.oracle_solve(prob(deb.Milstein.new(h)))
+        assert_same_solution(g, c, exact=False, rtol=1e-12)
+        assert (g.status == 0).all() and np.array_equal(g.evals, 1 + 3 * g.accepted)
+        em = prob(E.euler(h)).solve()
+        if sysm.system_id == deb.DEB_SDE_OU:
+            np.testing.assert_allclose(g.y_final, em.y_final, rtol=1e-12)  # additive noise: Milstein == Euler-Maruyama
+        else:
+            assert np.abs(g.y_final - em.y_final).max() > 1e-6               # multiplicative noise: the correction acts
