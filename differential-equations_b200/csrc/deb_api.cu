@@ -127,9 +127,22 @@ ode_launch_fn pick_ode_method(int method) {
             }
         }
     }
+    if (method == DEB_DOP853 && Sys::DIM == 2) {  // EXPERIMENT: launch-shape variants
+        const char* v = getenv("DEB_DP8_VARIANT");
+        if (v) {
+            switch (atoi(v)) {
+                case 1: return launch_dp<Sys, deb::TabDop853, 128, 3>;
+                case 2: return launch_dp<Sys, deb::TabDop853, 128, 2>;
+                case 3: return launch_dp<Sys, deb::TabDop853, 64, 7>;
+                case 4: return launch_dp<Sys, deb::TabDop853, 64, 8>;
+                case 5: return launch_dp<Sys, deb::TabDop853, 256, 1>;
+            }
+        }
+    }
     switch (method) {
         case DEB_DOPRI5: return launch_dp<Sys, deb::TabDopri5, 128, 5>;  // 96 regs, no spills, 20 warps/SM (sweep: profiles/)
-        case DEB_DOP853: return launch_dp<Sys, deb::TabDop853, 128, 2>;
+        // DOP853: 12 stage vectors; 4 CTAs/SM (<= 128 regs) for dim <= 2, 3 CTAs/SM (<= 168 regs) for dim 3 (sweep: DESIGN.md 7)
+        case DEB_DOP853: return (Sys::DIM <= 2) ? launch_dp<Sys, deb::TabDop853, 128, 4> : launch_dp<Sys, deb::TabDop853, 128, 3>;
         case DEB_RKF45: return launch_dp<Sys, deb::TabRkf45, 128, 4>;
         case DEB_CASH_KARP: return launch_dp<Sys, deb::TabCashKarp, 128, 4>;
         case DEB_EULER: return launch_fixed<Sys, deb::TabEuler>;
@@ -282,7 +295,11 @@ int user_kernel(UserSystem& us, int device, int method, UserKernel** out) {
     const NvrtcApi* rt = nvrtc_api();
     if (!rt) return fail(DEB_ERR_UNSUPPORTED, "libnvrtc not found: user-defined systems need the NVRTC runtime compiler");
     // occupancy hint: stage vectors live in registers, wider systems get the whole register file of fewer CTAs
-    const int min_blocks = adaptive ? (us.dim <= 3 ? (method == DEB_DOPRI5 ? 4 : 2) : (us.dim <= 6 ? 2 : 1)) : 1;
+    int min_blocks = 1;
+    if (adaptive) {
+        if (method == DEB_DOP853) min_blocks = us.dim <= 2 ? 4 : us.dim == 3 ? 3 : us.dim <= 6 ? 2 : 1;
+        else min_blocks = us.dim <= 3 ? 5 : us.dim <= 6 ? 3 : us.dim <= 10 ? 2 : 1;
+    }
     char expr[256];
     if (adaptive) snprintf(expr, sizeof expr, "deb::dp_ensemble_kernel<deb::UserSys, %s, 128, %d, false>", tab, min_blocks);
     else snprintf(expr, sizeof expr, "deb::fixed_ensemble_kernel<deb::UserSys, %s, 128>", tab);

@@ -140,12 +140,62 @@ def c5(log2n, reps):
                          "note": "whole deb_solve_heat_mol call incl. buffer allocation, D2D copy in/out and 401 launches"}}
 
 
+def widened(n, reps):
+    """The widened rows: RKF45 / Cash-Karp, EvenSolout, a user-defined (NVRTC) right-hand side, on the C2 shape."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    y0h = deb.perturbed_ensemble([1.0, 1.0, 1.0], np.arange(n))
+    y0 = torch.from_numpy(y0h).to(dev)
+    prm = np.array([10.0, 28.0, 8.0 / 3.0])
+    te = np.arange(1.0, 101.0)
+    user = deb.ode_from_source(3, "const double x = y[0], yv = y[1], z = y[2]; dydt[0] = p[0]*(yv-x); dydt[1] = x*(p[1]-z)-yv; dydt[2] = x*yv-p[2]*z;", prm)
+    out = []
+    for label, system, method, solout in (("DOPRI5 t_eval (C2 shape)", deb.DEB_SYS_LORENZ, deb.DEB_DOPRI5, 0), ("DOPRI5 even(1.0)", deb.DEB_SYS_LORENZ, deb.DEB_DOPRI5, 1),
+                                          ("RKF45 t_eval", deb.DEB_SYS_LORENZ, deb.DEB_RKF45, 0), ("Cash-Karp t_eval", deb.DEB_SYS_LORENZ, deb.DEB_CASH_KARP, 0),
+                                          ("DOP853 t_eval", deb.DEB_SYS_LORENZ, deb.DEB_DOP853, 0), ("user-defined Lorenz (NVRTC) DOPRI5 t_eval", user.system_id, deb.DEB_DOPRI5, 0)):
+        P = deb.OdeProblem()
+        P.struct_size = C.sizeof(deb.OdeProblem)
+        P.system, P.method, P.dim, P.n_params = system, method, 3, 3
+        P.n_traj, P.y0, P.params, P.params_shared = n, y0.data_ptr(), prm.ctypes.data, 1
+        P.n_eval, P.t_eval, P.t0, P.tf = (102 if solout else 100), te.ctypes.data_as(deb._dp), 0.0, 100.0
+        lib.deb_erk_options_default(C.byref(P.opt))
+        P.opt.rtol = 1e-8
+        P.solout, P.even_dt = solout, 1.0
+        P.device, P.memspace, P.stream = 0, deb.DEB_MEM_DEVICE, stream.cuda_stream
+        R, bufs = result_buffers(n, 102, 3)
+        def run():
+            assert lib.deb_solve_ode(C.byref(P), C.byref(R)) == 0, lib.deb_last_error()
+        best, avg = timed(run, reps)
+        acc = int(bufs["accepted"].sum(dtype=torch.int64)); rej = int(bufs["rejected"].sum(dtype=torch.int64))
+        out.append({"config": label, "n_traj": n, "ms": best, "accepted": acc, "rejected": rej, "complete": int((bufs["status"] == 0).sum()),
+                    "accepted_steps_per_s": acc / (best * 1e-3)})
+    # Milstein vs Euler-Maruyama, GBM
+    for label, meth in (("GBM Euler-Maruyama", deb.DEB_EULER), ("GBM Milstein", deb.DEB_MILSTEIN)):
+        params, y0v = np.array([0.1, 0.2]), np.array([100.0])
+        tev = np.array([1.0])
+        P = deb.SdeProblem()
+        P.struct_size = C.sizeof(deb.SdeProblem)
+        P.system, P.method, P.dim, P.n_params = deb.DEB_SDE_GBM, meth, 1, 2
+        P.n_traj, P.y0, P.y0_shared, P.params, P.params_shared = 10 * n, y0v.ctypes.data, 1, params.ctypes.data, 1
+        P.n_eval, P.t_eval, P.t0, P.tf = 1, tev.ctypes.data_as(deb._dp), 0.0, 1.0
+        lib.deb_erk_options_default(C.byref(P.opt))
+        P.opt.h0 = 1e-3
+        P.seed = 2026
+        P.device, P.memspace, P.stream = 0, deb.DEB_MEM_DEVICE, stream.cuda_stream
+        R, bufs = result_buffers(10 * n, 1, 1)
+        def run():
+            assert lib.deb_solve_sde(C.byref(P), C.byref(R)) == 0, lib.deb_last_error()
+        best, avg = timed(run, reps)
+        out.append({"config": label, "n_paths": 10 * n, "ms": best, "path_steps_per_s": int(bufs["accepted"].sum(dtype=torch.int64)) / (best * 1e-3)})
+    return out
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--c3", type=int, default=4_000_000)
     ap.add_argument("--c4", type=int, default=100_000_000)
     ap.add_argument("--c5", type=int, default=24)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--widened", type=int, default=0, help="also time the widened rows on this many trajectories")
     a = ap.parse_args()
     if a.c3:
         print(json.dumps(c3(a.c3, a.reps)), flush=True)
@@ -154,3 +204,6 @@ if __name__ == "__main__":
             print(json.dumps(c4(a.c4, w, a.reps)), flush=True)
     if a.c5:
         print(json.dumps(c5(a.c5, a.reps)), flush=True)
+    if a.widened:
+        for r in widened(a.widened, a.reps):
+            print(json.dumps(r), flush=True)
