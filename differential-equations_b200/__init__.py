@@ -41,6 +41,7 @@ LIB_PATH = os.path.join(_HERE, "libdeb200.so")
 # ---------------------------------------------------------------------------------------------- enums (deb_ensemble.h)
 DEB_EULER, DEB_MIDPOINT, DEB_HEUN, DEB_RALSTON, DEB_SSP_RK3, DEB_RK4, DEB_THREE_EIGHTHS = range(7)
 DEB_DOPRI5, DEB_DOP853, DEB_RKF45, DEB_CASH_KARP = 16, 17, 18, 19
+(DEB_RKV655E, DEB_RKV656E, DEB_RKV766E, DEB_RKV767E, DEB_RKV877E, DEB_RKV878E, DEB_RKV988E, DEB_RKV989E) = range(20, 28)
 DEB_MILSTEIN = 32
 (DEB_SYS_EXPONENTIAL, DEB_SYS_LINEAR, DEB_SYS_HARMONIC, DEB_SYS_LOGISTIC, DEB_SYS_VAN_DER_POL, DEB_SYS_LORENZ,
  DEB_SYS_BRUSSELATOR, DEB_SYS_ROBERTSON) = range(8)
@@ -49,7 +50,7 @@ DEB_STATUS_COMPLETE, DEB_STATUS_MAX_STEPS, DEB_STATUS_STEP_SIZE, DEB_STATUS_STIF
 DEB_MEM_HOST, DEB_MEM_DEVICE = 0, 1
 DEB_SOLOUT_T_EVAL, DEB_SOLOUT_EVEN = 0, 1
 DEB_OK, DEB_ERR_BAD_ARG, DEB_ERR_NO_DEVICE, DEB_ERR_CUDA, DEB_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
-DEB_ABI_VERSION = 3
+DEB_ABI_VERSION = 4
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -94,7 +95,7 @@ class HeatProblem(C.Structure):
 
 
 # every symbol include/deb_ensemble.h declares (tests check that the library exports all of them)
-ABI_SYMBOLS = ["deb_abi_version", "deb_last_error", "deb_device_count", "deb_erk_options_default", "deb_define_ode", "deb_solve_ode",
+ABI_SYMBOLS = ["deb_abi_version", "deb_last_error", "deb_device_count", "deb_erk_options_default", "deb_define_ode", "deb_check_ode", "deb_solve_ode",
                "deb_solve_sde", "deb_solve_heat_mol", "deb_heat_rhs", "deb_ensemble_stats", "deb_malloc", "deb_free", "deb_memcpy_h2d",
                "deb_memcpy_d2h", "deb_synchronize", "deb_pow_device", "deb_fp64_issue_peak"]
 
@@ -120,6 +121,7 @@ def load_library() -> C.CDLL:
     lib.deb_solve_sde.argtypes = [C.POINTER(SdeProblem), C.POINTER(Result)]
     lib.deb_solve_heat_mol.argtypes = [C.POINTER(HeatProblem)]
     lib.deb_define_ode.argtypes = [C.c_int32, C.c_int32, C.c_char_p, _ip]
+    lib.deb_check_ode.argtypes = [C.c_int32, C.c_int32]
     lib.deb_heat_rhs.argtypes = [C.POINTER(HeatProblem), C.c_void_p, C.c_void_p]
     lib.deb_erk_options_default.argtypes = [C.POINTER(ErkOptions)]
     lib.deb_erk_options_default.restype = None
@@ -228,6 +230,13 @@ def ode_from_source(dim: int, diff_body: str, params=(), lib=None) -> OdeSystem:
     return OdeSystem(sid.value, int(dim), prm)
 
 
+def check_ode(system: OdeSystem, method, lib=None) -> None:
+    """Compile a user-defined system for a method now (NVRTC, no GPU needed); raises ValueError with the compiler log."""
+    lib = lib or load_library()
+    mid = method.method_id if hasattr(method, "method_id") else int(method)
+    _check(lib, lib.deb_check_ode(int(system.system_id), mid), "deb_check_ode")
+
+
 @dataclass
 class SdeSystem:
     system_id: int
@@ -261,7 +270,7 @@ class ExplicitRungeKutta:
         self._h_min = 0.0
         self._h_max = math.inf
         self._max_steps = 10_000
-        self._max_rejects = 100  # read by the adaptive family (rkf45, cash_karp) only
+        self._max_rejects = 100  # read by the adaptive family (rkf45, cash_karp, rkv*) only
         self._safety_factor = 0.9
         self._min_scale = 0.2
         self._max_scale = 10.0
@@ -275,6 +284,23 @@ class ExplicitRungeKutta:
     def rkf45(cls): return cls(DEB_RKF45)          # adaptive/mod.rs:47-53
     @classmethod
     def cash_karp(cls): return cls(DEB_CASH_KARP)  # adaptive/mod.rs:54-60
+    # Verner pairs with a dense-output polynomial, adaptive/mod.rs:59-122
+    @classmethod
+    def rkv655e(cls): return cls(DEB_RKV655E)
+    @classmethod
+    def rkv656e(cls): return cls(DEB_RKV656E)
+    @classmethod
+    def rkv766e(cls): return cls(DEB_RKV766E)
+    @classmethod
+    def rkv767e(cls): return cls(DEB_RKV767E)
+    @classmethod
+    def rkv877e(cls): return cls(DEB_RKV877E)
+    @classmethod
+    def rkv878e(cls): return cls(DEB_RKV878E)
+    @classmethod
+    def rkv988e(cls): return cls(DEB_RKV988E)
+    @classmethod
+    def rkv989e(cls): return cls(DEB_RKV989E)
     @classmethod
     def euler(cls, h0): return cls(DEB_EULER, h0)
     @classmethod

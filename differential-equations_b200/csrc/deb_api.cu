@@ -24,6 +24,7 @@
 #include "ens_stats.cuh"
 #include "erk_ensemble.cuh"
 #include "erk_fixed.cuh"
+#include "ode_dispatch.cuh"
 #include "mol_heat.cuh"
 #include "sde_ensemble.cuh"
 #include "systems.cuh"
@@ -36,6 +37,12 @@ int fail(int code, const std::string& msg) {
     g_err = msg;
     return code;
 }
+
+}  // namespace
+
+int deb_fail(int code, const char* msg) { return fail(code, msg); }
+
+namespace {
 
 #define DEB_CUDA(call)                                                                                  \
     do {                                                                                                \
@@ -74,30 +81,7 @@ int device_info(int device, DeviceInfo* di) {
 }
 
 // ------------------------------------------------------------------------------------------------ kernel table
-typedef int (*ode_launch_fn)(const deb::OdeKernelArgs&, int sms, cudaStream_t);
-
-template <class Sys, class Tab, int BLOCK, int MIN_BLOCKS, bool SHARED_P>
-int launch_dp_impl(const deb::OdeKernelArgs& a, int sms, cudaStream_t st) {
-    auto kern = deb::dp_ensemble_kernel<Sys, Tab, BLOCK, MIN_BLOCKS, SHARED_P>;
-    int per_sm = 0;
-    DEB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, 0));
-    if (per_sm < 1) per_sm = 1;
-    // persistent grid: every resident CTA slot of every SM, but never more threads than trajectories
-    long long blocks = (long long)sms * per_sm;
-    const long long need = (a.n_traj + BLOCK - 1) / BLOCK;
-    if (blocks > need) blocks = need;
-    if (blocks < 1) blocks = 1;
-    kern<<<(unsigned)blocks, BLOCK, 0, st>>>(a);
-    DEB_CUDA(cudaGetLastError());
-    return DEB_OK;
-}
-
-template <class Sys, class Tab, int BLOCK, int MIN_BLOCKS>
-int launch_dp(const deb::OdeKernelArgs& a, int sms, cudaStream_t st) {
-    // a.pc is filled by the caller iff the parameter set is shared (params_stride == 0) and lives on the host
-    if (a.params_stride == 0 && a.params == nullptr) return launch_dp_impl<Sys, Tab, BLOCK, MIN_BLOCKS, true>(a, sms, st);
-    return launch_dp_impl<Sys, Tab, BLOCK, MIN_BLOCKS, false>(a, sms, st);
-}
+// (ode_launch_fn and the adaptive-family lookups: ode_dispatch.cuh)
 
 template <class Sys, class Tab>
 int launch_fixed(const deb::OdeKernelArgs& a, int sms, cudaStream_t st) {
@@ -113,38 +97,8 @@ int launch_fixed(const deb::OdeKernelArgs& a, int sms, cudaStream_t st) {
 }
 
 template <class Sys>
-ode_launch_fn pick_ode_method(int method) {
-    if (method == DEB_DOPRI5 && Sys::DIM == 3) {  // EXPERIMENT: launch-shape variants
-        const char* v = getenv("DEB_DP_VARIANT");
-        if (v) {
-            switch (atoi(v)) {
-                case 1: return launch_dp<Sys, deb::TabDopri5, 64, 9>;
-                case 2: return launch_dp<Sys, deb::TabDopri5, 64, 10>;
-                case 3: return launch_dp<Sys, deb::TabDopri5, 32, 19>;
-                case 4: return launch_dp<Sys, deb::TabDopri5, 32, 21>;
-                case 5: return launch_dp<Sys, deb::TabDopri5, 256, 2>;
-                case 6: return launch_dp<Sys, deb::TabDopri5, 128, 4>;
-            }
-        }
-    }
-    if (method == DEB_DOP853 && Sys::DIM == 2) {  // EXPERIMENT: launch-shape variants
-        const char* v = getenv("DEB_DP8_VARIANT");
-        if (v) {
-            switch (atoi(v)) {
-                case 1: return launch_dp<Sys, deb::TabDop853, 128, 3>;
-                case 2: return launch_dp<Sys, deb::TabDop853, 128, 2>;
-                case 3: return launch_dp<Sys, deb::TabDop853, 64, 7>;
-                case 4: return launch_dp<Sys, deb::TabDop853, 64, 8>;
-                case 5: return launch_dp<Sys, deb::TabDop853, 256, 1>;
-            }
-        }
-    }
+ode_launch_fn pick_fixed_method(int method) {
     switch (method) {
-        case DEB_DOPRI5: return launch_dp<Sys, deb::TabDopri5, 128, 5>;  // 96 regs, no spills, 20 warps/SM (sweep: profiles/)
-        // DOP853: 12 stage vectors; 4 CTAs/SM (<= 128 regs) for dim <= 2, 3 CTAs/SM (<= 168 regs) for dim 3 (sweep: DESIGN.md 7)
-        case DEB_DOP853: return (Sys::DIM <= 2) ? launch_dp<Sys, deb::TabDop853, 128, 4> : launch_dp<Sys, deb::TabDop853, 128, 3>;
-        case DEB_RKF45: return launch_dp<Sys, deb::TabRkf45, 128, 4>;
-        case DEB_CASH_KARP: return launch_dp<Sys, deb::TabCashKarp, 128, 4>;
         case DEB_EULER: return launch_fixed<Sys, deb::TabEuler>;
         case DEB_MIDPOINT: return launch_fixed<Sys, deb::TabMidpoint>;
         case DEB_HEUN: return launch_fixed<Sys, deb::TabHeun>;
@@ -156,8 +110,10 @@ ode_launch_fn pick_ode_method(int method) {
     return nullptr;
 }
 
+// (system, method) -> launcher.  The adaptive families live in their own translation units (ode_*.cu).
 ode_launch_fn pick_ode(int system, int method, int* dim, int* np) {
-#define DEB_SYS_CASE(ID, T) case ID: *dim = deb::T::DIM; *np = deb::T::NP; return pick_ode_method<deb::T>(method);
+    ode_launch_fn fixed = nullptr;
+#define DEB_SYS_CASE(ID, T) case ID: *dim = deb::T::DIM; *np = deb::T::NP; fixed = pick_fixed_method<deb::T>(method); break;
     switch (system) {
         DEB_SYS_CASE(DEB_SYS_EXPONENTIAL, SysExponential)
         DEB_SYS_CASE(DEB_SYS_LINEAR, SysLinear)
@@ -167,9 +123,18 @@ ode_launch_fn pick_ode(int system, int method, int* dim, int* np) {
         DEB_SYS_CASE(DEB_SYS_LORENZ, SysLorenz)
         DEB_SYS_CASE(DEB_SYS_BRUSSELATOR, SysBrusselator)
         DEB_SYS_CASE(DEB_SYS_ROBERTSON, SysRobertson)
+        default: *dim = -1; return nullptr;
     }
 #undef DEB_SYS_CASE
-    *dim = -1;
+    if (fixed) return fixed;
+    switch (method) {
+        case DEB_DOPRI5: case DEB_DOP853: return deb_pick_dopri(system, method);
+        case DEB_RKF45: case DEB_CASH_KARP: return deb_pick_rkf(system, method);
+        case DEB_RKV655E: case DEB_RKV656E: return deb_pick_rkv6(system, method);
+        case DEB_RKV766E: case DEB_RKV767E: return deb_pick_rkv7(system, method);
+        case DEB_RKV877E: case DEB_RKV878E: return deb_pick_rkv8(system, method);
+        case DEB_RKV988E: case DEB_RKV989E: return deb_pick_rkv9(system, method);
+    }
     return nullptr;
 }
 
@@ -274,6 +239,14 @@ const char* method_tab_name(int method, bool* adaptive) {
         case DEB_DOP853: *adaptive = true; return "deb::TabDop853";
         case DEB_RKF45: *adaptive = true; return "deb::TabRkf45";
         case DEB_CASH_KARP: *adaptive = true; return "deb::TabCashKarp";
+        case DEB_RKV655E: *adaptive = true; return "deb::TabRkv655e";
+        case DEB_RKV656E: *adaptive = true; return "deb::TabRkv656e";
+        case DEB_RKV766E: *adaptive = true; return "deb::TabRkv766e";
+        case DEB_RKV767E: *adaptive = true; return "deb::TabRkv767e";
+        case DEB_RKV877E: *adaptive = true; return "deb::TabRkv877e";
+        case DEB_RKV878E: *adaptive = true; return "deb::TabRkv878e";
+        case DEB_RKV988E: *adaptive = true; return "deb::TabRkv988e";
+        case DEB_RKV989E: *adaptive = true; return "deb::TabRkv989e";
         case DEB_EULER: return "deb::TabEuler";
         case DEB_MIDPOINT: return "deb::TabMidpoint";
         case DEB_HEUN: return "deb::TabHeun";
@@ -285,10 +258,8 @@ const char* method_tab_name(int method, bool* adaptive) {
     return nullptr;
 }
 
-// Compile (once per device/method) the ensemble kernel for a user system.  Caller holds g_user_mu.
-int user_kernel(UserSystem& us, int device, int method, UserKernel** out) {
-    auto it = us.kernels.find({device, method});
-    if (it != us.kernels.end()) { *out = &it->second; return DEB_OK; }
+// Compile the ensemble kernel for a user system and a method to a cubin (no device needed).
+int compile_user_cubin(const UserSystem& us, int method, std::vector<char>* cubin, std::string* kernel_name, bool* is_adaptive) {
     bool adaptive = false;
     const char* tab = method_tab_name(method, &adaptive);
     if (!tab) return fail(DEB_ERR_UNSUPPORTED, "unknown or unsupported method id");
@@ -298,6 +269,7 @@ int user_kernel(UserSystem& us, int device, int method, UserKernel** out) {
     int min_blocks = 1;
     if (adaptive) {
         if (method == DEB_DOP853) min_blocks = us.dim <= 2 ? 4 : us.dim == 3 ? 3 : us.dim <= 6 ? 2 : 1;
+        else if (method >= DEB_RKV655E && method <= DEB_RKV989E) min_blocks = us.dim <= 2 ? 4 : us.dim == 3 ? 3 : us.dim <= 5 ? 2 : 1;
         else min_blocks = us.dim <= 3 ? 5 : us.dim <= 6 ? 3 : us.dim <= 10 ? 2 : 1;
     }
     char expr[256];
@@ -317,7 +289,7 @@ int user_kernel(UserSystem& us, int device, int method, UserKernel** out) {
     static const char* k_stdint =
         "#pragma once\ntypedef signed char int8_t; typedef unsigned char uint8_t; typedef short int16_t; typedef unsigned short uint16_t;\n"
         "typedef int int32_t; typedef unsigned int uint32_t; typedef long long int64_t; typedef unsigned long long uint64_t;\n";
-    static const char* k_float = "#pragma once\n#define DBL_EPSILON 2.2204460492503131e-16\n";
+    static const char* k_float = "#pragma once\n#define DBL_EPSILON 2.2204460492503131e-16\n#define DBL_MAX 1.7976931348623157e+308\n";
     static const char* k_abi =
         "#pragma once\n#define DEB_MAX_DIM 16\n"
         "enum { DEB_STATUS_COMPLETE = 0, DEB_STATUS_MAX_STEPS = 1, DEB_STATUS_STEP_SIZE = 2, DEB_STATUS_STIFFNESS = 3, DEB_STATUS_BAD_INPUT = 4 };\n";
@@ -341,14 +313,25 @@ int user_kernel(UserSystem& us, int device, int method, UserKernel** out) {
     const char* lowered = nullptr;
     r = rt->GetLoweredName(prog, expr, &lowered);
     if (r != NVRTC_SUCCESS || !lowered) return fail(DEB_ERR_CUDA, "nvrtcGetLoweredName failed");
+    *kernel_name = lowered;
     size_t nbin = 0;
     rt->GetCUBINSize(prog, &nbin);
-    std::vector<char> cubin(nbin);
-    if (rt->GetCUBIN(prog, cubin.data()) != NVRTC_SUCCESS) return fail(DEB_ERR_CUDA, "nvrtcGetCUBIN failed");
+    cubin->resize(nbin);
+    if (rt->GetCUBIN(prog, cubin->data()) != NVRTC_SUCCESS) return fail(DEB_ERR_CUDA, "nvrtcGetCUBIN failed");
+    *is_adaptive = adaptive;
+    return DEB_OK;
+}
+
+// Compile and load (once per device/method) the ensemble kernel for a user system.  Caller holds g_user_mu.
+int user_kernel(UserSystem& us, int device, int method, UserKernel** out) {
+    auto it = us.kernels.find({device, method});
+    if (it != us.kernels.end()) { *out = &it->second; return DEB_OK; }
+    std::vector<char> cubin;
+    std::string lowered;
     UserKernel uk;
-    uk.adaptive = adaptive;
+    if (int rc = compile_user_cubin(us, method, &cubin, &lowered, &uk.adaptive)) return rc;
     DEB_CUDA(cudaLibraryLoadData(&uk.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
-    DEB_CUDA(cudaLibraryGetKernel(&uk.kernel, uk.lib, lowered));
+    DEB_CUDA(cudaLibraryGetKernel(&uk.kernel, uk.lib, lowered.c_str()));
     auto ins = us.kernels.emplace(std::make_pair(device, method), uk);
     *out = &ins.first->second;
     return DEB_OK;
@@ -718,6 +701,16 @@ extern "C" int deb_define_ode(int32_t dim, int32_t n_params, const char* diff_bo
     g_user_systems.push_back(std::move(us));
     *system_id = USER_SYSTEM_BASE + (int32_t)g_user_systems.size() - 1;
     return DEB_OK;
+}
+
+extern "C" int deb_check_ode(int32_t system_id, int32_t method) {
+    std::lock_guard<std::mutex> lk(g_user_mu);
+    const int u = system_id - USER_SYSTEM_BASE;
+    if (u < 0 || u >= (int)g_user_systems.size()) return fail(DEB_ERR_BAD_ARG, "not a user-defined system id");
+    std::vector<char> cubin;
+    std::string name;
+    bool adaptive = false;
+    return compile_user_cubin(*g_user_systems[u], method, &cubin, &name, &adaptive);
 }
 
 extern "C" int deb_solve_sde(const deb_sde_problem* P, deb_result* R) {

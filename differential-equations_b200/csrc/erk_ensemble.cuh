@@ -151,6 +151,40 @@ __device__ __forceinline__ void load_pow_tables(double* s_powlog, unsigned long 
 //   its step, asks for service and redoes the attempt afterwards -- same inputs, same bits.  The arithmetic is
 //   unchanged: same operands, same operations, later.  DOP853 (3 extra dense stages) interpolates on the spot.
 // SHARED_P: every trajectory uses the same parameter set (passed by value in a.pc: no registers).
+// One attempt of the adaptive family with EVERY tableau term, zero coefficients included, exactly as the reference loops
+// (adaptive/ordinary.rs:95-126): 0 * inf = NaN and all.  Out of line and through memory on purpose: it runs only for an
+// attempt whose error terms are not finite.  k[0] = f(t, y) on entry; k[1..S-1], y_new and the error norm on exit.
+template <class Sys, class Tab>
+__device__ __noinline__ void all_terms_attempt(const double* y, double* k, double t, double h, const double* p, const double* rtol,
+                                               const double* atol, double* ynew, double* err_out) {
+    constexpr int N = Sys::DIM, S = Tab::S;
+    for (int i = 1; i < S; i++) {
+        double ys[N];
+        for (int c = 0; c < N; c++) ys[c] = y[c];
+        for (int j = 0; j < i; j++) {
+            const double ah = Tab::av(i, j) * h;
+            for (int c = 0; c < N; c++) ys[c] = ys[c] + ah * k[j * N + c];
+        }
+        Sys::rhs(t + Tab::cv(i) * h, ys, k + i * N, p);
+    }
+    double ylow[N];
+    for (int c = 0; c < N; c++) { ynew[c] = y[c]; ylow[c] = y[c]; }
+    for (int i = 0; i < S; i++) {
+        const double bw = Tab::bv(i) * h;
+        for (int c = 0; c < N; c++) ynew[c] = ynew[c] + bw * k[i * N + c];
+    }
+    for (int i = 0; i < S; i++) {
+        const double bw = Tab::bhv(i) * h;
+        for (int c = 0; c < N; c++) ylow[c] = ylow[c] + bw * k[i * N + c];
+    }
+    double err = 0.0;
+    for (int c = 0; c < N; c++) {
+        const double sk = atol[c] + rtol[c] * fmax(fabs(y[c]), fabs(ynew[c]));
+        err = fmax(err, fabs((ynew[c] - ylow[c]) / sk));
+    }
+    *err_out = err;
+}
+
 template <class Sys, class Tab, int BLOCK, int MIN_BLOCKS, bool SHARED_P>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const OdeKernelArgs a) {
     constexpr int N = Sys::DIM, NP = Sys::NP, S = Tab::S, I = Tab::I, O = Tab::O;
@@ -285,8 +319,10 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
             }
             if (a.accepted) a.accepted[traj] = acc;
             if (a.rejected) a.rejected[traj] = rej;
-            // Evals.function: 1 (+2 for the automatic h0) + (S-1) per attempt + 1 (+ I-S-1 dense stages) per accepted step
-            if (a.evals) a.evals[traj] = evals_base + (S - 1) * (acc + rej) + acc * (1 + ((I > S) ? (I - S - 1) : 0));
+            // Evals.function: 1 (+2 for the automatic h0) + (S-1) per attempt + per accepted step: DP family 1 (+ I-S-1 dense
+            // stages); dense-polynomial pairs I-S dense stages (+1 unless FSAL), adaptive/ordinary.rs:145-174
+            constexpr int PER_ACC = Tab::BI_POLY ? ((I - S) + (Tab::FSAL ? 0 : 1)) : (1 + ((I > S) ? (I - S - 1) : 0));
+            if (a.evals) a.evals[traj] = evals_base + (S - 1) * (acc + rej) + acc * PER_ACC;
             if (a.n_emitted) a.n_emitted[traj] = idx;
             active = false;
             // idle dummy state: finite, never committed
@@ -380,94 +416,123 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
             const bool stepping = active && fin < 0;
             const int steps = acc + rej + 1;  // self.steps after the increment
 
-            // ---- stages, ordinary.rs:95-104 (all lanes)
-#pragma unroll
-            for (int i = 1; i < S; i++) {
-                double ys[N];
-#pragma unroll
-                for (int c = 0; c < N; c++) ys[c] = y[c];
-#pragma unroll
-                for (int j = 0; j < i; j++) {
-                    if (Tab::a(i, j) != 0.0) {
-                        const double ah = Tab::av(i, j) * h;
-#pragma unroll
-                        for (int c = 0; c < N; c++) ys[c] = ys[c] + ah * k[j][c];
-                    }
-                }
-                Sys::rhs(t + Tab::cv(i) * h, ys, k[i], p);
-            }
-            // ---- solution and error estimate
+            // ---- stages, solution and error estimate.  Terms whose tableau coefficient is zero are dropped
+            // (x + (0*h)*k == x for finite k).
             double yseg[N], ynew[N];
             const double t_new = t + h;
             double err = 0.0;
-            if (Tab::DP) {  // dormandprince/ordinary.rs:106-149
-                double es[N];
+            {
+                // stages, ordinary.rs:95-104 (all lanes)
 #pragma unroll
-                for (int c = 0; c < N; c++) { yseg[c] = 0.0; es[c] = 0.0; }
+                for (int i = 1; i < S; i++) {
+                    double ys[N];
 #pragma unroll
-                for (int i = 0; i < S; i++) {
-                    if (Tab::b(i) != 0.0) {
+                    for (int c = 0; c < N; c++) ys[c] = y[c];
 #pragma unroll
-                        for (int c = 0; c < N; c++) yseg[c] = __dadd_rn(yseg[c], Tab::bv(i) * k[i][c]);
+                    for (int j = 0; j < i; j++) {
+                        if (Tab::a(i, j) != 0.0) {
+                            const double ah = Tab::av(i, j) * h;
+#pragma unroll
+                            for (int c = 0; c < N; c++) ys[c] = ys[c] + ah * k[j][c];
+                        }
                     }
-                    if (Tab::er(i) != 0.0) {
-#pragma unroll
-                        for (int c = 0; c < N; c++) es[c] = __dadd_rn(es[c], Tab::erv(i) * k[i][c]);
-                    }
+                    Sys::rhs(t + Tab::cv(i) * h, ys, k[i], p);
                 }
-                double err2 = 0.0;
-                double sk[N];
+                if (Tab::DP) {  // dormandprince/ordinary.rs:106-149
+                    double es[N];
 #pragma unroll
-                for (int c = 0; c < N; c++) {
-                    ynew[c] = y[c] + h * yseg[c];
-                    sk[c] = a.atol[c] + a.rtol[c] * fmax(fabs(y[c]), fabs(ynew[c]));  // traits.rs:587-595
-                    const double e = es[c] / sk[c];
-                    err = err + e * e;
-                }
-                if (Tab::HAS_BH) {  // DOP853 second estimator, ordinary.rs:135-143
-                    double e2[N];
-#pragma unroll
-                    for (int c = 0; c < N; c++) e2[c] = yseg[c];
+                    for (int c = 0; c < N; c++) { yseg[c] = 0.0; es[c] = 0.0; }
 #pragma unroll
                     for (int i = 0; i < S; i++) {
-                        if (Tab::bh(i) != 0.0) {
+                        if (Tab::b(i) != 0.0) {
 #pragma unroll
-                            for (int c = 0; c < N; c++) e2[c] = e2[c] + (-Tab::bhv(i)) * k[i][c];
+                            for (int c = 0; c < N; c++) yseg[c] = __dadd_rn(yseg[c], Tab::bv(i) * k[i][c]);
+                        }
+                        if (Tab::er(i) != 0.0) {
+#pragma unroll
+                            for (int c = 0; c < N; c++) es[c] = __dadd_rn(es[c], Tab::erv(i) * k[i][c]);
+                        }
+                    }
+                    double err2 = 0.0;
+                    double sk[N];
+                    err = 0.0;
+#pragma unroll
+                    for (int c = 0; c < N; c++) {
+                        ynew[c] = y[c] + h * yseg[c];
+                        sk[c] = a.atol[c] + a.rtol[c] * fmax(fabs(y[c]), fabs(ynew[c]));  // traits.rs:587-595
+                        const double e = es[c] / sk[c];
+                        err = err + e * e;
+                    }
+                    if (Tab::HAS_BH) {  // DOP853 second estimator, ordinary.rs:135-143
+                        double e2[N];
+#pragma unroll
+                        for (int c = 0; c < N; c++) e2[c] = yseg[c];
+#pragma unroll
+                        for (int i = 0; i < S; i++) {
+                            if (Tab::bh(i) != 0.0) {
+#pragma unroll
+                                for (int c = 0; c < N; c++) e2[c] = e2[c] + (-Tab::bhv(i)) * k[i][c];
+                            }
+                        }
+#pragma unroll
+                        for (int c = 0; c < N; c++) {
+                            const double e = e2[c] / sk[c];
+                            err2 = err2 + e * e;
+                        }
+                    }
+                    double deno = err + 0.01 * err2;
+                    if (deno <= 0.0) deno = 1.0;
+                    err = fabs(h) * err * sqrt(1.0 / (deno * (double)N));  // ordinary.rs:148
+                } else {  // adaptive/ordinary.rs:107-126: y_high, y_low, infinity norm of (y_high - y_low)/sk
+                    double ylow[N];
+#pragma unroll
+                    for (int c = 0; c < N; c++) { ynew[c] = y[c]; ylow[c] = y[c]; yseg[c] = 0.0; }
+#pragma unroll
+                    for (int i = 0; i < S; i++) {
+                        if (Tab::b(i) != 0.0) {
+                            const double bw = Tab::bv(i) * h;
+#pragma unroll
+                            for (int c = 0; c < N; c++) ynew[c] = ynew[c] + bw * k[i][c];
                         }
                     }
 #pragma unroll
-                    for (int c = 0; c < N; c++) {
-                        const double e = e2[c] / sk[c];
-                        err2 = err2 + e * e;
+                    for (int i = 0; i < S; i++) {
+                        if (Tab::bh(i) != 0.0) {
+                            const double bw = Tab::bhv(i) * h;
+#pragma unroll
+                            for (int c = 0; c < N; c++) ylow[c] = ylow[c] + bw * k[i][c];
+                        }
                     }
-                }
-                double deno = err + 0.01 * err2;
-                if (deno <= 0.0) deno = 1.0;
-                err = fabs(h) * err * sqrt(1.0 / (deno * (double)N));  // ordinary.rs:148
-            } else {  // adaptive/ordinary.rs:107-126: y_high, y_low, infinity norm of (y_high - y_low)/sk
-                double ylow[N];
+                    double esum = 0.0;  // sum of the (non-negative) error terms: inf or NaN iff some term is not finite, or absurdly large
 #pragma unroll
-                for (int c = 0; c < N; c++) { ynew[c] = y[c]; ylow[c] = y[c]; yseg[c] = 0.0; }
-#pragma unroll
-                for (int i = 0; i < S; i++) {
-                    if (Tab::b(i) != 0.0) {
-                        const double bw = Tab::bv(i) * h;
-#pragma unroll
-                        for (int c = 0; c < N; c++) ynew[c] = ynew[c] + bw * k[i][c];
+                    for (int c = 0; c < N; c++) {  // error_norm_inf, traits.rs:413-434 (f64::max ignores a NaN term, as fmax does)
+                        const double sk = a.atol[c] + a.rtol[c] * fmax(fabs(y[c]), fabs(ynew[c]));
+                        const double e = fabs((ynew[c] - ylow[c]) / sk);
+                        esum = esum + e;
+                        err = fmax(err, e);
                     }
-                }
+                    // A non-finite error term means some stage value overflowed.  The reference then also produces NaN from
+                    // 0 * inf in the zero-coefficient terms dropped above, and its infinity norm drops NaN terms -- such a
+                    // step can be ACCEPTED (with a NaN state).  Redo the attempt with every term, out of line.  (Dormand-
+                    // Prince family: the 2-norm keeps NaN; the step is rejected and the controller sees min_scale either way.)
+                    if (!(esum <= DBL_MAX)) {
+                        // copies, so that the live register arrays never have their address taken
+                        double kk[S][N], yy[N], yn[N], pp[NP > 0 ? NP : 1], rt[N], at[N], ee;
 #pragma unroll
-                for (int i = 0; i < S; i++) {
-                    if (Tab::bh(i) != 0.0) {
-                        const double bw = Tab::bhv(i) * h;
+                        for (int c = 0; c < N; c++) { yy[c] = y[c]; kk[0][c] = k[0][c]; rt[c] = a.rtol[c]; at[c] = a.atol[c]; }
 #pragma unroll
-                        for (int c = 0; c < N; c++) ylow[c] = ylow[c] + bw * k[i][c];
+                        for (int q = 0; q < NP; q++) pp[q] = p[q];
+                        all_terms_attempt<Sys, Tab>(yy, &kk[0][0], t, h, pp, rt, at, yn, &ee);
+#pragma unroll
+                        for (int i = 1; i < S; i++) {
+#pragma unroll
+                            for (int c = 0; c < N; c++) k[i][c] = kk[i][c];
+                        }
+#pragma unroll
+                        for (int c = 0; c < N; c++) ynew[c] = yn[c];
+                        err = ee;
                     }
-                }
-#pragma unroll
-                for (int c = 0; c < N; c++) {  // error_norm_inf, traits.rs:413-434 (f64::max ignores a NaN term, as fmax does)
-                    const double sk = a.atol[c] + a.rtol[c] * fmax(fabs(y[c]), fabs(ynew[c]));
-                    err = fmax(err, fabs((ynew[c] - ylow[c]) / sk));
+                    __syncwarp();
                 }
             }
             // ---- controller, ordinary.rs:151-157
@@ -480,7 +545,12 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
             // ---- derivative at the new point (ordinary.rs:162; evaluated by every lane, committed only on accept)
             const bool accept = stepping && (err <= 1.0);
             double dydt[N];
-            Sys::rhs(t_new, ynew, dydt, p);
+            if constexpr (Tab::FSAL) {  // adaptive/ordinary.rs:166-169: the last stage is the derivative at the new point
+#pragma unroll
+                for (int c = 0; c < N; c++) dydt[c] = k[S - 1][c];
+            } else {
+                Sys::rhs(t_new, ynew, dydt, p);
+            }
 
             if (Tab::DP && accept && (steps % 100 == 0)) {  // stiffness test, ordinary.rs:165-194
                 // ysti = the argument of the last stage; rebuilt here (same operations, same bits) instead of being
@@ -546,16 +616,34 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
             } else {
                 if (hit) {
                     double c1[N], c2[N], c3[N];
+                    double ch[(O > 4) ? (O - 4) : 1][N];  // DP family: cont[4..O-1]
+                    double kx[(I > S) ? (I - S) : 1][N];  // stage vectors k[S..I-1]
+                    if constexpr (Tab::BI_POLY) {
+                        // extra stages of the dense-output polynomial, adaptive/ordinary.rs:145-160.  The reference evaluates
+                        // them on every accepted step (and counts them); only a step that emits a row reads them.
 #pragma unroll
-                    for (int c = 0; c < N; c++) {  // ordinary.rs:196-207
-                        c1[c] = ynew[c] - y[c];
-                        c2[c] = __dadd_rn(0.0, h * k[0][c]) - c1[c];
-                        c3[c] = (c1[c] + (-h) * dydt[c]) - c2[c];
-                    }
-                    double ch[(O > 4) ? (O - 4) : 1][N];  // cont[4..O-1]
-                    {
+                        for (int i = S; i < I; i++) {
+                            double ys[N];
+#pragma unroll
+                            for (int c = 0; c < N; c++) ys[c] = y[c];
+#pragma unroll
+                            for (int j = 0; j < i; j++) {
+                                if (Tab::a(i, j) != 0.0) {
+                                    const double ah = Tab::av(i, j) * h;
+#pragma unroll
+                                    for (int c = 0; c < N; c++) ys[c] = ys[c] + ah * ((j < S) ? k[(j < S) ? j : 0][c] : kx[(j >= S) ? (j - S) : 0][c]);
+                                }
+                            }
+                            Sys::rhs(t + Tab::cv(i) * h, ys, kx[i - S], p);
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < N; c++) {  // ordinary.rs:196-207
+                            c1[c] = ynew[c] - y[c];
+                            c2[c] = __dadd_rn(0.0, h * k[0][c]) - c1[c];
+                            c3[c] = (c1[c] + (-h) * dydt[c]) - c2[c];
+                        }
                         // extra dense stages, ordinary.rs:210-225: k[S] = dydt, stages S+1..I-1
-                        double kx[(I > S) ? (I - S) : 1][N];
 #pragma unroll
                         for (int c = 0; c < N; c++) kx[0][c] = dydt[c];
 #pragma unroll
@@ -568,7 +656,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
                                 if (Tab::a(i, j) != 0.0) {
                                     const double ah = Tab::av(i, j) * h;
 #pragma unroll
-                                    for (int c = 0; c < N; c++) ys[c] = ys[c] + ah * ((j < S) ? k[j][c] : kx[j - S][c]);
+                                    for (int c = 0; c < N; c++) ys[c] = ys[c] + ah * ((j < S) ? k[(j < S) ? j : 0][c] : kx[(j >= S) ? (j - S) : 0][c]);
                                 }
                             }
                             Sys::rhs(t + Tab::cv(i) * h, ys, kx[i - S], p);
@@ -582,7 +670,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
                                 if (Tab::bi(i, j) != 0.0) {
 #pragma unroll
                                     for (int c = 0; c < N; c++)
-                                        ch[i - 4][c] = __dadd_rn(ch[i - 4][c], Tab::biv(i, j) * ((j < S) ? k[j][c] : kx[j - S][c]));
+                                        ch[i - 4][c] = __dadd_rn(ch[i - 4][c], Tab::biv(i, j) * ((j < S) ? k[(j < S) ? j : 0][c] : kx[(j >= S) ? (j - S) : 0][c]));
                                 }
                             }
 #pragma unroll
@@ -609,6 +697,22 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
                         if (te == t_new && !a.even) {  // exact hit: the solver state itself (t_eval.rs:113-114)
 #pragma unroll
                             for (int c = 0; c < N; c++) row[c] = ynew[c];
+                        } else if constexpr (Tab::BI_POLY) {  // adaptive/ordinary.rs:246-277: Horner in s over bi[i][0..O-1], times s
+                            const double sx = (te - t) / h;
+#pragma unroll
+                            for (int c = 0; c < N; c++) row[c] = y[c];
+#pragma unroll
+                            for (int i = 0; i < I; i++) {
+                                if (Tab::bi_row(i)) {  // an all-zero row adds (+0 * h) * k[i]
+                                    double ci = Tab::biv(i, O - 1);
+#pragma unroll
+                                    for (int j = O - 2; j >= 0; j--) ci = ci * sx + Tab::biv(i, j);
+                                    ci = ci * sx;
+                                    const double w = ci * h;
+#pragma unroll
+                                    for (int c = 0; c < N; c++) row[c] = row[c] + w * ((i < S) ? k[(i < S) ? i : 0][c] : kx[(i >= S) ? (i - S) : 0][c]);
+                                }
+                            }
                         } else {  // interpolate, ordinary.rs:301-337, factor order as written
                             const double sx = (te - t) / h;
                             const double s1 = 1.0 - sx;

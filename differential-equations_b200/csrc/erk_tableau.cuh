@@ -22,29 +22,29 @@ namespace deb {
     __device__ __forceinline__ static double name##v(int i, int j) { return cmem::cname[i][j]; }
 
 namespace cmem {
-__constant__ double d5_c[7] = DEB_DOPRI5_C;
-__constant__ double d5_a[7][7] = DEB_DOPRI5_A;
-__constant__ double d5_b[7] = DEB_DOPRI5_B;
-__constant__ double d5_er[7] = DEB_DOPRI5_ER;
-__constant__ double d5_bi[7][7] = DEB_DOPRI5_BI;
-__constant__ double d8_c[16] = DEB_DOP853_C;
-__constant__ double d8_a[16][16] = DEB_DOP853_A;
-__constant__ double d8_b[12] = DEB_DOP853_B;
-__constant__ double d8_bh[12] = DEB_DOP853_BH;
-__constant__ double d8_er[12] = DEB_DOP853_ER;
-__constant__ double d8_bi[16][16] = DEB_DOP853_BI;
-__constant__ double rkf45_c[6] = DEB_RKF45_C;
-__constant__ double rkf45_a[6][6] = DEB_RKF45_A;
-__constant__ double rkf45_b[6] = DEB_RKF45_B;
-__constant__ double rkf45_bh[6] = DEB_RKF45_BH;
-__constant__ double ck_c[6] = DEB_CASH_KARP_C;
-__constant__ double ck_a[6][6] = DEB_CASH_KARP_A;
-__constant__ double ck_b[6] = DEB_CASH_KARP_B;
-__constant__ double ck_bh[6] = DEB_CASH_KARP_BH;
-#define DEB_CMEM_FIXED(pfx, PFX, n)                  \
-    __constant__ double pfx##_c[n] = DEB_##PFX##_C;  \
-    __constant__ double pfx##_a[n][n] = DEB_##PFX##_A; \
-    __constant__ double pfx##_b[n] = DEB_##PFX##_B;
+static __constant__ double d5_c[7] = DEB_DOPRI5_C;
+static __constant__ double d5_a[7][7] = DEB_DOPRI5_A;
+static __constant__ double d5_b[7] = DEB_DOPRI5_B;
+static __constant__ double d5_er[7] = DEB_DOPRI5_ER;
+static __constant__ double d5_bi[7][7] = DEB_DOPRI5_BI;
+static __constant__ double d8_c[16] = DEB_DOP853_C;
+static __constant__ double d8_a[16][16] = DEB_DOP853_A;
+static __constant__ double d8_b[12] = DEB_DOP853_B;
+static __constant__ double d8_bh[12] = DEB_DOP853_BH;
+static __constant__ double d8_er[12] = DEB_DOP853_ER;
+static __constant__ double d8_bi[16][16] = DEB_DOP853_BI;
+static __constant__ double rkf45_c[6] = DEB_RKF45_C;
+static __constant__ double rkf45_a[6][6] = DEB_RKF45_A;
+static __constant__ double rkf45_b[6] = DEB_RKF45_B;
+static __constant__ double rkf45_bh[6] = DEB_RKF45_BH;
+static __constant__ double ck_c[6] = DEB_CASH_KARP_C;
+static __constant__ double ck_a[6][6] = DEB_CASH_KARP_A;
+static __constant__ double ck_b[6] = DEB_CASH_KARP_B;
+static __constant__ double ck_bh[6] = DEB_CASH_KARP_BH;
+#define DEB_CMEM_FIXED(pfx, PFX, n)                           \
+    static __constant__ double pfx##_c[n] = DEB_##PFX##_C;    \
+    static __constant__ double pfx##_a[n][n] = DEB_##PFX##_A; \
+    static __constant__ double pfx##_b[n] = DEB_##PFX##_B;
 DEB_CMEM_FIXED(euler, EULER, 1)
 DEB_CMEM_FIXED(midpoint, MIDPOINT, 2)
 DEB_CMEM_FIXED(heun, HEUN, 2)
@@ -52,12 +52,26 @@ DEB_CMEM_FIXED(ralston, RALSTON, 2)
 DEB_CMEM_FIXED(ssp_rk3, SSP_RK3, 3)
 DEB_CMEM_FIXED(rk4, RK4, 4)
 DEB_CMEM_FIXED(three_eighths, THREE_EIGHTHS, 4)
+#define DEB_CMEM_VERNER(pfx, PFX, o, s, i)                    \
+    static __constant__ double pfx##_c[i] = DEB_##PFX##_C;    \
+    static __constant__ double pfx##_a[i][i] = DEB_##PFX##_A; \
+    static __constant__ double pfx##_b[s] = DEB_##PFX##_B;    \
+    static __constant__ double pfx##_bh[s] = DEB_##PFX##_BH;  \
+    static __constant__ double pfx##_bi[i][o] = DEB_##PFX##_BI;
+DEB_CMEM_VERNER(v655, RKV655E, 6, 9, 10)
+DEB_CMEM_VERNER(v656, RKV656E, 6, 9, 12)
+DEB_CMEM_VERNER(v766, RKV766E, 7, 10, 13)
+DEB_CMEM_VERNER(v767, RKV767E, 7, 10, 16)
+DEB_CMEM_VERNER(v877, RKV877E, 8, 13, 17)
+DEB_CMEM_VERNER(v878, RKV878E, 8, 13, 21)
+DEB_CMEM_VERNER(v988, RKV988E, 9, 16, 21)
+DEB_CMEM_VERNER(v989, RKV989E, 9, 16, 26)
 }  // namespace cmem
 
 // DOPRI5: /root/reference/src/tableau/dorman_prince.rs:37-117; (O,S,I) = (5,7,7) dormandprince/mod.rs:52-58
 struct TabDopri5 {
     static constexpr int O = 5, S = 7, I = 7;
-    static constexpr bool ADAPTIVE = true, HAS_BH = false, DP = true;
+    static constexpr bool ADAPTIVE = true, HAS_BH = false, DP = true, FSAL = false, BI_POLY = false;
     DEB_TAB_FN1(c, 7, DEB_DOPRI5_C, d5_c)
     DEB_TAB_FN2(a, 7, DEB_DOPRI5_A, d5_a)
     DEB_TAB_FN1(b, 7, DEB_DOPRI5_B, d5_b)
@@ -72,7 +86,7 @@ struct TabDopri5 {
 // DOP853: /root/reference/src/tableau/dorman_prince.rs:155-381; (O,S,I) = (8,12,16) dormandprince/mod.rs:45-51
 struct TabDop853 {
     static constexpr int O = 8, S = 12, I = 16;
-    static constexpr bool ADAPTIVE = true, HAS_BH = true, DP = true;
+    static constexpr bool ADAPTIVE = true, HAS_BH = true, DP = true, FSAL = false, BI_POLY = false;
     DEB_TAB_FN1(c, 16, DEB_DOP853_C, d8_c)
     DEB_TAB_FN2(a, 16, DEB_DOP853_A, d8_a)
     DEB_TAB_FN1(b, 12, DEB_DOP853_B, d8_b)
@@ -87,6 +101,7 @@ struct TabDop853 {
     struct Name {                                                                      \
         static constexpr int O = 5, S = 6, I = 6;                                      \
         static constexpr bool ADAPTIVE = true, HAS_BH = true, DP = false;              \
+        static constexpr bool FSAL = false, BI_POLY = false;                           \
         DEB_TAB_FN1(c, 6, DEB_##PFX##_C, pfx##_c)                                      \
         DEB_TAB_FN2(a, 6, DEB_##PFX##_A, pfx##_a)                                      \
         DEB_TAB_FN1(b, 6, DEB_##PFX##_B, pfx##_b)                                      \
@@ -98,6 +113,35 @@ struct TabDop853 {
     };
 DEB_ADAPTIVE_TAB(TabRkf45, RKF45, rkf45)        // runge_kutta.rs:335
 DEB_ADAPTIVE_TAB(TabCashKarp, CASH_KARP, ck)    // runge_kutta.rs:420
+
+// Verner pairs (/root/reference/src/tableau/verner.rs; (O,S,I) and fsal: methods/erk/adaptive/mod.rs:59-122): same stepper as
+// RKF45, plus I-S extra stages and a dense-output polynomial bi[i][0..O-1] in s (adaptive/ordinary.rs:145-160, :246-277).
+#define DEB_VERNER_TAB(Name, PFX, pfx, order, stages, dense, fsal)                                                  \
+    struct Name {                                                                                                   \
+        static constexpr int O = order, S = stages, I = dense;                                                      \
+        static constexpr bool ADAPTIVE = true, HAS_BH = true, DP = false, FSAL = fsal, BI_POLY = true;              \
+        DEB_TAB_FN1(c, dense, DEB_##PFX##_C, pfx##_c)                                                               \
+        DEB_TAB_FN2(a, dense, DEB_##PFX##_A, pfx##_a)                                                               \
+        DEB_TAB_FN1(b, stages, DEB_##PFX##_B, pfx##_b)                                                              \
+        DEB_TAB_FN1(bh, stages, DEB_##PFX##_BH, pfx##_bh)                                                           \
+        __host__ __device__ static constexpr double er(int) { return 0.0; }                                         \
+        __device__ __forceinline__ static double erv(int) { return 0.0; }                                           \
+        __host__ __device__ static constexpr double bi(int i, int j) { constexpr double v[dense][order] = DEB_##PFX##_BI; return v[i][j]; } \
+        __device__ __forceinline__ static double biv(int i, int j) { return cmem::pfx##_bi[i][j]; }                 \
+        /* does dense stage i enter the polynomial at all? */                                                       \
+        __host__ __device__ static constexpr bool bi_row(int i) {                                                   \
+            for (int j = 0; j < order; j++) if (bi(i, j) != 0.0) return true;                                       \
+            return false;                                                                                           \
+        }                                                                                                           \
+    };
+DEB_VERNER_TAB(TabRkv655e, RKV655E, v655, 6, 9, 10, true)
+DEB_VERNER_TAB(TabRkv656e, RKV656E, v656, 6, 9, 12, true)
+DEB_VERNER_TAB(TabRkv766e, RKV766E, v766, 7, 10, 13, false)
+DEB_VERNER_TAB(TabRkv767e, RKV767E, v767, 7, 10, 16, false)
+DEB_VERNER_TAB(TabRkv877e, RKV877E, v877, 8, 13, 17, false)
+DEB_VERNER_TAB(TabRkv878e, RKV878E, v878, 8, 13, 21, false)
+DEB_VERNER_TAB(TabRkv988e, RKV988E, v988, 9, 16, 21, false)
+DEB_VERNER_TAB(TabRkv989e, RKV989E, v989, 9, 16, 26, false)
 
 #define DEB_FIXED_TAB(Name, PFX, pfx, order, stages)                 \
     struct Name {                                                    \

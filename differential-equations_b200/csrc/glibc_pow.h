@@ -47,9 +47,9 @@ static inline double deb_as_f64_(uint64_t u) { double x; memcpy(&x, &u, 8); retu
 // the shared pointers in.
 #if defined(__CUDACC__)
 // scalar coefficients: constant-bank operands on the device (a 64-bit immediate costs two UMOV issue slots per use)
-__constant__ double deb_c_powk[17] = {DEB_POWLOG_LN2HI, DEB_POWLOG_LN2LO, DEB_POWLOG_A0, DEB_POWLOG_A1, DEB_POWLOG_A2, DEB_POWLOG_A3, DEB_POWLOG_A4, DEB_POWLOG_A5, DEB_POWLOG_A6, DEB_EXP_INVLN2N, DEB_EXP_SHIFT, DEB_EXP_NEGLN2HIN, DEB_EXP_NEGLN2LON, DEB_EXP_C2, DEB_EXP_C3, DEB_EXP_C4, DEB_EXP_C5};
-__constant__ double deb_c_powlog_tab[128 * 3] = DEB_POWLOG_TAB_INIT;
-__constant__ unsigned long long deb_c_exp_tab[128 * 2] = DEB_EXP_TAB_INIT;
+static __constant__ double deb_c_powk[17] = {DEB_POWLOG_LN2HI, DEB_POWLOG_LN2LO, DEB_POWLOG_A0, DEB_POWLOG_A1, DEB_POWLOG_A2, DEB_POWLOG_A3, DEB_POWLOG_A4, DEB_POWLOG_A5, DEB_POWLOG_A6, DEB_EXP_INVLN2N, DEB_EXP_SHIFT, DEB_EXP_NEGLN2HIN, DEB_EXP_NEGLN2LON, DEB_EXP_C2, DEB_EXP_C3, DEB_EXP_C4, DEB_EXP_C5};
+static __constant__ double deb_c_powlog_tab[128 * 3] = DEB_POWLOG_TAB_INIT;
+static __constant__ unsigned long long deb_c_exp_tab[128 * 2] = DEB_EXP_TAB_INIT;
 #endif
 #if !defined(__CUDA_ARCH__)
 static const double deb_h_powlog_tab[128 * 3] = DEB_POWLOG_TAB_INIT;

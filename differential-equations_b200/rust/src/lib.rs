@@ -18,7 +18,7 @@ use differential_equations::{
 };
 
 // ------------------------------------------------------------------------------------------------ raw ABI
-pub const DEB_ABI_VERSION: i32 = 3;
+pub const DEB_ABI_VERSION: i32 = 4;
 
 #[repr(C)]
 #[derive(Clone, Copy)]
@@ -84,6 +84,10 @@ extern "C" {
     pub fn deb_device_count() -> i32;
     pub fn deb_erk_options_default(opt: *mut deb_erk_options);
     pub fn deb_solve_ode(problem: *const deb_ode_problem, result: *mut deb_result) -> i32;
+    /// user-defined right-hand side as CUDA C++ text (the device-side `impl ODE`); returns a system id >= 1000
+    pub fn deb_define_ode(dim: i32, n_params: i32, diff_body: *const c_char, system_id: *mut i32) -> i32;
+    /// compile it for a method now (no device needed); the compiler log is in deb_last_error()
+    pub fn deb_check_ode(system_id: i32, method: i32) -> i32;
     // deb_solve_sde, deb_solve_heat_mol, deb_heat_rhs, deb_ensemble_stats, deb_malloc, ... : see deb_ensemble.h
 }
 
@@ -139,6 +143,14 @@ impl Method {
     pub fn dop853() -> Self { Self::new(17, 0.0) }
     pub fn rkf45() -> Self { Self::new(18, 0.0) }
     pub fn cash_karp() -> Self { Self::new(19, 0.0) }
+    pub fn rkv655e() -> Self { Self::new(20, 0.0) }
+    pub fn rkv656e() -> Self { Self::new(21, 0.0) }
+    pub fn rkv766e() -> Self { Self::new(22, 0.0) }
+    pub fn rkv767e() -> Self { Self::new(23, 0.0) }
+    pub fn rkv877e() -> Self { Self::new(24, 0.0) }
+    pub fn rkv878e() -> Self { Self::new(25, 0.0) }
+    pub fn rkv988e() -> Self { Self::new(26, 0.0) }
+    pub fn rkv989e() -> Self { Self::new(27, 0.0) }
     pub fn rtol(mut self, v: f64) -> Self { self.opt.rtol = v; self.rtol_vec = None; self }
     pub fn atol(mut self, v: f64) -> Self { self.opt.atol = v; self.atol_vec = None; self }
     pub fn rtol_vec(mut self, v: Vec<f64>) -> Self { self.rtol_vec = Some(v); self }

@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define DEB_ABI_VERSION 3
+#define DEB_ABI_VERSION 4
 #define DEB_MAX_DIM 16 /* widest state the register-resident kernels are instantiated for */
 
 typedef enum deb_error {
@@ -57,7 +57,7 @@ typedef enum deb_error {
 } deb_error;
 
 /* Explicit Runge-Kutta constructors of the reference that the kernels implement
- * (src/methods/erk/fixed/mod.rs:41-89, src/methods/erk/dormandprince/mod.rs:45-58, src/methods/erk/adaptive/mod.rs:47-60). */
+ * (src/methods/erk/fixed/mod.rs:41-89, src/methods/erk/dormandprince/mod.rs:45-58, src/methods/erk/adaptive/mod.rs:47-122). */
 typedef enum deb_method {
     DEB_EULER = 0,
     DEB_MIDPOINT = 1,
@@ -71,6 +71,16 @@ typedef enum deb_method {
     /* adaptive family with y_high - y_low error estimate (src/methods/erk/adaptive/mod.rs:47-60) */
     DEB_RKF45 = 18,
     DEB_CASH_KARP = 19,
+    /* Verner pairs with their own dense-output polynomial (src/methods/erk/adaptive/mod.rs:59-122, src/tableau/verner.rs):
+     * order(embedded order, interpolant order); the two 6(5) pairs are FSAL */
+    DEB_RKV655E = 20,
+    DEB_RKV656E = 21,
+    DEB_RKV766E = 22,
+    DEB_RKV767E = 23,
+    DEB_RKV877E = 24,
+    DEB_RKV878E = 25,
+    DEB_RKV988E = 26,
+    DEB_RKV989E = 27,
     /* SDE only: derivative-free Milstein, Milstein::new(h) (src/methods/milstein.rs:37-180) */
     DEB_MILSTEIN = 32
 } deb_method;
@@ -239,6 +249,9 @@ void deb_erk_options_default(deb_erk_options* opt);
  * serve the built-in systems, and cached.  Returns a system id (>= 1000) to put in deb_ode_problem.system.
  * A body that does not compile makes the first deb_solve_ode return DEB_ERR_BAD_ARG with the compiler log. */
 int deb_define_ode(int32_t dim, int32_t n_params, const char* diff_body, int32_t* system_id);
+/* Compile a user-defined system for `method` now, without a device and without running anything: DEB_OK, or
+ * DEB_ERR_BAD_ARG with the compiler log in deb_last_error().  (What a Rust caller gets from `cargo check`.) */
+int deb_check_ode(int32_t system_id, int32_t method);
 
 int deb_solve_ode(const deb_ode_problem* problem, deb_result* result);
 int deb_solve_sde(const deb_sde_problem* problem, deb_result* result);

@@ -100,7 +100,8 @@ struct Tableau {
     const double* b;   // [S]
     const double* bh;  // [S] or null
     const double* er;  // [S] or null
-    const double* bi;  // [I][I] or null
+    const double* bi;  // DP family: [I][I]; adaptive family with a dense-output polynomial: [I][O]; or null
+    bool fsal = false; // adaptive family only (adaptive/mod.rs:59-122)
 };
 const double D5_C[7] = DEB_DOPRI5_C;  const double D5_A[7][7] = DEB_DOPRI5_A;  const double D5_B[7] = DEB_DOPRI5_B;
 const double D5_ER[7] = DEB_DOPRI5_ER; const double D5_BI[7][7] = DEB_DOPRI5_BI;
@@ -114,6 +115,18 @@ const double RAL_C[2] = DEB_RALSTON_C; const double RAL_A[2][2] = DEB_RALSTON_A;
 const double SSP_C[3] = DEB_SSP_RK3_C; const double SSP_A[3][3] = DEB_SSP_RK3_A; const double SSP_B[3] = DEB_SSP_RK3_B;
 const double F45_C[6] = DEB_RKF45_C; const double F45_A[6][6] = DEB_RKF45_A; const double F45_B[6] = DEB_RKF45_B; const double F45_BH[6] = DEB_RKF45_BH;
 const double CK_C[6] = DEB_CASH_KARP_C; const double CK_A[6][6] = DEB_CASH_KARP_A; const double CK_B[6] = DEB_CASH_KARP_B; const double CK_BH[6] = DEB_CASH_KARP_BH;
+// Verner pairs, tableau/verner.rs; (O, S, I, fsal) from adaptive/mod.rs:59-122
+#define ORC_VERNER(NM, PFX, O, S, I) \
+    const double NM##_C[I] = DEB_##PFX##_C; const double NM##_A[I][I] = DEB_##PFX##_A; const double NM##_B[S] = DEB_##PFX##_B; \
+    const double NM##_BH[S] = DEB_##PFX##_BH; const double NM##_BI[I][O] = DEB_##PFX##_BI;
+ORC_VERNER(V655, RKV655E, 6, 9, 10)
+ORC_VERNER(V656, RKV656E, 6, 9, 12)
+ORC_VERNER(V766, RKV766E, 7, 10, 13)
+ORC_VERNER(V767, RKV767E, 7, 10, 16)
+ORC_VERNER(V877, RKV877E, 8, 13, 17)
+ORC_VERNER(V878, RKV878E, 8, 13, 21)
+ORC_VERNER(V988, RKV988E, 9, 16, 21)
+ORC_VERNER(V989, RKV989E, 9, 16, 26)
 const double EU_C[1] = DEB_EULER_C; const double EU_A[1][1] = DEB_EULER_A; const double EU_B[1] = DEB_EULER_B;
 
 bool get_tableau(int m, Tableau* t) {
@@ -123,6 +136,16 @@ bool get_tableau(int m, Tableau* t) {
         // adaptive family, adaptive/mod.rs:47-60: (order, S, I) = (5, 6, 6), fsal = false, bi = None
         case DEB_RKF45: *t = {5, 6, 6, true, false, F45_C, &F45_A[0][0], F45_B, F45_BH, nullptr, nullptr}; return true;
         case DEB_CASH_KARP: *t = {5, 6, 6, true, false, CK_C, &CK_A[0][0], CK_B, CK_BH, nullptr, nullptr}; return true;
+#define ORC_VERNER_CASE(ID, NM, O, S, I, FSAL) \
+        case ID: *t = {O, S, I, true, false, NM##_C, &NM##_A[0][0], NM##_B, NM##_BH, nullptr, &NM##_BI[0][0], FSAL}; return true;
+        ORC_VERNER_CASE(DEB_RKV655E, V655, 6, 9, 10, true)
+        ORC_VERNER_CASE(DEB_RKV656E, V656, 6, 9, 12, true)
+        ORC_VERNER_CASE(DEB_RKV766E, V766, 7, 10, 13, false)
+        ORC_VERNER_CASE(DEB_RKV767E, V767, 7, 10, 16, false)
+        ORC_VERNER_CASE(DEB_RKV877E, V877, 8, 13, 17, false)
+        ORC_VERNER_CASE(DEB_RKV878E, V878, 8, 13, 21, false)
+        ORC_VERNER_CASE(DEB_RKV988E, V988, 9, 16, 21, false)
+        ORC_VERNER_CASE(DEB_RKV989E, V989, 9, 16, 26, false)
         case DEB_RK4: *t = {4, 4, 4, false, false, RK4_C, &RK4_A[0][0], RK4_B, nullptr, nullptr, nullptr}; return true;
         case DEB_THREE_EIGHTHS: *t = {4, 4, 4, false, false, T38_C, &T38_A[0][0], T38_B, nullptr, nullptr, nullptr}; return true;
         case DEB_MIDPOINT: *t = {2, 2, 2, false, false, MID_C, &MID_A[0][0], MID_B, nullptr, nullptr, nullptr}; return true;
@@ -399,7 +422,7 @@ struct Erk {
         rejected = false;
         return true;
     }
-    // ---- adaptive family: step, adaptive/ordinary.rs:63-211 (bi = None, fsal = false for RKF45 / Cash-Karp)
+    // ---- adaptive family: step, adaptive/ordinary.rs:63-211 (bi = None, fsal = false for RKF45 / Cash-Karp; Verner pairs have bi)
     StepOutcome ad_step(const Problem& ode, int* evals_out) {
         int evals = 0;
         const int S = tb.stages, I = tb.dense;
@@ -424,10 +447,22 @@ struct Erk {
         if (err_norm <= 1.0) {
             t_prev = t; y_prev = y; dydt_prev = k[0]; h_prev = h;
             if (rejected) { stiffness_counter = 0; rejected = false; scale = rmin(scale, 1.0); }
+            if (tb.bi) {  // extra stages for the dense-output polynomial, :145-160 (on every accepted step)
+                for (int i = 0; i < I - S; i++) {
+                    Vec ys = y;
+                    for (int j = 0; j < S + i; j++) add_scaled(ys, tb.a[(S + i) * I + j] * h, k[j]);
+                    ode.diff(t + tb.c[S + i] * h, ys, k[S + i]);
+                }
+                evals += I - S;
+            }
             t += h;
             y = y_high;
-            ode.diff(t, y, dydt);
-            evals += 1;
+            if (tb.fsal) {  // :166-169
+                dydt = k[S - 1];
+            } else {
+                ode.diff(t, y, dydt);
+                evals += 1;
+            }
         } else {
             rejected = true;
             stiffness_counter += 1;
@@ -437,6 +472,21 @@ struct Erk {
         h = constrain_step_size(h, h_min, h_max);
         *evals_out += evals;
         return STEP_OK;
+    }
+
+    // dense-output polynomial of the adaptive family, adaptive/ordinary.rs:246-277: Horner in s over bi[i][0..O-1], times s
+    Vec ad_interpolate(double ti) const {
+        const int I = tb.dense, O = tb.order;
+        double s = (ti - t_prev) / h_prev;
+        Vec out = y_prev;
+        double cont[32];
+        for (int i = 0; i < I; i++) {
+            cont[i] = tb.bi[i * O + (O - 1)];
+            for (int j = O - 2; j >= 0; j--) cont[i] = cont[i] * s + tb.bi[i * O + j];
+            cont[i] *= s;
+        }
+        for (int i = 0; i < I; i++) add_scaled(out, cont[i] * h_prev, k[i]);
+        return out;
     }
 
     // ---- fixed step: init, fixed/ordinary.rs:16-56
@@ -613,7 +663,7 @@ void solve_one(const deb_ode_problem* P, const SysInfo& si, const Tableau& tb, i
     TEval te(even ? nullptr : P->t_eval, even ? 0 : P->n_eval, t0, tf);
     Even ev(P->even_dt, t0, tf);
     // adaptive family without bi: cubic Hermite on (t_prev, t, y_prev, y, dydt_prev, dydt), adaptive/ordinary.rs:282-295
-    auto interp = [&](double tv) { return tb.dp ? m.dp_interpolate(tv) : m.fx_interpolate(tv); };
+    auto interp = [&](double tv) { return tb.dp ? m.dp_interpolate(tv) : (tb.adaptive && tb.bi) ? m.ad_interpolate(tv) : m.fx_interpolate(tv); };
     auto record = [&]() {
         if (even) solout_even(ev, m.t, m.t_prev, m.y, m.y_prev, interp, ye, n, &n_emit);
         else solout_teval(te, m.t, m.t_prev, m.y, interp, ye, n, &n_emit);

@@ -443,13 +443,21 @@ def harmonic(k):
     return lambda t, y: [y[1], -k * y[0]]
 
 
+# (order, fsal): adaptive/mod.rs:43-122
+ADAPTIVE_ORDER_FSAL = dict(rkf45=(5, False), cash_karp=(5, False), rkv655e=(6, True), rkv656e=(6, True), rkv766e=(7, False),
+                           rkv767e=(7, False), rkv877e=(8, False), rkv878e=(8, False), rkv988e=(9, False), rkv989e=(9, False))
+
+
 def solve_adaptive(f, method, t0, tf, y0, rtol=1e-6, atol=1e-6, t_eval=(), h0=0.0, h_min=0.0, h_max=math.inf, max_steps=10000,
                    max_rejects=100, safety=0.9, min_scale=0.2, max_scale=10.0):
-    """Generic adaptive family (RKF45, Cash-Karp): /root/reference/src/methods/erk/adaptive/ordinary.rs:16-211, cubic
-    Hermite dense output (:282-295), driven by src/ode/solve_ivp.rs:139-277."""
+    """Generic adaptive family (RKF45, Cash-Karp, Verner pairs): /root/reference/src/methods/erk/adaptive/ordinary.rs:16-211,
+    dense output = the method's polynomial when it has one (:246-277) else cubic Hermite (:282-295), driven by
+    src/ode/solve_ivp.rs:139-277."""
     T = TAB[method.upper()]
     c, A, b, bh = T["C"], T["A"], T["B"], T["BH"]
-    S, O = len(b), 5
+    BI = T.get("BI")
+    S, I = len(b), len(c)
+    O, fsal = ADAPTIVE_ORDER_FSAL[method.lower()]
     n = len(y0)
     evals = 0
     if tf == t0:
@@ -471,7 +479,22 @@ def solve_adaptive(f, method, t0, tf, y0, rtol=1e-6, atol=1e-6, t_eval=(), h0=0.
     rows = []
     state = dict(idx=0)
 
+    kk = [None]  # the stage vectors of the last step (self.k)
+
     def interpolate(ti):
+        if BI is not None:  # :246-277
+            s = (ti - t_prev) / h_prev
+            out = list(y_prev)
+            cont = []
+            for i in range(I):
+                ci = BI[i][O - 1]
+                for j in range(O - 2, -1, -1):
+                    ci = ci * s + BI[i][j]
+                cont.append(ci * s)
+            for i in range(I):
+                w = cont[i] * h_prev
+                out = [out[q] + w * kk[0][i][q] for q in range(n)]
+            return out
         hh = t - t_prev
         s = (ti - t_prev) / hh
         s2 = s * s
@@ -548,10 +571,22 @@ def solve_adaptive(f, method, t0, tf, y0, rtol=1e-6, atol=1e-6, t_eval=(), h0=0.
                 stiff = 0
                 rejected = False
                 scale = rmin(scale, 1.0)
+            if BI is not None:  # extra stages for the dense-output polynomial, :145-160
+                for i in range(S, I):
+                    ys = list(y)
+                    for j in range(i):
+                        ah = A[i][j] * h
+                        ys = [ys[q] + ah * k[j][q] for q in range(n)]
+                    k.append(f(t + c[i] * h, ys))
+                step_evals += I - S
+                kk[0] = k
             t += h
             y = y_high
-            dydt = f(t, y)
-            step_evals += 1
+            if fsal:
+                dydt = list(k[S - 1])
+            else:
+                dydt = f(t, y)
+                step_evals += 1
             accepted = True
         else:
             rejected = True

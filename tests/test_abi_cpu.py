@@ -117,6 +117,20 @@ def test_empty_ensemble_and_t_eval_plan_without_device(lib):
     assert back.solve(lib).t_rows.tolist() == [3.0, 0.5, -1.0]
 
 
+def test_user_rhs_compiles_for_every_method_without_a_device(lib):
+    """deb_check_ode: the run-time (NVRTC) instantiation of the kernels for a user-defined right-hand side, for one method
+    of every kernel family -- this is a compile, no device and no compute.  A broken body reports the compiler log."""
+    E = deb.ExplicitRungeKutta
+    duffing = deb.ode_from_source(2, "dydt[0] = y[1]; dydt[1] = -p[0]*y[1] - y[0]*y[0]*y[0] + p[1]*cos(t);", params=[0.2, 0.3])
+    for m in (E.dopri5(), E.dop853(), E.rkf45(), E.rkv655e(), E.rkv989e(), E.rk4(0.01)):
+        deb.check_ode(duffing, m)
+    bad = deb.ode_from_source(1, "dydt[0] = undefined_symbol * y[0];", params=[1.0])
+    with pytest.raises(ValueError, match="did not compile"):
+        deb.check_ode(bad, E.dopri5())
+    with pytest.raises(ValueError, match="not a user-defined"):
+        deb.check_ode(deb.LorenzSystem(10.0, 28.0, 8.0 / 3.0), E.dopri5())
+
+
 def test_no_cpu_fallback_without_a_device(lib):
     """On a box without a GPU every compute entry point must fail loudly with DEB_ERR_NO_DEVICE."""
     if lib.deb_device_count() > 0:

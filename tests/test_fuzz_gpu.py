@@ -31,7 +31,7 @@ SYSTEMS = [
     # stiff: the explicit methods crawl, reject, and (adaptive family with a small max_rejects) report Stiffness
     ("robertson", lambda r, n: deb.RobertsonProblem(), 3, lambda r, n: np.array([1.0, 0.0, 0.0]) + r.uniform(0.0, 1e-3, (n, 3))),
 ]
-ADAPTIVE = ["dopri5", "dop853", "rkf45", "cash_karp"]
+ADAPTIVE = ["dopri5", "dop853", "rkf45", "cash_karp", "rkv655e", "rkv656e", "rkv766e", "rkv767e", "rkv877e", "rkv878e", "rkv988e", "rkv989e"]
 FIXED = ["euler", "midpoint", "heun", "ralston", "ssp_rk3", "rk4", "three_eighths"]
 
 

@@ -24,7 +24,7 @@ SYSTEMS = {"exponential": lambda p: deb.ExponentialGrowth(*p), "linear": lambda 
 
 
 def make_method(c):
-    if c["solver"] in ("dopri5", "dop853", "rkf45", "cash_karp"):
+    if c["solver"] in ("dopri5", "dop853", "rkf45", "cash_karp") or c["solver"].startswith("rkv"):
         m = getattr(E, c["solver"])()
     else:
         m = getattr(E, c["solver"])(c["h"])
@@ -38,7 +38,7 @@ def make_method(c):
 def test_reference_accuracy_goldens():
     """tests/ode/accuracy.rs: final state vs SciPy DOP853 constants with the reference's own tolerances."""
     cases = json.load(open(os.path.join(GOLDEN, "reference_accuracy.json")))["accuracy"]
-    assert len(cases) == 52
+    assert len(cases) == 87
     for c in cases:
         ivp = deb.EnsembleIVP.ode(SYSTEMS[c["system"]](c["params"]), c["t0"], c["tf"], [c["y0"]]).method(make_method(c))
         s = ob.oracle_solve(ivp)[0]  # the reference test unwrap()s: every case must solve
@@ -60,7 +60,7 @@ def test_reference_accuracy_tight():
 def test_reference_interpolation_kat():
     """tests/ode/interpolation.rs:35-79: y' = y, t_eval([0.5, 1.0, 1.69]); every solver within 1e-3 of e^t.  Only the
     listed points come back, in order."""
-    for m in (E.dop853(), E.dopri5(), E.rk4(0.01)):  # the explicit-RK solvers of that test
+    for m in (E.dop853(), E.dopri5(), E.rkv655e(), E.rkv877e(), E.rkv988e(), E.rkf45(), E.rk4(0.01)):  # the explicit-RK solvers of that test
         s = ob.oracle_solve(deb.EnsembleIVP.ode(deb.ExponentialGrowth(1.0), 0.0, 2.0, [[1.0]]).t_eval([0.5, 1.0, 1.69]).method(m))[0]
         assert s.t.tolist() == [0.5, 1.0, 1.69]
         np.testing.assert_allclose(s.y[:, 0], np.exp([0.5, 1.0, 1.69]), atol=1e-3)
@@ -77,6 +77,10 @@ def test_reference_error_kats():
     for ivp in (deb.EnsembleIVP.ode(deb.ExponentialGrowth(1.0), 0.0, 0.0, [[1.0]]).method(E.dopri5()),
                 deb.EnsembleIVP.ode(deb.ExponentialGrowth(1.0), 0.0, 1.0, [[1.0]]).method(E.dopri5().h0(10.0)),
                 deb.EnsembleIVP.ode(deb.ExponentialGrowth(1.0), 0.0, 1.0, [[1.0]]).method(E.rk4(10.0)),
+                deb.EnsembleIVP.ode(deb.ExponentialGrowth(1.0), 0.0, 0.0, [[1.0]]).method(E.rkv655e().h0(0.1)),   # errors.rs:102-103
+                deb.EnsembleIVP.ode(deb.ExponentialGrowth(1.0), 0.0, 0.0, [[1.0]]).method(E.rkv988e().h0(0.1)),
+                deb.EnsembleIVP.ode(deb.ExponentialGrowth(1.0), 0.0, 1.0, [[1.0]]).method(E.rkv655e().h0(10.0)),  # errors.rs:125-126
+                deb.EnsembleIVP.ode(deb.ExponentialGrowth(1.0), 0.0, 1.0, [[1.0]]).method(E.rkv988e().h0(10.0)),
                 deb.EnsembleIVP.ode(deb.ExponentialGrowth(1.0), 0.0, 1.0, [[1.0]]).method(E.rk4(-0.1)),
                 deb.EnsembleIVP.ode(deb.ExponentialGrowth(1.0), 0.0, 1.0, [[1.0]]).method(E.dopri5().h_min(1.0).h_max(0.5))):
         with pytest.raises(deb.BadInput):
@@ -199,6 +203,41 @@ def test_adaptive_family_restatements_agree_bitwise():
         assert p["status"] == "Stiffness" and c.status[0] == deb.DEB_STATUS_STIFFNESS
         assert (p["accepted"], p["rejected"], p["evals"]) == (int(c.accepted[0]), int(c.rejected[0]), int(c.evals[0]))
         assert _same_bits(p["y"], c.y_final[0]) and p["t"] == c.t_final[0]
+
+
+VERNER = (("rkv655e", 6, 9, 10, True), ("rkv656e", 6, 9, 12, True), ("rkv766e", 7, 10, 13, False), ("rkv767e", 7, 10, 16, False),
+          ("rkv877e", 8, 13, 17, False), ("rkv878e", 8, 13, 21, False), ("rkv988e", 9, 16, 21, False), ("rkv989e", 9, 16, 26, False))
+
+
+def test_verner_restatements_agree_bitwise():
+    """Verner pairs (adaptive/ordinary.rs with bi = Some, adaptive/mod.rs:59-122): C++ oracle vs the independent pure-Python
+    restatement, bit for bit -- dense-output stages on every accepted step, Horner polynomial in s, FSAL for the 6(5)
+    pairs -- plus the evaluation-count identity and the accuracy of the interpolant at its design order."""
+    lz = pr.lorenz(10.0, 28.0, 8.0 / 3.0)
+    for (meth, O, S, I, fsal) in VERNER:
+        cases = ((lz, deb.LorenzSystem(10.0, 28.0, 8.0 / 3.0), 0.0, 4.0, [1.0, 1.0, 1.0], dict(rtol=1e-7, atol=1e-8)),
+                 (pr.van_der_pol(1.5), deb.VanDerPolOscillator(1.5), 0.0, 6.0, [2.0, 0.0], dict(rtol=1e-5, atol=1e-6)),
+                 (pr.harmonic(1.0), deb.HarmonicOscillator(1.0), 5.0, 0.0, [1.0, 0.0], dict(rtol=1e-9, atol=1e-9)))  # backward
+        for (f, sysm, t0, tf, y0, tol) in cases:
+            te = list(np.linspace(t0, tf, 7)) + [0.5 * (t0 + tf) + 0.0123]
+            p = pr.solve_adaptive(f, meth, t0, tf, y0, t_eval=te, **tol)
+            c = ob.oracle_solve(deb.EnsembleIVP.ode(sysm, t0, tf, [y0]).t_eval(te)
+                                .method(getattr(E, meth)().rtol(tol["rtol"]).atol(tol["atol"])))
+            assert p["status"] == "Complete" and c.status[0] == 0
+            assert (p["accepted"], p["rejected"], p["evals"]) == (int(c.accepted[0]), int(c.rejected[0]), int(c.evals[0]))
+            assert p["evals"] == 5 + (S - 1) * (p["accepted"] + p["rejected"]) + p["accepted"] * ((I - S) + (0 if fsal else 1))
+            assert len(p["rows"]) == 8 == c.n_emitted[0]
+            assert _same_bits(p["y"], c.y_final[0]) and _same_bits([r[1] for r in p["rows"]], c.y_eval[0])
+        # the interpolant is a real dense output: harmonic oscillator rows against the closed form
+        sol = ob.oracle_solve(deb.EnsembleIVP.ode(deb.HarmonicOscillator(1.0), 0.0, 10.0, [[1.0, 0.0]]).t_eval(np.linspace(0.05, 9.95, 37))
+                              .method(getattr(E, meth)().rtol(1e-10).atol(1e-10)))[0]
+        np.testing.assert_allclose(sol.y[:, 0], np.cos(sol.t), atol=2e-7)
+        np.testing.assert_allclose(sol.y[:, 1], -np.sin(sol.t), atol=2e-7)
+        # even(dt) goes through the same polynomial
+        ev = ob.oracle_solve(deb.EnsembleIVP.ode(deb.HarmonicOscillator(1.0), 0.0, 3.0, [[1.0, 0.0]]).even(0.4)
+                             .method(getattr(E, meth)().rtol(1e-9).atol(1e-9)))[0]
+        assert ev.t[0] == 0.0 and ev.t[-1] == 3.0
+        np.testing.assert_allclose(ev.y[:, 0], np.cos(ev.t), atol=1e-6)
 
 
 def test_even_solout_restatements_agree_bitwise():

@@ -18,7 +18,12 @@ pytestmark = pytest.mark.gpu
 
 
 def bits(a):
-    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+    """Bit patterns, with every NaN mapped to one pattern: which NaN an invalid operation produces is a property of the
+    processor (x86 SSE: the negative 'indefinite' 0xFFF8..., the GPU: a positive canonical NaN), not of the algorithm."""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    b = a.view(np.uint64).copy()
+    b[np.isnan(a)] = np.uint64(0x7FF8000000000000)
+    return b
 
 
 def assert_same_solution(gpu, cpu, exact=True, rtol=0.0):
@@ -485,6 +490,66 @@ def test_adaptive_family_bit_exact(ctor):
     assert (g.status == deb.DEB_STATUS_STIFFNESS).all()
     with pytest.raises(deb.Stiffness):
         g[0]
+
+
+VERNER = {"rkv655e": (9, 10, True), "rkv656e": (9, 12, True), "rkv766e": (10, 13, False), "rkv767e": (10, 16, False),
+          "rkv877e": (13, 17, False), "rkv878e": (13, 21, False), "rkv988e": (16, 21, False), "rkv989e": (16, 26, False)}
+
+
+@pytest.mark.parametrize("ctor", sorted(VERNER))
+def test_verner_family_bit_exact(ctor):
+    """Verner pairs (adaptive/mod.rs:59-122, tableau/verner.rs): the adaptive-family stepper plus I-S dense-output stages,
+    the Horner dense-output polynomial (adaptive/ordinary.rs:246-277), FSAL for the 6(5) pairs, and the evaluation count
+    of the reference (dense stages on every accepted step)."""
+    S, I, fsal = VERNER[ctor]
+    per_acc = (I - S) + (0 if fsal else 1)
+    y0 = ob.lorenz_ensemble_y0(1200, seed=51)
+    te = np.concatenate([np.linspace(0.0, 6.0, 25), [6.0, 3.3333]])
+    def prob():
+        return deb.EnsembleIVP.ode(lorenz(), 0.0, 6.0, y0).t_eval(te).method(getattr(E, ctor)().rtol(1e-8).atol(1e-9))
+    g, c = prob().solve(), ob.oracle_solve(prob())
+    assert_same_solution(g, c)
+    assert (g.status == 0).all() and (g.n_emitted == len(te)).all()
+    assert np.array_equal(g.evals, 5 + (S - 1) * (g.accepted + g.rejected) + per_acc * g.accepted)
+    # per-trajectory parameters, backward time, vector tolerances, explicit h0, bounded h
+    mu = np.linspace(0.1, 4.0, 300)
+    def p2():
+        return (deb.EnsembleIVP.ode(deb.VanDerPolOscillator(mu), 5.0, 0.0, np.tile([2.0, 0.0], (300, 1))).t_eval([3.75, 1.25, 0.0, 4.999])
+                .method(getattr(E, ctor)().rtol([1e-6, 1e-7]).atol([1e-8, 1e-9]).h0(-1e-3).h_max(0.25)))
+    g, c = p2().solve(), ob.oracle_solve(p2())
+    assert_same_solution(g, c)
+    assert np.array_equal(g.evals, 1 + (S - 1) * (g.accepted + g.rejected) + per_acc * g.accepted)
+    # even(dt): every row through the polynomial; and the interpolant is accurate (harmonic oscillator, closed form)
+    def p3():
+        return (deb.EnsembleIVP.ode(deb.HarmonicOscillator(1.0), 0.0, 10.0, np.tile([1.0, 0.0], (96, 1)) * np.linspace(0.5, 2.0, 96)[:, None])
+                .even(0.37).method(getattr(E, ctor)().rtol(1e-10).atol(1e-10)))
+    g, c = p3().solve(), ob.oracle_solve(p3())
+    assert_same_solution(g, c)
+    s = g[95]
+    np.testing.assert_allclose(s.y[:, 0], 2.0 * np.cos(s.t), atol=5e-7)
+    # failures: MaxSteps mid-way (rows up to the failure), Stiffness through max_rejects
+    def p4():
+        return deb.EnsembleIVP.ode(lorenz(), 0.0, 20.0, y0[:64]).t_eval(np.arange(0.5, 20.0, 0.5)).method(getattr(E, ctor)().rtol(1e-9).max_steps(40))
+    g, c = p4().solve(), ob.oracle_solve(p4())
+    assert_same_solution(g, c)
+    assert (g.status == deb.DEB_STATUS_MAX_STEPS).all()
+    def p5():
+        return deb.EnsembleIVP.ode(deb.RobertsonProblem(), 0.0, 40.0, np.tile([1.0, 0.0, 0.0], (16, 1))).method(getattr(E, ctor)().h0(0.5).max_rejects(3))
+    g, c = p5().solve(), ob.oracle_solve(p5())
+    assert_same_solution(g, c)
+
+
+def test_verner_user_defined_rhs_bitwise():
+    """The NVRTC path instantiates the same kernel for a user system: Lorenz written as source == the built-in, for an
+    FSAL pair and for the widest tableau."""
+    y0 = ob.lorenz_ensemble_y0(200, seed=52)
+    src = "dydt[0] = p[0] * (y[1] - y[0]); dydt[1] = y[0] * (p[1] - y[2]) - y[1]; dydt[2] = y[0] * y[1] - p[2] * y[2];"
+    for ctor in ("rkv655e", "rkv989e"):
+        usr = deb.ode_from_source(3, src, params=[10.0, 28.0, 8.0 / 3.0])
+        def prob(sysm):
+            return deb.EnsembleIVP.ode(sysm, 0.0, 3.0, y0).t_eval([0.7, 1.9, 3.0]).method(getattr(E, ctor)().rtol(1e-8))
+        g, b = prob(usr).solve(), prob(lorenz()).solve()
+        assert_same_solution(g, b)
 
 
 # ------------------------------------------------------------------------------------------ EvenSolout (SURVEY 8f rank 1)

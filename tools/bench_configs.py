@@ -141,7 +141,7 @@ def c5(log2n, reps):
 
 
 def widened(n, reps):
-    """The widened rows: RKF45 / Cash-Karp, EvenSolout, a user-defined (NVRTC) right-hand side, on the C2 shape."""
+    """The widened rows: RKF45 / Cash-Karp, the Verner pairs, EvenSolout, a user-defined (NVRTC) right-hand side, on the C2 shape."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     y0h = deb.perturbed_ensemble([1.0, 1.0, 1.0], np.arange(n))
     y0 = torch.from_numpy(y0h).to(dev)
@@ -151,7 +151,12 @@ def widened(n, reps):
     out = []
     for label, system, method, solout in (("DOPRI5 t_eval (C2 shape)", deb.DEB_SYS_LORENZ, deb.DEB_DOPRI5, 0), ("DOPRI5 even(1.0)", deb.DEB_SYS_LORENZ, deb.DEB_DOPRI5, 1),
                                           ("RKF45 t_eval", deb.DEB_SYS_LORENZ, deb.DEB_RKF45, 0), ("Cash-Karp t_eval", deb.DEB_SYS_LORENZ, deb.DEB_CASH_KARP, 0),
-                                          ("DOP853 t_eval", deb.DEB_SYS_LORENZ, deb.DEB_DOP853, 0), ("user-defined Lorenz (NVRTC) DOPRI5 t_eval", user.system_id, deb.DEB_DOPRI5, 0)):
+                                          ("DOP853 t_eval", deb.DEB_SYS_LORENZ, deb.DEB_DOP853, 0), ("user-defined Lorenz (NVRTC) DOPRI5 t_eval", user.system_id, deb.DEB_DOPRI5, 0),
+                                          ("RKV655e t_eval", deb.DEB_SYS_LORENZ, deb.DEB_RKV655E, 0), ("RKV656e t_eval", deb.DEB_SYS_LORENZ, deb.DEB_RKV656E, 0),
+                                          ("RKV766e t_eval", deb.DEB_SYS_LORENZ, deb.DEB_RKV766E, 0), ("RKV767e t_eval", deb.DEB_SYS_LORENZ, deb.DEB_RKV767E, 0),
+                                          ("RKV877e t_eval", deb.DEB_SYS_LORENZ, deb.DEB_RKV877E, 0), ("RKV878e t_eval", deb.DEB_SYS_LORENZ, deb.DEB_RKV878E, 0),
+                                          ("RKV988e t_eval", deb.DEB_SYS_LORENZ, deb.DEB_RKV988E, 0), ("RKV989e t_eval", deb.DEB_SYS_LORENZ, deb.DEB_RKV989E, 0),
+                                          ("RKV655e even(1.0)", deb.DEB_SYS_LORENZ, deb.DEB_RKV655E, 1)):
         P = deb.OdeProblem()
         P.struct_size = C.sizeof(deb.OdeProblem)
         P.system, P.method, P.dim, P.n_params = system, method, 3, 3

@@ -12,7 +12,7 @@ on the GPU box, so the numbers are copied out ONCE, here, into a small fixture t
   tests/pde/method_of_lines.rs      heat equation KATs (coded directly in the tests; they are structural)
 
 Only cases whose system AND solver the ensemble path implements are kept (explicit RK: DOP853, DOPRI5, RK4,
-RKF45, CashKarp, ThreeEighths, Euler, Midpoint, Heun, Ralston); Verner and implicit solvers are out of scope.
+RKF45, CashKarp, ThreeEighths, Euler, Midpoint, Heun, Ralston, the Verner pairs); implicit, Adams and BDF solvers are out of scope.
 
 Usage: python tools/extract_reference_goldens.py   (writes tests/golden/reference_accuracy.json)
 """
@@ -26,7 +26,9 @@ OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 
 SYSTEMS = {"ExponentialGrowth": "exponential", "LinearEquation": "linear", "HarmonicOscillator": "harmonic",
            "LogisticEquation": "logistic", "RobertsonProblem": "robertson"}
 SOLVERS = {"DOP853": "dop853", "DOPRI5": "dopri5", "RKF45": "rkf45", "CashKarp": "cash_karp", "RK4": "rk4", "ThreeEighths": "three_eighths", "Euler": "euler",
-           "Midpoint": "midpoint", "Heun": "heun", "Ralston": "ralston"}
+           "Midpoint": "midpoint", "Heun": "heun", "Ralston": "ralston",
+           "RKV65": "rkv655e", "RKV766e": "rkv766e", "RKV767e": "rkv767e", "RKV877e": "rkv877e", "RKV878e": "rkv878e",
+           "RKV988e": "rkv988e", "RKV989e": "rkv989e"}
 
 
 def vec(s):
