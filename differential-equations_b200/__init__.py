@@ -48,9 +48,10 @@ DEB_MILSTEIN = 32
 DEB_SDE_OU, DEB_SDE_GBM = 0, 1
 DEB_STATUS_COMPLETE, DEB_STATUS_MAX_STEPS, DEB_STATUS_STEP_SIZE, DEB_STATUS_STIFFNESS, DEB_STATUS_BAD_INPUT = range(5)
 DEB_MEM_HOST, DEB_MEM_DEVICE = 0, 1
-DEB_SOLOUT_T_EVAL, DEB_SOLOUT_EVEN = 0, 1
+DEB_SOLOUT_T_EVAL, DEB_SOLOUT_EVEN, DEB_SOLOUT_DEFAULT, DEB_SOLOUT_DENSE, DEB_SOLOUT_CROSSING = 0, 1, 2, 3, 4
+CROSSING_BOTH, CROSSING_POSITIVE, CROSSING_NEGATIVE = 0, 1, -1  # CrossingDirection, src/solout/mod.rs
 DEB_OK, DEB_ERR_BAD_ARG, DEB_ERR_NO_DEVICE, DEB_ERR_CUDA, DEB_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
-DEB_ABI_VERSION = 4
+DEB_ABI_VERSION = 5
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -67,7 +68,8 @@ class OdeProblem(C.Structure):
                 ("n_params", C.c_int32), ("n_traj", C.c_int64), ("y0", C.c_void_p), ("params", C.c_void_p),
                 ("params_shared", C.c_int32), ("n_eval", C.c_int32), ("t_eval", _dp), ("t0", C.c_double), ("tf", C.c_double),
                 ("opt", ErkOptions), ("device", C.c_int32), ("memspace", C.c_int32), ("stream", C.c_void_p),
-                ("solout", C.c_int32), ("reserved0", C.c_int32), ("even_dt", C.c_double)]
+                ("solout", C.c_int32), ("dense_n", C.c_int32), ("even_dt", C.c_double),
+                ("cross_component", C.c_int32), ("cross_direction", C.c_int32), ("cross_threshold", C.c_double)]
 
 
 class SdeProblem(C.Structure):
@@ -82,7 +84,7 @@ class Result(C.Structure):
     _fields_ = [("struct_size", C.c_size_t), ("y_eval", C.c_void_p), ("n_emitted", C.c_void_p), ("t_final", C.c_void_p),
                 ("y_final", C.c_void_p), ("status", C.c_void_p), ("accepted", C.c_void_p), ("rejected", C.c_void_p),
                 ("evals", C.c_void_p), ("t_rows", _dp), ("n_rows", C.c_int32), ("kernel_ms", C.c_float),
-                ("total_ms", C.c_float)]
+                ("total_ms", C.c_float), ("t_out", C.c_void_p)]
 
 
 class HeatProblem(C.Structure):
@@ -121,7 +123,7 @@ def load_library() -> C.CDLL:
     lib.deb_solve_sde.argtypes = [C.POINTER(SdeProblem), C.POINTER(Result)]
     lib.deb_solve_heat_mol.argtypes = [C.POINTER(HeatProblem)]
     lib.deb_define_ode.argtypes = [C.c_int32, C.c_int32, C.c_char_p, _ip]
-    lib.deb_check_ode.argtypes = [C.c_int32, C.c_int32]
+    lib.deb_check_ode.argtypes = [C.c_int32, C.c_int32, C.c_int32]
     lib.deb_heat_rhs.argtypes = [C.POINTER(HeatProblem), C.c_void_p, C.c_void_p]
     lib.deb_erk_options_default.argtypes = [C.POINTER(ErkOptions)]
     lib.deb_erk_options_default.restype = None
@@ -230,11 +232,12 @@ def ode_from_source(dim: int, diff_body: str, params=(), lib=None) -> OdeSystem:
     return OdeSystem(sid.value, int(dim), prm)
 
 
-def check_ode(system: OdeSystem, method, lib=None) -> None:
-    """Compile a user-defined system for a method now (NVRTC, no GPU needed); raises ValueError with the compiler log."""
+def check_ode(system: OdeSystem, method, solout: int = DEB_SOLOUT_T_EVAL, lib=None) -> None:
+    """Compile the kernel for (system, method, recorder) now (NVRTC, no GPU needed); raises ValueError with the compiler
+    log when a user-defined right-hand side does not compile."""
     lib = lib or load_library()
     mid = method.method_id if hasattr(method, "method_id") else int(method)
-    _check(lib, lib.deb_check_ode(int(system.system_id), mid), "deb_check_ode")
+    _check(lib, lib.deb_check_ode(int(system.system_id), mid, int(solout)), "deb_check_ode")
 
 
 @dataclass
@@ -374,6 +377,7 @@ class EnsembleSolution:
         self.status, self.accepted, self.rejected, self.evals = status, accepted, rejected, evals
         self.kernel_ms, self.total_ms = kernel_ms, total_ms
         self.even_tf = None
+        self.t_out = None               # (N, n_eval) per-trajectory row times (per-step recorders), else None
 
     def __len__(self):
         return self.n
@@ -392,6 +396,8 @@ class EnsembleSolution:
         if st == DEB_STATUS_STIFFNESS:
             raise Stiffness(tfin, yf)
         m = int(self.n_emitted[i])
+        if self.t_out is not None and m > self.y_eval.shape[1]:
+            raise ValueError(f"trajectory {i} produced {m} rows but the row capacity is {self.y_eval.shape[1]}: raise max_rows")
         ts = self.row_times(i)
         return Solution(t=ts, y=self.y_eval[i, :m].copy(), status="Complete",
                         evals=Evals(int(self.evals[i])), steps=Steps(int(self.accepted[i]), int(self.rejected[i])),
@@ -400,6 +406,8 @@ class EnsembleSolution:
     def row_times(self, i) -> np.ndarray:
         """Solution.t of trajectory i."""
         m = int(self.n_emitted[i])
+        if self.t_out is not None:
+            return self.t_out[i, :min(m, self.t_out.shape[1])].copy()
         ts = np.empty(m)
         k = min(m, self.t_rows.size)
         ts[:k] = self.t_rows[:k]
@@ -413,15 +421,16 @@ class EnsembleSolution:
         return [_STATUS_NAME[int(s)] for s in self.status]
 
 
-def alloc_result_arrays(n, n_eval, dim):
-    return dict(y_eval=np.full((n, max(n_eval, 0), dim), np.nan), n_emitted=np.zeros(n, np.int32), t_final=np.zeros(n),
+def alloc_result_arrays(n, n_eval, dim, with_times=False):
+    extra = dict(t_out=np.full((n, max(n_eval, 0)), np.nan)) if with_times else {}
+    return dict(**extra, y_eval=np.full((n, max(n_eval, 0), dim), np.nan), n_emitted=np.zeros(n, np.int32), t_final=np.zeros(n),
                 y_final=np.zeros((n, dim)), status=np.full(n, -1, np.int32), accepted=np.zeros(n, np.int32),
                 rejected=np.zeros(n, np.int32), evals=np.zeros(n, np.int32))
 
 
 def bind_result(res: Result, arrs: dict, t_sorted: np.ndarray):
     res.struct_size = C.sizeof(Result)
-    for k in ("y_eval", "n_emitted", "t_final", "y_final", "status", "accepted", "rejected", "evals"):
+    for k in ("y_eval", "n_emitted", "t_final", "y_final", "status", "accepted", "rejected", "evals", "t_out"):
         a = arrs.get(k)
         setattr(res, k, a.ctypes.data if a is not None and a.size > 0 else None)
     res.t_rows = t_sorted.ctypes.data_as(_dp) if t_sorted.size else None
@@ -445,6 +454,7 @@ class EnsembleIVP:
         self.y0s = y0s
         self._t_eval = np.zeros(0)
         self._even_dt = 0.0
+        self._recorder = None  # (deb_solout, row capacity, dense n, component, threshold, direction)
         self._method: Optional[ExplicitRungeKutta] = None
         self._device = 0
         self.seed, self.path_offset = int(seed), int(path_offset)
@@ -471,6 +481,30 @@ class EnsembleIVP:
         self._t_eval = np.zeros(0)
         return self
 
+    # Per-step recorders: the rows of a trajectory depend on its own steps, so each trajectory gets `max_rows` row slots
+    # (rows beyond that are counted in n_emitted but not stored) and rows carry their own time (EnsembleSolution.t_out).
+    def _per_step(self, mode, max_rows, n=0, comp=0, thr=0.0, direction=0):
+        if self.kind != "ode":
+            raise ValueError("per-step recorders are implemented for ODE ensembles")
+        if int(max_rows) < 1:
+            raise ValueError("max_rows must be >= 1")
+        self._recorder = (mode, int(max_rows), int(n), int(comp), float(thr), int(direction))
+        self._even_dt, self._t_eval = 0.0, np.zeros(0)
+        return self
+
+    def every_step(self, max_rows: int):
+        """The recorder of a plain `IVP::solve()` (DefaultSolout, src/solout/default.rs): (t0, y0) and every accepted step."""
+        return self._per_step(DEB_SOLOUT_DEFAULT, max_rows)
+
+    def dense(self, n: int, max_rows: int):  # ivp.rs:650
+        """`IVP::dense(n)` (DenseSolout, src/solout/dense.rs): n-1 interpolated points inside every step + the step end."""
+        return self._per_step(DEB_SOLOUT_DENSE, max_rows, n=n)
+
+    def crossing(self, component_idx: int, threshold: float, direction: int = CROSSING_BOTH, max_rows: int = 64):  # ivp.rs:682
+        """`IVP::crossing(component, threshold, direction)` (CrossingSolout, src/solout/crossing.rs): only the points where
+        the component crosses the threshold, located by the reference's Newton iteration on the dense output."""
+        return self._per_step(DEB_SOLOUT_CROSSING, max_rows, comp=component_idx, thr=threshold, direction=direction)
+
     def method(self, m: ExplicitRungeKutta):  # ivp.rs:632
         self._method = m
         return self
@@ -495,6 +529,8 @@ class EnsembleIVP:
         n_eval = int(self._t_eval.size)
         if self._even_dt > 0.0:
             n_eval = int(math.floor(abs(self.tf - self.t0) / self._even_dt)) + 3  # row capacity per trajectory
+        if self._recorder is not None:
+            n_eval = self._recorder[1]
         res = Result()
         t_sorted = np.zeros(max(n_eval, 1))
         if self.kind == "ode":
@@ -524,9 +560,11 @@ class EnsembleIVP:
         P.t0, P.tf = self.t0, self.tf
         if self.kind == "ode" and self._even_dt > 0.0:
             P.solout, P.even_dt = DEB_SOLOUT_EVEN, self._even_dt
+        if self.kind == "ode" and self._recorder is not None:
+            P.solout, _, P.dense_n, P.cross_component, P.cross_threshold, P.cross_direction = self._recorder
         self._method.fill_options(P.opt, dim, keep)
         P.device, P.memspace, P.stream = self._device, DEB_MEM_HOST, None
-        arrs = alloc_result_arrays(n, n_eval, dim)
+        arrs = alloc_result_arrays(n, n_eval, dim, with_times=self._recorder is not None)
         bind_result(res, arrs, t_sorted)
         keep += [params, self.y0s, self._t_eval]
         return P, res, arrs, t_sorted, keep
@@ -550,6 +588,7 @@ class EnsembleIVP:
                                arrs["status"], arrs["accepted"], arrs["rejected"], arrs["evals"], res.kernel_ms, res.total_ms)
         if self._even_dt > 0.0:
             sol.even_tf = self.tf  # EvenSolout: a trajectory that lands exactly on tf has its last row at tf
+        sol.t_out = arrs.get("t_out")
         return sol
 
 

@@ -18,6 +18,7 @@
 #include <chrono>
 #include <mutex>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/deb_ensemble.h"
@@ -226,11 +227,31 @@ struct UserKernel {
 struct UserSystem {
     int dim = 0, np = 0;
     std::string body;
-    std::map<std::pair<int, int>, UserKernel> kernels;  // (device, method) -> compiled kernel
 };
 std::mutex g_user_mu;
 std::vector<std::unique_ptr<UserSystem>> g_user_systems;
 const int USER_SYSTEM_BASE = 1000;
+// run-time compiled kernels: (device, system id, method, per-step recorder) -> loaded kernel.  Besides user systems,
+// the per-step-recorder variants of the built-in systems are compiled on first use too (the ahead-of-time
+// instantiations cover the t_eval / even(dt) recorders).  Guarded by g_user_mu.
+std::map<std::tuple<int, int, int, int>, UserKernel> g_jit_kernels;
+
+// built-in system id -> (struct name, dim, n_params)
+const char* builtin_system_name(int system, int* dim, int* np) {
+#define DEB_SYS_CASE(ID, T) case ID: *dim = deb::T::DIM; *np = deb::T::NP; return "deb::" #T;
+    switch (system) {
+        DEB_SYS_CASE(DEB_SYS_EXPONENTIAL, SysExponential)
+        DEB_SYS_CASE(DEB_SYS_LINEAR, SysLinear)
+        DEB_SYS_CASE(DEB_SYS_HARMONIC, SysHarmonic)
+        DEB_SYS_CASE(DEB_SYS_LOGISTIC, SysLogistic)
+        DEB_SYS_CASE(DEB_SYS_VAN_DER_POL, SysVanDerPol)
+        DEB_SYS_CASE(DEB_SYS_LORENZ, SysLorenz)
+        DEB_SYS_CASE(DEB_SYS_BRUSSELATOR, SysBrusselator)
+        DEB_SYS_CASE(DEB_SYS_ROBERTSON, SysRobertson)
+    }
+#undef DEB_SYS_CASE
+    return nullptr;
+}
 
 const char* method_tab_name(int method, bool* adaptive) {
     *adaptive = false;
@@ -258,8 +279,14 @@ const char* method_tab_name(int method, bool* adaptive) {
     return nullptr;
 }
 
-// Compile the ensemble kernel for a user system and a method to a cubin (no device needed).
-int compile_user_cubin(const UserSystem& us, int method, std::vector<char>* cubin, std::string* kernel_name, bool* is_adaptive) {
+// Compile the ensemble kernel for (system, method, recorder kind) to a cubin (no device needed).  `us` = the user
+// system, or null for a built-in one.
+int compile_kernel_cubin(const UserSystem* us, int system, int method, bool rec, std::vector<char>* cubin, std::string* kernel_name,
+                         bool* is_adaptive) {
+    int sdim = 0, snp = 0;
+    const char* sys_name = us ? "deb::UserSys" : builtin_system_name(system, &sdim, &snp);
+    if (!sys_name) return fail(DEB_ERR_BAD_ARG, "unknown system id");
+    if (us) { sdim = us->dim; snp = us->np; }
     bool adaptive = false;
     const char* tab = method_tab_name(method, &adaptive);
     if (!tab) return fail(DEB_ERR_UNSUPPORTED, "unknown or unsupported method id");
@@ -268,21 +295,24 @@ int compile_user_cubin(const UserSystem& us, int method, std::vector<char>* cubi
     // occupancy hint: stage vectors live in registers, wider systems get the whole register file of fewer CTAs
     int min_blocks = 1;
     if (adaptive) {
-        if (method == DEB_DOP853) min_blocks = us.dim <= 2 ? 4 : us.dim == 3 ? 3 : us.dim <= 6 ? 2 : 1;
-        else if (method >= DEB_RKV655E && method <= DEB_RKV989E) min_blocks = us.dim <= 2 ? 4 : us.dim == 3 ? 3 : us.dim <= 5 ? 2 : 1;
-        else min_blocks = us.dim <= 3 ? 5 : us.dim <= 6 ? 3 : us.dim <= 10 ? 2 : 1;
+        if (method == DEB_DOP853) min_blocks = sdim <= 2 ? 4 : sdim == 3 ? 3 : sdim <= 6 ? 2 : 1;
+        else if (method >= DEB_RKV655E && method <= DEB_RKV989E) min_blocks = sdim <= 2 ? 4 : sdim == 3 ? 3 : sdim <= 5 ? 2 : 1;
+        else min_blocks = sdim <= 3 ? 5 : sdim <= 6 ? 3 : sdim <= 10 ? 2 : 1;
+        if (rec && min_blocks > 1) min_blocks -= 1;  // the recorder keeps the dense output of a step live
     }
     char expr[256];
-    if (adaptive) snprintf(expr, sizeof expr, "deb::dp_ensemble_kernel<deb::UserSys, %s, 128, %d, false>", tab, min_blocks);
-    else snprintf(expr, sizeof expr, "deb::fixed_ensemble_kernel<deb::UserSys, %s, 128>", tab);
+    if (adaptive) snprintf(expr, sizeof expr, "deb::dp_ensemble_kernel<%s, %s, 128, %d, false, %s>", sys_name, tab, min_blocks, rec ? "true" : "false");
+    else snprintf(expr, sizeof expr, "deb::fixed_ensemble_kernel<%s, %s, 128, %s>", sys_name, tab, rec ? "true" : "false");
     std::string src;
-    src += "#include \"erk_fixed.cuh\"\n";
-    src += "namespace deb {\nstruct UserSys {\n";
-    src += "    static constexpr int DIM = " + std::to_string(us.dim) + ", NP = " + std::to_string(us.np) + ";\n";
-    src += "    __device__ __forceinline__ static void rhs(double t, const double* y, double* dydt, const double* p) {\n";
-    src += "        (void)t; (void)y; (void)p;\n";
-    src += us.body;
-    src += "\n    }\n};\n}  // namespace deb\n";
+    src += "#include \"erk_fixed.cuh\"\n#include \"systems.cuh\"\n";
+    if (us) {
+        src += "namespace deb {\nstruct UserSys {\n";
+        src += "    static constexpr int DIM = " + std::to_string(us->dim) + ", NP = " + std::to_string(us->np) + ";\n";
+        src += "    __device__ __forceinline__ static void rhs(double t, const double* y, double* dydt, const double* p) {\n";
+        src += "        (void)t; (void)y; (void)p;\n";
+        src += us->body;
+        src += "\n    }\n};\n}  // namespace deb\n";
+    }
     // headers: the embedded kernel sources + minimal stand-ins for the C headers NVRTC does not ship
     std::vector<const char*> hdr_names, hdr_text;
     for (const auto& e : deb_embedded_sources) { hdr_names.push_back(e.name); hdr_text.push_back(e.text); }
@@ -308,7 +338,7 @@ int compile_user_cubin(const UserSystem& us, int method, std::vector<char>* cubi
         rt->GetProgramLogSize(prog, &n);
         std::string log(n, '\0');
         if (n) rt->GetProgramLog(prog, &log[0]);
-        return fail(DEB_ERR_BAD_ARG, "the right-hand side did not compile (NVRTC):\n" + log);
+        return fail(us ? DEB_ERR_BAD_ARG : DEB_ERR_CUDA, (us ? "the right-hand side did not compile (NVRTC):\n" : "run-time kernel compilation failed (NVRTC):\n") + log);
     }
     const char* lowered = nullptr;
     r = rt->GetLoweredName(prog, expr, &lowered);
@@ -319,20 +349,24 @@ int compile_user_cubin(const UserSystem& us, int method, std::vector<char>* cubi
     cubin->resize(nbin);
     if (rt->GetCUBIN(prog, cubin->data()) != NVRTC_SUCCESS) return fail(DEB_ERR_CUDA, "nvrtcGetCUBIN failed");
     *is_adaptive = adaptive;
+    if (const char* dump = getenv("DEB_DUMP_CUBIN")) {  // debugging aid: keep the last run-time compiled cubin for cuobjdump
+        if (FILE* f = fopen(dump, "wb")) { fwrite(cubin->data(), 1, cubin->size(), f); fclose(f); }
+    }
     return DEB_OK;
 }
 
-// Compile and load (once per device/method) the ensemble kernel for a user system.  Caller holds g_user_mu.
-int user_kernel(UserSystem& us, int device, int method, UserKernel** out) {
-    auto it = us.kernels.find({device, method});
-    if (it != us.kernels.end()) { *out = &it->second; return DEB_OK; }
+// Compile and load (once per device / system / method / recorder kind) a run-time kernel.  Caller holds g_user_mu.
+int jit_kernel(const UserSystem* us, int device, int system, int method, bool rec, UserKernel** out) {
+    const auto key = std::make_tuple(device, system, method, rec ? 1 : 0);
+    auto it = g_jit_kernels.find(key);
+    if (it != g_jit_kernels.end()) { *out = &it->second; return DEB_OK; }
     std::vector<char> cubin;
     std::string lowered;
     UserKernel uk;
-    if (int rc = compile_user_cubin(us, method, &cubin, &lowered, &uk.adaptive)) return rc;
+    if (int rc = compile_kernel_cubin(us, system, method, rec, &cubin, &lowered, &uk.adaptive)) return rc;
     DEB_CUDA(cudaLibraryLoadData(&uk.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
     DEB_CUDA(cudaLibraryGetKernel(&uk.kernel, uk.lib, lowered.c_str()));
-    auto ins = us.kernels.emplace(std::make_pair(device, method), uk);
+    auto ins = g_jit_kernels.emplace(key, uk);
     *out = &ins.first->second;
     return DEB_OK;
 }
@@ -350,6 +384,7 @@ int launch_user(const UserKernel& uk, const deb::OdeKernelArgs& a, int sms, cuda
     const long long need = (a.n_traj + uk.block - 1) / uk.block;
     if (blocks > need) blocks = need;
     if (blocks < 1) blocks = 1;
+    if (getenv("DEB_DEBUG_LAUNCH")) fprintf(stderr, "[deb] run-time kernel: grid %lld x %d\n", blocks, uk.block);
     void* args[] = {(void*)&a};
     DEB_CUDA(cudaLaunchKernel((const void*)uk.kernel, dim3((unsigned)blocks), dim3(uk.block), args, 0, st));
     return DEB_OK;
@@ -393,15 +428,16 @@ struct DevBuf {
 
 struct ResultPtrs {
     double* y_eval; int* n_emitted; double* t_final; double* y_final; int* status; int* accepted; int* rejected; int* evals;
+    double* t_out;
 };
 
 // Allocates device mirrors for the requested outputs (HOST memspace) or passes device pointers through.
 struct ResultStage {
-    DevBuf y_eval, n_emitted, t_final, y_final, status, accepted, rejected, evals;
+    DevBuf y_eval, n_emitted, t_final, y_final, status, accepted, rejected, evals, t_out;
     ResultPtrs dev{};
     int setup(const deb_result* R, bool host, long long n, int n_eval, int dim) {
         if (!host) {
-            dev = {R->y_eval, R->n_emitted, R->t_final, R->y_final, R->status, R->accepted, R->rejected, R->evals};
+            dev = {R->y_eval, R->n_emitted, R->t_final, R->y_final, R->status, R->accepted, R->rejected, R->evals, R->t_out};
             return DEB_OK;
         }
 #define DEB_STAGE(field, T, count)                                         \
@@ -417,6 +453,7 @@ struct ResultStage {
         DEB_STAGE(accepted, int, n)
         DEB_STAGE(rejected, int, n)
         DEB_STAGE(evals, int, n)
+        DEB_STAGE(t_out, double, (size_t)n * n_eval)
 #undef DEB_STAGE
         return DEB_OK;
     }
@@ -431,6 +468,7 @@ struct ResultStage {
         DEB_BACK(accepted, int, n)
         DEB_BACK(rejected, int, n)
         DEB_BACK(evals, int, n)
+        DEB_BACK(t_out, double, (size_t)n * n_eval)
 #undef DEB_BACK
         return DEB_OK;
     }
@@ -504,8 +542,17 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P, deb_result* R) {
     if (int rc = check_options(P->opt)) return rc;
     TEvalPlan plan;
     const bool even = (P->solout == DEB_SOLOUT_EVEN);
-    if (P->solout != DEB_SOLOUT_T_EVAL && !even) return fail(DEB_ERR_BAD_ARG, "unknown solout mode");
-    if (even) {
+    const bool rec = (P->solout == DEB_SOLOUT_DEFAULT || P->solout == DEB_SOLOUT_DENSE || P->solout == DEB_SOLOUT_CROSSING);
+    if (P->solout != DEB_SOLOUT_T_EVAL && !even && !rec) return fail(DEB_ERR_BAD_ARG, "unknown solout mode");
+    if (rec) {
+        // per-step recorders: no row plan; n_eval is the row capacity per trajectory
+        if (!R->y_eval) return fail(DEB_ERR_BAD_ARG, "a per-step recorder needs a y_eval buffer");
+        if (P->solout == DEB_SOLOUT_DENSE && P->dense_n < 0) return fail(DEB_ERR_BAD_ARG, "dense(n): n < 0");
+        if (P->solout == DEB_SOLOUT_CROSSING) {
+            if (P->cross_component < 0 || P->cross_component >= dim) return fail(DEB_ERR_BAD_ARG, "crossing: component index out of range");
+            if (P->cross_direction < -1 || P->cross_direction > 1) return fail(DEB_ERR_BAD_ARG, "crossing: direction must be -1, 0 or +1");
+        }
+    } else if (even) {
         // EvenSolout::solout (even.rs:69-199): t0 is emitted by the call before the loop, then last + dt*direction,
         // accumulated, while the point is not past tf
         if (!(P->even_dt > 0.0) || !(P->tf != P->t0)) return fail(DEB_ERR_BAD_ARG, "even(dt): dt must be > 0 and tf != t0");
@@ -527,10 +574,11 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P, deb_result* R) {
     if (int rc = select_device(P->device)) return rc;
     DeviceInfo di;
     if (int rc = device_info(P->device, &di)) return rc;
-    if (user) {  // user-defined right-hand side: compile (first use) and bind the run-time kernel
+    const bool jit = user || rec;
+    if (jit) {  // user-defined right-hand side, or a per-step recorder: compile (first use) and bind the run-time kernel
         std::lock_guard<std::mutex> lk(g_user_mu);
         UserKernel* uk = nullptr;
-        if (int rc = user_kernel(*user, P->device, P->method, &uk)) return rc;
+        if (int rc = jit_kernel(user, P->device, P->system, P->method, rec, &uk)) return rc;
         const UserKernel ukc = *uk;
         launch = [ukc](const deb::OdeKernelArgs& ka, int sms, cudaStream_t s2) { return launch_user(ukc, ka, sms, s2); };
     }
@@ -540,11 +588,11 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P, deb_result* R) {
     // ---- kernel arguments common to every launch of this call
     deb::OdeKernelArgs a;
     memset(&a, 0, sizeof a);
-    DevBuf d_shared_params;  // user kernels are built with SHARED_P = false: a shared set is read through the pointer (stride 0)
+    DevBuf d_shared_params;  // run-time kernels are built with SHARED_P = false: a shared set is read through the pointer (stride 0)
     if (np > 0 && P->params_shared) {
         // one parameter set for the whole ensemble: HOST memory by contract, passed by value (constant bank)
         for (int q = 0; q < np && q < 8; q++) a.pc[q] = P->params[q];
-        if (user || np > 8) {
+        if (jit || np > 8) {
             DEB_CUDA(d_shared_params.alloc(sizeof(double) * np));
             DEB_CUDA(cudaMemcpy(d_shared_params.p, P->params, sizeof(double) * np, cudaMemcpyHostToDevice));
         }
@@ -570,6 +618,11 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P, deb_result* R) {
     a.emit_t0 = plan.emit_t0 ? 1 : 0;
     a.even = even ? 1 : 0;
     a.even_tol = fabs(P->even_dt) * 1e-12 + 2.220446049250313e-16 * 10.0;
+    a.rec_mode = rec ? P->solout : 0;
+    a.dense_n = P->dense_n;
+    a.cross_component = P->cross_component;
+    a.cross_direction = P->cross_direction;
+    a.cross_threshold = P->cross_threshold;
     const bool per_traj_params = (np > 0 && !P->params_shared);
     const size_t rows_bytes = sizeof(double) * plan.rows.size();
 
@@ -588,6 +641,7 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P, deb_result* R) {
         a.n_traj = n;
         a.y_eval = R->y_eval; a.n_emitted = R->n_emitted; a.t_final = R->t_final; a.y_final = R->y_final;
         a.status = R->status; a.accepted = R->accepted; a.rejected = R->rejected; a.evals = R->evals;
+        a.t_out = R->t_out;
         return launch(a, di.sms, st);
     }
 
@@ -609,7 +663,7 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P, deb_result* R) {
     struct Slot {
         cudaStream_t st = nullptr;
         cudaEvent_t k0 = nullptr, k1 = nullptr;
-        DevBuf y0, params, small, y_eval, n_emitted, t_final, y_final, status, accepted, rejected, evals;
+        DevBuf y0, params, small, y_eval, n_emitted, t_final, y_final, status, accepted, rejected, evals, t_out;
         bool used = false;
         ~Slot() {
             if (k0) cudaEventDestroy(k0);
@@ -634,6 +688,7 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P, deb_result* R) {
         if (R->accepted) DEB_CUDA(S.accepted.alloc(sizeof(int) * (size_t)chunk));
         if (R->rejected) DEB_CUDA(S.rejected.alloc(sizeof(int) * (size_t)chunk));
         if (R->evals) DEB_CUDA(S.evals.alloc(sizeof(int) * (size_t)chunk));
+        if (R->t_out) DEB_CUDA(S.t_out.alloc(sizeof(double) * (size_t)chunk * n_eval));
     }
     float kernel_ms = 0.f;
     int ci = 0;
@@ -659,6 +714,7 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P, deb_result* R) {
         ac.y_eval = S.y_eval.as<double>(); ac.n_emitted = S.n_emitted.as<int>(); ac.t_final = S.t_final.as<double>();
         ac.y_final = S.y_final.as<double>(); ac.status = S.status.as<int>(); ac.accepted = S.accepted.as<int>();
         ac.rejected = S.rejected.as<int>(); ac.evals = S.evals.as<int>();
+        ac.t_out = S.t_out.as<double>();
         DEB_CUDA(cudaEventRecord(S.k0, S.st));
         if (int rc = launch(ac, di.sms, S.st)) return rc;
         DEB_CUDA(cudaEventRecord(S.k1, S.st));
@@ -674,6 +730,7 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P, deb_result* R) {
         DEB_BACK(accepted, int, 1)
         DEB_BACK(rejected, int, 1)
         DEB_BACK(evals, int, 1)
+        DEB_BACK(t_out, double, (size_t)n_eval)
 #undef DEB_BACK
     }
     for (int s = 0; s < n_slots; s++) {
@@ -703,14 +760,24 @@ extern "C" int deb_define_ode(int32_t dim, int32_t n_params, const char* diff_bo
     return DEB_OK;
 }
 
-extern "C" int deb_check_ode(int32_t system_id, int32_t method) {
+extern "C" int deb_check_ode(int32_t system_id, int32_t method, int32_t solout) {
     std::lock_guard<std::mutex> lk(g_user_mu);
-    const int u = system_id - USER_SYSTEM_BASE;
-    if (u < 0 || u >= (int)g_user_systems.size()) return fail(DEB_ERR_BAD_ARG, "not a user-defined system id");
+    const UserSystem* us = nullptr;
+    if (system_id >= USER_SYSTEM_BASE) {
+        const int u = system_id - USER_SYSTEM_BASE;
+        if (u >= (int)g_user_systems.size()) return fail(DEB_ERR_BAD_ARG, "unknown system id");
+        us = g_user_systems[u].get();
+    }
+    const bool rec = (solout == DEB_SOLOUT_DEFAULT || solout == DEB_SOLOUT_DENSE || solout == DEB_SOLOUT_CROSSING);
+    if (!us && !rec) {  // built-in system with a row-plan recorder: compiled ahead of time
+        int dim = 0, np = 0;
+        if (!pick_ode(system_id, method, &dim, &np)) return fail(dim < 0 ? DEB_ERR_BAD_ARG : DEB_ERR_UNSUPPORTED, "unknown system or method id");
+        return DEB_OK;
+    }
     std::vector<char> cubin;
     std::string name;
     bool adaptive = false;
-    return compile_user_cubin(*g_user_systems[u], method, &cubin, &name, &adaptive);
+    return compile_kernel_cubin(us, system_id, method, rec, &cubin, &name, &adaptive);
 }
 
 extern "C" int deb_solve_sde(const deb_sde_problem* P, deb_result* R) {

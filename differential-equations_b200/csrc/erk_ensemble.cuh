@@ -45,6 +45,12 @@ struct OdeKernelArgs {
     int even;               // EvenSolout (src/solout/even.rs): rows are t0 + k*dt, always interpolated; the LAST entry of
                             // t_rows is a sentinel equal to tf that triggers the final-point rule (even.rs:166-188)
     double even_tol;        // |dt|*1e-12 + 10 eps (even.rs:92-93)
+    // per-step recorders (step_recorder.cuh; kernels instantiated with REC = true): rows carry their own time
+    int rec_mode;           // 0, or DEB_SOLOUT_DEFAULT / DENSE / CROSSING
+    int dense_n;
+    int cross_component, cross_direction;
+    double cross_threshold;
+    double* t_out;          // [n_traj][row_stride] or null
     double* y_eval;
     int* n_emitted;
     double* t_final;
@@ -129,6 +135,12 @@ __device__ __forceinline__ void load_pow_tables(double* s_powlog, unsigned long 
     __syncthreads();
 }
 
+}  // namespace deb
+
+#include "step_recorder.cuh"
+
+namespace deb {
+
 // ------------------------------------------------------------------------------------------------------------
 // Dormand-Prince family (DOPRI5, DOP853): adaptive step, embedded error norm, I-controller, dense output.
 // ------------------------------------------------------------------------------------------------------------
@@ -185,7 +197,8 @@ __device__ __noinline__ void all_terms_attempt(const double* y, double* k, doubl
     *err_out = err;
 }
 
-template <class Sys, class Tab, int BLOCK, int MIN_BLOCKS, bool SHARED_P>
+// REC: the output goes through a per-step recorder (step_recorder.cuh) instead of the t_eval / even(dt) row plan.
+template <class Sys, class Tab, int BLOCK, int MIN_BLOCKS, bool SHARED_P, bool REC = false>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const OdeKernelArgs a) {
     constexpr int N = Sys::DIM, NP = Sys::NP, S = Tab::S, I = Tab::I, O = Tab::O;
     constexpr unsigned FULL = 0xffffffffu;
@@ -206,7 +219,8 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
     const int evals_base = (a.h0 == 0.0) ? (Tab::DP ? 3 : 5) : 1;
     const bool bounded_h = (a.h_min > 0.0) || (a.h_max < 1.0 / 0.0);  // constrain_step_size can change h at all
 
-    constexpr bool DEFER = (I == S);   // dense output needs no extra stages: emission can be parked
+    constexpr bool DEFER = (I == S) && !REC;   // dense output needs no extra stages: emission can be parked
+    StepRecorder<Sys, Tab> recd;
     constexpr int NSTASH = 2 + 4 * N;  // t, h, y, y_new, k0, f(y_new)
     __shared__ double s_stash[DEFER ? (BLOCK / 32) : 1][DEFER ? NSTASH : 1][32];
     double (*stash)[32] = s_stash[DEFER ? (threadIdx.x >> 5) : 0];
@@ -323,7 +337,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
             // stages); dense-polynomial pairs I-S dense stages (+1 unless FSAL), adaptive/ordinary.rs:145-174
             constexpr int PER_ACC = Tab::BI_POLY ? ((I - S) + (Tab::FSAL ? 0 : 1)) : (1 + ((I > S) ? (I - S - 1) : 0));
             if (a.evals) a.evals[traj] = evals_base + (S - 1) * (acc + rej) + acc * PER_ACC;
-            if (a.n_emitted) a.n_emitted[traj] = idx;
+            if (a.n_emitted) a.n_emitted[traj] = REC ? recd.rows : idx;
             active = false;
             // idle dummy state: finite, never committed
             t = t0; h = 0.0; h_prev = 0.0; te = te_none;
@@ -387,6 +401,10 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
                             idx = 1;
                         }
                         te = (idx < a.n_rows) ? a.t_rows[idx] : te_none;
+                        if constexpr (REC) {  // the solout call that precedes the loop
+                            recd.reset();
+                            recd.first(a, traj, t0, y);
+                        }
                         active = true;
                     }
                 }
@@ -739,6 +757,11 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
                         te = (idx < a.n_rows) ? a.t_rows[idx] : te_none;
                     }
                 }
+                __syncwarp();
+            }
+
+            if constexpr (REC) {  // solout after an accepted step (solve_ivp.rs:239-246)
+                if (accept && fin < 0) recd.step(a, traj, t, h, y, ynew, k, dydt, p);
                 __syncwarp();
             }
 

@@ -14,7 +14,7 @@
 
 namespace deb {
 
-template <class Sys, class Tab, int BLOCK>
+template <class Sys, class Tab, int BLOCK, bool REC = false>
 __global__ void __launch_bounds__(BLOCK) fixed_ensemble_kernel(const OdeKernelArgs a) {
     constexpr int N = Sys::DIM, NP = Sys::NP, S = Tab::S;
     const double t0 = a.t0, tf = a.tf;
@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(BLOCK) fixed_ensemble_kernel(const OdeKernelAr
         for (int q = 0; q < NP; q++) p[q] = a.params ? a.params[traj * a.params_stride + q] : a.pc[q];
         int steps = 0, evals = 0, n_emit = 0, idx = 0;
         int fin = -1;
+        StepRecorder<Sys, Tab> recd;
         double t = t0;
         // ---- init, fixed/ordinary.rs:16-56
         double h = a.h0;
@@ -48,6 +49,7 @@ __global__ void __launch_bounds__(BLOCK) fixed_ensemble_kernel(const OdeKernelAr
                 n_emit = 1;
                 idx = 1;
             }
+            if constexpr (REC) recd.first(a, traj, t0, y);  // the solout call that precedes the loop
         }
         double te = (idx < a.n_rows) ? a.t_rows[idx] : te_none;
         while (fin < 0) {
@@ -92,8 +94,9 @@ __global__ void __launch_bounds__(BLOCK) fixed_ensemble_kernel(const OdeKernelAr
             const double t_new = t + h;
             Sys::rhs(t_new, ynew, dnew, p);
             evals += S;  // S-1 stages + the new derivative (fsal = false)
+            if constexpr (REC) recd.step(a, traj, t, h, y, ynew, k, dnew, p);
             // ---- TEvalSolout with cubic Hermite interpolation
-            while ((dir > 0.0) ? (te <= t_new) : (te >= t_new)) {
+            while (!REC && ((dir > 0.0) ? (te <= t_new) : (te >= t_new))) {
                 if (a.even && idx == a.n_rows - 1) {  // the tf sentinel: EvenSolout final-point rule, even.rs:166-188
                     int w = -1;
                     if (t_new == tf) {
@@ -154,7 +157,7 @@ __global__ void __launch_bounds__(BLOCK) fixed_ensemble_kernel(const OdeKernelAr
         if (a.accepted) a.accepted[traj] = steps;
         if (a.rejected) a.rejected[traj] = 0;
         if (a.evals) a.evals[traj] = evals;
-        if (a.n_emitted) a.n_emitted[traj] = n_emit;
+        if (a.n_emitted) a.n_emitted[traj] = REC ? recd.rows : n_emit;
     }
 }
 

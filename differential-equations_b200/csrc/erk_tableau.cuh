@@ -147,6 +147,7 @@ DEB_VERNER_TAB(TabRkv989e, RKV989E, v989, 9, 16, 26, false)
     struct Name {                                                    \
         static constexpr int O = order, S = stages, I = stages;      \
         static constexpr bool ADAPTIVE = false, HAS_BH = false;      \
+        static constexpr bool DP = false, FSAL = false, BI_POLY = false; \
         DEB_TAB_FN1(c, stages, DEB_##PFX##_C, pfx##_c)               \
         DEB_TAB_FN2(a, stages, DEB_##PFX##_A, pfx##_a)               \
         DEB_TAB_FN1(b, stages, DEB_##PFX##_B, pfx##_b)               \

@@ -6,6 +6,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/deb_ensemble.h"
 #include "erk_ensemble.cuh"
@@ -48,6 +49,7 @@ int launch_dp_impl(const deb::OdeKernelArgs& a, int sms, cudaStream_t st) {
     const long long need = (a.n_traj + BLOCK - 1) / BLOCK;
     if (blocks > need) blocks = need;
     if (blocks < 1) blocks = 1;
+    if (getenv("DEB_DEBUG_LAUNCH")) fprintf(stderr, "[deb] built-in kernel: grid %lld x %d\n", blocks, BLOCK);
     kern<<<(unsigned)blocks, BLOCK, 0, st>>>(a);
     DEB_DISPATCH_CUDA(cudaGetLastError());
     return DEB_OK;

@@ -1,0 +1,275 @@
+// step_recorder.cuh -- the per-step output recorders of the reference, on the device:
+//     DefaultSolout    /root/reference/src/solout/default.rs:54-75     every accepted step (t, y)
+//     DenseSolout      /root/reference/src/solout/dense.rs:74-108      n-1 interpolated points per step + the step end
+//     CrossingSolout   /root/reference/src/solout/crossing.rs:115-263  component crossing a threshold, refined by the
+//                                                                      reference's Newton iteration on the dense output
+// Unlike t_eval / even(dt), the row times depend on the trajectory, so rows carry their own time (t_out) and the
+// number of rows is not known in advance: each trajectory owns `row_stride` row slots; pushes beyond that are counted
+// (n_emitted) but not stored.
+//
+// DenseStep is the dense output of one accepted step, as the reference's `Interpolation::interpolate` computes it:
+//     Dormand-Prince family   dormandprince/ordinary.rs:196-234 (cont) + :301-337 (nested polynomial)
+//     Verner pairs            adaptive/ordinary.rs:145-160 (extra stages) + :246-277 (Horner in s)
+//     everything else         cubic Hermite, src/interpolate.rs:40-60
+// The reference's bounds check (`t < t_prev || t > t_curr` => Err(OutOfBounds), unwrapped by the recorders) is written
+// for forward time; where it would panic (backward time, or the Newton probe t + 1e-6*(step) just past the step end)
+// the polynomial is simply evaluated.
+// (included by erk_ensemble.cuh after OdeKernelArgs and d_signum)
+#pragma once
+
+namespace deb {
+
+enum { REC_NONE = 0, REC_DEFAULT = 2, REC_DENSE = 3, REC_CROSSING = 4 };  // = deb_solout values
+
+template <class Sys, class Tab>
+struct DenseStep {
+    static constexpr int N = Sys::DIM, S = Tab::S, I = Tab::I, O = Tab::O;
+    static constexpr bool DP = Tab::ADAPTIVE && Tab::DP, BI = Tab::ADAPTIVE && Tab::BI_POLY;
+    static constexpr int NK = BI ? I : 1;
+    double t, h, t_new;
+    double y[N], yn[N];
+    double c1[N], c2[N], c3[N], ch[(O > 4) ? (O - 4) : 1][N];  // DP family
+    double kk[NK][N];                                          // Verner pairs: all I stage vectors
+    double d0[N], d1[N];                                       // Hermite: derivatives at both ends
+
+    // state before the step (t, y, k[0] = f(t,y)), the step (h, k[1..S-1], y_new) and dydt = f(t+h, y_new)
+    __device__ __forceinline__ void prepare(double t_, double h_, const double (&y_)[N], const double (&yn_)[N],
+                                            const double (&k)[S][N], const double (&dydt)[N], const double* p) {
+        t = t_; h = h_; t_new = t_ + h_;
+#pragma unroll
+        for (int c = 0; c < N; c++) { y[c] = y_[c]; yn[c] = yn_[c]; d0[c] = k[0][c]; d1[c] = dydt[c]; }
+        if constexpr (DP) {
+#pragma unroll
+            for (int c = 0; c < N; c++) {
+                c1[c] = yn[c] - y[c];
+                c2[c] = __dadd_rn(0.0, h * k[0][c]) - c1[c];
+                c3[c] = (c1[c] + (-h) * dydt[c]) - c2[c];
+            }
+            double kx[(I > S) ? (I - S) : 1][N];
+#pragma unroll
+            for (int c = 0; c < N; c++) kx[0][c] = dydt[c];
+#pragma unroll
+            for (int i = S + 1; i < I; i++) {
+                double ys[N];
+#pragma unroll
+                for (int c = 0; c < N; c++) ys[c] = y[c];
+#pragma unroll
+                for (int j = 0; j < i; j++) {
+                    if (Tab::a(i, j) != 0.0) {
+                        const double ah = Tab::av(i, j) * h;
+#pragma unroll
+                        for (int c = 0; c < N; c++) ys[c] = ys[c] + ah * ((j < S) ? k[(j < S) ? j : 0][c] : kx[(j >= S) ? (j - S) : 0][c]);
+                    }
+                }
+                Sys::rhs(t + Tab::cv(i) * h, ys, kx[i - S], p);
+            }
+#pragma unroll
+            for (int i = 4; i < O; i++) {
+#pragma unroll
+                for (int c = 0; c < N; c++) ch[i - 4][c] = 0.0;
+#pragma unroll
+                for (int j = 0; j < I; j++) {
+                    if (Tab::bi(i, j) != 0.0) {
+#pragma unroll
+                        for (int c = 0; c < N; c++)
+                            ch[i - 4][c] = __dadd_rn(ch[i - 4][c], Tab::biv(i, j) * ((j < S) ? k[(j < S) ? j : 0][c] : kx[(j >= S) ? (j - S) : 0][c]));
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < N; c++) ch[i - 4][c] = ch[i - 4][c] * h;
+            }
+        } else if constexpr (BI) {
+#pragma unroll
+            for (int i = 0; i < S; i++) {
+#pragma unroll
+                for (int c = 0; c < N; c++) kk[i][c] = k[i][c];
+            }
+#pragma unroll
+            for (int i = S; i < I; i++) {
+                double ys[N];
+#pragma unroll
+                for (int c = 0; c < N; c++) ys[c] = y[c];
+#pragma unroll
+                for (int j = 0; j < i; j++) {
+                    if (Tab::a(i, j) != 0.0) {
+                        const double ah = Tab::av(i, j) * h;
+#pragma unroll
+                        for (int c = 0; c < N; c++) ys[c] = ys[c] + ah * kk[j][c];
+                    }
+                }
+                Sys::rhs(t + Tab::cv(i) * h, ys, kk[i], p);
+            }
+        }
+    }
+
+    __device__ __forceinline__ void eval(double te, double (&row)[N]) const {
+        if constexpr (DP) {
+            const double sx = (te - t) / h;
+            const double s1 = 1.0 - sx;
+#pragma unroll
+            for (int c = 0; c < N; c++) {
+                double accp = (O > 4) ? ch[(O > 4) ? (O - 5) : 0][c] : c3[c];
+#pragma unroll
+                for (int i = O - 2; i >= 1; i--) {
+                    double factor;
+                    if (i >= 4) factor = (((O - 1) - i) % 2 == 1) ? s1 : sx;
+                    else factor = (i % 2 == 1) ? s1 : sx;
+                    const double ci = (i >= 4) ? ch[(i >= 4) ? (i - 4) : 0][c] : (i == 3 ? c3[c] : (i == 2 ? c2[c] : c1[c]));
+                    accp = accp * factor + ci;
+                }
+                row[c] = y[c] + sx * accp;
+            }
+        } else if constexpr (BI) {
+            const double sx = (te - t) / h;
+#pragma unroll
+            for (int c = 0; c < N; c++) row[c] = y[c];
+#pragma unroll
+            for (int i = 0; i < I; i++) {
+                if (Tab::bi_row(i)) {
+                    double ci = Tab::biv(i, O - 1);
+#pragma unroll
+                    for (int j = O - 2; j >= 0; j--) ci = ci * sx + Tab::biv(i, j);
+                    ci = ci * sx;
+                    const double w = ci * h;
+#pragma unroll
+                    for (int c = 0; c < N; c++) row[c] = row[c] + w * kk[i][c];
+                }
+            }
+        } else {
+            const double hh = t_new - t;
+            const double sx = (te - t) / hh;
+            const double s2 = sx * sx, s3 = s2 * sx;
+            const double h00 = 2.0 * s3 - 3.0 * s2 + 1.0;
+            const double h10 = s3 - 2.0 * s2 + sx;
+            const double h01 = -2.0 * s3 + 3.0 * s2;
+            const double h11 = s3 - s2;
+            const double w10 = h10 * hh, w11 = h11 * hh;
+#pragma unroll
+            for (int c = 0; c < N; c++) {
+                double v = __dadd_rn(0.0, h00 * y[c]);
+                v = v + w10 * d0[c];
+                v = v + h01 * yn[c];
+                v = v + w11 * d1[c];
+                row[c] = v;
+            }
+        }
+    }
+};
+
+template <class Sys, class Tab>
+struct StepRecorder {
+    static constexpr int N = Sys::DIM, S = Tab::S;
+    int rows = 0;             // pushes so far (Solution.t.len())
+    bool have_last = false;   // CrossingSolout::last_offset_value
+    double last_off = 0.0;
+
+    __device__ __forceinline__ void reset() { rows = 0; have_last = false; last_off = 0.0; }
+
+    __device__ __forceinline__ void push(const OdeKernelArgs& a, long long traj, double t, const double (&y)[N]) {
+        if (rows < a.row_stride) {
+            const size_t r = (size_t)traj * a.row_stride + rows;
+            if (a.y_eval) {
+#pragma unroll
+                for (int c = 0; c < N; c++) a.y_eval[r * N + c] = y[c];
+            }
+            if (a.t_out) a.t_out[r] = t;
+        }
+        rows += 1;
+    }
+
+    __device__ __forceinline__ static double component(const double (&y)[N], int idx) {
+        double v = y[0];
+#pragma unroll
+        for (int c = 1; c < N; c++) v = (c == idx) ? y[c] : v;
+        return v;
+    }
+
+    // the solout call that precedes the loop (solve_ivp.rs:160): t_prev == t_curr == t0
+    __device__ __forceinline__ void first(const OdeKernelArgs& a, long long traj, double t0, const double (&y0)[N]) {
+        if (a.rec_mode == REC_CROSSING) {
+            last_off = component(y0, a.cross_component) - a.cross_threshold;
+            have_last = true;
+        } else {
+            push(a, traj, t0, y0);  // Default: always; Dense: t_prev == t_curr, only the point itself
+        }
+    }
+
+    // find_crossing_newton, crossing.rs:185-263
+    __device__ __forceinline__ bool newton(const OdeKernelArgs& a, const DenseStep<Sys, Tab>& ds, double t_lower, double t_upper,
+                                           double off_lower, double off_upper, double* t_out) const {
+        double t = t_lower - off_lower * (t_upper - t_lower) / (off_upper - off_lower);
+        const double tolerance = DBL_EPSILON * 100.0;
+        double row[N];
+        double off;
+        for (int it = 0; it < 10; it++) {
+            ds.eval(t, row);
+            off = component(row, a.cross_component) - a.cross_threshold;
+            if (fabs(off) < tolerance) { *t_out = t; return true; }
+            const double delta_t = (t_upper - t_lower) * 1e-6;
+            const double t_plus = t + delta_t;
+            ds.eval(t_plus, row);
+            const double off_plus = component(row, a.cross_component) - a.cross_threshold;
+            const double derivative = (off_plus - off) / delta_t;
+            if (fabs(derivative) < DBL_EPSILON * 10.0) break;
+            const double t_next = t - off / derivative;
+            if (t_next < t_lower || t_next > t_upper) {
+                t = (t_lower + t_upper) / 2.0;
+            } else {
+                const double change = fabs(t_next - t);
+                if (change < tolerance * 0.1) { t = t_next; break; }
+                t = t_next;
+            }
+        }
+        ds.eval(t, row);
+        off = component(row, a.cross_component) - a.cross_threshold;
+        *t_out = t;
+        return fabs(off) < tolerance * 10.0;
+    }
+
+    // solout after an accepted step from (t, y) to (t + h, yn); k[0] = f(t, y), dydt = f(t + h, yn)
+    __device__ __forceinline__ void step(const OdeKernelArgs& a, long long traj, double t, double h, const double (&y)[N],
+                                         const double (&yn)[N], const double (&k)[S][N], const double (&dydt)[N], const double* p) {
+        const double t_new = t + h;
+        if (a.rec_mode == REC_DEFAULT) {
+            push(a, traj, t_new, yn);
+        } else if (a.rec_mode == REC_DENSE) {
+            if (t != t_new && a.dense_n > 1) {
+                DenseStep<Sys, Tab> ds;
+                ds.prepare(t, h, y, yn, k, dydt, p);
+                for (int i = 1; i < a.dense_n; i++) {
+                    const double h_old = t_new - t;
+                    const double ti = t + (double)i * h_old / (double)a.dense_n;
+                    double row[N];
+                    ds.eval(ti, row);
+                    push(a, traj, ti, row);
+                }
+            }
+            push(a, traj, t_new, yn);
+        } else {  // REC_CROSSING
+            const double off = component(yn, a.cross_component) - a.cross_threshold;
+            if (have_last) {
+                const bool is_crossing = d_signum(last_off) != d_signum(off);  // NaN != anything
+                if (is_crossing) {
+                    const bool record = (a.cross_direction > 0) ? (last_off < 0.0 && off >= 0.0)
+                                      : (a.cross_direction < 0) ? (last_off > 0.0 && off <= 0.0) : true;
+                    if (record) {
+                        DenseStep<Sys, Tab> ds;
+                        ds.prepare(t, h, y, yn, k, dydt, p);
+                        double t_cross;
+                        if (!newton(a, ds, t, t_new, last_off, off, &t_cross)) {
+                            const double frac = -last_off / (off - last_off);
+                            t_cross = t + frac * (t_new - t);
+                        }
+                        double row[N];
+                        ds.eval(t_cross, row);
+                        push(a, traj, t_cross, row);
+                    }
+                }
+            }
+            last_off = off;
+            have_last = true;
+        }
+    }
+};
+
+}  // namespace deb

@@ -18,7 +18,7 @@ use differential_equations::{
 };
 
 // ------------------------------------------------------------------------------------------------ raw ABI
-pub const DEB_ABI_VERSION: i32 = 4;
+pub const DEB_ABI_VERSION: i32 = 5;
 
 #[repr(C)]
 #[derive(Clone, Copy)]
@@ -56,9 +56,12 @@ pub struct deb_ode_problem {
     pub device: i32,
     pub memspace: i32,
     pub stream: *mut c_void,
-    pub solout: i32, // 0 = t_eval, 1 = even(dt)
-    pub reserved0: i32,
+    pub solout: i32, // 0 = t_eval, 1 = even(dt), 2 = every step (DefaultSolout), 3 = dense(n), 4 = crossing
+    pub dense_n: i32,
     pub even_dt: f64,
+    pub cross_component: i32,
+    pub cross_direction: i32, // 0 Both, +1 Positive, -1 Negative
+    pub cross_threshold: f64,
 }
 
 #[repr(C)]
@@ -76,6 +79,7 @@ pub struct deb_result {
     pub n_rows: i32,
     pub kernel_ms: f32,
     pub total_ms: f32,
+    pub t_out: *mut f64, // [n_traj][n_eval] row times of the per-step recorders, or null
 }
 
 extern "C" {
@@ -87,7 +91,7 @@ extern "C" {
     /// user-defined right-hand side as CUDA C++ text (the device-side `impl ODE`); returns a system id >= 1000
     pub fn deb_define_ode(dim: i32, n_params: i32, diff_body: *const c_char, system_id: *mut i32) -> i32;
     /// compile it for a method now (no device needed); the compiler log is in deb_last_error()
-    pub fn deb_check_ode(system_id: i32, method: i32) -> i32;
+    pub fn deb_check_ode(system_id: i32, method: i32, solout: i32) -> i32;
     // deb_solve_sde, deb_solve_heat_mol, deb_heat_rhs, deb_ensemble_stats, deb_malloc, ... : see deb_ensemble.h
 }
 
@@ -225,8 +229,11 @@ impl<const N: usize> EnsembleIVP<N> {
             memspace: 0, // DEB_MEM_HOST
             stream: std::ptr::null_mut(),
             solout: 0,
-            reserved0: 0,
+            dense_n: 0,
             even_dt: 0.0,
+            cross_component: 0,
+            cross_direction: 0,
+            cross_threshold: 0.0,
         };
         let mut result = deb_result {
             struct_size: std::mem::size_of::<deb_result>(),
@@ -242,6 +249,7 @@ impl<const N: usize> EnsembleIVP<N> {
             n_rows: 0,
             kernel_ms: 0.0,
             total_ms: 0.0,
+            t_out: std::ptr::null_mut(),
         };
         let rc = unsafe { deb_solve_ode(&problem, &mut result) };
         if rc != 0 {

@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define DEB_ABI_VERSION 4
+#define DEB_ABI_VERSION 5
 #define DEB_MAX_DIM 16 /* widest state the register-resident kernels are instantiated for */
 
 typedef enum deb_error {
@@ -119,8 +119,12 @@ typedef enum deb_memspace { DEB_MEM_HOST = 0, DEB_MEM_DEVICE = 1 } deb_memspace;
 /* Output recorder (`Solout`, src/solout/): which rows go to y_eval. */
 typedef enum deb_solout {
     DEB_SOLOUT_T_EVAL = 0, /* IVP::t_eval(points): TEvalSolout, src/solout/t_eval.rs:87-171 */
-    DEB_SOLOUT_EVEN = 1    /* IVP::even(dt): EvenSolout, src/solout/even.rs:69-199 -- t0, t0+dt, t0+2dt, ... (accumulated),
+    DEB_SOLOUT_EVEN = 1,   /* IVP::even(dt): EvenSolout, src/solout/even.rs:69-199 -- t0, t0+dt, t0+2dt, ... (accumulated),
                               every point interpolated, plus the exact final state when a step lands on tf */
+    /* per-step recorders: rows carry their own times (deb_result.t_out), n_eval is the row capacity per trajectory */
+    DEB_SOLOUT_DEFAULT = 2,  /* the recorder of a plain IVP::solve(): every accepted step, src/solout/default.rs:54-75 */
+    DEB_SOLOUT_DENSE = 3,    /* IVP::dense(n): DenseSolout, src/solout/dense.rs:74-108 */
+    DEB_SOLOUT_CROSSING = 4  /* IVP::crossing(component, threshold, direction): CrossingSolout, src/solout/crossing.rs:115-263 */
 } deb_solout;
 
 /* Options of ExplicitRungeKutta (src/methods/erk/mod.rs:135-144 defaults, :164-228 setters). */
@@ -158,10 +162,14 @@ typedef struct deb_ode_problem {
     int32_t memspace;     /* deb_memspace for y0, params and every result pointer */
     void* stream;         /* cudaStream_t when memspace == DEB_MEM_DEVICE (NULL = default stream) */
     int32_t solout;       /* deb_solout; 0 = t_eval */
-    int32_t reserved0;
+    int32_t dense_n;      /* DEB_SOLOUT_DENSE: DenseSolout::new(n), n-1 interpolated points per step + the step end */
     double even_dt;       /* DEB_SOLOUT_EVEN: the spacing dt > 0.  t_eval is ignored; n_eval is the row capacity of y_eval per
                              trajectory and must be at least floor(|tf-t0|/dt) + 2.  t_rows receives t0 + k*dt; a trajectory
                              whose t_final == tf has its last row at tf (even.rs:166-188) */
+    /* DEB_SOLOUT_CROSSING: CrossingSolout::new(component, threshold).with_direction(d) (src/solout/crossing.rs) */
+    int32_t cross_component;
+    int32_t cross_direction; /* 0 = Both, +1 = Positive (below -> above), -1 = Negative */
+    double cross_threshold;
 } deb_ode_problem;
 
 typedef struct deb_sde_problem {
@@ -209,6 +217,11 @@ typedef struct deb_result {
     int32_t n_rows;
     float kernel_ms;       /* device time of the integration kernel(s), DEB_MEM_HOST calls only */
     float total_ms;        /* H2D + kernel + D2H, DEB_MEM_HOST calls only */
+    /* Per-step recorders (DEB_SOLOUT_DEFAULT / DENSE / CROSSING): the row times depend on the trajectory.
+     * t_out[i][r] is the time of row r of trajectory i (Solution.t), in `memspace` like y_eval; n_eval is the row
+     * capacity per trajectory; n_emitted[i] counts every row the reference would have pushed -- rows beyond the
+     * capacity are counted but not stored.  n_rows is 0 for these recorders.  May be NULL. */
+    double* t_out;         /* [n_traj][n_eval] */
 } deb_result;
 
 /* Method-of-lines heat equation u_t = (alpha u_x)_x on a uniform 1-D grid, second-order finite differences,
@@ -249,9 +262,11 @@ void deb_erk_options_default(deb_erk_options* opt);
  * serve the built-in systems, and cached.  Returns a system id (>= 1000) to put in deb_ode_problem.system.
  * A body that does not compile makes the first deb_solve_ode return DEB_ERR_BAD_ARG with the compiler log. */
 int deb_define_ode(int32_t dim, int32_t n_params, const char* diff_body, int32_t* system_id);
-/* Compile a user-defined system for `method` now, without a device and without running anything: DEB_OK, or
- * DEB_ERR_BAD_ARG with the compiler log in deb_last_error().  (What a Rust caller gets from `cargo check`.) */
-int deb_check_ode(int32_t system_id, int32_t method);
+/* Compile the kernel for (system, method, recorder) now, without a device and without running anything: DEB_OK, or
+ * an error with the compiler log in deb_last_error() (DEB_ERR_BAD_ARG for a user-defined right-hand side that does not
+ * compile: what a Rust caller gets from `cargo check`).  Kernels that were compiled ahead of time (built-in system with
+ * a t_eval / even(dt) recorder) return DEB_OK at once. */
+int deb_check_ode(int32_t system_id, int32_t method, int32_t solout);
 
 int deb_solve_ode(const deb_ode_problem* problem, deb_result* result);
 int deb_solve_sde(const deb_sde_problem* problem, deb_result* result);

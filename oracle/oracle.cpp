@@ -554,7 +554,90 @@ struct TEval {
 struct Out {  // per-trajectory output slots
     double* y_eval; int32_t* n_emitted; double* t_final; double* y_final;
     int32_t* status; int32_t* accepted; int32_t* rejected; int32_t* evals;
+    double* t_out = nullptr;
 };
+
+// Per-step recorders: DefaultSolout (src/solout/default.rs:54-75), DenseSolout (src/solout/dense.rs:74-108),
+// CrossingSolout (src/solout/crossing.rs:115-263).  Rows carry their own time; `cap` row slots per trajectory, pushes
+// beyond that are counted only.  Where the reference's interpolate() would return Err(OutOfBounds) and the recorder
+// would panic on unwrap (backward time; the Newton probe just past the step end) the polynomial is evaluated.
+struct PerStep {
+    int mode = 0, dense_n = 0, comp = 0, direction = 0, cap = 0;
+    double threshold = 0.0;
+    bool have_last = false;
+    double last_off = 0.0;
+};
+template <class Interp>
+bool crossing_newton(const PerStep& ps, Interp&& interp, double t_lower, double t_upper, double off_lower, double off_upper, double* t_found) {
+    double t = t_lower - off_lower * (t_upper - t_lower) / (off_upper - off_lower);
+    const double tolerance = DBL_EPSILON * 100.0;
+    double off;
+    for (int it = 0; it < 10; it++) {
+        Vec y_t = interp(t);
+        off = y_t[ps.comp] - ps.threshold;
+        if (std::fabs(off) < tolerance) { *t_found = t; return true; }
+        const double delta_t = (t_upper - t_lower) * 1e-6;
+        const double t_plus = t + delta_t;
+        Vec y_plus = interp(t_plus);
+        const double off_plus = y_plus[ps.comp] - ps.threshold;
+        const double derivative = (off_plus - off) / delta_t;
+        if (std::fabs(derivative) < DBL_EPSILON * 10.0) break;
+        const double t_new = t - off / derivative;
+        if (t_new < t_lower || t_new > t_upper) {
+            t = (t_lower + t_upper) / 2.0;
+        } else {
+            const double change = std::fabs(t_new - t);
+            if (change < tolerance * 0.1) { t = t_new; break; }
+            t = t_new;
+        }
+    }
+    Vec y_t = interp(t);
+    off = y_t[ps.comp] - ps.threshold;
+    *t_found = t;
+    return std::fabs(off) < tolerance * 10.0;
+}
+template <class Interp>
+void solout_per_step(PerStep& ps, double t_curr, double t_prev, const Vec& y_curr, Interp&& interp, double* y_eval, double* t_out,
+                     int n, int* n_emit) {
+    auto push = [&](double t, const Vec& v) {
+        if (*n_emit < ps.cap) {
+            if (y_eval) std::memcpy(y_eval + (size_t)(*n_emit) * n, v.data(), sizeof(double) * n);
+            if (t_out) t_out[*n_emit] = t;
+        }
+        *n_emit += 1;
+    };
+    if (ps.mode == DEB_SOLOUT_DEFAULT) {
+        push(t_curr, y_curr);
+    } else if (ps.mode == DEB_SOLOUT_DENSE) {
+        if (t_prev != t_curr) {
+            for (int i = 1; i < ps.dense_n; i++) {
+                const double h_old = t_curr - t_prev;
+                const double ti = t_prev + (double)i * h_old / (double)ps.dense_n;
+                push(ti, interp(ti));
+            }
+        }
+        push(t_curr, y_curr);
+    } else {  // crossing
+        const double off = y_curr[ps.comp] - ps.threshold;
+        if (ps.have_last) {
+            const double last = ps.last_off;
+            const bool is_crossing = signum(last) != signum(off);
+            if (is_crossing) {
+                const bool record = ps.direction > 0 ? (last < 0.0 && off >= 0.0) : ps.direction < 0 ? (last > 0.0 && off <= 0.0) : true;
+                if (record) {
+                    double t_cross;
+                    if (!crossing_newton(ps, interp, t_prev, t_curr, last, off, &t_cross)) {
+                        const double frac = -last / (off - last);
+                        t_cross = t_prev + frac * (t_curr - t_prev);
+                    }
+                    push(t_cross, interp(t_cross));
+                }
+            }
+        }
+        ps.last_off = off;
+        ps.have_last = true;
+    }
+}
 
 template <class Interp>
 void solout_teval(TEval& te, double t_curr, double t_prev, const Vec& y_curr, Interp&& interp, double* y_eval, int n, int* n_emit) {
@@ -660,12 +743,19 @@ void solve_one(const deb_ode_problem* P, const SysInfo& si, const Tableau& tb, i
     bool ok = tb.dp ? m.dp_init(ode, t0, tf, y0, &evals) : tb.adaptive ? m.ad_init(ode, t0, tf, y0, &evals) : m.fx_init(ode, t0, tf, y0, &evals);
     if (!ok) { evals = 0; finish(DEB_STATUS_BAD_INPUT, t0, y0); return; }
     const bool even = (P->solout == DEB_SOLOUT_EVEN);
-    TEval te(even ? nullptr : P->t_eval, even ? 0 : P->n_eval, t0, tf);
+    const bool no_points = even || P->solout == DEB_SOLOUT_DEFAULT || P->solout == DEB_SOLOUT_DENSE || P->solout == DEB_SOLOUT_CROSSING;
+    TEval te(no_points ? nullptr : P->t_eval, no_points ? 0 : P->n_eval, t0, tf);
     Even ev(P->even_dt, t0, tf);
     // adaptive family without bi: cubic Hermite on (t_prev, t, y_prev, y, dydt_prev, dydt), adaptive/ordinary.rs:282-295
     auto interp = [&](double tv) { return tb.dp ? m.dp_interpolate(tv) : (tb.adaptive && tb.bi) ? m.ad_interpolate(tv) : m.fx_interpolate(tv); };
+    PerStep ps;
+    ps.mode = P->solout; ps.dense_n = P->dense_n; ps.comp = P->cross_component; ps.direction = P->cross_direction;
+    ps.threshold = P->cross_threshold; ps.cap = P->n_eval;
+    const bool per_step = (P->solout == DEB_SOLOUT_DEFAULT || P->solout == DEB_SOLOUT_DENSE || P->solout == DEB_SOLOUT_CROSSING);
+    double* to = o.t_out ? o.t_out + (size_t)i * P->n_eval : nullptr;
     auto record = [&]() {
-        if (even) solout_even(ev, m.t, m.t_prev, m.y, m.y_prev, interp, ye, n, &n_emit);
+        if (per_step) solout_per_step(ps, m.t, m.t_prev, m.y, interp, ye, to, n, &n_emit);
+        else if (even) solout_even(ev, m.t, m.t_prev, m.y, m.y_prev, interp, ye, n, &n_emit);
         else solout_teval(te, m.t, m.t_prev, m.y, interp, ye, n, &n_emit);
     };
     record();  // :160
@@ -846,7 +936,7 @@ int orc_solve_ode(const deb_ode_problem* P, deb_result* R, int n_threads) {
     if (!P || !R || !get_system(P->system, &si) || !get_tableau(P->method, &tb)) return DEB_ERR_BAD_ARG;
     if (si.dim != P->dim || si.np != P->n_params) return DEB_ERR_BAD_ARG;
     if (n_threads <= 0) n_threads = orc_hardware_threads();
-    Out o{R->y_eval, R->n_emitted, R->t_final, R->y_final, R->status, R->accepted, R->rejected, R->evals};
+    Out o{R->y_eval, R->n_emitted, R->t_final, R->y_final, R->status, R->accepted, R->rejected, R->evals, R->t_out};
     parallel_for(P->n_traj, n_threads, [&](int64_t i) { solve_one(P, si, tb, i, o); });
     // sorted t_eval bookkeeping for the caller
     return DEB_OK;

@@ -141,7 +141,64 @@ def make_even_solout(dt, t0, tf, rows, interpolate):
     return solout
 
 
-def solve_dp(f, method, t0, tf, y0, rtol=1e-6, atol=1e-6, t_eval=(), even=None, h0=0.0, h_min=0.0, h_max=math.inf, max_steps=10000,
+def make_per_step_solout(recorder, rows, interpolate):
+    """DefaultSolout (src/solout/default.rs:54-75), DenseSolout (dense.rs:74-108), CrossingSolout (crossing.rs:115-263).
+    recorder = ("default",) | ("dense", n) | ("crossing", component, threshold, direction in {0, +1, -1})."""
+    kind = recorder[0]
+    st = dict(last=None)
+    eps = 2.220446049250313e-16
+
+    def newton(comp, thr, t_lower, t_upper, off_lower, off_upper):
+        t = t_lower - off_lower * (t_upper - t_lower) / (off_upper - off_lower)
+        tolerance = eps * 100.0
+        for _ in range(10):
+            off = interpolate(t)[comp] - thr
+            if abs(off) < tolerance:
+                return t
+            delta_t = (t_upper - t_lower) * 1e-6
+            off_plus = interpolate(t + delta_t)[comp] - thr
+            derivative = (off_plus - off) / delta_t
+            if abs(derivative) < eps * 10.0:
+                break
+            t_new = t - off / derivative
+            if t_new < t_lower or t_new > t_upper:
+                t = (t_lower + t_upper) / 2.0
+            else:
+                change = abs(t_new - t)
+                t = t_new
+                if change < tolerance * 0.1:
+                    break
+        off = interpolate(t)[comp] - thr
+        return t if abs(off) < tolerance * 10.0 else None
+
+    def solout(t_curr, t_prev, y_curr):
+        if kind == "default":
+            rows.append((t_curr, list(y_curr)))
+        elif kind == "dense":
+            n = recorder[1]
+            if t_prev != t_curr:
+                for i in range(1, n):
+                    h_old = t_curr - t_prev
+                    ti = t_prev + float(i) * h_old / float(n)
+                    rows.append((ti, interpolate(ti)))
+            rows.append((t_curr, list(y_curr)))
+        else:
+            _, comp, thr, direction = recorder
+            off = y_curr[comp] - thr
+            last = st["last"]
+            if last is not None and signum(last) != signum(off):
+                record = (last < 0.0 and off >= 0.0) if direction > 0 else (last > 0.0 and off <= 0.0) if direction < 0 else True
+                if record:
+                    tc = newton(comp, thr, t_prev, t_curr, last, off)
+                    if tc is None:
+                        frac = -last / (off - last)
+                        tc = t_prev + frac * (t_curr - t_prev)
+                    rows.append((tc, interpolate(tc)))
+            st["last"] = off
+    return solout
+
+
+def solve_dp(f, method, t0, tf, y0, rtol=1e-6, atol=1e-6, t_eval=(), even=None, recorder=None, h0=0.0, h_min=0.0, h_max=math.inf, max_steps=10000,
              safety=0.9, min_scale=0.2, max_scale=10.0):
     """Returns dict(status, t, y, accepted, rejected, evals, rows=[(t, y)])."""
     T = TAB["DOPRI5" if method == "dopri5" else "DOP853"]
@@ -206,6 +263,8 @@ def solve_dp(f, method, t0, tf, y0, rtol=1e-6, atol=1e-6, t_eval=(), even=None, 
     if even is not None:
         even_solout = make_even_solout(even, t0, tf, rows, interpolate)
         solout = lambda tc, tp, yc: even_solout(tc, tp, yc, y_before)
+    if recorder is not None:
+        solout = make_per_step_solout(recorder, rows, interpolate)
     solout(t, t_prev, y)
     status = "Complete"
     while True:
@@ -332,7 +391,7 @@ def solve_dp(f, method, t0, tf, y0, rtol=1e-6, atol=1e-6, t_eval=(), even=None, 
     return dict(status=status, t=t, y=y, accepted=acc, rejected=rej, evals=evals, rows=rows)
 
 
-def solve_fixed(f, method, h0, t0, tf, y0, t_eval=(), max_steps=10000):
+def solve_fixed(f, method, h0, t0, tf, y0, t_eval=(), max_steps=10000, recorder=None):
     T = TAB[method.upper()]
     c, A, b = T["C"], T["A"], T["B"]
     S = len(b)
@@ -385,6 +444,8 @@ def solve_fixed(f, method, h0, t0, tf, y0, t_eval=(), max_steps=10000):
                 idx += 1
         state["idx"] = idx
 
+    if recorder is not None:
+        solout = make_per_step_solout(recorder, rows, interpolate)
     solout(t, t_prev, y)
     steps = 0
     status = "Complete"
@@ -448,7 +509,7 @@ ADAPTIVE_ORDER_FSAL = dict(rkf45=(5, False), cash_karp=(5, False), rkv655e=(6, T
                            rkv767e=(7, False), rkv877e=(8, False), rkv878e=(8, False), rkv988e=(9, False), rkv989e=(9, False))
 
 
-def solve_adaptive(f, method, t0, tf, y0, rtol=1e-6, atol=1e-6, t_eval=(), h0=0.0, h_min=0.0, h_max=math.inf, max_steps=10000,
+def solve_adaptive(f, method, t0, tf, y0, rtol=1e-6, atol=1e-6, t_eval=(), recorder=None, h0=0.0, h_min=0.0, h_max=math.inf, max_steps=10000,
                    max_rejects=100, safety=0.9, min_scale=0.2, max_scale=10.0):
     """Generic adaptive family (RKF45, Cash-Karp, Verner pairs): /root/reference/src/methods/erk/adaptive/ordinary.rs:16-211,
     dense output = the method's polynomial when it has one (:246-277) else cubic Hermite (:282-295), driven by
@@ -527,6 +588,8 @@ def solve_adaptive(f, method, t0, tf, y0, rtol=1e-6, atol=1e-6, t_eval=(), h0=0.
                 idx += 1
         state["idx"] = idx
 
+    if recorder is not None:
+        solout = make_per_step_solout(recorder, rows, interpolate)
     solout(t, t_prev, y)
     status = "Complete"
     while True:

@@ -127,8 +127,11 @@ def test_user_rhs_compiles_for_every_method_without_a_device(lib):
     bad = deb.ode_from_source(1, "dydt[0] = undefined_symbol * y[0];", params=[1.0])
     with pytest.raises(ValueError, match="did not compile"):
         deb.check_ode(bad, E.dopri5())
-    with pytest.raises(ValueError, match="not a user-defined"):
-        deb.check_ode(deb.LorenzSystem(10.0, 28.0, 8.0 / 3.0), E.dopri5())
+    deb.check_ode(deb.LorenzSystem(10.0, 28.0, 8.0 / 3.0), E.dopri5())  # compiled ahead of time
+    # per-step recorders are compiled at first use, for built-in and user-defined systems alike
+    for m in (E.dopri5(), E.dop853(), E.cash_karp(), E.rkv767e(), E.heun(0.01)):
+        deb.check_ode(deb.LorenzSystem(10.0, 28.0, 8.0 / 3.0), m, deb.DEB_SOLOUT_DENSE)
+    deb.check_ode(duffing, E.dopri5(), deb.DEB_SOLOUT_CROSSING)
 
 
 def test_no_cpu_fallback_without_a_device(lib):

@@ -46,8 +46,11 @@ def random_case(seed):
     tf = t0 - span if backward else t0 + span
     d = -1.0 if backward else 1.0
     adaptive = bool(r.random() < 0.7)
+    u = r.random()  # recorder kind; per-step recorders are compiled at first use, so they get a small method set
+    per_step = 0.25 <= u < 0.5
     if adaptive:
-        ctor = ADAPTIVE[int(r.integers(len(ADAPTIVE)))]
+        pool = ["dopri5", "rkf45"] if per_step else ADAPTIVE
+        ctor = pool[int(r.integers(len(pool)))]
         m = getattr(E, ctor)()
         if r.random() < 0.5:
             m.rtol(float(10.0 ** r.uniform(-10, -4))).atol(float(10.0 ** r.uniform(-11, -5)))
@@ -66,13 +69,23 @@ def random_case(seed):
         if r.random() < 0.2:
             m.max_rejects(int(r.integers(1, 6)))
     else:
-        ctor = FIXED[int(r.integers(len(FIXED)))]
+        pool = ["rk4"] if per_step else FIXED
+        ctor = pool[int(r.integers(len(pool)))]
         m = getattr(E, ctor)(d * span / float(r.integers(20, 400)) if r.random() < 0.85 else 0.0)
         if r.random() < 0.2:
             m.max_steps(int(r.integers(10, 100)))
     ivp = deb.EnsembleIVP.ode(sysm, t0, tf, y0)
-    if r.random() < 0.3:
+    if u < 0.25:
         ivp.even(span / float(r.uniform(2.5, 40.0)))
+    elif u < 0.5:  # per-step recorders (capacity sometimes too small on purpose)
+        cap = int(r.integers(5, 600))
+        which = int(r.integers(3))
+        if which == 0:
+            ivp.every_step(cap)
+        elif which == 1:
+            ivp.dense(int(r.integers(0, 5)), cap)
+        else:
+            ivp.crossing(int(r.integers(dim)), float(np.median(y0[:, 0]) + r.uniform(-0.5, 0.5)), int(r.integers(-1, 2)), int(r.integers(1, 40)))
     else:
         k = int(r.integers(0, 12))
         pts = r.uniform(min(t0, tf) - 0.2 * span, max(t0, tf) + 0.2 * span, k).tolist()
@@ -98,3 +111,6 @@ def test_random_problem_descriptions_bitwise(block):
         assert np.array_equal(bits(g.y_final[fin]), bits(c.y_final[fin])), label
         m = (np.arange(g.y_eval.shape[1])[None, :] < g.n_emitted[:, None]) & fin[:, None]
         assert np.array_equal(bits(g.y_eval)[m], bits(c.y_eval)[m]), label
+        assert (g.t_out is None) == (c.t_out is None), label
+        if g.t_out is not None:
+            assert np.array_equal(bits(g.t_out)[m], bits(c.t_out)[m]), label

@@ -240,6 +240,38 @@ def test_verner_restatements_agree_bitwise():
         np.testing.assert_allclose(ev.y[:, 0], np.cos(ev.t), atol=1e-6)
 
 
+def test_per_step_recorder_restatements_agree_bitwise():
+    """DefaultSolout / DenseSolout / CrossingSolout (src/solout/default.rs, dense.rs, crossing.rs): C++ oracle vs the
+    independent Python restatement, bit for bit (row times and states), for every kernel family; and the documented
+    shapes (every step; n rows per step; rows on the threshold)."""
+    lz = pr.lorenz(10.0, 28.0, 8.0 / 3.0)
+    recs = ((("default",), lambda ivp: ivp.every_step(600)), (("dense", 3), lambda ivp: ivp.dense(3, 1800)),
+            (("dense", 1), lambda ivp: ivp.dense(1, 600)), (("crossing", 0, 0.5, 0), lambda ivp: ivp.crossing(0, 0.5, 0, 64)),
+            (("crossing", 2, 20.0, 1), lambda ivp: ivp.crossing(2, 20.0, 1, 64)), (("crossing", 1, -1.0, -1), lambda ivp: ivp.crossing(1, -1.0, -1, 64)))
+    for rec, setter in recs:
+        for meth in ("dopri5", "dop853", "rkf45", "rkv655e", "rkv878e", "rk4"):
+            if meth in ("dopri5", "dop853"):
+                p, m = pr.solve_dp(lz, meth, 0.0, 8.0, [1.0, 1.0, 1.0], rtol=1e-7, atol=1e-8, recorder=rec), getattr(E, meth)().rtol(1e-7).atol(1e-8)
+            elif meth == "rk4":
+                p, m = pr.solve_fixed(lz, "rk4", 0.02, 0.0, 8.0, [1.0, 1.0, 1.0], recorder=rec), E.rk4(0.02)
+            else:
+                p, m = pr.solve_adaptive(lz, meth, 0.0, 8.0, [1.0, 1.0, 1.0], rtol=1e-7, atol=1e-8, recorder=rec), getattr(E, meth)().rtol(1e-7).atol(1e-8)
+            c = ob.oracle_solve(setter(deb.EnsembleIVP.ode(deb.LorenzSystem(10.0, 28.0, 8.0 / 3.0), 0.0, 8.0, [[1.0, 1.0, 1.0]])).method(m))
+            sol = c[0]
+            assert len(p["rows"]) == len(sol.t) and p["evals"] == c.evals[0]
+            assert _same_bits([r[0] for r in p["rows"]], sol.t) and _same_bits([r[1] for r in p["rows"]], sol.y)
+            if rec[0] == "default":
+                assert len(sol.t) == c.accepted[0] + 1 and sol.t[0] == 0.0 and sol.t[-1] == 8.0
+            if rec == ("dense", 3):
+                assert len(sol.t) == 3 * c.accepted[0] + 1
+    # crossings of cos(t) through 0 (examples/ode/08 pattern): pi/2 + k pi; direction filter
+    for d, want in ((0, [0.5, 1.5, 2.5]), (1, [1.5]), (-1, [0.5, 2.5])):
+        sol = ob.oracle_solve(deb.EnsembleIVP.ode(deb.HarmonicOscillator(1.0), 0.0, 10.0, [[1.0, 0.0]]).crossing(0, 0.0, d, 16)
+                              .method(E.dopri5().rtol(1e-10).atol(1e-10)))[0]
+        np.testing.assert_allclose(sol.t / np.pi, want, atol=1e-8)
+        assert np.abs(sol.y[:, 0]).max() < 1e-12
+
+
 def test_even_solout_restatements_agree_bitwise():
     """EvenSolout (src/solout/even.rs:69-199): C++ oracle vs the independent Python restatement, bit for bit; and the
     documented output shape (t0 first, tf last, spacing dt)."""

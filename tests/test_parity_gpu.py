@@ -7,6 +7,8 @@ Fixed-step RK4 and SDE paths: 1e-12 relative (asserted bitwise where the arithme
 """
 import importlib
 
+import math
+
 import numpy as np
 import pytest
 
@@ -34,6 +36,9 @@ def assert_same_solution(gpu, cpu, exact=True, rtol=0.0):
     assert np.array_equal(gpu.n_emitted, cpu.n_emitted), "number of emitted t_eval rows differs"
     assert np.array_equal(gpu.t_rows, cpu.t_rows)
     mask = np.arange(gpu.y_eval.shape[1])[None, :] < gpu.n_emitted[:, None]
+    assert (gpu.t_out is None) == (cpu.t_out is None)
+    if gpu.t_out is not None:
+        assert np.array_equal(bits(gpu.t_out)[mask], bits(cpu.t_out)[mask]), "row times differ bitwise"
     if exact:
         assert np.array_equal(bits(gpu.t_final), bits(cpu.t_final)), "t_final differs bitwise"
         assert np.array_equal(bits(gpu.y_final), bits(cpu.y_final)), "y_final differs bitwise"
@@ -550,6 +555,84 @@ def test_verner_user_defined_rhs_bitwise():
             return deb.EnsembleIVP.ode(sysm, 0.0, 3.0, y0).t_eval([0.7, 1.9, 3.0]).method(getattr(E, ctor)().rtol(1e-8))
         g, b = prob(usr).solve(), prob(lorenz()).solve()
         assert_same_solution(g, b)
+
+
+# ------------------------------------------------------------------------------------------ per-step recorders
+RECORDERS = {"every_step": lambda ivp, cap: ivp.every_step(cap), "dense3": lambda ivp, cap: ivp.dense(3, 3 * cap),
+             "dense1": lambda ivp, cap: ivp.dense(1, cap), "cross_x_both": lambda ivp, cap: ivp.crossing(0, 0.5, deb.CROSSING_BOTH, 64),
+             "cross_z_up": lambda ivp, cap: ivp.crossing(2, 25.0, deb.CROSSING_POSITIVE, 64),
+             "cross_y_down": lambda ivp, cap: ivp.crossing(1, -2.0, deb.CROSSING_NEGATIVE, 64)}
+
+
+@pytest.mark.parametrize("rec", sorted(RECORDERS))
+@pytest.mark.parametrize("meth", ["dopri5", "dop853", "cash_karp", "rkv655e", "rkv878e", "rk4"])
+def test_per_step_recorders_bit_exact(meth, rec):
+    """DefaultSolout / DenseSolout / CrossingSolout (src/solout/default.rs, dense.rs, crossing.rs): rows with their own
+    times, Newton-refined crossings on each method's own dense output; kernels compiled at first use."""
+    y0 = ob.lorenz_ensemble_y0(300, seed=61)
+    def prob():
+        m = E.rk4(0.01) if meth == "rk4" else getattr(E, meth)().rtol(1e-7).atol(1e-8)
+        return RECORDERS[rec](deb.EnsembleIVP.ode(lorenz(), 0.0, 6.0, y0), 700).method(m)
+    g, c = prob().solve(), ob.oracle_solve(prob())
+    assert_same_solution(g, c)
+    assert (g.status == 0).all()
+    s = g[17]
+    assert len(s.t) == g.n_emitted[17] and (np.diff(s.t) > 0).all()
+    if rec == "every_step":
+        assert np.array_equal(g.n_emitted, g.accepted + 1) and s.t[0] == 0.0 and s.t[-1] == 6.0
+    if rec == "dense3":
+        assert np.array_equal(g.n_emitted, 3 * g.accepted + 1)
+    if rec == "cross_z_up":
+        # Newton-refined rows sit on the threshold; rows where the reference's iteration gives up use its linear fallback
+        assert len(s.t) >= 2
+        if meth == "dopri5":
+            assert np.median(np.abs(s.y[:, 2] - 25.0)) < 1e-9
+
+
+def test_per_step_recorders_capacity_backward_and_failures():
+    """Row capacity smaller than the number of rows (counted, not stored), backward time, trajectories that fail mid-way."""
+    y0 = np.tile([1.0, 0.0], (64, 1)) * np.linspace(0.5, 2.0, 64)[:, None]
+    def p1():  # capacity overflow
+        return deb.EnsembleIVP.ode(deb.HarmonicOscillator(1.0), 0.0, 20.0, y0).every_step(10).method(E.dopri5().rtol(1e-8))
+    g, c = p1().solve(), ob.oracle_solve(p1())
+    assert np.array_equal(g.n_emitted, c.n_emitted) and (g.n_emitted > 10).all()
+    assert np.array_equal(bits(g.y_eval), bits(c.y_eval)) and np.array_equal(bits(g.t_out), bits(c.t_out))
+    with pytest.raises(ValueError, match="row capacity"):
+        g[0]
+    for setter in (lambda ivp: ivp.every_step(400), lambda ivp: ivp.dense(4, 1600), lambda ivp: ivp.crossing(0, 0.1, deb.CROSSING_BOTH, 16)):
+        for m in (lambda: E.dopri5().rtol(1e-9), lambda: E.dop853().rtol(1e-9), lambda: E.rkf45().rtol(1e-8), lambda: E.rkv766e().rtol(1e-9),
+                  lambda: E.rk4(-0.05)):
+            def p2():  # backward
+                return setter(deb.EnsembleIVP.ode(deb.HarmonicOscillator(1.0), 10.0, 0.0, y0)).method(m())
+            g, c = p2().solve(), ob.oracle_solve(p2())
+            assert_same_solution(g, c)
+            assert (g.status == 0).all()
+    def p3():  # MaxSteps: rows up to the failure
+        return deb.EnsembleIVP.ode(lorenz(), 0.0, 50.0, ob.lorenz_ensemble_y0(96, seed=62)).dense(2, 400).method(E.dopri5().rtol(1e-9).max_steps(150))
+    g, c = p3().solve(), ob.oracle_solve(p3())
+    assert_same_solution(g, c)
+    assert (g.status == deb.DEB_STATUS_MAX_STEPS).all()
+
+
+def test_crossing_example_08_damped_oscillator_user_rhs():
+    """examples/ode/08_damped_oscillator: x'' = -b x' - k x as a user-defined right-hand side, zero crossings of x with
+    dopri5().rtol(1e-8).atol(1e-8): against the independent Python restatement (bitwise) and the closed form."""
+    import py_restatement as pr
+    osc = deb.ode_from_source(2, "dydt[0] = y[1]; dydt[1] = -p[0] * y[1] - p[1] * y[0];", params=[0.5, 1.0])
+    g = (deb.EnsembleIVP.ode(osc, 0.0, 20.0, [[1.0, 0.0]]).crossing(0, 0.0, deb.CROSSING_BOTH, 32)
+         .method(E.dopri5().rtol(1e-8).atol(1e-8)).solve())
+    f = lambda t, y: [y[1], -0.5 * y[1] - 1.0 * y[0]]
+    p = pr.solve_dp(f, "dopri5", 0.0, 20.0, [1.0, 0.0], rtol=1e-8, atol=1e-8, recorder=("crossing", 0, 0.0, 0))
+    s = g[0]
+    assert (int(g.accepted[0]), int(g.rejected[0]), int(g.evals[0])) == (p["accepted"], p["rejected"], p["evals"])
+    assert np.array_equal(bits(s.t), bits([r[0] for r in p["rows"]])) and np.array_equal(bits(s.y), bits([r[1] for r in p["rows"]]))
+    # x(t) = e^{-t/4} (cos wt + sin wt / (4w)), w = sqrt(15)/4: zeros at wt = atan(-4w) + k pi
+    w = math.sqrt(15.0) / 4.0
+    zeros = [(math.atan(-4.0 * w) + k * math.pi) / w for k in range(1, 8)]
+    zeros = [z for z in zeros if z < 20.0]
+    assert len(s.t) == len(zeros)
+    np.testing.assert_allclose(s.t, zeros, atol=1e-5)
+    assert np.abs(s.y[:, 0]).max() < 1e-9
 
 
 # ------------------------------------------------------------------------------------------ EvenSolout (SURVEY 8f rank 1)
