@@ -50,8 +50,11 @@ DEB_STATUS_COMPLETE, DEB_STATUS_MAX_STEPS, DEB_STATUS_STEP_SIZE, DEB_STATUS_STIF
 DEB_MEM_HOST, DEB_MEM_DEVICE = 0, 1
 DEB_SOLOUT_T_EVAL, DEB_SOLOUT_EVEN, DEB_SOLOUT_DEFAULT, DEB_SOLOUT_DENSE, DEB_SOLOUT_CROSSING = 0, 1, 2, 3, 4
 CROSSING_BOTH, CROSSING_POSITIVE, CROSSING_NEGATIVE = 0, 1, -1  # CrossingDirection, src/solout/mod.rs
+DEB_EVENT_NONE, DEB_EVENT_LINEAR = 0, 1
+DEB_MAX_DIM = 16
+DEB_STATUS_INTERRUPTED = 5
 DEB_OK, DEB_ERR_BAD_ARG, DEB_ERR_NO_DEVICE, DEB_ERR_CUDA, DEB_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
-DEB_ABI_VERSION = 5
+DEB_ABI_VERSION = 6
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -69,7 +72,9 @@ class OdeProblem(C.Structure):
                 ("params_shared", C.c_int32), ("n_eval", C.c_int32), ("t_eval", _dp), ("t0", C.c_double), ("tf", C.c_double),
                 ("opt", ErkOptions), ("device", C.c_int32), ("memspace", C.c_int32), ("stream", C.c_void_p),
                 ("solout", C.c_int32), ("dense_n", C.c_int32), ("even_dt", C.c_double),
-                ("cross_component", C.c_int32), ("cross_direction", C.c_int32), ("cross_threshold", C.c_double)]
+                ("cross_component", C.c_int32), ("cross_direction", C.c_int32), ("cross_threshold", C.c_double),
+                ("event", C.c_int32), ("event_direction", C.c_int32), ("event_terminate", C.c_int32), ("row_capacity", C.c_int32),
+                ("event_coef", C.c_double * (DEB_MAX_DIM + 2))]
 
 
 class SdeProblem(C.Structure):
@@ -97,7 +102,7 @@ class HeatProblem(C.Structure):
 
 
 # every symbol include/deb_ensemble.h declares (tests check that the library exports all of them)
-ABI_SYMBOLS = ["deb_abi_version", "deb_last_error", "deb_device_count", "deb_erk_options_default", "deb_define_ode", "deb_check_ode", "deb_solve_ode",
+ABI_SYMBOLS = ["deb_abi_version", "deb_last_error", "deb_device_count", "deb_erk_options_default", "deb_define_ode", "deb_define_event", "deb_check_ode", "deb_solve_ode",
                "deb_solve_sde", "deb_solve_heat_mol", "deb_heat_rhs", "deb_ensemble_stats", "deb_malloc", "deb_free", "deb_memcpy_h2d",
                "deb_memcpy_d2h", "deb_synchronize", "deb_pow_device", "deb_fp64_issue_peak"]
 
@@ -123,7 +128,8 @@ def load_library() -> C.CDLL:
     lib.deb_solve_sde.argtypes = [C.POINTER(SdeProblem), C.POINTER(Result)]
     lib.deb_solve_heat_mol.argtypes = [C.POINTER(HeatProblem)]
     lib.deb_define_ode.argtypes = [C.c_int32, C.c_int32, C.c_char_p, _ip]
-    lib.deb_check_ode.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+    lib.deb_check_ode.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+    lib.deb_define_event.argtypes = [C.c_int32, C.c_char_p, _ip]
     lib.deb_heat_rhs.argtypes = [C.POINTER(HeatProblem), C.c_void_p, C.c_void_p]
     lib.deb_erk_options_default.argtypes = [C.POINTER(ErkOptions)]
     lib.deb_erk_options_default.restype = None
@@ -232,12 +238,34 @@ def ode_from_source(dim: int, diff_body: str, params=(), lib=None) -> OdeSystem:
     return OdeSystem(sid.value, int(dim), prm)
 
 
-def check_ode(system: OdeSystem, method, solout: int = DEB_SOLOUT_T_EVAL, lib=None) -> None:
-    """Compile the kernel for (system, method, recorder) now (NVRTC, no GPU needed); raises ValueError with the compiler
-    log when a user-defined right-hand side does not compile."""
+def check_ode(system: OdeSystem, method, solout: int = DEB_SOLOUT_T_EVAL, event=None, lib=None) -> None:
+    """Compile the kernel for (system, method, recorder, event) now (NVRTC, no GPU needed); raises ValueError with the
+    compiler log when a user-defined right-hand side or event function does not compile."""
     lib = lib or load_library()
     mid = method.method_id if hasattr(method, "method_id") else int(method)
-    _check(lib, lib.deb_check_ode(int(system.system_id), mid, int(solout)), "deb_check_ode")
+    eid = 0 if event is None else event.event_id
+    _check(lib, lib.deb_check_ode(int(system.system_id), mid, int(solout), int(eid)), "deb_check_ode")
+
+
+@dataclass
+class EventSpec:
+    """Mirror of an `impl Event` (src/solout/event.rs:60-70): the function g(t, y) whose zero crossings are located."""
+    event_id: int
+    coef: tuple = ()
+
+
+def LinearEvent(c0: float, ct: float, cy: Sequence[float]) -> EventSpec:
+    """g(t, y) = c0 + ct*t + sum_i cy[i]*y[i], accumulated in that order (`y[0] - 0.9*m` is LinearEvent(-0.9*m, 0, [1]))."""
+    return EventSpec(DEB_EVENT_LINEAR, (float(c0), float(ct)) + tuple(float(v) for v in cy))
+
+
+def event_from_source(dim: int, event_body: str, lib=None) -> EventSpec:
+    """`impl Event { fn event(&self, t, y) -> T }` for the device: the body of
+    `double event(double t, const double* y, const double* p)` as CUDA C++ text (p = the trajectory's ODE parameters)."""
+    lib = lib or load_library()
+    eid = C.c_int32(-1)
+    _check(lib, lib.deb_define_event(int(dim), event_body.encode(), C.byref(eid)), "deb_define_event")
+    return EventSpec(eid.value)
 
 
 @dataclass
@@ -360,7 +388,7 @@ class Milstein(ExplicitRungeKutta):
 
 
 # ---------------------------------------------------------------------------------------------- results
-_STATUS_NAME = {DEB_STATUS_COMPLETE: "Complete", DEB_STATUS_MAX_STEPS: "MaxSteps", DEB_STATUS_STEP_SIZE: "StepSize",
+_STATUS_NAME = {DEB_STATUS_INTERRUPTED: "Interrupted", DEB_STATUS_COMPLETE: "Complete", DEB_STATUS_MAX_STEPS: "MaxSteps", DEB_STATUS_STEP_SIZE: "StepSize",
                 DEB_STATUS_STIFFNESS: "Stiffness", DEB_STATUS_BAD_INPUT: "BadInput"}
 
 
@@ -399,7 +427,7 @@ class EnsembleSolution:
         if self.t_out is not None and m > self.y_eval.shape[1]:
             raise ValueError(f"trajectory {i} produced {m} rows but the row capacity is {self.y_eval.shape[1]}: raise max_rows")
         ts = self.row_times(i)
-        return Solution(t=ts, y=self.y_eval[i, :m].copy(), status="Complete",
+        return Solution(t=ts, y=self.y_eval[i, :m].copy(), status=_STATUS_NAME[st],
                         evals=Evals(int(self.evals[i])), steps=Steps(int(self.accepted[i]), int(self.rejected[i])),
                         t_final=tfin, y_final=yf)
 
@@ -455,6 +483,7 @@ class EnsembleIVP:
         self._t_eval = np.zeros(0)
         self._even_dt = 0.0
         self._recorder = None  # (deb_solout, row capacity, dense n, component, threshold, direction)
+        self._event = None     # (EventSpec, direction, terminate count or 0, extra rows)
         self._method: Optional[ExplicitRungeKutta] = None
         self._device = 0
         self.seed, self.path_offset = int(seed), int(path_offset)
@@ -505,6 +534,16 @@ class EnsembleIVP:
         the component crosses the threshold, located by the reference's Newton iteration on the dense output."""
         return self._per_step(DEB_SOLOUT_CROSSING, max_rows, comp=component_idx, thr=threshold, direction=direction)
 
+    def event(self, ev: EventSpec, direction: int = CROSSING_BOTH, terminate: Optional[int] = None, max_event_rows: int = 16):  # ivp.rs:662
+        """`IVP::event(&e)`: wrap the current recorder with event detection (EventWrappedSolout, src/solout/event.rs).
+        `direction`/`terminate` are the event's `EventConfig` (terminate=1 is `.terminal()`).  Without a recorder the base is
+        the reference's default (every accepted step) and `max_event_rows` is the whole row capacity; with t_eval / even(dt)
+        it is the number of extra row slots for event rows."""
+        if self.kind != "ode":
+            raise ValueError("events are implemented for ODE ensembles")
+        self._event = (ev, int(direction), int(terminate or 0), int(max_event_rows))
+        return self
+
     def method(self, m: ExplicitRungeKutta):  # ivp.rs:632
         self._method = m
         return self
@@ -531,6 +570,13 @@ class EnsembleIVP:
             n_eval = int(math.floor(abs(self.tf - self.t0) / self._even_dt)) + 3  # row capacity per trajectory
         if self._recorder is not None:
             n_eval = self._recorder[1]
+        rows_cap = n_eval
+        if self.kind == "ode" and self._event is not None:
+            if self._recorder is None and self._even_dt <= 0.0 and self._t_eval.size == 0:
+                self._recorder = (DEB_SOLOUT_DEFAULT, self._event[3], 0, 0, 0.0, 0)  # plain solve().event(): every step + events
+                n_eval = rows_cap = self._event[3]
+            elif self._recorder is None:
+                rows_cap = n_eval + self._event[3]
         res = Result()
         t_sorted = np.zeros(max(n_eval, 1))
         if self.kind == "ode":
@@ -562,9 +608,14 @@ class EnsembleIVP:
             P.solout, P.even_dt = DEB_SOLOUT_EVEN, self._even_dt
         if self.kind == "ode" and self._recorder is not None:
             P.solout, _, P.dense_n, P.cross_component, P.cross_threshold, P.cross_direction = self._recorder
+        if self.kind == "ode" and self._event is not None:
+            ev, P.event_direction, P.event_terminate, _ = self._event
+            P.event, P.row_capacity = ev.event_id, rows_cap
+            for q, v in enumerate(ev.coef):
+                P.event_coef[q] = v
         self._method.fill_options(P.opt, dim, keep)
         P.device, P.memspace, P.stream = self._device, DEB_MEM_HOST, None
-        arrs = alloc_result_arrays(n, n_eval, dim, with_times=self._recorder is not None)
+        arrs = alloc_result_arrays(n, rows_cap, dim, with_times=(self._recorder is not None or (self.kind == "ode" and self._event is not None)))
         bind_result(res, arrs, t_sorted)
         keep += [params, self.y0s, self._t_eval]
         return P, res, arrs, t_sorted, keep

@@ -231,10 +231,12 @@ struct UserSystem {
 std::mutex g_user_mu;
 std::vector<std::unique_ptr<UserSystem>> g_user_systems;
 const int USER_SYSTEM_BASE = 1000;
-// run-time compiled kernels: (device, system id, method, per-step recorder) -> loaded kernel.  Besides user systems,
+struct UserEvent { int dim = 0; std::string body; };
+std::vector<std::unique_ptr<UserEvent>> g_user_events;  // ids USER_SYSTEM_BASE + index; guarded by g_user_mu
+// run-time compiled kernels: (device, system id, method, per-step recorder, event id) -> loaded kernel.  Besides user systems,
 // the per-step-recorder variants of the built-in systems are compiled on first use too (the ahead-of-time
 // instantiations cover the t_eval / even(dt) recorders).  Guarded by g_user_mu.
-std::map<std::tuple<int, int, int, int>, UserKernel> g_jit_kernels;
+std::map<std::tuple<int, int, int, int, int>, UserKernel> g_jit_kernels;
 
 // built-in system id -> (struct name, dim, n_params)
 const char* builtin_system_name(int system, int* dim, int* np) {
@@ -281,8 +283,8 @@ const char* method_tab_name(int method, bool* adaptive) {
 
 // Compile the ensemble kernel for (system, method, recorder kind) to a cubin (no device needed).  `us` = the user
 // system, or null for a built-in one.
-int compile_kernel_cubin(const UserSystem* us, int system, int method, bool rec, std::vector<char>* cubin, std::string* kernel_name,
-                         bool* is_adaptive) {
+int compile_kernel_cubin(const UserSystem* us, int system, int method, bool rec, int event, std::vector<char>* cubin,
+                         std::string* kernel_name, bool* is_adaptive) {
     int sdim = 0, snp = 0;
     const char* sys_name = us ? "deb::UserSys" : builtin_system_name(system, &sdim, &snp);
     if (!sys_name) return fail(DEB_ERR_BAD_ARG, "unknown system id");
@@ -300,9 +302,24 @@ int compile_kernel_cubin(const UserSystem* us, int system, int method, bool rec,
         else min_blocks = sdim <= 3 ? 5 : sdim <= 6 ? 3 : sdim <= 10 ? 2 : 1;
         if (rec && min_blocks > 1) min_blocks -= 1;  // the recorder keeps the dense output of a step live
     }
-    char expr[256];
-    if (adaptive) snprintf(expr, sizeof expr, "deb::dp_ensemble_kernel<%s, %s, 128, %d, false, %s>", sys_name, tab, min_blocks, rec ? "true" : "false");
-    else snprintf(expr, sizeof expr, "deb::fixed_ensemble_kernel<%s, %s, 128, %s>", sys_name, tab, rec ? "true" : "false");
+    // event functor
+    const UserEvent* ue = nullptr;
+    std::string evt = "deb::EvtNone";
+    if (event == DEB_EVENT_LINEAR) {
+        evt = "deb::EvtLinear<" + std::to_string(sdim) + ">";
+    } else if (event >= USER_SYSTEM_BASE) {
+        const size_t k = (size_t)(event - USER_SYSTEM_BASE);
+        if (k >= g_user_events.size()) return fail(DEB_ERR_BAD_ARG, "unknown event id");
+        ue = g_user_events[k].get();
+        if (ue->dim != sdim) return fail(DEB_ERR_BAD_ARG, "the event was defined for a different state dimension");
+        evt = "deb::UserEvt";
+    } else if (event != DEB_EVENT_NONE) {
+        return fail(DEB_ERR_BAD_ARG, "unknown event id");
+    }
+    if (event != DEB_EVENT_NONE && !rec) return fail(DEB_ERR_BAD_ARG, "internal: events need a recorder kernel");
+    char expr[384];
+    if (adaptive) snprintf(expr, sizeof expr, "deb::dp_ensemble_kernel<%s, %s, 128, %d, false, %s, %s>", sys_name, tab, min_blocks, rec ? "true" : "false", evt.c_str());
+    else snprintf(expr, sizeof expr, "deb::fixed_ensemble_kernel<%s, %s, 128, %s, %s>", sys_name, tab, rec ? "true" : "false", evt.c_str());
     std::string src;
     src += "#include \"erk_fixed.cuh\"\n#include \"systems.cuh\"\n";
     if (us) {
@@ -311,6 +328,13 @@ int compile_kernel_cubin(const UserSystem* us, int system, int method, bool rec,
         src += "    __device__ __forceinline__ static void rhs(double t, const double* y, double* dydt, const double* p) {\n";
         src += "        (void)t; (void)y; (void)p;\n";
         src += us->body;
+        src += "\n    }\n};\n}  // namespace deb\n";
+    }
+    if (ue) {
+        src += "namespace deb {\nstruct UserEvt {\n    static constexpr bool ENABLED = true;\n";
+        src += "    __device__ __forceinline__ static double g(const OdeKernelArgs&, double t, const double* y, const double* p) {\n";
+        src += "        (void)t; (void)y; (void)p;\n";
+        src += ue->body;
         src += "\n    }\n};\n}  // namespace deb\n";
     }
     // headers: the embedded kernel sources + minimal stand-ins for the C headers NVRTC does not ship
@@ -322,7 +346,7 @@ int compile_kernel_cubin(const UserSystem* us, int system, int method, bool rec,
     static const char* k_float = "#pragma once\n#define DBL_EPSILON 2.2204460492503131e-16\n#define DBL_MAX 1.7976931348623157e+308\n";
     static const char* k_abi =
         "#pragma once\n#define DEB_MAX_DIM 16\n"
-        "enum { DEB_STATUS_COMPLETE = 0, DEB_STATUS_MAX_STEPS = 1, DEB_STATUS_STEP_SIZE = 2, DEB_STATUS_STIFFNESS = 3, DEB_STATUS_BAD_INPUT = 4 };\n";
+        "enum { DEB_STATUS_COMPLETE = 0, DEB_STATUS_MAX_STEPS = 1, DEB_STATUS_STEP_SIZE = 2, DEB_STATUS_STIFFNESS = 3, DEB_STATUS_BAD_INPUT = 4, DEB_STATUS_INTERRUPTED = 5 };\n";
     hdr_names.push_back("stdint.h"); hdr_text.push_back(k_stdint);
     hdr_names.push_back("float.h"); hdr_text.push_back(k_float);
     hdr_names.push_back("../../include/deb_ensemble.h"); hdr_text.push_back(k_abi);
@@ -338,7 +362,7 @@ int compile_kernel_cubin(const UserSystem* us, int system, int method, bool rec,
         rt->GetProgramLogSize(prog, &n);
         std::string log(n, '\0');
         if (n) rt->GetProgramLog(prog, &log[0]);
-        return fail(us ? DEB_ERR_BAD_ARG : DEB_ERR_CUDA, (us ? "the right-hand side did not compile (NVRTC):\n" : "run-time kernel compilation failed (NVRTC):\n") + log);
+        return fail((us || ue) ? DEB_ERR_BAD_ARG : DEB_ERR_CUDA, ((us || ue) ? "the right-hand side / event function did not compile (NVRTC):\n" : "run-time kernel compilation failed (NVRTC):\n") + log);
     }
     const char* lowered = nullptr;
     r = rt->GetLoweredName(prog, expr, &lowered);
@@ -356,14 +380,14 @@ int compile_kernel_cubin(const UserSystem* us, int system, int method, bool rec,
 }
 
 // Compile and load (once per device / system / method / recorder kind) a run-time kernel.  Caller holds g_user_mu.
-int jit_kernel(const UserSystem* us, int device, int system, int method, bool rec, UserKernel** out) {
-    const auto key = std::make_tuple(device, system, method, rec ? 1 : 0);
+int jit_kernel(const UserSystem* us, int device, int system, int method, bool rec, int event, UserKernel** out) {
+    const auto key = std::make_tuple(device, system, method, rec ? 1 : 0, event);
     auto it = g_jit_kernels.find(key);
     if (it != g_jit_kernels.end()) { *out = &it->second; return DEB_OK; }
     std::vector<char> cubin;
     std::string lowered;
     UserKernel uk;
-    if (int rc = compile_kernel_cubin(us, system, method, rec, &cubin, &lowered, &uk.adaptive)) return rc;
+    if (int rc = compile_kernel_cubin(us, system, method, rec, event, &cubin, &lowered, &uk.adaptive)) return rc;
     DEB_CUDA(cudaLibraryLoadData(&uk.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
     DEB_CUDA(cudaLibraryGetKernel(&uk.kernel, uk.lib, lowered.c_str()));
     auto ins = g_jit_kernels.emplace(key, uk);
@@ -542,9 +566,18 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P, deb_result* R) {
     if (int rc = check_options(P->opt)) return rc;
     TEvalPlan plan;
     const bool even = (P->solout == DEB_SOLOUT_EVEN);
-    const bool rec = (P->solout == DEB_SOLOUT_DEFAULT || P->solout == DEB_SOLOUT_DENSE || P->solout == DEB_SOLOUT_CROSSING);
-    if (P->solout != DEB_SOLOUT_T_EVAL && !even && !rec) return fail(DEB_ERR_BAD_ARG, "unknown solout mode");
-    if (rec) {
+    const bool per_step = (P->solout == DEB_SOLOUT_DEFAULT || P->solout == DEB_SOLOUT_DENSE || P->solout == DEB_SOLOUT_CROSSING);
+    if (P->solout != DEB_SOLOUT_T_EVAL && !even && !per_step) return fail(DEB_ERR_BAD_ARG, "unknown solout mode");
+    const bool has_event = (P->event != DEB_EVENT_NONE);
+    const bool rec = per_step || has_event;  // rows with their own times: recorder kernels (compiled at first use)
+    if (has_event) {
+        if (P->event_direction < -1 || P->event_direction > 1) return fail(DEB_ERR_BAD_ARG, "event: direction must be -1, 0 or +1");
+        if (P->event_terminate < 0) return fail(DEB_ERR_BAD_ARG, "event: terminate count < 0");
+        if (P->row_capacity < 0) return fail(DEB_ERR_BAD_ARG, "row_capacity < 0");
+        if (!R->y_eval) return fail(DEB_ERR_BAD_ARG, "event detection needs a y_eval buffer");
+    }
+    const int row_cap = (has_event && P->row_capacity > 0) ? P->row_capacity : P->n_eval;
+    if (per_step) {
         // per-step recorders: no row plan; n_eval is the row capacity per trajectory
         if (!R->y_eval) return fail(DEB_ERR_BAD_ARG, "a per-step recorder needs a y_eval buffer");
         if (P->solout == DEB_SOLOUT_DENSE && P->dense_n < 0) return fail(DEB_ERR_BAD_ARG, "dense(n): n < 0");
@@ -578,7 +611,7 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P, deb_result* R) {
     if (jit) {  // user-defined right-hand side, or a per-step recorder: compile (first use) and bind the run-time kernel
         std::lock_guard<std::mutex> lk(g_user_mu);
         UserKernel* uk = nullptr;
-        if (int rc = jit_kernel(user, P->device, P->system, P->method, rec, &uk)) return rc;
+        if (int rc = jit_kernel(user, P->device, P->system, P->method, rec, P->event, &uk)) return rc;
         const UserKernel ukc = *uk;
         launch = [ukc](const deb::OdeKernelArgs& ka, int sms, cudaStream_t s2) { return launch_user(ukc, ka, sms, s2); };
     }
@@ -614,11 +647,14 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P, deb_result* R) {
     a.max_steps = (int)std::min<int64_t>(P->opt.max_steps, 0x7fffffff / 16);
     a.max_rejects = (int)std::min<int64_t>(std::max<int64_t>(P->opt.max_rejects, 0), 0x7fffffff);
     a.n_rows = (int)plan.rows.size();
-    a.row_stride = P->n_eval;
+    a.row_stride = row_cap;
     a.emit_t0 = plan.emit_t0 ? 1 : 0;
     a.even = even ? 1 : 0;
     a.even_tol = fabs(P->even_dt) * 1e-12 + 2.220446049250313e-16 * 10.0;
-    a.rec_mode = rec ? P->solout : 0;
+    a.rec_mode = P->solout;
+    a.event_direction = P->event_direction;
+    a.event_terminate = P->event_terminate;
+    for (int c = 0; c < DEB_MAX_DIM + 2; c++) a.event_coef[c] = P->event_coef[c];
     a.dense_n = P->dense_n;
     a.cross_component = P->cross_component;
     a.cross_direction = P->cross_direction;
@@ -659,7 +695,7 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P, deb_result* R) {
     const long long n_chunks = (n + CHUNK - 1) / CHUNK;
     const long long chunk = (n + n_chunks - 1) / n_chunks;
     const int n_slots = (n > chunk) ? 2 : 1;
-    const int n_eval = P->n_eval;
+    const int n_eval = row_cap;  // rows per trajectory in y_eval / t_out
     struct Slot {
         cudaStream_t st = nullptr;
         cudaEvent_t k0 = nullptr, k1 = nullptr;
@@ -760,7 +796,19 @@ extern "C" int deb_define_ode(int32_t dim, int32_t n_params, const char* diff_bo
     return DEB_OK;
 }
 
-extern "C" int deb_check_ode(int32_t system_id, int32_t method, int32_t solout) {
+extern "C" int deb_define_event(int32_t dim, const char* event_body, int32_t* event_id) {
+    if (!event_body || !event_id) return fail(DEB_ERR_BAD_ARG, "NULL argument");
+    if (dim < 1 || dim > DEB_MAX_DIM) return fail(DEB_ERR_BAD_ARG, "dim must be in 1..DEB_MAX_DIM");
+    std::lock_guard<std::mutex> lk(g_user_mu);
+    std::unique_ptr<UserEvent> ue(new UserEvent);
+    ue->dim = dim;
+    ue->body = event_body;
+    g_user_events.push_back(std::move(ue));
+    *event_id = USER_SYSTEM_BASE + (int32_t)g_user_events.size() - 1;
+    return DEB_OK;
+}
+
+extern "C" int deb_check_ode(int32_t system_id, int32_t method, int32_t solout, int32_t event) {
     std::lock_guard<std::mutex> lk(g_user_mu);
     const UserSystem* us = nullptr;
     if (system_id >= USER_SYSTEM_BASE) {
@@ -768,7 +816,7 @@ extern "C" int deb_check_ode(int32_t system_id, int32_t method, int32_t solout) 
         if (u >= (int)g_user_systems.size()) return fail(DEB_ERR_BAD_ARG, "unknown system id");
         us = g_user_systems[u].get();
     }
-    const bool rec = (solout == DEB_SOLOUT_DEFAULT || solout == DEB_SOLOUT_DENSE || solout == DEB_SOLOUT_CROSSING);
+    const bool rec = (solout == DEB_SOLOUT_DEFAULT || solout == DEB_SOLOUT_DENSE || solout == DEB_SOLOUT_CROSSING || event != DEB_EVENT_NONE);
     if (!us && !rec) {  // built-in system with a row-plan recorder: compiled ahead of time
         int dim = 0, np = 0;
         if (!pick_ode(system_id, method, &dim, &np)) return fail(dim < 0 ? DEB_ERR_BAD_ARG : DEB_ERR_UNSUPPORTED, "unknown system or method id");
@@ -777,7 +825,7 @@ extern "C" int deb_check_ode(int32_t system_id, int32_t method, int32_t solout) 
     std::vector<char> cubin;
     std::string name;
     bool adaptive = false;
-    return compile_kernel_cubin(us, system_id, method, rec, &cubin, &name, &adaptive);
+    return compile_kernel_cubin(us, system_id, method, rec, event, &cubin, &name, &adaptive);
 }
 
 extern "C" int deb_solve_sde(const deb_sde_problem* P, deb_result* R) {

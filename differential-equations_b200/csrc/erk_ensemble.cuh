@@ -51,6 +51,10 @@ struct OdeKernelArgs {
     int cross_component, cross_direction;
     double cross_threshold;
     double* t_out;          // [n_traj][row_stride] or null
+    // event detection wrapped around the recorder (EventWrappedSolout, src/solout/event.rs); REC kernels with an Evt functor
+    int event_direction;    // 0 both, +1 positive, -1 negative
+    int event_terminate;    // stop after this many events (0 = never)
+    double event_coef[DEB_MAX_DIM + 2];  // EvtLinear: g = c0 + c1*t + sum c[2+i]*y[i]
     double* y_eval;
     int* n_emitted;
     double* t_final;
@@ -198,7 +202,7 @@ __device__ __noinline__ void all_terms_attempt(const double* y, double* k, doubl
 }
 
 // REC: the output goes through a per-step recorder (step_recorder.cuh) instead of the t_eval / even(dt) row plan.
-template <class Sys, class Tab, int BLOCK, int MIN_BLOCKS, bool SHARED_P, bool REC = false>
+template <class Sys, class Tab, int BLOCK, int MIN_BLOCKS, bool SHARED_P, bool REC = false, class Evt = EvtNone>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const OdeKernelArgs a) {
     constexpr int N = Sys::DIM, NP = Sys::NP, S = Tab::S, I = Tab::I, O = Tab::O;
     constexpr unsigned FULL = 0xffffffffu;
@@ -220,7 +224,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
     const bool bounded_h = (a.h_min > 0.0) || (a.h_max < 1.0 / 0.0);  // constrain_step_size can change h at all
 
     constexpr bool DEFER = (I == S) && !REC;   // dense output needs no extra stages: emission can be parked
-    StepRecorder<Sys, Tab> recd;
+    StepRecorder<Sys, Tab, Evt> recd;
     constexpr int NSTASH = 2 + 4 * N;  // t, h, y, y_new, k0, f(y_new)
     __shared__ double s_stash[DEFER ? (BLOCK / 32) : 1][DEFER ? NSTASH : 1][32];
     double (*stash)[32] = s_stash[DEFER ? (threadIdx.x >> 5) : 0];
@@ -393,17 +397,17 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
                         rejected_prev = false;
                         Sys::rhs(t, y, k[0], p);
                         // solout before the loop (solve_ivp.rs:160): emits rows[0] iff it equals t0
-                        if (a.emit_t0) {
+                        if (!REC && a.emit_t0) {
                             if (a.y_eval) {
 #pragma unroll
                                 for (int c = 0; c < N; c++) a.y_eval[(traj * a.row_stride) * N + c] = y[c];
                             }
                             idx = 1;
                         }
-                        te = (idx < a.n_rows) ? a.t_rows[idx] : te_none;
+                        te = (!REC && idx < a.n_rows) ? a.t_rows[idx] : te_none;
                         if constexpr (REC) {  // the solout call that precedes the loop
                             recd.reset();
-                            recd.first(a, traj, t0, y);
+                            recd.first(a, traj, t0, y, p);
                         }
                         active = true;
                     }
@@ -760,8 +764,9 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
                 __syncwarp();
             }
 
+            bool interrupt = false;  // ControlFlag::Terminate from an event: the step is kept, then Status::Interrupted
             if constexpr (REC) {  // solout after an accepted step (solve_ivp.rs:239-246)
-                if (accept && fin < 0) recd.step(a, traj, t, h, y, ynew, k, dydt, p);
+                if (accept && fin < 0) interrupt = recd.step(a, traj, t, h, y, ynew, k, dydt, p);
                 __syncwarp();
             }
 
@@ -794,6 +799,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
                 if (bounded_h) h = constrain_step_size(h, a.h_min, a.h_max);  // identity for h_min = 0, h_max = inf
                 // accepted: end-of-interval test, solve_ivp.rs:263
                 if (commit && fabs(tf - t) <= eps10) fin = DEB_STATUS_COMPLETE;
+                if (REC && interrupt) fin = DEB_STATUS_INTERRUPTED;  // solve_ivp.rs:255-260, before the end-of-interval test
             }
             service = (active && fin >= 0) || blocked;
         } while (!__any_sync(FULL, service));

@@ -14,7 +14,7 @@
 
 namespace deb {
 
-template <class Sys, class Tab, int BLOCK, bool REC = false>
+template <class Sys, class Tab, int BLOCK, bool REC = false, class Evt = EvtNone>
 __global__ void __launch_bounds__(BLOCK) fixed_ensemble_kernel(const OdeKernelArgs a) {
     constexpr int N = Sys::DIM, NP = Sys::NP, S = Tab::S;
     const double t0 = a.t0, tf = a.tf;
@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(BLOCK) fixed_ensemble_kernel(const OdeKernelAr
         for (int q = 0; q < NP; q++) p[q] = a.params ? a.params[traj * a.params_stride + q] : a.pc[q];
         int steps = 0, evals = 0, n_emit = 0, idx = 0;
         int fin = -1;
-        StepRecorder<Sys, Tab> recd;
+        StepRecorder<Sys, Tab, Evt> recd;
         double t = t0;
         // ---- init, fixed/ordinary.rs:16-56
         double h = a.h0;
@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(BLOCK) fixed_ensemble_kernel(const OdeKernelAr
         } else {
             Sys::rhs(t, y, dydt, p);
             evals = 1;
-            if (a.emit_t0) {
+            if (!REC && a.emit_t0) {
                 if (a.y_eval) {
 #pragma unroll
                     for (int c = 0; c < N; c++) a.y_eval[(traj * a.row_stride) * N + c] = y[c];
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(BLOCK) fixed_ensemble_kernel(const OdeKernelAr
                 n_emit = 1;
                 idx = 1;
             }
-            if constexpr (REC) recd.first(a, traj, t0, y);  // the solout call that precedes the loop
+            if constexpr (REC) recd.first(a, traj, t0, y, p);  // the solout call that precedes the loop
         }
         double te = (idx < a.n_rows) ? a.t_rows[idx] : te_none;
         while (fin < 0) {
@@ -94,7 +94,8 @@ __global__ void __launch_bounds__(BLOCK) fixed_ensemble_kernel(const OdeKernelAr
             const double t_new = t + h;
             Sys::rhs(t_new, ynew, dnew, p);
             evals += S;  // S-1 stages + the new derivative (fsal = false)
-            if constexpr (REC) recd.step(a, traj, t, h, y, ynew, k, dnew, p);
+            bool interrupt = false;
+            if constexpr (REC) interrupt = recd.step(a, traj, t, h, y, ynew, k, dnew, p);
             // ---- TEvalSolout with cubic Hermite interpolation
             while (!REC && ((dir > 0.0) ? (te <= t_new) : (te >= t_new))) {
                 if (a.even && idx == a.n_rows - 1) {  // the tf sentinel: EvenSolout final-point rule, even.rs:166-188
@@ -147,6 +148,7 @@ __global__ void __launch_bounds__(BLOCK) fixed_ensemble_kernel(const OdeKernelAr
 #pragma unroll
             for (int c = 0; c < N; c++) { y[c] = ynew[c]; dydt[c] = dnew[c]; }
             if (fabs(tf - t) <= eps10) fin = DEB_STATUS_COMPLETE;  // solve_ivp.rs:263
+            if (REC && interrupt) fin = DEB_STATUS_INTERRUPTED;    // solve_ivp.rs:255-260 (an event asked to terminate)
         }
         if (a.status) a.status[traj] = fin;
         if (a.t_final) a.t_final[traj] = t;

@@ -19,7 +19,24 @@
 
 namespace deb {
 
-enum { REC_NONE = 0, REC_DEFAULT = 2, REC_DENSE = 3, REC_CROSSING = 4 };  // = deb_solout values
+enum { REC_T_EVAL = 0, REC_EVEN = 1, REC_DEFAULT = 2, REC_DENSE = 3, REC_CROSSING = 4 };  // = deb_solout values
+
+// Event functions g(t, y) (the `Event` trait, src/solout/event.rs:60-70).  EvtNone: no event detection.
+struct EvtNone {
+    static constexpr bool ENABLED = false;
+    __device__ __forceinline__ static double g(const OdeKernelArgs&, double, const double*, const double*) { return 0.0; }
+};
+// g(t, y) = c0 + c1*t + sum_c c[2+c]*y[c], accumulated in that order (e.g. `y[0] - 0.9*m` is {-0.9*m, 0, 1}: same bits)
+template <int N>
+struct EvtLinear {
+    static constexpr bool ENABLED = true;
+    __device__ __forceinline__ static double g(const OdeKernelArgs& a, double t, const double* y, const double*) {
+        double v = a.event_coef[0] + a.event_coef[1] * t;
+#pragma unroll
+        for (int c = 0; c < N; c++) v = v + a.event_coef[2 + c] * y[c];
+        return v;
+    }
+};
 
 template <class Sys, class Tab>
 struct DenseStep {
@@ -156,14 +173,21 @@ struct DenseStep {
     }
 };
 
-template <class Sys, class Tab>
+// Base recorder + optional event detection (EventWrappedSolout, src/solout/event.rs:300-470): the base recorder pushes its
+// rows first, then a sign change of g over the step is located with Brent-Dekker on the dense output and pushed; after
+// `event_terminate` events the integration stops with Status::Interrupted.
+template <class Sys, class Tab, class Evt = EvtNone>
 struct StepRecorder {
     static constexpr int N = Sys::DIM, S = Tab::S;
     int rows = 0;             // pushes so far (Solution.t.len())
+    double last_t = 0.0;      // time of the last pushed row (solution.t.last())
     bool have_last = false;   // CrossingSolout::last_offset_value
     double last_off = 0.0;
+    int idx = 0;              // t_eval / even bases: next entry of the row plan
+    double last_g = 0.0;      // EventWrappedSolout::last_g (always Some after the first call)
+    int event_count = 0;
 
-    __device__ __forceinline__ void reset() { rows = 0; have_last = false; last_off = 0.0; }
+    __device__ __forceinline__ void reset() { rows = 0; have_last = false; last_off = 0.0; idx = 0; last_g = 0.0; event_count = 0; last_t = 0.0; }
 
     __device__ __forceinline__ void push(const OdeKernelArgs& a, long long traj, double t, const double (&y)[N]) {
         if (rows < a.row_stride) {
@@ -175,23 +199,27 @@ struct StepRecorder {
             if (a.t_out) a.t_out[r] = t;
         }
         rows += 1;
+        last_t = t;
     }
 
-    __device__ __forceinline__ static double component(const double (&y)[N], int idx) {
+    __device__ __forceinline__ static double component(const double (&y)[N], int idx_) {
         double v = y[0];
 #pragma unroll
-        for (int c = 1; c < N; c++) v = (c == idx) ? y[c] : v;
+        for (int c = 1; c < N; c++) v = (c == idx_) ? y[c] : v;
         return v;
     }
 
     // the solout call that precedes the loop (solve_ivp.rs:160): t_prev == t_curr == t0
-    __device__ __forceinline__ void first(const OdeKernelArgs& a, long long traj, double t0, const double (&y0)[N]) {
+    __device__ __forceinline__ void first(const OdeKernelArgs& a, long long traj, double t0, const double (&y0)[N], const double* p) {
         if (a.rec_mode == REC_CROSSING) {
             last_off = component(y0, a.cross_component) - a.cross_threshold;
             have_last = true;
+        } else if (a.rec_mode == REC_T_EVAL || a.rec_mode == REC_EVEN) {
+            if (a.emit_t0) { push(a, traj, t0, y0); idx = 1; }  // the row plan starts with t0 (t_eval.rs:113-114 / even.rs:100-104)
         } else {
             push(a, traj, t0, y0);  // Default: always; Dense: t_prev == t_curr, only the point itself
         }
+        if (Evt::ENABLED) last_g = Evt::g(a, t0, y0, p);  // event.rs:373-380: first call only stores g
     }
 
     // find_crossing_newton, crossing.rs:185-263
@@ -226,16 +254,70 @@ struct StepRecorder {
         return fabs(off) < tolerance * 10.0;
     }
 
-    // solout after an accepted step from (t, y) to (t + h, yn); k[0] = f(t, y), dydt = f(t + h, yn)
-    __device__ __forceinline__ void step(const OdeKernelArgs& a, long long traj, double t, double h, const double (&y)[N],
+    // brent_dekker, event.rs:386-470.  `interpolate(b).ok()?`: a point outside [t_prev, t_curr] AS THE REFERENCE TESTS IT
+    // (t < t_prev || t > t_curr, written for forward time) ends the search without an event.
+    __device__ __forceinline__ bool brent_dekker(const OdeKernelArgs& ka, const DenseStep<Sys, Tab>& ds, const double* p, double a, double b,
+                                                 double fa, double fb, double* t_event) const {
+        const double rel_tol = 1e-12, abs_tol = 1e-14;
+        if (fabs(fa) < fabs(fb)) { double x = a; a = b; b = x; x = fa; fa = fb; fb = x; }
+        double c = a, fc = fa, d = b - a, e = d;
+        for (int it = 0; it < 50; it++) {
+            if (fb == 0.0) { *t_event = b; return true; }
+            if (d_signum(fa) == d_signum(fb)) { a = c; fa = fc; c = b; fc = fb; d = b - a; e = d; }
+            if (fabs(fa) < fabs(fb)) { c = b; b = a; a = c; fc = fb; fb = fa; fa = fc; }
+            const double tol = fmax(abs_tol, rel_tol * fabs(b));
+            const double m = 0.5 * (a - b);
+            if (fabs(m) <= tol || fb == 0.0) { *t_event = b; return true; }
+            bool use_bis = true;
+            if (fabs(e) > tol && fabs(fa) > fabs(fb)) {
+                const double s = fb / fa;
+                double pp, q;
+                if (a == c) {
+                    pp = 2.0 * m * s;
+                    q = 1.0 - s;
+                } else {
+                    const double q1 = fa / fc;
+                    const double r = fb / fc;
+                    pp = s * (2.0 * m * q1 * (q1 - r) - (b - a) * (r - 1.0));
+                    q = (q1 - 1.0) * (r - 1.0) * (s - 1.0);
+                }
+                double q_mod = q, p_mod = pp;
+                if (q_mod > 0.0) p_mod = -p_mod; else q_mod = -q_mod;
+                if (fabs(2.0 * p_mod) < (3.0 * m * q_mod - fabs(tol * q_mod)) && p_mod < fabs(e * 0.5 * q_mod)) {
+                    e = d;
+                    d = p_mod / q_mod;
+                    use_bis = false;
+                }
+            }
+            if (use_bis) { d = m; e = m; }
+            a = b;
+            fa = fb;
+            b = (fabs(d) > tol) ? (b + d) : (b + ((m > 0.0) ? tol : -tol));
+            if (b < ds.t || b > ds.t_new) return false;  // interpolate(b) is Err(OutOfBounds)
+            double yb[N];
+            ds.eval(b, yb);
+            fb = Evt::g(ka, b, yb, p);
+            c = a;
+            fc = fa;
+        }
+        return false;
+    }
+
+    // solout after an accepted step from (t, y) to (t + h, yn); k[0] = f(t, y), dydt = f(t + h, yn).  Returns true when
+    // an event asks to terminate (ControlFlag::Terminate).
+    __device__ __forceinline__ bool step(const OdeKernelArgs& a, long long traj, double t, double h, const double (&y)[N],
                                          const double (&yn)[N], const double (&k)[S][N], const double (&dydt)[N], const double* p) {
         const double t_new = t + h;
+        const double dir = d_signum(a.tf - a.t0);
+        DenseStep<Sys, Tab> ds;
+        bool prepared = false;
+        // ---- base recorder
         if (a.rec_mode == REC_DEFAULT) {
             push(a, traj, t_new, yn);
         } else if (a.rec_mode == REC_DENSE) {
             if (t != t_new && a.dense_n > 1) {
-                DenseStep<Sys, Tab> ds;
                 ds.prepare(t, h, y, yn, k, dydt, p);
+                prepared = true;
                 for (int i = 1; i < a.dense_n; i++) {
                     const double h_old = t_new - t;
                     const double ti = t + (double)i * h_old / (double)a.dense_n;
@@ -245,7 +327,7 @@ struct StepRecorder {
                 }
             }
             push(a, traj, t_new, yn);
-        } else {  // REC_CROSSING
+        } else if (a.rec_mode == REC_CROSSING) {
             const double off = component(yn, a.cross_component) - a.cross_threshold;
             if (have_last) {
                 const bool is_crossing = d_signum(last_off) != d_signum(off);  // NaN != anything
@@ -253,8 +335,8 @@ struct StepRecorder {
                     const bool record = (a.cross_direction > 0) ? (last_off < 0.0 && off >= 0.0)
                                       : (a.cross_direction < 0) ? (last_off > 0.0 && off <= 0.0) : true;
                     if (record) {
-                        DenseStep<Sys, Tab> ds;
                         ds.prepare(t, h, y, yn, k, dydt, p);
+                        prepared = true;
                         double t_cross;
                         if (!newton(a, ds, t, t_new, last_off, off, &t_cross)) {
                             const double frac = -last_off / (off - last_off);
@@ -268,7 +350,58 @@ struct StepRecorder {
             }
             last_off = off;
             have_last = true;
+        } else {
+            // t_eval / even(dt) through the host's row plan (see erk_ensemble.cuh: every planned point a step passes is emitted;
+            // even: always interpolated, and the last plan entry is the tf sentinel of the final-point rule, even.rs:166-188)
+            while (idx < a.n_rows && (a.t_rows[idx] - t_new) * dir <= 0.0) {
+                const double te = a.t_rows[idx];
+                if (a.rec_mode == REC_EVEN && idx == a.n_rows - 1) {
+                    if (t_new == a.tf) {
+                        const double t_prev_row = a.t_rows[idx - 1];
+                        if (fabs(t_prev_row - a.tf) <= a.even_tol) rows -= 1;  // solution.pop(): replace the near-duplicate
+                        push(a, traj, a.tf, yn);
+                    }
+                    idx = a.n_rows;
+                    break;
+                }
+                if (te == t_new && a.rec_mode == REC_T_EVAL) {
+                    push(a, traj, te, yn);
+                } else {
+                    if (!prepared) { ds.prepare(t, h, y, yn, k, dydt, p); prepared = true; }
+                    double row[N];
+                    ds.eval(te, row);
+                    push(a, traj, te, row);
+                }
+                idx += 1;
+            }
         }
+        // ---- event detection, event.rs:361-384 (detect_event)
+        bool terminate = false;
+        if (Evt::ENABLED) {
+            const double g_curr = Evt::g(a, t_new, yn, p);
+            const double g_prev = last_g;
+            const bool sign_change = d_signum(g_prev) != d_signum(g_curr);
+            const bool direction_ok = (a.event_direction > 0) ? (sign_change && g_prev < 0.0 && g_curr >= 0.0)
+                                    : (a.event_direction < 0) ? (sign_change && g_prev > 0.0 && g_curr <= 0.0) : sign_change;
+            if (direction_ok) {
+                double ea = t, eb = t_new, fa = g_prev, fb = g_curr;
+                if ((dir > 0.0 && ea > eb) || (dir < 0.0 && ea < eb)) { double x = ea; ea = eb; eb = x; x = fa; fa = fb; fb = x; }
+                if (fa * fb <= 0.0) {
+                    if (!prepared) { ds.prepare(t, h, y, yn, k, dydt, p); prepared = true; }
+                    double t_event;
+                    if (brent_dekker(a, ds, p, ea, eb, fa, fb, &t_event)) {
+                        double row[N];
+                        ds.eval(t_event, row);
+                        const bool push_point = (rows > 0) ? (fabs(t_event - last_t) > 1e-14) : true;
+                        if (push_point) push(a, traj, t_event, row);
+                        event_count += 1;
+                        if (a.event_terminate > 0 && event_count >= a.event_terminate) terminate = true;
+                    }
+                }
+            }
+            last_g = g_curr;
+        }
+        return terminate;
     }
 };
 

@@ -18,7 +18,7 @@ use differential_equations::{
 };
 
 // ------------------------------------------------------------------------------------------------ raw ABI
-pub const DEB_ABI_VERSION: i32 = 5;
+pub const DEB_ABI_VERSION: i32 = 6;
 
 #[repr(C)]
 #[derive(Clone, Copy)]
@@ -62,6 +62,11 @@ pub struct deb_ode_problem {
     pub cross_component: i32,
     pub cross_direction: i32, // 0 Both, +1 Positive, -1 Negative
     pub cross_threshold: f64,
+    pub event: i32,           // 0 none, 1 linear (event_coef), >= 1000 from deb_define_event
+    pub event_direction: i32, // EventConfig.direction
+    pub event_terminate: i32, // EventConfig.terminate (0 = None)
+    pub row_capacity: i32,    // rows per trajectory when an event is set
+    pub event_coef: [f64; 18],
 }
 
 #[repr(C)]
@@ -91,7 +96,9 @@ extern "C" {
     /// user-defined right-hand side as CUDA C++ text (the device-side `impl ODE`); returns a system id >= 1000
     pub fn deb_define_ode(dim: i32, n_params: i32, diff_body: *const c_char, system_id: *mut i32) -> i32;
     /// compile it for a method now (no device needed); the compiler log is in deb_last_error()
-    pub fn deb_check_ode(system_id: i32, method: i32, solout: i32) -> i32;
+    pub fn deb_check_ode(system_id: i32, method: i32, solout: i32, event: i32) -> i32;
+    /// user-defined event function g(t, y) as CUDA C++ text (the device-side `impl Event`); returns an event id >= 1000
+    pub fn deb_define_event(dim: i32, event_body: *const c_char, event_id: *mut i32) -> i32;
     // deb_solve_sde, deb_solve_heat_mol, deb_heat_rhs, deb_ensemble_stats, deb_malloc, ... : see deb_ensemble.h
 }
 
@@ -234,6 +241,11 @@ impl<const N: usize> EnsembleIVP<N> {
             cross_component: 0,
             cross_direction: 0,
             cross_threshold: 0.0,
+            event: 0,
+            event_direction: 0,
+            event_terminate: 0,
+            row_capacity: 0,
+            event_coef: [0.0; 18],
         };
         let mut result = deb_result {
             struct_size: std::mem::size_of::<deb_result>(),

@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define DEB_ABI_VERSION 5
+#define DEB_ABI_VERSION 6
 #define DEB_MAX_DIM 16 /* widest state the register-resident kernels are instantiated for */
 
 typedef enum deb_error {
@@ -111,8 +111,16 @@ typedef enum deb_status {
     DEB_STATUS_MAX_STEPS = 1, /* Error::MaxSteps{t,y}   dormandprince/ordinary.rs:82-91 */
     DEB_STATUS_STEP_SIZE = 2, /* Error::StepSize{t,y}   dormandprince/ordinary.rs:70-79 */
     DEB_STATUS_STIFFNESS = 3, /* Error::Stiffness{t,y}  dormandprince/ordinary.rs:165-194 */
-    DEB_STATUS_BAD_INPUT = 4  /* Error::BadInput{..}    utils.rs:60-157, solve_ivp.rs:139-147 */
+    DEB_STATUS_BAD_INPUT = 4, /* Error::BadInput{..}    utils.rs:60-157, solve_ivp.rs:139-147 */
+    DEB_STATUS_INTERRUPTED = 5 /* Ok(Solution) with Status::Interrupted: an event asked to terminate (solve_ivp.rs:255-260) */
 } deb_status;
+
+/* Event functions g(t, y) (the `Event` trait, src/solout/event.rs:60-70) for deb_ode_problem.event */
+enum {
+    DEB_EVENT_NONE = 0,
+    DEB_EVENT_LINEAR = 1 /* g(t, y) = c[0] + c[1]*t + sum_i c[2+i]*y[i] (event_coef), accumulated in that order */
+    /* >= 1000: ids returned by deb_define_event */
+};
 
 typedef enum deb_memspace { DEB_MEM_HOST = 0, DEB_MEM_DEVICE = 1 } deb_memspace;
 
@@ -170,6 +178,16 @@ typedef struct deb_ode_problem {
     int32_t cross_component;
     int32_t cross_direction; /* 0 = Both, +1 = Positive (below -> above), -1 = Negative */
     double cross_threshold;
+    /* IVP::event(&e): event detection wrapped around the recorder above (EventWrappedSolout, src/solout/event.rs:300-470).
+     * After the recorder has pushed the rows of a step, a sign change of g over the step is located by Brent-Dekker on the
+     * dense output and pushed as a row; after `event_terminate` events the trajectory stops with DEB_STATUS_INTERRUPTED.
+     * With an event every recorder produces per-trajectory rows: times in t_out, `row_capacity` rows per trajectory. */
+    int32_t event;           /* DEB_EVENT_NONE, DEB_EVENT_LINEAR or an id from deb_define_event */
+    int32_t event_direction; /* EventConfig.direction: 0 = Both, +1 = Positive, -1 = Negative */
+    int32_t event_terminate; /* EventConfig.terminate: stop after this many events; 0 = None (never) */
+    int32_t row_capacity;    /* rows per trajectory in y_eval / t_out when an event is set (0 = n_eval); for t_eval / even(dt)
+                                recorders n_eval keeps its meaning (number of points / row-plan capacity) */
+    double event_coef[DEB_MAX_DIM + 2];
 } deb_ode_problem;
 
 typedef struct deb_sde_problem {
@@ -262,11 +280,16 @@ void deb_erk_options_default(deb_erk_options* opt);
  * serve the built-in systems, and cached.  Returns a system id (>= 1000) to put in deb_ode_problem.system.
  * A body that does not compile makes the first deb_solve_ode return DEB_ERR_BAD_ARG with the compiler log. */
 int deb_define_ode(int32_t dim, int32_t n_params, const char* diff_body, int32_t* system_id);
-/* Compile the kernel for (system, method, recorder) now, without a device and without running anything: DEB_OK, or
+/* User-defined event function: the BODY of
+ *     double event(double t, const double* y, const double* p)
+ * as CUDA C++ text (p = the trajectory's ODE parameters), the device-side `impl Event for S { fn event(&self, t, y) }`.
+ * Returns an id (>= 1000) for deb_ode_problem.event. */
+int deb_define_event(int32_t dim, const char* event_body, int32_t* event_id);
+/* Compile the kernel for (system, method, recorder, event) now, without a device and without running anything: DEB_OK, or
  * an error with the compiler log in deb_last_error() (DEB_ERR_BAD_ARG for a user-defined right-hand side that does not
  * compile: what a Rust caller gets from `cargo check`).  Kernels that were compiled ahead of time (built-in system with
  * a t_eval / even(dt) recorder) return DEB_OK at once. */
-int deb_check_ode(int32_t system_id, int32_t method, int32_t solout);
+int deb_check_ode(int32_t system_id, int32_t method, int32_t solout, int32_t event);
 
 int deb_solve_ode(const deb_ode_problem* problem, deb_result* result);
 int deb_solve_sde(const deb_sde_problem* problem, deb_result* result);

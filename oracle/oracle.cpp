@@ -557,6 +557,22 @@ struct Out {  // per-trajectory output slots
     double* t_out = nullptr;
 };
 
+// Row sink = Solution.t / Solution.y of one trajectory: `cap` row slots; pushes beyond that are counted only.
+struct Rows {
+    double* y_eval; double* t_out; int n; int cap;
+    int n_emit = 0;
+    double last_t = 0.0;  // solution.t.last()
+    void push(double t, const Vec& v) {
+        if (n_emit < cap) {
+            if (y_eval) std::memcpy(y_eval + (size_t)n_emit * n, v.data(), sizeof(double) * n);
+            if (t_out) t_out[n_emit] = t;
+        }
+        n_emit += 1;
+        last_t = t;
+    }
+    void pop() { n_emit -= 1; }
+};
+
 // Per-step recorders: DefaultSolout (src/solout/default.rs:54-75), DenseSolout (src/solout/dense.rs:74-108),
 // CrossingSolout (src/solout/crossing.rs:115-263).  Rows carry their own time; `cap` row slots per trajectory, pushes
 // beyond that are counted only.  Where the reference's interpolate() would return Err(OutOfBounds) and the recorder
@@ -597,15 +613,8 @@ bool crossing_newton(const PerStep& ps, Interp&& interp, double t_lower, double 
     return std::fabs(off) < tolerance * 10.0;
 }
 template <class Interp>
-void solout_per_step(PerStep& ps, double t_curr, double t_prev, const Vec& y_curr, Interp&& interp, double* y_eval, double* t_out,
-                     int n, int* n_emit) {
-    auto push = [&](double t, const Vec& v) {
-        if (*n_emit < ps.cap) {
-            if (y_eval) std::memcpy(y_eval + (size_t)(*n_emit) * n, v.data(), sizeof(double) * n);
-            if (t_out) t_out[*n_emit] = t;
-        }
-        *n_emit += 1;
-    };
+void solout_per_step(PerStep& ps, double t_curr, double t_prev, const Vec& y_curr, Interp&& interp, Rows& rows) {
+    auto push = [&](double t, const Vec& v) { rows.push(t, v); };
     if (ps.mode == DEB_SOLOUT_DEFAULT) {
         push(t_curr, y_curr);
     } else if (ps.mode == DEB_SOLOUT_DENSE) {
@@ -640,7 +649,7 @@ void solout_per_step(PerStep& ps, double t_curr, double t_prev, const Vec& y_cur
 }
 
 template <class Interp>
-void solout_teval(TEval& te, double t_curr, double t_prev, const Vec& y_curr, Interp&& interp, double* y_eval, int n, int* n_emit) {
+void solout_teval(TEval& te, double t_curr, double t_prev, const Vec& y_curr, Interp&& interp, Rows& rows) {
     size_t idx = te.idx;
     while (idx < te.pts.size()) {
         double tv = te.pts[idx];
@@ -648,8 +657,7 @@ void solout_teval(TEval& te, double t_curr, double t_prev, const Vec& y_curr, In
                                        : ((tv == t_prev && idx == 0) || (tv < t_prev && tv >= t_curr));
         if (in_range) {
             Vec yv = (tv == t_curr) ? y_curr : interp(tv);
-            if (y_eval) std::memcpy(y_eval + (size_t)(*n_emit) * n, yv.data(), sizeof(double) * n);
-            *n_emit += 1;
+            rows.push(tv, yv);
             idx += 1;
         } else {
             if ((te.dir > 0.0 && tv > t_curr) || (te.dir < 0.0 && tv < t_curr)) break;
@@ -667,8 +675,8 @@ struct Even {
     Even(double dt_, double t0_, double tf_) : dt(dt_), t0(t0_), tf(tf_), dir(signum(tf_ - t0_)) {}
 };
 template <class Interp>
-void solout_even(Even& ev, double t_curr, double t_prev, const Vec& y_curr, const Vec& y_prev, Interp&& interp, double* y_eval, int n, int* n_emit) {
-    auto push = [&](const Vec& v) { if (y_eval) std::memcpy(y_eval + (size_t)(*n_emit) * n, v.data(), sizeof(double) * n); *n_emit += 1; };
+void solout_even(Even& ev, double t_curr, double t_prev, const Vec& y_curr, const Vec& y_prev, Interp&& interp, Rows& rows) {
+    auto push = [&](double t, const Vec& v) { rows.push(t, v); };
     const double offset = std::fmod(ev.t0, ev.dt);
     const double tol = std::fabs(ev.dt) * 1e-12 + DBL_EPSILON * 10.0;
     double start_t;
@@ -676,7 +684,7 @@ void solout_even(Even& ev, double t_curr, double t_prev, const Vec& y_curr, cons
         start_t = ev.last + ev.dt * ev.dir;
     } else {
         if (std::fabs(t_prev - ev.t0) < DBL_EPSILON) {
-            push(y_prev);
+            push(ev.t0, y_prev);
             ev.last = ev.t0; ev.has_last = true;
             start_t = ev.t0 + ev.dt * ev.dir;
         } else {
@@ -691,7 +699,7 @@ void solout_even(Even& ev, double t_curr, double t_prev, const Vec& y_curr, cons
             if (ev.has_last && std::fabs(ti - ev.last) <= tol) {
                 // near-duplicate: skip
             } else {
-                push(interp(ti));
+                push(ti, interp(ti));
                 ev.last = ti; ev.has_last = true;
             }
         }
@@ -700,18 +708,108 @@ void solout_even(Even& ev, double t_curr, double t_prev, const Vec& y_curr, cons
     if (t_curr == ev.tf) {  // even.rs:166-188
         if (ev.has_last) {
             if (std::fabs(ev.last - ev.tf) <= tol) {
-                *n_emit -= 1;  // solution.pop()
-                push(y_curr);
+                rows.pop();  // solution.pop()
+                push(ev.tf, y_curr);
                 ev.last = ev.tf;
             } else if (ev.last != ev.tf) {
-                push(y_curr);
+                push(ev.tf, y_curr);
                 ev.last = ev.tf;
             }
         } else {
-            push(y_curr);
+            push(ev.tf, y_curr);
             ev.last = ev.tf; ev.has_last = true;
         }
     }
+}
+
+// Event detection wrapped around a recorder: EventWrappedSolout, src/solout/event.rs:300-470.  The event function is the
+// ABI's linear form g(t, y) = c0 + c1*t + sum c[2+i]*y[i] (arbitrary `impl Event` bodies are covered by tests/py_restatement.py).
+struct EventState {
+    int direction = 0, terminate = 0, n = 0;
+    const double* coef = nullptr;
+    double dir = 1.0;
+    bool has_last = false;
+    double last_g = 0.0;
+    int count = 0;
+    double g(double t, const Vec& y) const {
+        double v = coef[0] + coef[1] * t;
+        for (int c = 0; c < n; c++) v = v + coef[2 + c] * y[c];
+        return v;
+    }
+};
+// brent_dekker, event.rs:386-450.  interpolate(b).ok()?: the reference's bounds test (written for forward time) ends the search
+template <class Interp>
+bool brent_dekker(const EventState& es, Interp&& interp, double t_prev, double t_curr, double a, double b, double fa, double fb, double* t_event) {
+    const double rel_tol = 1e-12, abs_tol = 1e-14;
+    if (std::fabs(fa) < std::fabs(fb)) { std::swap(a, b); std::swap(fa, fb); }
+    double c = a, fc = fa, d = b - a, e = d;
+    for (int it = 0; it < 50; it++) {
+        if (fb == 0.0) { *t_event = b; return true; }
+        if (signum(fa) == signum(fb)) { a = c; fa = fc; c = b; fc = fb; d = b - a; e = d; }
+        if (std::fabs(fa) < std::fabs(fb)) { c = b; b = a; a = c; fc = fb; fb = fa; fa = fc; }
+        const double tol = rmax(abs_tol, rel_tol * std::fabs(b));
+        const double m = 0.5 * (a - b);
+        if (std::fabs(m) <= tol || fb == 0.0) { *t_event = b; return true; }
+        bool use_bis = true;
+        if (std::fabs(e) > tol && std::fabs(fa) > std::fabs(fb)) {
+            const double s = fb / fa;
+            double p, q;
+            if (a == c) {
+                p = 2.0 * m * s;
+                q = 1.0 - s;
+            } else {
+                const double q1 = fa / fc;
+                const double r = fb / fc;
+                p = s * (2.0 * m * q1 * (q1 - r) - (b - a) * (r - 1.0));
+                q = (q1 - 1.0) * (r - 1.0) * (s - 1.0);
+            }
+            double q_mod = q, p_mod = p;
+            if (q_mod > 0.0) p_mod = -p_mod; else q_mod = -q_mod;
+            if (std::fabs(2.0 * p_mod) < (3.0 * m * q_mod - std::fabs(tol * q_mod)) && p_mod < std::fabs(e * 0.5 * q_mod)) {
+                e = d;
+                d = p_mod / q_mod;
+                use_bis = false;
+            }
+        }
+        if (use_bis) { d = m; e = m; }
+        a = b;
+        fa = fb;
+        b = (std::fabs(d) > tol) ? (b + d) : (b + ((m > 0.0) ? tol : -tol));
+        if (b < t_prev || b > t_curr) return false;  // Err(OutOfBounds).ok()? -> None
+        Vec yb = interp(b);
+        fb = es.g(b, yb);
+        c = a;
+        fc = fa;
+    }
+    return false;
+}
+// detect_event, event.rs:318-384; returns true for ControlFlag::Terminate
+template <class Interp>
+bool detect_event(EventState& es, double t_curr, double t_prev, const Vec& y_curr, const Vec& y_prev, Interp&& interp, Rows& rows) {
+    const double g_curr = es.g(t_curr, y_curr);
+    if (!es.has_last) {
+        (void)es.g(t_prev, y_prev);
+        es.last_g = g_curr; es.has_last = true;
+        return false;
+    }
+    const double g_prev = es.last_g;
+    const bool sign_change = signum(g_prev) != signum(g_curr);
+    const bool direction_ok = es.direction > 0 ? (sign_change && g_prev < 0.0 && g_curr >= 0.0)
+                            : es.direction < 0 ? (sign_change && g_prev > 0.0 && g_curr <= 0.0) : sign_change;
+    if (direction_ok) {
+        double a = t_prev, b = t_curr, fa = g_prev, fb = g_curr;
+        if ((es.dir > 0.0 && a > b) || (es.dir < 0.0 && a < b)) { std::swap(a, b); std::swap(fa, fb); }
+        double t_event;
+        if (fa * fb <= 0.0 && brent_dekker(es, interp, t_prev, t_curr, a, b, fa, fb, &t_event)) {
+            Vec y_event = interp(t_event);
+            const bool push_point = rows.n_emit > 0 ? (std::fabs(t_event - rows.last_t) > 1e-14) : true;
+            if (push_point) rows.push(t_event, y_event);
+            es.count += 1;
+            if (es.terminate > 0 && es.count >= es.terminate) { es.last_g = g_curr; return true; }
+        }
+    }
+    es.last_g = g_curr;
+    return false;
 }
 
 // solve_ode, src/ode/solve_ivp.rs:116-277, for one trajectory
@@ -726,9 +824,14 @@ void solve_one(const deb_ode_problem* P, const SysInfo& si, const Tableau& tb, i
     m.h0 = P->opt.h0; m.h_min = P->opt.h_min; m.h_max = P->opt.h_max; m.max_steps = P->opt.max_steps;
     m.safety = P->opt.safety_factor; m.min_scale = P->opt.min_scale; m.max_scale = P->opt.max_scale;
     m.max_rejects = P->opt.max_rejects;
-    int evals = 0, acc = 0, rej = 0, n_emit = 0;
+    int evals = 0, acc = 0, rej = 0;
     int status = DEB_STATUS_COMPLETE;
-    double* ye = o.y_eval ? o.y_eval + (size_t)i * P->n_eval * n : nullptr;
+    const bool has_event = (P->event != DEB_EVENT_NONE);
+    const int row_cap = (has_event && P->row_capacity > 0) ? P->row_capacity : P->n_eval;
+    const bool per_step = (P->solout == DEB_SOLOUT_DEFAULT || P->solout == DEB_SOLOUT_DENSE || P->solout == DEB_SOLOUT_CROSSING);
+    Rows rows{o.y_eval ? o.y_eval + (size_t)i * row_cap * n : nullptr, o.t_out ? o.t_out + (size_t)i * row_cap : nullptr, n,
+              (per_step || has_event) ? row_cap : 0x7fffffff};
+    int& n_emit = rows.n_emit;
     auto finish = [&](int st, double t, const Vec& y) {
         if (o.status) o.status[i] = st;
         if (o.t_final) o.t_final[i] = t;
@@ -750,13 +853,16 @@ void solve_one(const deb_ode_problem* P, const SysInfo& si, const Tableau& tb, i
     auto interp = [&](double tv) { return tb.dp ? m.dp_interpolate(tv) : (tb.adaptive && tb.bi) ? m.ad_interpolate(tv) : m.fx_interpolate(tv); };
     PerStep ps;
     ps.mode = P->solout; ps.dense_n = P->dense_n; ps.comp = P->cross_component; ps.direction = P->cross_direction;
-    ps.threshold = P->cross_threshold; ps.cap = P->n_eval;
-    const bool per_step = (P->solout == DEB_SOLOUT_DEFAULT || P->solout == DEB_SOLOUT_DENSE || P->solout == DEB_SOLOUT_CROSSING);
-    double* to = o.t_out ? o.t_out + (size_t)i * P->n_eval : nullptr;
-    auto record = [&]() {
-        if (per_step) solout_per_step(ps, m.t, m.t_prev, m.y, interp, ye, to, n, &n_emit);
-        else if (even) solout_even(ev, m.t, m.t_prev, m.y, m.y_prev, interp, ye, n, &n_emit);
-        else solout_teval(te, m.t, m.t_prev, m.y, interp, ye, n, &n_emit);
+    ps.threshold = P->cross_threshold;
+    EventState es;
+    es.direction = P->event_direction; es.terminate = P->event_terminate; es.coef = P->event_coef; es.n = n; es.dir = dir;
+    // EventWrappedSolout::solout, event.rs:452-470: the base recorder first, then event detection; true = Terminate
+    auto record = [&]() -> bool {
+        if (per_step) solout_per_step(ps, m.t, m.t_prev, m.y, interp, rows);
+        else if (even) solout_even(ev, m.t, m.t_prev, m.y, m.y_prev, interp, rows);
+        else solout_teval(te, m.t, m.t_prev, m.y, interp, rows);
+        if (has_event) return detect_event(es, m.t, m.t_prev, m.y, m.y_prev, interp, rows);
+        return false;
     };
     record();  // :160
     const double eps10 = DBL_EPSILON * 10.0;
@@ -773,7 +879,7 @@ void solve_one(const deb_ode_problem* P, const SysInfo& si, const Tableau& tb, i
         }
         if (m.rejected) { rej += 1; continue; }  // :218-221
         acc += 1;
-        record();
+        if (record()) { status = DEB_STATUS_INTERRUPTED; break; }  // ControlFlag::Terminate, :255-260
         if (std::fabs(tf - m.t) <= eps10) break;  // :263
     }
     finish(status, m.t, m.y);
@@ -832,7 +938,10 @@ void solve_one_sde(const deb_sde_problem* P, const SdeSys& ss, const Tableau& tb
         Vec yc(1, y_curr);
         // linear interpolation, src/interpolate.rs:71-74 via stochastic.rs:177-190
         auto interp = [&](double tv) { double s = (tv - tp) / (t_curr - tp); Vec out(1, 0.0); out[0] += (1.0 - s) * y_prev; out[0] += s * y_curr; return out; };
-        solout_teval(te, t_curr, tp, yc, interp, ye, 1, &n_emit);
+        Rows rows{ye, nullptr, 1, 0x7fffffff};
+        rows.n_emit = n_emit;
+        solout_teval(te, t_curr, tp, yc, interp, rows);
+        n_emit = rows.n_emit;
     };
     emit(t, t_prev, y);
     const double eps10 = DBL_EPSILON * 10.0;

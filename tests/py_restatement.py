@@ -198,7 +198,103 @@ def make_per_step_solout(recorder, rows, interpolate):
     return solout
 
 
-def solve_dp(f, method, t0, tf, y0, rtol=1e-6, atol=1e-6, t_eval=(), even=None, recorder=None, h0=0.0, h_min=0.0, h_max=math.inf, max_steps=10000,
+def make_event_solout(base, event, rows, interpolate, dirn, bounds):
+    """EventWrappedSolout (src/solout/event.rs:300-470).  event = (g(t, y), direction in {0, +1, -1}, terminate count or 0);
+    bounds() -> (t_prev, t_curr) of the step for the reference's interpolate() bounds test.  Returns True to terminate."""
+    g, direction, terminate = event
+    st = dict(last=None, count=0)
+    rel_tol, abs_tol = 1e-12, 1e-14
+
+    def brent_dekker(a, b, fa, fb):
+        if abs(fa) < abs(fb):
+            a, b, fa, fb = b, a, fb, fa
+        c, fc = a, fa
+        d = b - a
+        e = d
+        for _ in range(50):
+            if fb == 0.0:
+                return b
+            if signum(fa) == signum(fb):
+                a, fa = c, fc
+                c, fc = b, fb
+                d = b - a
+                e = d
+            if abs(fa) < abs(fb):
+                c = b
+                b = a
+                a = c
+                fc = fb
+                fb = fa
+                fa = fc
+            tol = rmax(abs_tol, rel_tol * abs(b))
+            m = 0.5 * (a - b)
+            if abs(m) <= tol or fb == 0.0:
+                return b
+            use_bis = True
+            if abs(e) > tol and abs(fa) > abs(fb):
+                s_ = fb / fa
+                if a == c:
+                    p_ = 2.0 * m * s_
+                    q_ = 1.0 - s_
+                else:
+                    q1 = fa / fc
+                    r = fb / fc
+                    p_ = s_ * (2.0 * m * q1 * (q1 - r) - (b - a) * (r - 1.0))
+                    q_ = (q1 - 1.0) * (r - 1.0) * (s_ - 1.0)
+                if q_ > 0.0:
+                    p_ = -p_
+                else:
+                    q_ = -q_
+                if abs(2.0 * p_) < (3.0 * m * q_ - abs(tol * q_)) and p_ < abs(e * 0.5 * q_):
+                    e = d
+                    d = p_ / q_
+                    use_bis = False
+            if use_bis:
+                d = m
+                e = m
+            a, fa = b, fb
+            b = b + d if abs(d) > tol else b + (tol if m > 0.0 else -tol)
+            tp, tc = bounds()
+            if b < tp or b > tc:  # interpolate(b) -> Err(OutOfBounds) -> .ok()? -> None
+                return None
+            fb = g(b, interpolate(b))
+            c, fc = a, fa
+        return None
+
+    def solout(t_curr, t_prev, y_curr):
+        base(t_curr, t_prev, y_curr)
+        g_curr = g(t_curr, y_curr)
+        if st["last"] is None:
+            st["last"] = g_curr
+            return False
+        g_prev = st["last"]
+        sign_change = signum(g_prev) != signum(g_curr)
+        if direction > 0:
+            ok = sign_change and g_prev < 0.0 and g_curr >= 0.0
+        elif direction < 0:
+            ok = sign_change and g_prev > 0.0 and g_curr <= 0.0
+        else:
+            ok = sign_change
+        if ok:
+            a, b, fa, fb = t_prev, t_curr, g_prev, g_curr
+            if (dirn > 0 and a > b) or (dirn < 0 and a < b):
+                a, b, fa, fb = b, a, fb, fa
+            if fa * fb <= 0.0:
+                te = brent_dekker(a, b, fa, fb)
+                if te is not None:
+                    ye = interpolate(te)
+                    if not rows or abs(te - rows[-1][0]) > abs_tol:
+                        rows.append((te, ye))
+                    st["count"] += 1
+                    if terminate and st["count"] >= terminate:
+                        st["last"] = g_curr
+                        return True
+        st["last"] = g_curr
+        return False
+    return solout
+
+
+def solve_dp(f, method, t0, tf, y0, rtol=1e-6, atol=1e-6, t_eval=(), even=None, recorder=None, event=None, h0=0.0, h_min=0.0, h_max=math.inf, max_steps=10000,
              safety=0.9, min_scale=0.2, max_scale=10.0):
     """Returns dict(status, t, y, accepted, rejected, evals, rows=[(t, y)])."""
     T = TAB["DOPRI5" if method == "dopri5" else "DOP853"]
@@ -265,6 +361,8 @@ def solve_dp(f, method, t0, tf, y0, rtol=1e-6, atol=1e-6, t_eval=(), even=None, 
         solout = lambda tc, tp, yc: even_solout(tc, tp, yc, y_before)
     if recorder is not None:
         solout = make_per_step_solout(recorder, rows, interpolate)
+    if event is not None:
+        solout = make_event_solout(solout, event, rows, interpolate, dirn, lambda: (t_prev, t))
     solout(t, t_prev, y)
     status = "Complete"
     while True:
@@ -385,13 +483,15 @@ def solve_dp(f, method, t0, tf, y0, rtol=1e-6, atol=1e-6, t_eval=(), even=None, 
             rej += 1
             continue
         acc += 1
-        solout(t, t_prev, y)
+        if solout(t, t_prev, y):  # ControlFlag::Terminate (an event), solve_ivp.rs:255-260
+            status = "Interrupted"
+            break
         if abs(tf - t) <= EPS10:
             break
     return dict(status=status, t=t, y=y, accepted=acc, rejected=rej, evals=evals, rows=rows)
 
 
-def solve_fixed(f, method, h0, t0, tf, y0, t_eval=(), max_steps=10000, recorder=None):
+def solve_fixed(f, method, h0, t0, tf, y0, t_eval=(), max_steps=10000, recorder=None, event=None):
     T = TAB[method.upper()]
     c, A, b = T["C"], T["A"], T["B"]
     S = len(b)
@@ -446,6 +546,8 @@ def solve_fixed(f, method, h0, t0, tf, y0, t_eval=(), max_steps=10000, recorder=
 
     if recorder is not None:
         solout = make_per_step_solout(recorder, rows, interpolate)
+    if event is not None:
+        solout = make_event_solout(solout, event, rows, interpolate, dirn, lambda: (t_prev, t))
     solout(t, t_prev, y)
     steps = 0
     status = "Complete"
@@ -475,7 +577,9 @@ def solve_fixed(f, method, h0, t0, tf, y0, t_eval=(), max_steps=10000, recorder=
         y = yn
         dydt = f(t, y)
         evals += S
-        solout(t, t_prev, y)
+        if solout(t, t_prev, y):  # ControlFlag::Terminate (an event), solve_ivp.rs:255-260
+            status = "Interrupted"
+            break
         if abs(tf - t) <= EPS10:
             break
     return dict(status=status, t=t, y=y, accepted=steps, rejected=0, evals=evals, rows=rows)
@@ -509,7 +613,7 @@ ADAPTIVE_ORDER_FSAL = dict(rkf45=(5, False), cash_karp=(5, False), rkv655e=(6, T
                            rkv767e=(7, False), rkv877e=(8, False), rkv878e=(8, False), rkv988e=(9, False), rkv989e=(9, False))
 
 
-def solve_adaptive(f, method, t0, tf, y0, rtol=1e-6, atol=1e-6, t_eval=(), recorder=None, h0=0.0, h_min=0.0, h_max=math.inf, max_steps=10000,
+def solve_adaptive(f, method, t0, tf, y0, rtol=1e-6, atol=1e-6, t_eval=(), recorder=None, event=None, h0=0.0, h_min=0.0, h_max=math.inf, max_steps=10000,
                    max_rejects=100, safety=0.9, min_scale=0.2, max_scale=10.0):
     """Generic adaptive family (RKF45, Cash-Karp, Verner pairs): /root/reference/src/methods/erk/adaptive/ordinary.rs:16-211,
     dense output = the method's polynomial when it has one (:246-277) else cubic Hermite (:282-295), driven by
@@ -590,6 +694,8 @@ def solve_adaptive(f, method, t0, tf, y0, rtol=1e-6, atol=1e-6, t_eval=(), recor
 
     if recorder is not None:
         solout = make_per_step_solout(recorder, rows, interpolate)
+    if event is not None:
+        solout = make_event_solout(solout, event, rows, interpolate, dirn, lambda: (t_prev, t))
     solout(t, t_prev, y)
     status = "Complete"
     while True:
@@ -669,7 +775,9 @@ def solve_adaptive(f, method, t0, tf, y0, rtol=1e-6, atol=1e-6, t_eval=(), recor
             rej += 1
             continue
         acc += 1
-        solout(t, t_prev, y)
+        if solout(t, t_prev, y):  # ControlFlag::Terminate (an event), solve_ivp.rs:255-260
+            status = "Interrupted"
+            break
         if abs(tf - t) <= EPS10:
             break
     return dict(status=status, t=t, y=y, accepted=acc, rejected=rej, evals=evals, rows=rows)

@@ -132,6 +132,13 @@ def test_user_rhs_compiles_for_every_method_without_a_device(lib):
     for m in (E.dopri5(), E.dop853(), E.cash_karp(), E.rkv767e(), E.heun(0.01)):
         deb.check_ode(deb.LorenzSystem(10.0, 28.0, 8.0 / 3.0), m, deb.DEB_SOLOUT_DENSE)
     deb.check_ode(duffing, E.dopri5(), deb.DEB_SOLOUT_CROSSING)
+    # event detection wraps any recorder: linear event and an `impl Event` body
+    near_rest = deb.event_from_source(2, "return fmax(fabs(y[0]), fabs(y[1])) - 0.01;")
+    deb.check_ode(deb.HarmonicOscillator(1.0), E.rkf45(), deb.DEB_SOLOUT_T_EVAL, deb.LinearEvent(0.0, 0.0, [1.0, 0.0]))
+    deb.check_ode(duffing, E.dop853(), deb.DEB_SOLOUT_EVEN, near_rest)
+    deb.check_ode(deb.HarmonicOscillator(1.0), E.rk4(0.01), deb.DEB_SOLOUT_DEFAULT, near_rest)
+    with pytest.raises(ValueError, match="did not compile"):
+        deb.check_ode(deb.HarmonicOscillator(1.0), E.dopri5(), deb.DEB_SOLOUT_T_EVAL, deb.event_from_source(2, "return nonsense(y[0]);"))
 
 
 def test_no_cpu_fallback_without_a_device(lib):

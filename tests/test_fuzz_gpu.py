@@ -48,6 +48,8 @@ def random_case(seed):
     adaptive = bool(r.random() < 0.7)
     u = r.random()  # recorder kind; per-step recorders are compiled at first use, so they get a small method set
     per_step = 0.25 <= u < 0.5
+    has_event = bool(r.random() < 0.15)  # IVP::event(..) around whichever recorder; also compiled at first use
+    per_step = per_step or has_event     # (only restricts the method pool below)
     if adaptive:
         pool = ["dopri5", "rkf45"] if per_step else ADAPTIVE
         ctor = pool[int(r.integers(len(pool)))]
@@ -93,6 +95,13 @@ def random_case(seed):
             pts += [t0, tf, 0.5 * (t0 + tf), tf]
         r.shuffle(pts)
         ivp.t_eval(pts)
+    if has_event:
+        coef = r.uniform(-1.0, 1.0, dim)
+        coef[int(r.integers(dim))] = 1.0
+        c0 = -float(np.median(y0 @ coef)) + float(r.uniform(-0.3, 0.3))
+        ct = float(r.uniform(-0.2, 0.2)) if r.random() < 0.3 else 0.0
+        ivp.event(deb.LinearEvent(c0, ct, coef.tolist()), int(r.integers(-1, 2)), int(r.integers(1, 4)) if r.random() < 0.5 else None,
+                  max_event_rows=int(r.integers(2, 300)))
     return ivp.method(m), f"seed {seed}: {name} n={n} {ctor} t0={t0:.3g} tf={tf:.3g}"
 
 

@@ -272,6 +272,67 @@ def test_per_step_recorder_restatements_agree_bitwise():
         assert np.abs(sol.y[:, 0]).max() < 1e-12
 
 
+def _solve_py(f, meth, t0, tf, y0, tol, **kw):
+    if meth in ("dopri5", "dop853"):
+        return pr.solve_dp(f, meth, t0, tf, y0, rtol=tol, atol=tol, **kw)
+    if meth == "rk4":
+        kw.pop("even", None)
+        return pr.solve_fixed(f, "rk4", math.copysign(0.01, tf - t0), t0, tf, y0, **kw)
+    return pr.solve_adaptive(f, meth, t0, tf, y0, rtol=tol, atol=tol, **kw)
+
+
+def _method(meth, tol, t0=0.0, tf=1.0):
+    return E.rk4(math.copysign(0.01, tf - t0)) if meth == "rk4" else getattr(E, meth)().rtol(tol).atol(tol)
+
+
+def test_event_restatements_agree_bitwise():
+    """IVP::event (EventWrappedSolout + Brent-Dekker, src/solout/event.rs:300-470): C++ oracle vs the independent Python
+    restatement, bit for bit, on the patterns of the reference's own examples and tests; event times against closed forms."""
+    # examples/ode/03_logistic_growth: even(2.0).event(y - 0.9 m).terminal(), dop853 rtol = atol = 1e-12
+    k, mm = 1.0, 10.0
+    f = lambda t, y: [k * y[0] * (1.0 - y[0] / mm)]
+    g = lambda t, y: y[0] - 0.9 * mm
+    for meth in ("dop853", "dopri5", "rkv655e", "cash_karp"):
+        p = _solve_py(f, meth, 0.0, 10.0, [1.0], 1e-12, even=2.0, event=(g, 0, 1)) if meth in ("dop853", "dopri5") else None
+        c = ob.oracle_solve(deb.EnsembleIVP.ode(deb.LogisticEquation(k, mm), 0.0, 10.0, [[1.0]]).even(2.0)
+                            .event(deb.LinearEvent(-0.9 * mm, 0.0, [1.0]), terminate=1).method(_method(meth, 1e-12)))
+        sol = c[0]
+        assert sol.status == "Interrupted" and sol.t[:3].tolist() == [0.0, 2.0, 4.0] and len(sol.t) == 4
+        assert abs(sol.t[3] - math.log(81.0)) < 1e-8 and abs(sol.y[3, 0] - 9.0) < 1e-9  # y = m / (1 + 9 e^-t) = 0.9 m  at  t = ln 81
+        assert 4.39 < c.t_final[0] < 6.0  # the step that contains the event is kept (solver state), then Interrupted
+        if p is not None:
+            assert p["status"] == "Interrupted" and p["evals"] == c.evals[0] and p["t"] == c.t_final[0]
+            assert _same_bits([r[0] for r in p["rows"]], sol.t) and _same_bits([r[1] for r in p["rows"]], sol.y)
+    # tests/ode/errors.rs:12-28: y' = y with the terminal event t - 10 on a plain solve() (every step + the event row)
+    for meth in ("dopri5", "dop853", "rkf45", "rkv878e", "rk4"):
+        p = _solve_py(lambda t, y: [y[0]], meth, 0.0, 20.0, [1.0], 1e-6, recorder=("default",), event=(lambda t, y: t - 10.0, 0, 1))
+        c = ob.oracle_solve(deb.EnsembleIVP.ode(deb.ExponentialGrowth(1.0), 0.0, 20.0, [[1.0]])
+                            .event(deb.LinearEvent(-10.0, 1.0, [0.0]), terminate=1, max_event_rows=2500).method(_method(meth, 1e-6, 0.0, 20.0)))
+        sol = c[0]
+        assert sol.status == p["status"] == "Interrupted" and abs(sol.t[-1] - 10.0) <= 1e-11 and c.t_final[0] >= 10.0
+        assert len(sol.t) == c.accepted[0] + 2 or (len(sol.t) == c.accepted[0] + 1 and sol.t[-2] != 10.0)  # t0 + steps (+ event row unless it coincides)
+        assert _same_bits([r[0] for r in p["rows"]], sol.t) and _same_bits([r[1] for r in p["rows"]], sol.y)
+    # non-terminal and counted events on t_eval: zero crossings of cos t, direction filter, terminate_after(3)
+    hf = pr.harmonic(1.0)
+    te = [1.0, 2.0, 4.0, 7.5, 9.0]
+    for meth in ("dopri5", "dop853", "rkf45", "rkv766e", "rk4"):
+        for direction, term, want in ((0, 0, [0.5, 1.5, 2.5]), (1, 0, [1.5]), (-1, 0, [0.5, 2.5]), (0, 3, [0.5, 1.5, 2.5]), (0, 2, [0.5, 1.5])):
+            p = _solve_py(hf, meth, 0.0, 10.0, [1.0, 0.0], 1e-10, t_eval=te, event=(lambda t, y: y[0], direction, term))
+            c = ob.oracle_solve(deb.EnsembleIVP.ode(deb.HarmonicOscillator(1.0), 0.0, 10.0, [[1.0, 0.0]]).t_eval(te)
+                                .event(deb.LinearEvent(0.0, 0.0, [1.0, 0.0]), direction, term or None).method(_method(meth, 1e-10, 0.0, 10.0)))
+            sol = c[0]
+            assert sol.status == p["status"] == ("Interrupted" if term else "Complete")
+            assert _same_bits([r[0] for r in p["rows"]], sol.t) and _same_bits([r[1] for r in p["rows"]], sol.y)
+            ev_t = np.array([t for t in sol.t if t not in te])
+            np.testing.assert_allclose(ev_t / np.pi, want, atol=2e-6)
+    # backward time: the reference's interpolate() bounds test rejects every interior point, so Brent-Dekker gives up
+    # (`.ok()?`) unless an end point is an exact zero -- as written
+    p = pr.solve_dp(hf, "dopri5", 10.0, 0.0, [1.0, 0.0], rtol=1e-8, atol=1e-8, t_eval=[5.0], event=(lambda t, y: y[0], 0, 0))
+    c = ob.oracle_solve(deb.EnsembleIVP.ode(deb.HarmonicOscillator(1.0), 10.0, 0.0, [[1.0, 0.0]]).t_eval([5.0])
+                        .event(deb.LinearEvent(0.0, 0.0, [1.0, 0.0])).method(E.dopri5().rtol(1e-8).atol(1e-8)))
+    assert [r[0] for r in p["rows"]] == c[0].t.tolist() == [5.0]
+
+
 def test_even_solout_restatements_agree_bitwise():
     """EvenSolout (src/solout/even.rs:69-199): C++ oracle vs the independent Python restatement, bit for bit; and the
     documented output shape (t0 first, tf last, spacing dt)."""

@@ -635,6 +635,71 @@ def test_crossing_example_08_damped_oscillator_user_rhs():
     assert np.abs(s.y[:, 0]).max() < 1e-9
 
 
+# ------------------------------------------------------------------------------------------ events
+@pytest.mark.parametrize("meth", ["dopri5", "dop853", "rkf45", "rkv655e", "rk4"])
+def test_event_detection_bit_exact(meth):
+    """IVP::event(&e) (EventWrappedSolout + Brent-Dekker, src/solout/event.rs:300-470) around every recorder: rows, event
+    rows, counters and the Interrupted status, bitwise against the oracle."""
+    n = 200
+    def m():
+        return E.rk4(0.01) if meth == "rk4" else getattr(E, meth)().rtol(1e-9).atol(1e-9)
+    # examples/ode/03_logistic_growth as a sweep over the carrying capacity: even(2.0) + terminal event y - 9
+    cap = np.linspace(9.5, 30.0, n)
+    def p1():
+        return (deb.EnsembleIVP.ode(deb.LogisticEquation(1.0, cap), 0.0, 10.0, np.ones((n, 1))).even(2.0)
+                .event(deb.LinearEvent(-9.0, 0.0, [1.0]), terminate=1).method(m()))
+    g, c = p1().solve(), ob.oracle_solve(p1())
+    assert_same_solution(g, c)
+    assert (g.status == deb.DEB_STATUS_INTERRUPTED).all()
+    s = g[0]
+    assert s.status == "Interrupted" and abs(s.y[-1, 0] - 9.0) < 1e-6 and (np.diff(s.t) > 0).all()
+    # zero crossings of x on t_eval rows, every direction, terminate_after(k) and never
+    y0 = np.tile([1.0, 0.0], (n, 1)) * np.linspace(0.5, 2.0, n)[:, None]
+    kk = np.linspace(0.5, 4.0, n)
+    for direction, term in ((deb.CROSSING_BOTH, None), (deb.CROSSING_POSITIVE, None), (deb.CROSSING_NEGATIVE, 2), (deb.CROSSING_BOTH, 3)):
+        def p2():
+            return (deb.EnsembleIVP.ode(deb.HarmonicOscillator(kk), 0.0, 10.0, y0).t_eval([1.0, 2.0, 4.0, 7.5, 9.0, 10.0])
+                    .event(deb.LinearEvent(0.0, 0.0, [1.0, 0.0]), direction, term).method(m()))
+        g, c = p2().solve(), ob.oracle_solve(p2())
+        assert_same_solution(g, c)
+        assert set(np.unique(g.status)) <= {0, deb.DEB_STATUS_INTERRUPTED}
+    # plain solve() + event (every step + event rows), time-dependent event, capacity too small for some trajectories
+    def p3():
+        return (deb.EnsembleIVP.ode(lorenz(), 0.0, 4.0, ob.lorenz_ensemble_y0(n, seed=71))
+                .event(deb.LinearEvent(-25.0, 1.0, [0.0, 0.0, 1.0]), deb.CROSSING_BOTH, None, max_event_rows=300).method(m()))
+    g, c = p3().solve(), ob.oracle_solve(p3())
+    assert_same_solution(g, c)
+    # dense(2) and crossing bases; backward time (no events by the reference's bounds test)
+    for setter in (lambda ivp: ivp.dense(2, 900), lambda ivp: ivp.crossing(1, 0.0, deb.CROSSING_BOTH, 64)):
+        def p4():
+            return setter(deb.EnsembleIVP.ode(deb.HarmonicOscillator(kk), 0.0, 6.0, y0)).event(deb.LinearEvent(-0.25, 0.0, [1.0, 0.0])).method(m())
+        g, c = p4().solve(), ob.oracle_solve(p4())
+        assert_same_solution(g, c)
+    def p5():
+        mm = E.rk4(-0.01) if meth == "rk4" else m()
+        return deb.EnsembleIVP.ode(deb.HarmonicOscillator(kk), 6.0, 0.0, y0).t_eval([3.0, 0.0]).event(deb.LinearEvent(0.0, 0.0, [1.0, 0.0])).method(mm)
+    g, c = p5().solve(), ob.oracle_solve(p5())
+    assert_same_solution(g, c)
+
+
+def test_user_defined_event_function_vs_python_restatement():
+    """examples/ode/05_damped_pendulum pattern (linearised so that the right-hand side is IEEE-exact on both sides): a
+    user-defined right-hand side AND a user-defined terminal event g = max(|theta|, |omega|) - 0.01 on t_eval rows, rkf45():
+    bitwise against the independent Python restatement."""
+    import py_restatement as pr
+    pend = deb.ode_from_source(2, "dydt[0] = y[1]; dydt[1] = -(p[0] / p[1]) * y[1] - (p[2] / p[3]) * y[0];", params=[0.2, 1.0, 9.81, 1.0])
+    near_rest = deb.event_from_source(2, "return fmax(fabs(y[0]), fabs(y[1])) - 0.01;")
+    t_out = [0.0, 1.0, 3.0, 4.5, 6.9, 10.0]
+    g = (deb.EnsembleIVP.ode(pend, 0.0, 100.0, [[1.0, 0.0]]).t_eval(t_out).event(near_rest, terminate=1).method(E.rkf45()).solve())
+    f = lambda t, y: [y[1], -(0.2 / 1.0) * y[1] - (9.81 / 1.0) * y[0]]
+    p = pr.solve_adaptive(f, "rkf45", 0.0, 100.0, [1.0, 0.0], t_eval=t_out, event=(lambda t, y: pr.rmax(abs(y[0]), abs(y[1])) - 0.01, 0, 1))
+    s = g[0]
+    assert s.status == p["status"] == "Interrupted" and len(s.t) == 7 and s.t[:6].tolist() == t_out
+    assert (int(g.accepted[0]), int(g.rejected[0]), int(g.evals[0])) == (p["accepted"], p["rejected"], p["evals"])
+    assert np.array_equal(bits(s.t), bits([r[0] for r in p["rows"]])) and np.array_equal(bits(s.y), bits([r[1] for r in p["rows"]]))
+    assert abs(max(abs(s.y[-1, 0]), abs(s.y[-1, 1])) - 0.01) < 1e-6 and 40.0 < s.t[-1] < 60.0
+
+
 # ------------------------------------------------------------------------------------------ EvenSolout (SURVEY 8f rank 1)
 @pytest.mark.parametrize("meth", ["dopri5", "dop853", "rkf45", "rk4"])
 def test_even_solout_bit_exact(meth):
