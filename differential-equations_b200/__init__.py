@@ -48,13 +48,13 @@ DEB_MILSTEIN = 32
 DEB_SDE_OU, DEB_SDE_GBM = 0, 1
 DEB_STATUS_COMPLETE, DEB_STATUS_MAX_STEPS, DEB_STATUS_STEP_SIZE, DEB_STATUS_STIFFNESS, DEB_STATUS_BAD_INPUT = range(5)
 DEB_MEM_HOST, DEB_MEM_DEVICE = 0, 1
-DEB_SOLOUT_T_EVAL, DEB_SOLOUT_EVEN, DEB_SOLOUT_DEFAULT, DEB_SOLOUT_DENSE, DEB_SOLOUT_CROSSING = 0, 1, 2, 3, 4
+DEB_SOLOUT_T_EVAL, DEB_SOLOUT_EVEN, DEB_SOLOUT_DEFAULT, DEB_SOLOUT_DENSE, DEB_SOLOUT_CROSSING, DEB_SOLOUT_HYPERPLANE = 0, 1, 2, 3, 4, 5
 CROSSING_BOTH, CROSSING_POSITIVE, CROSSING_NEGATIVE = 0, 1, -1  # CrossingDirection, src/solout/mod.rs
 DEB_EVENT_NONE, DEB_EVENT_LINEAR = 0, 1
 DEB_MAX_DIM = 16
 DEB_STATUS_INTERRUPTED = 5
 DEB_OK, DEB_ERR_BAD_ARG, DEB_ERR_NO_DEVICE, DEB_ERR_CUDA, DEB_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
-DEB_ABI_VERSION = 6
+DEB_ABI_VERSION = 7
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -74,7 +74,9 @@ class OdeProblem(C.Structure):
                 ("solout", C.c_int32), ("dense_n", C.c_int32), ("even_dt", C.c_double),
                 ("cross_component", C.c_int32), ("cross_direction", C.c_int32), ("cross_threshold", C.c_double),
                 ("event", C.c_int32), ("event_direction", C.c_int32), ("event_terminate", C.c_int32), ("row_capacity", C.c_int32),
-                ("event_coef", C.c_double * (DEB_MAX_DIM + 2))]
+                ("event_coef", C.c_double * (DEB_MAX_DIM + 2)),
+                ("plane_dim", C.c_int32), ("plane_index", C.c_int32 * DEB_MAX_DIM), ("plane_point", C.c_double * DEB_MAX_DIM),
+                ("plane_normal", C.c_double * DEB_MAX_DIM)]
 
 
 class SdeProblem(C.Structure):
@@ -534,6 +536,16 @@ class EnsembleIVP:
         the component crosses the threshold, located by the reference's Newton iteration on the dense output."""
         return self._per_step(DEB_SOLOUT_CROSSING, max_rows, comp=component_idx, thr=threshold, direction=direction)
 
+    def hyperplane_crossing(self, point: Sequence[float], normal: Sequence[float], components: Sequence[int],
+                            direction: int = CROSSING_BOTH, max_rows: int = 64):  # ivp.rs:695
+        """`IVP::hyperplane_crossing(point, normal, extractor, direction)` (HyperplaneCrossingSolout, src/solout/hyperplane.rs):
+        rows where the selected state components (the extractor) cross the hyperplane through `point` with normal `normal`."""
+        if not (len(point) == len(normal) == len(components)) or len(components) < 1:
+            raise ValueError("point, normal and components must have the same, non-zero length")
+        self._per_step(DEB_SOLOUT_HYPERPLANE, max_rows, direction=direction)
+        self._plane = ([float(v) for v in point], [float(v) for v in normal], [int(v) for v in components])
+        return self
+
     def event(self, ev: EventSpec, direction: int = CROSSING_BOTH, terminate: Optional[int] = None, max_event_rows: int = 16):  # ivp.rs:662
         """`IVP::event(&e)`: wrap the current recorder with event detection (EventWrappedSolout, src/solout/event.rs).
         `direction`/`terminate` are the event's `EventConfig` (terminate=1 is `.terminal()`).  Without a recorder the base is
@@ -608,6 +620,11 @@ class EnsembleIVP:
             P.solout, P.even_dt = DEB_SOLOUT_EVEN, self._even_dt
         if self.kind == "ode" and self._recorder is not None:
             P.solout, _, P.dense_n, P.cross_component, P.cross_threshold, P.cross_direction = self._recorder
+            if P.solout == DEB_SOLOUT_HYPERPLANE:
+                pt, nrm, comps = self._plane
+                P.plane_dim = len(comps)
+                for q in range(len(comps)):
+                    P.plane_index[q], P.plane_point[q], P.plane_normal[q] = comps[q], pt[q], nrm[q]
         if self.kind == "ode" and self._event is not None:
             ev, P.event_direction, P.event_terminate, _ = self._event
             P.event, P.row_capacity = ev.event_id, rows_cap

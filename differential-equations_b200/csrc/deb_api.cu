@@ -566,7 +566,8 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P, deb_result* R) {
     if (int rc = check_options(P->opt)) return rc;
     TEvalPlan plan;
     const bool even = (P->solout == DEB_SOLOUT_EVEN);
-    const bool per_step = (P->solout == DEB_SOLOUT_DEFAULT || P->solout == DEB_SOLOUT_DENSE || P->solout == DEB_SOLOUT_CROSSING);
+    const bool per_step = (P->solout == DEB_SOLOUT_DEFAULT || P->solout == DEB_SOLOUT_DENSE || P->solout == DEB_SOLOUT_CROSSING ||
+                           P->solout == DEB_SOLOUT_HYPERPLANE);
     if (P->solout != DEB_SOLOUT_T_EVAL && !even && !per_step) return fail(DEB_ERR_BAD_ARG, "unknown solout mode");
     const bool has_event = (P->event != DEB_EVENT_NONE);
     const bool rec = per_step || has_event;  // rows with their own times: recorder kernels (compiled at first use)
@@ -584,6 +585,12 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P, deb_result* R) {
         if (P->solout == DEB_SOLOUT_CROSSING) {
             if (P->cross_component < 0 || P->cross_component >= dim) return fail(DEB_ERR_BAD_ARG, "crossing: component index out of range");
             if (P->cross_direction < -1 || P->cross_direction > 1) return fail(DEB_ERR_BAD_ARG, "crossing: direction must be -1, 0 or +1");
+        }
+        if (P->solout == DEB_SOLOUT_HYPERPLANE) {
+            if (P->plane_dim < 1 || P->plane_dim > dim) return fail(DEB_ERR_BAD_ARG, "hyperplane_crossing: plane_dim must be in 1..dim");
+            for (int q = 0; q < P->plane_dim; q++)
+                if (P->plane_index[q] < 0 || P->plane_index[q] >= dim) return fail(DEB_ERR_BAD_ARG, "hyperplane_crossing: component index out of range");
+            if (P->cross_direction < -1 || P->cross_direction > 1) return fail(DEB_ERR_BAD_ARG, "hyperplane_crossing: direction must be -1, 0 or +1");
         }
     } else if (even) {
         // EvenSolout::solout (even.rs:69-199): t0 is emitted by the call before the loop, then last + dt*direction,
@@ -655,6 +662,19 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P, deb_result* R) {
     a.event_direction = P->event_direction;
     a.event_terminate = P->event_terminate;
     for (int c = 0; c < DEB_MAX_DIM + 2; c++) a.event_coef[c] = P->event_coef[c];
+    if (P->solout == DEB_SOLOUT_HYPERPLANE) {
+        // HyperplaneCrossingSolout::new (hyperplane.rs:124-139): normal /= ||normal|| unless the norm is below epsilon
+        a.plane_dim = P->plane_dim;
+        double nsq = 0.0;
+        for (int q = 0; q < P->plane_dim; q++) nsq = nsq + P->plane_normal[q] * P->plane_normal[q];
+        const double norm = sqrt(nsq);
+        const double inv = 1.0 / norm;
+        for (int q = 0; q < P->plane_dim; q++) {
+            a.plane_index[q] = P->plane_index[q];
+            a.plane_point[q] = P->plane_point[q];
+            a.plane_normal[q] = (norm > 2.220446049250313e-16) ? P->plane_normal[q] * inv : P->plane_normal[q];
+        }
+    }
     a.dense_n = P->dense_n;
     a.cross_component = P->cross_component;
     a.cross_direction = P->cross_direction;
@@ -816,7 +836,8 @@ extern "C" int deb_check_ode(int32_t system_id, int32_t method, int32_t solout, 
         if (u >= (int)g_user_systems.size()) return fail(DEB_ERR_BAD_ARG, "unknown system id");
         us = g_user_systems[u].get();
     }
-    const bool rec = (solout == DEB_SOLOUT_DEFAULT || solout == DEB_SOLOUT_DENSE || solout == DEB_SOLOUT_CROSSING || event != DEB_EVENT_NONE);
+    const bool rec = (solout == DEB_SOLOUT_DEFAULT || solout == DEB_SOLOUT_DENSE || solout == DEB_SOLOUT_CROSSING ||
+                      solout == DEB_SOLOUT_HYPERPLANE || event != DEB_EVENT_NONE);
     if (!us && !rec) {  // built-in system with a row-plan recorder: compiled ahead of time
         int dim = 0, np = 0;
         if (!pick_ode(system_id, method, &dim, &np)) return fail(dim < 0 ? DEB_ERR_BAD_ARG : DEB_ERR_UNSUPPORTED, "unknown system or method id");

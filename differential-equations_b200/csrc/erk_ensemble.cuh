@@ -55,6 +55,10 @@ struct OdeKernelArgs {
     int event_direction;    // 0 both, +1 positive, -1 negative
     int event_terminate;    // stop after this many events (0 = never)
     double event_coef[DEB_MAX_DIM + 2];  // EvtLinear: g = c0 + c1*t + sum c[2+i]*y[i]
+    // HyperplaneCrossingSolout: signed distance of the extracted components to the plane (normal already normalised)
+    int plane_dim;
+    int plane_index[DEB_MAX_DIM];
+    double plane_point[DEB_MAX_DIM], plane_normal[DEB_MAX_DIM];
     double* y_eval;
     int* n_emitted;
     double* t_final;

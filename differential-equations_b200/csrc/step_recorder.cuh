@@ -3,6 +3,7 @@
 //     DenseSolout      /root/reference/src/solout/dense.rs:74-108      n-1 interpolated points per step + the step end
 //     CrossingSolout   /root/reference/src/solout/crossing.rs:115-263  component crossing a threshold, refined by the
 //                                                                      reference's Newton iteration on the dense output
+//     HyperplaneCrossingSolout  src/solout/hyperplane.rs:170-330       selected components crossing a hyperplane
 // Unlike t_eval / even(dt), the row times depend on the trajectory, so rows carry their own time (t_out) and the
 // number of rows is not known in advance: each trajectory owns `row_stride` row slots; pushes beyond that are counted
 // (n_emitted) but not stored.
@@ -19,7 +20,7 @@
 
 namespace deb {
 
-enum { REC_T_EVAL = 0, REC_EVEN = 1, REC_DEFAULT = 2, REC_DENSE = 3, REC_CROSSING = 4 };  // = deb_solout values
+enum { REC_T_EVAL = 0, REC_EVEN = 1, REC_DEFAULT = 2, REC_DENSE = 3, REC_CROSSING = 4, REC_HYPERPLANE = 5 };  // = deb_solout values
 
 // Event functions g(t, y) (the `Event` trait, src/solout/event.rs:60-70).  EvtNone: no event detection.
 struct EvtNone {
@@ -209,10 +210,48 @@ struct StepRecorder {
         return v;
     }
 
+    // signed_distance((extractor)(y)), hyperplane.rs:160-162: (pos - point) . normal, summed from zero in index order
+    __device__ __forceinline__ static double plane_distance(const OdeKernelArgs& a, const double (&y)[N]) {
+        double sum = 0.0;
+        for (int i = 0; i < a.plane_dim; i++) {
+            const double d = component(y, a.plane_index[i]) + (-1.0) * a.plane_point[i];
+            sum = sum + d * a.plane_normal[i];
+        }
+        return sum;
+    }
+
+    // find_crossing_newton of the hyperplane recorder, hyperplane.rs:262-330 (no step-size exit, derivative floor eps)
+    __device__ __forceinline__ bool newton_plane(const OdeKernelArgs& a, const DenseStep<Sys, Tab>& ds, double t_lower, double t_upper,
+                                                 double dist_lower, double dist_upper, double* t_out) const {
+        double t = t_lower - dist_lower * (t_upper - t_lower) / (dist_upper - dist_lower);
+        const double tolerance = DBL_EPSILON * 100.0;
+        double row[N];
+        double dist;
+        for (int it = 0; it < 10; it++) {
+            ds.eval(t, row);
+            dist = plane_distance(a, row);
+            if (fabs(dist) < tolerance) { *t_out = t; return true; }
+            const double delta_t = (t_upper - t_lower) * 1e-6;
+            ds.eval(t + delta_t, row);
+            const double dist_plus = plane_distance(a, row);
+            const double derivative = (dist_plus - dist) / delta_t;
+            if (fabs(derivative) < DBL_EPSILON) break;
+            const double t_next = t - dist / derivative;
+            t = (t_next < t_lower || t_next > t_upper) ? (t_lower + t_upper) / 2.0 : t_next;
+        }
+        ds.eval(t, row);
+        dist = plane_distance(a, row);
+        *t_out = t;
+        return fabs(dist) < tolerance * 10.0;
+    }
+
     // the solout call that precedes the loop (solve_ivp.rs:160): t_prev == t_curr == t0
     __device__ __forceinline__ void first(const OdeKernelArgs& a, long long traj, double t0, const double (&y0)[N], const double* p) {
         if (a.rec_mode == REC_CROSSING) {
             last_off = component(y0, a.cross_component) - a.cross_threshold;
+            have_last = true;
+        } else if (a.rec_mode == REC_HYPERPLANE) {
+            last_off = plane_distance(a, y0);
             have_last = true;
         } else if (a.rec_mode == REC_T_EVAL || a.rec_mode == REC_EVEN) {
             if (a.emit_t0) { push(a, traj, t0, y0); idx = 1; }  // the row plan starts with t0 (t_eval.rs:113-114 / even.rs:100-104)
@@ -349,6 +388,30 @@ struct StepRecorder {
                 }
             }
             last_off = off;
+            have_last = true;
+        } else if (a.rec_mode == REC_HYPERPLANE) {
+            const double dist = plane_distance(a, yn);
+            if (have_last) {
+                const double last = last_off;
+                const bool is_crossing = d_signum(last) != d_signum(dist) || (last == 0.0 && dist != 0.0) || (last != 0.0 && dist == 0.0);
+                if (is_crossing) {
+                    const bool record = (a.cross_direction > 0) ? (last < 0.0 && dist >= 0.0)
+                                      : (a.cross_direction < 0) ? (last > 0.0 && dist <= 0.0) : true;
+                    if (record) {
+                        ds.prepare(t, h, y, yn, k, dydt, p);
+                        prepared = true;
+                        double t_cross;
+                        if (!newton_plane(a, ds, t, t_new, last, dist, &t_cross)) {
+                            const double frac = -last / (dist - last);
+                            t_cross = t + frac * (t_new - t);
+                        }
+                        double row[N];
+                        ds.eval(t_cross, row);
+                        push(a, traj, t_cross, row);
+                    }
+                }
+            }
+            last_off = dist;
             have_last = true;
         } else {
             // t_eval / even(dt) through the host's row plan (see erk_ensemble.cuh: every planned point a step passes is emitted;

@@ -18,7 +18,7 @@ use differential_equations::{
 };
 
 // ------------------------------------------------------------------------------------------------ raw ABI
-pub const DEB_ABI_VERSION: i32 = 6;
+pub const DEB_ABI_VERSION: i32 = 7;
 
 #[repr(C)]
 #[derive(Clone, Copy)]
@@ -56,7 +56,7 @@ pub struct deb_ode_problem {
     pub device: i32,
     pub memspace: i32,
     pub stream: *mut c_void,
-    pub solout: i32, // 0 = t_eval, 1 = even(dt), 2 = every step (DefaultSolout), 3 = dense(n), 4 = crossing
+    pub solout: i32, // 0 = t_eval, 1 = even(dt), 2 = every step (DefaultSolout), 3 = dense(n), 4 = crossing, 5 = hyperplane_crossing
     pub dense_n: i32,
     pub even_dt: f64,
     pub cross_component: i32,
@@ -67,6 +67,10 @@ pub struct deb_ode_problem {
     pub event_terminate: i32, // EventConfig.terminate (0 = None)
     pub row_capacity: i32,    // rows per trajectory when an event is set
     pub event_coef: [f64; 18],
+    pub plane_dim: i32,          // hyperplane_crossing: number of extracted components
+    pub plane_index: [i32; 16],
+    pub plane_point: [f64; 16],
+    pub plane_normal: [f64; 16],
 }
 
 #[repr(C)]
@@ -246,6 +250,10 @@ impl<const N: usize> EnsembleIVP<N> {
             event_terminate: 0,
             row_capacity: 0,
             event_coef: [0.0; 18],
+            plane_dim: 0,
+            plane_index: [0; 16],
+            plane_point: [0.0; 16],
+            plane_normal: [0.0; 16],
         };
         let mut result = deb_result {
             struct_size: std::mem::size_of::<deb_result>(),

@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define DEB_ABI_VERSION 6
+#define DEB_ABI_VERSION 7
 #define DEB_MAX_DIM 16 /* widest state the register-resident kernels are instantiated for */
 
 typedef enum deb_error {
@@ -132,7 +132,9 @@ typedef enum deb_solout {
     /* per-step recorders: rows carry their own times (deb_result.t_out), n_eval is the row capacity per trajectory */
     DEB_SOLOUT_DEFAULT = 2,  /* the recorder of a plain IVP::solve(): every accepted step, src/solout/default.rs:54-75 */
     DEB_SOLOUT_DENSE = 3,    /* IVP::dense(n): DenseSolout, src/solout/dense.rs:74-108 */
-    DEB_SOLOUT_CROSSING = 4  /* IVP::crossing(component, threshold, direction): CrossingSolout, src/solout/crossing.rs:115-263 */
+    DEB_SOLOUT_CROSSING = 4, /* IVP::crossing(component, threshold, direction): CrossingSolout, src/solout/crossing.rs:115-263 */
+    DEB_SOLOUT_HYPERPLANE = 5 /* IVP::hyperplane_crossing(point, normal, extractor, direction): HyperplaneCrossingSolout,
+                                 src/solout/hyperplane.rs:170-330; the extractor is a selection of state components */
 } deb_solout;
 
 /* Options of ExplicitRungeKutta (src/methods/erk/mod.rs:135-144 defaults, :164-228 setters). */
@@ -188,6 +190,13 @@ typedef struct deb_ode_problem {
     int32_t row_capacity;    /* rows per trajectory in y_eval / t_out when an event is set (0 = n_eval); for t_eval / even(dt)
                                 recorders n_eval keeps its meaning (number of points / row-plan capacity) */
     double event_coef[DEB_MAX_DIM + 2];
+    /* DEB_SOLOUT_HYPERPLANE: the extractor picks components plane_index[0..plane_dim) of the state; rows are pushed where
+     * the signed distance sum_i (y[plane_index[i]] - plane_point[i]) * n_i changes sign, n = plane_normal normalised as in
+     * HyperplaneCrossingSolout::new; cross_direction filters the direction. */
+    int32_t plane_dim;
+    int32_t plane_index[DEB_MAX_DIM];
+    double plane_point[DEB_MAX_DIM];
+    double plane_normal[DEB_MAX_DIM];
 } deb_ode_problem;
 
 typedef struct deb_sde_problem {

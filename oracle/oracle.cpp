@@ -582,7 +582,40 @@ struct PerStep {
     double threshold = 0.0;
     bool have_last = false;
     double last_off = 0.0;
+    // HyperplaneCrossingSolout (src/solout/hyperplane.rs): extractor = component selection, normal normalised in new()
+    int plane_dim = 0;
+    int plane_index[DEB_MAX_DIM];
+    double plane_point[DEB_MAX_DIM], plane_normal[DEB_MAX_DIM];
+    double distance(const Vec& y) const {  // signed_distance, hyperplane.rs:160-162: pos.minus(point).dot(normal)
+        double sum = 0.0;
+        for (int i = 0; i < plane_dim; i++) {
+            const double d = y[plane_index[i]] + (-1.0) * plane_point[i];
+            sum = sum + d * plane_normal[i];
+        }
+        return sum;
+    }
 };
+// find_crossing_newton of the hyperplane recorder, hyperplane.rs:262-330
+template <class Interp>
+bool plane_newton(const PerStep& ps, Interp&& interp, double t_lower, double t_upper, double dist_lower, double dist_upper, double* t_found) {
+    double t = t_lower - dist_lower * (t_upper - t_lower) / (dist_upper - dist_lower);
+    const double tolerance = DBL_EPSILON * 100.0;
+    double dist;
+    for (int it = 0; it < 10; it++) {
+        dist = ps.distance(interp(t));
+        if (std::fabs(dist) < tolerance) { *t_found = t; return true; }
+        const double delta_t = (t_upper - t_lower) * 1e-6;
+        const double dist_plus = ps.distance(interp(t + delta_t));
+        const double derivative = (dist_plus - dist) / delta_t;
+        if (std::fabs(derivative) < DBL_EPSILON) break;
+        const double t_new = t - dist / derivative;
+        if (t_new < t_lower || t_new > t_upper) t = (t_lower + t_upper) / 2.0;
+        else t = t_new;
+    }
+    dist = ps.distance(interp(t));
+    *t_found = t;
+    return std::fabs(dist) < tolerance * 10.0;
+}
 template <class Interp>
 bool crossing_newton(const PerStep& ps, Interp&& interp, double t_lower, double t_upper, double off_lower, double off_upper, double* t_found) {
     double t = t_lower - off_lower * (t_upper - t_lower) / (off_upper - off_lower);
@@ -626,6 +659,25 @@ void solout_per_step(PerStep& ps, double t_curr, double t_prev, const Vec& y_cur
             }
         }
         push(t_curr, y_curr);
+    } else if (ps.mode == DEB_SOLOUT_HYPERPLANE) {  // hyperplane.rs:182-236
+        const double dist = ps.distance(y_curr);
+        if (ps.have_last) {
+            const double last = ps.last_off;
+            const bool is_crossing = signum(last) != signum(dist) || (last == 0.0 && dist != 0.0) || (last != 0.0 && dist == 0.0);
+            if (is_crossing) {
+                const bool record = ps.direction > 0 ? (last < 0.0 && dist >= 0.0) : ps.direction < 0 ? (last > 0.0 && dist <= 0.0) : true;
+                if (record) {
+                    double t_cross;
+                    if (!plane_newton(ps, interp, t_prev, t_curr, last, dist, &t_cross)) {
+                        const double frac = -last / (dist - last);
+                        t_cross = t_prev + frac * (t_curr - t_prev);
+                    }
+                    push(t_cross, interp(t_cross));
+                }
+            }
+        }
+        ps.last_off = dist;
+        ps.have_last = true;
     } else {  // crossing
         const double off = y_curr[ps.comp] - ps.threshold;
         if (ps.have_last) {
@@ -828,7 +880,8 @@ void solve_one(const deb_ode_problem* P, const SysInfo& si, const Tableau& tb, i
     int status = DEB_STATUS_COMPLETE;
     const bool has_event = (P->event != DEB_EVENT_NONE);
     const int row_cap = (has_event && P->row_capacity > 0) ? P->row_capacity : P->n_eval;
-    const bool per_step = (P->solout == DEB_SOLOUT_DEFAULT || P->solout == DEB_SOLOUT_DENSE || P->solout == DEB_SOLOUT_CROSSING);
+    const bool per_step = (P->solout == DEB_SOLOUT_DEFAULT || P->solout == DEB_SOLOUT_DENSE || P->solout == DEB_SOLOUT_CROSSING ||
+                           P->solout == DEB_SOLOUT_HYPERPLANE);
     Rows rows{o.y_eval ? o.y_eval + (size_t)i * row_cap * n : nullptr, o.t_out ? o.t_out + (size_t)i * row_cap : nullptr, n,
               (per_step || has_event) ? row_cap : 0x7fffffff};
     int& n_emit = rows.n_emit;
@@ -846,7 +899,7 @@ void solve_one(const deb_ode_problem* P, const SysInfo& si, const Tableau& tb, i
     bool ok = tb.dp ? m.dp_init(ode, t0, tf, y0, &evals) : tb.adaptive ? m.ad_init(ode, t0, tf, y0, &evals) : m.fx_init(ode, t0, tf, y0, &evals);
     if (!ok) { evals = 0; finish(DEB_STATUS_BAD_INPUT, t0, y0); return; }
     const bool even = (P->solout == DEB_SOLOUT_EVEN);
-    const bool no_points = even || P->solout == DEB_SOLOUT_DEFAULT || P->solout == DEB_SOLOUT_DENSE || P->solout == DEB_SOLOUT_CROSSING;
+    const bool no_points = even || per_step;
     TEval te(no_points ? nullptr : P->t_eval, no_points ? 0 : P->n_eval, t0, tf);
     Even ev(P->even_dt, t0, tf);
     // adaptive family without bi: cubic Hermite on (t_prev, t, y_prev, y, dydt_prev, dydt), adaptive/ordinary.rs:282-295
@@ -854,6 +907,17 @@ void solve_one(const deb_ode_problem* P, const SysInfo& si, const Tableau& tb, i
     PerStep ps;
     ps.mode = P->solout; ps.dense_n = P->dense_n; ps.comp = P->cross_component; ps.direction = P->cross_direction;
     ps.threshold = P->cross_threshold;
+    if (P->solout == DEB_SOLOUT_HYPERPLANE) {  // HyperplaneCrossingSolout::new, hyperplane.rs:124-139
+        ps.plane_dim = P->plane_dim;
+        double nsq = 0.0;
+        for (int q = 0; q < P->plane_dim; q++) nsq = nsq + P->plane_normal[q] * P->plane_normal[q];
+        const double norm = std::sqrt(nsq);
+        for (int q = 0; q < P->plane_dim; q++) {
+            ps.plane_index[q] = P->plane_index[q];
+            ps.plane_point[q] = P->plane_point[q];
+            ps.plane_normal[q] = (norm > DBL_EPSILON) ? P->plane_normal[q] * (1.0 / norm) : P->plane_normal[q];
+        }
+    }
     EventState es;
     es.direction = P->event_direction; es.terminate = P->event_terminate; es.coef = P->event_coef; es.n = n; es.dir = dir;
     // EventWrappedSolout::solout, event.rs:452-470: the base recorder first, then event detection; true = Terminate

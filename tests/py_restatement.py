@@ -143,7 +143,8 @@ def make_even_solout(dt, t0, tf, rows, interpolate):
 
 def make_per_step_solout(recorder, rows, interpolate):
     """DefaultSolout (src/solout/default.rs:54-75), DenseSolout (dense.rs:74-108), CrossingSolout (crossing.rs:115-263).
-    recorder = ("default",) | ("dense", n) | ("crossing", component, threshold, direction in {0, +1, -1})."""
+    recorder = ("default",) | ("dense", n) | ("crossing", component, threshold, direction in {0, +1, -1})
+             | ("hyperplane", point, normal, component indices, direction)  (src/solout/hyperplane.rs)."""
     kind = recorder[0]
     st = dict(last=None)
     eps = 2.220446049250313e-16
@@ -171,8 +172,48 @@ def make_per_step_solout(recorder, rows, interpolate):
         off = interpolate(t)[comp] - thr
         return t if abs(off) < tolerance * 10.0 else None
 
+    if kind == "hyperplane":  # HyperplaneCrossingSolout::new, src/solout/hyperplane.rs:124-139
+        _, pl_point, pl_normal, pl_comps, pl_dir = recorder
+        nsq = 0.0
+        for v in pl_normal:
+            nsq = nsq + v * v
+        norm = math.sqrt(nsq)
+        pl_n = [v * (1.0 / norm) for v in pl_normal] if norm > eps else list(pl_normal)
+
+        def distance(y):
+            sm = 0.0
+            for i, cidx in enumerate(pl_comps):
+                sm = sm + (y[cidx] + (-1.0) * pl_point[i]) * pl_n[i]
+            return sm
+
+        def plane_newton(t_lower, t_upper, d_lower, d_upper):
+            t = t_lower - d_lower * (t_upper - t_lower) / (d_upper - d_lower)
+            tolerance = eps * 100.0
+            for _ in range(10):
+                dist = distance(interpolate(t))
+                if abs(dist) < tolerance:
+                    return t
+                delta_t = (t_upper - t_lower) * 1e-6
+                derivative = (distance(interpolate(t + delta_t)) - dist) / delta_t
+                if abs(derivative) < eps:
+                    break
+                t_new = t - dist / derivative
+                t = (t_lower + t_upper) / 2.0 if (t_new < t_lower or t_new > t_upper) else t_new
+            return t if abs(distance(interpolate(t))) < tolerance * 10.0 else None
+
     def solout(t_curr, t_prev, y_curr):
-        if kind == "default":
+        if kind == "hyperplane":  # hyperplane.rs:182-236
+            dist = distance(y_curr)
+            last = st["last"]
+            if last is not None and (signum(last) != signum(dist) or (last == 0.0 and dist != 0.0) or (last != 0.0 and dist == 0.0)):
+                record = (last < 0.0 and dist >= 0.0) if pl_dir > 0 else (last > 0.0 and dist <= 0.0) if pl_dir < 0 else True
+                if record:
+                    tc = plane_newton(t_prev, t_curr, last, dist)
+                    if tc is None:
+                        tc = t_prev + (-last / (dist - last)) * (t_curr - t_prev)
+                    rows.append((tc, interpolate(tc)))
+            st["last"] = dist
+        elif kind == "default":
             rows.append((t_curr, list(y_curr)))
         elif kind == "dense":
             n = recorder[1]

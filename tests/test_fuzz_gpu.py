@@ -81,13 +81,17 @@ def random_case(seed):
         ivp.even(span / float(r.uniform(2.5, 40.0)))
     elif u < 0.5:  # per-step recorders (capacity sometimes too small on purpose)
         cap = int(r.integers(5, 600))
-        which = int(r.integers(3))
+        which = int(r.integers(4))
         if which == 0:
             ivp.every_step(cap)
         elif which == 1:
             ivp.dense(int(r.integers(0, 5)), cap)
-        else:
+        elif which == 2:
             ivp.crossing(int(r.integers(dim)), float(np.median(y0[:, 0]) + r.uniform(-0.5, 0.5)), int(r.integers(-1, 2)), int(r.integers(1, 40)))
+        else:
+            comps = sorted(r.choice(dim, size=int(r.integers(1, dim + 1)), replace=False).tolist())
+            ivp.hyperplane_crossing((np.median(y0[:, comps], axis=0) + r.uniform(-0.3, 0.3, len(comps))).tolist(),
+                                    r.uniform(-1.0, 1.0, len(comps)).tolist(), comps, int(r.integers(-1, 2)), int(r.integers(1, 40)))
     else:
         k = int(r.integers(0, 12))
         pts = r.uniform(min(t0, tf) - 0.2 * span, max(t0, tf) + 0.2 * span, k).tolist()

@@ -247,7 +247,10 @@ def test_per_step_recorder_restatements_agree_bitwise():
     lz = pr.lorenz(10.0, 28.0, 8.0 / 3.0)
     recs = ((("default",), lambda ivp: ivp.every_step(600)), (("dense", 3), lambda ivp: ivp.dense(3, 1800)),
             (("dense", 1), lambda ivp: ivp.dense(1, 600)), (("crossing", 0, 0.5, 0), lambda ivp: ivp.crossing(0, 0.5, 0, 64)),
-            (("crossing", 2, 20.0, 1), lambda ivp: ivp.crossing(2, 20.0, 1, 64)), (("crossing", 1, -1.0, -1), lambda ivp: ivp.crossing(1, -1.0, -1, 64)))
+            (("crossing", 2, 20.0, 1), lambda ivp: ivp.crossing(2, 20.0, 1, 64)), (("crossing", 1, -1.0, -1), lambda ivp: ivp.crossing(1, -1.0, -1, 64)),
+            (("hyperplane", [0.0, 0.0], [1.0, -1.0], [0, 1], 0), lambda ivp: ivp.hyperplane_crossing([0.0, 0.0], [1.0, -1.0], [0, 1], 0, 64)),
+            (("hyperplane", [1.0, 2.0, 20.0], [0.3, -0.2, 1.0], [0, 1, 2], 1), lambda ivp: ivp.hyperplane_crossing([1.0, 2.0, 20.0], [0.3, -0.2, 1.0], [0, 1, 2], 1, 64)),
+            (("hyperplane", [25.0], [-2.0], [2], -1), lambda ivp: ivp.hyperplane_crossing([25.0], [-2.0], [2], -1, 64)))
     for rec, setter in recs:
         for meth in ("dopri5", "dop853", "rkf45", "rkv655e", "rkv878e", "rk4"):
             if meth in ("dopri5", "dop853"):

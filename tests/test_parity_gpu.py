@@ -561,14 +561,17 @@ def test_verner_user_defined_rhs_bitwise():
 RECORDERS = {"every_step": lambda ivp, cap: ivp.every_step(cap), "dense3": lambda ivp, cap: ivp.dense(3, 3 * cap),
              "dense1": lambda ivp, cap: ivp.dense(1, cap), "cross_x_both": lambda ivp, cap: ivp.crossing(0, 0.5, deb.CROSSING_BOTH, 64),
              "cross_z_up": lambda ivp, cap: ivp.crossing(2, 25.0, deb.CROSSING_POSITIVE, 64),
-             "cross_y_down": lambda ivp, cap: ivp.crossing(1, -2.0, deb.CROSSING_NEGATIVE, 64)}
+             "cross_y_down": lambda ivp, cap: ivp.crossing(1, -2.0, deb.CROSSING_NEGATIVE, 64),
+             "plane_xy": lambda ivp, cap: ivp.hyperplane_crossing([0.0, 0.0], [1.0, -1.0], [0, 1], deb.CROSSING_BOTH, 64),
+             "plane_xyz_up": lambda ivp, cap: ivp.hyperplane_crossing([1.0, 2.0, 20.0], [0.3, -0.2, 1.0], [0, 1, 2], deb.CROSSING_POSITIVE, 64)}
 
 
 @pytest.mark.parametrize("rec", sorted(RECORDERS))
 @pytest.mark.parametrize("meth", ["dopri5", "dop853", "cash_karp", "rkv655e", "rkv878e", "rk4"])
 def test_per_step_recorders_bit_exact(meth, rec):
-    """DefaultSolout / DenseSolout / CrossingSolout (src/solout/default.rs, dense.rs, crossing.rs): rows with their own
-    times, Newton-refined crossings on each method's own dense output; kernels compiled at first use."""
+    """DefaultSolout / DenseSolout / CrossingSolout / HyperplaneCrossingSolout (src/solout/default.rs, dense.rs, crossing.rs,
+    hyperplane.rs): rows with their own times, Newton-refined crossings on each method's own dense output; kernels compiled
+    at first use."""
     y0 = ob.lorenz_ensemble_y0(300, seed=61)
     def prob():
         m = E.rk4(0.01) if meth == "rk4" else getattr(E, meth)().rtol(1e-7).atol(1e-8)
