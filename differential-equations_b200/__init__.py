@@ -45,7 +45,7 @@ DEB_DOPRI5, DEB_DOP853, DEB_RKF45, DEB_CASH_KARP = 16, 17, 18, 19
 DEB_MILSTEIN = 32
 (DEB_SYS_EXPONENTIAL, DEB_SYS_LINEAR, DEB_SYS_HARMONIC, DEB_SYS_LOGISTIC, DEB_SYS_VAN_DER_POL, DEB_SYS_LORENZ,
  DEB_SYS_BRUSSELATOR, DEB_SYS_ROBERTSON) = range(8)
-DEB_SDE_OU, DEB_SDE_GBM = 0, 1
+DEB_SDE_OU, DEB_SDE_GBM, DEB_SDE_HESTON = 0, 1, 2
 DEB_STATUS_COMPLETE, DEB_STATUS_MAX_STEPS, DEB_STATUS_STEP_SIZE, DEB_STATUS_STIFFNESS, DEB_STATUS_BAD_INPUT = range(5)
 DEB_MEM_HOST, DEB_MEM_DEVICE = 0, 1
 DEB_SOLOUT_T_EVAL, DEB_SOLOUT_EVEN, DEB_SOLOUT_DEFAULT, DEB_SOLOUT_DENSE, DEB_SOLOUT_CROSSING, DEB_SOLOUT_HYPERPLANE = 0, 1, 2, 3, 4, 5
@@ -274,10 +274,13 @@ def event_from_source(dim: int, event_body: str, lib=None) -> EventSpec:
 class SdeSystem:
     system_id: int
     params: np.ndarray
+    dim: int = 1
 
 
 def OrnsteinUhlenbeck(theta, mu, sigma): return SdeSystem(DEB_SDE_OU, _params(theta, mu, sigma))
 def GeometricBrownianMotion(mu, sigma): return SdeSystem(DEB_SDE_GBM, _params(mu, sigma))
+def HestonModel(mu, kappa, theta, sigma, rho):  # examples/sde/02_heston_model/main.rs: y = (price, variance)
+    return SdeSystem(DEB_SDE_HESTON, _params(mu, kappa, theta, sigma, rho), 2)
 
 
 def _params(*cols) -> np.ndarray:
@@ -480,7 +483,7 @@ class EnsembleIVP:
             if y0s.ndim != 2 or y0s.shape[1] != system.dim:
                 raise ValueError(f"y0 must have shape (N, {system.dim})")
         else:
-            y0s = y0s.reshape(-1)
+            y0s = y0s.reshape(-1, system.dim) if system.dim > 1 else y0s.reshape(-1)
         self.y0s = y0s
         self._t_eval = np.zeros(0)
         self._even_dt = 0.0
@@ -599,10 +602,10 @@ class EnsembleIVP:
             P.system, P.method, P.dim = sysm.system_id, self._method.method_id, dim
             params = np.ascontiguousarray(sysm.params, dtype=np.float64)
         else:
-            dim = 1
+            dim = self.system.dim
             P = SdeProblem()
             P.struct_size = C.sizeof(SdeProblem)
-            P.system, P.method, P.dim = self.system.system_id, self._method.method_id, 1
+            P.system, P.method, P.dim = self.system.system_id, self._method.method_id, dim
             params = np.ascontiguousarray(self.system.params, dtype=np.float64)
             P.y0_shared = 0
             P.seed, P.path_offset = self.seed, self.path_offset
@@ -651,7 +654,7 @@ class EnsembleIVP:
 
     def wrap_result(self, arrs, rows, res) -> EnsembleSolution:
         n = int(self.y0s.shape[0])
-        dim = self.system.dim if self.kind == "ode" else 1
+        dim = self.system.dim
         sol = EnsembleSolution(n, dim, rows, arrs["y_eval"], arrs["n_emitted"], arrs["t_final"], arrs["y_final"],
                                arrs["status"], arrs["accepted"], arrs["rejected"], arrs["evals"], res.kernel_ms, res.total_ms)
         if self._even_dt > 0.0:

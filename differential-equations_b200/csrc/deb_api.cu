@@ -854,12 +854,13 @@ extern "C" int deb_solve_sde(const deb_sde_problem* P, deb_result* R) {
     if (P->struct_size != sizeof(deb_sde_problem) || R->struct_size != sizeof(deb_result))
         return fail(DEB_ERR_BAD_ARG, "struct_size mismatch (ABI version skew)");
     sde_launch_fn launch = nullptr;
-    int np = 0;
+    int np = 0, dim = 1;
     if (P->system == DEB_SDE_OU) { launch = pick_sde_method<deb::SdeOU>(P->method); np = deb::SdeOU::NP; }
     else if (P->system == DEB_SDE_GBM) { launch = pick_sde_method<deb::SdeGBM>(P->method); np = deb::SdeGBM::NP; }
+    else if (P->system == DEB_SDE_HESTON) { launch = pick_sde_method<deb::SdeHeston>(P->method); np = deb::SdeHeston::NP; dim = deb::SdeHeston::DIM; }
     else return fail(DEB_ERR_BAD_ARG, "unknown SDE system id");
     if (!launch) return fail(DEB_ERR_UNSUPPORTED, "SDE ensembles take a fixed-step method id or DEB_MILSTEIN");
-    if (P->dim != 1 || P->n_params != np) return fail(DEB_ERR_BAD_ARG, "dim / n_params do not match the SDE system");
+    if (P->dim != dim || P->n_params != np) return fail(DEB_ERR_BAD_ARG, "dim / n_params do not match the SDE system");
     if (P->n_traj < 0 || P->n_eval < 0) return fail(DEB_ERR_BAD_ARG, "negative size");
     if (P->n_traj > 0 && (!P->y0 || !P->params)) return fail(DEB_ERR_BAD_ARG, "NULL y0/params");
     if (int rc = check_options(P->opt)) return rc;
@@ -884,15 +885,15 @@ extern "C" int deb_solve_sde(const deb_sde_problem* P, deb_result* R) {
     memset(&a, 0, sizeof a);
     DevBuf d_y0, d_params;
     // y0: [n_traj] in `memspace`, or ONE value in HOST memory when y0_shared; params likewise (see the header)
-    double y0_one = 0.0;
+    double y0_one[DEB_MAX_DIM];
     if (P->y0_shared) {
-        y0_one = P->y0[0];
-        DEB_CUDA(d_y0.alloc(sizeof(double)));
-        DEB_CUDA(cudaMemcpyAsync(d_y0.p, &y0_one, sizeof(double), cudaMemcpyHostToDevice, st));
+        for (int c = 0; c < dim; c++) y0_one[c] = P->y0[c];
+        DEB_CUDA(d_y0.alloc(sizeof(double) * dim));
+        DEB_CUDA(cudaMemcpyAsync(d_y0.p, y0_one, sizeof(double) * dim, cudaMemcpyHostToDevice, st));
         a.y0 = d_y0.as<double>();
     } else if (host) {
-        DEB_CUDA(d_y0.alloc(sizeof(double) * (size_t)n));
-        DEB_CUDA(cudaMemcpyAsync(d_y0.p, P->y0, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+        DEB_CUDA(d_y0.alloc(sizeof(double) * (size_t)n * dim));
+        DEB_CUDA(cudaMemcpyAsync(d_y0.p, P->y0, sizeof(double) * (size_t)n * dim, cudaMemcpyHostToDevice, st));
         a.y0 = d_y0.as<double>();
     } else {
         a.y0 = P->y0;
@@ -907,7 +908,7 @@ extern "C" int deb_solve_sde(const deb_sde_problem* P, deb_result* R) {
     } else {
         a.params = P->params;
     }
-    a.y0_stride = P->y0_shared ? 0 : 1;
+    a.y0_stride = P->y0_shared ? 0 : dim;
     a.params_stride = P->params_shared ? 0 : np;
     a.n_traj = n;
     a.path_offset = P->path_offset;
@@ -928,7 +929,7 @@ extern "C" int deb_solve_sde(const deb_sde_problem* P, deb_result* R) {
     a.row_stride = P->n_eval;
     a.emit_t0 = plan.emit_t0 ? 1 : 0;
     ResultStage rs;
-    if (int rc = rs.setup(R, host, n, P->n_eval, 1)) return rc;
+    if (int rc = rs.setup(R, host, n, P->n_eval, dim)) return rc;
     a.y_eval = rs.dev.y_eval;
     a.n_emitted = rs.dev.n_emitted;
     a.t_final = rs.dev.t_final;
@@ -941,7 +942,7 @@ extern "C" int deb_solve_sde(const deb_sde_problem* P, deb_result* R) {
     if (int rc = launch(a, di.sms, st)) return rc;
     if (host) {
         DEB_CUDA(cudaEventRecord(ev[2], st));
-        if (int rc = rs.copy_back(R, n, P->n_eval, 1, st)) return rc;
+        if (int rc = rs.copy_back(R, n, P->n_eval, dim, st)) return rc;
         DEB_CUDA(cudaEventRecord(ev[3], st));
         DEB_CUDA(cudaStreamSynchronize(st));
         DEB_CUDA(cudaEventElapsedTime(&R->kernel_ms, ev[1], ev[2]));

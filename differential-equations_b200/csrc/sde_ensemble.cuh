@@ -1,4 +1,4 @@
-// sde_ensemble.cuh -- fixed-step stochastic ERK ensembles (Euler-Maruyama = euler(h) on an SDE), scalar state.
+// sde_ensemble.cuh -- fixed-step stochastic ERK ensembles (Euler-Maruyama = euler(h) on an SDE), diagonal noise.
 //
 // Fuses, per path (one per thread, everything in registers, zero HBM traffic per step):
 //     solve_sde loop             /root/reference/src/sde/solve_ivp.rs:158-287
@@ -14,7 +14,7 @@ namespace deb {
 
 struct SdeKernelArgs {
     const double* y0;
-    int y0_stride;       // 1, or 0 when one y0 is shared by all paths
+    int y0_stride;       // DIM, or 0 when one y0 is shared by all paths
     const double* params;
     int params_stride;   // NP, or 0 when shared
     double pc[8];        // the shared parameter set by value (params == nullptr)
@@ -36,10 +36,10 @@ struct SdeKernelArgs {
 };
 
 // MILSTEIN: derivative-free Milstein step (/root/reference/src/methods/milstein.rs:107-180) instead of the stochastic ERK step
-// (Tab is then unused).
+// (Tab is then unused).  Vector states with diagonal noise: component c of step s uses normal number s*DIM + c.
 template <class Sde, class Tab, int BLOCK, bool MILSTEIN = false>
 __global__ void __launch_bounds__(BLOCK) sde_ensemble_kernel(const SdeKernelArgs a) {
-    constexpr int NP = Sde::NP, S = Tab::S;
+    constexpr int N = Sde::DIM, NP = Sde::NP, S = Tab::S;
     const double t0 = a.t0, tf = a.tf;
     const double dir = d_signum(tf - t0);
     const double eps10 = DBL_EPSILON * 10.0;
@@ -50,27 +50,33 @@ __global__ void __launch_bounds__(BLOCK) sde_ensemble_kernel(const SdeKernelArgs
         double p[NP > 0 ? NP : 1];
 #pragma unroll
         for (int q = 0; q < NP; q++) p[q] = a.params ? a.params[traj * a.params_stride + q] : a.pc[q];
-        double y = a.y0[traj * a.y0_stride];
+        double y[N], dydt[N];
+#pragma unroll
+        for (int c = 0; c < N; c++) { y[c] = a.y0[traj * a.y0_stride + c]; dydt[c] = 0.0; }
         const unsigned long long path = (unsigned long long)(a.path_offset + traj);
         int steps = 0, evals = 0, n_emit = 0, idx = 0, fin = -1;
-        double t = t0, dydt = 0.0;
+        double t = t0;
         // ---- init, stochastic.rs:18-65
         double h = a.h0;
         if (h == 0.0) h = fabs(tf - t0) / 100.0;
         if (!validate_step_size_parameters(h, a.h_min, a.h_max, t0, tf)) {
             fin = DEB_STATUS_BAD_INPUT;
         } else {
-            dydt = Sde::drift(t, y, p);
+            Sde::drift(t, y, dydt, p);
             evals = MILSTEIN ? 1 : 2;  // ERK: drift + diffusion (the initial diffusion value is not used); Milstein: drift only
             if (a.emit_t0) {
-                if (a.y_eval) a.y_eval[traj * a.row_stride] = y;
+                if (a.y_eval) {
+#pragma unroll
+                    for (int c = 0; c < N; c++) a.y_eval[(traj * a.row_stride) * N + c] = y[c];
+                }
                 n_emit = 1;
                 idx = 1;
             }
         }
         double te = (idx < a.n_rows) ? a.t_rows[idx] : te_none;
         double h_cached = h, sqrt_h = sqrt(h);
-        double z_odd = 0.0;
+        double z_odd = 0.0;                          // the odd normal of the last Philox call ...
+        unsigned long long odd_pair = ~0ull;         // ... and its pair index
         while (fin < 0) {
             if ((t + h - tf) * dir > 0.0) {  // solve_ivp.rs:211-227
                 const double h_new = tf - t;
@@ -78,64 +84,113 @@ __global__ void __launch_bounds__(BLOCK) sde_ensemble_kernel(const SdeKernelArgs
                 h = h_new;
             }
             if (steps >= a.max_steps) { fin = DEB_STATUS_MAX_STEPS; break; }  // stochastic.rs:74-83
-            const unsigned long long q = (unsigned long long)steps;       // normal index of this step (dim = 1)
+            const unsigned long long q0 = (unsigned long long)steps * N;  // first normal index of this step
             steps += 1;
             if (h != h_cached) { h_cached = h; sqrt_h = sqrt(h); }
-            double z;
-            if ((q & 1ull) == 0) normal_pair(a.seed, path, q >> 1, &z, &z_odd);
-            else z = z_odd;
-            const double dw = sqrt_h * z;  // noise(h, dw)
-            double y_next;
+            double dw[N];  // noise(h, dw)
+            if constexpr (N % 2 == 0) {
+                // even dimension: the step's normals are whole Philox pairs
+#pragma unroll
+                for (int c = 0; c < N; c += 2) {
+                    double ze, zo;
+                    normal_pair(a.seed, path, (q0 + c) >> 1, &ze, &zo);
+                    dw[c] = sqrt_h * ze;
+                    dw[c + 1] = sqrt_h * zo;
+                }
+            } else if constexpr (N == 1) {
+                // one normal per step: every other step reuses the odd normal of the previous call
+                double z;
+                if ((q0 & 1ull) == 0) normal_pair(a.seed, path, q0 >> 1, &z, &z_odd);
+                else z = z_odd;
+                dw[0] = sqrt_h * z;
+            } else {
+#pragma unroll
+                for (int c = 0; c < N; c++) {
+                    const unsigned long long q = q0 + c;
+                    double z;
+                    if ((q & 1ull) == 0) { normal_pair(a.seed, path, q >> 1, &z, &z_odd); odd_pair = q >> 1; }
+                    else if (odd_pair == (q >> 1)) z = z_odd;
+                    else { double ze; normal_pair(a.seed, path, q >> 1, &ze, &z); }
+                    dw[c] = sqrt_h * z;
+                }
+            }
+            Sde::mix(dw, p);
+            double y_next[N], g[N];
+            Sde::diffusion(t, y, g, p);  // stochastic.rs:113-115 / milstein.rs:127-130
             if (MILSTEIN) {
-                const double g = Sde::diffusion(t, y, p);
-                const double g_aux = Sde::diffusion(t, y + sqrt_h * g, p);  // b(t_n, y_n + b sqrt(h))
+                double y_aux[N], g_aux[N];
+#pragma unroll
+                for (int c = 0; c < N; c++) y_aux[c] = y[c] + sqrt_h * g[c];  // b(t_n, y_n + b sqrt(h))
+                Sde::diffusion(t, y_aux, g_aux, p);
                 const double factor = 1.0 / (2.0 * sqrt_h);
-                const double milstein_term = ((g_aux - g) * (dw * dw - h)) * factor;  // milstein.rs:148-156
-                y_next = ((y + dydt * h) + g * dw) + milstein_term;                   // milstein.rs:158-170
+#pragma unroll
+                for (int c = 0; c < N; c++) {
+                    const double milstein_term = ((g_aux[c] - g[c]) * (dw[c] * dw[c] - h)) * factor;  // milstein.rs:148-156
+                    y_next[c] = ((y[c] + dydt[c] * h) + g[c] * dw[c]) + milstein_term;                // milstein.rs:158-170
+                }
                 evals += 3;  // diffusion, auxiliary diffusion, new drift
             } else {
-            double k[S];
-            k[0] = dydt;
+                double k[S][N];
 #pragma unroll
-            for (int i = 1; i < S; i++) {  // drift stages, stochastic.rs:96-104
-                double ys = y;
+                for (int c = 0; c < N; c++) k[0][c] = dydt[c];
 #pragma unroll
-                for (int j = 0; j < i; j++) {
-                    if (Tab::a(i, j) != 0.0) ys = ys + (Tab::av(i, j) * h) * k[j];
+                for (int i = 1; i < S; i++) {  // drift stages, stochastic.rs:96-104
+                    double ys[N];
+#pragma unroll
+                    for (int c = 0; c < N; c++) ys[c] = y[c];
+#pragma unroll
+                    for (int j = 0; j < i; j++) {
+                        if (Tab::a(i, j) != 0.0) {
+                            const double ah = Tab::av(i, j) * h;
+#pragma unroll
+                            for (int c = 0; c < N; c++) ys[c] = ys[c] + ah * k[j][c];
+                        }
+                    }
+                    Sde::drift(t + Tab::cv(i) * h, ys, k[i], p);
                 }
-                k[i] = Sde::drift(t + Tab::cv(i) * h, ys, p);
-            }
-            double drift_inc = 0.0;  // stochastic.rs:107-110
 #pragma unroll
-            for (int i = 0; i < S; i++) {
-                if (Tab::b(i) != 0.0) drift_inc = __dadd_rn(drift_inc, (Tab::bv(i) * h) * k[i]);
-            }
-            const double g = Sde::diffusion(t, y, p);  // stochastic.rs:113-115
-            y_next = (y + drift_inc) + g * dw;         // stochastic.rs:122-128 (coefficients 1.0); dw = noise(h), :118-119
-            evals += S + 1;  // S-1 drift stages + diffusion + new drift
+                for (int c = 0; c < N; c++) {
+                    double drift_inc = 0.0;  // stochastic.rs:107-110
+#pragma unroll
+                    for (int i = 0; i < S; i++) {
+                        if (Tab::b(i) != 0.0) drift_inc = __dadd_rn(drift_inc, (Tab::bv(i) * h) * k[i][c]);
+                    }
+                    y_next[c] = (y[c] + drift_inc) + g[c] * dw[c];  // stochastic.rs:122-128 (coefficients 1.0)
+                }
+                evals += S + 1;  // S-1 drift stages + diffusion + new drift
             }
             const double t_new = t + h;
-            const double d_new = Sde::drift(t_new, y_next, p);
+            double d_new[N];
+            Sde::drift(t_new, y_next, d_new, p);
             while ((dir > 0.0) ? (te <= t_new) : (te >= t_new)) {
-                double row;
-                if (te == t_new) row = y_next;
-                else {
+                double row[N];
+                if (te == t_new) {
+#pragma unroll
+                    for (int c = 0; c < N; c++) row[c] = y_next[c];
+                } else {
                     const double s = (te - t) / (t_new - t);
-                    row = __dadd_rn(0.0, (1.0 - s) * y) + s * y_next;
+#pragma unroll
+                    for (int c = 0; c < N; c++) row[c] = __dadd_rn(0.0, (1.0 - s) * y[c]) + s * y_next[c];
                 }
-                if (a.y_eval) a.y_eval[traj * a.row_stride + n_emit] = row;
+                if (a.y_eval) {
+#pragma unroll
+                    for (int c = 0; c < N; c++) a.y_eval[(traj * a.row_stride + n_emit) * N + c] = row[c];
+                }
                 n_emit += 1;
                 idx += 1;
                 te = (idx < a.n_rows) ? a.t_rows[idx] : te_none;
             }
             t = t_new;
-            y = y_next;
-            dydt = d_new;
+#pragma unroll
+            for (int c = 0; c < N; c++) { y[c] = y_next[c]; dydt[c] = d_new[c]; }
             if (fabs(tf - t) <= eps10) fin = DEB_STATUS_COMPLETE;
         }
         if (a.status) a.status[traj] = fin;
         if (a.t_final) a.t_final[traj] = t;
-        if (a.y_final) a.y_final[traj] = y;
+        if (a.y_final) {
+#pragma unroll
+            for (int c = 0; c < N; c++) a.y_final[traj * N + c] = y[c];
+        }
         if (a.accepted) a.accepted[traj] = steps;
         if (a.rejected) a.rejected[traj] = 0;
         if (a.evals) a.evals[traj] = evals;

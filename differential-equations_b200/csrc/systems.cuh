@@ -64,16 +64,31 @@ struct SysRobertson {  // systems.rs:161-173 (stiff; the reference tests DOP853/
     }
 };
 
-// Scalar SDEs (`SDE::drift` / `SDE::diffusion`, /root/reference/src/sde/sde.rs:16-52)
+// SDEs with diagonal noise (`SDE::drift` / `SDE::diffusion`, /root/reference/src/sde/sde.rs:16-52).  `mix` is what the
+// system's `SDE::noise` does with the independent Wiener increments of the library's Philox stream.
 struct SdeOU {  // examples/sde/03_ornstein_uhlenbeck/main.rs:42-49
-    static constexpr int NP = 3;
-    __device__ __forceinline__ static double drift(double, double y, const double* p) { return p[0] * (p[1] - y); }
-    __device__ __forceinline__ static double diffusion(double, double, const double* p) { return p[2]; }
+    static constexpr int DIM = 1, NP = 3;
+    __device__ __forceinline__ static void drift(double, const double* y, double* d, const double* p) { d[0] = p[0] * (p[1] - y[0]); }
+    __device__ __forceinline__ static void diffusion(double, const double*, double* g, const double* p) { g[0] = p[2]; }
+    __device__ __forceinline__ static void mix(double*, const double*) {}
 };
 struct SdeGBM {  // src/sde/solve_ivp.rs doc example: drift mu*y, diffusion sigma*y
-    static constexpr int NP = 2;
-    __device__ __forceinline__ static double drift(double, double y, const double* p) { return p[0] * y; }
-    __device__ __forceinline__ static double diffusion(double, double y, const double* p) { return p[1] * y; }
+    static constexpr int DIM = 1, NP = 2;
+    __device__ __forceinline__ static void drift(double, const double* y, double* d, const double* p) { d[0] = p[0] * y[0]; }
+    __device__ __forceinline__ static void diffusion(double, const double* y, double* g, const double* p) { g[0] = p[1] * y[0]; }
+    __device__ __forceinline__ static void mix(double*, const double*) {}
+};
+struct SdeHeston {  // examples/sde/02_heston_model/main.rs:53-72; p = {mu, kappa, theta, sigma, rho}, y = {price, variance}
+    static constexpr int DIM = 2, NP = 5;
+    __device__ __forceinline__ static void drift(double, const double* y, double* d, const double* p) {
+        d[0] = p[0] * y[0];
+        d[1] = p[1] * (p[2] - y[1]);
+    }
+    __device__ __forceinline__ static void diffusion(double, const double* y, double* g, const double* p) {
+        g[0] = y[0] * sqrt(y[1]);
+        g[1] = p[3] * sqrt(y[1]);
+    }
+    __device__ __forceinline__ static void mix(double* dw, const double* p) { dw[1] = p[4] * dw[0] + sqrt(1.0 - p[4] * p[4]) * dw[1]; }
 };
 
 }  // namespace deb

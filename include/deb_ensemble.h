@@ -102,7 +102,10 @@ typedef enum deb_system {
 /* Built-in SDEs (`SDE::drift/diffusion`, src/sde/sde.rs:16-52), scalar state. */
 typedef enum deb_sde_system {
     DEB_SDE_OU = 0, /* params {theta,mu,sigma}: drift theta*(mu-y), diffusion sigma   examples/sde/03_ornstein_uhlenbeck/main.rs:42-49 */
-    DEB_SDE_GBM = 1 /* params {mu,sigma}:       drift mu*y,         diffusion sigma*y src/sde/solve_ivp.rs doc example               */
+    DEB_SDE_GBM = 1, /* params {mu,sigma}:       drift mu*y,         diffusion sigma*y src/sde/solve_ivp.rs doc example              */
+    DEB_SDE_HESTON = 2 /* dim 2 {price, variance}, params {mu,kappa,theta,sigma,rho}: dS = mu S dt + sqrt(v) S dW1,
+                          dv = kappa (theta - v) dt + sigma sqrt(v) dW2, dW2 = rho dW1 + sqrt(1-rho^2) dW2'
+                          (examples/sde/02_heston_model/main.rs:53-72) */
 } deb_sde_system;
 
 /* Per-trajectory outcome, mirrors Status/Error of the reference (src/status.rs:26, src/error.rs:13-41). */
@@ -203,10 +206,10 @@ typedef struct deb_sde_problem {
     size_t struct_size;
     int32_t system;       /* deb_sde_system */
     int32_t method;       /* fixed-step deb_method; DEB_EULER = Euler-Maruyama */
-    int32_t dim;          /* 1 */
+    int32_t dim;          /* must equal the system's dimension (1 for OU / GBM, 2 for Heston) */
     int32_t n_params;
     int64_t n_traj;
-    const double* y0;     /* [n_traj] in `memspace`; or, when y0_shared != 0, ONE value in HOST memory */
+    const double* y0;     /* [n_traj][dim] in `memspace`; or, when y0_shared != 0, ONE state [dim] in HOST memory */
     int32_t y0_shared;
     int32_t params_shared;
     const double* params; /* [n_traj][n_params] in `memspace`; or ONE set in HOST memory when params_shared != 0 */

@@ -949,34 +949,50 @@ void solve_one(const deb_ode_problem* P, const SysInfo& si, const Tableau& tb, i
     finish(status, m.t, m.y);
 }
 
-// ---------------------------------------------------------------- SDE (fixed step), scalar built-ins
-struct SdeSys { int np; void (*drift)(double, double, double*, const double*); void (*diffusion)(double, double, double*, const double*); };
-void ou_drift(double, double y, double* d, const double* p) { *d = p[0] * (p[1] - y); }   // examples/sde/03_ornstein_uhlenbeck/main.rs:43-45
-void ou_diff(double, double, double* g, const double* p) { *g = p[2]; }                    // :47-49
-void gbm_drift(double, double y, double* d, const double* p) { *d = p[0] * y; }            // src/sde/solve_ivp.rs doc example
-void gbm_diff(double, double y, double* g, const double* p) { *g = p[1] * y; }
+// ---------------------------------------------------------------- SDE (fixed step), built-ins
+// drift / diffusion: SDE::drift, SDE::diffusion (src/sde/sde.rs:16-52).  mix: what the system's SDE::noise does with the
+// independent increments of the library's Philox stream (identity, or the Heston correlation).
+struct SdeSys {
+    int dim, np;
+    void (*drift)(double, const double*, double*, const double*);
+    void (*diffusion)(double, const double*, double*, const double*);
+    void (*mix)(double*, const double*);
+};
+void ou_drift(double, const double* y, double* d, const double* p) { d[0] = p[0] * (p[1] - y[0]); }   // examples/sde/03_ornstein_uhlenbeck/main.rs:43-45
+void ou_diff(double, const double*, double* g, const double* p) { g[0] = p[2]; }                      // :47-49
+void gbm_drift(double, const double* y, double* d, const double* p) { d[0] = p[0] * y[0]; }           // src/sde/solve_ivp.rs doc example
+void gbm_diff(double, const double* y, double* g, const double* p) { g[0] = p[1] * y[0]; }
+void no_mix(double*, const double*) {}
+// examples/sde/02_heston_model/main.rs:53-72: p = {mu, kappa, theta, sigma, rho}; y = {price, variance}
+void heston_drift(double, const double* y, double* d, const double* p) { d[0] = p[0] * y[0]; d[1] = p[1] * (p[2] - y[1]); }
+void heston_diff(double, const double* y, double* g, const double* p) { g[0] = y[0] * std::sqrt(y[1]); g[1] = p[3] * std::sqrt(y[1]); }
+void heston_mix(double* dw, const double* p) { dw[1] = p[4] * dw[0] + std::sqrt(1.0 - p[4] * p[4]) * dw[1]; }
 bool get_sde(int id, SdeSys* s) {
-    if (id == DEB_SDE_OU) { *s = {3, ou_drift, ou_diff}; return true; }
-    if (id == DEB_SDE_GBM) { *s = {2, gbm_drift, gbm_diff}; return true; }
+    if (id == DEB_SDE_OU) { *s = {1, 3, ou_drift, ou_diff, no_mix}; return true; }
+    if (id == DEB_SDE_GBM) { *s = {1, 2, gbm_drift, gbm_diff, no_mix}; return true; }
+    if (id == DEB_SDE_HESTON) { *s = {2, 5, heston_drift, heston_diff, heston_mix}; return true; }
     return false;
 }
 
-// solve_sde (src/sde/solve_ivp.rs:135-287) + ExplicitRungeKutta<Stochastic, Fixed> (fixed/stochastic.rs:18-146), scalar state.
-// SDE::noise is the library's Philox Wiener increment (see philox_ref.h).
+// solve_sde (src/sde/solve_ivp.rs:135-287) + ExplicitRungeKutta<Stochastic, Fixed> (fixed/stochastic.rs:18-146) / Milstein
+// (milstein.rs:107-180), diagonal noise.  SDE::noise is the library's Philox Wiener increment (see philox_ref.h):
+// component c of step s is normal number s*dim + c of the path's stream, times sqrt(h); then the system's mix.
 void solve_one_sde(const deb_sde_problem* P, const SdeSys& ss, const Tableau& tb, int64_t i, const Out& o) {
+    const int n = ss.dim;
     const double* p = P->params_shared ? P->params : P->params + (size_t)i * ss.np;
-    double y0 = P->y0_shared ? P->y0[0] : P->y0[i];
+    Vec y0(n, 0.0);
+    for (int c = 0; c < n; c++) y0[c] = P->y0_shared ? P->y0[c] : P->y0[(size_t)i * n + c];
     const double t0 = P->t0, tf = P->tf;
-    int evals = 0, acc = 0, n_emit = 0;
-    double* ye = o.y_eval ? o.y_eval + (size_t)i * P->n_eval : nullptr;
-    auto finish = [&](int st, double t, double y) {
+    int evals = 0, acc = 0;
+    Rows rows{o.y_eval ? o.y_eval + (size_t)i * P->n_eval * n : nullptr, nullptr, n, 0x7fffffff};
+    auto finish = [&](int st, double t, const Vec& y) {
         if (o.status) o.status[i] = st;
         if (o.t_final) o.t_final[i] = t;
-        if (o.y_final) o.y_final[i] = y;
+        if (o.y_final) std::memcpy(o.y_final + (size_t)i * n, y.data(), sizeof(double) * n);
         if (o.accepted) o.accepted[i] = acc;
         if (o.rejected) o.rejected[i] = 0;
         if (o.evals) o.evals[i] = evals;
-        if (o.n_emitted) o.n_emitted[i] = n_emit;
+        if (o.n_emitted) o.n_emitted[i] = rows.n_emit;
     };
     double dir = signum(tf - t0);
     if (!(dir == 1.0 || dir == -1.0)) { finish(DEB_STATUS_BAD_INPUT, t0, y0); return; }
@@ -984,33 +1000,41 @@ void solve_one_sde(const deb_sde_problem* P, const SdeSys& ss, const Tableau& tb
     double h0 = P->opt.h0;
     if (h0 == 0.0) h0 = std::fabs(tf - t0) / 100.0;
     if (!validate_step_size_parameters(h0, P->opt.h_min, P->opt.h_max, t0, tf)) { finish(DEB_STATUS_BAD_INPUT, t0, y0); return; }
-    double h = h0, t = t0, y = y0, dydt = 0.0, g = 0.0;
+    double h = h0, t = t0;
+    Vec y = y0, dydt(n, 0.0), g(n, 0.0);
     int64_t steps = 0;
     const int S = tb.stages, I = tb.dense;
     const bool milstein = (P->method == DEB_MILSTEIN);
-    double k[8];
-    ss.drift(t, y, &dydt, p);
+    std::vector<Vec> k(8, Vec(n, 0.0));
+    ss.drift(t, y.data(), dydt.data(), p);
     if (milstein) {
         evals += 1;  // Milstein::init evaluates the drift only, milstein.rs:88-100
     } else {
-        ss.diffusion(t, y, &g, p);
+        ss.diffusion(t, y.data(), g.data(), p);
         evals += 2;
     }
-    double t_prev = t, y_prev = y;
+    double t_prev = t;
+    Vec y_prev = y;
     TEval te(P->t_eval, P->n_eval, t0, tf);
-    auto emit = [&](double t_curr, double tp, double y_curr) {
-        Vec yc(1, y_curr);
+    auto emit = [&](double t_curr, double tp, const Vec& y_curr) {
         // linear interpolation, src/interpolate.rs:71-74 via stochastic.rs:177-190
-        auto interp = [&](double tv) { double s = (tv - tp) / (t_curr - tp); Vec out(1, 0.0); out[0] += (1.0 - s) * y_prev; out[0] += s * y_curr; return out; };
-        Rows rows{ye, nullptr, 1, 0x7fffffff};
-        rows.n_emit = n_emit;
-        solout_teval(te, t_curr, tp, yc, interp, rows);
-        n_emit = rows.n_emit;
+        auto interp = [&](double tv) {
+            double s = (tv - tp) / (t_curr - tp);
+            Vec out(n, 0.0);
+            add_scaled(out, 1.0 - s, y_prev);
+            add_scaled(out, s, y_curr);
+            return out;
+        };
+        solout_teval(te, t_curr, tp, y_curr, interp, rows);
     };
     emit(t, t_prev, y);
     const double eps10 = DBL_EPSILON * 10.0;
     const uint64_t path = (uint64_t)(P->path_offset + i);
     int status = DEB_STATUS_COMPLETE;
+    auto noise = [&](Vec& dw) {
+        for (int c = 0; c < n; c++) dw[c] = deb_ref::wiener_increment(P->seed, path, (uint64_t)(steps - 1), c, n, h);
+        ss.mix(dw.data(), p);
+    };
     for (;;) {
         if ((t + h - tf) * dir > 0.0) {
             double h_new = tf - t;
@@ -1021,56 +1045,50 @@ void solve_one_sde(const deb_sde_problem* P, const SdeSys& ss, const Tableau& tb
         if (steps >= P->opt.max_steps) { status = DEB_STATUS_MAX_STEPS; break; }
         steps += 1;
         t_prev = t; y_prev = y;
-        if (milstein) {  // Milstein::step, milstein.rs:107-180 (scalar state)
-            ss.diffusion(t, y, &g, p);
+        Vec dw(n, 0.0), y_next = y;
+        if (milstein) {  // Milstein::step, milstein.rs:107-180
+            ss.diffusion(t, y.data(), g.data(), p);
             evals += 1;
-            double dw = deb_ref::wiener_increment(P->seed, path, (uint64_t)(steps - 1), 0, 1, h);
+            noise(dw);
             double sqrt_h = std::sqrt(h);
-            double y_aux = y;
-            y_aux += sqrt_h * g;
-            double g_aux = 0.0;
-            ss.diffusion(t, y_aux, &g_aux, p);
+            Vec y_aux = y;
+            add_scaled(y_aux, sqrt_h, g);
+            Vec g_aux(n, 0.0);
+            ss.diffusion(t, y_aux.data(), g_aux.data(), p);
             evals += 1;
-            double dw_sq = dw * dw;
             double factor = 1.0 / (2.0 * sqrt_h);
-            double diff = g_aux - g;
-            double dws_minus_h = dw_sq - h;
-            double milstein_term = diff * dws_minus_h * factor;
-            double drift_inc = dydt;
-            drift_inc *= h;
-            double diff_inc = g * dw;
-            double y_next = y;
-            y_next += 1.0 * drift_inc;
-            y_next += 1.0 * diff_inc;
-            y_next += 1.0 * milstein_term;
-            t += h;
-            y = y_next;
-            ss.drift(t, y, &dydt, p);
+            Vec milstein_term(n, 0.0), drift_inc = dydt, diff_inc(n, 0.0);
+            for (int c = 0; c < n; c++) {
+                double diff = g_aux[c] - g[c];
+                double dws_minus_h = dw[c] * dw[c] - h;
+                milstein_term[c] = diff * dws_minus_h * factor;
+                drift_inc[c] *= h;
+                diff_inc[c] = g[c] * dw[c];
+            }
+            add_scaled(y_next, 1.0, drift_inc);
+            add_scaled(y_next, 1.0, diff_inc);
+            add_scaled(y_next, 1.0, milstein_term);
+        } else {
+            k[0] = dydt;
+            for (int s = 1; s < S; s++) {
+                Vec ys = y;
+                for (int j = 0; j < s; j++) add_scaled(ys, tb.a[s * I + j] * h, k[j]);
+                ss.drift(t + tb.c[s] * h, ys.data(), k[s].data(), p);
+            }
+            evals += S - 1;
+            Vec drift_inc(n, 0.0);
+            for (int s = 0; s < S; s++) add_scaled(drift_inc, tb.b[s] * h, k[s]);
+            ss.diffusion(t, y.data(), g.data(), p);
             evals += 1;
-            acc += 1;
-            emit(t, t_prev, y);
-            if (std::fabs(tf - t) <= eps10) break;
-            continue;
+            noise(dw);
+            Vec diff_inc(n, 0.0);
+            for (int c = 0; c < n; c++) diff_inc[c] = g[c] * dw[c];  // component_multiply, linalg/util.rs:21
+            add_scaled(y_next, 1.0, drift_inc);                      // plus_linear_combination, traits.rs:343-349
+            add_scaled(y_next, 1.0, diff_inc);
         }
-        k[0] = dydt;
-        for (int s = 1; s < S; s++) {
-            double ys = y;
-            for (int j = 0; j < s; j++) ys += (tb.a[s * I + j] * h) * k[j];
-            ss.drift(t + tb.c[s] * h, ys, &k[s], p);
-        }
-        evals += S - 1;
-        double drift_inc = 0.0;
-        for (int s = 0; s < S; s++) drift_inc += (tb.b[s] * h) * k[s];
-        ss.diffusion(t, y, &g, p);
-        evals += 1;
-        double dw = deb_ref::wiener_increment(P->seed, path, (uint64_t)(steps - 1), 0, 1, h);
-        double diff_inc = g * dw;  // component_multiply, linalg/util.rs:21
-        double y_next = y;         // plus_linear_combination, traits.rs:343-349
-        y_next += 1.0 * drift_inc;
-        y_next += 1.0 * diff_inc;
         t += h;
         y = y_next;
-        ss.drift(t, y, &dydt, p);
+        ss.drift(t, y.data(), dydt.data(), p);
         evals += 1;
         acc += 1;
         emit(t, t_prev, y);
@@ -1120,7 +1138,7 @@ int orc_solve_sde(const deb_sde_problem* P, deb_result* R, int n_threads) {
     const bool milstein = P && P->method == DEB_MILSTEIN;
     if (milstein) get_tableau(DEB_EULER, &tb);
     if (!P || !R || !get_sde(P->system, &ss) || (!milstein && (!get_tableau(P->method, &tb) || tb.adaptive))) return DEB_ERR_BAD_ARG;
-    if (P->dim != 1 || ss.np != P->n_params) return DEB_ERR_BAD_ARG;
+    if (P->dim != ss.dim || ss.np != P->n_params) return DEB_ERR_BAD_ARG;
     if (n_threads <= 0) n_threads = orc_hardware_threads();
     Out o{R->y_eval, R->n_emitted, R->t_final, R->y_final, R->status, R->accepted, R->rejected, R->evals};
     parallel_for(P->n_traj, n_threads, [&](int64_t i) { solve_one_sde(P, ss, tb, i, o); });

@@ -124,3 +124,61 @@ def test_builder_mirror_semantics():
         deb.EnsembleIVP.ode(deb.VanDerPolOscillator(1.0), 0.0, 1.0, [[2.0, 0.0]]).solve()  # no method
     with pytest.raises(ValueError):
         deb.EnsembleIVP.ode(deb.VanDerPolOscillator(1.0), 0.0, 1.0, [[2.0, 0.0]]).method(E.dopri5().rtol([1e-3])).build_problem()
+
+
+def test_heston_vector_sde_oracle_against_a_python_restatement():
+    """examples/sde/02_heston_model: 2-D state, diagonal noise, correlated increments, three_eighths(0.01) drift stages
+    (fixed/stochastic.rs:67-146).  The oracle against a direct Python restatement that takes its Wiener increments from the
+    same stream definition (component c of step s = normal number 2s + c); plus Milstein (milstein.rs:107-180)."""
+    import math
+    lib = ob.load_oracle()
+    mu, kappa, theta, sigma, rho = 0.1, 2.0, 0.04, 0.3, -0.7
+    seed, off, h = 42, 1000, 0.01
+    drift = lambda y: [mu * y[0], kappa * (theta - y[1])]
+    diff = lambda y: [y[0] * math.sqrt(y[1]), sigma * math.sqrt(y[1])]
+    T = pr.TAB["THREE_EIGHTHS"]
+    def path_py(i, milstein):
+        t, y, steps = 0.0, [100.0, 0.04], 0
+        dydt = drift(y)
+        hh = h
+        while True:
+            if t + hh - 1.0 > 0.0:
+                if abs(1.0 - t) < pr.EPS10:
+                    break
+                hh = 1.0 - t
+            steps += 1
+            dw = [lib.orc_wiener_increment(seed, off + i, steps - 1, c, 2, hh) for c in range(2)]
+            dw[1] = rho * dw[0] + math.sqrt(1.0 - rho * rho) * dw[1]
+            g = diff(y)
+            if milstein:
+                sq = math.sqrt(hh)
+                ga = diff([y[c] + sq * g[c] for c in range(2)])
+                factor = 1.0 / (2.0 * sq)
+                yn = [((y[c] + 1.0 * (dydt[c] * hh)) + 1.0 * (g[c] * dw[c])) + 1.0 * ((ga[c] - g[c]) * (dw[c] * dw[c] - hh) * factor) for c in range(2)]
+            else:
+                k = [dydt]
+                for s_ in range(1, 4):
+                    ys = list(y)
+                    for j in range(s_):
+                        ah = T["A"][s_][j] * hh
+                        ys = [ys[c] + ah * k[j][c] for c in range(2)]
+                    k.append(drift(ys))
+                inc = [0.0, 0.0]
+                for s_ in range(4):
+                    w = T["B"][s_] * hh
+                    inc = [inc[c] + w * k[s_][c] for c in range(2)]
+                yn = [(y[c] + 1.0 * inc[c]) + 1.0 * (g[c] * dw[c]) for c in range(2)]
+            t += hh
+            y = yn
+            dydt = drift(y)
+            if abs(1.0 - t) <= pr.EPS10:
+                break
+        return y, steps
+    for meth, mil in ((E.three_eighths(h), False), (deb.Milstein.new(h), True)):
+        sol = ob.oracle_solve(deb.EnsembleIVP.sde(deb.HestonModel(mu, kappa, theta, sigma, rho), 0.0, 1.0, np.tile([100.0, 0.04], (6, 1)),
+                                                  seed=seed, path_offset=off).t_eval([0.5, 1.0]).method(meth))
+        assert sol.y_eval.shape == (6, 2, 2) and (sol.status == 0).all()
+        for i in range(6):
+            y, steps = path_py(i, mil)
+            assert steps == sol.accepted[i] and np.array_equal(np.array(y).view(np.uint64), sol.y_final[i].view(np.uint64))
+            assert np.array_equal(sol.y_eval[i, 1].view(np.uint64), sol.y_final[i].view(np.uint64))

@@ -271,6 +271,29 @@ def test_sde_rk4_drift_stages():
     assert_same_solution(prob().solve(), ob.oracle_solve(prob()), exact=False, rtol=1e-12)
 
 
+def test_heston_vector_sde_matches_host_regenerated_philox():
+    """examples/sde/02_heston_model: two-dimensional state, diagonal noise with correlated increments (rho), three_eighths(dt)
+    drift stages, Euler-Maruyama and Milstein; a sweep over rho; sample moments of the price."""
+    n = 8192
+    y0 = np.tile([100.0, 0.04], (n, 1))
+    for meth in (lambda: E.three_eighths(0.01), lambda: E.euler(0.002), lambda: deb.Milstein.new(0.005)):
+        def prob():
+            return (deb.EnsembleIVP.sde(deb.HestonModel(0.1, 2.0, 0.04, 0.3, -0.7), 0.0, 1.0, y0, seed=42, path_offset=77)
+                    .t_eval([0.25, 0.5, 1.0]).method(meth()))
+        g, c = prob().solve(), ob.oracle_solve(prob())
+        assert g.y_eval.shape == (n, 3, 2) and (g.status == 0).all()
+        assert_same_solution(g, c, exact=False, rtol=1e-12)
+        ok = np.isfinite(g.y_final).all(axis=1)   # a variance that dips below zero gives sqrt(v) = NaN, as in the reference
+        assert ok.mean() > 0.95
+        assert abs(g.y_final[ok, 0].mean() / (100.0 * math.exp(0.1)) - 1.0) < 0.02   # E[S_T] = S_0 e^{mu T}
+        assert abs(g.y_final[ok, 1].mean() - 0.04) < 0.004                            # v starts at its long-run mean theta
+    rho = np.linspace(-0.9, 0.9, n)
+    prm = np.stack([np.full(n, 0.1), np.full(n, 2.0), np.full(n, 0.04), np.full(n, 0.3), rho], axis=1)
+    def p2():
+        return deb.EnsembleIVP.sde(deb.SdeSystem(deb.DEB_SDE_HESTON, prm, 2), 0.0, 0.5, y0, seed=3).method(E.three_eighths(0.01))
+    assert_same_solution(p2().solve(), ob.oracle_solve(p2()), exact=False, rtol=1e-12)
+
+
 # ------------------------------------------------------------------------------------------ heat (config C5, reduced)
 @pytest.mark.parametrize("n,lo,hi", [(4097, 0.0, 4096.0), (4096, 0.0, 1.0), (41, 0.0, 1.0), (2, 0.0, 1.0), (65537, 0.0, 65536.0)])
 @pytest.mark.parametrize("bc", ["dirichlet", "neumann", "mixed"])

@@ -85,29 +85,35 @@ def c3(n, reps):
 
 
 def c4(n, which, reps):
+    dim = 1
     if which == "ou":
         sysid, params, t0, tf, h, y0v, nsteps = deb.DEB_SDE_OU, np.array([0.5, 1.0, 0.3]), 0.0, 10.0, 0.01, 5.0, 1001
+    elif which == "heston":  # examples/sde/02_heston_model (2-D state), Euler-Maruyama h = 1e-3
+        sysid, params, t0, tf, h, y0v, nsteps, dim = deb.DEB_SDE_HESTON, np.array([0.1, 2.0, 0.04, 0.3, -0.7]), 0.0, 1.0, 1e-3, [100.0, 0.04], 1000, 2
     else:
         sysid, params, t0, tf, h, y0v, nsteps = deb.DEB_SDE_GBM, np.array([0.1, 0.2]), 0.0, 1.0, 1e-3, 100.0, 1000
-    y0 = np.array([y0v])
+    y0 = np.array(y0v, dtype=np.float64).reshape(-1)
     te = np.array([tf])
     P = deb.SdeProblem()
     P.struct_size = C.sizeof(deb.SdeProblem)
-    P.system, P.method, P.dim, P.n_params = sysid, deb.DEB_EULER, 1, params.size
+    P.system, P.method, P.dim, P.n_params = sysid, deb.DEB_EULER, dim, params.size
     P.n_traj, P.y0, P.y0_shared, P.params, P.params_shared = n, y0.ctypes.data, 1, params.ctypes.data, 1
     P.n_eval, P.t_eval, P.t0, P.tf = 1, te.ctypes.data_as(deb._dp), t0, tf
     lib.deb_erk_options_default(C.byref(P.opt))
     P.opt.h0 = h
     P.seed, P.path_offset = 2026, 0
     P.device, P.memspace, P.stream = 0, deb.DEB_MEM_DEVICE, stream.cuda_stream
-    R, bufs = result_buffers(n, 1, 1)
+    R, bufs = result_buffers(n, 1, dim)
     def run():
         assert lib.deb_solve_sde(C.byref(P), C.byref(R)) == 0, lib.deb_last_error()
     best, avg = timed(run, reps)
     steps = int(bufs["accepted"].sum(dtype=torch.int64))
-    yf = bufs["y_final"].reshape(-1)
+    yf = bufs["y_final"].reshape(-1, dim)[:, 0]
+    yf = yf[torch.isfinite(yf)]
     mean, var = float(yf.mean()), float(yf.var())
-    if which == "ou":  # exact moments of the EM chain are close to the SDE's: mean 1 + 4 e^{-5}, var sigma^2/(2 theta)(1 - e^{-10})
+    if which == "heston":
+        exp_mean, exp_var = 100.0 * np.exp(0.1), float("nan")
+    elif which == "ou":  # exact moments of the EM chain are close to the SDE's: mean 1 + 4 e^{-5}, var sigma^2/(2 theta)(1 - e^{-10})
         exp_mean, exp_var = 1.0 + 4.0 * np.exp(-5.0), 0.09 / 1.0 * (1 - np.exp(-10.0))
     else:
         exp_mean, exp_var = 100.0 * np.exp(0.1), 100.0 ** 2 * np.exp(0.2) * (np.exp(0.04) - 1)
@@ -205,7 +211,7 @@ if __name__ == "__main__":
     if a.c3:
         print(json.dumps(c3(a.c3, a.reps)), flush=True)
     if a.c4:
-        for w in ("ou", "gbm"):
+        for w in ("ou", "gbm", "heston"):
             print(json.dumps(c4(a.c4, w, a.reps)), flush=True)
     if a.c5:
         print(json.dumps(c5(a.c5, a.reps)), flush=True)
