@@ -227,9 +227,11 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
     const int evals_base = (a.h0 == 0.0) ? (Tab::DP ? 3 : 5) : 1;
     const bool bounded_h = (a.h_min > 0.0) || (a.h_max < 1.0 / 0.0);  // constrain_step_size can change h at all
 
-    constexpr bool DEFER = (I == S) && !REC;   // dense output needs no extra stages: emission can be parked
-    StepRecorder<Sys, Tab, Evt> recd;
     constexpr int NSTASH = 2 + 4 * N;  // t, h, y, y_new, k0, f(y_new)
+    // dense output needs no extra stages: emission can be parked -- as long as the stash fits the static shared-memory
+    // budget next to the pow tables (wide systems interpolate on the spot)
+    constexpr bool DEFER = (I == S) && !REC && (NSTASH * BLOCK * 8 <= 40 * 1024);
+    StepRecorder<Sys, Tab, Evt> recd;
     __shared__ double s_stash[DEFER ? (BLOCK / 32) : 1][DEFER ? NSTASH : 1][32];
     double (*stash)[32] = s_stash[DEFER ? (threadIdx.x >> 5) : 0];
     const bool want_rows = (a.y_eval != nullptr);
@@ -662,7 +664,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
                             }
                             Sys::rhs(t + Tab::cv(i) * h, ys, kx[i - S], p);
                         }
-                    } else {
+                    } else if constexpr (Tab::DP) {
 #pragma unroll
                         for (int c = 0; c < N; c++) {  // ordinary.rs:196-207
                             c1[c] = ynew[c] - y[c];
@@ -738,6 +740,23 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
 #pragma unroll
                                     for (int c = 0; c < N; c++) row[c] = row[c] + w * ((i < S) ? k[(i < S) ? i : 0][c] : kx[(i >= S) ? (i - S) : 0][c]);
                                 }
+                            }
+                        } else if constexpr (!Tab::DP) {  // cubic Hermite (adaptive family without bi; only wide systems get here)
+                            const double hh = t_new - t;
+                            const double sx = (te - t) / hh;
+                            const double s2 = sx * sx, s3 = s2 * sx;
+                            const double h00 = 2.0 * s3 - 3.0 * s2 + 1.0;
+                            const double h10 = s3 - 2.0 * s2 + sx;
+                            const double h01 = -2.0 * s3 + 3.0 * s2;
+                            const double h11 = s3 - s2;
+                            const double w10 = h10 * hh, w11 = h11 * hh;
+#pragma unroll
+                            for (int c = 0; c < N; c++) {
+                                double v = __dadd_rn(0.0, h00 * y[c]);
+                                v = v + w10 * k[0][c];
+                                v = v + h01 * ynew[c];
+                                v = v + w11 * dydt[c];
+                                row[c] = v;
                             }
                         } else {  // interpolate, ordinary.rs:301-337, factor order as written
                             const double sx = (te - t) / h;

@@ -483,6 +483,58 @@ def test_user_defined_six_dimensional_system_vs_python_restatement():
             assert np.array_equal(bits([r[1] for r in p["rows"]]), bits(g.y_eval[i, :len(p["rows"])]))
 
 
+def test_user_defined_wide_system_forward_sensitivities():
+    """A 12-dimensional user system: Lorenz with its forward sensitivities dy/dp (the augmented system of
+    src/ode/sensitivity/forward.rs: S' = J_y S + J_p, row-major S after y).  Wide systems do not park their t_eval rows
+    (the stash would not fit shared memory), so this covers the immediate-emission path of DOPRI5 and of the cubic-Hermite
+    family; bitwise against the independent Python restatement, and dy/drho against a finite difference."""
+    import py_restatement as pr
+    src = """
+const double s = p[0], r = p[1], b = p[2];
+const double x = y[0], v = y[1], z = y[2];
+dydt[0] = s * (v - x); dydt[1] = x * (r - z) - v; dydt[2] = x * v - b * z;
+const double J[3][3] = {{-s, s, 0.0}, {r - z, -1.0, -x}, {v, x, -b}};
+const double Jp[3][3] = {{v - x, 0.0, 0.0}, {0.0, x, 0.0}, {0.0, 0.0, -z}};
+for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+    double a = Jp[i][j];
+    for (int k = 0; k < 3; k++) a = a + J[i][k] * y[3 + 3 * k + j];
+    dydt[3 + 3 * i + j] = a;
+}"""
+    def f(t, y, s=10.0, r=28.0, b=8.0 / 3.0):
+        x, v, z = y[0], y[1], y[2]
+        J = [[-s, s, 0.0], [r - z, -1.0, -x], [v, x, -b]]
+        Jp = [[v - x, 0.0, 0.0], [0.0, x, 0.0], [0.0, 0.0, -z]]
+        out = [s * (v - x), x * (r - z) - v, x * v - b * z] + [0.0] * 9
+        for i in range(3):
+            for j in range(3):
+                a = Jp[i][j]
+                for k in range(3):
+                    a = a + J[i][k] * y[3 + 3 * k + j]
+                out[3 + 3 * i + j] = a
+        return out
+    sysm = deb.ode_from_source(12, src, params=[10.0, 28.0, 8.0 / 3.0])
+    y0 = np.zeros((40, 12))
+    y0[:, :3] = ob.lorenz_ensemble_y0(40, seed=81)
+    te = [0.0, 0.4, 1.1, 2.0]
+    for meth in ("dopri5", "rkf45", "dop853"):
+        g = deb.EnsembleIVP.ode(sysm, 0.0, 2.0, y0).t_eval(te).method(getattr(E, meth)().rtol(1e-8).atol(1e-8)).solve()
+        assert (g.status == 0).all() and (g.n_emitted == 4).all()
+        for i in (0, 17, 39):
+            if meth == "rkf45":
+                p = pr.solve_adaptive(f, meth, 0.0, 2.0, y0[i].tolist(), rtol=1e-8, atol=1e-8, t_eval=te)
+            else:
+                p = pr.solve_dp(f, meth, 0.0, 2.0, y0[i].tolist(), rtol=1e-8, atol=1e-8, t_eval=te)
+            assert (int(g.accepted[i]), int(g.rejected[i]), int(g.evals[i])) == (p["accepted"], p["rejected"], p["evals"])
+            assert np.array_equal(bits(g.y_final[i]), bits(p["y"])) and np.array_equal(bits(g.y_eval[i]), bits([r[1] for r in p["rows"]]))
+    # dy/drho from the sensitivities against a central finite difference of two plain Lorenz runs
+    d = 1e-6
+    hi = deb.EnsembleIVP.ode(deb.LorenzSystem(10.0, 28.0 + d, 8.0 / 3.0), 0.0, 2.0, y0[:, :3].copy()).method(E.dop853().rtol(1e-12).atol(1e-12)).solve()
+    lo = deb.EnsembleIVP.ode(deb.LorenzSystem(10.0, 28.0 - d, 8.0 / 3.0), 0.0, 2.0, y0[:, :3].copy()).method(E.dop853().rtol(1e-12).atol(1e-12)).solve()
+    fd = (hi.y_final - lo.y_final) / (2.0 * d)
+    sens = deb.EnsembleIVP.ode(sysm, 0.0, 2.0, y0).method(E.dop853().rtol(1e-12).atol(1e-12)).solve().y_final[:, 3:].reshape(-1, 3, 3)[:, :, 1]
+    np.testing.assert_allclose(sens, fd, rtol=2e-4, atol=1e-6)
+
+
 def test_user_defined_rhs_compile_error_is_reported():
     bad = deb.ode_from_source(1, "dydt[0] = undefined_symbol * y[0];", [1.0])
     with pytest.raises(ValueError, match="did not compile"):
