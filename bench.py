@@ -260,8 +260,18 @@ def main():
     lib.deb_fp64_issue_peak(local_rank, 0, C.byref(peak), C.byref(pk_ms))
     ops_local = OPS_PER_ATTEMPT * (acc_local + rej_local) + OPS_PER_ACCEPT * acc_local
     achieved = ops_local / (kernel_ms * 1e-3) / 1e12
+    # the same launch against the HBM roofline (why the bound is not "hbm"): algorithmic bytes = y0 in + rows and finals out
+    hbm_peak = 6650.0
+    try:
+        hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    alg_bytes = n * (3 * 8 + N_EVAL * 3 * 8 + 3 * 8 + 8 + 5 * 4)
+    hbm_achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak.value / 1e12, "unit": "TFLOP/s",
                 "frac": achieved / (peak.value / 1e12),
+                "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
+                        "note": "algorithmic bytes per launch / kernel time: two orders of magnitude below the HBM roofline"},
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on the full 10 M config (profiles/r01_dram_traffic_10M.csv):
                 # 7.60 GB + 31.64 GB; algorithmic 0.24 GB in + 24.5 GB out (24-byte rows are written as partial sectors)
                 "traffic": (39.24e9 * n / 10_000_000) if n_total == 10_000_000 else None, "traffic_unit": "bytes per launch (ncu, r01)",
