@@ -450,6 +450,15 @@ struct DevBuf {
     template <class T> T* as() { return (T*)p; }
 };
 
+// buffer from the stream-ordered memory pool: allocation and release are ordered on the stream, no device-wide sync
+struct PoolBuf {
+    void* p = nullptr;
+    cudaStream_t st = nullptr;
+    ~PoolBuf() { if (p) cudaFreeAsync(p, st); }
+    cudaError_t alloc(size_t bytes, cudaStream_t s) { st = s; return cudaMallocAsync(&p, bytes ? bytes : 8, s); }
+    template <class T> T* as() { return (T*)p; }
+};
+
 struct ResultPtrs {
     double* y_eval; int* n_emitted; double* t_final; double* y_final; int* status; int* accepted; int* rejected; int* evals;
     double* t_out;
@@ -966,21 +975,21 @@ int heat_launch_stage(const deb::HeatArgs& a, bool pow2, cudaStream_t st) {
 }
 
 // launches stages STAGE..S-1 (each writes ks[STAGE])
-template <class Tab, int STAGE>
-int heat_run_stages(deb::HeatArgs& a, double* const* ks, bool pow2, cudaStream_t st) {
-    if constexpr (STAGE < Tab::S) {
-        a.out_k = ks[STAGE];
-        if (int rc = heat_launch_stage<Tab, STAGE>(a, pow2, st)) return rc;
-        return heat_run_stages<Tab, STAGE + 1>(a, ks, pow2, st);
-    } else {
-        return DEB_OK;
-    }
+// One whole time step: a single launch of the all-stages-in-registers kernel (mol_heat.cuh); 8 independent warps per CTA.
+template <class Tab>
+int heat_launch_step(const deb::HeatArgs& a, bool pow2, cudaStream_t st) {
+    const long long warps = (a.n + deb::HEAT_OUT - 1) / deb::HEAT_OUT;
+    const unsigned blocks = (unsigned)((warps + 7) / 8);
+    if (pow2) deb::heat_step_kernel<Tab, true><<<blocks, 256, 0, st>>>(a);
+    else deb::heat_step_kernel<Tab, false><<<blocks, 256, 0, st>>>(a);
+    DEB_CUDA(cudaGetLastError());
+    return DEB_OK;
 }
 
-// solve_ode loop (solve_ivp.rs:139-277) on the host around per-stage kernels; t and h are scalars.
+// solve_ode loop (solve_ivp.rs:193-263) + Fixed::init/step (fixed/ordinary.rs:16-139) around the launches
 template <class Tab>
-int heat_solve(const deb_heat_problem* P, double* y_a, double* y_b, double* const* kbuf, double* knew, bool pow2,
-               cudaStream_t st, double* t_out, long long* steps_out, int* status_out, double** y_out) {
+int heat_solve(const deb_heat_problem* P, double* y_a, double* y_b, bool pow2, cudaStream_t st, double* t_out, long long* steps_out,
+               int* status_out, double** y_out) {
     const double t0 = P->t0, tf = P->tf;
     const double d = tf - t0;
     const double dir = (d != d) ? d : copysign(1.0, d);
@@ -1001,11 +1010,6 @@ int heat_solve(const deb_heat_problem* P, double* y_a, double* y_b, double* cons
     a.bc_lo_val = P->bc_lower_value; a.bc_hi_val = P->bc_upper_value;
     double* y = y_a;
     double* y_next = y_b;
-    double* k0 = kbuf[0];
-    double* k0_next = knew;
-    // init: dydt = f(t0, y0)
-    a.y = y; a.h = 0.0; a.out_k = k0;
-    if (int rc = heat_launch_stage<Tab, 0>(a, pow2, st)) return rc;
     double t = t0;
     long long steps = 0;
     int status = DEB_STATUS_COMPLETE;
@@ -1018,17 +1022,10 @@ int heat_solve(const deb_heat_problem* P, double* y_a, double* y_b, double* cons
         }
         if (steps >= P->max_steps) { status = DEB_STATUS_MAX_STEPS; break; }
         steps += 1;
-        a.y = y; a.h = h;
-        double* ks[8];
-        ks[0] = k0;
-        for (int i = 1; i < Tab::S; i++) ks[i] = kbuf[i];
-        for (int i = 0; i < Tab::S; i++) a.k[i] = ks[i];
-        if (int rc = heat_run_stages<Tab, 1>(a, ks, pow2, st)) return rc;
-        a.out_y = y_next; a.out_k = k0_next;
-        if (int rc = heat_launch_stage<Tab, Tab::S>(a, pow2, st)) return rc;
+        a.y = y; a.h = h; a.out_y = y_next;
+        if (int rc = heat_launch_step<Tab>(a, pow2, st)) return rc;
         t += h;
         std::swap(y, y_next);
-        std::swap(k0, k0_next);
         if (fabs(tf - t) <= eps10) break;
     }
     *t_out = t; *steps_out = steps; *status_out = status; *y_out = y;
@@ -1054,21 +1051,15 @@ extern "C" int deb_solve_heat_mol(const deb_heat_problem* P) {
     const bool host = (P->memspace == DEB_MEM_HOST);
     cudaStream_t st = host ? (cudaStream_t)0 : (cudaStream_t)P->stream;
     const size_t bytes = sizeof(double) * (size_t)P->n_nodes;
-    int S = 0;
     switch (P->method) {
-        case DEB_EULER: S = 1; break;
-        case DEB_MIDPOINT: case DEB_HEUN: case DEB_RALSTON: S = 2; break;
-        case DEB_SSP_RK3: S = 3; break;
-        case DEB_RK4: case DEB_THREE_EIGHTHS: S = 4; break;
+        case DEB_EULER: case DEB_MIDPOINT: case DEB_HEUN: case DEB_RALSTON: case DEB_SSP_RK3: case DEB_RK4: case DEB_THREE_EIGHTHS: break;
         default: return fail(DEB_ERR_UNSUPPORTED, "method of lines takes a fixed-step method id");
     }
-    // work buffers: two state buffers (ping-pong), S stage buffers + one for the next k_1
-    DevBuf ya, yb, kk[9];
-    DEB_CUDA(ya.alloc(bytes));
-    DEB_CUDA(yb.alloc(bytes));
-    double* kbuf[8] = {nullptr};
-    for (int i = 0; i < S; i++) { DEB_CUDA(kk[i].alloc(bytes)); kbuf[i] = kk[i].as<double>(); }
-    DEB_CUDA(kk[8].alloc(bytes));
+    // work buffers: two state buffers (ping-pong) from the stream-ordered pool (no device-wide synchronisation on
+    // allocation or release); the stage derivatives never leave the chip
+    PoolBuf ya, yb;
+    DEB_CUDA(ya.alloc(bytes, st));
+    DEB_CUDA(yb.alloc(bytes, st));
     DEB_CUDA(cudaMemcpyAsync(ya.p, P->u0, bytes, host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
     const double dx = (P->hi - P->lo) / (double)(P->n_nodes - 1);
     const bool pow2 = is_pow2(dx);
@@ -1077,7 +1068,7 @@ extern "C" int deb_solve_heat_mol(const deb_heat_problem* P) {
     int status = 0;
     double* yout = nullptr;
     int rc = DEB_OK;
-#define DEB_HEAT_CASE(ID, T) case ID: rc = heat_solve<deb::T>(P, ya.as<double>(), yb.as<double>(), kbuf, kk[8].as<double>(), pow2, st, &t, &steps, &status, &yout); break;
+#define DEB_HEAT_CASE(ID, T) case ID: rc = heat_solve<deb::T>(P, ya.as<double>(), yb.as<double>(), pow2, st, &t, &steps, &status, &yout); break;
     switch (P->method) {
         DEB_HEAT_CASE(DEB_EULER, TabEuler)
         DEB_HEAT_CASE(DEB_MIDPOINT, TabMidpoint)

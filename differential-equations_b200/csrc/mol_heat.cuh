@@ -9,9 +9,14 @@
 // Time stepping = Fixed::step (/root/reference/src/methods/erk/fixed/ordinary.rs:58-139): stage i evaluates the RHS at
 // y + sum_j (a_ij*h)*k_j, the solution is y + sum_i (b_i*h)*k_i, and the new derivative is evaluated at once.
 //
-// Kernel design: one kernel per stage, each fusing "stage combine + stencil": a stage reads y and the k_j it
-// needs and writes k_i (3 N doubles for RK4); the final kernel fuses "solution combine + next k_1" (reads
-// y,k_1..k_S, writes y' and k_1: 7 N doubles for RK4).  16 N doubles = 128 B per node per RK4 step.
+// Kernel design, whole-step kernel (heat_step_kernel, what deb_solve_heat_mol runs): ONE launch per time step; all S
+// stages of a node run on chip, in registers, with a 4-node halo per warp that is recomputed by the neighbouring warp.
+// Per node and step the kernel reads 8 B and writes 8 B -- instead of the 128 B of a stage-by-stage sweep (16 arrays for
+// RK4) -- and every node sees exactly the operations of the reference (k_0 = f(t_n, y_n) is recomputed from y_n; same
+// bits as the value the reference carries over from the previous step).
+// Per-stage kernels (heat_stage_kernel; STAGE 0 is what deb_heat_rhs runs): each fuses "stage combine + stencil": a stage
+// reads y and the k_j it needs and writes k_i (3 N doubles for RK4); the final kernel fuses "solution combine + next k_1"
+// (reads y,k_1..k_S, writes y' and k_1: 7 N doubles for RK4).  16 N doubles = 128 B per node per RK4 step.
 // Every thread owns two adjacent nodes (16-byte loads/stores).  The combined state of the neighbouring nodes
 // comes from the adjacent lanes by warp shuffle (the two warp-edge lanes fetch their halo through L1/L2), and the
 // face gradient g = (w_i - w_{i-1})/dx is computed once per face and shared the same way, so a node costs two IEEE
@@ -124,6 +129,107 @@ __global__ void __launch_bounds__(256) heat_stage_kernel(const HeatArgs a) {
         if (STAGE == Tab::S) a.out_y[i0] = w0;
         a.out_k[i0] = d0;
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Whole-step kernel: y_{n+1} = y_n + sum_i (b_i h) k_i with all stages evaluated in registers, one launch per step.
+// Every WARP is independent: it owns HEAT_OUT = 120 output nodes and works on 128 consecutive nodes (4 halo nodes per
+// side, 4 per lane), starting at a multiple of 4 so that each lane's state is two aligned 16-byte loads.  A stage needs
+// the stage state of the neighbouring nodes: w[3] of the lane below and w[0] of the lane above, by warp shuffle.  Lanes 0
+// and 31 have no valid neighbour on one side; the error this puts into their edge node moves inwards by one node per
+// stage and, with at most 4 stages, never leaves those two halo lanes, whose results are not stored.  No shared memory,
+// no block-level synchronisation, 6.7 % redundant stencil work.
+constexpr int HEAT_OUT = 120;
+
+// EDGE = false: the warp's 128 nodes and their neighbours are all interior nodes (no boundary tests at all).
+template <class Tab, bool POW2, bool EDGE>
+__device__ __forceinline__ void heat_warp_step(const HeatArgs& a, const long long i0, const unsigned lane) {
+    constexpr int S = Tab::S;
+    const long long n = a.n;
+    double u[4];
+    if (!EDGE || (i0 >= 0 && i0 + 3 < n)) {
+        const double2 lo = *reinterpret_cast<const double2*>(a.y + i0);
+        const double2 hi = *reinterpret_cast<const double2*>(a.y + i0 + 2);
+        u[0] = lo.x; u[1] = lo.y; u[2] = hi.x; u[3] = hi.y;
+    } else {
+#pragma unroll
+        for (int m = 0; m < 4; m++) u[m] = (i0 + m >= 0 && i0 + m < n) ? a.y[i0 + m] : 0.0;
+    }
+    const bool dir_lo = (a.bc_lo_kind == 0), dir_hi = (a.bc_hi_kind == 0);
+    double k[S][4];
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        double w[4];
+#pragma unroll
+        for (int m = 0; m < 4; m++) w[m] = u[m];
+#pragma unroll
+        for (int j = 0; j < s; j++) {  // stage state y + sum_j (a_sj h) k_j, fixed/ordinary.rs:80-88
+            if (Tab::a(s, j) != 0.0) {
+                const double ah = Tab::av(s, j) * a.h;
+#pragma unroll
+                for (int m = 0; m < 4; m++) w[m] = w[m] + ah * k[j][m];
+            }
+        }
+        const double wl = __shfl_up_sync(0xffffffffu, w[3], 1);
+        const double wr = __shfl_down_sync(0xffffffffu, w[0], 1);
+        // face gradients (semi_discrete.rs:150-172): g[m] is the lower face of node m, g[4] the upper face of node 3;
+        // a face on the domain boundary carries the prescribed (Neumann) gradient
+        double g[5];
+        if (EDGE) {
+            g[0] = (i0 > 0) ? div_dx<POW2>(w[0] - wl, a) : a.bc_lo_val;
+#pragma unroll
+            for (int m = 1; m < 4; m++)
+                g[m] = (i0 + m > 0) ? ((i0 + m < n) ? div_dx<POW2>(w[m] - w[m - 1], a) : a.bc_hi_val) : a.bc_lo_val;
+            g[4] = (i0 + 4 < n) ? div_dx<POW2>(wr - w[3], a) : a.bc_hi_val;
+        } else {
+            g[0] = div_dx<POW2>(w[0] - wl, a);
+#pragma unroll
+            for (int m = 1; m < 4; m++) g[m] = div_dx<POW2>(w[m] - w[m - 1], a);
+            g[4] = div_dx<POW2>(wr - w[3], a);
+        }
+        double f[5];
+#pragma unroll
+        for (int m = 0; m < 5; m++) f[m] = a.alpha * g[m];
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+            double d = __dadd_rn(0.0, div_dx<POW2>(f[m + 1] - f[m], a));                              // :132-139, :181-190
+            if (EDGE && ((dir_lo && i0 + m == 0) || (dir_hi && i0 + m == n - 1))) d = 0.0;            // Dirichlet nodes, :264-267
+            k[s][m] = d;
+        }
+    }
+    if (lane == 0 || lane == 31) return;  // halo lanes
+    double v[4];
+#pragma unroll
+    for (int m = 0; m < 4; m++) v[m] = u[m];
+#pragma unroll
+    for (int j = 0; j < S; j++) {  // solution, fixed/ordinary.rs:98-102
+        if (Tab::b(j) != 0.0) {
+            const double bh = Tab::bv(j) * a.h;
+#pragma unroll
+            for (int m = 0; m < 4; m++) v[m] = v[m] + bh * k[j][m];
+        }
+    }
+    if (!EDGE || i0 + 3 < n) {
+        *reinterpret_cast<double2*>(a.out_y + i0) = make_double2(v[0], v[1]);
+        *reinterpret_cast<double2*>(a.out_y + i0 + 2) = make_double2(v[2], v[3]);
+    } else {
+#pragma unroll
+        for (int m = 0; m < 4; m++)
+            if (i0 + m < n) a.out_y[i0 + m] = v[m];
+    }
+}
+
+template <class Tab, bool POW2>
+__global__ void __launch_bounds__(256) heat_step_kernel(const HeatArgs a) {
+    static_assert(Tab::S <= 4, "the 4-node halo covers at most 4 stages");
+    const long long warp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const unsigned lane = threadIdx.x & 31u;
+    const long long first = warp * HEAT_OUT - 4;     // first of the warp's 128 nodes
+    if (warp * HEAT_OUT >= a.n) return;              // whole warp out of range
+    const long long i0 = first + 4 * (long long)lane;
+    // warp-uniform: do the 128 nodes or their outer neighbours touch the ends of the grid?
+    if (first > 1 && first + 128 < a.n - 1) heat_warp_step<Tab, POW2, false>(a, i0, lane);
+    else heat_warp_step<Tab, POW2, true>(a, i0, lane);
 }
 
 }  // namespace deb
