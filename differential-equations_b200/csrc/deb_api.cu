@@ -720,10 +720,27 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P, deb_result* R) {
         const long long v = atoll(e);
         if (v > 0) CHUNK = v;
     }
-    // equal chunks of at most CHUNK trajectories
-    const long long n_chunks = (n + CHUNK - 1) / CHUNK;
-    const long long chunk = (n + n_chunks - 1) / n_chunks;
-    const int n_slots = (n > chunk) ? 2 : 1;
+    // Chunks of at most CHUNK trajectories; the last ones shrink geometrically (each takes half of what is left, down to
+    // CHUNK/16), because the result copy of the LAST chunk is the one transfer nothing overlaps with (measured on C2:
+    // 1845 ms per pass instead of 1930 ms with equal chunks).
+    std::vector<long long> chunk_sizes;
+    {
+        long long min_chunk = std::max<long long>(CHUNK / 16, 1);
+        if (const char* e = getenv("DEB_HOST_TAIL")) {  // tuning knob: 0 = equal chunks, k = smallest chunk CHUNK/k
+            const long long v = atoll(e);
+            min_chunk = (v <= 0) ? CHUNK : std::max<long long>(CHUNK / v, 1);
+        }
+        long long left = n;
+        while (left > 0) {
+            long long c = std::min(CHUNK, left);
+            if (left > CHUNK) c = std::min(CHUNK, std::max(min_chunk, left / 2));
+            else if (left > 2 * min_chunk && n > CHUNK) c = std::max(min_chunk, left / 2);
+            chunk_sizes.push_back(c);
+            left -= c;
+        }
+    }
+    const long long chunk = *std::max_element(chunk_sizes.begin(), chunk_sizes.end());  // buffer size of a slot
+    const int n_slots = (chunk_sizes.size() > 1) ? 2 : 1;
     const int n_eval = row_cap;  // rows per trajectory in y_eval / t_out
     struct Slot {
         cudaStream_t st = nullptr;
@@ -757,9 +774,9 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P, deb_result* R) {
     }
     float kernel_ms = 0.f;
     int ci = 0;
-    for (long long off = 0; off < n; off += chunk, ci++) {
+    for (long long off = 0; off < n; off += chunk_sizes[ci], ci++) {
         Slot& S = slot[ci % n_slots];
-        const long long cnt = std::min(chunk, n - off);
+        const long long cnt = chunk_sizes[ci];
         if (S.used) {  // collect the kernel time of the chunk that used this slot before (its stream has passed k1)
             DEB_CUDA(cudaEventSynchronize(S.k1));
             float ms = 0.f;
