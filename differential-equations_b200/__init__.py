@@ -54,7 +54,7 @@ DEB_EVENT_NONE, DEB_EVENT_LINEAR = 0, 1
 DEB_MAX_DIM = 16
 DEB_STATUS_INTERRUPTED = 5
 DEB_OK, DEB_ERR_BAD_ARG, DEB_ERR_NO_DEVICE, DEB_ERR_CUDA, DEB_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
-DEB_ABI_VERSION = 7
+DEB_ABI_VERSION = 8
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -104,7 +104,7 @@ class HeatProblem(C.Structure):
 
 
 # every symbol include/deb_ensemble.h declares (tests check that the library exports all of them)
-ABI_SYMBOLS = ["deb_abi_version", "deb_last_error", "deb_device_count", "deb_erk_options_default", "deb_define_ode", "deb_define_event", "deb_check_ode", "deb_solve_ode",
+ABI_SYMBOLS = ["deb_abi_version", "deb_last_error", "deb_device_count", "deb_erk_options_default", "deb_define_ode", "deb_define_event", "deb_check_ode", "deb_trim_memory", "deb_solve_ode",
                "deb_solve_sde", "deb_solve_heat_mol", "deb_heat_rhs", "deb_ensemble_stats", "deb_malloc", "deb_free", "deb_memcpy_h2d",
                "deb_memcpy_d2h", "deb_synchronize", "deb_pow_device", "deb_fp64_issue_peak"]
 

@@ -55,6 +55,8 @@ namespace {
         }                                                                                               \
     } while (0)
 
+thread_local int g_device = 0;  // device selected by the current call
+
 int select_device(int device) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -63,10 +65,14 @@ int select_device(int device) {
                                            "); the ensemble integrator has no CPU fallback");
     if (device < 0 || device >= n) return fail(DEB_ERR_BAD_ARG, "device ordinal out of range");
     DEB_CUDA(cudaSetDevice(device));
+    g_device = device;
     return DEB_OK;
 }
 
-struct DeviceInfo { int sms = 0; };
+// The library's own stream-ordered memory pool per device: staging buffers of HOST-memspace calls and work buffers are
+// cached across calls (release threshold = never) instead of paying cudaMalloc/cudaFree (tens to hundreds of ms for
+// multi-GB buffers, with a device-wide synchronisation) in every call.  deb_trim_memory() gives the memory back.
+struct DeviceInfo { int sms = 0; cudaMemPool_t pool = nullptr; };
 int device_info(int device, DeviceInfo* di) {
     static std::mutex mu;
     static std::vector<DeviceInfo> cache;
@@ -75,6 +81,17 @@ int device_info(int device, DeviceInfo* di) {
     if (cache[device].sms == 0) {
         int sms = 0;
         DEB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        cudaMemPoolProps props;
+        memset(&props, 0, sizeof props);
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        cudaMemPool_t pool = nullptr;
+        DEB_CUDA(cudaMemPoolCreate(&pool, &props));
+        unsigned long long keep = ~0ull;
+        DEB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        cache[device].pool = pool;
         cache[device].sms = sms;
     }
     *di = cache[device];
@@ -454,8 +471,14 @@ struct DevBuf {
 struct PoolBuf {
     void* p = nullptr;
     cudaStream_t st = nullptr;
-    ~PoolBuf() { if (p) cudaFreeAsync(p, st); }
-    cudaError_t alloc(size_t bytes, cudaStream_t s) { st = s; return cudaMallocAsync(&p, bytes ? bytes : 8, s); }
+    ~PoolBuf() { release(); }
+    void release() { if (p) { cudaFreeAsync(p, st); p = nullptr; } }
+    cudaError_t alloc(size_t bytes, cudaStream_t s) {
+        st = s;
+        DeviceInfo di;
+        if (device_info(g_device, &di) != DEB_OK || !di.pool) return cudaErrorMemoryAllocation;
+        return cudaMallocFromPoolAsync(&p, bytes ? bytes : 8, di.pool, s);
+    }
     template <class T> T* as() { return (T*)p; }
 };
 
@@ -522,6 +545,15 @@ void publish_rows(deb_result* R, const TEvalPlan& plan, bool even = false) {
 }  // namespace
 
 extern "C" int deb_abi_version(void) { return DEB_ABI_VERSION; }
+
+extern "C" int deb_trim_memory(int32_t device) {
+    if (int rc = select_device(device)) return rc;
+    DeviceInfo di;
+    if (int rc = device_info(device, &di)) return rc;
+    DEB_CUDA(cudaDeviceSynchronize());
+    DEB_CUDA(cudaMemPoolTrimTo(di.pool, 0));
+    return DEB_OK;
+}
 extern "C" const char* deb_last_error(void) { return g_err.c_str(); }
 
 extern "C" int deb_device_count(void) {
@@ -715,7 +747,9 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P, deb_result* R) {
     //      PCIe traffic: n_eval*dim*8 B per trajectory) overlaps the integration of the next, and the tail of one
     //      persistent kernel overlaps the start of the following one.  Device memory is 2 chunks, not the ensemble.
     const auto wall0 = std::chrono::steady_clock::now();
-    long long CHUNK = 1ll << 21;  // 2 Mi trajectories: measured best for C2 (tail loss vs exposed last copy), profiles/
+    // 2 Mi trajectories: measured best for C2 (tail loss vs exposed last copy), profiles/; smaller ensembles are still cut
+    // into about four chunks (not below 256 Ki) so that their result copy overlaps the integration too
+    long long CHUNK = std::min<long long>(1ll << 21, std::max<long long>(n / 4, 1ll << 18));
     if (const char* e = getenv("DEB_HOST_CHUNK")) {  // tuning / test knob
         const long long v = atoll(e);
         if (v > 0) CHUNK = v;
@@ -745,9 +779,11 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P, deb_result* R) {
     struct Slot {
         cudaStream_t st = nullptr;
         cudaEvent_t k0 = nullptr, k1 = nullptr;
-        DevBuf y0, params, small, y_eval, n_emitted, t_final, y_final, status, accepted, rejected, evals, t_out;
+        PoolBuf y0, params, small, y_eval, n_emitted, t_final, y_final, status, accepted, rejected, evals, t_out;
         bool used = false;
         ~Slot() {
+            // stream-ordered frees first: they use the stream that is destroyed below
+            for (PoolBuf* b : {&y0, &params, &small, &y_eval, &n_emitted, &t_final, &y_final, &status, &accepted, &rejected, &evals, &t_out}) b->release();
             if (k0) cudaEventDestroy(k0);
             if (k1) cudaEventDestroy(k1);
             if (st) cudaStreamDestroy(st);
@@ -758,19 +794,19 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P, deb_result* R) {
         DEB_CUDA(cudaStreamCreateWithFlags(&S.st, cudaStreamNonBlocking));
         DEB_CUDA(cudaEventCreate(&S.k0));
         DEB_CUDA(cudaEventCreate(&S.k1));
-        DEB_CUDA(S.y0.alloc(sizeof(double) * (size_t)chunk * dim));
-        if (per_traj_params) DEB_CUDA(S.params.alloc(sizeof(double) * (size_t)chunk * np));
-        DEB_CUDA(S.small.alloc(8 + rows_bytes));
+        DEB_CUDA(S.y0.alloc(sizeof(double) * (size_t)chunk * dim, S.st));
+        if (per_traj_params) DEB_CUDA(S.params.alloc(sizeof(double) * (size_t)chunk * np, S.st));
+        DEB_CUDA(S.small.alloc(8 + rows_bytes, S.st));
         if (rows_bytes) DEB_CUDA(cudaMemcpyAsync((char*)S.small.p + 8, plan.rows.data(), rows_bytes, cudaMemcpyHostToDevice, S.st));
-        if (R->y_eval) DEB_CUDA(S.y_eval.alloc(sizeof(double) * (size_t)chunk * n_eval * dim));
-        if (R->n_emitted) DEB_CUDA(S.n_emitted.alloc(sizeof(int) * (size_t)chunk));
-        if (R->t_final) DEB_CUDA(S.t_final.alloc(sizeof(double) * (size_t)chunk));
-        if (R->y_final) DEB_CUDA(S.y_final.alloc(sizeof(double) * (size_t)chunk * dim));
-        if (R->status) DEB_CUDA(S.status.alloc(sizeof(int) * (size_t)chunk));
-        if (R->accepted) DEB_CUDA(S.accepted.alloc(sizeof(int) * (size_t)chunk));
-        if (R->rejected) DEB_CUDA(S.rejected.alloc(sizeof(int) * (size_t)chunk));
-        if (R->evals) DEB_CUDA(S.evals.alloc(sizeof(int) * (size_t)chunk));
-        if (R->t_out) DEB_CUDA(S.t_out.alloc(sizeof(double) * (size_t)chunk * n_eval));
+        if (R->y_eval) DEB_CUDA(S.y_eval.alloc(sizeof(double) * (size_t)chunk * n_eval * dim, S.st));
+        if (R->n_emitted) DEB_CUDA(S.n_emitted.alloc(sizeof(int) * (size_t)chunk, S.st));
+        if (R->t_final) DEB_CUDA(S.t_final.alloc(sizeof(double) * (size_t)chunk, S.st));
+        if (R->y_final) DEB_CUDA(S.y_final.alloc(sizeof(double) * (size_t)chunk * dim, S.st));
+        if (R->status) DEB_CUDA(S.status.alloc(sizeof(int) * (size_t)chunk, S.st));
+        if (R->accepted) DEB_CUDA(S.accepted.alloc(sizeof(int) * (size_t)chunk, S.st));
+        if (R->rejected) DEB_CUDA(S.rejected.alloc(sizeof(int) * (size_t)chunk, S.st));
+        if (R->evals) DEB_CUDA(S.evals.alloc(sizeof(int) * (size_t)chunk, S.st));
+        if (R->t_out) DEB_CUDA(S.t_out.alloc(sizeof(double) * (size_t)chunk * n_eval, S.st));
     }
     float kernel_ms = 0.f;
     int ci = 0;

@@ -18,7 +18,7 @@ use differential_equations::{
 };
 
 // ------------------------------------------------------------------------------------------------ raw ABI
-pub const DEB_ABI_VERSION: i32 = 7;
+pub const DEB_ABI_VERSION: i32 = 8;
 
 #[repr(C)]
 #[derive(Clone, Copy)]
@@ -98,6 +98,8 @@ extern "C" {
     pub fn deb_erk_options_default(opt: *mut deb_erk_options);
     pub fn deb_solve_ode(problem: *const deb_ode_problem, result: *mut deb_result) -> i32;
     /// user-defined right-hand side as CUDA C++ text (the device-side `impl ODE`); returns a system id >= 1000
+    /// release the device memory the library caches between calls
+    pub fn deb_trim_memory(device: i32) -> i32;
     pub fn deb_define_ode(dim: i32, n_params: i32, diff_body: *const c_char, system_id: *mut i32) -> i32;
     /// compile it for a method now (no device needed); the compiler log is in deb_last_error()
     pub fn deb_check_ode(system_id: i32, method: i32, solout: i32, event: i32) -> i32;

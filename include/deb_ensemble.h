@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define DEB_ABI_VERSION 7
+#define DEB_ABI_VERSION 8
 #define DEB_MAX_DIM 16 /* widest state the register-resident kernels are instantiated for */
 
 typedef enum deb_error {
@@ -302,6 +302,10 @@ int deb_define_event(int32_t dim, const char* event_body, int32_t* event_id);
  * compile: what a Rust caller gets from `cargo check`).  Kernels that were compiled ahead of time (built-in system with
  * a t_eval / even(dt) recorder) return DEB_OK at once. */
 int deb_check_ode(int32_t system_id, int32_t method, int32_t solout, int32_t event);
+
+/* Device memory the library caches between calls (staging buffers of DEB_MEM_HOST calls, work buffers) lives in a
+ * library-owned stream-ordered pool; this releases it back to the driver.  Synchronises the device. */
+int deb_trim_memory(int32_t device);
 
 int deb_solve_ode(const deb_ode_problem* problem, deb_result* result);
 int deb_solve_sde(const deb_sde_problem* problem, deb_result* result);
