@@ -1188,7 +1188,7 @@ extern "C" int deb_ensemble_stats(const double* y_eval, const int32_t* n_emitted
     const bool host = (memspace == DEB_MEM_HOST);
     cudaStream_t st = host ? (cudaStream_t)0 : (cudaStream_t)stream;
     const int ne = n_eval * dim;
-    int n_cta = di.sms * 4;
+    int n_cta = di.sms * 8;
     if ((long long)n_cta > n_traj) n_cta = (int)std::max<int64_t>(1, n_traj);
     DevBuf d_y, d_ne, d_sums, d_counts;
     const double* dy = y_eval;

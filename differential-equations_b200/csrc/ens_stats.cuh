@@ -7,7 +7,7 @@
 namespace deb {
 
 // Each CTA owns a contiguous slab of trajectories; thread e owns element e = r*dim + c of a trajectory's block
-// (consecutive threads read consecutive doubles: one trajectory = one coalesced 8*ne-byte read).  Four trajectories
+// (consecutive threads read consecutive doubles: one trajectory = one coalesced 8*ne-byte read).  Eight trajectories
 // are loaded before they are accumulated (memory-level parallelism); the accumulation order stays i, i+1, i+2, ...
 // partial[(cta*ne + e)*2 + {0,1}], pcount[cta*n_eval + r].
 __global__ void __launch_bounds__(512) stats_partial_kernel(const double* __restrict__ y_eval, const int* __restrict__ n_emitted,
@@ -22,16 +22,16 @@ __global__ void __launch_bounds__(512) stats_partial_kernel(const double* __rest
         double s = 0.0, s2 = 0.0;
         long long cnt = 0;
         long long i = b;
-        for (; i + 4 <= e_end; i += 4) {
-            double v[4];
-            bool ok[4];
+        for (; i + 8 <= e_end; i += 8) {
+            double v[8];
+            bool ok[8];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < 8; u++) {
                 ok[u] = n_emitted[i + u] > r;
                 v[u] = ok[u] ? y_eval[(i + u) * ne + e] : 0.0;
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < 8; u++) {
                 if (ok[u]) { s += v[u]; s2 += v[u] * v[u]; cnt += 1; }
             }
         }
