@@ -245,6 +245,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
     double y[N], k[S][N], p_reg[(NP > 0 && !SHARED_P) ? NP : 1];
     const double* p = SHARED_P ? a.pc : p_reg;
     int acc = 0, rej = 0, stiff = 0, nonstiff = 0;
+    int m100 = 0;  // (acc + rej) % 100, kept incrementally
     int idx = 0;   // next t_eval row == rows emitted so far (rows are pre-filtered: every consumed point is emitted)
     int fin = -1;  // >= 0: the trajectory has ended with this status and waits for the service section
     bool rejected_prev = false;
@@ -395,7 +396,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
                     } else {
 #pragma unroll
                         for (int c = 0; c < N; c++) y[c] = y0v[c];
-                        acc = 0; rej = 0; idx = 0;
+                        acc = 0; rej = 0; idx = 0; m100 = 0;
                         t = t0;
                         h = h0;
                         h_prev = 0.0;
@@ -442,7 +443,6 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
                 }
             }
             const bool stepping = active && fin < 0;
-            const int steps = acc + rej + 1;  // self.steps after the increment
 
             // ---- stages, solution and error estimate.  Terms whose tableau coefficient is zero are dropped
             // (x + (0*h)*k == x for finite k).
@@ -487,7 +487,11 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
 #pragma unroll
                     for (int c = 0; c < N; c++) {
                         ynew[c] = y[c] + h * yseg[c];
-                        sk[c] = a.atol[c] + a.rtol[c] * fmax(fabs(y[c]), fabs(ynew[c]));  // traits.rs:587-595
+                        // |y|.max(|y_new|), traits.rs:587-595.  Written as a compare + select on the two non-negative values:
+                        // same result as fmax whenever y is not NaN (a NaN y_new is dropped, as f64::max does; a NaN y makes
+                        // every stage, hence the error norm, NaN whatever sk is)
+                        const double ay = fabs(y[c]), an = fabs(ynew[c]);
+                        sk[c] = a.atol[c] + a.rtol[c] * ((an > ay) ? an : ay);
                         const double e = es[c] / sk[c];
                         err = err + e * e;
                     }
@@ -580,7 +584,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
                 Sys::rhs(t_new, ynew, dydt, p);
             }
 
-            if (Tab::DP && accept && (steps % 100 == 0)) {  // stiffness test, ordinary.rs:165-194
+            if (Tab::DP && accept && m100 == 99) {  // steps % 100 == 0 with steps = acc + rej + 1: stiffness test, ordinary.rs:165-194
                 // ysti = the argument of the last stage; rebuilt here (same operations, same bits) instead of being
                 // kept alive in registers through 99 steps out of 100
                 double ysti[N];
@@ -807,6 +811,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
                 }
                 rejected_prev = false;
                 acc += 1;
+                m100 = (m100 == 99) ? 0 : m100 + 1;
             }
             if (reject) {
                 rejected_prev = true;  // Status::RejectedStep
@@ -814,7 +819,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
                     stiff += 1;
                     if (stiff >= a.max_rejects) fin = DEB_STATUS_STIFFNESS;  // Err: the attempt is not counted
                 }
-                if (fin < 0) rej += 1;
+                if (fin < 0) { rej += 1; m100 = (m100 == 99) ? 0 : m100 + 1; }
             }
             if ((commit || reject) && fin < 0) {
                 // ---- step-size update, ordinary.rs:261-267 (filter = identity)
