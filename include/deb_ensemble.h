@@ -7,13 +7,18 @@
  *
  *   deb_solve_ode     <->  IVP::ode(&sys,t0,tf,y0).t_eval(pts).method(ExplicitRungeKutta::<m>()...).solve()
  *                          src/ivp.rs:279,656,632,781 -> solve_ode src/ode/solve_ivp.rs:116-277
- *                          -> init/step/interpolate src/methods/erk/dormandprince/ordinary.rs:16,63,301
- *                             or src/methods/erk/fixed/ordinary.rs:16,58,169
- *                          -> TEvalSolout::solout src/solout/t_eval.rs:87-137
+ *                          -> init/step/interpolate src/methods/erk/dormandprince/ordinary.rs:16,63,301,
+ *                             src/methods/erk/adaptive/ordinary.rs:16,63,246 or src/methods/erk/fixed/ordinary.rs:16,58,169
+ *                          -> the recorder: TEvalSolout src/solout/t_eval.rs:87-137, or .even(dt) / plain solve() /
+ *                             .dense(n) / .crossing(..) / .hyperplane_crossing(..) (src/solout/{even,default,dense,
+ *                             crossing,hyperplane}.rs), optionally wrapped by .event(&e) (src/solout/event.rs:300-470)
+ *   deb_define_ode    <->  impl ODE for S { fn diff(&self, t, y, dydt) }  (src/ode/ode.rs:20-44), as CUDA C++ text
+ *   deb_define_event  <->  impl Event for S { fn event(&self, t, y) -> T }  (src/solout/event.rs:60-70), as CUDA C++ text
  *   deb_solve_sde     <->  IVP::sde(&mut sde,t0,tf,y0).t_eval(pts).method(ExplicitRungeKutta::euler(h)).solve()
  *                          src/ivp.rs:504,857 -> solve_sde src/sde/solve_ivp.rs:135-287
  *                          -> src/methods/erk/fixed/stochastic.rs:18,67,177 ; SDE::noise (src/sde/sde.rs:67)
  *                             is replaced by counter-based Philox4x32-10 Wiener increments (documented below)
+ *                          scalar OU / GBM and the two-dimensional Heston model (diagonal noise); Milstein::new(h)
  *   deb_solve_heat_mol <-> IVP::pde(..).space(MethodOfLines::finite_difference(grid).boundary(bc))
  *                             .method(ExplicitRungeKutta::rk4(h)).solve()
  *                          src/ivp.rs:419,713 ; RHS = SemiDiscretePde::diff src/pde/semi_discrete.rs:250-287
