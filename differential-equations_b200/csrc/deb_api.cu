@@ -669,16 +669,25 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P, deb_result* R) {
     // ---- kernel arguments common to every launch of this call
     deb::OdeKernelArgs a;
     memset(&a, 0, sizeof a);
-    DevBuf d_shared_params;  // run-time kernels are built with SHARED_P = false: a shared set is read through the pointer (stride 0)
+    // run-time kernels are built with SHARED_P = false: a shared set is read through the pointer (stride 0).  DEVICE calls
+    // take the few bytes from the stream-ordered pool on the caller's stream (no device-wide synchronisation: the call
+    // stays asynchronous); HOST calls are synchronous anyway
+    DevBuf d_shared_params;
+    PoolBuf p_shared_params;
     if (np > 0 && P->params_shared) {
         // one parameter set for the whole ensemble: HOST memory by contract, passed by value (constant bank)
         for (int q = 0; q < np && q < 8; q++) a.pc[q] = P->params[q];
         if (jit || np > 8) {
-            DEB_CUDA(d_shared_params.alloc(sizeof(double) * np));
-            DEB_CUDA(cudaMemcpy(d_shared_params.p, P->params, sizeof(double) * np, cudaMemcpyHostToDevice));
+            if (P->memspace == DEB_MEM_HOST) {
+                DEB_CUDA(d_shared_params.alloc(sizeof(double) * np));
+                DEB_CUDA(cudaMemcpy(d_shared_params.p, P->params, sizeof(double) * np, cudaMemcpyHostToDevice));
+            } else {
+                DEB_CUDA(p_shared_params.alloc(sizeof(double) * np, (cudaStream_t)P->stream));
+                DEB_CUDA(cudaMemcpyAsync(p_shared_params.p, P->params, sizeof(double) * np, cudaMemcpyHostToDevice, (cudaStream_t)P->stream));
+            }
         }
     }
-    const double* shared_params_dev = d_shared_params.as<double>();
+    const double* shared_params_dev = d_shared_params.p ? d_shared_params.as<double>() : p_shared_params.as<double>();
     a.params_stride = P->params_shared ? 0 : np;
     a.t0 = P->t0;
     a.tf = P->tf;
