@@ -541,6 +541,26 @@ def test_user_defined_rhs_compile_error_is_reported():
         deb.EnsembleIVP.ode(bad, 0.0, 1.0, [[1.0]]).method(E.dopri5()).solve()
 
 
+@pytest.mark.parametrize("meth", ["dopri5", "dop853", "rkf45", "rkv655e", "rk4"])
+def test_non_finite_and_degenerate_initial_states(meth):
+    """NaN, +-inf, all-zero, -0.0 and 1e300 initial states next to ordinary ones: every family reproduces what the reference
+    arithmetic does with them (Dormand-Prince: the 2-norm keeps NaN -> rejected until MaxSteps; adaptive family: the
+    infinity norm drops NaN terms -> "Complete" with a NaN state; h_init overflow -> BadInput), for three recorders."""
+    y0 = ob.lorenz_ensemble_y0(8)
+    y0[1, 0] = np.nan; y0[2, 1] = np.inf; y0[3, 2] = -np.inf; y0[4, :] = 0.0; y0[5, :] = 1e300; y0[6, :] = -0.0
+    for setter in (lambda i: i.t_eval([0.5, 1.0]), lambda i: i.even(0.25), lambda i: i.every_step(50)):
+        def prob():
+            m = E.rk4(0.01) if meth == "rk4" else getattr(E, meth)().rtol(1e-8)
+            return setter(deb.EnsembleIVP.ode(lorenz(), 0.0, 1.0, y0)).method(m)
+        g, c = prob().solve(), ob.oracle_solve(prob())
+        for name in ("status", "accepted", "rejected", "evals", "n_emitted"):
+            assert np.array_equal(getattr(g, name), getattr(c, name)), name
+        assert np.array_equal(bits(g.y_final), bits(c.y_final)) and np.array_equal(bits(g.t_final), bits(c.t_final))
+        m = np.arange(g.y_eval.shape[1])[None, :] < np.minimum(g.n_emitted, g.y_eval.shape[1])[:, None]
+        assert np.array_equal(bits(g.y_eval)[m], bits(c.y_eval)[m])
+        assert g.status[0] == 0 and g.status[7] == 0 and np.isfinite(g.y_final[[0, 4, 6, 7]]).all()
+
+
 # ------------------------------------------------------------------------------------------ adaptive family (SURVEY 8f)
 @pytest.mark.parametrize("ctor", ["rkf45", "cash_karp"])
 def test_adaptive_family_bit_exact(ctor):
