@@ -561,6 +561,24 @@ def test_non_finite_and_degenerate_initial_states(meth):
         assert g.status[0] == 0 and g.status[7] == 0 and np.isfinite(g.y_final[[0, 4, 6, 7]]).all()
 
 
+def test_degenerate_options_bitwise():
+    """Options at and beyond their sensible range -- zero tolerances (division by a zero scale), max_steps 0 / 1, h_min
+    above the natural step, h_min/h_max pinching, h0 too large or of the wrong sign, a safety factor above 1, min_scale
+    above max_scale, max_rejects 0 / 1 -- with duplicated / out-of-range t_eval points: whatever the reference arithmetic
+    does with them, the GPU does the same, bit for bit."""
+    y0 = ob.lorenz_ensemble_y0(40)
+    cases = [lambda m: m.rtol(0.0).atol(0.0), lambda m: m.rtol(0.0).atol(1e-9), lambda m: m.max_steps(0), lambda m: m.max_steps(1),
+             lambda m: m.h_min(1e-3), lambda m: m.h_min(1e-3).h_max(2e-3), lambda m: m.h0(0.9), lambda m: m.h0(-0.1),
+             lambda m: m.safety_factor(1.5).min_scale(0.9).max_scale(1.1), lambda m: m.min_scale(5.0).max_scale(0.1),
+             lambda m: m.max_rejects(1), lambda m: m.max_rejects(0)]
+    for meth in ("dopri5", "dop853", "cash_karp", "rkv766e"):
+        for opt in cases:
+            for te in ([0.3, 0.3, 1.0, -1.0, 2.0], []):
+                def prob():
+                    return deb.EnsembleIVP.ode(lorenz(), 0.0, 1.0, y0).t_eval(te).method(opt(getattr(E, meth)()))
+                assert_same_solution(prob().solve(), ob.oracle_solve(prob()))
+
+
 # ------------------------------------------------------------------------------------------ adaptive family (SURVEY 8f)
 @pytest.mark.parametrize("ctor", ["rkf45", "cash_karp"])
 def test_adaptive_family_bit_exact(ctor):
