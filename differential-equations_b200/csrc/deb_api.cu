@@ -990,13 +990,63 @@ extern "C" int deb_solve_sde(const deb_sde_problem* P, deb_result* R) {
     a.h_min = P->opt.h_min;
     a.h_max = P->opt.h_max;
     a.max_steps = (int)std::min<int64_t>(P->opt.max_steps, 0x7fffffff / 16);
+    // ---- the step schedule, identical for every path: solve_sde bookkeeping (solve_ivp.rs:211-227, :263),
+    //      Fixed/Milstein init and max_steps (stochastic.rs:18-65, :74-83), TEvalSolout row placement (t_eval.rs:100-130)
+    std::vector<int> row_step(plan.rows.size(), -1);
+    std::vector<double> row_s(plan.rows.size(), -1.0);
+    {
+        const double t0 = P->t0, tf = P->tf;
+        const double dd = tf - t0;
+        const double dir = (dd != dd) ? dd : copysign(1.0, dd);
+        double h = P->opt.h0;
+        if (h == 0.0) h = fabs(tf - t0) / 100.0;
+        const double sgh = (h != h) ? h : copysign(1.0, h);
+        const bool ok = (tf != t0) && (dir == 1.0 || dir == -1.0) && sgh == dir && !(P->opt.h_min < 0.0) && !(P->opt.h_max < 0.0) &&
+                        !(P->opt.h_min > P->opt.h_max) && !(fabs(h) < P->opt.h_min) && !(fabs(h) > P->opt.h_max) &&
+                        !(fabs(h) > fabs(tf - t0)) && h != 0.0;  // validate_step_size_parameters, utils.rs:60-157
+        a.n_steps = 0;
+        a.h_last = h;
+        a.final_status = ok ? DEB_STATUS_COMPLETE : DEB_STATUS_BAD_INPUT;
+        if (ok) {
+            const double eps10 = 2.220446049250313e-16 * 10.0;
+            double t = t0;
+            long long steps = 0;
+            size_t idx = plan.emit_t0 ? 1 : 0;
+            for (;;) {
+                if ((t + h - tf) * dir > 0.0) {
+                    const double h_new = tf - t;
+                    if (fabs(h_new) < eps10) break;
+                    h = h_new;
+                }
+                if (steps >= a.max_steps) { a.final_status = DEB_STATUS_MAX_STEPS; break; }
+                const double t_new = t + h;
+                while (idx < plan.rows.size() && ((dir > 0.0) ? (plan.rows[idx] <= t_new) : (plan.rows[idx] >= t_new))) {
+                    row_step[idx] = (int)steps;
+                    row_s[idx] = (plan.rows[idx] == t_new) ? -1.0 : (plan.rows[idx] - t) / (t_new - t);
+                    idx++;
+                }
+                steps += 1;
+                a.h_last = h;  // only the final step can differ from h0 (the clip at tf)
+                t = t_new;
+                if (fabs(tf - t) <= eps10) break;
+            }
+            a.n_steps = (int)steps;
+        }
+    }
+    const size_t nr = plan.rows.size();
+    const size_t rows_bytes = 8 + sizeof(double) * nr * 2 + sizeof(int) * nr;
     void* d_rows = nullptr;
-    DEB_CUDA(cudaMallocAsync(&d_rows, 8 + sizeof(double) * plan.rows.size(), st));
+    DEB_CUDA(cudaMallocAsync(&d_rows, rows_bytes, st));
     struct SmallFree { void* p; cudaStream_t st; ~SmallFree() { if (p) cudaFreeAsync(p, st); } } small_free{d_rows, st};
-    if (!plan.rows.empty())
-        DEB_CUDA(cudaMemcpyAsync(d_rows, plan.rows.data(), sizeof(double) * plan.rows.size(), cudaMemcpyHostToDevice, st));
+    if (nr) {
+        DEB_CUDA(cudaMemcpyAsync(d_rows, plan.rows.data(), sizeof(double) * nr, cudaMemcpyHostToDevice, st));
+        DEB_CUDA(cudaMemcpyAsync((char*)d_rows + sizeof(double) * nr, row_s.data(), sizeof(double) * nr, cudaMemcpyHostToDevice, st));
+        DEB_CUDA(cudaMemcpyAsync((char*)d_rows + sizeof(double) * nr * 2, row_step.data(), sizeof(int) * nr, cudaMemcpyHostToDevice, st));
+    }
     a.t_rows = (const double*)d_rows;
-    a.n_rows = (int)plan.rows.size();
+    a.row_s = (const double*)((char*)d_rows + sizeof(double) * nr);
+    a.row_step = (const int*)((char*)d_rows + sizeof(double) * nr * 2);
+    a.n_rows = (int)nr;
     a.row_stride = P->n_eval;
     a.emit_t0 = plan.emit_t0 ? 1 : 0;
     ResultStage rs;

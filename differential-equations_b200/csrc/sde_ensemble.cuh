@@ -25,6 +25,15 @@ struct SdeKernelArgs {
     int max_steps;
     const double* t_rows;
     int n_rows, row_stride, emit_t0;
+    // The step schedule does not depend on the path (same t0, tf, h0, t_eval for every path), so the host runs the
+    // solve_sde bookkeeping once (solve_ivp.rs:211-227, :263; stochastic.rs:74-83) and the kernel's step loop carries no
+    // end-of-interval tests: n_steps steps of size h0, the last one of size h_last; row r is emitted in step row_step[r]
+    // with the interpolation weight row_s[r] (negative: the row is the end of the step itself).
+    int n_steps;
+    double h_last;
+    int final_status;       // DEB_STATUS_COMPLETE / MAX_STEPS / BAD_INPUT (then n_steps = 0)
+    const int* row_step;    // [n_rows]
+    const double* row_s;    // [n_rows]
     double* y_eval;
     int* n_emitted;
     double* t_final;
@@ -41,9 +50,6 @@ template <class Sde, class Tab, int BLOCK, bool MILSTEIN = false>
 __global__ void __launch_bounds__(BLOCK) sde_ensemble_kernel(const SdeKernelArgs a) {
     constexpr int N = Sde::DIM, NP = Sde::NP, S = Tab::S;
     const double t0 = a.t0, tf = a.tf;
-    const double dir = d_signum(tf - t0);
-    const double eps10 = DBL_EPSILON * 10.0;
-    const double te_none = (dir > 0.0) ? (1.0 / 0.0) : -(1.0 / 0.0);
     const long long stride = (long long)gridDim.x * BLOCK;
 
     for (long long traj = (long long)blockIdx.x * BLOCK + threadIdx.x; traj < a.n_traj; traj += stride) {
@@ -54,14 +60,11 @@ __global__ void __launch_bounds__(BLOCK) sde_ensemble_kernel(const SdeKernelArgs
 #pragma unroll
         for (int c = 0; c < N; c++) { y[c] = a.y0[traj * a.y0_stride + c]; dydt[c] = 0.0; }
         const unsigned long long path = (unsigned long long)(a.path_offset + traj);
-        int steps = 0, evals = 0, n_emit = 0, idx = 0, fin = -1;
+        int evals = 0, n_emit = 0, idx = 0;
         double t = t0;
-        // ---- init, stochastic.rs:18-65
-        double h = a.h0;
-        if (h == 0.0) h = fabs(tf - t0) / 100.0;
-        if (!validate_step_size_parameters(h, a.h_min, a.h_max, t0, tf)) {
-            fin = DEB_STATUS_BAD_INPUT;
-        } else {
+        const double h0 = (a.h0 == 0.0) ? fabs(tf - t0) / 100.0 : a.h0;  // stochastic.rs:23-28
+        // ---- init, stochastic.rs:18-65 (BadInput was decided on the host: utils.rs:60-157 does not look at the state)
+        if (a.final_status != DEB_STATUS_BAD_INPUT) {
             Sde::drift(t, y, dydt, p);
             evals = MILSTEIN ? 1 : 2;  // ERK: drift + diffusion (the initial diffusion value is not used); Milstein: drift only
             if (a.emit_t0) {
@@ -73,20 +76,15 @@ __global__ void __launch_bounds__(BLOCK) sde_ensemble_kernel(const SdeKernelArgs
                 idx = 1;
             }
         }
-        double te = (idx < a.n_rows) ? a.t_rows[idx] : te_none;
-        double h_cached = h, sqrt_h = sqrt(h);
+        int next_step = (idx < a.n_rows) ? a.row_step[idx] : -1;
+        const double sqrt_h0 = sqrt(h0), sqrt_hl = sqrt(a.h_last);
         double z_odd = 0.0;                          // the odd normal of the last Philox call ...
         unsigned long long odd_pair = ~0ull;         // ... and its pair index
-        while (fin < 0) {
-            if ((t + h - tf) * dir > 0.0) {  // solve_ivp.rs:211-227
-                const double h_new = tf - t;
-                if (fabs(h_new) < eps10) { fin = DEB_STATUS_COMPLETE; break; }
-                h = h_new;
-            }
-            if (steps >= a.max_steps) { fin = DEB_STATUS_MAX_STEPS; break; }  // stochastic.rs:74-83
-            const unsigned long long q0 = (unsigned long long)steps * N;  // first normal index of this step
-            steps += 1;
-            if (h != h_cached) { h_cached = h; sqrt_h = sqrt(h); }
+        for (int step = 0; step < a.n_steps; step++) {
+            const bool last = (step == a.n_steps - 1);
+            const double h = last ? a.h_last : h0;
+            const double sqrt_h = last ? sqrt_hl : sqrt_h0;
+            const unsigned long long q0 = (unsigned long long)step * N;  // first normal index of this step
             double dw[N];  // noise(h, dw)
             if constexpr (N % 2 == 0) {
                 // even dimension: the step's normals are whole Philox pairs
@@ -162,15 +160,15 @@ __global__ void __launch_bounds__(BLOCK) sde_ensemble_kernel(const SdeKernelArgs
             const double t_new = t + h;
             double d_new[N];
             Sde::drift(t_new, y_next, d_new, p);
-            while ((dir > 0.0) ? (te <= t_new) : (te >= t_new)) {
+            while (next_step == step) {  // TEvalSolout rows of this step (t_eval.rs:100-130), linear dense output
+                const double sw = a.row_s[idx];
                 double row[N];
-                if (te == t_new) {
+                if (sw < 0.0) {
 #pragma unroll
                     for (int c = 0; c < N; c++) row[c] = y_next[c];
                 } else {
-                    const double s = (te - t) / (t_new - t);
 #pragma unroll
-                    for (int c = 0; c < N; c++) row[c] = __dadd_rn(0.0, (1.0 - s) * y[c]) + s * y_next[c];
+                    for (int c = 0; c < N; c++) row[c] = __dadd_rn(0.0, (1.0 - sw) * y[c]) + sw * y_next[c];
                 }
                 if (a.y_eval) {
 #pragma unroll
@@ -178,13 +176,14 @@ __global__ void __launch_bounds__(BLOCK) sde_ensemble_kernel(const SdeKernelArgs
                 }
                 n_emit += 1;
                 idx += 1;
-                te = (idx < a.n_rows) ? a.t_rows[idx] : te_none;
+                next_step = (idx < a.n_rows) ? a.row_step[idx] : -1;
             }
             t = t_new;
 #pragma unroll
             for (int c = 0; c < N; c++) { y[c] = y_next[c]; dydt[c] = d_new[c]; }
-            if (fabs(tf - t) <= eps10) fin = DEB_STATUS_COMPLETE;
         }
+        const int fin = a.final_status;
+        const int steps = a.n_steps;
         if (a.status) a.status[traj] = fin;
         if (a.t_final) a.t_final[traj] = t;
         if (a.y_final) {

@@ -271,6 +271,29 @@ def test_sde_rk4_drift_stages():
     assert_same_solution(prob().solve(), ob.oracle_solve(prob()), exact=False, rtol=1e-12)
 
 
+def test_sde_step_schedule_edge_cases():
+    """The SDE step schedule is planned on the host (it does not depend on the path): MaxSteps part-way (rows up to the
+    failure), BadInput (h0 larger than the interval / wrong sign), the default h0 = |tf - t0| / 100, a clipped last step,
+    backward time, t_eval points on and between step ends, duplicated and out-of-range points."""
+    n = 256
+    ou = deb.OrnsteinUhlenbeck(0.5, 1.0, 0.3)
+    cases = [
+        (0.0, 1.0, E.euler(0.01).max_steps(37), [0.1, 0.2, 0.5, 0.9]),        # MaxSteps at t = 0.37
+        (0.0, 1.0, E.euler(2.0), [0.5]),                                       # BadInput: h0 > interval
+        (0.0, 1.0, E.euler(-0.01), [0.5]),                                     # BadInput: wrong direction
+        (0.0, 1.0, E.euler(0.0), [0.005, 0.01, 0.5, 1.0]),                     # default h0
+        (0.0, 1.0, E.rk4(0.03), [0.0, 0.03, 0.5, 0.99, 1.0, 1.5, -1.0, 0.5]),  # clipped last step, duplicates, out of range
+        (2.0, -1.0, E.heun(-0.07), [1.93, 0.0, -1.0, 1.0]),                    # backward
+        (0.0, 1.0, deb.Milstein.new(0.013), [0.4, 1.0]),
+        (0.0, 1.0, E.euler(0.25), []),                                         # no rows
+    ]
+    for t0, tf, meth, te in cases:
+        def prob():
+            return deb.EnsembleIVP.sde(ou, t0, tf, np.linspace(0.5, 5.0, n), seed=11, path_offset=5).t_eval(te).method(meth)
+        g, c = prob().solve(), ob.oracle_solve(prob())
+        assert_same_solution(g, c, exact=False, rtol=1e-12)
+
+
 def test_heston_vector_sde_matches_host_regenerated_philox():
     """examples/sde/02_heston_model: two-dimensional state, diagonal noise with correlated increments (rho), three_eighths(dt)
     drift stages, Euler-Maruyama and Milstein; a sweep over rho; sample moments of the price."""
