@@ -166,7 +166,9 @@ def widened(n, reps):
                                           ("RKV766e t_eval", deb.DEB_SYS_LORENZ, deb.DEB_RKV766E, 0), ("RKV767e t_eval", deb.DEB_SYS_LORENZ, deb.DEB_RKV767E, 0),
                                           ("RKV877e t_eval", deb.DEB_SYS_LORENZ, deb.DEB_RKV877E, 0), ("RKV878e t_eval", deb.DEB_SYS_LORENZ, deb.DEB_RKV878E, 0),
                                           ("RKV988e t_eval", deb.DEB_SYS_LORENZ, deb.DEB_RKV988E, 0), ("RKV989e t_eval", deb.DEB_SYS_LORENZ, deb.DEB_RKV989E, 0),
-                                          ("RKV655e even(1.0)", deb.DEB_SYS_LORENZ, deb.DEB_RKV655E, 1)):
+                                          ("RKV655e even(1.0)", deb.DEB_SYS_LORENZ, deb.DEB_RKV655E, 1),
+                                          ("RK4 h=0.01 (10^4 fixed steps) t_eval", deb.DEB_SYS_LORENZ, deb.DEB_RK4, 0),
+                                          ("Euler h=0.01 (10^4 fixed steps) t_eval", deb.DEB_SYS_LORENZ, deb.DEB_EULER, 0)):
         P = deb.OdeProblem()
         P.struct_size = C.sizeof(deb.OdeProblem)
         P.system, P.method, P.dim, P.n_params = system, method, 3, 3
@@ -174,6 +176,9 @@ def widened(n, reps):
         P.n_eval, P.t_eval, P.t0, P.tf = (102 if solout else 100), te.ctypes.data_as(deb._dp), 0.0, 100.0
         lib.deb_erk_options_default(C.byref(P.opt))
         P.opt.rtol = 1e-8
+        if method < deb.DEB_DOPRI5:  # fixed-step constructors take h
+            P.opt.h0 = 0.01
+            P.opt.max_steps = 20000
         P.solout, P.even_dt = solout, 1.0
         P.device, P.memspace, P.stream = 0, deb.DEB_MEM_DEVICE, stream.cuda_stream
         R, bufs = result_buffers(n, 102, 3)
