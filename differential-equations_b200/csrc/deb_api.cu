@@ -984,6 +984,10 @@ extern "C" int deb_solve_sde(const deb_sde_problem* P, deb_result* R) {
     a.n_traj = n;
     a.path_offset = P->path_offset;
     a.seed = P->seed;
+    for (int r = 0; r < 10; r++) {
+        a.round_keys[2 * r] = (unsigned int)(P->seed & 0xffffffffu) + (unsigned int)r * 0x9E3779B9u;
+        a.round_keys[2 * r + 1] = (unsigned int)(P->seed >> 32) + (unsigned int)r * 0xBB67AE85u;
+    }
     a.t0 = P->t0;
     a.tf = P->tf;
     a.h0 = P->opt.h0;

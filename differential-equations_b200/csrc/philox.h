@@ -47,6 +47,21 @@ DEB_PHILOX_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint3
 }
 
 #if defined(__CUDACC__)
+// Philox4x32-10 with the ten round keys (key + r * Weyl constants) given: they depend on the seed only, so the host puts
+// them into the kernel arguments and every XOR takes its key from the constant bank (no per-round key arithmetic).
+__device__ __forceinline__ Philox4 philox4x32_10_keys(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t* rk) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ rk[2 * r], n2 = hi0 ^ c3 ^ rk[2 * r + 1];
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    }
+    Philox4 o;
+    o.w[0] = c0; o.w[1] = c1; o.w[2] = c2; o.w[3] = c3;
+    return o;
+}
+
 // log(u) for u in [2^-53, 1] and sin / cos of 2*pi*u for u in [0, 1), for the Box-Muller transform.  Written out (instead of
 // the CUDA math library's log / sincos) so that every polynomial coefficient is a constant-bank operand of its DFMA: the
 // library versions load their ~30 double constants as 64-bit immediates, two UMOV issue slots each, which was 13 % of all
@@ -104,10 +119,9 @@ __device__ __forceinline__ void deb_sincos_2pi(double u, double* sn, double* cs)
     *cs = ((q + 1) & 2) ? -b : b;
 }
 
-// Both Box-Muller normals of pair index `pair` for path `path`.
-__device__ __forceinline__ void normal_pair(uint64_t seed, uint64_t path, uint64_t pair, double* z_even, double* z_odd) {
-    const Philox4 o = philox4x32_10((uint32_t)pair, (uint32_t)(pair >> 32), (uint32_t)path, (uint32_t)(path >> 32),
-                                    (uint32_t)seed, (uint32_t)(seed >> 32));
+// Both Box-Muller normals of pair index `pair` for path `path`; rk = the ten round keys of the seed.
+__device__ __forceinline__ void normal_pair(const uint32_t* rk, uint64_t path, uint64_t pair, double* z_even, double* z_odd) {
+    const Philox4 o = philox4x32_10_keys((uint32_t)pair, (uint32_t)(pair >> 32), (uint32_t)path, (uint32_t)(path >> 32), rk);
     const uint64_t a = (((uint64_t)o.w[0] << 32) | o.w[1]) >> 11;
     const uint64_t b = (((uint64_t)o.w[2] << 32) | o.w[3]) >> 11;
     const double u1 = (double)(a + 1) * 0x1p-53;

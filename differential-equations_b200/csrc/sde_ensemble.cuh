@@ -21,6 +21,7 @@ struct SdeKernelArgs {
     long long n_traj;
     long long path_offset;
     unsigned long long seed;
+    unsigned int round_keys[20];  // Philox round keys of `seed`: (lo32 + r*0x9E3779B9, hi32 + r*0xBB67AE85), r = 0..9
     double t0, tf, h0, h_min, h_max;
     int max_steps;
     const double* t_rows;
@@ -78,40 +79,8 @@ __global__ void __launch_bounds__(BLOCK) sde_ensemble_kernel(const SdeKernelArgs
         }
         int next_step = (idx < a.n_rows) ? a.row_step[idx] : -1;
         const double sqrt_h0 = sqrt(h0), sqrt_hl = sqrt(a.h_last);
-        double z_odd = 0.0;                          // the odd normal of the last Philox call ...
-        unsigned long long odd_pair = ~0ull;         // ... and its pair index
-        for (int step = 0; step < a.n_steps; step++) {
-            const bool last = (step == a.n_steps - 1);
-            const double h = last ? a.h_last : h0;
-            const double sqrt_h = last ? sqrt_hl : sqrt_h0;
-            const unsigned long long q0 = (unsigned long long)step * N;  // first normal index of this step
-            double dw[N];  // noise(h, dw)
-            if constexpr (N % 2 == 0) {
-                // even dimension: the step's normals are whole Philox pairs
-#pragma unroll
-                for (int c = 0; c < N; c += 2) {
-                    double ze, zo;
-                    normal_pair(a.seed, path, (q0 + c) >> 1, &ze, &zo);
-                    dw[c] = sqrt_h * ze;
-                    dw[c + 1] = sqrt_h * zo;
-                }
-            } else if constexpr (N == 1) {
-                // one normal per step: every other step reuses the odd normal of the previous call
-                double z;
-                if ((q0 & 1ull) == 0) normal_pair(a.seed, path, q0 >> 1, &z, &z_odd);
-                else z = z_odd;
-                dw[0] = sqrt_h * z;
-            } else {
-#pragma unroll
-                for (int c = 0; c < N; c++) {
-                    const unsigned long long q = q0 + c;
-                    double z;
-                    if ((q & 1ull) == 0) { normal_pair(a.seed, path, q >> 1, &z, &z_odd); odd_pair = q >> 1; }
-                    else if (odd_pair == (q >> 1)) z = z_odd;
-                    else { double ze; normal_pair(a.seed, path, q >> 1, &ze, &z); }
-                    dw[c] = sqrt_h * z;
-                }
-            }
+        // one step from (t, y, dydt) with the Wiener increments dw
+        auto do_step = [&](const int step, const double h, const double sqrt_h, double (&dw)[N]) {
             Sde::mix(dw, p);
             double y_next[N], g[N];
             Sde::diffusion(t, y, g, p);  // stochastic.rs:113-115 / milstein.rs:127-130
@@ -181,6 +150,48 @@ __global__ void __launch_bounds__(BLOCK) sde_ensemble_kernel(const SdeKernelArgs
             t = t_new;
 #pragma unroll
             for (int c = 0; c < N; c++) { y[c] = y_next[c]; dydt[c] = d_new[c]; }
+        };
+        // noise(h, dw): component c of step s is normal number s*N + c of the path's stream, times sqrt(h)
+        int step = 0;
+        if constexpr (N == 1) {
+            // one normal per step: a Philox call feeds two consecutive steps; all but the last step have size h0
+            for (; step + 2 < a.n_steps; step += 2) {
+                double ze, zo;
+                normal_pair(a.round_keys, path, (unsigned long long)(step >> 1), &ze, &zo);
+                double dw0[1] = {sqrt_h0 * ze}, dw1[1] = {sqrt_h0 * zo};
+                do_step(step, h0, sqrt_h0, dw0);
+                do_step(step + 1, h0, sqrt_h0, dw1);
+            }
+        }
+        double z_odd = 0.0;                          // the odd normal of the last Philox call ...
+        unsigned long long odd_pair = ~0ull;         // ... and its pair index
+        for (; step < a.n_steps; step++) {
+            const bool last = (step == a.n_steps - 1);
+            const double h = last ? a.h_last : h0;
+            const double sqrt_h = last ? sqrt_hl : sqrt_h0;
+            const unsigned long long q0 = (unsigned long long)step * N;  // first normal index of this step
+            double dw[N];
+            if constexpr (N % 2 == 0) {
+                // even dimension: the step's normals are whole Philox pairs
+#pragma unroll
+                for (int c = 0; c < N; c += 2) {
+                    double ze, zo;
+                    normal_pair(a.round_keys, path, (q0 + c) >> 1, &ze, &zo);
+                    dw[c] = sqrt_h * ze;
+                    dw[c + 1] = sqrt_h * zo;
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < N; c++) {
+                    const unsigned long long q = q0 + c;
+                    double z;
+                    if ((q & 1ull) == 0) { normal_pair(a.round_keys, path, q >> 1, &z, &z_odd); odd_pair = q >> 1; }
+                    else if (odd_pair == (q >> 1)) z = z_odd;
+                    else { double ze; normal_pair(a.round_keys, path, q >> 1, &ze, &z); }
+                    dw[c] = sqrt_h * z;
+                }
+            }
+            do_step(step, h, sqrt_h, dw);
         }
         const int fin = a.final_status;
         const int steps = a.n_steps;
