@@ -703,6 +703,46 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P, deb_result* R) {
     a.max_scale = P->opt.max_scale;
     a.max_steps = (int)std::min<int64_t>(P->opt.max_steps, 0x7fffffff / 16);
     a.max_rejects = (int)std::min<int64_t>(std::max<int64_t>(P->opt.max_rejects, 0), 0x7fffffff);
+    {   // fixed-step methods: the step schedule is the same for every trajectory; run the solve_ode bookkeeping here
+        // (validate_step_size_parameters utils.rs:60-157 with the method's h_min / h_max; loop solve_ivp.rs:193-209, :263)
+        bool adaptive_m = false;
+        method_tab_name(P->method, &adaptive_m);
+        a.fx_n_steps = 0;
+        a.fx_h_last = 0.0;
+        a.fx_status = DEB_STATUS_COMPLETE;
+        if (!adaptive_m) {
+            const double t0 = P->t0, tf = P->tf;
+            const double dd = tf - t0;
+            const double dir = (dd != dd) ? dd : copysign(1.0, dd);
+            double h = P->opt.h0;
+            if (h == 0.0) h = fabs(tf - t0) / 100.0;
+            const double sgh = (h != h) ? h : copysign(1.0, h);
+            const bool ok = (tf != t0) && (dir == 1.0 || dir == -1.0) && sgh == dir && !(P->opt.h_min < 0.0) && !(P->opt.h_max < 0.0) &&
+                            !(P->opt.h_min > P->opt.h_max) && !(fabs(h) < P->opt.h_min) && !(fabs(h) > P->opt.h_max) &&
+                            !(fabs(h) > fabs(tf - t0)) && h != 0.0;
+            a.fx_h_last = h;
+            if (!ok) {
+                a.fx_status = DEB_STATUS_BAD_INPUT;
+            } else {
+                const double eps10 = 2.220446049250313e-16 * 10.0;
+                double t = t0;
+                long long steps = 0;
+                for (;;) {
+                    if ((t + h - tf) * dir > 0.0) {
+                        const double h_new = tf - t;
+                        if (fabs(h_new) < eps10) break;
+                        h = h_new;
+                    }
+                    if (steps >= a.max_steps) { a.fx_status = DEB_STATUS_MAX_STEPS; break; }
+                    steps += 1;
+                    a.fx_h_last = h;  // only the final step can differ from h0 (the clip at tf)
+                    t += h;
+                    if (fabs(tf - t) <= eps10) break;
+                }
+                a.fx_n_steps = (int)steps;
+            }
+        }
+    }
     a.n_rows = (int)plan.rows.size();
     a.row_stride = row_cap;
     a.emit_t0 = plan.emit_t0 ? 1 : 0;

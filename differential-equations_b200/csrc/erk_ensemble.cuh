@@ -55,6 +55,12 @@ struct OdeKernelArgs {
     int event_direction;    // 0 both, +1 positive, -1 negative
     int event_terminate;    // stop after this many events (0 = never)
     double event_coef[DEB_MAX_DIM + 2];  // EvtLinear: g = c0 + c1*t + sum c[2+i]*y[i]
+    // fixed-step kernels: the step schedule does not depend on the trajectory (same t0, tf, h for all), so the host runs the
+    // solve_ode bookkeeping (solve_ivp.rs:193-209, :263; fixed/ordinary.rs:16-56, :66-75) once: fx_n_steps steps of size
+    // h0 (|tf-t0|/100 when h0 = 0), the last one of size fx_h_last, ending with status fx_status (BAD_INPUT: no steps)
+    int fx_n_steps;
+    double fx_h_last;
+    int fx_status;
     // HyperplaneCrossingSolout: signed distance of the extracted components to the plane (normal already normalised)
     int plane_dim;
     int plane_index[DEB_MAX_DIM];

@@ -19,7 +19,6 @@ __global__ void __launch_bounds__(BLOCK) fixed_ensemble_kernel(const OdeKernelAr
     constexpr int N = Sys::DIM, NP = Sys::NP, S = Tab::S;
     const double t0 = a.t0, tf = a.tf;
     const double dir = d_signum(tf - t0);
-    const double eps10 = DBL_EPSILON * 10.0;
     const double te_none = (dir > 0.0) ? (1.0 / 0.0) : -(1.0 / 0.0);
     const long long stride = (long long)gridDim.x * BLOCK;
 
@@ -33,10 +32,10 @@ __global__ void __launch_bounds__(BLOCK) fixed_ensemble_kernel(const OdeKernelAr
         int fin = -1;
         StepRecorder<Sys, Tab, Evt> recd;
         double t = t0;
-        // ---- init, fixed/ordinary.rs:16-56
-        double h = a.h0;
-        if (h == 0.0) h = fabs(tf - t0) / 100.0;
-        if (!validate_step_size_parameters(h, a.h_min, a.h_max, t0, tf)) {
+        // ---- init, fixed/ordinary.rs:16-56 (BadInput was decided on the host: utils.rs:60-157 does not look at the state)
+        const double h_full = (a.h0 == 0.0) ? fabs(tf - t0) / 100.0 : a.h0;
+        double h = h_full;
+        if (a.fx_status == DEB_STATUS_BAD_INPUT) {
             fin = DEB_STATUS_BAD_INPUT;
         } else {
             Sys::rhs(t, y, dydt, p);
@@ -52,16 +51,11 @@ __global__ void __launch_bounds__(BLOCK) fixed_ensemble_kernel(const OdeKernelAr
             if constexpr (REC) recd.first(a, traj, t0, y, p);  // the solout call that precedes the loop
         }
         double te = (idx < a.n_rows) ? a.t_rows[idx] : te_none;
-        while (fin < 0) {
-            // ---- loop head, solve_ivp.rs:193-209
-            if ((t + h - tf) * dir > 0.0) {
-                const double h_new = tf - t;
-                if (fabs(h_new) < eps10) { fin = DEB_STATUS_COMPLETE; break; }
-                h = h_new;
-            }
-            // ---- step, fixed/ordinary.rs:58-139
-            if (steps >= a.max_steps) { fin = DEB_STATUS_MAX_STEPS; break; }
+        // the loop head (clip at tf, solve_ivp.rs:193-209), the max_steps test and the end test (:263) ran on the host
+        for (int step = 0; fin < 0 && step < a.fx_n_steps; step++) {
+            h = (step == a.fx_n_steps - 1) ? a.fx_h_last : h_full;
             steps += 1;
+            // ---- step, fixed/ordinary.rs:58-139
 #pragma unroll
             for (int c = 0; c < N; c++) k[0][c] = dydt[c];
 #pragma unroll
@@ -147,9 +141,9 @@ __global__ void __launch_bounds__(BLOCK) fixed_ensemble_kernel(const OdeKernelAr
             t = t_new;
 #pragma unroll
             for (int c = 0; c < N; c++) { y[c] = ynew[c]; dydt[c] = dnew[c]; }
-            if (fabs(tf - t) <= eps10) fin = DEB_STATUS_COMPLETE;  // solve_ivp.rs:263
             if (REC && interrupt) fin = DEB_STATUS_INTERRUPTED;    // solve_ivp.rs:255-260 (an event asked to terminate)
         }
+        if (fin < 0) fin = a.fx_status;  // Complete, or MaxSteps after fx_n_steps steps
         if (a.status) a.status[traj] = fin;
         if (a.t_final) a.t_final[traj] = t;
         if (a.y_final) {
