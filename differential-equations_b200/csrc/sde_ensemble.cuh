@@ -54,9 +54,10 @@ __global__ void __launch_bounds__(BLOCK) sde_ensemble_kernel(const SdeKernelArgs
     const long long stride = (long long)gridDim.x * BLOCK;
 
     for (long long traj = (long long)blockIdx.x * BLOCK + threadIdx.x; traj < a.n_traj; traj += stride) {
-        double p[NP > 0 ? NP : 1];
+        double p[(NP + Sde::NPX) > 0 ? (NP + Sde::NPX) : 1];
 #pragma unroll
         for (int q = 0; q < NP; q++) p[q] = a.params ? a.params[traj * a.params_stride + q] : a.pc[q];
+        Sde::prepare(p);
         double y[N], dydt[N];
 #pragma unroll
         for (int c = 0; c < N; c++) { y[c] = a.y0[traj * a.y0_stride + c]; dydt[c] = 0.0; }

@@ -66,20 +66,24 @@ struct SysRobertson {  // systems.rs:161-173 (stiff; the reference tests DOP853/
 
 // SDEs with diagonal noise (`SDE::drift` / `SDE::diffusion`, /root/reference/src/sde/sde.rs:16-52).  `mix` is what the
 // system's `SDE::noise` does with the independent Wiener increments of the library's Philox stream.
+// NPX extra parameter slots hold per-path constants that `prepare` derives once (loop-invariant parts of `mix`).
 struct SdeOU {  // examples/sde/03_ornstein_uhlenbeck/main.rs:42-49
-    static constexpr int DIM = 1, NP = 3;
+    static constexpr int DIM = 1, NP = 3, NPX = 0;
+    __device__ __forceinline__ static void prepare(double*) {}
     __device__ __forceinline__ static void drift(double, const double* y, double* d, const double* p) { d[0] = p[0] * (p[1] - y[0]); }
     __device__ __forceinline__ static void diffusion(double, const double*, double* g, const double* p) { g[0] = p[2]; }
     __device__ __forceinline__ static void mix(double*, const double*) {}
 };
 struct SdeGBM {  // src/sde/solve_ivp.rs doc example: drift mu*y, diffusion sigma*y
-    static constexpr int DIM = 1, NP = 2;
+    static constexpr int DIM = 1, NP = 2, NPX = 0;
+    __device__ __forceinline__ static void prepare(double*) {}
     __device__ __forceinline__ static void drift(double, const double* y, double* d, const double* p) { d[0] = p[0] * y[0]; }
     __device__ __forceinline__ static void diffusion(double, const double* y, double* g, const double* p) { g[0] = p[1] * y[0]; }
     __device__ __forceinline__ static void mix(double*, const double*) {}
 };
 struct SdeHeston {  // examples/sde/02_heston_model/main.rs:53-72; p = {mu, kappa, theta, sigma, rho}, y = {price, variance}
-    static constexpr int DIM = 2, NP = 5;
+    static constexpr int DIM = 2, NP = 5, NPX = 1;
+    __device__ __forceinline__ static void prepare(double* p) { p[5] = sqrt(1.0 - p[4] * p[4]); }  // the same value every step
     __device__ __forceinline__ static void drift(double, const double* y, double* d, const double* p) {
         d[0] = p[0] * y[0];
         d[1] = p[1] * (p[2] - y[1]);
@@ -88,7 +92,7 @@ struct SdeHeston {  // examples/sde/02_heston_model/main.rs:53-72; p = {mu, kapp
         g[0] = y[0] * sqrt(y[1]);
         g[1] = p[3] * sqrt(y[1]);
     }
-    __device__ __forceinline__ static void mix(double* dw, const double* p) { dw[1] = p[4] * dw[0] + sqrt(1.0 - p[4] * p[4]) * dw[1]; }
+    __device__ __forceinline__ static void mix(double* dw, const double* p) { dw[1] = p[4] * dw[0] + p[5] * dw[1]; }
 };
 
 }  // namespace deb
