@@ -55,6 +55,9 @@ int main(void) {
   printf("%zu %zu %zu %zu\n", offsetof(deb_ode_problem, opt), offsetof(deb_ode_problem, device), offsetof(deb_result, n_rows), offsetof(deb_heat_problem, status));
   printf("%zu\n", offsetof(deb_ode_problem, even_dt));
   printf("%zu %zu\n", offsetof(deb_sde_problem, seed), offsetof(deb_sde_problem, device));
+  printf("%zu %zu %zu %zu %zu %zu %zu\n", offsetof(deb_ode_problem, dense_n), offsetof(deb_ode_problem, cross_threshold), offsetof(deb_ode_problem, event),
+         offsetof(deb_ode_problem, row_capacity), offsetof(deb_ode_problem, event_coef), offsetof(deb_ode_problem, plane_dim), offsetof(deb_ode_problem, plane_normal));
+  printf("%zu\n", offsetof(deb_result, t_out));
   return 0; }'''
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "s.c"), "w").write(src)
@@ -65,6 +68,8 @@ int main(void) {
             deb.OdeProblem.opt.offset, deb.OdeProblem.device.offset, deb.Result.n_rows.offset, deb.HeatProblem.status.offset,
             deb.SdeProblem.seed.offset, deb.SdeProblem.device.offset]
     want.insert(9, deb.OdeProblem.even_dt.offset)
+    want += [deb.OdeProblem.dense_n.offset, deb.OdeProblem.cross_threshold.offset, deb.OdeProblem.event.offset, deb.OdeProblem.row_capacity.offset,
+             deb.OdeProblem.event_coef.offset, deb.OdeProblem.plane_dim.offset, deb.OdeProblem.plane_normal.offset, deb.Result.t_out.offset]
     assert got == want
 
 
