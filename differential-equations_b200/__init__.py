@@ -54,7 +54,10 @@ DEB_EVENT_NONE, DEB_EVENT_LINEAR = 0, 1
 DEB_MAX_DIM = 16
 DEB_STATUS_INTERRUPTED = 5
 DEB_OK, DEB_ERR_BAD_ARG, DEB_ERR_NO_DEVICE, DEB_ERR_CUDA, DEB_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
-DEB_ABI_VERSION = 8
+DEB_ABI_VERSION = 9
+DEB_MAX_DEVICES = 16
+DEB_LAYOUT_TRAJ_MAJOR, DEB_LAYOUT_ROW_MAJOR = 0, 1
+DEB_FILTER_IDENTITY, DEB_FILTER_TRUNCATE_MANTISSA = 0, 1
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -76,7 +79,10 @@ class OdeProblem(C.Structure):
                 ("event", C.c_int32), ("event_direction", C.c_int32), ("event_terminate", C.c_int32), ("row_capacity", C.c_int32),
                 ("event_coef", C.c_double * (DEB_MAX_DIM + 2)),
                 ("plane_dim", C.c_int32), ("plane_index", C.c_int32 * DEB_MAX_DIM), ("plane_point", C.c_double * DEB_MAX_DIM),
-                ("plane_normal", C.c_double * DEB_MAX_DIM)]
+                ("plane_normal", C.c_double * DEB_MAX_DIM),
+                # appended in ABI 9
+                ("filter", C.c_int32), ("filter_bits", C.c_int32), ("layout", C.c_int32), ("n_devices", C.c_int32),
+                ("devices", C.c_int32 * DEB_MAX_DEVICES)]
 
 
 class SdeProblem(C.Structure):
@@ -91,7 +97,9 @@ class Result(C.Structure):
     _fields_ = [("struct_size", C.c_size_t), ("y_eval", C.c_void_p), ("n_emitted", C.c_void_p), ("t_final", C.c_void_p),
                 ("y_final", C.c_void_p), ("status", C.c_void_p), ("accepted", C.c_void_p), ("rejected", C.c_void_p),
                 ("evals", C.c_void_p), ("t_rows", _dp), ("n_rows", C.c_int32), ("kernel_ms", C.c_float),
-                ("total_ms", C.c_float), ("t_out", C.c_void_p)]
+                ("total_ms", C.c_float), ("t_out", C.c_void_p),
+                # appended in ABI 9
+                ("stats_sums", C.c_void_p), ("stats_counts", C.c_void_p), ("gpu_launches", C.c_int32), ("reserved0", C.c_int32)]
 
 
 class HeatProblem(C.Structure):
@@ -104,7 +112,8 @@ class HeatProblem(C.Structure):
 
 
 # every symbol include/deb_ensemble.h declares (tests check that the library exports all of them)
-ABI_SYMBOLS = ["deb_abi_version", "deb_last_error", "deb_device_count", "deb_erk_options_default", "deb_define_ode", "deb_define_event", "deb_check_ode", "deb_trim_memory", "deb_solve_ode",
+ABI_SYMBOLS = ["deb_abi_version", "deb_last_error", "deb_device_count", "deb_erk_options_default", "deb_define_ode", "deb_define_event",
+               "deb_define_sde", "deb_check_sde", "deb_define_ode_sensitivity", "deb_launch_count", "deb_check_ode", "deb_trim_memory", "deb_solve_ode",
                "deb_solve_sde", "deb_solve_heat_mol", "deb_heat_rhs", "deb_ensemble_stats", "deb_malloc", "deb_free", "deb_memcpy_h2d",
                "deb_memcpy_d2h", "deb_synchronize", "deb_pow_device", "deb_fp64_issue_peak"]
 
@@ -132,6 +141,10 @@ def load_library() -> C.CDLL:
     lib.deb_define_ode.argtypes = [C.c_int32, C.c_int32, C.c_char_p, _ip]
     lib.deb_check_ode.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32]
     lib.deb_define_event.argtypes = [C.c_int32, C.c_char_p, _ip]
+    lib.deb_define_sde.argtypes = [C.c_int32, C.c_int32, C.c_char_p, C.c_char_p, C.c_char_p, _ip]
+    lib.deb_check_sde.argtypes = [C.c_int32, C.c_int32]
+    lib.deb_define_ode_sensitivity.argtypes = [C.c_int32, C.c_int32, C.c_char_p, C.c_char_p, C.c_char_p, _ip]
+    lib.deb_launch_count.restype = C.c_int64
     lib.deb_heat_rhs.argtypes = [C.POINTER(HeatProblem), C.c_void_p, C.c_void_p]
     lib.deb_erk_options_default.argtypes = [C.POINTER(ErkOptions)]
     lib.deb_erk_options_default.restype = None
@@ -249,6 +262,22 @@ def check_ode(system: OdeSystem, method, solout: int = DEB_SOLOUT_T_EVAL, event=
     _check(lib, lib.deb_check_ode(int(system.system_id), mid, int(solout), int(eid)), "deb_check_ode")
 
 
+def ode_sensitivity_from_source(dim: int, diff_body: str, jac_y_body: str, jac_p_body: str, params, lib=None) -> OdeSystem:
+    """`ForwardSensitivityOde::new(ode, y_proto)` (src/ode/sensitivity/forward.rs:43-116) for the device: the augmented system
+    [y, S] with S' = J_y S + J_p (S row-major after y, S[r][c] = dy_r/dp_c) is generated from the bodies of
+    `diff(t, y, dydt, p)`, `jacobian(t, y, J, p)` (J[r*dim + k], zeroed) and `jacobian_p(t, y, Jp, p)` (Jp[r*m + c], zeroed).
+    The returned system has dimension dim*(1 + len(params)); start it from [y0, 0...]."""
+    lib = lib or load_library()
+    prm = np.ascontiguousarray(params, dtype=np.float64)
+    if prm.ndim == 0:
+        prm = prm.reshape(1)
+    m = int(prm.shape[-1])
+    sid = C.c_int32(-1)
+    _check(lib, lib.deb_define_ode_sensitivity(int(dim), m, diff_body.encode(), jac_y_body.encode(), jac_p_body.encode(), C.byref(sid)),
+           "deb_define_ode_sensitivity")
+    return OdeSystem(sid.value, int(dim) * (1 + m), prm)
+
+
 @dataclass
 class EventSpec:
     """Mirror of an `impl Event` (src/solout/event.rs:60-70): the function g(t, y) whose zero crossings are located."""
@@ -283,6 +312,21 @@ def HestonModel(mu, kappa, theta, sigma, rho):  # examples/sde/02_heston_model/m
     return SdeSystem(DEB_SDE_HESTON, _params(mu, kappa, theta, sigma, rho), 2)
 
 
+def sde_from_source(dim: int, drift_body: str, diffusion_body: str, params=(), noise_body: Optional[str] = None, lib=None) -> SdeSystem:
+    """`impl SDE for S { fn drift; fn diffusion; fn noise }` (src/sde/sde.rs:16-67) for the device: the bodies of
+    `drift(t, y, dydt, p)`, `diffusion(t, y, g, p)` (diagonal noise: dY_c += g[c]*dW_c) and, optionally, `noise(dw, p)` which
+    mixes the independent N(0, h) increments of the library's Philox stream in place (e.g. Heston's correlation), as CUDA C++
+    text.  Compiled at first use (NVRTC)."""
+    lib = lib or load_library()
+    prm = np.ascontiguousarray(params, dtype=np.float64)
+    if prm.ndim == 0:
+        prm = prm.reshape(1)
+    sid = C.c_int32(-1)
+    _check(lib, lib.deb_define_sde(int(dim), int(prm.shape[-1]), drift_body.encode(), diffusion_body.encode(),
+                                   noise_body.encode() if noise_body else None, C.byref(sid)), "deb_define_sde")
+    return SdeSystem(sid.value, prm, int(dim))
+
+
 def _params(*cols) -> np.ndarray:
     arrs = [np.asarray(c, dtype=np.float64) for c in cols]
     if all(a.ndim == 0 for a in arrs):
@@ -310,6 +354,7 @@ class ExplicitRungeKutta:
         self._safety_factor = 0.9
         self._min_scale = 0.2
         self._max_scale = 10.0
+        self._filter = (DEB_FILTER_IDENTITY, 0)
 
     # constructors: dormandprince/mod.rs:45-58, fixed/mod.rs:41-89
     @classmethod
@@ -362,6 +407,12 @@ class ExplicitRungeKutta:
     def safety_factor(self, v): self._safety_factor = float(v); return self
     def min_scale(self, v): self._min_scale = float(v); return self
     def max_scale(self, v): self._max_scale = float(v); return self
+
+    def filter_truncate_mantissa(self, bits: int):
+        """`.filter(|h| f64::from_bits(h.to_bits() & MASK))` (erk/mod.rs:225) with MASK keeping the leading `bits` mantissa
+        bits: the built-in step-size filter that can cross the C ABI (a Rust fn pointer cannot)."""
+        self._filter = (DEB_FILTER_TRUNCATE_MANTISSA, int(bits))
+        return self
 
     def fill_options(self, opt: ErkOptions, dim: int, keep: list):
         def tol(v, name):
@@ -463,7 +514,7 @@ def alloc_result_arrays(n, n_eval, dim, with_times=False):
 
 def bind_result(res: Result, arrs: dict, t_sorted: np.ndarray):
     res.struct_size = C.sizeof(Result)
-    for k in ("y_eval", "n_emitted", "t_final", "y_final", "status", "accepted", "rejected", "evals", "t_out"):
+    for k in ("y_eval", "n_emitted", "t_final", "y_final", "status", "accepted", "rejected", "evals", "t_out", "stats_sums", "stats_counts"):
         a = arrs.get(k)
         setattr(res, k, a.ctypes.data if a is not None and a.size > 0 else None)
     res.t_rows = t_sorted.ctypes.data_as(_dp) if t_sorted.size else None
@@ -491,6 +542,9 @@ class EnsembleIVP:
         self._event = None     # (EventSpec, direction, terminate count or 0, extra rows)
         self._method: Optional[ExplicitRungeKutta] = None
         self._device = 0
+        self._devices: List[int] = []
+        self._layout = DEB_LAYOUT_TRAJ_MAJOR
+        self._stats = False
         self.seed, self.path_offset = int(seed), int(path_offset)
 
     @classmethod
@@ -573,6 +627,23 @@ class EnsembleIVP:
         self._device = int(ordinal)
         return self
 
+    def devices(self, ordinals: Sequence[int]):
+        """Split the ensemble over several GPUs inside one solve() (deb_ode_problem.devices): blocks of 4096 trajectories
+        dealt round-robin, one host thread and one persistent kernel per device, results exactly as for one device."""
+        self._devices = [int(d) for d in ordinals]
+        return self
+
+    def layout(self, layout: int):
+        """DEB_LAYOUT_TRAJ_MAJOR (default, y_eval[i][r][c]) or DEB_LAYOUT_ROW_MAJOR (y_eval[r][c][i])."""
+        self._layout = int(layout)
+        return self
+
+    def with_stats(self, on: bool = True):
+        """Also reduce the per-t_eval ensemble sums {sum y, sum y^2} and counts on the device(s) (all-reduced across the
+        devices of the call): EnsembleSolution.stats_sums (n_eval, dim, 2) and .stats_counts (n_eval)."""
+        self._stats = bool(on)
+        return self
+
     def build_problem(self):
         """Assemble the C-ABI problem/result structs for this builder (host buffers).  Returns
         (problem, result, result_arrays, t_sorted, keepalive)."""
@@ -636,6 +707,17 @@ class EnsembleIVP:
         self._method.fill_options(P.opt, dim, keep)
         P.device, P.memspace, P.stream = self._device, DEB_MEM_HOST, None
         arrs = alloc_result_arrays(n, rows_cap, dim, with_times=(self._recorder is not None or (self.kind == "ode" and self._event is not None)))
+        if self.kind == "ode":
+            P.filter, P.filter_bits = self._method._filter
+            P.layout = self._layout
+            if self._layout == DEB_LAYOUT_ROW_MAJOR:
+                arrs["y_eval"] = np.full((max(rows_cap, 0), dim, n), np.nan)
+            P.n_devices = len(self._devices)
+            for q, d in enumerate(self._devices):
+                P.devices[q] = d
+            if self._stats:
+                arrs["stats_sums"] = np.zeros((max(rows_cap, 0), dim, 2))
+                arrs["stats_counts"] = np.zeros(max(rows_cap, 0), np.int64)
         bind_result(res, arrs, t_sorted)
         keep += [params, self.y0s, self._t_eval]
         return P, res, arrs, t_sorted, keep
@@ -660,6 +742,11 @@ class EnsembleIVP:
         if self._even_dt > 0.0:
             sol.even_tf = self.tf  # EvenSolout: a trajectory that lands exactly on tf has its last row at tf
         sol.t_out = arrs.get("t_out")
+        sol.stats_sums, sol.stats_counts = arrs.get("stats_sums"), arrs.get("stats_counts")
+        sol.gpu_launches = int(res.gpu_launches)
+        if self.kind == "ode" and self._layout == DEB_LAYOUT_ROW_MAJOR:
+            sol.y_eval_row_major = sol.y_eval                       # (n_eval, dim, N) as the library wrote it
+            sol.y_eval = np.ascontiguousarray(np.transpose(sol.y_eval, (2, 0, 1)))  # per-trajectory view for Solution
         return sol
 
 

@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(512) stats_partial_kernel(const double* __rest
 
 // One warp per element: lanes stride over the CTAs' partials, then a fixed-order shuffle tree.
 __global__ void __launch_bounds__(128) stats_final_kernel(const double* partial, const long long* pcount, int n_cta, int n_eval, int dim,
-                                                         double* sums, long long* counts) {
+                                                         double* sums, long long* counts, int accumulate) {
     const int ne = n_eval * dim;
     const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -69,10 +69,10 @@ __global__ void __launch_bounds__(128) stats_final_kernel(const double* partial,
         s2 += __shfl_down_sync(0xffffffffu, s2, o);
         cnt += __shfl_down_sync(0xffffffffu, cnt, o);
     }
-    if (lane == 0) {
-        sums[e * 2 + 0] = s;
-        sums[e * 2 + 1] = s2;
-        if (e % dim == 0) counts[e / dim] = cnt;
+    if (lane == 0) {  // accumulate: add to what the previous chunks of the ensemble left (chunk order is fixed: deterministic)
+        sums[e * 2 + 0] = accumulate ? sums[e * 2 + 0] + s : s;
+        sums[e * 2 + 1] = accumulate ? sums[e * 2 + 1] + s2 : s2;
+        if (e % dim == 0) counts[e / dim] = accumulate ? counts[e / dim] + cnt : cnt;
     }
 }
 

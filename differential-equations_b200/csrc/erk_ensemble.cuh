@@ -26,6 +26,8 @@
 
 namespace deb {
 
+constexpr int DEB_FX_MAX_TAIL = 4;
+
 struct OdeKernelArgs {
     const double* y0;       // [n_traj][DIM]
     const double* params;   // [n_traj][NP] or [NP]
@@ -56,10 +58,13 @@ struct OdeKernelArgs {
     int event_terminate;    // stop after this many events (0 = never)
     double event_coef[DEB_MAX_DIM + 2];  // EvtLinear: g = c0 + c1*t + sum c[2+i]*y[i]
     // fixed-step kernels: the step schedule does not depend on the trajectory (same t0, tf, h for all), so the host runs the
-    // solve_ode bookkeeping (solve_ivp.rs:193-209, :263; fixed/ordinary.rs:16-56, :66-75) once: fx_n_steps steps of size
-    // h0 (|tf-t0|/100 when h0 = 0), the last one of size fx_h_last, ending with status fx_status (BAD_INPUT: no steps)
+    // solve_ode bookkeeping (solve_ivp.rs:193-209, :263; fixed/ordinary.rs:16-56, :66-75) once: fx_n_steps steps, all of
+    // size h0 (|tf-t0|/100 when h0 = 0) except the last fx_n_tail ones, whose sizes are fx_h_tail[0..fx_n_tail) -- the clip
+    // at tf can fire more than once (t + (tf - t) may miss tf by an ulp, which exceeds 10 eps for |tf| > 10: one more tiny
+    // step).  fx_n_tail >= 1 whenever fx_n_steps >= 1.  Ends with status fx_status (BAD_INPUT: no steps)
     int fx_n_steps;
-    double fx_h_last;
+    int fx_n_tail;
+    double fx_h_tail[DEB_FX_MAX_TAIL];
     int fx_status;
     // HyperplaneCrossingSolout: signed distance of the extracted components to the plane (normal already normalised)
     int plane_dim;
@@ -74,6 +79,115 @@ struct OdeKernelArgs {
     int* rejected;
     int* evals;
     unsigned long long* queue;  // next unclaimed trajectory index
+    // Completion watermark for the streamed result copy of DEB_MEM_HOST calls (deb_api.cu): wm_done[b] counts the
+    // written-out trajectories of block b = traj >> wm_shift; the lane that completes a block raises wm_ready[b] (pinned
+    // host memory the host polls) behind a system-scope fence, and the host copies finished blocks out while the kernel
+    // is still integrating the rest.  Null: no watermark.
+    int* wm_done;
+    int* wm_ready;
+    int wm_shift;
+    int rows_vec;  // y_eval row groups (RowStage) start 32-byte aligned: whole-sector 16-byte vector stores are safe
+    // step-size filter (erk/mod.rs:225): 0 = identity, else h = from_bits(to_bits(h) & filter_mask) (mantissa truncation)
+    unsigned long long filter_mask;
+};
+
+// see OdeKernelArgs::wm_done.  Called by the lane that has just written every output of trajectory `traj`.
+__device__ __forceinline__ void wm_publish(const OdeKernelArgs& a, long long traj) {
+    if (a.wm_done) {
+        __threadfence();  // this trajectory's rows and final fields are visible device-wide before it is counted
+        const long long b = traj >> a.wm_shift;
+        const long long left = a.n_traj - (b << a.wm_shift);
+        const long long full = 1ll << a.wm_shift;
+        const int expected = (int)(left < full ? left : full);
+        if (atomicAdd(a.wm_done + b, 1) == expected - 1) {
+            __threadfence_system();  // cumulative: everything the other lanes fenced before their count is ordered before the flag
+            *(volatile int*)(a.wm_ready + b) = 1;
+        }
+    }
+}
+
+// FILTER kernels only (compiled at first use: the ahead-of-time instantiations carry no filter code at all)
+__device__ __forceinline__ double apply_filter(const OdeKernelArgs& a, double h) {
+    return __longlong_as_double((long long)((unsigned long long)__double_as_longlong(h) & a.filter_mask));
+}
+
+// Row staging for the t_eval / even(dt) recorders ("output rows written to HBM as coalesced, vectorised stores").
+// A trajectory's rows form one contiguous block of y_eval (row_stride * N doubles) and arrive one at a time, each an
+// 8N-byte piece: written directly, a 24-byte Lorenz row covers parts of two 32-byte sectors, and because the block of a
+// trajectory stays open for its whole lifetime (~100 rows over ~1500 steps, 95 k trajectories in flight: more than L2)
+// the partial sectors reach DRAM as read-modify-write (measured in round 1: 1.59x the algorithmic traffic).
+// Instead each lane collects ROWG = 4/gcd(N,4) consecutive rows -- a multiple of 32 bytes -- in shared memory and
+// writes the group at once: whole sectors, 16-byte vector stores, no fill reads.  Groups are aligned to the start of
+// the trajectory's block; `rows_vec` says whether that is 32-byte aligned (row_stride*N % 4 == 0), else scalar stores.
+// Writes one complete row group from a lane's column of the staging buffer (element e at src[e * stride]).  Deliberately
+// NOT inlined: the kernels that call it keep ~90 registers of trajectory state live across the call site, and inlining the
+// group copy there made ptxas spill loop-carried state of the hot loop (measured: 8 local-memory instructions per step
+// attempt); as a call, only the call site pays.
+template <int CNT>
+__device__ __noinline__ void store_row_group(double* dst, const double* src, int stride, int vec) {
+    if (vec) {
+#pragma unroll
+        for (int e = 0; e < CNT; e += 2) *reinterpret_cast<double2*>(dst + e) = make_double2(src[e * stride], src[(e + 1) * stride]);
+    } else {
+#pragma unroll
+        for (int e = 0; e < CNT; e++) dst[e] = src[e * stride];
+    }
+}
+
+template <int N, int BLOCK, bool ON = true>
+struct RowStage {
+    static constexpr int G4 = (N % 4 == 0) ? 4 : (N % 2 == 0) ? 2 : 1;  // gcd(N, 4)
+    static constexpr int ROWG = 4 / G4;
+    static constexpr bool ENABLED = ON && (ROWG > 1) && (ROWG * N * BLOCK * 8 <= 16 * 1024);
+    static constexpr int SLOTS = ENABLED ? ROWG * N : 1;
+
+    // row w of trajectory `traj`; `emitted` = rows emitted before this call (w == emitted for an append; w == emitted - 1
+    // when EvenSolout replaces its last point, even.rs:166-188)
+    // buf: the lane's warp-private staging rows, buf[slot][lane] (same base register as the parked-step stash)
+    __device__ __forceinline__ static void put(const OdeKernelArgs& a, double (*buf)[32], unsigned lane, long long traj, int w, int emitted,
+                                               const double (&row)[N]) {
+        if constexpr (ENABLED) {
+            if (w / ROWG == emitted / ROWG) {  // the group being collected
+                const int s0 = (w % ROWG) * N;
+#pragma unroll
+                for (int c = 0; c < N; c++) buf[s0 + c][lane] = row[c];
+                if (w % ROWG == ROWG - 1)  // group complete
+                    store_row_group<ROWG * N>(a.y_eval + ((size_t)traj * a.row_stride + (size_t)(w - (ROWG - 1))) * N, &buf[0][lane], 32, a.rows_vec);
+                return;
+            }
+        }
+        double* dst = a.y_eval + ((size_t)traj * a.row_stride + w) * N;
+        if ((N % 2 == 0) && a.rows_vec) {
+#pragma unroll
+            for (int c = 0; c + 1 < N; c += 2) *reinterpret_cast<double2*>(dst + c) = make_double2(row[c], row[c + 1]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < N; c++) dst[c] = row[c];
+        }
+    }
+
+    // component-wise variant of put: set() every component of row w, then done()
+    __device__ __forceinline__ static void set(const OdeKernelArgs& a, double (*buf)[32], unsigned lane, long long traj, int w, int emitted,
+                                               int c, double v) {
+        if (ENABLED && w / ROWG == emitted / ROWG) buf[(w % ROWG) * N + c][lane] = v;
+        else a.y_eval[((size_t)traj * a.row_stride + w) * N + c] = v;
+    }
+    __device__ __forceinline__ static void done(const OdeKernelArgs& a, double (*buf)[32], unsigned lane, long long traj, int w, int emitted) {
+        if constexpr (ENABLED) {
+            if (w / ROWG == emitted / ROWG && w % ROWG == ROWG - 1)
+                store_row_group<ROWG * N>(a.y_eval + ((size_t)traj * a.row_stride + (size_t)(w - (ROWG - 1))) * N, &buf[0][lane], 32, a.rows_vec);
+        }
+    }
+
+    // the trajectory has ended with `emitted` rows: write the rows of the incomplete last group
+    __device__ __forceinline__ static void finish(const OdeKernelArgs& a, double (*buf)[32], unsigned lane, long long traj, int emitted) {
+        if constexpr (ENABLED) {
+            const int first = (emitted / ROWG) * ROWG;
+            double* dst = a.y_eval + ((size_t)traj * a.row_stride + first) * N;
+            const int n = (emitted - first) * N;
+            for (int e = 0; e < n; e++) dst[e] = buf[e][lane];
+        }
+    }
 };
 
 __device__ __forceinline__ double d_signum(double x) { return (x != x) ? x : copysign(1.0, x); }  // f64::signum
@@ -212,7 +326,8 @@ __device__ __noinline__ void all_terms_attempt(const double* y, double* k, doubl
 }
 
 // REC: the output goes through a per-step recorder (step_recorder.cuh) instead of the t_eval / even(dt) row plan.
-template <class Sys, class Tab, int BLOCK, int MIN_BLOCKS, bool SHARED_P, bool REC = false, class Evt = EvtNone>
+// FILTER: the step-size filter hook is not the identity (a.filter_mask).
+template <class Sys, class Tab, int BLOCK, int MIN_BLOCKS, bool SHARED_P, bool REC = false, class Evt = EvtNone, bool FILTER = false>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const OdeKernelArgs a) {
     constexpr int N = Sys::DIM, NP = Sys::NP, S = Tab::S, I = Tab::I, O = Tab::O;
     constexpr unsigned FULL = 0xffffffffu;
@@ -238,8 +353,12 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
     // budget next to the pow tables (wide systems interpolate on the spot)
     constexpr bool DEFER = (I == S) && !REC && (NSTASH * BLOCK * 8 <= 40 * 1024);
     StepRecorder<Sys, Tab, Evt> recd;
-    __shared__ double s_stash[DEFER ? (BLOCK / 32) : 1][DEFER ? NSTASH : 1][32];
-    double (*stash)[32] = s_stash[DEFER ? (threadIdx.x >> 5) : 0];
+    using Rows = RowStage<N, BLOCK, !REC>;  // (per-step recorders write their rows themselves, step_recorder.cuh)
+    // per warp: [parked step (DEFER)] [row group being collected]; one array so that both are addressed from one base register
+    constexpr int NPARK = DEFER ? NSTASH : 0;
+    __shared__ double s_lane[BLOCK / 32][NPARK + Rows::SLOTS][32];
+    double (*stash)[32] = s_lane[threadIdx.x >> 5];
+    double (*s_rows)[32] = stash + NPARK;
     const bool want_rows = (a.y_eval != nullptr);
     bool pending = false;  // this lane has a parked step
     int pend_idx = 0;      // first row of the parked step
@@ -267,74 +386,66 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
         // SERVICE SECTION
         // =====================================================================================================
         if (DEFER) {
-            // ---- flush parked rows
+            // ---- flush parked rows.  Everything is re-read from the stash per row and per component (a parked step nearly
+            //      always covers ONE row): a few live registers instead of five N-vectors next to the whole trajectory state.
             if (pending) {
                 const double ts = stash[0][lane], hs = stash[1][lane];
-                double ys[N], yn[N], c1[N], c2[N], c3[N];
-#pragma unroll
-                for (int c = 0; c < N; c++) {  // ordinary.rs:196-207
-                    ys[c] = stash[2 + c][lane];
-                    yn[c] = stash[2 + N + c][lane];
-                    const double k0s = stash[2 + 2 * N + c][lane], dys = stash[2 + 3 * N + c][lane];
-                    c1[c] = yn[c] - ys[c];
-                    c2[c] = __dadd_rn(0.0, hs * k0s) - c1[c];
-                    c3[c] = (c1[c] + (-hs) * dys) - c2[c];
-                }
-                const double c4 = __dmul_rn(0.0, hs);  // bi rows 4.. are all zero => cont[4] = (+0) * h
                 const double tn = ts + hs;
-                const double hh = tn - ts;  // cubic Hermite (adaptive family): t1 - t0, interpolate.rs:53
                 // the parked step covers rows [pend_idx, idx): idx was advanced past the step when the lane parked
                 for (int r = pend_idx; r < idx; r++) {
+                    int w = r;           // row slot written
+                    int mode;            // 0: the state at the end of the step; 1: dense output of the method
+                    double sx = 0.0;
                     if (a.even && r == a.n_rows - 1) {  // the tf sentinel: even.rs:166-188, only when the step landed exactly on tf
-                        int w = -1;
+                        w = -1;
                         if (tn == a.tf) {
                             const double t_last = a.t_rows[r - 1];  // r >= 1: row 0 (t0) was emitted at init
                             if (fabs(t_last - a.tf) <= a.even_tol) w = r - 1;  // pop + push(tf, y): replace the near-duplicate
                             else w = r;                                       // push(tf, y)
                         }
-                        if (w >= 0) {
-                            double* dst = a.y_eval + ((size_t)traj * a.row_stride + w) * N;
-#pragma unroll
-                            for (int c = 0; c < N; c++) dst[c] = yn[c];
-                        }
+                        mode = 0;
                         idx = w + 1 > r ? r + 1 : r;  // rows emitted so far: the sentinel slot counts only if it was written
-                        break;
+                    } else {
+                        const double ter = a.t_rows[r];
+                        mode = (ter == tn && !a.even) ? 0 : 1;  // exact hit: the solver state itself (t_eval.rs:113-114); EvenSolout always interpolates
+                        // DP: (t - t_prev) / h_prev, ordinary.rs:312; Hermite: (t - t0) / (t1 - t0) with t1 - t0 = tn - ts, interpolate.rs:53
+                        sx = (ter - ts) / (Tab::DP ? hs : (tn - ts));
                     }
-                    const double ter = a.t_rows[r];
-                    double row[N];
-                    if (ter == tn && !a.even) {  // exact hit: the solver state itself (t_eval.rs:113-114); EvenSolout always interpolates
-#pragma unroll
-                        for (int c = 0; c < N; c++) row[c] = yn[c];
-                    } else if (Tab::DP) {  // interpolate, ordinary.rs:301-337 with O = 5
-                        const double sx = (ter - ts) / hs;
-                        const double s1 = 1.0 - sx;
+                    if (w >= 0) {
 #pragma unroll
                         for (int c = 0; c < N; c++) {
-                            double accp = c4 * s1 + c3[c];
-                            accp = accp * sx + c2[c];
-                            accp = accp * s1 + c1[c];
-                            row[c] = ys[c] + sx * accp;
+                            const double ysc = stash[2 + c][lane], ync = stash[2 + N + c][lane];
+                            double v = ync;
+                            if (mode != 0) {
+                                const double k0s = stash[2 + 2 * N + c][lane], dys = stash[2 + 3 * N + c][lane];
+                                if (Tab::DP) {  // cont, ordinary.rs:196-207; interpolate, ordinary.rs:301-337 with O = 5
+                                    const double c1 = ync - ysc;
+                                    const double c2 = __dadd_rn(0.0, hs * k0s) - c1;
+                                    const double c3 = (c1 + (-hs) * dys) - c2;
+                                    const double c4 = __dmul_rn(0.0, hs);  // bi rows 4.. are all zero => cont[4] = (+0) * h
+                                    const double s1 = 1.0 - sx;
+                                    double accp = c4 * s1 + c3;
+                                    accp = accp * sx + c2;
+                                    accp = accp * s1 + c1;
+                                    v = ysc + sx * accp;
+                                } else {  // cubic Hermite on (t_prev, t, y_prev, y, dydt_prev, dydt): interpolate.rs:40-60 via adaptive/ordinary.rs:282-295
+                                    const double hh = tn - ts;
+                                    const double s2 = sx * sx, s3 = s2 * sx;
+                                    const double h00 = 2.0 * s3 - 3.0 * s2 + 1.0;
+                                    const double h10 = s3 - 2.0 * s2 + sx;
+                                    const double h01 = -2.0 * s3 + 3.0 * s2;
+                                    const double h11 = s3 - s2;
+                                    const double w10 = h10 * hh, w11 = h11 * hh;
+                                    v = __dadd_rn(0.0, h00 * ysc);
+                                    v = v + w10 * k0s;
+                                    v = v + h01 * ync;
+                                    v = v + w11 * dys;
+                                }
+                            }
+                            Rows::set(a, s_rows, lane, traj, w, r, c, v);
                         }
-                    } else {  // cubic Hermite on (t_prev, t, y_prev, y, dydt_prev, dydt): interpolate.rs:40-60 via adaptive/ordinary.rs:282-295
-                        const double sx = (ter - ts) / hh;
-                        const double s2 = sx * sx, s3 = s2 * sx;
-                        const double h00 = 2.0 * s3 - 3.0 * s2 + 1.0;
-                        const double h10 = s3 - 2.0 * s2 + sx;
-                        const double h01 = -2.0 * s3 + 3.0 * s2;
-                        const double h11 = s3 - s2;
-                        const double w10 = h10 * hh, w11 = h11 * hh;
-#pragma unroll
-                        for (int c = 0; c < N; c++) {
-                            double v = __dadd_rn(0.0, h00 * ys[c]);
-                            v = v + w10 * stash[2 + 2 * N + c][lane];
-                            v = v + h01 * yn[c];
-                            v = v + w11 * stash[2 + 3 * N + c][lane];
-                            row[c] = v;
-                        }
+                        Rows::done(a, s_rows, lane, traj, w, r);
                     }
-                    double* dst = a.y_eval + ((size_t)traj * a.row_stride + r) * N;
-#pragma unroll
-                    for (int c = 0; c < N; c++) dst[c] = row[c];
                 }
                 pending = false;
             }
@@ -342,6 +453,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
         }
         // ---- finished trajectories: Solution / Error fields
         if (active && fin >= 0) {
+            if (!REC && want_rows) Rows::finish(a, s_rows, lane, traj, idx);
             if (a.status) a.status[traj] = fin;
             if (a.t_final) a.t_final[traj] = t;
             if (a.y_final) {
@@ -355,6 +467,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
             constexpr int PER_ACC = Tab::BI_POLY ? ((I - S) + (Tab::FSAL ? 0 : 1)) : (1 + ((I > S) ? (I - S - 1) : 0));
             if (a.evals) a.evals[traj] = evals_base + (S - 1) * (acc + rej) + acc * PER_ACC;
             if (a.n_emitted) a.n_emitted[traj] = REC ? recd.rows : idx;
+            wm_publish(a, traj);
             active = false;
             // idle dummy state: finite, never committed
             t = t0; h = 0.0; h_prev = 0.0; te = te_none;
@@ -399,22 +512,20 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
                         if (a.rejected) a.rejected[traj] = 0;
                         if (a.evals) a.evals[traj] = 0;
                         if (a.n_emitted) a.n_emitted[traj] = 0;
+                        wm_publish(a, traj);
                     } else {
 #pragma unroll
                         for (int c = 0; c < N; c++) y[c] = y0v[c];
                         acc = 0; rej = 0; idx = 0; m100 = 0;
                         t = t0;
-                        h = h0;
+                        h = FILTER ? apply_filter(a, h0) : h0;  // ordinary.rs:33
                         h_prev = 0.0;
                         stiff = 0; nonstiff = 0;
                         rejected_prev = false;
                         Sys::rhs(t, y, k[0], p);
                         // solout before the loop (solve_ivp.rs:160): emits rows[0] iff it equals t0
                         if (!REC && a.emit_t0) {
-                            if (a.y_eval) {
-#pragma unroll
-                                for (int c = 0; c < N; c++) a.y_eval[(traj * a.row_stride) * N + c] = y[c];
-                            }
+                            if (want_rows) Rows::put(a, s_rows, lane, traj, 0, 0, y);
                             idx = 1;
                         }
                         te = (!REC && idx < a.n_rows) ? a.t_rows[idx] : te_none;
@@ -441,7 +552,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
                 const double h_new = tf - t;
                 if ((t + h - tf) * dir > 0.0) {
                     if (fabs(h_new) < eps10) fin = DEB_STATUS_COMPLETE;
-                    else h = h_new;
+                    else h = FILTER ? apply_filter(a, h_new) : h_new;  // solver.set_h(h_new) filters too (ordinary.rs:288)
                 }
                 if (fin < 0) {
                     if (fabs(h) < fabs(h_prev) * 1e-14) fin = DEB_STATUS_STEP_SIZE;
@@ -590,7 +701,11 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
                 Sys::rhs(t_new, ynew, dydt, p);
             }
 
-            if (Tab::DP && accept && m100 == 99) {  // steps % 100 == 0 with steps = acc + rej + 1: stiffness test, ordinary.rs:165-194
+            // steps % 100 == 0 with steps = acc + rej + 1: stiffness test, ordinary.rs:165-194.  With parked emission, a lane whose
+            // step contains a t_eval point while its row slot is still occupied does not commit this attempt: it is redone, bit
+            // for bit, after the service section.  The counters below must not advance for the attempt that is thrown away
+            // (the reference advances them once per 100th step).
+            if (Tab::DP && accept && m100 == 99 && !(DEFER && pending && ((te - t_new) * dir <= 0.0))) {
                 // ysti = the argument of the last stage; rebuilt here (same operations, same bits) instead of being
                 // kept alive in registers through 99 steps out of 100
                 double ysti[N];
@@ -722,11 +837,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
                                 const double t_last = a.t_rows[idx - 1];
                                 w = (fabs(t_last - tf) <= a.even_tol) ? idx - 1 : idx;
                             }
-                            if (w >= 0 && want_rows) {
-                                double* dst = a.y_eval + ((size_t)traj * a.row_stride + w) * N;
-#pragma unroll
-                                for (int c = 0; c < N; c++) dst[c] = ynew[c];
-                            }
+                            if (w >= 0 && want_rows) Rows::put(a, s_rows, lane, traj, w, idx, ynew);
                             if (w == idx) idx += 1;
                             te = te_none;
                             break;
@@ -785,11 +896,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
                                 row[c] = y[c] + sx * accp;
                             }
                         }
-                        if (want_rows) {
-                            double* dst = a.y_eval + ((size_t)traj * a.row_stride + idx) * N;
-#pragma unroll
-                            for (int c = 0; c < N; c++) dst[c] = row[c];
-                        }
+                        if (want_rows) Rows::put(a, s_rows, lane, traj, idx, idx, row);
                         idx += 1;
                         te = (idx < a.n_rows) ? a.t_rows[idx] : te_none;
                     }
@@ -831,6 +938,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
                 // ---- step-size update, ordinary.rs:261-267 (filter = identity)
                 h = h * scale;
                 if (bounded_h) h = constrain_step_size(h, a.h_min, a.h_max);  // identity for h_min = 0, h_max = inf
+                if constexpr (FILTER) h = apply_filter(a, h);                 // ordinary.rs:267
                 // accepted: end-of-interval test, solve_ivp.rs:263
                 if (commit && fabs(tf - t) <= eps10) fin = DEB_STATUS_COMPLETE;
                 if (REC && interrupt) fin = DEB_STATUS_INTERRUPTED;  // solve_ivp.rs:255-260, before the end-of-interval test

@@ -21,6 +21,10 @@ __global__ void __launch_bounds__(BLOCK) fixed_ensemble_kernel(const OdeKernelAr
     const double dir = d_signum(tf - t0);
     const double te_none = (dir > 0.0) ? (1.0 / 0.0) : -(1.0 / 0.0);
     const long long stride = (long long)gridDim.x * BLOCK;
+    using Rows = RowStage<N, BLOCK, !REC>;  // whole-sector row groups, see erk_ensemble.cuh
+    __shared__ double s_lane[BLOCK / 32][Rows::SLOTS][32];
+    double (*s_rows)[32] = s_lane[threadIdx.x >> 5];
+    const unsigned lane = threadIdx.x & 31u;
 
     for (long long traj = (long long)blockIdx.x * BLOCK + threadIdx.x; traj < a.n_traj; traj += stride) {
         double y[N], dydt[N], k[S][N], p[NP > 0 ? NP : 1];
@@ -41,10 +45,7 @@ __global__ void __launch_bounds__(BLOCK) fixed_ensemble_kernel(const OdeKernelAr
             Sys::rhs(t, y, dydt, p);
             evals = 1;
             if (!REC && a.emit_t0) {
-                if (a.y_eval) {
-#pragma unroll
-                    for (int c = 0; c < N; c++) a.y_eval[(traj * a.row_stride) * N + c] = y[c];
-                }
+                if (a.y_eval) Rows::put(a, s_rows, lane, traj, 0, 0, y);
                 n_emit = 1;
                 idx = 1;
             }
@@ -53,7 +54,8 @@ __global__ void __launch_bounds__(BLOCK) fixed_ensemble_kernel(const OdeKernelAr
         double te = (idx < a.n_rows) ? a.t_rows[idx] : te_none;
         // the loop head (clip at tf, solve_ivp.rs:193-209), the max_steps test and the end test (:263) ran on the host
         for (int step = 0; fin < 0 && step < a.fx_n_steps; step++) {
-            h = (step == a.fx_n_steps - 1) ? a.fx_h_last : h_full;
+            const int tail = step - (a.fx_n_steps - a.fx_n_tail);  // >= 0: one of the clipped steps at the end
+            h = (tail >= 0) ? a.fx_h_tail[tail] : h_full;
             steps += 1;
             // ---- step, fixed/ordinary.rs:58-139
 #pragma unroll
@@ -98,11 +100,7 @@ __global__ void __launch_bounds__(BLOCK) fixed_ensemble_kernel(const OdeKernelAr
                         const double t_last = a.t_rows[idx - 1];
                         w = (fabs(t_last - tf) <= a.even_tol) ? idx - 1 : idx;
                     }
-                    if (w >= 0 && a.y_eval) {
-                        double* dst = a.y_eval + ((size_t)traj * a.row_stride + w) * N;
-#pragma unroll
-                        for (int c = 0; c < N; c++) dst[c] = ynew[c];
-                    }
+                    if (w >= 0 && a.y_eval) Rows::put(a, s_rows, lane, traj, w, n_emit, ynew);
                     if (w == idx) { idx += 1; n_emit += 1; }
                     te = te_none;
                     break;
@@ -129,11 +127,7 @@ __global__ void __launch_bounds__(BLOCK) fixed_ensemble_kernel(const OdeKernelAr
                         row[c] = v;
                     }
                 }
-                if (a.y_eval) {
-                    double* dst = a.y_eval + ((size_t)traj * a.row_stride + n_emit) * N;
-#pragma unroll
-                    for (int c = 0; c < N; c++) dst[c] = row[c];
-                }
+                if (a.y_eval) Rows::put(a, s_rows, lane, traj, n_emit, n_emit, row);
                 n_emit += 1;
                 idx += 1;
                 te = (idx < a.n_rows) ? a.t_rows[idx] : te_none;
@@ -144,6 +138,7 @@ __global__ void __launch_bounds__(BLOCK) fixed_ensemble_kernel(const OdeKernelAr
             if (REC && interrupt) fin = DEB_STATUS_INTERRUPTED;    // solve_ivp.rs:255-260 (an event asked to terminate)
         }
         if (fin < 0) fin = a.fx_status;  // Complete, or MaxSteps after fx_n_steps steps
+        if (!REC && a.y_eval) Rows::finish(a, s_rows, lane, traj, n_emit);
         if (a.status) a.status[traj] = fin;
         if (a.t_final) a.t_final[traj] = t;
         if (a.y_final) {
@@ -154,6 +149,7 @@ __global__ void __launch_bounds__(BLOCK) fixed_ensemble_kernel(const OdeKernelAr
         if (a.rejected) a.rejected[traj] = 0;
         if (a.evals) a.evals[traj] = evals;
         if (a.n_emitted) a.n_emitted[traj] = REC ? recd.rows : n_emit;
+        wm_publish(a, traj);
     }
 }
 

@@ -14,6 +14,8 @@
 
 // defined in deb_api.cu: records the text for deb_last_error() and returns `code`
 int deb_fail(int code, const char* msg);
+// defined in deb_api.cu: the library counts its kernel launches (deb_launch_count)
+void deb_count_launch(int n);
 
 typedef int (*ode_launch_fn)(const deb::OdeKernelArgs&, int sms, cudaStream_t);
 
@@ -52,6 +54,7 @@ int launch_dp_impl(const deb::OdeKernelArgs& a, int sms, cudaStream_t st) {
     if (getenv("DEB_DEBUG_LAUNCH")) fprintf(stderr, "[deb] built-in kernel: grid %lld x %d\n", blocks, BLOCK);
     kern<<<(unsigned)blocks, BLOCK, 0, st>>>(a);
     DEB_DISPATCH_CUDA(cudaGetLastError());
+    deb_count_launch(1);
     return DEB_OK;
 }
 

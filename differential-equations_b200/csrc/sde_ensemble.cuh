@@ -28,10 +28,12 @@ struct SdeKernelArgs {
     int n_rows, row_stride, emit_t0;
     // The step schedule does not depend on the path (same t0, tf, h0, t_eval for every path), so the host runs the
     // solve_sde bookkeeping once (solve_ivp.rs:211-227, :263; stochastic.rs:74-83) and the kernel's step loop carries no
-    // end-of-interval tests: n_steps steps of size h0, the last one of size h_last; row r is emitted in step row_step[r]
-    // with the interpolation weight row_s[r] (negative: the row is the end of the step itself).
+    // end-of-interval tests: n_steps steps of size h0 except the last n_tail (>= 1) ones, of sizes h_tail[0..n_tail) (the
+    // clip at tf can fire twice, see OdeKernelArgs); row r is emitted in step row_step[r] with the interpolation weight
+    // row_s[r] (negative: the row is the end of the step itself).
     int n_steps;
-    double h_last;
+    int n_tail;
+    double h_tail[DEB_FX_MAX_TAIL];
     int final_status;       // DEB_STATUS_COMPLETE / MAX_STEPS / BAD_INPUT (then n_steps = 0)
     const int* row_step;    // [n_rows]
     const double* row_s;    // [n_rows]
@@ -79,7 +81,8 @@ __global__ void __launch_bounds__(BLOCK) sde_ensemble_kernel(const SdeKernelArgs
             }
         }
         int next_step = (idx < a.n_rows) ? a.row_step[idx] : -1;
-        const double sqrt_h0 = sqrt(h0), sqrt_hl = sqrt(a.h_last);
+        const double sqrt_h0 = sqrt(h0);
+        const int n_main = a.n_steps - a.n_tail;  // steps of size h0
         // one step from (t, y, dydt) with the Wiener increments dw
         auto do_step = [&](const int step, const double h, const double sqrt_h, double (&dw)[N]) {
             Sde::mix(dw, p);
@@ -156,7 +159,7 @@ __global__ void __launch_bounds__(BLOCK) sde_ensemble_kernel(const SdeKernelArgs
         int step = 0;
         if constexpr (N == 1) {
             // one normal per step: a Philox call feeds two consecutive steps; all but the last step have size h0
-            for (; step + 2 < a.n_steps; step += 2) {
+            for (; step + 2 <= n_main; step += 2) {
                 double ze, zo;
                 normal_pair(a.round_keys, path, (unsigned long long)(step >> 1), &ze, &zo);
                 double dw0[1] = {sqrt_h0 * ze}, dw1[1] = {sqrt_h0 * zo};
@@ -167,9 +170,9 @@ __global__ void __launch_bounds__(BLOCK) sde_ensemble_kernel(const SdeKernelArgs
         double z_odd = 0.0;                          // the odd normal of the last Philox call ...
         unsigned long long odd_pair = ~0ull;         // ... and its pair index
         for (; step < a.n_steps; step++) {
-            const bool last = (step == a.n_steps - 1);
-            const double h = last ? a.h_last : h0;
-            const double sqrt_h = last ? sqrt_hl : sqrt_h0;
+            const int tail = step - n_main;
+            const double h = (tail >= 0) ? a.h_tail[tail] : h0;
+            const double sqrt_h = (tail >= 0) ? sqrt(h) : sqrt_h0;
             const unsigned long long q0 = (unsigned long long)step * N;  // first normal index of this step
             double dw[N];
             if constexpr (N % 2 == 0) {

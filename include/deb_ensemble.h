@@ -27,7 +27,9 @@
  *
  * Conventions
  *  - Plain C: pointers + sizes, no C++/torch types.  All structs start with `struct_size` (set it to
- *    sizeof(the struct)) so fields can be appended compatibly.
+ *    sizeof(the struct)).  Fields are only ever appended: a caller built against an OLDER header passes a smaller
+ *    struct_size and the library reads the missing tail as zeros (= the defaults); a struct_size larger than the
+ *    library's own (a NEWER header) is rejected with DEB_ERR_BAD_ARG.
  *  - Every function returns 0 on success, a negative deb_error otherwise; deb_last_error() gives the text.
  *    Numerical failures of a trajectory are NOT call failures: they are reported per trajectory in
  *    `status[]` with the same meaning as the reference's `Error` variants (src/error.rs:13-41), and the
@@ -50,8 +52,9 @@
 extern "C" {
 #endif
 
-#define DEB_ABI_VERSION 8
+#define DEB_ABI_VERSION 9
 #define DEB_MAX_DIM 16 /* widest state the register-resident kernels are instantiated for */
+#define DEB_MAX_DEVICES 16 /* longest device list of one call */
 
 typedef enum deb_error {
     DEB_OK = 0,
@@ -132,6 +135,23 @@ enum {
 
 typedef enum deb_memspace { DEB_MEM_HOST = 0, DEB_MEM_DEVICE = 1 } deb_memspace;
 
+/* Memory layout of y_eval (t_eval / even(dt) recorders). */
+typedef enum deb_layout {
+    DEB_LAYOUT_TRAJ_MAJOR = 0, /* y_eval[i][r][c]: each trajectory's Solution.y is one contiguous block (Vec<[f64; N]>) */
+    DEB_LAYOUT_ROW_MAJOR = 1   /* y_eval[r][c][i]: structure of arrays, one contiguous vector of n_traj values per (row, component):
+                                  what a per-t_eval reduction or a columnar sink (the crate's polars feature) reads */
+} deb_layout;
+
+/* Step-size filter: the `filter: fn(T) -> T` hook of ExplicitRungeKutta (src/methods/erk/mod.rs:85,225), applied to h at init
+ * (dormandprince/ordinary.rs:33), after every step-size update (:267) and in set_h, i.e. to the clip at tf (:288).  A Rust
+ * function pointer cannot cross the boundary; the built-ins below can. */
+typedef enum deb_filter {
+    DEB_FILTER_IDENTITY = 0,          /* |h| h   (the default, erk/mod.rs:144) */
+    DEB_FILTER_TRUNCATE_MANTISSA = 1  /* |h| f64::from_bits(h.to_bits() & !((1u64 << (52 - filter_bits)) - 1)): keep the leading
+                                         filter_bits (1..52) bits of the mantissa; quantises h so that results do not depend on
+                                         the last bits of the controller's pow ("Plan B") */
+} deb_filter;
+
 /* Output recorder (`Solout`, src/solout/): which rows go to y_eval. */
 typedef enum deb_solout {
     DEB_SOLOUT_T_EVAL = 0, /* IVP::t_eval(points): TEvalSolout, src/solout/t_eval.rs:87-171 */
@@ -205,6 +225,16 @@ typedef struct deb_ode_problem {
     int32_t plane_index[DEB_MAX_DIM];
     double plane_point[DEB_MAX_DIM];
     double plane_normal[DEB_MAX_DIM];
+    /* ---- appended in ABI 9 (zero = previous behaviour) */
+    int32_t filter;       /* deb_filter; adaptive methods only (the fixed-step stepper never calls the hook) */
+    int32_t filter_bits;  /* DEB_FILTER_TRUNCATE_MANTISSA: mantissa bits kept, 1..52 */
+    int32_t layout;       /* deb_layout of y_eval; DEB_LAYOUT_ROW_MAJOR needs a t_eval / even(dt) recorder without event */
+    /* Device list: with n_devices >= 2 the ensemble is split over devices[0..n_devices) inside ONE call (memspace must be
+     * DEB_MEM_HOST): blocks of 4096 consecutive trajectories are dealt round-robin (block b -> devices[b mod n_devices],
+     * which balances a sorted parameter sweep), one host thread and one persistent kernel per device, no exchange during
+     * the integration; results land in the caller's arrays exactly as for one device.  n_devices <= 1: `device` is used. */
+    int32_t n_devices;
+    int32_t devices[DEB_MAX_DEVICES];
 } deb_ode_problem;
 
 typedef struct deb_sde_problem {
@@ -257,6 +287,15 @@ typedef struct deb_result {
      * capacity per trajectory; n_emitted[i] counts every row the reference would have pushed -- rows beyond the
      * capacity are counted but not stored.  n_rows is 0 for these recorders.  May be NULL. */
     double* t_out;         /* [n_traj][n_eval] */
+    /* ---- appended in ABI 9 */
+    /* Ensemble statistics per t_eval row, reduced on the device(s) while the rows are still resident, then summed across the
+     * devices of the call (NCCL all-reduce over NVLink when n_devices >= 2) -- the only cross-device traffic of a solve.
+     * HOST memory always, DEB_MEM_HOST calls with a t_eval / even(dt) recorder only; may be NULL.
+     * stats_sums[(r*dim + c)*2 + {0,1}] = sum over trajectories with n_emitted > r of {y, y^2}; stats_counts[r] = how many. */
+    double* stats_sums;    /* [n_eval][dim][2] */
+    int64_t* stats_counts; /* [n_eval] */
+    int32_t gpu_launches;  /* filled by the library: kernels this call launched (all devices) */
+    int32_t reserved0;
 } deb_result;
 
 /* Method-of-lines heat equation u_t = (alpha u_x)_x on a uniform 1-D grid, second-order finite differences,
@@ -271,7 +310,7 @@ typedef struct deb_heat_problem {
     int32_t method;      /* fixed-step deb_method (DEB_RK4) */
     double h;            /* step size (rk4(h)) */
     double t0, tf;
-    int64_t max_steps;   /* default 10000 */
+    int64_t max_steps;   /* <= 0: the reference default, 10000 (erk/mod.rs:139) */
     const double* u0;    /* [n_nodes] */
     double* u_final;     /* [n_nodes] */
     double* t_final;     /* HOST, 1 value (may be NULL) */
@@ -302,6 +341,31 @@ int deb_define_ode(int32_t dim, int32_t n_params, const char* diff_body, int32_t
  * as CUDA C++ text (p = the trajectory's ODE parameters), the device-side `impl Event for S { fn event(&self, t, y) }`.
  * Returns an id (>= 1000) for deb_ode_problem.event. */
 int deb_define_event(int32_t dim, const char* event_body, int32_t* event_id);
+/* User-defined SDE with diagonal noise: the device-side `impl SDE for S { fn drift; fn diffusion; fn noise }`
+ * (src/sde/sde.rs:16-67).  The bodies are CUDA C++ text:
+ *     void drift(double t, const double* y, double* dydt, const double* p)        -- write dydt[0..dim)
+ *     void diffusion(double t, const double* y, double* g, const double* p)       -- write g[0..dim): dY_c += g[c] * dW_c
+ *     void noise(double* dw, const double* p)                                      -- optional (NULL = independent increments):
+ *         dw[0..dim) arrive as independent N(0, h) increments from the library's Philox stream; mix them in place, as the
+ *         reference's `noise` implementations do after drawing (examples/sde/02_heston_model/main.rs:62-72)
+ * Returns a system id (>= 1000) for deb_sde_problem.system (n_params <= 8).  Compiled at first use (NVRTC, sm_100a, --fmad=false). */
+int deb_define_sde(int32_t dim, int32_t n_params, const char* drift_body, const char* diffusion_body, const char* noise_body,
+                   int32_t* system_id);
+/* Compile the SDE kernel for (system, method) now, without a device (like deb_check_ode). */
+int deb_check_sde(int32_t system_id, int32_t method);
+/* Forward sensitivity analysis, ForwardSensitivityOde (src/ode/sensitivity/forward.rs:43-116): builds the augmented system
+ *     z = [y (n = dim), S (n x m, row-major: S[r][c] = dy_r/dp_c at z[n + r*m + c])],  m = n_params,
+ *     y' = f(t, y, p),   S' = J_y S + J_p
+ * from the text of `ODE::diff`, `ODE::jacobian` and `ParametrizedODE::jacobian_p` and registers it like deb_define_ode
+ * (state dimension n*(1+m) <= DEB_MAX_DIM):
+ *     diff_body:  body of void diff(double t, const double* y, double* dydt, const double* p)
+ *     jac_y_body: body of void jacobian(double t, const double* y, double* J, const double* p)     -- J[r*n + k] = df_r/dy_k
+ *     jac_p_body: body of void jacobian_p(double t, const double* y, double* Jp, const double* p)  -- Jp[r*m + c] = df_r/dp_c
+ * J and Jp arrive zeroed (the reference's Matrix::full).  Each entry is accumulated as the reference does (forward.rs:103-111):
+ * dS_rc = Jp[r][c]; for k in 0..n: dS_rc += J[r][k] * S[k][c].  Initial state: [y0, S(t0)] (S(t0) = 0 for parameters that do
+ * not enter y0). */
+int deb_define_ode_sensitivity(int32_t dim, int32_t n_params, const char* diff_body, const char* jac_y_body,
+                               const char* jac_p_body, int32_t* system_id);
 /* Compile the kernel for (system, method, recorder, event) now, without a device and without running anything: DEB_OK, or
  * an error with the compiler log in deb_last_error() (DEB_ERR_BAD_ARG for a user-defined right-hand side that does not
  * compile: what a Rust caller gets from `cargo check`).  Kernels that were compiled ahead of time (built-in system with
@@ -311,6 +375,9 @@ int deb_check_ode(int32_t system_id, int32_t method, int32_t solout, int32_t eve
 /* Device memory the library caches between calls (staging buffers of DEB_MEM_HOST calls, work buffers) lives in a
  * library-owned stream-ordered pool; this releases it back to the driver.  Synchronises the device. */
 int deb_trim_memory(int32_t device);
+
+/* Number of CUDA kernels the library has launched in this process so far (all entry points, all devices). */
+int64_t deb_launch_count(void);
 
 int deb_solve_ode(const deb_ode_problem* problem, deb_result* result);
 int deb_solve_sde(const deb_sde_problem* problem, deb_result* result);

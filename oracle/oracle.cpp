@@ -274,12 +274,22 @@ struct Erk {
     int64_t steps = 0;
     int stiffness_counter = 0, non_stiffness_counter = 0;
     bool rejected = false;  // Status::RejectedStep
+    // the `filter: fn(T) -> T` hook (erk/mod.rs:85,225): identity, or keep the leading mantissa bits (deb_filter)
+    uint64_t filter_mask = 0;
+    double filter(double v) const {
+        if (!filter_mask) return v;
+        uint64_t b;
+        std::memcpy(&b, &v, 8);
+        b &= filter_mask;
+        std::memcpy(&v, &b, 8);
+        return v;
+    }
 
     // ---- Dormand-Prince: init, dormandprince/ordinary.rs:16-61
     bool dp_init(const Problem& ode, double t0, double tf, const Vec& y0, int* evals) {
         if (h0 == 0.0) h0 = h_init(ode, t0, tf, y0, tb.order, rtol, atol, h_min, h_max, evals);
         if (!validate_step_size_parameters(h0, h_min, h_max, t0, tf)) return false;
-        h = h0;
+        h = filter(h0);  // ordinary.rs:33 / adaptive/ordinary.rs:34
         stiffness_counter = 0;
         t = t0; y = y0;
         int n = ode.n;
@@ -382,6 +392,7 @@ struct Erk {
         }
         h *= scale;                                   // :261
         h = constrain_step_size(h, h_min, h_max);     // :264
+        h = filter(h);                                // :267
         *evals_out += evals;
         return STEP_OK;
     }
@@ -410,7 +421,7 @@ struct Erk {
             *evals += 2;  // (sic) counted twice: compute() already added its two evaluations (:24-29)
         }
         if (!validate_step_size_parameters(h0, h_min, h_max, t0, tf)) return false;
-        h = h0;
+        h = filter(h0);  // ordinary.rs:33 / adaptive/ordinary.rs:34
         stiffness_counter = 0;
         t = t0; y = y0;
         int n = ode.n;
@@ -470,6 +481,7 @@ struct Erk {
         }
         h *= scale;
         h = constrain_step_size(h, h_min, h_max);
+        h = filter(h);  // adaptive/ordinary.rs:207
         *evals_out += evals;
         return STEP_OK;
     }
@@ -876,6 +888,7 @@ void solve_one(const deb_ode_problem* P, const SysInfo& si, const Tableau& tb, i
     m.h0 = P->opt.h0; m.h_min = P->opt.h_min; m.h_max = P->opt.h_max; m.max_steps = P->opt.max_steps;
     m.safety = P->opt.safety_factor; m.min_scale = P->opt.min_scale; m.max_scale = P->opt.max_scale;
     m.max_rejects = P->opt.max_rejects;
+    if (P->filter == DEB_FILTER_TRUNCATE_MANTISSA) m.filter_mask = ~((1ull << (52 - P->filter_bits)) - 1ull);
     int evals = 0, acc = 0, rej = 0;
     int status = DEB_STATUS_COMPLETE;
     const bool has_event = (P->event != DEB_EVENT_NONE);
@@ -934,7 +947,7 @@ void solve_one(const deb_ode_problem* P, const SysInfo& si, const Tableau& tb, i
         if ((m.t + m.h - tf) * dir > 0.0) {  // :193-209
             double h_new = tf - m.t;
             if (std::fabs(h_new) < eps10) { status = DEB_STATUS_COMPLETE; break; }
-            m.h = h_new;
+            m.h = tb.adaptive ? m.filter(h_new) : h_new;  // set_h: the adaptive steppers filter (ordinary.rs:288), the fixed one does not
         }
         StepOutcome so = tb.dp ? m.dp_step(ode, &evals) : tb.adaptive ? m.ad_step(ode, &evals) : m.fx_step(ode, &evals);
         if (so != STEP_OK) {

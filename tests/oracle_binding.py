@@ -45,7 +45,13 @@ def load_oracle():
 def oracle_solve(ivp, n_threads=0):
     """Run the problem described by an EnsembleIVP builder through the CPU oracle; same result container."""
     lib = load_oracle()
-    P, res, arrs, t_sorted, keep = ivp.build_problem()
+    # the oracle is one trajectory after the other on the host: no device list, trajectory-major rows, no fused statistics
+    saved = (ivp._devices, ivp._layout, ivp._stats)
+    ivp._devices, ivp._layout, ivp._stats = [], deb.DEB_LAYOUT_TRAJ_MAJOR, False
+    try:
+        P, res, arrs, t_sorted, keep = ivp.build_problem()
+    finally:
+        ivp._devices, ivp._layout, ivp._stats = saved
     fn = lib.orc_solve_ode if ivp.kind == "ode" else lib.orc_solve_sde
     rc = fn(C.byref(P), C.byref(res), int(n_threads))
     if rc != 0:

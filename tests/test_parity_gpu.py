@@ -420,6 +420,7 @@ def test_host_path_chunk_pipeline_is_transparent(monkeypatch):
     monkeypatch.setenv("DEB_HOST_CHUNK", "100000000")
     one = prob().solve()
     monkeypatch.setenv("DEB_HOST_CHUNK", "700")
+    monkeypatch.setenv("DEB_WM_SHIFT", "6")  # chunks are whole watermark blocks: 64-trajectory blocks -> chunks of 704
     many = prob().solve()
     assert (one.status != 0).any() and (one.status == 0).any()
     for name in ("status", "accepted", "rejected", "evals", "n_emitted"):

