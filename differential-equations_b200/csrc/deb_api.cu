@@ -1040,6 +1040,8 @@ struct ShardOut {
 // Two slots alternate when there are several chunks: the next chunk's kernel is queued before the current one is drained,
 // so its CTAs fill the SMs as the current kernel's tail retires.
 int run_shard(const OdeCall& C, const ShardMap& M, int device, ShardOut* out) {
+    const auto t_start = std::chrono::steady_clock::now();
+    auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
     out->device = device;
     if (int rc = select_device(device)) return rc;
     DeviceInfo di;
@@ -1187,8 +1189,14 @@ int run_shard(const OdeCall& C, const ShardMap& M, int device, ShardOut* out) {
     };
 
     const long long batch = 8;  // copy out when at least this many blocks are ready (or the kernel has ended)
+    // DEB_DEBUG_TIMING=1: where the wall time of a HOST call goes (stderr)
+    const bool dbg_t = getenv("DEB_DEBUG_TIMING") != nullptr;
+    long long dbg_blocks_before_end = 0, dbg_copy_calls = 0;
+    const double dbg_t_setup = since();
     auto drain = [&](Slot& S) -> int {
         const long long nb = S.lb1 - S.lb0;
+        const double dbg_t0 = since();
+        double dbg_t_kernel_done = 0.0, dbg_t_first = 0.0;
         volatile int* flags = S.r->flags;
         long long next = 0;
         bool kernel_done = false;
@@ -1197,8 +1205,11 @@ int run_shard(const OdeCall& C, const ShardMap& M, int device, ShardOut* out) {
             long long hi = next;
             while (hi < nb && flags[hi] != 0) hi++;
             std::atomic_thread_fence(std::memory_order_acquire);
+            if (dbg_t && dbg_t_first == 0.0 && hi > 0) dbg_t_first = since();
             if (hi > next && (hi - next >= batch || hi == nb || kernel_done)) {
                 if (int rc = copy_out(S, S.lb0 + next, S.lb0 + hi, true)) return rc;
+                dbg_copy_calls += 1;
+                if (!kernel_done) dbg_blocks_before_end += hi - next;
                 next = hi;
                 idle_spins = 0;
                 continue;
@@ -1210,7 +1221,7 @@ int run_shard(const OdeCall& C, const ShardMap& M, int device, ShardOut* out) {
                 break;
             }
             const cudaError_t q = cudaEventQuery(S.r->k1);
-            if (q == cudaSuccess) { kernel_done = true; continue; }
+            if (q == cudaSuccess) { kernel_done = true; dbg_t_kernel_done = since(); continue; }
             if (q != cudaErrorNotReady) DEB_CUDA(q);
             if (++idle_spins > 64) std::this_thread::sleep_for(std::chrono::microseconds(30));
         }
@@ -1242,6 +1253,14 @@ int run_shard(const OdeCall& C, const ShardMap& M, int device, ShardOut* out) {
         }
         if (C.want_stats || row_major) DEB_CUDA(cudaStreamSynchronize(S.r->st));
         DEB_CUDA(cudaEventRecord(S.r->cp_done, S.r->cp));
+        if (dbg_t) {
+            const double t_issued = since();
+            cudaStreamSynchronize(S.r->cp);
+            fprintf(stderr, "[deb timing] device %d chunk of %lld blocks: buffers ready %.1f ms, kernel enqueued %.1f ms, first block done %.1f ms, "
+                            "kernel end seen %.1f ms, last copy issued %.1f ms, copies complete %.1f ms; kernel %.1f ms; %lld of %lld blocks copied "
+                            "before the kernel ended, %lld copy batches\n",
+                    device, nb, dbg_t_setup, dbg_t0, dbg_t_first, dbg_t_kernel_done, t_issued, since(), ms, dbg_blocks_before_end, nb, dbg_copy_calls);
+        }
         return DEB_OK;
     };
 

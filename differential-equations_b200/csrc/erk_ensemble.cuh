@@ -127,7 +127,13 @@ template <int CNT>
 __device__ __noinline__ void store_row_group(double* dst, const double* src, int stride, int vec) {
     if (vec) {
 #pragma unroll
-        for (int e = 0; e < CNT; e += 2) *reinterpret_cast<double2*>(dst + e) = make_double2(src[e * stride], src[(e + 1) * stride]);
+        for (int e = 0; e < CNT; e += 2) {
+#ifdef DEB_VAR_STCS  // EXPERIMENT: evict-first stores, so that the row stream does not push the finals' partial sectors out of L2
+            __stcs(reinterpret_cast<double2*>(dst + e), make_double2(src[e * stride], src[(e + 1) * stride]));
+#else
+            *reinterpret_cast<double2*>(dst + e) = make_double2(src[e * stride], src[(e + 1) * stride]);
+#endif
+        }
     } else {
 #pragma unroll
         for (int e = 0; e < CNT; e++) dst[e] = src[e * stride];
@@ -328,7 +334,11 @@ __device__ __noinline__ void all_terms_attempt(const double* y, double* k, doubl
 // REC: the output goes through a per-step recorder (step_recorder.cuh) instead of the t_eval / even(dt) row plan.
 // FILTER: the step-size filter hook is not the identity (a.filter_mask).
 template <class Sys, class Tab, int BLOCK, int MIN_BLOCKS, bool SHARED_P, bool REC = false, class Evt = EvtNone, bool FILTER = false>
+#ifdef DEB_VAR_MAXNREG  // EXPERIMENT: an explicit register cap instead of the one derived from MIN_BLOCKS
+__global__ void __maxnreg__(DEB_VAR_MAXNREG) dp_ensemble_kernel(const OdeKernelArgs a) {
+#else
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const OdeKernelArgs a) {
+#endif
     constexpr int N = Sys::DIM, NP = Sys::NP, S = Tab::S, I = Tab::I, O = Tab::O;
     constexpr unsigned FULL = 0xffffffffu;
     __shared__ double s_powlog[384];

@@ -6,7 +6,11 @@ using namespace deb_dispatch;
 template <class Sys>
 static ode_launch_fn pick_method(int method) {
     switch (method) {
+#ifdef DEB_VAR_BLOCK  // EXPERIMENT: launch shape of the DOPRI5 kernels
+        case DEB_DOPRI5: return launch_dp<Sys, deb::TabDopri5, DEB_VAR_BLOCK, DEB_VAR_MINB>;
+#else
         case DEB_DOPRI5: return launch_dp<Sys, deb::TabDopri5, 128, 5>;  // 96 regs, no spills, 20 warps/SM (sweep: profiles/)
+#endif
         // DOP853: 12 stage vectors; 4 CTAs/SM (<= 128 regs) for dim <= 2, 3 CTAs/SM (<= 168 regs) for dim 3 (sweep: DESIGN.md 7)
         case DEB_DOP853: return (Sys::DIM <= 2) ? launch_dp<Sys, deb::TabDop853, 128, 4> : launch_dp<Sys, deb::TabDop853, 128, 3>;
     }

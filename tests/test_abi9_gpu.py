@@ -174,7 +174,8 @@ def test_device_list_equals_one_device(monkeypatch, shift):
     assert_same_solution(many, ob.oracle_solve(prob()))
     if len(devs) > 1:
         rm = prob().devices(devs).layout(deb.DEB_LAYOUT_ROW_MAJOR).solve()
-        assert np.array_equal(bits(rm.y_eval), bits(one.y_eval))
+        m = np.arange(one.y_eval.shape[1])[None, :] < one.n_emitted[:, None]  # rows beyond n_emitted are unspecified
+        assert np.array_equal(bits(rm.y_eval)[m], bits(one.y_eval)[m])
 
 
 def test_device_list_is_validated():

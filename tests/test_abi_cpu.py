@@ -175,3 +175,86 @@ def test_product_never_references_the_oracle():
                 assert "liboracle" not in txt and "oracle_binding" not in txt and "orc_" not in txt and "oracle/" not in txt.replace("the oracle keeps its own copy: oracle/", ""), os.path.join(dirpath, f)
     out = subprocess.run(["ldd", deb.LIB_PATH], capture_output=True, text=True).stdout
     assert "oracle" not in out
+
+
+# ------------------------------------------------------------------------------------------ ABI 9
+def test_abi9_struct_tail_matches_header(lib):
+    """Offsets of every field appended in ABI 9 (device list, layout, filter; fused statistics, launch count)."""
+    src = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "deb_ensemble.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %d\n", offsetof(deb_ode_problem, filter), offsetof(deb_ode_problem, filter_bits), offsetof(deb_ode_problem, layout),
+         offsetof(deb_ode_problem, n_devices), offsetof(deb_ode_problem, devices), DEB_MAX_DEVICES);
+  printf("%zu %zu %zu %d\n", offsetof(deb_result, stats_sums), offsetof(deb_result, stats_counts), offsetof(deb_result, gpu_launches), DEB_ABI_VERSION);
+  return 0; }'''
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "s.c"), "w").write(src)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "s.c"), "-o", os.path.join(d, "s")], check=True)
+        got = [int(x) for x in subprocess.run([os.path.join(d, "s")], capture_output=True, text=True, check=True).stdout.split()]
+    O, R = deb.OdeProblem, deb.Result
+    assert got == [O.filter.offset, O.filter_bits.offset, O.layout.offset, O.n_devices.offset, O.devices.offset, deb.DEB_MAX_DEVICES,
+                   R.stats_sums.offset, R.stats_counts.offset, R.gpu_launches.offset, deb.DEB_ABI_VERSION]
+
+
+def test_struct_size_rules_need_no_device(lib):
+    """A smaller struct_size (older header) is accepted, a larger one (newer header) and a truncated one are refused."""
+    ivp = deb.EnsembleIVP.ode(deb.LorenzSystem(10.0, 28.0, 8.0 / 3.0), 0.0, 1.0, np.zeros((0, 3))).t_eval([0.5]).method(E.dopri5())
+    P, R, arrs, ts, keep = ivp.build_problem()
+    P.struct_size = deb.OdeProblem.filter.offset   # ABI 8 size
+    R.struct_size = deb.Result.stats_sums.offset
+    P.n_devices = 77                                # beyond the declared size: must be ignored
+    assert lib.deb_solve_ode(C.byref(P), C.byref(R)) == deb.DEB_OK, lib.deb_last_error()
+    assert R.struct_size == deb.Result.stats_sums.offset and R.n_rows == 1
+    P.struct_size = C.sizeof(deb.OdeProblem) + 16
+    assert lib.deb_solve_ode(C.byref(P), C.byref(R)) == deb.DEB_ERR_BAD_ARG and b"struct_size" in lib.deb_last_error()
+    P.struct_size = deb.OdeProblem.opt.offset       # cut inside the mandatory part
+    assert lib.deb_solve_ode(C.byref(P), C.byref(R)) == deb.DEB_ERR_BAD_ARG
+    # the ABI 9 fields are validated
+    for field, value, msg in (("filter", 9, b"filter"), ("layout", 3, b"layout"), ("n_devices", 99, b"n_devices")):
+        P, R, arrs, ts, keep = ivp.build_problem()
+        setattr(P, field, value)
+        assert lib.deb_solve_ode(C.byref(P), C.byref(R)) == deb.DEB_ERR_BAD_ARG and msg in lib.deb_last_error(), field
+    P, R, arrs, ts, keep = ivp.build_problem()
+    P.filter, P.filter_bits = deb.DEB_FILTER_TRUNCATE_MANTISSA, 0
+    assert lib.deb_solve_ode(C.byref(P), C.byref(R)) == deb.DEB_ERR_BAD_ARG and b"filter_bits" in lib.deb_last_error()
+    P, R, arrs, ts, keep = ivp.build_problem()
+    P.memspace, P.n_devices = deb.DEB_MEM_DEVICE, 2
+    P.devices[0], P.devices[1] = 0, 1
+    assert lib.deb_solve_ode(C.byref(P), C.byref(R)) == deb.DEB_ERR_BAD_ARG and b"DEB_MEM_HOST" in lib.deb_last_error()
+
+
+def test_user_sde_and_sensitivity_system_compile_without_a_device(lib, tmp_path, monkeypatch):
+    """deb_check_sde / deb_check_ode compile the run-time kernels of a user-defined SDE (drift, diffusion, noise mixing) and
+    of a generated forward-sensitivity system; the cubins land in the disk cache and the second compile is a cache hit."""
+    monkeypatch.setenv("DEB_CACHE_DIR", str(tmp_path))
+    heston = deb.sde_from_source(2, "dydt[0] = p[0] * y[0]; dydt[1] = p[1] * (p[2] - y[1]);", "g[0] = y[0] * sqrt(y[1]); g[1] = p[3] * sqrt(y[1]);",
+                                 params=[0.1, 2.0, 0.04, 0.3, -0.7], noise_body="dw[1] = p[4] * dw[0] + sqrt(1.0 - p[4] * p[4]) * dw[1];")
+    import time
+    t0 = time.perf_counter()
+    for mid in (deb.DEB_EULER, deb.DEB_RK4, deb.DEB_MILSTEIN):
+        assert lib.deb_check_sde(heston.system_id, mid) == deb.DEB_OK, lib.deb_last_error()
+    cold = time.perf_counter() - t0
+    files = sorted(os.listdir(tmp_path))
+    assert len(files) == 3 and all(f.startswith("deb200-") and f.endswith(".cubin") for f in files)
+    t0 = time.perf_counter()
+    for mid in (deb.DEB_EULER, deb.DEB_RK4, deb.DEB_MILSTEIN):
+        assert lib.deb_check_sde(heston.system_id, mid) == deb.DEB_OK
+    assert time.perf_counter() - t0 < cold / 5, "the second compile did not come from the disk cache"
+    assert lib.deb_check_sde(heston.system_id, deb.DEB_DOPRI5) == deb.DEB_ERR_UNSUPPORTED
+    assert lib.deb_check_sde(deb.DEB_SDE_OU, deb.DEB_EULER) == deb.DEB_OK
+    bad = deb.sde_from_source(1, "dydt[0] = nonsense;", "g[0] = 1.0;", params=[1.0])
+    assert lib.deb_check_sde(bad.system_id, deb.DEB_EULER) == deb.DEB_ERR_BAD_ARG and b"did not compile" in lib.deb_last_error()
+    # forward sensitivities of the logistic equation: z = [y, dy/dk, dy/dm]
+    sens = deb.ode_sensitivity_from_source(1, "dydt[0] = p[0] * y[0] * (1.0 - y[0] / p[1]);", "J[0] = p[0] * (1.0 - 2.0 * y[0] / p[1]);",
+                                           "Jp[0] = y[0] * (1.0 - y[0] / p[1]); Jp[1] = p[0] * y[0] * y[0] / (p[1] * p[1]);", [1.0, 10.0])
+    assert sens.dim == 3
+    for m in (E.dopri5(), E.dop853(), E.rk4(0.01)):
+        deb.check_ode(sens, m)
+    with pytest.raises(ValueError, match="DEB_MAX_DIM"):
+        deb.ode_sensitivity_from_source(6, "dydt[0] = 0.0;", "", "", [1.0, 2.0, 3.0])
+
+
+def test_launch_counter_is_exported(lib):
+    assert lib.deb_launch_count() >= 0

@@ -3,7 +3,7 @@
 N=${1:-2000000}
 for lib in differential-equations_b200/libdeb200.so build/alt/*.so; do
   echo -n "$lib: "
-  DEB200_LIB=$PWD/$lib python bench.py --n-traj $N --steps 2 --warmup 1 --no-e2e --no-cpu 2>&1 | python -c "
+  DEB200_LIB=$PWD/$lib python bench.py --n-traj $N --steps 2 --warmup 1 --no-e2e --no-cpu --no-extra 2>&1 | python -c "
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):
