@@ -16,8 +16,9 @@ import re
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def load_tableaux():
-    """Parse the generated coefficient header (hex-float brace lists)."""
+def load_header_tableaux():
+    """The coefficient header the kernels and the C++ oracle are built from (tools/gen_tableau.py): only used to cross-check
+    the two extractions against each other (tests/test_host_logic.py), NOT by the restatement itself."""
     txt = open(os.path.join(ROOT, "oracle", "erk_tableau_data.h")).read().replace("\\\n", " ")
     out = {}
     for m in re.finditer(r"#define DEB_(\w+?)_(C|A|B|BH|ER|BI) (.*)", txt):
@@ -26,6 +27,15 @@ def load_tableaux():
         vals = [[float.fromhex(x.strip()) for x in r.split(",")] for r in rows]
         out.setdefault(name, {})[kind] = vals[0] if kind in ("C", "B", "BH", "ER") else vals
     return out
+
+
+def load_tableaux():
+    """The restatement's own tableaux: read from the reference's Rust sources by tests/support/reference_tableaux.py, a reader
+    that shares nothing with the generator of the header above, and committed as tests/golden/reference_tableaux.json."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "support"))
+    import reference_tableaux
+    return reference_tableaux.load_fixture()
 
 
 TAB = load_tableaux()

@@ -258,3 +258,35 @@ def test_user_sde_and_sensitivity_system_compile_without_a_device(lib, tmp_path,
 
 def test_launch_counter_is_exported(lib):
     assert lib.deb_launch_count() >= 0
+
+
+def test_rust_shim_structs_follow_the_header_field_for_field():
+    """The Rust shim cannot be compiled here (no toolchain): at least keep its #[repr(C)] transcriptions in lock step with
+    include/deb_ensemble.h -- same structs, same fields, same order, same array lengths -- and its ABI constant current."""
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "deb_ensemble.h")).read(), flags=re.S)
+    rs = re.sub(r"//[^\n]*", "", open(os.path.join(ROOT, "differential-equations_b200", "rust", "src", "lib.rs")).read())
+    consts = {"DEB_MAX_DIM": 16, "DEB_MAX_DEVICES": 16}
+    def c_fields(name):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), hdr, re.S).group(1)
+        out = []
+        for decl in body.split(";"):
+            decl = " ".join(decl.split())
+            if not decl:
+                continue
+            rest = re.match(r"^(?:const )?\w+ ?\** ?(.*)$", decl).group(1)  # drop the type (and its pointer stars)
+            for part in rest.split(","):
+                m = re.match(r"^\*? ?(\w+)(?:\[(.+)\])?$", part.strip())
+                out.append((m.group(1), eval(m.group(2), {}, consts) if m.group(2) else None))
+        return out
+    def rs_fields(name):
+        body = re.search(r"pub struct %s \{(.*?)\n\}" % name, rs, re.S).group(1)
+        out = []
+        for m in re.finditer(r"pub (\w+): ([^,\n]+),", body):
+            arr = re.match(r"\[\w+; (.+)\]", m.group(2).strip())
+            out.append((m.group(1), eval(arr.group(1), {}, consts) if arr else None))
+        return out
+    for s in ("deb_erk_options", "deb_ode_problem", "deb_sde_problem", "deb_result", "deb_heat_problem"):
+        assert rs_fields(s) == c_fields(s), s
+    assert "pub const DEB_ABI_VERSION: i32 = %d;" % deb.DEB_ABI_VERSION in rs
+    for fn in ("deb_solve_ode", "deb_solve_sde", "deb_solve_heat_mol", "deb_define_ode", "deb_define_event", "deb_define_sde", "deb_define_ode_sensitivity"):
+        assert "pub fn %s(" % fn in rs, fn

@@ -26,6 +26,30 @@ def test_tableau_data_is_what_the_generator_extracts_from_the_reference():
     assert out == open(os.path.join(ROOT, "oracle", "erk_tableau_data.h")).read()
 
 
+def test_two_independent_tableau_extractions_agree():
+    """The Python restatement reads its tableaux from tests/golden/reference_tableaux.json (tests/support/reference_tableaux.py:
+    tokenizer + recursive-descent evaluator over the Rust sources); the kernels and the C++ oracle are built from
+    erk_tableau_data.h (tools/gen_tableau.py: regular expressions + Python eval).  Two readers, no shared code, same bits."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "support"))
+    import reference_tableaux as rt
+    fixture = rt.load_fixture()
+    header = pr.load_header_tableaux()
+    assert sorted(fixture) == sorted(header) and len(fixture) == 19
+    for name, t in header.items():
+        for kind, vals in t.items():
+            a = np.array(vals, dtype=np.float64)
+            b = np.array(fixture[name][kind], dtype=np.float64)
+            if kind == "BI" and a.shape != b.shape:  # the crate declares the Verner dense-output array I x I; columns >= order are zero
+                assert (b[:, a.shape[1]:] == 0.0).all()
+                b = b[:, :a.shape[1]]
+            assert a.shape == b.shape and np.array_equal(a.view(np.uint64), b.view(np.uint64)), (name, kind)
+    if os.path.isdir("/root/reference/src/tableau"):  # the committed fixture is what the reader extracts from the crate today
+        fresh = rt.read_all()
+        for name, t in fresh.items():
+            for kind, vals in t.items():
+                assert np.array_equal(np.array(vals, dtype=np.float64).view(np.uint64), np.array(fixture[name][kind], dtype=np.float64).view(np.uint64)), (name, kind)
+
+
 def test_tableau_consistency_conditions():
     """Row sums c_i = sum_j a_ij and sum b_i = 1 (to the precision of the reference's literals), DOPRI5 FSAL row,
     the misplaced DOPRI5 dense row, literal spot checks."""
