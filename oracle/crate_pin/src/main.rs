@@ -3,7 +3,7 @@
 //! The build image of this repository has no Rust toolchain, so the oracle is a C++ restatement whose bits have never been
 //! compared with the crate itself ("parity unpinned" at the bit level).  On any machine with cargo:
 //!
-//!     tools/pin_oracle_against_crate.sh          # cargo run --release --example dump_reference_bits > tests/golden/reference_bits.json
+//!     tools/pin_oracle_against_crate.sh          # (cd oracle/crate_pin && cargo run --release) > tests/golden/reference_bits.json
 //!     python -m pytest tests/test_oracle_golden.py -k reference_bits
 //!
 //! The program runs the reference's own `IVP::ode(..).method(..).solve()` (src/ivp.rs:279,632,656,781) on a fixed list of cases

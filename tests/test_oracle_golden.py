@@ -361,7 +361,7 @@ def _unhex(v):
 
 def _replay_case(case):
     """Run one case of tests/golden/reference_bits.json (written by the Rust program
-    differential-equations_b200/rust/examples/dump_reference_bits.rs from the real crate) through the oracle."""
+    oracle/crate_pin/src/main.rs from the real crate) through the oracle."""
     y0 = np.array(_unhex(case["y0"]), dtype=np.float64).reshape(len(case["results"]), -1)
     if "params_per_traj" in case:
         prm = np.array(_unhex(case["params_per_traj"]))

@@ -5,6 +5,6 @@
 set -e
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
 command -v cargo >/dev/null || { echo "cargo not found: nothing pinned (this is the state of the build image)"; exit 3; }
-cd "$ROOT/differential-equations_b200/rust"
-cargo run --release --example dump_reference_bits > "$ROOT/tests/golden/reference_bits.json"
+cd "$ROOT/oracle/crate_pin"
+cargo run --release > "$ROOT/tests/golden/reference_bits.json"
 echo "wrote tests/golden/reference_bits.json; now run: python -m pytest tests/test_oracle_golden.py -k crate_bit_for_bit"
