@@ -253,11 +253,14 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the C3/C4/C5 lines")
     ap.add_argument("--quick-extra", action="store_true", help="C3/C4/C5 at a tenth of their size (smoke runs)")
+    ap.add_argument("--e2e-only", action="store_true", help="diagnostic: only the end-to-end leg (one warm-up device-resident step for the counters)")
     ap.add_argument("--single-process", action="store_true",
                     help="one process drives --gpus devices through the C ABI's device list (e2e only); not the driver's launch mode")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.e2e_only:
+        args.steps, args.warmup, args.no_cpu, args.no_extra = 1, 0, True, True
 
     import torch
     deb = importlib.import_module("differential-equations_b200")

@@ -850,6 +850,8 @@ int copy_blocks(const ShardMap& M, char* host_base, char* dev_base, size_t bpt, 
 struct SlotRes {
     cudaStream_t st = nullptr;  // H2D + kernel
     cudaStream_t cp = nullptr;  // streamed D2H
+    cudaStream_t cpx[3] = {nullptr, nullptr, nullptr};  // optional extra D2H streams (DEB_COPY_STREAMS > 1): more copy engines in flight
+    cudaEvent_t cpx_done[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t k0 = nullptr, k1 = nullptr, cp_done = nullptr;
     int* flags = nullptr;       // pinned, mapped: completion flags of the watermark blocks
     size_t n_flags = 0;
@@ -871,6 +873,10 @@ int acquire_slot(int device, size_t n_flags, SlotRes** out) {
         DEB_CUDA(cudaEventCreate(&r->k0));
         DEB_CUDA(cudaEventCreate(&r->k1));
         DEB_CUDA(cudaEventCreateWithFlags(&r->cp_done, cudaEventDisableTiming));
+        for (int q = 0; q < 3; q++) {
+            DEB_CUDA(cudaStreamCreateWithFlags(&r->cpx[q], cudaStreamNonBlocking));
+            DEB_CUDA(cudaEventCreateWithFlags(&r->cpx_done[q], cudaEventDisableTiming));
+        }
     }
     if (r->n_flags < n_flags) {
         if (r->flags) cudaFreeHost(r->flags);
@@ -1094,7 +1100,11 @@ int run_shard(const OdeCall& C, const ShardMap& M, int device, ShardOut* out) {
         Slot* s; int n; int device; ShardOut* out;
         ~SlotGuard() {
             for (int i = 0; i < n; i++) {
-                if (s[i].r) { cudaStreamSynchronize(s[i].r->st); cudaStreamSynchronize(s[i].r->cp); }
+                if (s[i].r) {
+                    cudaStreamSynchronize(s[i].r->st);
+                    cudaStreamSynchronize(s[i].r->cp);
+                    for (int q = 0; q < 3; q++) cudaStreamSynchronize(s[i].r->cpx[q]);
+                }
                 s[i].release_buffers();
                 if (s[i].r) release_slot(device, s[i].r);
             }
@@ -1135,11 +1145,20 @@ int run_shard(const OdeCall& C, const ShardMap& M, int device, ShardOut* out) {
     }
 
     // D2H of local blocks [b0, b1) of the chunk in slot S, on its copy stream
+    int n_copy_streams = 1;  // D2H streams per device; the row copies of a batch are dealt over them
+    if (const char* e = getenv("DEB_COPY_STREAMS")) n_copy_streams = std::max(1, std::min(4, atoi(e)));
     auto copy_out = [&](Slot& S, long long b0, long long b1, bool with_rows) -> int {
         cudaStream_t cp = S.r->cp;
 #define DEB_OUT(field, T, per) \
     if (R->field) { if (int rc = copy_blocks(M, (char*)R->field, (char*)S.field.p, sizeof(T) * (size_t)(per), S.lb0, b0, b1, true, cp)) return rc; }
-        if (with_rows && !row_major) DEB_OUT(y_eval, double, ne)
+        if (with_rows && !row_major && R->y_eval && n_copy_streams > 1 && b1 - b0 >= n_copy_streams) {
+            const long long per_stream = (b1 - b0 + n_copy_streams - 1) / n_copy_streams;
+            for (int q = 0; q < n_copy_streams; q++) {
+                const long long q0 = b0 + q * per_stream, q1 = std::min(b1, q0 + per_stream);
+                if (q1 <= q0) break;
+                if (int rc = copy_blocks(M, (char*)R->y_eval, (char*)S.y_eval.p, sizeof(double) * ne, S.lb0, q0, q1, true, q == 0 ? cp : S.r->cpx[q - 1])) return rc;
+            }
+        } else if (with_rows && !row_major) DEB_OUT(y_eval, double, ne)
         DEB_OUT(n_emitted, int, 1)
         DEB_OUT(t_final, double, 1)
         DEB_OUT(y_final, double, dim)
@@ -1252,6 +1271,10 @@ int run_shard(const OdeCall& C, const ShardMap& M, int device, ShardOut* out) {
             }
         }
         if (C.want_stats || row_major) DEB_CUDA(cudaStreamSynchronize(S.r->st));
+        for (int q = 0; q + 1 < n_copy_streams; q++) {  // the extra copy streams join the main one
+            DEB_CUDA(cudaEventRecord(S.r->cpx_done[q], S.r->cpx[q]));
+            DEB_CUDA(cudaStreamWaitEvent(S.r->cp, S.r->cpx_done[q], 0));
+        }
         DEB_CUDA(cudaEventRecord(S.r->cp_done, S.r->cp));
         if (dbg_t) {
             const double t_issued = since();

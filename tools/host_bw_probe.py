@@ -72,6 +72,31 @@ def main():
             per = [v]
         res[label] = {"per_rank_gbs": per, "sum_of_best_gbs": sum(per), "wall_s_for_3_reps": wall,
                       "aggregate_gbs_by_wall": world * 3 * n * 8 / wall / 1e9}
+    # D2H in 78 MB pieces (the size of a streamed batch of the HOST pipeline) on 1, 2 and 4 streams at once
+    for n_streams in (1, 2, 4):
+        streams = [torch.cuda.Stream(dev) for _ in range(n_streams)]
+        piece = 78_643_200 // 8
+        pieces = [(o, min(o + piece, n)) for o in range(0, n, piece)]
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        for i, (a, b) in enumerate(pieces):
+            with torch.cuda.stream(streams[i % n_streams]):
+                h[a:b].copy_(d[a:b], non_blocking=True)
+        torch.cuda.synchronize()
+        mine = n * 8 / (time.perf_counter() - t) / 1e9
+        if dist is not None:
+            dist.barrier()
+        wall = time.perf_counter() - t
+        vals = torch.tensor([mine], device=dev, dtype=torch.float64)
+        if dist is not None:
+            allv = [torch.zeros_like(vals) for _ in range(world)]
+            dist.all_gather(allv, vals)
+            per = [float(x.item()) for x in allv]
+        else:
+            per = [mine]
+        res["d2h_78MB_pieces_%d_streams" % n_streams] = {"per_rank_gbs": per, "aggregate_gbs_by_wall": world * n * 8 / wall / 1e9}
     if rank == 0:
         print(json.dumps({"world": world, "bytes_per_rank": n * 8, "results": res, "topology": topo()}), flush=True)
     if dist is not None:
