@@ -253,6 +253,7 @@ struct UserKernel {
     cudaKernel_t kernel = nullptr;
     bool adaptive = false;
     int block = 128;
+    unsigned dyn_smem = 0;  // dynamic shared memory of the instantiation (parked steps of the methods with extra dense stages)
 };
 struct UserSystem {
     int dim = 0, np = 0;
@@ -433,6 +434,31 @@ int nvrtc_compile(const std::string& src, const char* expr, bool user_code, std:
     return DEB_OK;
 }
 
+// (S, I) of the adaptive constructors: dormandprince/mod.rs:45-58, adaptive/mod.rs:47-122
+bool method_stage_counts(int method, int* S, int* I) {
+    switch (method) {
+        case DEB_DOPRI5: *S = 7; *I = 7; return true;
+        case DEB_DOP853: *S = 12; *I = 16; return true;
+        case DEB_RKF45: case DEB_CASH_KARP: *S = 6; *I = 6; return true;
+        case DEB_RKV655E: *S = 9; *I = 10; return true;
+        case DEB_RKV656E: *S = 9; *I = 12; return true;
+        case DEB_RKV766E: *S = 10; *I = 13; return true;
+        case DEB_RKV767E: *S = 10; *I = 16; return true;
+        case DEB_RKV877E: *S = 13; *I = 17; return true;
+        case DEB_RKV878E: *S = 13; *I = 21; return true;
+        case DEB_RKV988E: *S = 16; *I = 21; return true;
+        case DEB_RKV989E: *S = 16; *I = 26; return true;
+    }
+    return false;
+}
+// dynamic shared memory of a run-time instantiation dp_ensemble_kernel<.., 128, .., REC>: the formula of dp_dynamic_smem_bytes
+unsigned jit_dynamic_smem(int method, int dim, bool rec) {
+    int S = 0, I = 0;
+    if (!method_stage_counts(method, &S, &I) || rec || I <= S) return 0;
+    const long long bytes = (2ll + (long long)dim * (S + 3)) * 128 * 8;
+    return bytes <= 64 * 1024 ? (unsigned)bytes : 0u;
+}
+
 // Compile the ensemble kernel for (system, method, recorder kind) to a cubin (no device needed).  `us` = the user
 // system, or null for a built-in one.
 int compile_kernel_cubin(const UserSystem* us, int system, int method, bool rec, int event, bool filter, std::vector<char>* cubin,
@@ -502,6 +528,12 @@ int jit_kernel(const UserSystem* us, int device, int system, int method, bool re
     if (int rc = compile_kernel_cubin(us, system, method, rec, event, filter, &cubin, &lowered, &uk.adaptive)) return rc;
     DEB_CUDA(cudaLibraryLoadData(&uk.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
     DEB_CUDA(cudaLibraryGetKernel(&uk.kernel, uk.lib, lowered.c_str()));
+    if (uk.adaptive) {
+        int sdim = 0, snp = 0;
+        if (us) sdim = us->dim; else builtin_system_name(system, &sdim, &snp);
+        uk.dyn_smem = jit_dynamic_smem(method, sdim, rec);
+        if (uk.dyn_smem > 0) DEB_CUDA(cudaFuncSetAttribute((const void*)uk.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)uk.dyn_smem));
+    }
     auto ins = g_jit_kernels.emplace(key, uk);
     *out = &ins.first->second;
     return DEB_OK;
@@ -511,7 +543,7 @@ int launch_user(const UserKernel& uk, const deb::OdeKernelArgs& a, int sms, cuda
     long long blocks;
     if (uk.adaptive) {
         int per_sm = 0;
-        DEB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)uk.kernel, uk.block, 0));
+        DEB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)uk.kernel, uk.block, uk.dyn_smem));
         if (per_sm < 1) per_sm = 1;
         blocks = (long long)sms * per_sm;
     } else {
@@ -522,7 +554,7 @@ int launch_user(const UserKernel& uk, const deb::OdeKernelArgs& a, int sms, cuda
     if (blocks < 1) blocks = 1;
     if (getenv("DEB_DEBUG_LAUNCH")) fprintf(stderr, "[deb] run-time kernel: grid %lld x %d\n", blocks, uk.block);
     void* args[] = {(void*)&a};
-    DEB_CUDA(cudaLaunchKernel((const void*)uk.kernel, dim3((unsigned)blocks), dim3(uk.block), args, 0, st));
+    DEB_CUDA(cudaLaunchKernel((const void*)uk.kernel, dim3((unsigned)blocks), dim3(uk.block), args, uk.dyn_smem, st));
     deb_count_launch(1);
     return DEB_OK;
 }

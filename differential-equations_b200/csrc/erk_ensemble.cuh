@@ -295,7 +295,9 @@ namespace deb {
 //   vectors the interpolant needs (t, h, y, y_new, k0, f(y_new)) in shared memory and keeps stepping; the rows of all
 //   parked lanes are computed together in the service section.  A lane that hits again while parked does not commit
 //   its step, asks for service and redoes the attempt afterwards -- same inputs, same bits.  The arithmetic is
-//   unchanged: same operands, same operations, later.  DOP853 (3 extra dense stages) interpolates on the spot.
+//   unchanged: same operands, same operations, later.  Methods whose dense output needs extra stages (DOP853, the Verner pairs)
+//   park the WHOLE step -- the S stage vectors too -- in dynamic shared memory; the extra stages and the rows of all parked lanes
+//   are evaluated together by flush_dense_parked in the service section.
 // SHARED_P: every trajectory uses the same parameter set (passed by value in a.pc: no registers).
 // One attempt of the adaptive family with EVERY tableau term, zero coefficients included, exactly as the reference loops
 // (adaptive/ordinary.rs:95-126): 0 * inf = NaN and all.  Out of line and through memory on purpose: it runs only for an
@@ -331,13 +333,198 @@ __device__ __noinline__ void all_terms_attempt(const double* y, double* k, doubl
     *err_out = err;
 }
 
+// Rows [r0, r1) of the t_eval / even(dt) plan lie in the accepted step (t, y) -> (t + h, ynew); k[0] = f(t, y), k[1..S-1] are the
+// stages of the step, dydt = f(t + h, ynew).  Evaluates the method's dense output exactly as its `interpolate` does --
+//     Dormand-Prince family   cont[0..3], the extra stages S+1..I-1 and cont[4..O-1] (ordinary.rs:196-234), nested polynomial (:301-337)
+//     Verner pairs            the I - S extra stages (adaptive/ordinary.rs:145-160; the reference evaluates and counts them on EVERY
+//                             accepted step, only a step that emits a row reads them), Horner in s (:246-277)
+//     otherwise               cubic Hermite (interpolate.rs:40-60)
+// -- and hands the rows to the row staging.  Returns the number of rows emitted so far: r1, unless the EvenSolout tf sentinel
+// (the last plan entry) is among them, whose final-point rule (even.rs:166-188) decides.
+template <class Sys, class Tab, class RowsT>
+__device__ __forceinline__ int emit_dense_rows(const OdeKernelArgs& a, double (*s_rows)[32], unsigned lane, long long traj, double t, double h,
+                                               const double (&y)[Sys::DIM], const double (&ynew)[Sys::DIM], const double (&k)[Tab::S][Sys::DIM],
+                                               const double (&dydt)[Sys::DIM], const double* p, int r0, int r1) {
+    constexpr int N = Sys::DIM, S = Tab::S, I = Tab::I, O = Tab::O;
+    const double t_new = t + h;
+    double c1[N], c2[N], c3[N];
+    double ch[(O > 4) ? (O - 4) : 1][N];  // DP family: cont[4..O-1]
+    double kx[(I > S) ? (I - S) : 1][N];  // stage vectors k[S..I-1]
+    if constexpr (Tab::BI_POLY) {
+#pragma unroll
+        for (int i = S; i < I; i++) {
+            double ys[N];
+#pragma unroll
+            for (int c = 0; c < N; c++) ys[c] = y[c];
+#pragma unroll
+            for (int j = 0; j < i; j++) {
+                if (Tab::a(i, j) != 0.0) {
+                    const double ah = Tab::av(i, j) * h;
+#pragma unroll
+                    for (int c = 0; c < N; c++) ys[c] = ys[c] + ah * ((j < S) ? k[(j < S) ? j : 0][c] : kx[(j >= S) ? (j - S) : 0][c]);
+                }
+            }
+            Sys::rhs(t + Tab::cv(i) * h, ys, kx[i - S], p);
+        }
+    } else if constexpr (Tab::DP) {
+#pragma unroll
+        for (int c = 0; c < N; c++) {  // ordinary.rs:196-207
+            c1[c] = ynew[c] - y[c];
+            c2[c] = __dadd_rn(0.0, h * k[0][c]) - c1[c];
+            c3[c] = (c1[c] + (-h) * dydt[c]) - c2[c];
+        }
+        // extra dense stages, ordinary.rs:210-225: k[S] = dydt, stages S+1..I-1
+#pragma unroll
+        for (int c = 0; c < N; c++) kx[0][c] = dydt[c];
+#pragma unroll
+        for (int i = S + 1; i < I; i++) {
+            double ys[N];
+#pragma unroll
+            for (int c = 0; c < N; c++) ys[c] = y[c];
+#pragma unroll
+            for (int j = 0; j < i; j++) {
+                if (Tab::a(i, j) != 0.0) {
+                    const double ah = Tab::av(i, j) * h;
+#pragma unroll
+                    for (int c = 0; c < N; c++) ys[c] = ys[c] + ah * ((j < S) ? k[(j < S) ? j : 0][c] : kx[(j >= S) ? (j - S) : 0][c]);
+                }
+            }
+            Sys::rhs(t + Tab::cv(i) * h, ys, kx[i - S], p);
+        }
+#pragma unroll
+        for (int i = 4; i < O; i++) {  // ordinary.rs:228-234
+#pragma unroll
+            for (int c = 0; c < N; c++) ch[i - 4][c] = 0.0;
+#pragma unroll
+            for (int j = 0; j < I; j++) {
+                if (Tab::bi(i, j) != 0.0) {
+#pragma unroll
+                    for (int c = 0; c < N; c++)
+                        ch[i - 4][c] = __dadd_rn(ch[i - 4][c], Tab::biv(i, j) * ((j < S) ? k[(j < S) ? j : 0][c] : kx[(j >= S) ? (j - S) : 0][c]));
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < N; c++) ch[i - 4][c] = ch[i - 4][c] * h;
+        }
+    }
+    for (int r = r0; r < r1; r++) {
+        if (a.even && r == a.n_rows - 1) {  // the tf sentinel: final-point rule, even.rs:166-188
+            int w = -1;
+            if (t_new == a.tf) {
+                const double t_last = a.t_rows[r - 1];  // r >= 1: row 0 (t0) was emitted at init
+                w = (fabs(t_last - a.tf) <= a.even_tol) ? r - 1 : r;  // pop + push(tf, y): replace the near-duplicate; or push(tf, y)
+            }
+            if (w >= 0) RowsT::put(a, s_rows, lane, traj, w, r, ynew);
+            return (w == r) ? r + 1 : r;  // the sentinel slot counts only if it was written
+        }
+        const double te = a.t_rows[r];
+        double row[N];
+        if (te == t_new && !a.even) {  // exact hit: the solver state itself (t_eval.rs:113-114); EvenSolout always interpolates
+#pragma unroll
+            for (int c = 0; c < N; c++) row[c] = ynew[c];
+        } else if constexpr (Tab::BI_POLY) {  // adaptive/ordinary.rs:246-277: Horner in s over bi[i][0..O-1], times s
+            const double sx = (te - t) / h;
+#pragma unroll
+            for (int c = 0; c < N; c++) row[c] = y[c];
+#pragma unroll
+            for (int i = 0; i < I; i++) {
+                if (Tab::bi_row(i)) {  // an all-zero row adds (+0 * h) * k[i]
+                    double ci = Tab::biv(i, O - 1);
+#pragma unroll
+                    for (int j = O - 2; j >= 0; j--) ci = ci * sx + Tab::biv(i, j);
+                    ci = ci * sx;
+                    const double w = ci * h;
+#pragma unroll
+                    for (int c = 0; c < N; c++) row[c] = row[c] + w * ((i < S) ? k[(i < S) ? i : 0][c] : kx[(i >= S) ? (i - S) : 0][c]);
+                }
+            }
+        } else if constexpr (!Tab::DP) {  // cubic Hermite (adaptive family without bi; only wide systems get here)
+            const double hh = t_new - t;
+            const double sx = (te - t) / hh;
+            const double s2 = sx * sx, s3 = s2 * sx;
+            const double h00 = 2.0 * s3 - 3.0 * s2 + 1.0;
+            const double h10 = s3 - 2.0 * s2 + sx;
+            const double h01 = -2.0 * s3 + 3.0 * s2;
+            const double h11 = s3 - s2;
+            const double w10 = h10 * hh, w11 = h11 * hh;
+#pragma unroll
+            for (int c = 0; c < N; c++) {
+                double v = __dadd_rn(0.0, h00 * y[c]);
+                v = v + w10 * k[0][c];
+                v = v + h01 * ynew[c];
+                v = v + w11 * dydt[c];
+                row[c] = v;
+            }
+        } else {  // interpolate, ordinary.rs:301-337, factor order as written
+            const double sx = (te - t) / h;
+            const double s1 = 1.0 - sx;
+#pragma unroll
+            for (int c = 0; c < N; c++) {
+                double accp = (O > 4) ? ch[O - 5][c] : c3[c];
+#pragma unroll
+                for (int i = O - 2; i >= 1; i--) {
+                    double factor;
+                    if (i >= 4) factor = (((O - 1) - i) % 2 == 1) ? s1 : sx;
+                    else factor = (i % 2 == 1) ? s1 : sx;
+                    const double ci = (i >= 4) ? ch[(i >= 4) ? (i - 4) : 0][c] : (i == 3 ? c3[c] : (i == 2 ? c2[c] : c1[c]));
+                    accp = accp * factor + ci;
+                }
+                row[c] = y[c] + sx * accp;
+            }
+        }
+        RowsT::put(a, s_rows, lane, traj, r, r, row);
+    }
+    return r1;
+}
+
+// Parked emission for the methods whose dense output needs extra stages (DOP853, the Verner pairs): a lane whose step contains
+// t_eval points stores the whole step -- t, h, y, y_new, f(y_new) and the S stage vectors -- in dynamic shared memory and keeps
+// stepping; in the service section every parked lane of the warp runs this function TOGETHER (extra stages, cont / Horner rows), instead
+// of one or two lanes doing it on the spot while the other thirty wait (round 1: rkv989e 600 ms against rkv988e 338 ms per 1 M
+// trajectories).  Slot layout: [t][h][y: N][y_new: N][dydt: N][k: S x N], each slot 32 lanes wide.  Out of line on purpose: its ~200
+// registers of working set must not shape the register allocation of the hot loop.
+template <class Sys, class Tab>
+__host__ __device__ constexpr int dense_park_slots() { return 2 + Sys::DIM * (Tab::S + 3); }
+
+template <class Sys, class Tab, class RowsT>
+__device__ __noinline__ int flush_dense_parked(const OdeKernelArgs& a, const double* st, double (*s_rows)[32], unsigned lane, long long traj,
+                                               int r0, int r1) {
+    constexpr int N = Sys::DIM, S = Tab::S, NP = Sys::NP;
+    double y[N], ynew[N], dydt[N], k[S][N], p[NP > 0 ? NP : 1];
+    const double t = st[0 * 32], h = st[1 * 32];
+#pragma unroll
+    for (int c = 0; c < N; c++) {
+        y[c] = st[(2 + c) * 32];
+        ynew[c] = st[(2 + N + c) * 32];
+        dydt[c] = st[(2 + 2 * N + c) * 32];
+    }
+#pragma unroll
+    for (int i = 0; i < S; i++) {
+#pragma unroll
+        for (int c = 0; c < N; c++) k[i][c] = st[(2 + 3 * N + i * N + c) * 32];
+    }
+#pragma unroll
+    for (int q = 0; q < NP; q++) p[q] = a.params ? a.params[traj * a.params_stride + q] : a.pc[q];
+    return emit_dense_rows<Sys, Tab, RowsT>(a, s_rows, lane, traj, t, h, y, ynew, k, dydt, p, r0, r1);
+}
+
+// dynamic shared memory of dp_ensemble_kernel<Sys, Tab, BLOCK, .., REC>: the parked steps of the methods with extra dense stages
+template <class Sys, class Tab, int BLOCK, bool REC>
+__host__ __device__ constexpr bool dense_park_enabled() {
+    return (Tab::I > Tab::S) && !REC && ((long long)dense_park_slots<Sys, Tab>() * BLOCK * 8 <= 64 * 1024);
+}
+template <class Sys, class Tab, int BLOCK, bool REC>
+__host__ __device__ constexpr unsigned dp_dynamic_smem_bytes() {
+    return dense_park_enabled<Sys, Tab, BLOCK, REC>() ? (unsigned)(dense_park_slots<Sys, Tab>() * BLOCK * 8) : 0u;
+}
+
 // REC: the output goes through a per-step recorder (step_recorder.cuh) instead of the t_eval / even(dt) row plan.
 // FILTER: the step-size filter hook is not the identity (a.filter_mask).
 template <class Sys, class Tab, int BLOCK, int MIN_BLOCKS, bool SHARED_P, bool REC = false, class Evt = EvtNone, bool FILTER = false>
 #ifdef DEB_VAR_MAXNREG  // EXPERIMENT: an explicit register cap instead of the one derived from MIN_BLOCKS
-__global__ void __maxnreg__(DEB_VAR_MAXNREG) dp_ensemble_kernel(const OdeKernelArgs a) {
+__global__ void __maxnreg__(DEB_VAR_MAXNREG) dp_ensemble_kernel(const __grid_constant__ OdeKernelArgs a) {
 #else
-__global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const OdeKernelArgs a) {
+__global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const __grid_constant__ OdeKernelArgs a) {
 #endif
     constexpr int N = Sys::DIM, NP = Sys::NP, S = Tab::S, I = Tab::I, O = Tab::O;
     constexpr unsigned FULL = 0xffffffffu;
@@ -369,6 +556,11 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
     __shared__ double s_lane[BLOCK / 32][NPARK + Rows::SLOTS][32];
     double (*stash)[32] = s_lane[threadIdx.x >> 5];
     double (*s_rows)[32] = stash + NPARK;
+    // methods with extra dense stages park the whole step in dynamic shared memory (flush_dense_parked)
+    constexpr bool DEFER2 = dense_park_enabled<Sys, Tab, BLOCK, REC>();
+    constexpr int NPARK2 = dense_park_slots<Sys, Tab>();
+    extern __shared__ double s_dyn[];
+    double (*dstash)[32] = reinterpret_cast<double (*)[32]>(s_dyn) + (DEFER2 ? (threadIdx.x >> 5) * NPARK2 : 0);
     const bool want_rows = (a.y_eval != nullptr);
     bool pending = false;  // this lane has a parked step
     int pend_idx = 0;      // first row of the parked step
@@ -457,6 +649,13 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
                         Rows::done(a, s_rows, lane, traj, w, r);
                     }
                 }
+                pending = false;
+            }
+            __syncwarp();
+        }
+        if (DEFER2) {
+            if (pending) {  // all parked lanes of the warp together
+                idx = flush_dense_parked<Sys, Tab, Rows>(a, &dstash[0][lane], s_rows, lane, traj, pend_idx, idx);
                 pending = false;
             }
             __syncwarp();
@@ -715,7 +914,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
             // step contains a t_eval point while its row slot is still occupied does not commit this attempt: it is redone, bit
             // for bit, after the service section.  The counters below must not advance for the attempt that is thrown away
             // (the reference advances them once per 100th step).
-            if (Tab::DP && accept && m100 == 99 && !(DEFER && pending && ((te - t_new) * dir <= 0.0))) {
+            if (Tab::DP && accept && m100 == 99 && !((DEFER || DEFER2) && pending && ((te - t_new) * dir <= 0.0))) {
                 // ysti = the argument of the last stage; rebuilt here (same operations, same bits) instead of being
                 // kept alive in registers through 99 steps out of 100
                 double ysti[N];
@@ -754,18 +953,34 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
             // ---- TEvalSolout (t_eval.rs:100-130): does a t_eval point lie in this step?  (te - t_new == 0 iff te == t_new)
             const bool hit = accept && fin < 0 && ((te - t_new) * dir <= 0.0);
             bool blocked = false;
-            if (DEFER) {
+            if (DEFER || DEFER2) {
                 blocked = hit && pending;  // slot occupied: do not commit, get the slot flushed, redo this attempt
                 if (hit && !blocked) {
                     if (want_rows) {  // park the step
-                        stash[0][lane] = t;
-                        stash[1][lane] = h;
+                        if constexpr (DEFER2) {
+                            dstash[0][lane] = t;
+                            dstash[1][lane] = h;
 #pragma unroll
-                        for (int c = 0; c < N; c++) {
-                            stash[2 + c][lane] = y[c];
-                            stash[2 + N + c][lane] = ynew[c];
-                            stash[2 + 2 * N + c][lane] = k[0][c];
-                            stash[2 + 3 * N + c][lane] = dydt[c];
+                            for (int c = 0; c < N; c++) {
+                                dstash[2 + c][lane] = y[c];
+                                dstash[2 + N + c][lane] = ynew[c];
+                                dstash[2 + 2 * N + c][lane] = dydt[c];
+                            }
+#pragma unroll
+                            for (int i = 0; i < S; i++) {
+#pragma unroll
+                                for (int c = 0; c < N; c++) dstash[2 + 3 * N + i * N + c][lane] = k[i][c];
+                            }
+                        } else {
+                            stash[0][lane] = t;
+                            stash[1][lane] = h;
+#pragma unroll
+                            for (int c = 0; c < N; c++) {
+                                stash[2 + c][lane] = y[c];
+                                stash[2 + N + c][lane] = ynew[c];
+                                stash[2 + 2 * N + c][lane] = k[0][c];
+                                stash[2 + 3 * N + c][lane] = dydt[c];
+                            }
                         }
                         pend_idx = idx;
                         pending = true;
@@ -777,139 +992,13 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const Od
                 }
                 __syncwarp();
             } else {
-                if (hit) {
-                    double c1[N], c2[N], c3[N];
-                    double ch[(O > 4) ? (O - 4) : 1][N];  // DP family: cont[4..O-1]
-                    double kx[(I > S) ? (I - S) : 1][N];  // stage vectors k[S..I-1]
-                    if constexpr (Tab::BI_POLY) {
-                        // extra stages of the dense-output polynomial, adaptive/ordinary.rs:145-160.  The reference evaluates
-                        // them on every accepted step (and counts them); only a step that emits a row reads them.
-#pragma unroll
-                        for (int i = S; i < I; i++) {
-                            double ys[N];
-#pragma unroll
-                            for (int c = 0; c < N; c++) ys[c] = y[c];
-#pragma unroll
-                            for (int j = 0; j < i; j++) {
-                                if (Tab::a(i, j) != 0.0) {
-                                    const double ah = Tab::av(i, j) * h;
-#pragma unroll
-                                    for (int c = 0; c < N; c++) ys[c] = ys[c] + ah * ((j < S) ? k[(j < S) ? j : 0][c] : kx[(j >= S) ? (j - S) : 0][c]);
-                                }
-                            }
-                            Sys::rhs(t + Tab::cv(i) * h, ys, kx[i - S], p);
-                        }
-                    } else if constexpr (Tab::DP) {
-#pragma unroll
-                        for (int c = 0; c < N; c++) {  // ordinary.rs:196-207
-                            c1[c] = ynew[c] - y[c];
-                            c2[c] = __dadd_rn(0.0, h * k[0][c]) - c1[c];
-                            c3[c] = (c1[c] + (-h) * dydt[c]) - c2[c];
-                        }
-                        // extra dense stages, ordinary.rs:210-225: k[S] = dydt, stages S+1..I-1
-#pragma unroll
-                        for (int c = 0; c < N; c++) kx[0][c] = dydt[c];
-#pragma unroll
-                        for (int i = S + 1; i < I; i++) {
-                            double ys[N];
-#pragma unroll
-                            for (int c = 0; c < N; c++) ys[c] = y[c];
-#pragma unroll
-                            for (int j = 0; j < i; j++) {
-                                if (Tab::a(i, j) != 0.0) {
-                                    const double ah = Tab::av(i, j) * h;
-#pragma unroll
-                                    for (int c = 0; c < N; c++) ys[c] = ys[c] + ah * ((j < S) ? k[(j < S) ? j : 0][c] : kx[(j >= S) ? (j - S) : 0][c]);
-                                }
-                            }
-                            Sys::rhs(t + Tab::cv(i) * h, ys, kx[i - S], p);
-                        }
-#pragma unroll
-                        for (int i = 4; i < O; i++) {  // ordinary.rs:228-234
-#pragma unroll
-                            for (int c = 0; c < N; c++) ch[i - 4][c] = 0.0;
-#pragma unroll
-                            for (int j = 0; j < I; j++) {
-                                if (Tab::bi(i, j) != 0.0) {
-#pragma unroll
-                                    for (int c = 0; c < N; c++)
-                                        ch[i - 4][c] = __dadd_rn(ch[i - 4][c], Tab::biv(i, j) * ((j < S) ? k[(j < S) ? j : 0][c] : kx[(j >= S) ? (j - S) : 0][c]));
-                                }
-                            }
-#pragma unroll
-                            for (int c = 0; c < N; c++) ch[i - 4][c] = ch[i - 4][c] * h;
-                        }
-                    }
+                if (hit) {  // interpolate on the spot (per-step-recorder kernels never get here with rows; wide systems do)
+                    const int r0 = idx;
                     while ((te - t_new) * dir <= 0.0) {
-                        if (a.even && idx == a.n_rows - 1) {  // the tf sentinel: final-point rule, even.rs:166-188
-                            int w = -1;
-                            if (t_new == tf) {
-                                const double t_last = a.t_rows[idx - 1];
-                                w = (fabs(t_last - tf) <= a.even_tol) ? idx - 1 : idx;
-                            }
-                            if (w >= 0 && want_rows) Rows::put(a, s_rows, lane, traj, w, idx, ynew);
-                            if (w == idx) idx += 1;
-                            te = te_none;
-                            break;
-                        }
-                        double row[N];
-                        if (te == t_new && !a.even) {  // exact hit: the solver state itself (t_eval.rs:113-114)
-#pragma unroll
-                            for (int c = 0; c < N; c++) row[c] = ynew[c];
-                        } else if constexpr (Tab::BI_POLY) {  // adaptive/ordinary.rs:246-277: Horner in s over bi[i][0..O-1], times s
-                            const double sx = (te - t) / h;
-#pragma unroll
-                            for (int c = 0; c < N; c++) row[c] = y[c];
-#pragma unroll
-                            for (int i = 0; i < I; i++) {
-                                if (Tab::bi_row(i)) {  // an all-zero row adds (+0 * h) * k[i]
-                                    double ci = Tab::biv(i, O - 1);
-#pragma unroll
-                                    for (int j = O - 2; j >= 0; j--) ci = ci * sx + Tab::biv(i, j);
-                                    ci = ci * sx;
-                                    const double w = ci * h;
-#pragma unroll
-                                    for (int c = 0; c < N; c++) row[c] = row[c] + w * ((i < S) ? k[(i < S) ? i : 0][c] : kx[(i >= S) ? (i - S) : 0][c]);
-                                }
-                            }
-                        } else if constexpr (!Tab::DP) {  // cubic Hermite (adaptive family without bi; only wide systems get here)
-                            const double hh = t_new - t;
-                            const double sx = (te - t) / hh;
-                            const double s2 = sx * sx, s3 = s2 * sx;
-                            const double h00 = 2.0 * s3 - 3.0 * s2 + 1.0;
-                            const double h10 = s3 - 2.0 * s2 + sx;
-                            const double h01 = -2.0 * s3 + 3.0 * s2;
-                            const double h11 = s3 - s2;
-                            const double w10 = h10 * hh, w11 = h11 * hh;
-#pragma unroll
-                            for (int c = 0; c < N; c++) {
-                                double v = __dadd_rn(0.0, h00 * y[c]);
-                                v = v + w10 * k[0][c];
-                                v = v + h01 * ynew[c];
-                                v = v + w11 * dydt[c];
-                                row[c] = v;
-                            }
-                        } else {  // interpolate, ordinary.rs:301-337, factor order as written
-                            const double sx = (te - t) / h;
-                            const double s1 = 1.0 - sx;
-#pragma unroll
-                            for (int c = 0; c < N; c++) {
-                                double accp = (O > 4) ? ch[O - 5][c] : c3[c];
-#pragma unroll
-                                for (int i = O - 2; i >= 1; i--) {
-                                    double factor;
-                                    if (i >= 4) factor = (((O - 1) - i) % 2 == 1) ? s1 : sx;
-                                    else factor = (i % 2 == 1) ? s1 : sx;
-                                    const double ci = (i >= 4) ? ch[(i >= 4) ? (i - 4) : 0][c] : (i == 3 ? c3[c] : (i == 2 ? c2[c] : c1[c]));
-                                    accp = accp * factor + ci;
-                                }
-                                row[c] = y[c] + sx * accp;
-                            }
-                        }
-                        if (want_rows) Rows::put(a, s_rows, lane, traj, idx, idx, row);
                         idx += 1;
                         te = (idx < a.n_rows) ? a.t_rows[idx] : te_none;
                     }
+                    if (want_rows) idx = emit_dense_rows<Sys, Tab, Rows>(a, s_rows, lane, traj, t, h, y, ynew, k, dydt, p, r0, idx);
                 }
                 __syncwarp();
             }

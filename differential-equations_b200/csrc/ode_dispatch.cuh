@@ -43,8 +43,11 @@ inline int cuda_fail(cudaError_t e, const char* what, const char* file, int line
 template <class Sys, class Tab, int BLOCK, int MIN_BLOCKS, bool SHARED_P>
 int launch_dp_impl(const deb::OdeKernelArgs& a, int sms, cudaStream_t st) {
     auto kern = deb::dp_ensemble_kernel<Sys, Tab, BLOCK, MIN_BLOCKS, SHARED_P>;
+    // methods with extra dense stages park whole steps in dynamic shared memory (erk_ensemble.cuh: flush_dense_parked)
+    constexpr unsigned dyn = deb::dp_dynamic_smem_bytes<Sys, Tab, BLOCK, false>();
+    if (dyn > 0) DEB_DISPATCH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     int per_sm = 0;
-    DEB_DISPATCH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, 0));
+    DEB_DISPATCH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, dyn));
     if (per_sm < 1) per_sm = 1;
     // persistent grid: every resident CTA slot of every SM, but never more threads than trajectories
     long long blocks = (long long)sms * per_sm;
@@ -52,7 +55,7 @@ int launch_dp_impl(const deb::OdeKernelArgs& a, int sms, cudaStream_t st) {
     if (blocks > need) blocks = need;
     if (blocks < 1) blocks = 1;
     if (getenv("DEB_DEBUG_LAUNCH")) fprintf(stderr, "[deb] built-in kernel: grid %lld x %d\n", blocks, BLOCK);
-    kern<<<(unsigned)blocks, BLOCK, 0, st>>>(a);
+    kern<<<(unsigned)blocks, BLOCK, dyn, st>>>(a);
     DEB_DISPATCH_CUDA(cudaGetLastError());
     deb_count_launch(1);
     return DEB_OK;
