@@ -1901,6 +1901,7 @@ extern "C" int deb_solve_sde(const deb_sde_problem* P_user, deb_result* R_user) 
         a.y_eval = R->y_eval; a.n_emitted = R->n_emitted; a.t_final = R->t_final; a.y_final = R->y_final;
         a.status = R->status; a.accepted = R->accepted; a.rejected = R->rejected; a.evals = R->evals;
     }
+    a.rows_vec = (a.y_eval && ((size_t)P->n_eval * dim) % 4 == 0 && ((uintptr_t)a.y_eval % 32) == 0) ? 1 : 0;
     if (host) DEB_CUDA(cudaEventRecord(res->k0, st));
     if (user) { if (int rc = launch_user_sde(user_kernel, a, di.sms, st)) return rc; }
     else if (int rc = launch(a, di.sms, st)) return rc;

@@ -140,6 +140,14 @@ __device__ __noinline__ void store_row_group(double* dst, const double* src, int
     }
 }
 
+// where the rows of an ensemble go: base of y_eval, rows per trajectory, and whether row groups start 32-byte aligned
+struct RowSink {
+    double* y_eval;
+    int row_stride;
+    int rows_vec;
+};
+__device__ __forceinline__ RowSink row_sink(const OdeKernelArgs& a) { return RowSink{a.y_eval, a.row_stride, a.rows_vec}; }
+
 template <int N, int BLOCK, bool ON = true>
 struct RowStage {
     static constexpr int G4 = (N % 4 == 0) ? 4 : (N % 2 == 0) ? 2 : 1;  // gcd(N, 4)
@@ -150,7 +158,7 @@ struct RowStage {
     // row w of trajectory `traj`; `emitted` = rows emitted before this call (w == emitted for an append; w == emitted - 1
     // when EvenSolout replaces its last point, even.rs:166-188)
     // buf: the lane's warp-private staging rows, buf[slot][lane] (same base register as the parked-step stash)
-    __device__ __forceinline__ static void put(const OdeKernelArgs& a, double (*buf)[32], unsigned lane, long long traj, int w, int emitted,
+    __device__ __forceinline__ static void put(const RowSink& a, double (*buf)[32], unsigned lane, long long traj, int w, int emitted,
                                                const double (&row)[N]) {
         if constexpr (ENABLED) {
             if (w / ROWG == emitted / ROWG) {  // the group being collected
@@ -173,12 +181,12 @@ struct RowStage {
     }
 
     // component-wise variant of put: set() every component of row w, then done()
-    __device__ __forceinline__ static void set(const OdeKernelArgs& a, double (*buf)[32], unsigned lane, long long traj, int w, int emitted,
+    __device__ __forceinline__ static void set(const RowSink& a, double (*buf)[32], unsigned lane, long long traj, int w, int emitted,
                                                int c, double v) {
         if (ENABLED && w / ROWG == emitted / ROWG) buf[(w % ROWG) * N + c][lane] = v;
         else a.y_eval[((size_t)traj * a.row_stride + w) * N + c] = v;
     }
-    __device__ __forceinline__ static void done(const OdeKernelArgs& a, double (*buf)[32], unsigned lane, long long traj, int w, int emitted) {
+    __device__ __forceinline__ static void done(const RowSink& a, double (*buf)[32], unsigned lane, long long traj, int w, int emitted) {
         if constexpr (ENABLED) {
             if (w / ROWG == emitted / ROWG && w % ROWG == ROWG - 1)
                 store_row_group<ROWG * N>(a.y_eval + ((size_t)traj * a.row_stride + (size_t)(w - (ROWG - 1))) * N, &buf[0][lane], 32, a.rows_vec);
@@ -186,13 +194,24 @@ struct RowStage {
     }
 
     // the trajectory has ended with `emitted` rows: write the rows of the incomplete last group
-    __device__ __forceinline__ static void finish(const OdeKernelArgs& a, double (*buf)[32], unsigned lane, long long traj, int emitted) {
+    __device__ __forceinline__ static void finish(const RowSink& a, double (*buf)[32], unsigned lane, long long traj, int emitted) {
         if constexpr (ENABLED) {
             const int first = (emitted / ROWG) * ROWG;
             double* dst = a.y_eval + ((size_t)traj * a.row_stride + first) * N;
             const int n = (emitted - first) * N;
             for (int e = 0; e < n; e++) dst[e] = buf[e][lane];
         }
+    }
+    // the same, from the kernel arguments of the ODE kernels
+    __device__ __forceinline__ static void put(const OdeKernelArgs& a, double (*buf)[32], unsigned lane, long long traj, int w, int emitted,
+                                               const double (&row)[N]) { put(row_sink(a), buf, lane, traj, w, emitted, row); }
+    __device__ __forceinline__ static void set(const OdeKernelArgs& a, double (*buf)[32], unsigned lane, long long traj, int w, int emitted,
+                                               int c, double v) { set(row_sink(a), buf, lane, traj, w, emitted, c, v); }
+    __device__ __forceinline__ static void done(const OdeKernelArgs& a, double (*buf)[32], unsigned lane, long long traj, int w, int emitted) {
+        done(row_sink(a), buf, lane, traj, w, emitted);
+    }
+    __device__ __forceinline__ static void finish(const OdeKernelArgs& a, double (*buf)[32], unsigned lane, long long traj, int emitted) {
+        finish(row_sink(a), buf, lane, traj, emitted);
     }
 };
 

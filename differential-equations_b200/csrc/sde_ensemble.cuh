@@ -38,6 +38,7 @@ struct SdeKernelArgs {
     const int* row_step;    // [n_rows]
     const double* row_s;    // [n_rows]
     double* y_eval;
+    int rows_vec;           // y_eval row groups start 32-byte aligned (RowStage, erk_ensemble.cuh)
     int* n_emitted;
     double* t_final;
     double* y_final;
@@ -54,6 +55,11 @@ __global__ void __launch_bounds__(BLOCK) sde_ensemble_kernel(const SdeKernelArgs
     constexpr int N = Sde::DIM, NP = Sde::NP, S = Tab::S;
     const double t0 = a.t0, tf = a.tf;
     const long long stride = (long long)gridDim.x * BLOCK;
+    using Rows = RowStage<N, BLOCK>;  // rows leave the chip as whole 32-byte sectors (erk_ensemble.cuh)
+    __shared__ double s_lane[BLOCK / 32][Rows::SLOTS][32];
+    double (*s_rows)[32] = s_lane[threadIdx.x >> 5];
+    const unsigned lane = threadIdx.x & 31u;
+    const RowSink sink{a.y_eval, a.row_stride, a.rows_vec};
 
     for (long long traj = (long long)blockIdx.x * BLOCK + threadIdx.x; traj < a.n_traj; traj += stride) {
         double p[(NP + Sde::NPX) > 0 ? (NP + Sde::NPX) : 1];
@@ -72,10 +78,7 @@ __global__ void __launch_bounds__(BLOCK) sde_ensemble_kernel(const SdeKernelArgs
             Sde::drift(t, y, dydt, p);
             evals = MILSTEIN ? 1 : 2;  // ERK: drift + diffusion (the initial diffusion value is not used); Milstein: drift only
             if (a.emit_t0) {
-                if (a.y_eval) {
-#pragma unroll
-                    for (int c = 0; c < N; c++) a.y_eval[(traj * a.row_stride) * N + c] = y[c];
-                }
+                if (a.y_eval) Rows::put(sink, s_rows, lane, traj, 0, 0, y);
                 n_emit = 1;
                 idx = 1;
             }
@@ -143,10 +146,7 @@ __global__ void __launch_bounds__(BLOCK) sde_ensemble_kernel(const SdeKernelArgs
 #pragma unroll
                     for (int c = 0; c < N; c++) row[c] = __dadd_rn(0.0, (1.0 - sw) * y[c]) + sw * y_next[c];
                 }
-                if (a.y_eval) {
-#pragma unroll
-                    for (int c = 0; c < N; c++) a.y_eval[(traj * a.row_stride + n_emit) * N + c] = row[c];
-                }
+                if (a.y_eval) Rows::put(sink, s_rows, lane, traj, n_emit, n_emit, row);
                 n_emit += 1;
                 idx += 1;
                 next_step = (idx < a.n_rows) ? a.row_step[idx] : -1;
@@ -199,6 +199,7 @@ __global__ void __launch_bounds__(BLOCK) sde_ensemble_kernel(const SdeKernelArgs
         }
         const int fin = a.final_status;
         const int steps = a.n_steps;
+        if (a.y_eval) Rows::finish(sink, s_rows, lane, traj, n_emit);
         if (a.status) a.status[traj] = fin;
         if (a.t_final) a.t_final[traj] = t;
         if (a.y_final) {
