@@ -1327,6 +1327,7 @@ int run_shard(const OdeCall& C, const ShardMap& M, int device, ShardOut* out) {
     }
     if (n_chunks > 0) { if (int rc = drain(slot[(n_chunks - 1) % n_slots])) return rc; }
     for (int s = 0; s < n_slots && n_chunks > 0; s++) DEB_CUDA(cudaStreamSynchronize(slot[s].r->cp));
+    if (dbg_t) fprintf(stderr, "[deb timing] device %d: shard finished %.1f ms (before buffers are released)\n", device, since());
     return DEB_OK;
 }
 
@@ -1597,6 +1598,8 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P_user, deb_result* R_user) 
     }
     float kernel_ms = 0.f;
     for (int g = 0; g < G; g++) kernel_ms = std::max(kernel_ms, outs[g].kernel_ms);
+    const bool dbg_t = getenv("DEB_DEBUG_TIMING") != nullptr;
+    const double t_joined = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
     if (C.want_stats) {
         // every device holds the sums over its own trajectories; the all-reduce of these 2*ne doubles + n_eval counts is the
         // only cross-device traffic of the call
@@ -1634,6 +1637,7 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P_user, deb_result* R_user) 
     }
     R->kernel_ms = kernel_ms;  // per device: sum over its chunks; the call reports the slowest device
     R->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+    if (dbg_t) fprintf(stderr, "[deb timing] call: all %d device(s) done %.1f ms, statistics reduced and copied %.1f ms\n", G, t_joined, (double)R->total_ms);
     R->gpu_launches = (int32_t)(g_launches.load() - launches0);
     return DEB_OK;
 }

@@ -314,3 +314,18 @@ def test_launch_counter_counts_kernels():
     assert lib.deb_launch_count() - before == 1 and s.gpu_launches == 1
     s = deb.EnsembleIVP.ode(lorenz(), 0.0, 1.0, y0).t_eval([1.0]).method(E.dopri5()).with_stats().solve()
     assert s.gpu_launches == 3  # integration + the two statistics kernels
+
+
+# ------------------------------------------------------------------------------------------ an output of the real crate
+def test_gpu_reproduces_the_output_printed_in_the_crates_documentation():
+    """docs/ode.md:108-123 (tests/golden/reference_docs_output.json): the kernels -- DOP853, EvenSolout, event detection with a terminal
+    event -- give the 325 evaluations, 20 + 2 steps and six rows the real crate printed, for every trajectory of an ensemble of copies."""
+    import json
+    import os
+    from test_oracle_golden import _docs_example, check_docs_example
+    doc = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_docs_output.json")))
+    ivp = _docs_example(doc)
+    ivp.y0s = np.full((64, 1), doc["y0"])
+    sol = ivp.solve()
+    check_docs_example(sol, doc)
+    assert (sol.evals == 325).all() and (sol.accepted == 20).all() and (sol.rejected == 2).all() and (sol.status == deb.DEB_STATUS_INTERRUPTED).all()

@@ -435,3 +435,29 @@ def test_reference_bits_replay_machinery_round_trips():
         case["results"] = res
         _assert_case_matches(json.loads(json.dumps(case)), _replay_case(case))
     assert cases[1]["results"][0]["status"] == "Stiffness"
+
+
+# ------------------------------------------------------------------------------------------ an output of the real crate
+def _docs_example(doc):
+    ev = deb.LinearEvent(*doc["event"]["linear"][:2], doc["event"]["linear"][2:])
+    return (deb.EnsembleIVP.ode(deb.LogisticEquation(*doc["params"]), doc["t0"], doc["tf"], [[doc["y0"]]]).even(doc["even_dt"])
+            .event(ev, doc["event"]["direction"], terminate=doc["event"]["terminate"])
+            .method(getattr(E, doc["method"])().rtol(doc["rtol"]).atol(doc["atol"])))
+
+
+def check_docs_example(sol_set, doc):
+    want = doc["expected"]
+    sol = sol_set[0]
+    assert sol.status == want["status"]
+    assert (sol.evals.function, sol.steps.accepted, sol.steps.rejected) == (want["function_evaluations"], want["accepted"], want["rejected"])
+    assert sol.steps.accepted + sol.steps.rejected == want["steps_total"]
+    got = [[round(float(t), 4), round(float(y[0]), 4)] for t, y in zip(sol.t, sol.y)]
+    assert got == want["rows_4_decimals"]
+
+
+def test_oracle_reproduces_the_output_printed_in_the_crates_documentation():
+    """docs/ode.md prints what the crate itself produced for its logistic-growth example: 325 function evaluations, 20 accepted
+    and 2 rejected steps, six rows.  Step counts are integers that depend on every detail of h_init, the DOP853 stages, the
+    error norm, the controller, EvenSolout and the Brent-Dekker event location: the C++ oracle must hit them exactly."""
+    doc = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_docs_output.json")))
+    check_docs_example(ob.oracle_solve(_docs_example(doc)), doc)
