@@ -81,7 +81,7 @@ int select_device(int device) {
 // The library's own stream-ordered memory pool per device: staging buffers of HOST-memspace calls and work buffers are
 // cached across calls (release threshold = never) instead of paying cudaMalloc/cudaFree (tens to hundreds of ms for
 // multi-GB buffers, with a device-wide synchronisation) in every call.  deb_trim_memory() gives the memory back.
-struct DeviceInfo { int sms = 0; cudaMemPool_t pool = nullptr; };
+struct DeviceInfo { int sms = 0; cudaMemPool_t pool = nullptr; size_t total_mem = 0; };
 int device_info(int device, DeviceInfo* di) {
     static std::mutex mu;
     static std::vector<DeviceInfo> cache;
@@ -102,6 +102,8 @@ int device_info(int device, DeviceInfo* di) {
         DEB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
         cache[device].pool = pool;
         cache[device].sms = sms;
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) cache[device].total_mem = prop.totalGlobalMem;
     }
     *di = cache[device];
     return DEB_OK;
@@ -1098,11 +1100,16 @@ int run_shard(const OdeCall& C, const ShardMap& M, int device, ShardOut* out) {
     if (C.per_traj_params) bpt += sizeof(double) * np;
     if (R->y_eval || C.want_stats) bpt += sizeof(double) * ne * (row_major ? 2 : 1);
     if (R->t_out) bpt += sizeof(double) * n_eval;
-    size_t free_b = 0, total_b = 0;
-    DEB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    unsigned long long pooled = 0;
-    cudaMemPoolGetAttribute(di.pool, cudaMemPoolAttrReservedMemCurrent, &pooled);  // cached staging buffers are reusable
-    size_t budget = (size_t)((free_b + pooled) * 0.40);
+    // device-memory budget of the resident buffers: 40 % of what is free (plus what the library's pool already holds).  The query takes
+    // a process-wide driver lock, so a share that is small against the device (every multi-GPU split of C2) does not ask.
+    size_t budget = (size_t)(di.total_mem * 0.40);
+    if ((double)M.local_count() * (double)bpt > (double)di.total_mem * 0.15) {
+        size_t free_b = 0, total_b = 0;
+        DEB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        unsigned long long pooled = 0;
+        cudaMemPoolGetAttribute(di.pool, cudaMemPoolAttrReservedMemCurrent, &pooled);  // cached staging buffers are reusable
+        budget = (size_t)((free_b + pooled) * 0.40);
+    }
     if (const char* e = getenv("DEB_HOST_CHUNK_BYTES")) {
         const long long v = atoll(e);
         if (v > 0) budget = (size_t)v;
@@ -1271,10 +1278,16 @@ int run_shard(const OdeCall& C, const ShardMap& M, int device, ShardOut* out) {
                 next = nb;
                 break;
             }
-            const cudaError_t q = cudaEventQuery(S.r->k1);
-            if (q == cudaSuccess) { kernel_done = true; dbg_t_kernel_done = since(); continue; }
-            if (q != cudaErrorNotReady) DEB_CUDA(q);
-            if (++idle_spins > 64) std::this_thread::sleep_for(std::chrono::microseconds(30));
+            // Nothing new: wait on the flags alone (plain host memory).  The kernel-end query is a driver call behind a process-wide
+            // lock -- with one polling thread per device it would slow the other threads' copies down -- and every kernel publishes its
+            // last block anyway, so it is asked only every few milliseconds, as a safety net.
+            idle_spins += 1;
+            if (idle_spins % 128 == 0) {
+                const cudaError_t q = cudaEventQuery(S.r->k1);
+                if (q == cudaSuccess) { kernel_done = true; dbg_t_kernel_done = since(); continue; }
+                if (q != cudaErrorNotReady) DEB_CUDA(q);
+            }
+            std::this_thread::sleep_for(std::chrono::microseconds(idle_spins < 16 ? 5 : 40));
         }
         DEB_CUDA(cudaEventSynchronize(S.r->k1));
         float ms = 0.f;

@@ -8,8 +8,11 @@
 // Rust toolchain, so the crate itself cannot be run here.  The reference's own tests pin this path only
 // coarsely (tests/ode/accuracy.rs 1e-3..1e3, tests/ode/interpolation.rs 1e-3, tests/ode/from_fn.rs 1e-3,
 // tests/pde/method_of_lines.rs 5e-4 / 1e-12 KATs); tests/test_oracle_golden.py checks this file against
-// every one of those.  Everything beyond that is a line-by-line restatement, with the operation order of
-// the Rust source kept exactly (no FMA contraction: build with -ffp-contract=off; libm pow/sqrt).
+// every one of those.  One output of the real crate exists in the tree -- the run printed in docs/ode.md:108-123
+// (DOP853, even(1.0), terminal event): 325 function evaluations, 20 accepted + 2 rejected steps, six rows -- and this
+// file reproduces it exactly (tests/golden/reference_docs_output.json).  oracle/crate_pin/ + tools/pin_oracle_against_crate.sh
+// produce the bit-level pin on any machine with cargo.  Everything beyond that is a line-by-line restatement, with the
+// operation order of the Rust source kept exactly (no FMA contraction: build with -ffp-contract=off; libm pow/sqrt).
 //
 // Each function cites the reference file:line it follows (paths relative to /root/reference/).
 #include <algorithm>
