@@ -543,9 +543,11 @@ int jit_kernel(const UserSystem* us, int device, int system, int method, bool re
 
 int launch_user(const UserKernel& uk, const deb::OdeKernelArgs& a, int sms, cudaStream_t st) {
     long long blocks;
+    // parked steps live in dynamic shared memory; a launch that emits no rows does not touch it (ode_dispatch.cuh)
+    const unsigned dyn = (a.n_rows > 0 && a.y_eval != nullptr) ? uk.dyn_smem : 0u;
     if (uk.adaptive) {
         int per_sm = 0;
-        DEB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)uk.kernel, uk.block, uk.dyn_smem));
+        DEB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)uk.kernel, uk.block, dyn));
         if (per_sm < 1) per_sm = 1;
         blocks = (long long)sms * per_sm;
     } else {
@@ -556,7 +558,7 @@ int launch_user(const UserKernel& uk, const deb::OdeKernelArgs& a, int sms, cuda
     if (blocks < 1) blocks = 1;
     if (getenv("DEB_DEBUG_LAUNCH")) fprintf(stderr, "[deb] run-time kernel: grid %lld x %d\n", blocks, uk.block);
     void* args[] = {(void*)&a};
-    DEB_CUDA(cudaLaunchKernel((const void*)uk.kernel, dim3((unsigned)blocks), dim3(uk.block), args, uk.dyn_smem, st));
+    DEB_CUDA(cudaLaunchKernel((const void*)uk.kernel, dim3((unsigned)blocks), dim3(uk.block), args, dyn, st));
     deb_count_launch(1);
     return DEB_OK;
 }
@@ -1507,6 +1509,12 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P_user, deb_result* R_user) 
     a.even = even ? 1 : 0;
     a.even_tol = fabs(P->even_dt) * 1e-12 + 2.220446049250313e-16 * 10.0;
     a.rec_mode = P->solout;
+    {   // lanes that gather before a warp refines crossings / events together (erk_ensemble.cuh: rec_park); measured optimum
+        static const int park = [] { const char* e = getenv("DEB_REC_PARK"); return e ? atoi(e) : 16; }();
+        a.rec_park = (park < 0) ? 0 : (park > 32 ? 32 : park);
+        static const int park_rows = [] { const char* e = getenv("DEB_REC_PARK_ROWS"); return e ? atoi(e) : 0; }();
+        a.rec_park_rows = park_rows;
+    }
     a.event_direction = P->event_direction;
     a.event_terminate = P->event_terminate;
     for (int c = 0; c < DEB_MAX_DIM + 2; c++) a.event_coef[c] = P->event_coef[c];

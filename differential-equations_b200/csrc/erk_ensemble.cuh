@@ -89,6 +89,10 @@ struct OdeKernelArgs {
     int rows_vec;  // y_eval row groups (RowStage) start 32-byte aligned: whole-sector 16-byte vector stores are safe
     // step-size filter (erk/mod.rs:225): 0 = identity, else h = from_bits(to_bits(h) & filter_mask) (mantissa truncation)
     unsigned long long filter_mask;
+    // per-step recorders: a lane whose accepted step needs a refinement (crossing / event root search, interpolated rows)
+    // waits until this many lanes of its warp need one, then they all refine in the same iteration (0: refine on the spot)
+    int rec_park;
+    int rec_park_rows;  // EXPERIMENT (DEB_REC_PARK_ROWS): interpolated t_eval / even rows of a recorder kernel gather too
 };
 
 // see OdeKernelArgs::wm_done.  Called by the lane that has just written every output of trajectory `traj`.
@@ -582,6 +586,8 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const __
     double (*dstash)[32] = reinterpret_cast<double (*)[32]>(s_dyn) + (DEFER2 ? (threadIdx.x >> 5) * NPARK2 : 0);
     const bool want_rows = (a.y_eval != nullptr);
     bool pending = false;  // this lane has a parked step
+    // per-step recorders: lanes whose step needs a refinement gather (OdeKernelArgs::rec_park); warp-uniform
+    bool rec_go = !REC || a.rec_park <= 0;
     int pend_idx = 0;      // first row of the parked step
 
     // per-lane trajectory state (registers); starts as the idle dummy
@@ -933,7 +939,12 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const __
             // step contains a t_eval point while its row slot is still occupied does not commit this attempt: it is redone, bit
             // for bit, after the service section.  The counters below must not advance for the attempt that is thrown away
             // (the reference advances them once per 100th step).
-            if (Tab::DP && accept && m100 == 99 && !((DEFER || DEFER2) && pending && ((te - t_new) * dir <= 0.0))) {
+            // Per-step recorders: an accepted step that needs a root search or interpolated rows is thrown away in the same manner
+            // until enough lanes of the warp wait for one (rec_go); the waiting lanes repeat the attempt, bit for bit, beside the
+            // lanes that keep stepping, and then refine together instead of one or two lanes at a time.
+            bool rec_blocked = false;
+            if constexpr (REC) rec_blocked = !rec_go && accept && fin < 0 && recd.slow_work(a, t_new, ynew, p);
+            if (Tab::DP && accept && m100 == 99 && !rec_blocked && !((DEFER || DEFER2) && pending && ((te - t_new) * dir <= 0.0))) {
                 // ysti = the argument of the last stage; rebuilt here (same operations, same bits) instead of being
                 // kept alive in registers through 99 steps out of 100
                 double ysti[N];
@@ -971,7 +982,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const __
 
             // ---- TEvalSolout (t_eval.rs:100-130): does a t_eval point lie in this step?  (te - t_new == 0 iff te == t_new)
             const bool hit = accept && fin < 0 && ((te - t_new) * dir <= 0.0);
-            bool blocked = false;
+            bool blocked = rec_blocked;
             if (DEFER || DEFER2) {
                 blocked = hit && pending;  // slot occupied: do not commit, get the slot flushed, redo this attempt
                 if (hit && !blocked) {
@@ -1024,7 +1035,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const __
 
             bool interrupt = false;  // ControlFlag::Terminate from an event: the step is kept, then Status::Interrupted
             if constexpr (REC) {  // solout after an accepted step (solve_ivp.rs:239-246)
-                if (accept && fin < 0) interrupt = recd.step(a, traj, t, h, y, ynew, k, dydt, p);
+                if (accept && fin < 0 && !blocked) interrupt = recd.step(a, traj, t, h, y, ynew, k, dydt, p);
                 __syncwarp();
             }
 
@@ -1061,7 +1072,15 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const __
                 if (commit && fabs(tf - t) <= eps10) fin = DEB_STATUS_COMPLETE;
                 if (REC && interrupt) fin = DEB_STATUS_INTERRUPTED;  // solve_ivp.rs:255-260, before the end-of-interval test
             }
-            service = (active && fin >= 0) || blocked;
+            if constexpr (REC) {
+                // refine in the next iteration when enough lanes wait, or when no lane of the warp can advance without it
+                const unsigned waiting = __ballot_sync(FULL, blocked);
+                const unsigned advancing = __ballot_sync(FULL, stepping && fin < 0 && !blocked);
+                rec_go = a.rec_park <= 0 || __popc(waiting) >= a.rec_park || (waiting != 0u && advancing == 0u);
+                service = active && fin >= 0;
+            } else {
+                service = (active && fin >= 0) || blocked;
+            }
         } while (!__any_sync(FULL, service));
     }
 }

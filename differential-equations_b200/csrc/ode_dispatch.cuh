@@ -44,7 +44,9 @@ template <class Sys, class Tab, int BLOCK, int MIN_BLOCKS, bool SHARED_P>
 int launch_dp_impl(const deb::OdeKernelArgs& a, int sms, cudaStream_t st) {
     auto kern = deb::dp_ensemble_kernel<Sys, Tab, BLOCK, MIN_BLOCKS, SHARED_P>;
     // methods with extra dense stages park whole steps in dynamic shared memory (erk_ensemble.cuh: flush_dense_parked)
-    constexpr unsigned dyn = deb::dp_dynamic_smem_bytes<Sys, Tab, BLOCK, false>();
+    // (only launches that can emit rows touch it: a final-state-only launch keeps the shared memory for the L1 cache)
+    constexpr unsigned dyn_max = deb::dp_dynamic_smem_bytes<Sys, Tab, BLOCK, false>();
+    const unsigned dyn = (a.n_rows > 0 && a.y_eval != nullptr) ? dyn_max : 0u;
     if (dyn > 0) DEB_DISPATCH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     int per_sm = 0;
     DEB_DISPATCH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, dyn));

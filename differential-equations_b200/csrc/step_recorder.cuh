@@ -342,6 +342,25 @@ struct StepRecorder {
         return false;
     }
 
+    // Does the solout call for the accepted step ending at (t_new, yn) need a refinement -- a crossing / event root search on
+    // the dense output, or interpolated rows?  (Same tests as in step(); a superset is harmless: the caller only uses the
+    // answer to let such lanes of a warp refine together.)  The dense(n) recorder interpolates in every step of every lane.
+    __device__ __forceinline__ bool slow_work(const OdeKernelArgs& a, double t_new, const double (&yn)[N], const double* p) const {
+        bool slow = false;
+        if (a.rec_mode == REC_CROSSING) {
+            const double off = component(yn, a.cross_component) - a.cross_threshold;
+            slow = have_last && d_signum(last_off) != d_signum(off);
+        } else if (a.rec_mode == REC_HYPERPLANE) {
+            const double dist = plane_distance(a, yn);
+            slow = have_last && (d_signum(last_off) != d_signum(dist) || (last_off == 0.0) != (dist == 0.0));
+        } else if ((a.rec_mode == REC_T_EVAL || a.rec_mode == REC_EVEN) && a.rec_park_rows) {
+            const double dir = d_signum(a.tf - a.t0);
+            slow = idx < a.n_rows && (a.t_rows[idx] - t_new) * dir <= 0.0;
+        }
+        if (Evt::ENABLED) slow = slow || d_signum(last_g) != d_signum(Evt::g(a, t_new, yn, p));
+        return slow;
+    }
+
     // solout after an accepted step from (t, y) to (t + h, yn); k[0] = f(t, y), dydt = f(t + h, yn).  Returns true when
     // an event asks to terminate (ControlFlag::Terminate).
     __device__ __forceinline__ bool step(const OdeKernelArgs& a, long long traj, double t, double h, const double (&y)[N],

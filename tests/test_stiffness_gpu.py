@@ -63,3 +63,30 @@ def test_dp_stiffness_mixed_ensemble_dense_t_eval():
     assert_same_solution(gpu, cpu)
     assert (gpu.status[::3] == deb.DEB_STATUS_STIFFNESS).all()
     assert (gpu.status[1::3] == deb.DEB_STATUS_COMPLETE).all()
+
+
+@pytest.mark.parametrize("method", ["dopri5", "dop853"])
+@pytest.mark.parametrize("wrap", ["crossing", "event_on_every_step", "event_on_t_eval"])
+def test_dp_stiffness_detector_with_gathered_refinements(method, wrap):
+    """Recorder kernels let the lanes whose step holds a crossing / event candidate wait for each other (erk_ensemble.cuh:
+    rec_go); the waiting lane repeats its attempt, and the detector must not count the repeats.  y' = k y, y0 = exp(-tc):
+    the crossing of y = 1 falls on step tc / 0.002, which covers every residue mod 100 over the ensemble -- the 100th steps
+    included -- and every trajectory still ends with Stiffness after 1499 accepted steps."""
+    n = 400
+    tc = 0.2 + 0.002 * np.arange(n) + 0.0007
+    y0 = np.exp(-tc).reshape(-1, 1)
+    def prob():
+        p = deb.EnsembleIVP.ode(deb.ExponentialGrowth(1.0000001), 0.0, 10.0, y0)
+        if wrap == "crossing":
+            p = p.crossing(0, 1.0, deb.CROSSING_BOTH, 8)
+        elif wrap == "event_on_every_step":
+            p = p.every_step(max_rows=1600).event(deb.LinearEvent(-1.0, 0.0, [1.0]), max_event_rows=1600)
+        else:
+            p = p.t_eval(np.linspace(0.0, 10.0, 700)).event(deb.LinearEvent(-1.0, 0.0, [1.0]), max_event_rows=720)
+        return p.method(getattr(E, method)().h_max(0.002).max_steps(100000))
+    gpu, cpu = prob().solve(), ob.oracle_solve(prob())
+    assert_same_solution(gpu, cpu)
+    assert (gpu.status == deb.DEB_STATUS_STIFFNESS).all() and (gpu.accepted == 1499).all()
+    if wrap == "crossing":
+        assert (gpu.n_emitted == 1).all()
+        assert np.abs(gpu.t_out[:, 0] - tc).max() < 1e-6

@@ -97,6 +97,28 @@ def main():
         else:
             per = [mine]
         res["d2h_78MB_pieces_%d_streams" % n_streams] = {"per_rank_gbs": per, "aggregate_gbs_by_wall": world * n * 8 / wall / 1e9}
+    # who shares what: only a SUBSET of the ranks copies (78 MB pieces, one stream), the others wait at the barrier
+    if dist is not None and world >= 2:
+        half = world // 2
+        subsets = [[0], [world - 1], list(range(half)), list(range(half, world)), [0, world - 1], list(range(world))]
+        piece = 78_643_200 // 8
+        pieces = [(o, min(o + piece, n)) for o in range(0, n, piece)]
+        res["d2h_subsets_78MB_pieces"] = []
+        for sub in subsets:
+            dist.barrier()
+            torch.cuda.synchronize()
+            mine = 0.0
+            if rank in sub:
+                t = time.perf_counter()
+                for a, b in pieces:
+                    h[a:b].copy_(d[a:b], non_blocking=True)
+                torch.cuda.synchronize()
+                mine = n * 8 / (time.perf_counter() - t) / 1e9
+            dist.barrier()
+            vals = torch.tensor([mine], device=dev, dtype=torch.float64)
+            allv = [torch.zeros_like(vals) for _ in range(world)]
+            dist.all_gather(allv, vals)
+            res["d2h_subsets_78MB_pieces"].append({"ranks_copying": sub, "per_rank_gbs": [round(float(x.item()), 2) for x in allv]})
     if rank == 0:
         print(json.dumps({"world": world, "bytes_per_rank": n * 8, "results": res, "topology": topo()}), flush=True)
     if dist is not None:
