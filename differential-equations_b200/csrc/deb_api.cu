@@ -1047,6 +1047,7 @@ struct OdeCall {
     deb::OdeKernelArgs a;   // everything that does not depend on the device / chunk
     std::vector<int> devices;
     bool want_stats = false;
+    std::chrono::steady_clock::time_point wall0;  // start of the deb_solve_ode call (DEB_DEBUG_TIMING)
 };
 typedef std::function<int(const deb::OdeKernelArgs&, int, cudaStream_t)> LaunchFn;
 
@@ -1085,6 +1086,9 @@ int run_shard(const OdeCall& C, const ShardMap& M, int device, ShardOut* out) {
     const auto t_start = std::chrono::steady_clock::now();
     auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
     out->device = device;
+    if (getenv("DEB_DEBUG_TIMING"))
+        fprintf(stderr, "[deb timing] device %d: shard starts %.2f ms into the call\n", device,
+                std::chrono::duration<double, std::milli>(t_start - C.wall0).count());
     if (int rc = select_device(device)) return rc;
     DeviceInfo di;
     if (int rc = device_info(device, &di)) return rc;
@@ -1581,6 +1585,7 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P_user, deb_result* R_user) 
 
     // ---- HOST memspace: one persistent launch per device (and chunk) with watermark-streamed result copies (run_shard)
     const auto wall0 = std::chrono::steady_clock::now();
+    C.wall0 = wall0;
     const int G = (int)C.devices.size();
     int shift = 12;
     if (const char* e = getenv("DEB_WM_SHIFT")) {  // test knob: log2 of the watermark / distribution block

@@ -97,6 +97,46 @@ def main():
         else:
             per = [mine]
         res["d2h_78MB_pieces_%d_streams" % n_streams] = {"per_rank_gbs": per, "aggregate_gbs_by_wall": world * n * 8 / wall / 1e9}
+    # Does the page size of the pinned buffer matter (IOMMU translations of a virtualised box)?  The same piecewise copy into an
+    # anonymous mapping with transparent huge pages requested, registered with cudaHostRegister.
+    try:
+        import mmap
+        size = n * 8
+        mm = mmap.mmap(-1, size + (2 << 20), flags=mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS)
+        mm.madvise(mmap.MADV_HUGEPAGE)
+        base = ctypes.addressof(ctypes.c_char.from_buffer(mm))
+        off = (-base) % (2 << 20)
+        hh = torch.frombuffer(mm, dtype=torch.float64, count=n, offset=off)
+        hh.zero_()
+        rc = torch.cuda.cudart().cudaHostRegister(base + off, size, 0)
+        thp = {"registered_rc": int(rc), "is_pinned": bool(hh.is_pinned())}
+        try:
+            thp["AnonHugePages_kB_of_process"] = int([l for l in open("/proc/self/smaps_rollup") if l.startswith("AnonHugePages")][0].split()[1])
+            thp["thp_enabled"] = open("/sys/kernel/mm/transparent_hugepage/enabled").read().strip()
+        except Exception as e:  # noqa: BLE001
+            thp["thp_query"] = repr(e)
+        piece = 78_643_200 // 8
+        pieces = [(o, min(o + piece, n)) for o in range(0, n, piece)]
+        for label, buf in (("torch_pinned", h), ("thp_registered", hh)):
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            for a, b in pieces:
+                buf[a:b].copy_(d[a:b], non_blocking=True)
+            torch.cuda.synchronize()
+            mine = n * 8 / (time.perf_counter() - t) / 1e9
+            vals = torch.tensor([mine], device=dev, dtype=torch.float64)
+            if dist is not None:
+                dist.barrier()
+                allv = [torch.zeros_like(vals) for _ in range(world)]
+                dist.all_gather(allv, vals)
+                thp[label + "_per_rank_gbs"] = [round(float(x.item()), 2) for x in allv]
+            else:
+                thp[label + "_per_rank_gbs"] = [round(mine, 2)]
+        res["d2h_page_size"] = thp
+    except Exception as e:  # noqa: BLE001
+        res["d2h_page_size"] = {"failed": repr(e)}
     # who shares what: only a SUBSET of the ranks copies (78 MB pieces, one stream), the others wait at the barrier
     if dist is not None and world >= 2:
         half = world // 2
