@@ -463,8 +463,9 @@ unsigned jit_dynamic_smem(int method, int dim, bool rec) {
 
 // Compile the ensemble kernel for (system, method, recorder kind) to a cubin (no device needed).  `us` = the user
 // system, or null for a built-in one.
-int compile_kernel_cubin(const UserSystem* us, int system, int method, bool rec, int event, bool filter, std::vector<char>* cubin,
+int compile_kernel_cubin(const UserSystem* us, int system, int method, int rec_mode, int event, bool filter, std::vector<char>* cubin,
                          std::string* kernel_name, bool* is_adaptive) {
+    const bool rec = rec_mode >= 0;  // -1: the row-plan kernels (t_eval / even(dt) without event)
     int sdim = 0, snp = 0;
     const char* sys_name = us ? "deb::UserSys" : builtin_system_name(system, &sdim, &snp);
     if (!sys_name) return fail(DEB_ERR_BAD_ARG, "unknown system id");
@@ -478,7 +479,8 @@ int compile_kernel_cubin(const UserSystem* us, int system, int method, bool rec,
         if (method == DEB_DOP853) min_blocks = sdim <= 2 ? 4 : sdim == 3 ? 3 : sdim <= 6 ? 2 : 1;
         else if (method >= DEB_RKV655E && method <= DEB_RKV989E) min_blocks = sdim <= 2 ? 4 : sdim == 3 ? 3 : sdim <= 5 ? 2 : 1;
         else min_blocks = sdim <= 3 ? 5 : sdim <= 6 ? 3 : sdim <= 10 ? 2 : 1;
-        if (rec && min_blocks > 1) min_blocks -= 1;  // the recorder keeps the dense output of a step live
+        // a recorder that interpolates keeps the dense output of a step live
+        if (rec && min_blocks > 1 && !(rec_mode == DEB_SOLOUT_DEFAULT && event == DEB_EVENT_NONE)) min_blocks -= 1;
     }
     // event functor
     const UserEvent* ue = nullptr;
@@ -499,6 +501,7 @@ int compile_kernel_cubin(const UserSystem* us, int system, int method, bool rec,
     if (adaptive) snprintf(expr, sizeof expr, "deb::dp_ensemble_kernel<%s, %s, 128, %d, false, %s, %s, %s>", sys_name, tab, min_blocks, rec ? "true" : "false", evt.c_str(), filter ? "true" : "false");
     else snprintf(expr, sizeof expr, "deb::fixed_ensemble_kernel<%s, %s, 128, %s, %s>", sys_name, tab, rec ? "true" : "false", evt.c_str());
     std::string src;
+    if (rec) src += "#define DEB_JIT_REC_MODE " + std::to_string(rec_mode) + "\n";  // step_recorder.cuh: one kernel per recorder
     src += "#include \"erk_fixed.cuh\"\n#include \"systems.cuh\"\n";
     if (us) {
         src += "namespace deb {\nstruct UserSys {\n";
@@ -520,14 +523,15 @@ int compile_kernel_cubin(const UserSystem* us, int system, int method, bool rec,
 }
 
 // Compile and load (once per device / system / method / recorder kind) a run-time kernel.  Caller holds g_user_mu.
-int jit_kernel(const UserSystem* us, int device, int system, int method, bool rec, int event, bool filter, UserKernel** out) {
-    const auto key = std::make_tuple(device, system, method, rec ? 1 : 0, event, filter ? 1 : 0);
+int jit_kernel(const UserSystem* us, int device, int system, int method, int rec_mode, int event, bool filter, UserKernel** out) {
+    const bool rec = rec_mode >= 0;
+    const auto key = std::make_tuple(device, system, method, rec_mode, event, filter ? 1 : 0);
     auto it = g_jit_kernels.find(key);
     if (it != g_jit_kernels.end()) { *out = &it->second; return DEB_OK; }
     std::vector<char> cubin;
     std::string lowered;
     UserKernel uk;
-    if (int rc = compile_kernel_cubin(us, system, method, rec, event, filter, &cubin, &lowered, &uk.adaptive)) return rc;
+    if (int rc = compile_kernel_cubin(us, system, method, rec_mode, event, filter, &cubin, &lowered, &uk.adaptive)) return rc;
     DEB_CUDA(cudaLibraryLoadData(&uk.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
     DEB_CUDA(cudaLibraryGetKernel(&uk.kernel, uk.lib, lowered.c_str()));
     if (uk.adaptive) {
@@ -1059,7 +1063,7 @@ int bind_launcher(const OdeCall& C, int device, LaunchFn* launch) {
     }
     std::lock_guard<std::mutex> lk(g_user_mu);
     UserKernel* uk = nullptr;
-    if (int rc = jit_kernel(C.user, device, C.P.system, C.P.method, C.rec, C.P.event, C.a.filter_mask != 0ull, &uk)) return rc;
+    if (int rc = jit_kernel(C.user, device, C.P.system, C.P.method, C.rec ? C.P.solout : -1, C.P.event, C.a.filter_mask != 0ull, &uk)) return rc;
     const UserKernel ukc = *uk;
     *launch = [ukc](const deb::OdeKernelArgs& ka, int sms, cudaStream_t s2) { return launch_user(ukc, ka, sms, s2); };
     return DEB_OK;
@@ -1245,6 +1249,7 @@ int run_shard(const OdeCall& C, const ShardMap& M, int device, ShardOut* out) {
         ac.wm_ready = S.r->flags;
         ac.wm_shift = M.shift;
         ac.rows_vec = (ac.y_eval && ((size_t)C.row_cap * dim) % 4 == 0 && ((uintptr_t)ac.y_eval % 32) == 0) ? 1 : 0;
+        ac.tout_vec = (ac.t_out && C.row_cap % 4 == 0 && ((uintptr_t)ac.t_out % 32) == 0) ? 1 : 0;
         DEB_CUDA(cudaEventRecord(S.r->k0, st));
         if (int rc = launch(ac, di.sms, st)) return rc;
         DEB_CUDA(cudaEventRecord(S.r->k1, st));
@@ -1576,6 +1581,7 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P_user, deb_result* R_user) 
         a.status = R->status; a.accepted = R->accepted; a.rejected = R->rejected; a.evals = R->evals;
         a.t_out = R->t_out;
         a.rows_vec = (a.y_eval && (ne % 4) == 0 && ((uintptr_t)a.y_eval % 32) == 0) ? 1 : 0;
+        a.tout_vec = (a.t_out && row_cap % 4 == 0 && ((uintptr_t)a.t_out % 32) == 0) ? 1 : 0;
         if (int rc = launch(a, di.sms, st)) return rc;
         if (row_major)
             if (int rc = launch_transpose(tmp_rows.as<double>(), n, (int)ne, R->y_eval, n, 0, st)) return rc;
@@ -1772,7 +1778,7 @@ extern "C" int deb_check_ode(int32_t system_id, int32_t method, int32_t solout, 
     std::vector<char> cubin;
     std::string name;
     bool adaptive = false;
-    return compile_kernel_cubin(us, system_id, method, rec, event, false, &cubin, &name, &adaptive);
+    return compile_kernel_cubin(us, system_id, method, rec ? solout : -1, event, false, &cubin, &name, &adaptive);
 }
 
 extern "C" int deb_solve_sde(const deb_sde_problem* P_user, deb_result* R_user) {

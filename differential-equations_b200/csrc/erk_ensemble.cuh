@@ -91,6 +91,7 @@ struct OdeKernelArgs {
     unsigned long long filter_mask;
     // per-step recorders: a lane whose accepted step needs a refinement (crossing / event root search, interpolated rows)
     // waits until this many lanes of its warp need one, then they all refine in the same iteration (0: refine on the spot)
+    int tout_vec;  // per-step recorders: groups of four t_out entries start 32-byte aligned
     int rec_park;
     int rec_park_rows;  // EXPERIMENT (DEB_REC_PARK_ROWS): interpolated t_eval / even rows of a recorder kernel gather too
 };
@@ -127,6 +128,8 @@ __device__ __forceinline__ double apply_filter(const OdeKernelArgs& a, double h)
 // NOT inlined: the kernels that call it keep ~90 registers of trajectory state live across the call site, and inlining the
 // group copy there made ptxas spill loop-carried state of the hot loop (measured: 8 local-memory instructions per step
 // attempt); as a call, only the call site pays.
+// (A 256-bit `st.global.v4.f64` per sector was tried in round 2: ptxas 12.9 turned it into a 64-bit store in some of the per-kernel
+// clones of this function -- tools/microbench/st256_check.cu shows the instruction itself works -- so the stores stay 128-bit.)
 template <int CNT>
 __device__ __noinline__ void store_row_group(double* dst, const double* src, int stride, int vec) {
     if (vec) {
@@ -572,11 +575,13 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const __
     // dense output needs no extra stages: emission can be parked -- as long as the stash fits the static shared-memory
     // budget next to the pow tables (wide systems interpolate on the spot)
     constexpr bool DEFER = (I == S) && !REC && (NSTASH * BLOCK * 8 <= 40 * 1024);
-    StepRecorder<Sys, Tab, Evt> recd;
+    using Recorder = StepRecorder<Sys, Tab, Evt, BLOCK>;
+    Recorder recd;
     using Rows = RowStage<N, BLOCK, !REC>;  // (per-step recorders write their rows themselves, step_recorder.cuh)
     // per warp: [parked step (DEFER)] [row group being collected]; one array so that both are addressed from one base register
     constexpr int NPARK = DEFER ? NSTASH : 0;
-    __shared__ double s_lane[BLOCK / 32][NPARK + Rows::SLOTS][32];
+    constexpr int ROW_SLOTS = REC ? Recorder::STAGE_SLOTS : Rows::SLOTS;  // recorder kernels stage (y, t) rows, see StepRecorder::push
+    __shared__ double s_lane[BLOCK / 32][NPARK + ROW_SLOTS][32];
     double (*stash)[32] = s_lane[threadIdx.x >> 5];
     double (*s_rows)[32] = stash + NPARK;
     // methods with extra dense stages park the whole step in dynamic shared memory (flush_dense_parked)
@@ -700,6 +705,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const __
             // stages); dense-polynomial pairs I-S dense stages (+1 unless FSAL), adaptive/ordinary.rs:145-174
             constexpr int PER_ACC = Tab::BI_POLY ? ((I - S) + (Tab::FSAL ? 0 : 1)) : (1 + ((I > S) ? (I - S - 1) : 0));
             if (a.evals) a.evals[traj] = evals_base + (S - 1) * (acc + rej) + acc * PER_ACC;
+            if constexpr (REC) recd.finish(a, s_rows, lane, traj);
             if (a.n_emitted) a.n_emitted[traj] = REC ? recd.rows : idx;
             wm_publish(a, traj);
             active = false;
@@ -765,7 +771,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const __
                         te = (!REC && idx < a.n_rows) ? a.t_rows[idx] : te_none;
                         if constexpr (REC) {  // the solout call that precedes the loop
                             recd.reset();
-                            recd.first(a, traj, t0, y, p);
+                            recd.first(a, s_rows, lane, traj, t0, y, p);
                         }
                         active = true;
                     }
@@ -1035,7 +1041,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const __
 
             bool interrupt = false;  // ControlFlag::Terminate from an event: the step is kept, then Status::Interrupted
             if constexpr (REC) {  // solout after an accepted step (solve_ivp.rs:239-246)
-                if (accept && fin < 0 && !blocked) interrupt = recd.step(a, traj, t, h, y, ynew, k, dydt, p);
+                if (accept && fin < 0 && !blocked) interrupt = recd.step(a, s_rows, lane, traj, t, h, y, ynew, k, dydt, p);
                 __syncwarp();
             }
 

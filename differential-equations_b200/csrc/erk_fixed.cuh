@@ -22,7 +22,8 @@ __global__ void __launch_bounds__(BLOCK) fixed_ensemble_kernel(const OdeKernelAr
     const double te_none = (dir > 0.0) ? (1.0 / 0.0) : -(1.0 / 0.0);
     const long long stride = (long long)gridDim.x * BLOCK;
     using Rows = RowStage<N, BLOCK, !REC>;  // whole-sector row groups, see erk_ensemble.cuh
-    __shared__ double s_lane[BLOCK / 32][Rows::SLOTS][32];
+    using Recorder = StepRecorder<Sys, Tab, Evt, BLOCK>;
+    __shared__ double s_lane[BLOCK / 32][REC ? Recorder::STAGE_SLOTS : Rows::SLOTS][32];
     double (*s_rows)[32] = s_lane[threadIdx.x >> 5];
     const unsigned lane = threadIdx.x & 31u;
 
@@ -34,7 +35,7 @@ __global__ void __launch_bounds__(BLOCK) fixed_ensemble_kernel(const OdeKernelAr
         for (int q = 0; q < NP; q++) p[q] = a.params ? a.params[traj * a.params_stride + q] : a.pc[q];
         int steps = 0, evals = 0, n_emit = 0, idx = 0;
         int fin = -1;
-        StepRecorder<Sys, Tab, Evt> recd;
+        Recorder recd;
         double t = t0;
         // ---- init, fixed/ordinary.rs:16-56 (BadInput was decided on the host: utils.rs:60-157 does not look at the state)
         const double h_full = (a.h0 == 0.0) ? fabs(tf - t0) / 100.0 : a.h0;
@@ -49,7 +50,7 @@ __global__ void __launch_bounds__(BLOCK) fixed_ensemble_kernel(const OdeKernelAr
                 n_emit = 1;
                 idx = 1;
             }
-            if constexpr (REC) recd.first(a, traj, t0, y, p);  // the solout call that precedes the loop
+            if constexpr (REC) recd.first(a, s_rows, lane, traj, t0, y, p);  // the solout call that precedes the loop
         }
         double te = (idx < a.n_rows) ? a.t_rows[idx] : te_none;
         // the loop head (clip at tf, solve_ivp.rs:193-209), the max_steps test and the end test (:263) ran on the host
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(BLOCK) fixed_ensemble_kernel(const OdeKernelAr
             Sys::rhs(t_new, ynew, dnew, p);
             evals += S;  // S-1 stages + the new derivative (fsal = false)
             bool interrupt = false;
-            if constexpr (REC) interrupt = recd.step(a, traj, t, h, y, ynew, k, dnew, p);
+            if constexpr (REC) interrupt = recd.step(a, s_rows, lane, traj, t, h, y, ynew, k, dnew, p);
             // ---- TEvalSolout with cubic Hermite interpolation
             while (!REC && ((dir > 0.0) ? (te <= t_new) : (te >= t_new))) {
                 if (a.even && idx == a.n_rows - 1) {  // the tf sentinel: EvenSolout final-point rule, even.rs:166-188
@@ -148,6 +149,7 @@ __global__ void __launch_bounds__(BLOCK) fixed_ensemble_kernel(const OdeKernelAr
         if (a.accepted) a.accepted[traj] = steps;
         if (a.rejected) a.rejected[traj] = 0;
         if (a.evals) a.evals[traj] = evals;
+        if constexpr (REC) recd.finish(a, s_rows, lane, traj);
         if (a.n_emitted) a.n_emitted[traj] = REC ? recd.rows : n_emit;
         wm_publish(a, traj);
     }

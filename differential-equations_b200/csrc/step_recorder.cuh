@@ -22,6 +22,18 @@ namespace deb {
 
 enum { REC_T_EVAL = 0, REC_EVEN = 1, REC_DEFAULT = 2, REC_DENSE = 3, REC_CROSSING = 4, REC_HYPERPLANE = 5 };  // = deb_solout values
 
+// The recorder kernels are compiled at first use, one per recorder: the translation unit fixes the mode (DEB_JIT_REC_MODE), so
+// the code of the other recorders -- dense-output preparation, Newton, the row plan -- is not part of the kernel at all.
+#ifdef DEB_JIT_REC_MODE
+__device__ __forceinline__ constexpr int rec_mode_of(const OdeKernelArgs&) { return DEB_JIT_REC_MODE; }
+// rows are staged in shared memory (StepRecorder::push) by the recorders that emit in every step; for the others -- a row
+// every few dozen steps -- the staging code only costs registers (measured: t_eval + event 19.5 -> 22.6 ms with it)
+constexpr bool REC_ROWS_STAGED = (DEB_JIT_REC_MODE == 2 /* REC_DEFAULT */ || DEB_JIT_REC_MODE == 3 /* REC_DENSE */);
+#else
+__device__ __forceinline__ int rec_mode_of(const OdeKernelArgs& a) { return a.rec_mode; }
+constexpr bool REC_ROWS_STAGED = true;
+#endif
+
 // Event functions g(t, y) (the `Event` trait, src/solout/event.rs:60-70).  EvtNone: no event detection.
 struct EvtNone {
     static constexpr bool ENABLED = false;
@@ -177,9 +189,15 @@ struct DenseStep {
 // Base recorder + optional event detection (EventWrappedSolout, src/solout/event.rs:300-470): the base recorder pushes its
 // rows first, then a sign change of g over the step is located with Brent-Dekker on the dense output and pushed; after
 // `event_terminate` events the integration stops with Status::Interrupted.
-template <class Sys, class Tab, class Evt = EvtNone>
+template <class Sys, class Tab, class Evt = EvtNone, int BLOCK = 128>
 struct StepRecorder {
     static constexpr int N = Sys::DIM, S = Tab::S;
+    // Rows are staged per lane in warp-private shared memory (RowStage, erk_ensemble.cuh) and leave as whole 32-byte
+    // sectors: four (t) and 4/gcd(N,4) (y) rows per group.  A lane appends one row at a time to its own trajectory, so
+    // without staging every 8-byte store of a warp is a separate partial-sector write at L2.
+    using RowsY = RowStage<N, BLOCK, REC_ROWS_STAGED>;
+    using RowsT = RowStage<1, BLOCK, REC_ROWS_STAGED>;
+    static constexpr int STAGE_SLOTS = RowsY::SLOTS + RowsT::SLOTS;
     int rows = 0;             // pushes so far (Solution.t.len())
     double last_t = 0.0;      // time of the last pushed row (solution.t.last())
     bool have_last = false;   // CrossingSolout::last_offset_value
@@ -190,17 +208,25 @@ struct StepRecorder {
 
     __device__ __forceinline__ void reset() { rows = 0; have_last = false; last_off = 0.0; idx = 0; last_g = 0.0; event_count = 0; last_t = 0.0; }
 
-    __device__ __forceinline__ void push(const OdeKernelArgs& a, long long traj, double t, const double (&y)[N]) {
+    // `rows` is both the row being written and the number of rows before it, also when EvenSolout has just popped its
+    // last point (rows -= 1; push): the staged group still holds the rows around the popped one and is written again.
+    __device__ __forceinline__ void push(const OdeKernelArgs& a, double (*buf)[32], unsigned lane, long long traj, double t, const double (&y)[N]) {
         if (rows < a.row_stride) {
-            const size_t r = (size_t)traj * a.row_stride + rows;
-            if (a.y_eval) {
-#pragma unroll
-                for (int c = 0; c < N; c++) a.y_eval[r * N + c] = y[c];
+            if (a.y_eval) RowsY::put(RowSink{a.y_eval, a.row_stride, a.rows_vec}, buf, lane, traj, rows, rows, y);
+            if (a.t_out) {
+                const double tr[1] = {t};
+                RowsT::put(RowSink{a.t_out, a.row_stride, a.tout_vec}, buf + RowsY::SLOTS, lane, traj, rows, rows, tr);
             }
-            if (a.t_out) a.t_out[r] = t;
         }
         rows += 1;
         last_t = t;
+    }
+
+    // the trajectory has ended: the rows of the incomplete last groups
+    __device__ __forceinline__ void finish(const OdeKernelArgs& a, double (*buf)[32], unsigned lane, long long traj) const {
+        const int stored = (rows < a.row_stride) ? rows : a.row_stride;
+        if (a.y_eval) RowsY::finish(RowSink{a.y_eval, a.row_stride, a.rows_vec}, buf, lane, traj, stored);
+        if (a.t_out) RowsT::finish(RowSink{a.t_out, a.row_stride, a.tout_vec}, buf + RowsY::SLOTS, lane, traj, stored);
     }
 
     __device__ __forceinline__ static double component(const double (&y)[N], int idx_) {
@@ -246,17 +272,18 @@ struct StepRecorder {
     }
 
     // the solout call that precedes the loop (solve_ivp.rs:160): t_prev == t_curr == t0
-    __device__ __forceinline__ void first(const OdeKernelArgs& a, long long traj, double t0, const double (&y0)[N], const double* p) {
-        if (a.rec_mode == REC_CROSSING) {
+    __device__ __forceinline__ void first(const OdeKernelArgs& a, double (*buf)[32], unsigned lane, long long traj, double t0, const double (&y0)[N],
+                                          const double* p) {
+        if (rec_mode_of(a) == REC_CROSSING) {
             last_off = component(y0, a.cross_component) - a.cross_threshold;
             have_last = true;
-        } else if (a.rec_mode == REC_HYPERPLANE) {
+        } else if (rec_mode_of(a) == REC_HYPERPLANE) {
             last_off = plane_distance(a, y0);
             have_last = true;
-        } else if (a.rec_mode == REC_T_EVAL || a.rec_mode == REC_EVEN) {
-            if (a.emit_t0) { push(a, traj, t0, y0); idx = 1; }  // the row plan starts with t0 (t_eval.rs:113-114 / even.rs:100-104)
+        } else if (rec_mode_of(a) == REC_T_EVAL || rec_mode_of(a) == REC_EVEN) {
+            if (a.emit_t0) { push(a, buf, lane, traj, t0, y0); idx = 1; }  // the row plan starts with t0 (t_eval.rs:113-114 / even.rs:100-104)
         } else {
-            push(a, traj, t0, y0);  // Default: always; Dense: t_prev == t_curr, only the point itself
+            push(a, buf, lane, traj, t0, y0);  // Default: always; Dense: t_prev == t_curr, only the point itself
         }
         if (Evt::ENABLED) last_g = Evt::g(a, t0, y0, p);  // event.rs:373-380: first call only stores g
     }
@@ -347,13 +374,13 @@ struct StepRecorder {
     // answer to let such lanes of a warp refine together.)  The dense(n) recorder interpolates in every step of every lane.
     __device__ __forceinline__ bool slow_work(const OdeKernelArgs& a, double t_new, const double (&yn)[N], const double* p) const {
         bool slow = false;
-        if (a.rec_mode == REC_CROSSING) {
+        if (rec_mode_of(a) == REC_CROSSING) {
             const double off = component(yn, a.cross_component) - a.cross_threshold;
             slow = have_last && d_signum(last_off) != d_signum(off);
-        } else if (a.rec_mode == REC_HYPERPLANE) {
+        } else if (rec_mode_of(a) == REC_HYPERPLANE) {
             const double dist = plane_distance(a, yn);
             slow = have_last && (d_signum(last_off) != d_signum(dist) || (last_off == 0.0) != (dist == 0.0));
-        } else if ((a.rec_mode == REC_T_EVAL || a.rec_mode == REC_EVEN) && a.rec_park_rows) {
+        } else if ((rec_mode_of(a) == REC_T_EVAL || rec_mode_of(a) == REC_EVEN) && a.rec_park_rows) {
             const double dir = d_signum(a.tf - a.t0);
             slow = idx < a.n_rows && (a.t_rows[idx] - t_new) * dir <= 0.0;
         }
@@ -363,16 +390,16 @@ struct StepRecorder {
 
     // solout after an accepted step from (t, y) to (t + h, yn); k[0] = f(t, y), dydt = f(t + h, yn).  Returns true when
     // an event asks to terminate (ControlFlag::Terminate).
-    __device__ __forceinline__ bool step(const OdeKernelArgs& a, long long traj, double t, double h, const double (&y)[N],
+    __device__ __forceinline__ bool step(const OdeKernelArgs& a, double (*buf)[32], unsigned lane, long long traj, double t, double h, const double (&y)[N],
                                          const double (&yn)[N], const double (&k)[S][N], const double (&dydt)[N], const double* p) {
         const double t_new = t + h;
         const double dir = d_signum(a.tf - a.t0);
         DenseStep<Sys, Tab> ds;
         bool prepared = false;
         // ---- base recorder
-        if (a.rec_mode == REC_DEFAULT) {
-            push(a, traj, t_new, yn);
-        } else if (a.rec_mode == REC_DENSE) {
+        if (rec_mode_of(a) == REC_DEFAULT) {
+            push(a, buf, lane, traj, t_new, yn);
+        } else if (rec_mode_of(a) == REC_DENSE) {
             if (t != t_new && a.dense_n > 1) {
                 ds.prepare(t, h, y, yn, k, dydt, p);
                 prepared = true;
@@ -381,11 +408,11 @@ struct StepRecorder {
                     const double ti = t + (double)i * h_old / (double)a.dense_n;
                     double row[N];
                     ds.eval(ti, row);
-                    push(a, traj, ti, row);
+                    push(a, buf, lane, traj, ti, row);
                 }
             }
-            push(a, traj, t_new, yn);
-        } else if (a.rec_mode == REC_CROSSING) {
+            push(a, buf, lane, traj, t_new, yn);
+        } else if (rec_mode_of(a) == REC_CROSSING) {
             const double off = component(yn, a.cross_component) - a.cross_threshold;
             if (have_last) {
                 const bool is_crossing = d_signum(last_off) != d_signum(off);  // NaN != anything
@@ -402,13 +429,13 @@ struct StepRecorder {
                         }
                         double row[N];
                         ds.eval(t_cross, row);
-                        push(a, traj, t_cross, row);
+                        push(a, buf, lane, traj, t_cross, row);
                     }
                 }
             }
             last_off = off;
             have_last = true;
-        } else if (a.rec_mode == REC_HYPERPLANE) {
+        } else if (rec_mode_of(a) == REC_HYPERPLANE) {
             const double dist = plane_distance(a, yn);
             if (have_last) {
                 const double last = last_off;
@@ -426,7 +453,7 @@ struct StepRecorder {
                         }
                         double row[N];
                         ds.eval(t_cross, row);
-                        push(a, traj, t_cross, row);
+                        push(a, buf, lane, traj, t_cross, row);
                     }
                 }
             }
@@ -437,22 +464,22 @@ struct StepRecorder {
             // even: always interpolated, and the last plan entry is the tf sentinel of the final-point rule, even.rs:166-188)
             while (idx < a.n_rows && (a.t_rows[idx] - t_new) * dir <= 0.0) {
                 const double te = a.t_rows[idx];
-                if (a.rec_mode == REC_EVEN && idx == a.n_rows - 1) {
+                if (rec_mode_of(a) == REC_EVEN && idx == a.n_rows - 1) {
                     if (t_new == a.tf) {
                         const double t_prev_row = a.t_rows[idx - 1];
                         if (fabs(t_prev_row - a.tf) <= a.even_tol) rows -= 1;  // solution.pop(): replace the near-duplicate
-                        push(a, traj, a.tf, yn);
+                        push(a, buf, lane, traj, a.tf, yn);
                     }
                     idx = a.n_rows;
                     break;
                 }
-                if (te == t_new && a.rec_mode == REC_T_EVAL) {
-                    push(a, traj, te, yn);
+                if (te == t_new && rec_mode_of(a) == REC_T_EVAL) {
+                    push(a, buf, lane, traj, te, yn);
                 } else {
                     if (!prepared) { ds.prepare(t, h, y, yn, k, dydt, p); prepared = true; }
                     double row[N];
                     ds.eval(te, row);
-                    push(a, traj, te, row);
+                    push(a, buf, lane, traj, te, row);
                 }
                 idx += 1;
             }
@@ -475,7 +502,7 @@ struct StepRecorder {
                         double row[N];
                         ds.eval(t_event, row);
                         const bool push_point = (rows > 0) ? (fabs(t_event - last_t) > 1e-14) : true;
-                        if (push_point) push(a, traj, t_event, row);
+                        if (push_point) push(a, buf, lane, traj, t_event, row);
                         event_count += 1;
                         if (a.event_terminate > 0 && event_count >= a.event_terminate) terminate = true;
                     }

@@ -1,8 +1,8 @@
 """Parity at BASELINE.json's full sizes (the other parity tests use sizes the oracle finishes in a second or two).
 
-  C2  10 M Lorenz / DOPRI5 trajectories, t_eval at 100 points: ONE device-resident launch of the real size; every 4001st
-      trajectory (2 500 of them, spread over the whole index range and over every watermark block class) bitwise against the
-      oracle -- rows, final states, counters
+  C2  10 M Lorenz / DOPRI5 trajectories, t_eval at 100 points: ONE device-resident launch of the real size; every 100th
+      trajectory (100 000 of them, spread over the whole index range and over every watermark block class) bitwise against the
+      oracle -- rows, final states, counters; ensemble mean / variance per t_eval point over all 10 M
   C2' the same ensemble shape through the HOST path (streamed copies, every visible device), 2 M trajectories, same check
   C4  Euler-Maruyama OU and GBM, 1 M paths x 1000 steps: final states within 1e-12 of the oracle on the host-regenerated stream
   C5  heat equation on 2^24 nodes, RK4, 100 steps: bitwise against the oracle
@@ -74,7 +74,23 @@ def test_c2_full_10m_launch_subset_bitwise():
     assert bool((out["evals"].long() == 3 + 6 * (acc + rej) + acc).all())
     assert int(acc.sum()) == 59955285202 and int(rej.sum()) == 4043829491  # the totals every bench line of this ensemble reports
     assert bool(torch.isfinite(out["y_eval"]).all())
-    sub = np.arange(0, n, 4001)
+    # ensemble mean / variance per t_eval point over all 10 M trajectories: the library's sums against torch's
+    # (different summation order: to rounding)
+    sums = torch.zeros((N_EVAL, 3, 2), dtype=torch.float64, device=dev)
+    counts = torch.zeros(N_EVAL, dtype=torch.int64, device=dev)
+    assert lib.deb_ensemble_stats(out["y_eval"].data_ptr(), out["n_emitted"].data_ptr(), n, N_EVAL, 3, sums.data_ptr(), counts.data_ptr(), 0,
+                                  deb.DEB_MEM_DEVICE, torch.cuda.current_stream(dev).cuda_stream) == 0, lib.deb_last_error()
+    torch.cuda.synchronize()
+    assert bool((counts == n).all())
+    s1, s2 = out["y_eval"].sum(dim=0), torch.zeros((N_EVAL, 3), dtype=torch.float64, device=dev)
+    for lo in range(0, n, 1_000_000):  # squares in slices: no second 24 GB tensor
+        s2 += (out["y_eval"][lo:lo + 1_000_000] ** 2).sum(dim=0)
+    mean_ref, var_ref = s1 / n, s2 / n - (s1 / n) ** 2
+    mean, var = sums[..., 0] / n, sums[..., 1] / n - (sums[..., 0] / n) ** 2
+    assert torch.allclose(mean, mean_ref, rtol=0.0, atol=1e-9) and torch.allclose(var, var_ref, rtol=1e-9, atol=1e-9)
+    assert 100.0 < float(var[-1].sum()) < 300.0  # the attractor's spread: the ensemble has decorrelated by t = 100
+    # every 100th trajectory -- 100 000 of them, over the whole index range -- bitwise against the oracle (all host cores)
+    sub = np.arange(0, n, 100)
     sel = torch.from_numpy(sub).to(dev)
     check_subset(sub, {k: v[sel].cpu().numpy() for k, v in out.items()})
 
