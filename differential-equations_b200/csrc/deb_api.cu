@@ -976,6 +976,7 @@ const NcclApi* nccl_api() {
     static NcclApi api;
     static std::once_flag once;
     std::call_once(once, [] {
+        if (getenv("DEB_NO_NCCL")) return;  // test knob: take the host-sum path of deb_solve_ode
         // a copy that is already in the process (e.g. the one PyTorch bundles) wins over the system library
         api.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
         const char* names[] = {"libnccl.so.2", "libnccl.so", "/usr/lib/x86_64-linux-gnu/libnccl.so.2"};
@@ -1651,9 +1652,26 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P_user, deb_result* R_user) 
                 bufs_c.push_back((char*)outs[g].stats.p + sizeof(double) * nd);
                 sts.push_back(outs[g].stats_stream);
             }
-            if (devs.size() > 1) {
+            if (devs.size() > 1 && nccl_api()) {
                 if (int rc = allreduce_across_devices(devs, bufs_d, nd, /*ncclDouble*/ 8, sts)) return rc;
                 if (int rc = allreduce_across_devices(devs, bufs_c, nc, /*ncclInt64*/ 4, sts)) return rc;
+            } else if (devs.size() > 1) {
+                // no libnccl in the process or on the loader path: the per-device sums (a few KB each) are added on the host, in device order
+                std::vector<double> acc_d(nd, 0.0), tmp_d(nd);
+                std::vector<long long> acc_c(nc, 0), tmp_c(nc);
+                for (size_t q = 0; q < devs.size(); q++) {
+                    if (int rc = select_device(devs[q])) return rc;
+                    DEB_CUDA(cudaMemcpyAsync(tmp_d.data(), bufs_d[q], sizeof(double) * nd, cudaMemcpyDeviceToHost, sts[q]));
+                    DEB_CUDA(cudaMemcpyAsync(tmp_c.data(), bufs_c[q], sizeof(long long) * nc, cudaMemcpyDeviceToHost, sts[q]));
+                    DEB_CUDA(cudaStreamSynchronize(sts[q]));
+                    for (size_t i = 0; i < nd; i++) acc_d[i] += tmp_d[i];
+                    for (size_t i = 0; i < nc; i++) acc_c[i] += tmp_c[i];
+                }
+                if (int rc = select_device(C.devices[first])) return rc;
+                DEB_CUDA(cudaMemcpyAsync(outs[first].stats.p, acc_d.data(), sizeof(double) * nd, cudaMemcpyHostToDevice, outs[first].stats_stream));
+                DEB_CUDA(cudaMemcpyAsync((char*)outs[first].stats.p + sizeof(double) * nd, acc_c.data(), sizeof(long long) * nc, cudaMemcpyHostToDevice,
+                                         outs[first].stats_stream));
+                DEB_CUDA(cudaStreamSynchronize(outs[first].stats_stream));
             }
         }
         if (int rc = select_device(C.devices[first])) return rc;

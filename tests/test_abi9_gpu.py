@@ -178,6 +178,29 @@ def test_device_list_equals_one_device(monkeypatch, shift):
         assert np.array_equal(bits(rm.y_eval)[m], bits(one.y_eval)[m])
 
 
+def test_device_list_statistics_without_nccl():
+    """When no libnccl can be loaded the per-device sums are added on the host (DEB_NO_NCCL=1 takes that path): the same
+    statistics to rounding.  A fresh process, because the library looks NCCL up once."""
+    if n_gpus() < 2:
+        pytest.skip("needs two devices")
+    import os, subprocess, sys
+    code = (
+        "import importlib, sys, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "deb = importlib.import_module('differential-equations_b200'); E = deb.ExplicitRungeKutta\n"
+        "mu = np.linspace(0.5, 3.0, 9001)\n"
+        "def prob():\n"
+        "    return (deb.EnsembleIVP.ode(deb.VanDerPolOscillator(mu), 0.0, 3.0, np.tile([2.0, 0.0], (9001, 1))).t_eval(np.linspace(0.0, 3.0, 7))\n"
+        "            .method(E.dopri5().rtol(1e-8)))\n"
+        "one = prob().with_stats().solve(); two = prob().devices([0, 1]).with_stats().solve()\n"
+        "np.testing.assert_allclose(two.stats_sums, one.stats_sums, rtol=1e-12, atol=1e-12)\n"
+        "assert np.array_equal(two.stats_counts, one.stats_counts)\n"
+        "assert np.array_equal(two.y_eval.view(np.uint64), one.y_eval.view(np.uint64))\n"
+        "print('ok')\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, DEB_NO_NCCL="1"), capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
 def test_device_list_is_validated():
     prob = vdp_problem(100)
     with pytest.raises(ValueError, match="duplicate"):
