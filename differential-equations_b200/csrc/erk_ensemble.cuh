@@ -593,6 +593,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const __
     bool pending = false;  // this lane has a parked step
     // per-step recorders: lanes whose step needs a refinement gather (OdeKernelArgs::rec_park); warp-uniform
     bool rec_go = !REC || a.rec_park <= 0;
+    int rec_idle = 0;  // lane-iterations spent waiting since the last refinement (warp-uniform)
     int pend_idx = 0;      // first row of the parked step
 
     // per-lane trajectory state (registers); starts as the idle dummy
@@ -1080,9 +1081,13 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) dp_ensemble_kernel(const __
             }
             if constexpr (REC) {
                 // refine in the next iteration when enough lanes wait, or when no lane of the warp can advance without it
+                // (or when the lanes that wait have idled for 8 iterations per lane of the threshold: an ensemble in which few trajectories
+                // have events never fills the threshold, and its waiting lanes must not idle until their neighbours finish)
                 const unsigned waiting = __ballot_sync(FULL, blocked);
                 const unsigned advancing = __ballot_sync(FULL, stepping && fin < 0 && !blocked);
-                rec_go = a.rec_park <= 0 || __popc(waiting) >= a.rec_park || (waiting != 0u && advancing == 0u);
+                const int n_wait = __popc(waiting);
+                rec_idle = n_wait ? rec_idle + n_wait : 0;
+                rec_go = a.rec_park <= 0 || n_wait >= a.rec_park || rec_idle >= 8 * a.rec_park || (waiting != 0u && advancing == 0u);
                 service = active && fin >= 0;
             } else {
                 service = (active && fin >= 0) || blocked;

@@ -822,6 +822,23 @@ def test_event_detection_bit_exact(meth):
     assert_same_solution(g, c)
 
 
+def test_events_in_a_few_trajectories_only():
+    """Lanes whose step holds an event candidate wait for each other (erk_ensemble.cuh: rec_go).  An ensemble in which one
+    trajectory in eight ever has events (Lorenz rho = 28 among rho = 10: z settles at 9 and never reaches 25) never fills the
+    warp's threshold: the waiting lanes are released by their idle budget.  Results as ever: bitwise the oracle's."""
+    n = 512
+    rho = np.where(np.arange(n) % 8 == 3, 28.0, 10.0)
+    y0 = ob.lorenz_ensemble_y0(n, seed=77)
+    ev = deb.LinearEvent(-25.0, 0.0, [0.0, 0.0, 1.0])
+    for meth in ("dopri5", "rkv656e"):
+        def prob():
+            return (deb.EnsembleIVP.ode(deb.LorenzSystem(10.0, rho, 8.0 / 3.0), 0.0, 8.0, y0).t_eval(np.linspace(0.0, 8.0, 33))
+                    .event(ev, max_event_rows=64).method(getattr(E, meth)().rtol(1e-8)))
+        g, c = prob().solve(), ob.oracle_solve(prob())
+        assert_same_solution(g, c)
+        assert (g.n_emitted[rho == 10.0] <= 34).all() and (g.n_emitted[rho == 28.0] > 36).all()
+
+
 def test_user_defined_event_function_vs_python_restatement():
     """examples/ode/05_damped_pendulum pattern (linearised so that the right-hand side is IEEE-exact on both sides): a
     user-defined right-hand side AND a user-defined terminal event g = max(|theta|, |omega|) - 0.01 on t_eval rows, rkf45():

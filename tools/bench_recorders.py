@@ -30,6 +30,10 @@ def main():
                  ("crossing z=25 both", lambda: base().crossing(2, 25.0, deb.CROSSING_BOTH, 128).method(m())),
                  ("t_eval 100 rows + non-terminal linear event z=25", lambda: base().t_eval(te).event(ev, max_event_rows=128).method(m())),
                  ("every_step + terminal event z=25 (terminate after 3)", lambda: base().every_step(400).event(ev, terminate=3, max_event_rows=400).method(m()))]
+        # events in one trajectory of eight only (rho = 10: z settles at 9 and never reaches 25): the warp's threshold is never filled
+        rho = np.where(np.arange(n) % 8 == 3, 28.0, 10.0)
+        cases.append(("t_eval 100 rows + event z=25, events in 1 trajectory of 8 only",
+                      lambda: deb.EnsembleIVP.ode(deb.LorenzSystem(10.0, rho, 8.0 / 3.0), 0.0, 20.0, y0).t_eval(te).event(ev, max_event_rows=128).method(m())))
         for label, mk in cases:
             mk().solve()  # compile / warm up
             best = None
