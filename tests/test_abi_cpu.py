@@ -290,3 +290,24 @@ def test_rust_shim_structs_follow_the_header_field_for_field():
     assert "pub const DEB_ABI_VERSION: i32 = %d;" % deb.DEB_ABI_VERSION in rs
     for fn in ("deb_solve_ode", "deb_solve_sde", "deb_solve_heat_mol", "deb_define_ode", "deb_define_event", "deb_define_sde", "deb_define_ode_sensitivity"):
         assert "pub fn %s(" % fn in rs, fn
+
+
+def build_c_caller(tmpdir):
+    """examples/c_caller/lorenz_ensemble.c: a plain-C program against include/deb_ensemble.h and libdeb200.so (gcc only)."""
+    exe = os.path.join(str(tmpdir), "lorenz_ensemble")
+    pkg = os.path.join(ROOT, "differential-equations_b200")
+    subprocess.run(["gcc", "-O2", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "c_caller", "lorenz_ensemble.c"), "-L", pkg, "-ldeb200", "-Wl,-rpath," + pkg, "-o", exe], check=True)
+    return exe
+
+
+def test_plain_c_caller_links_and_fails_loudly_without_a_device(lib, tmp_path):
+    """The boundary is usable from C with nothing but the header and the shared library; without a GPU the call reports
+    DEB_ERR_NO_DEVICE (exit code 3 of the example) instead of computing anything on the CPU."""
+    exe = build_c_caller(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    import torch
+    if torch.cuda.is_available():
+        assert out.returncode == 0 and "known answers reproduced" in out.stdout, out.stdout + out.stderr
+    else:
+        assert out.returncode == 3 and "no CPU fallback" in out.stderr, out.stdout + out.stderr

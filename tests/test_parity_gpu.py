@@ -895,3 +895,12 @@ def test_milstein_matches_host_regenerated_philox():
             np.testing.assert_allclose(g.y_final, em.y_final, rtol=1e-12)  # additive noise: Milstein == Euler-Maruyama
         else:
             assert np.abs(g.y_final - em.y_final).max() > 1e-6               # multiplicative noise: the correction acts
+
+
+def test_plain_c_caller_reproduces_the_known_answers(tmp_path):
+    """examples/c_caller/lorenz_ensemble.c through the C ABI with host buffers, no Python in the loop: the L100 / L10 known
+    answers of SURVEY.md appendix A (step counts, final state and t_eval rows of the (1,1,1) Lorenz trajectory), bit for bit."""
+    import subprocess
+    from test_abi_cpu import build_c_caller
+    out = subprocess.run([build_c_caller(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "known answers reproduced" in out.stdout, out.stdout + out.stderr
