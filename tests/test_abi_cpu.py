@@ -311,3 +311,37 @@ def test_plain_c_caller_links_and_fails_loudly_without_a_device(lib, tmp_path):
         assert out.returncode == 0 and "known answers reproduced" in out.stdout, out.stdout + out.stderr
     else:
         assert out.returncode == 3 and "no CPU fallback" in out.stderr, out.stdout + out.stderr
+
+
+def build_cpp_caller(tmpdir):
+    """examples/cpp_caller/builder_api.cpp: the C++ host mirror (include/deb_ensemble.hpp) against libdeb200.so."""
+    exe = os.path.join(str(tmpdir), "builder_api")
+    pkg = os.path.join(ROOT, "differential-equations_b200")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "cpp_caller", "builder_api.cpp"), "-L", pkg, "-ldeb200", "-Wl,-rpath," + pkg, "-o", exe], check=True)
+    return exe
+
+
+def test_cpp_host_mirror_example_links_and_fails_loudly_without_a_device(lib, tmp_path):
+    exe = build_cpp_caller(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    import torch
+    if torch.cuda.is_available():
+        assert out.returncode == 0 and "all checks passed" in out.stdout, out.stdout + out.stderr
+    else:
+        assert out.returncode == 3 and "no CPU fallback" in out.stderr, out.stdout + out.stderr
+
+
+def test_cpp_host_mirror_marshalling_against_the_oracle(tmp_path):
+    """include/deb_ensemble.hpp (EnsembleIVP / ExplicitRungeKutta / System / Event / Solution / Error in C++) with the CPU oracle
+    behind the C ABI (tests/support/abi_on_oracle.cpp, test infrastructure): recorder and event marshalling, row capacities,
+    the per-trajectory Solution view and the Error variants, the reference's known answers."""
+    import oracle_binding as ob
+    ob.load_oracle()  # builds oracle/liboracle.so when missing
+    exe = os.path.join(str(tmp_path), "hpp_check")
+    sup = os.path.join(ROOT, "tests", "support")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(sup, "hpp_host_mirror_check.cpp"), os.path.join(sup, "abi_on_oracle.cpp"), "-L", os.path.join(ROOT, "oracle"),
+                    "-loracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-o", exe], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "all checks passed" in out.stdout, out.stdout + out.stderr

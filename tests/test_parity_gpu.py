@@ -904,3 +904,12 @@ def test_plain_c_caller_reproduces_the_known_answers(tmp_path):
     from test_abi_cpu import build_c_caller
     out = subprocess.run([build_c_caller(tmp_path)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "known answers reproduced" in out.stdout, out.stdout + out.stderr
+
+
+def test_cpp_host_mirror_example_on_the_gpu(tmp_path):
+    """examples/cpp_caller/builder_api.cpp: the crate's builder calls in C++ (include/deb_ensemble.hpp) on the GPU -- known answers
+    bit for bit, a swept terminal event, a user-defined right-hand side with crossings, the Error variants."""
+    import subprocess
+    from test_abi_cpu import build_cpp_caller
+    out = subprocess.run([build_cpp_caller(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "all checks passed" in out.stdout, out.stdout + out.stderr
