@@ -101,6 +101,34 @@ int main() {
             CHECK(thrown);
             std::printf("MaxSteps and BadInput come back as the reference's Error variants\n");
         }
+        // --- examples/sde/03_ornstein_uhlenbeck as an ensemble, and a user-defined SDE that must reproduce it bit for bit
+        {
+            const int n = 100000;
+            auto run = [&](const deb::SdeSystem& sys) {
+                return deb::EnsembleSDE::sde(sys, 0.0, 10.0, std::vector<double>(n, 5.0), 42).t_eval({10.0}).method(ExplicitRungeKutta::euler(0.01)).solve();
+            };
+            auto ou = run(deb::SdeSystem::ornstein_uhlenbeck(0.5, 1.0, 0.3));
+            auto user = run(deb::SdeSystem::from_source(1, "dydt[0] = p[0] * (p[1] - y[0]);", "g[0] = p[2];", {0.5, 1.0, 0.3}));
+            double mean = 0.0, var = 0.0;
+            bool same = true;
+            for (int i = 0; i < n; i++) { mean += ou.y_final[i]; same = same && ou.y_final[i] == user.y_final[i]; }
+            mean /= n;
+            for (int i = 0; i < n; i++) var += (ou.y_final[i] - mean) * (ou.y_final[i] - mean);
+            var /= n;
+            CHECK(same);
+            CHECK(std::fabs(mean - (1.0 + 4.0 * std::exp(-5.0))) < 5e-3 && std::fabs(var - 0.09 * (1.0 - std::exp(-10.0))) < 3e-3);  // sigma^2 / (2 theta) = 0.09
+            std::printf("Ornstein-Uhlenbeck x %d: mean %.4f, variance %.4f at t = 10; the user-defined SDE gives the same bits\n", n, mean, var);
+        }
+        // --- tests/pde/method_of_lines.rs:37-70: heat equation, decay of the first sine mode
+        {
+            const int n = 4097;
+            const double PI = 3.14159265358979323846, alpha = 0.1, dx = 1.0 / (n - 1.0);
+            std::vector<double> u0(n);
+            for (int i = 0; i < n; i++) u0[i] = std::sin(PI * i / (n - 1.0));
+            auto heat = deb::solve_heat_mol(u0, 0.0, 1.0, alpha, ExplicitRungeKutta::rk4(0.2 * dx * dx / alpha).max_steps(1000000), 0.0, 0.01);
+            CHECK(heat.status == DEB_STATUS_COMPLETE && std::fabs(heat.u[n / 2] - std::exp(-alpha * PI * PI * 0.01)) < 1e-6);
+            std::printf("heat equation, %d nodes, %lld RK4 steps: u(1/2, 0.01) = %.9f (exact %.9f)\n", n, heat.steps, heat.u[n / 2], std::exp(-alpha * PI * PI * 0.01));
+        }
     } catch (const deb::CallError& e) {
         std::fprintf(stderr, "%s\n", e.what());
         return e.code == DEB_ERR_NO_DEVICE ? 3 : 1;

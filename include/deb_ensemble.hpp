@@ -11,6 +11,8 @@
 //        .method(ExplicitRungeKutta::dopri5().rtol(..)) :632                  .method(deb::ExplicitRungeKutta::dopri5().rtol(..))
 //        .solve() -> Result<Solution, Error>            :781                  .solve() -> EnsembleSolution; .at(i) returns the Solution of
 //                                                                             trajectory i or throws the reference's Error variant
+//     IVP::sde(&mut sde, t0, tf, y0).method(ExplicitRungeKutta::euler(h)).solve()   :504,857   deb::EnsembleSDE::sde(sde, t0, tf, y0s, seed)...solve()
+//     IVP::pde(&heat, ..).space(MethodOfLines::finite_difference(grid).boundary(bc)).method(rk4(h)).solve()   :419,713   deb::solve_heat_mol(..)
 //
 // The ODE right-hand side is a built-in system of the crate's tests (deb::System::lorenz(..), ...) or the body of `ODE::diff` as
 // CUDA C++ text (deb::System::from_source), compiled into the same kernels at first use.  Per-trajectory parameter sets
@@ -87,6 +89,8 @@ public:
     static ExplicitRungeKutta ralston(double h) { return ExplicitRungeKutta(DEB_RALSTON).h0(h); }
     static ExplicitRungeKutta rk4(double h) { return ExplicitRungeKutta(DEB_RK4).h0(h); }
     static ExplicitRungeKutta three_eighths(double h) { return ExplicitRungeKutta(DEB_THREE_EIGHTHS).h0(h); }
+    // Milstein::new(h) (src/methods/milstein.rs:37-68): derivative-free Milstein, SDE ensembles only
+    static ExplicitRungeKutta milstein(double h) { return ExplicitRungeKutta(DEB_MILSTEIN).h0(h); }
 
     ExplicitRungeKutta& rtol(double v) { opt_.rtol = v; rtol_vec_.clear(); return *this; }
     ExplicitRungeKutta& atol(double v) { opt_.atol = v; atol_vec_.clear(); return *this; }
@@ -419,5 +423,166 @@ private:
     std::vector<int> devices_;
     bool stats_ = false;
 };
+
+// `impl SDE` (src/sde/sde.rs:16-67): the systems of the crate's SDE examples, or drift / diffusion / noise bodies as CUDA C++ text.
+// The Wiener increments come from a counter-based Philox stream keyed by (seed, path index), see deb_sde_problem.
+class SdeSystem {
+public:
+    static SdeSystem ornstein_uhlenbeck(double theta, double mu, double sigma) { return SdeSystem(DEB_SDE_OU, 1, {theta, mu, sigma}); }
+    static SdeSystem geometric_brownian_motion(double mu, double sigma) { return SdeSystem(DEB_SDE_GBM, 1, {mu, sigma}); }
+    // examples/sde/02_heston_model: y = (price, variance)
+    static SdeSystem heston(double mu, double kappa, double theta, double sigma, double rho) { return SdeSystem(DEB_SDE_HESTON, 2, {mu, kappa, theta, sigma, rho}); }
+    // drift(t, y, dydt, p), diffusion(t, y, g, p) (diagonal noise) and, optionally, noise(dw, p) mixing the independent increments in place
+    static SdeSystem from_source(int dim, const std::string& drift_body, const std::string& diffusion_body, std::vector<double> params,
+                                 const std::string& noise_body = std::string()) {
+        int32_t id = 0;
+        check(deb_define_sde(dim, (int)params.size(), drift_body.c_str(), diffusion_body.c_str(), noise_body.empty() ? nullptr : noise_body.c_str(), &id),
+              "deb_define_sde");
+        return SdeSystem(id, dim, std::move(params));
+    }
+    int id() const { return id_; }
+    int dim() const { return dim_; }
+    const std::vector<double>& params() const { return params_; }
+
+private:
+    SdeSystem(int id, int dim, std::vector<double> p) : id_(id), dim_(dim), params_(std::move(p)) {}
+    int id_, dim_;
+    std::vector<double> params_;
+};
+
+// `IVP::sde(&mut sde, t0, tf, y0)` (src/ivp.rs:504) for N paths
+class EnsembleSDE {
+public:
+    static EnsembleSDE sde(SdeSystem system, double t0, double tf, std::vector<double> y0s, uint64_t seed) {
+        if (y0s.size() % (size_t)system.dim() != 0) throw std::invalid_argument("y0s: n * dim values expected");
+        return EnsembleSDE(std::move(system), t0, tf, std::move(y0s), seed);
+    }
+    EnsembleSDE& t_eval(std::vector<double> points) { t_eval_ = std::move(points); return *this; }
+    EnsembleSDE& method(ExplicitRungeKutta m) { method_.assign(1, std::move(m)); return *this; }
+    EnsembleSDE& device(int d) { device_ = d; return *this; }
+    // global index of path 0 (an ensemble split over several calls keeps its noise)
+    EnsembleSDE& path_offset(long long o) { path_offset_ = o; return *this; }
+
+    EnsembleSolution solve() const {
+        if (method_.empty()) throw std::invalid_argument("method(...) must be set before solve()");
+        const int dim = system_.dim();
+        const long long n = (long long)(y0s_.size() / (size_t)dim);
+        const int n_eval = (int)t_eval_.size();
+        EnsembleSolution out;
+        out.n = n;
+        out.dim = dim;
+        out.row_capacity = n_eval;
+        out.y_eval.assign((size_t)n * n_eval * dim, std::numeric_limits<double>::quiet_NaN());
+        out.n_emitted.assign(n, 0);
+        out.status.assign(n, -1);
+        out.accepted.assign(n, 0);
+        out.rejected.assign(n, 0);
+        out.evals.assign(n, 0);
+        out.t_final.assign(n, 0.0);
+        out.y_final.assign((size_t)n * dim, 0.0);
+        std::vector<double> t_rows((size_t)(n_eval > 0 ? n_eval : 1), 0.0);
+        deb_sde_problem P;
+        std::memset(&P, 0, sizeof P);
+        P.struct_size = sizeof P;
+        P.system = system_.id();
+        P.method = method_[0].method_id();
+        P.dim = dim;
+        P.n_params = (int)system_.params().size();
+        P.n_traj = n;
+        P.y0 = y0s_.data();
+        P.params_shared = 1;
+        P.params = system_.params().data();
+        P.n_eval = n_eval;
+        P.t_eval = t_eval_.empty() ? nullptr : t_eval_.data();
+        P.t0 = t0_;
+        P.tf = tf_;
+        P.opt = method_[0].options(dim);
+        P.seed = seed_;
+        P.path_offset = path_offset_;
+        P.device = device_;
+        P.memspace = DEB_MEM_HOST;
+        deb_result R;
+        std::memset(&R, 0, sizeof R);
+        R.struct_size = sizeof R;
+        R.y_eval = out.y_eval.empty() ? nullptr : out.y_eval.data();
+        R.n_emitted = out.n_emitted.data();
+        R.t_final = out.t_final.data();
+        R.y_final = out.y_final.data();
+        R.status = out.status.data();
+        R.accepted = out.accepted.data();
+        R.rejected = out.rejected.data();
+        R.evals = out.evals.data();
+        R.t_rows = t_rows.data();
+        check(deb_solve_sde(&P, &R), "deb_solve_sde");
+        out.t_rows.assign(t_rows.begin(), t_rows.begin() + R.n_rows);
+        out.kernel_ms = R.kernel_ms;
+        out.total_ms = R.total_ms;
+        out.gpu_launches = R.gpu_launches;
+        return out;
+    }
+
+private:
+    EnsembleSDE(SdeSystem s, double t0, double tf, std::vector<double> y0s, uint64_t seed)
+        : system_(std::move(s)), t0_(t0), tf_(tf), y0s_(std::move(y0s)), seed_(seed) {}
+    SdeSystem system_;
+    double t0_, tf_;
+    std::vector<double> y0s_, t_eval_;
+    uint64_t seed_;
+    long long path_offset_ = 0;
+    std::vector<ExplicitRungeKutta> method_;
+    int device_ = 0;
+};
+
+// BoundaryCondition of the method-of-lines grid (src/pde/boundary.rs)
+struct Boundary {
+    int kind;  // 0 = Dirichlet(value), 1 = Neumann(gradient)
+    double value;
+    static Boundary dirichlet(double v) { return Boundary{0, v}; }
+    static Boundary neumann(double g) { return Boundary{1, g}; }
+};
+struct HeatSolution {
+    std::vector<double> u;
+    double t;
+    long long steps;
+    int status;  // deb_status
+};
+// IVP::pde(&HeatEquation{alpha}, t0, tf, u0).space(MethodOfLines::finite_difference(StructuredGrid::uniform([lo], [hi], [n])).boundary(..))
+//     .method(ExplicitRungeKutta::rk4(h)).solve()   (src/ivp.rs:419,713; tests/pde/method_of_lines.rs:37-70): one large state on one GPU
+inline HeatSolution solve_heat_mol(const std::vector<double>& u0, double lo, double hi, double alpha, const ExplicitRungeKutta& method, double t0,
+                                   double tf, Boundary lower = Boundary::dirichlet(0.0), Boundary upper = Boundary::dirichlet(0.0), int device = 0) {
+    HeatSolution out;
+    out.u.assign(u0.size(), 0.0);
+    out.t = 0.0;
+    int64_t steps = 0;
+    int32_t status = -1;
+    const deb_erk_options o = method.options(1);
+    deb_heat_problem P;
+    std::memset(&P, 0, sizeof P);
+    P.struct_size = sizeof P;
+    P.n_nodes = (int64_t)u0.size();
+    P.lo = lo;
+    P.hi = hi;
+    P.alpha = alpha;
+    P.bc_lower_kind = lower.kind;
+    P.bc_lower_value = lower.value;
+    P.bc_upper_kind = upper.kind;
+    P.bc_upper_value = upper.value;
+    P.method = method.method_id();
+    P.h = o.h0;
+    P.t0 = t0;
+    P.tf = tf;
+    P.max_steps = o.max_steps;
+    P.u0 = u0.data();
+    P.u_final = out.u.data();
+    P.t_final = &out.t;
+    P.steps = &steps;
+    P.status = &status;
+    P.device = device;
+    P.memspace = DEB_MEM_HOST;
+    check(deb_solve_heat_mol(&P), "deb_solve_heat_mol");
+    out.steps = steps;
+    out.status = status;
+    return out;
+}
 
 }  // namespace deb

@@ -9,6 +9,8 @@
 #include "deb_ensemble.h"
 
 extern "C" int orc_solve_ode(const deb_ode_problem* P, deb_result* R, int n_threads);
+extern "C" int orc_solve_sde(const deb_sde_problem* P, deb_result* R, int n_threads);
+extern "C" int orc_solve_heat_mol(const deb_heat_problem* P, int n_threads);
 
 static thread_local std::string g_err;
 
@@ -21,6 +23,19 @@ void deb_erk_options_default(deb_erk_options* o) {  // erk/mod.rs:135-144
     o->safety_factor = 0.9; o->min_scale = 0.2; o->max_scale = 10.0; o->max_rejects = 100;
 }
 int deb_define_ode(int32_t, int32_t, const char*, int32_t*) { g_err = "user-defined systems need the GPU library"; return DEB_ERR_UNSUPPORTED; }
+int deb_define_sde(int32_t, int32_t, const char*, const char*, const char*, int32_t*) { g_err = "user-defined SDEs need the GPU library"; return DEB_ERR_UNSUPPORTED; }
+int deb_solve_sde(const deb_sde_problem* P, deb_result* R) {
+    if (orc_solve_sde(P, R, 0) != 0) { g_err = "the oracle rejected the problem"; return DEB_ERR_BAD_ARG; }
+    int nr = 0;
+    for (int i = 0; i < P->n_eval; i++)
+        if (P->t_eval[i] > P->t0 || (i == 0 && P->t_eval[i] == P->t0)) { if (R->t_rows) R->t_rows[nr] = P->t_eval[i]; nr++; }
+    R->n_rows = nr;
+    return DEB_OK;
+}
+int deb_solve_heat_mol(const deb_heat_problem* P) {
+    if (orc_solve_heat_mol(P, 0) != 0) { g_err = "the oracle rejected the problem"; return DEB_ERR_BAD_ARG; }
+    return DEB_OK;
+}
 int deb_define_event(int32_t, const char*, int32_t*) { g_err = "user-defined events need the GPU library"; return DEB_ERR_UNSUPPORTED; }
 
 int deb_solve_ode(const deb_ode_problem* P, deb_result* R) {

@@ -121,6 +121,30 @@ int main() {
         auto rk4 = EnsembleIVP::ode(System::exponential_growth(1.0), 0.0, 1.0, {1.0}).t_eval({1.0}).method(ExplicitRungeKutta::rk4(0.01)).solve();
         CHECK(rk4.at(0).steps.accepted == 100 && std::fabs(rk4.at(0).y[0][0] - std::exp(1.0)) < 1e-9);
     }
+    {   // IVP::sde: Ornstein-Uhlenbeck paths with Euler-Maruyama and Milstein; the sample moments follow the SDE's
+        const int n = 4000;
+        auto run = [&](const deb::ExplicitRungeKutta& m, uint64_t seed) {
+            return deb::EnsembleSDE::sde(deb::SdeSystem::ornstein_uhlenbeck(0.5, 1.0, 0.3), 0.0, 2.0, std::vector<double>(n, 5.0), seed).t_eval({1.0, 2.0}).method(m).solve();
+        };
+        auto em = run(ExplicitRungeKutta::euler(0.01), 7), em2 = run(ExplicitRungeKutta::euler(0.01), 7), other = run(ExplicitRungeKutta::euler(0.01), 8);
+        auto mil = run(ExplicitRungeKutta::milstein(0.01), 7);
+        double mean = 0.0;
+        for (int i = 0; i < n; i++) mean += em.at(i).y[1][0];
+        mean /= n;
+        CHECK(std::fabs(mean - (1.0 + 4.0 * std::exp(-1.0))) < 0.03);  // E[y(2)] = mu + (y0 - mu) e^{-theta t}
+        CHECK(em.at(17).t.size() == 2 && em.at(17).t[1] == 2.0 && em.at(17).steps.accepted == 200);
+        CHECK(em.at(17).y[1][0] == em2.at(17).y[1][0] && em.at(17).y[1][0] != other.at(17).y[1][0]);  // the stream is a function of (seed, path)
+        CHECK(std::fabs(mil.at(17).y[1][0] - em.at(17).y[1][0]) < 1e-12);  // additive noise: the Milstein correction vanishes
+    }
+    {   // IVP::pde: heat equation by the method of lines, tests/pde/method_of_lines.rs:37-70 (decay of the first sine mode)
+        const int n = 41;
+        std::vector<double> u0(n);
+        for (int i = 0; i < n; i++) u0[i] = std::sin(PI * i / (n - 1.0));
+        const double alpha = 0.1, dx = 1.0 / (n - 1.0);
+        auto heat = deb::solve_heat_mol(u0, 0.0, 1.0, alpha, ExplicitRungeKutta::rk4(0.2 * dx * dx / alpha), 0.0, 0.1);
+        CHECK(heat.status == DEB_STATUS_COMPLETE && std::fabs(heat.t - 0.1) < 1e-12 && heat.steps > 0);
+        CHECK(std::fabs(heat.u[n / 2] - std::exp(-alpha * PI * PI * 0.1)) < 5e-4 && heat.u[0] == u0[0] && heat.u[n - 1] == u0[n - 1]);  // Dirichlet nodes do not move
+    }
     std::printf(failures ? "%d check(s) FAILED\n" : "all checks passed\n", failures);
     return failures ? 1 : 0;
 }
