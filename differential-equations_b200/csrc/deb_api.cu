@@ -1692,6 +1692,18 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P_user, deb_result* R_user) 
     return DEB_OK;
 }
 
+extern "C" int deb_plan_fixed_steps(double t0, double tf, double h0, double h_min, double h_max, int64_t max_steps, int64_t* n_steps, int32_t* n_tail,
+                                    double* h_tail, int32_t* status) {
+    if (!n_steps || !n_tail || !h_tail || !status) return fail(DEB_ERR_BAD_ARG, "NULL argument");
+    FixedSchedule fs;
+    if (int rc = plan_fixed_schedule(t0, tf, h0, h_min, h_max, (long long)max_steps, &fs, [](long long, double, double) {})) return rc;
+    *n_steps = fs.n_steps;
+    *n_tail = fs.n_tail;
+    for (int q = 0; q < deb::DEB_FX_MAX_TAIL; q++) h_tail[q] = fs.h_tail[q];
+    *status = fs.status;
+    return DEB_OK;
+}
+
 extern "C" int deb_define_ode(int32_t dim, int32_t n_params, const char* diff_body, int32_t* system_id) {
     if (!diff_body || !system_id) return fail(DEB_ERR_BAD_ARG, "NULL argument");
     if (dim < 1 || dim > DEB_MAX_DIM) return fail(DEB_ERR_BAD_ARG, "dim must be in 1..DEB_MAX_DIM");

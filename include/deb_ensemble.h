@@ -408,6 +408,12 @@ int deb_synchronize(int32_t device);
  *   for the compute-bound ensemble kernels (MEASURED_PEAKS.json has no FP64 entry). */
 int deb_pow_device(const double* x, double y, int64_t n, double* out, int32_t device);
 int deb_fp64_issue_peak(int32_t device, int32_t use_fma, double* dp_inst_per_s, float* ms);
+/* deb_plan_fixed_steps: the step schedule the fixed-step and SDE kernels follow, planned on the host exactly as the reference's loop
+ *   produces it (solve_ivp.rs:193-209, :263; fixed/ordinary.rs:16-56): n_steps steps, all of size h0 (|tf - t0| / 100 when h0 == 0)
+ *   except the last n_tail (1..4), whose sizes are h_tail[0..n_tail) -- the clip at tf can fire more than once.  status is
+ *   DEB_STATUS_COMPLETE, DEB_STATUS_MAX_STEPS or DEB_STATUS_BAD_INPUT (then n_steps = 0).  Host only: no device is touched. */
+int deb_plan_fixed_steps(double t0, double tf, double h0, double h_min, double h_max, int64_t max_steps, int64_t* n_steps, int32_t* n_tail,
+                         double* h_tail, int32_t* status);
 
 #ifdef __cplusplus
 }

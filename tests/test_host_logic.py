@@ -206,3 +206,66 @@ def test_heston_vector_sde_oracle_against_a_python_restatement():
             y, steps = path_py(i, mil)
             assert steps == sol.accepted[i] and np.array_equal(np.array(y).view(np.uint64), sol.y_final[i].view(np.uint64))
             assert np.array_equal(sol.y_eval[i, 1].view(np.uint64), sol.y_final[i].view(np.uint64))
+
+
+def test_fixed_step_schedule_planner_follows_the_reference_loop():
+    """deb_plan_fixed_steps (host only): the schedule the fixed-step / SDE kernels follow = the reference's loop
+    (solve_ivp.rs:193-209, :263), including the cases where the clip at tf fires twice (t + (tf - t) misses tf by an ulp when
+    t and tf have opposite signs: one more tiny step).  Random sweep of the class the round-1 review found (t0 << 0 < tf, coarse
+    h) plus ordinary cases: replaying (n_steps, h0, tail) must visit exactly the reference loop's times."""
+    import ctypes as C
+    import importlib
+    deb = importlib.import_module("differential-equations_b200")
+    lib = deb.load_library()
+    eps10 = 10.0 * np.finfo(float).eps
+
+    def reference_loop(t0, tf, h, max_steps):
+        d = math.copysign(1.0, tf - t0)
+        if tf == t0 or math.copysign(1.0, h) != d or abs(h) > abs(tf - t0) or h == 0.0:  # validate_step_size_parameters, utils.rs:60-157
+            return [], t0, deb.DEB_STATUS_BAD_INPUT
+        t, hs = t0, []
+        while True:
+            if (t + h - tf) * d > 0.0:
+                h_new = tf - t
+                if abs(h_new) < eps10:
+                    return hs, t, deb.DEB_STATUS_COMPLETE
+                h = h_new
+            if len(hs) >= max_steps:
+                return hs, t, deb.DEB_STATUS_MAX_STEPS
+            hs.append(h)
+            t = t + h
+            if abs(tf - t) <= eps10:
+                return hs, t, deb.DEB_STATUS_COMPLETE
+
+    rng = np.random.default_rng(11)
+    cases = [(-22246.572886668695, 976.800691167858, 7199.779502015325)]  # the reviewer's example: 5 steps, the last two clipped
+    for _ in range(3000):
+        t0 = -10.0 ** rng.uniform(0, 5)
+        tf = 10.0 ** rng.uniform(0, 4)
+        cases.append((t0, tf, (tf - t0) / rng.uniform(1.5, 12.0)))
+    for _ in range(1000):
+        t0, span = rng.uniform(-5, 5), 10.0 ** rng.uniform(-2, 2)
+        sgn = 1.0 if rng.uniform() < 0.5 else -1.0
+        cases.append((t0, t0 + sgn * span, sgn * span / rng.integers(1, 400)))
+    double_clips = 0
+    for t0, tf, h in cases:
+        n_steps, n_tail, status = C.c_int64(0), C.c_int32(0), C.c_int32(-1)
+        tail = (C.c_double * 4)()
+        rc = lib.deb_plan_fixed_steps(t0, tf, h, 0.0, float("inf"), 10000, C.byref(n_steps), C.byref(n_tail), tail, C.byref(status))
+        hs, t_end, st = reference_loop(t0, tf, h, 10000)
+        assert rc == 0 and status.value == st and n_steps.value == len(hs), (t0, tf, h)
+        k = n_steps.value - n_tail.value
+        replay = [h] * k + [tail[q] for q in range(n_tail.value)]
+        assert replay == hs, (t0, tf, h, replay[-3:], hs[-3:])
+        double_clips += n_tail.value >= 2
+    assert double_clips > 100  # the sweep does reach the double clip
+    # BadInput (utils.rs:60-157) and MaxSteps
+    for t0, tf, h in ((0.0, 0.0, 0.1), (0.0, 1.0, -0.1), (0.0, 1.0, 2.0)):
+        n_steps, n_tail, status = C.c_int64(0), C.c_int32(0), C.c_int32(-1)
+        tail = (C.c_double * 4)()
+        assert lib.deb_plan_fixed_steps(t0, tf, h, 0.0, float("inf"), 10000, C.byref(n_steps), C.byref(n_tail), tail, C.byref(status)) == 0
+        assert status.value == deb.DEB_STATUS_BAD_INPUT and n_steps.value == 0
+    n_steps, n_tail, status = C.c_int64(0), C.c_int32(0), C.c_int32(-1)
+    tail = (C.c_double * 4)()
+    assert lib.deb_plan_fixed_steps(0.0, 1.0, 1e-3, 0.0, float("inf"), 100, C.byref(n_steps), C.byref(n_tail), tail, C.byref(status)) == 0
+    assert status.value == deb.DEB_STATUS_MAX_STEPS and n_steps.value == 100
