@@ -115,7 +115,7 @@ class HeatProblem(C.Structure):
 ABI_SYMBOLS = ["deb_abi_version", "deb_last_error", "deb_device_count", "deb_erk_options_default", "deb_define_ode", "deb_define_event",
                "deb_define_sde", "deb_check_sde", "deb_define_ode_sensitivity", "deb_launch_count", "deb_check_ode", "deb_trim_memory", "deb_solve_ode",
                "deb_solve_sde", "deb_solve_heat_mol", "deb_heat_rhs", "deb_ensemble_stats", "deb_malloc", "deb_free", "deb_memcpy_h2d",
-               "deb_memcpy_d2h", "deb_synchronize", "deb_pow_device", "deb_fp64_issue_peak", "deb_plan_fixed_steps"]
+               "deb_memcpy_d2h", "deb_synchronize", "deb_pow_device", "deb_fp64_issue_peak", "deb_plan_fixed_steps", "deb_shard_layout"]
 
 _lib = None
 
@@ -152,6 +152,7 @@ def load_library() -> C.CDLL:
                                        C.c_int32, C.c_int32, C.c_void_p]
     lib.deb_pow_device.argtypes = [_dp, C.c_double, C.c_int64, _dp, C.c_int32]
     lib.deb_fp64_issue_peak.argtypes = [C.c_int32, C.c_int32, _dp, C.POINTER(C.c_float)]
+    lib.deb_shard_layout.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.deb_plan_fixed_steps.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64, C.POINTER(C.c_int64),
                                          C.POINTER(C.c_int32), _dp, C.POINTER(C.c_int32)]
     lib.deb_malloc.argtypes = [C.c_int32, C.c_size_t, C.POINTER(C.c_void_p)]

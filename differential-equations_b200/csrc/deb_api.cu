@@ -1692,6 +1692,21 @@ extern "C" int deb_solve_ode(const deb_ode_problem* P_user, deb_result* R_user) 
     return DEB_OK;
 }
 
+extern "C" int deb_shard_layout(int64_t n_traj, int32_t n_devices, int32_t index, int32_t shift, int64_t local_block, int64_t* n_local_blocks,
+                                int64_t* n_local_traj, int64_t* global_block) {
+    if (!n_local_blocks || !n_local_traj || !global_block) return fail(DEB_ERR_BAD_ARG, "NULL argument");
+    if (n_traj < 0 || n_devices < 1 || index < 0 || index >= n_devices || shift < 0 || shift > 30) return fail(DEB_ERR_BAD_ARG, "bad shard description");
+    ShardMap M;
+    M.n_total = n_traj;
+    M.shift = shift;
+    M.G = n_devices;
+    M.g = index;
+    *n_local_blocks = M.local_blocks();
+    *n_local_traj = M.local_count();
+    *global_block = (local_block >= 0 && local_block < M.local_blocks()) ? M.global_block(local_block) : -1;
+    return DEB_OK;
+}
+
 extern "C" int deb_plan_fixed_steps(double t0, double tf, double h0, double h_min, double h_max, int64_t max_steps, int64_t* n_steps, int32_t* n_tail,
                                     double* h_tail, int32_t* status) {
     if (!n_steps || !n_tail || !h_tail || !status) return fail(DEB_ERR_BAD_ARG, "NULL argument");

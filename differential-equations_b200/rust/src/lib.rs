@@ -170,6 +170,9 @@ extern "C" {
     pub fn deb_last_error() -> *const c_char;
     pub fn deb_device_count() -> i32;
     pub fn deb_launch_count() -> i64;
+    /// host only: how a device list splits an ensemble (block b of 2^shift trajectories on devices[b mod n_devices])
+    pub fn deb_shard_layout(n_traj: i64, n_devices: i32, index: i32, shift: i32, local_block: i64, n_local_blocks: *mut i64,
+                            n_local_traj: *mut i64, global_block: *mut i64) -> i32;
     /// host only: the step schedule of the fixed-step / SDE kernels (n_steps steps of h0, the last n_tail with sizes h_tail[..n_tail])
     pub fn deb_plan_fixed_steps(t0: f64, tf: f64, h0: f64, h_min: f64, h_max: f64, max_steps: i64, n_steps: *mut i64, n_tail: *mut i32,
                                 h_tail: *mut f64, status: *mut i32) -> i32;

@@ -412,6 +412,12 @@ int deb_fp64_issue_peak(int32_t device, int32_t use_fma, double* dp_inst_per_s, 
  *   produces it (solve_ivp.rs:193-209, :263; fixed/ordinary.rs:16-56): n_steps steps, all of size h0 (|tf - t0| / 100 when h0 == 0)
  *   except the last n_tail (1..4), whose sizes are h_tail[0..n_tail) -- the clip at tf can fire more than once.  status is
  *   DEB_STATUS_COMPLETE, DEB_STATUS_MAX_STEPS or DEB_STATUS_BAD_INPUT (then n_steps = 0).  Host only: no device is touched. */
+/* deb_shard_layout: how a call with a device list splits an ensemble (blocks of 2^shift consecutive trajectories, block b on
+ *   devices[b mod n_devices]; shift = 12 unless DEB_WM_SHIFT says otherwise): the number of blocks and of trajectories that device
+ *   number `index` of the list integrates, and the global number of its local block `local_block` (-1 when it has no such block).
+ *   Host only. */
+int deb_shard_layout(int64_t n_traj, int32_t n_devices, int32_t index, int32_t shift, int64_t local_block, int64_t* n_local_blocks,
+                     int64_t* n_local_traj, int64_t* global_block);
 int deb_plan_fixed_steps(double t0, double tf, double h0, double h_min, double h_max, int64_t max_steps, int64_t* n_steps, int32_t* n_tail,
                          double* h_tail, int32_t* status);
 

@@ -269,3 +269,35 @@ def test_fixed_step_schedule_planner_follows_the_reference_loop():
     tail = (C.c_double * 4)()
     assert lib.deb_plan_fixed_steps(0.0, 1.0, 1e-3, 0.0, float("inf"), 100, C.byref(n_steps), C.byref(n_tail), tail, C.byref(status)) == 0
     assert status.value == deb.DEB_STATUS_MAX_STEPS and n_steps.value == 100
+
+
+def test_device_list_split_is_a_partition():
+    """deb_shard_layout (host only): the block-cyclic split behind deb_ode_problem.devices -- every block of 2^shift trajectories on
+    exactly one device, block b on device b mod G, the last block partial; counts add up for every ensemble size around the block
+    boundaries."""
+    import ctypes as C
+    import importlib
+    deb = importlib.import_module("differential-equations_b200")
+    lib = deb.load_library()
+    for shift in (2, 5, 12):
+        B = 1 << shift
+        for G in (1, 2, 3, 8, 16):
+            for n in sorted({0, 1, B - 1, B, B + 1, G * B - 1, G * B, G * B + 1, 7 * B + 3, 10_000_000 if shift == 12 else 1000}):
+                nb = (n + B - 1) // B
+                seen, total = set(), 0
+                for g in range(G):
+                    nlb, cnt, gb = C.c_int64(-1), C.c_int64(-1), C.c_int64(-2)
+                    assert lib.deb_shard_layout(n, G, g, shift, 0, C.byref(nlb), C.byref(cnt), C.byref(gb)) == 0
+                    mine = [b for b in range(nb) if b % G == g]
+                    assert nlb.value == len(mine) and cnt.value == sum(min(B, n - b * B) for b in mine), (shift, G, n, g)
+                    assert gb.value == (mine[0] if mine else -1)
+                    probe = [0, len(mine) - 1] if len(mine) > 1 else list(range(len(mine)))
+                    for lb in probe + ([len(mine) // 2] if len(mine) > 2 else []):
+                        assert lib.deb_shard_layout(n, G, g, shift, lb, C.byref(nlb), C.byref(cnt), C.byref(gb)) == 0
+                        assert gb.value == mine[lb]
+                    assert lib.deb_shard_layout(n, G, g, shift, len(mine), C.byref(nlb), C.byref(cnt), C.byref(gb)) == 0 and gb.value == -1
+                    seen.update(mine)
+                    total += cnt.value
+                assert total == n and seen == set(range(nb))
+    nlb, cnt, gb = C.c_int64(), C.c_int64(), C.c_int64()
+    assert lib.deb_shard_layout(100, 2, 2, 12, 0, C.byref(nlb), C.byref(cnt), C.byref(gb)) == deb.DEB_ERR_BAD_ARG
