@@ -101,6 +101,16 @@ int main() {
             CHECK(thrown);
             std::printf("MaxSteps and BadInput come back as the reference's Error variants\n");
         }
+        // --- examples/ode/16_sensitivity pattern: forward sensitivities generated from diff / jacobian / jacobian_p (logistic growth, p = {k, m})
+        {
+            System sens = System::sensitivity_from_source(1, "dydt[0] = p[0] * y[0] * (1.0 - y[0] / p[1]);", "J[0] = p[0] * (1.0 - 2.0 * y[0] / p[1]);",
+                                                          "Jp[0] = y[0] * (1.0 - y[0] / p[1]); Jp[1] = p[0] * y[0] * y[0] / (p[1] * p[1]);", {1.0, 10.0});
+            auto sol = EnsembleIVP::ode(sens, 0.0, 2.0, {1.0, 0.0, 0.0}).t_eval({2.0}).method(ExplicitRungeKutta::dop853().rtol(1e-11).atol(1e-11)).solve();
+            const std::vector<double> z = sol.at(0).y[0];  // [y, dy/dk, dy/dm]
+            const double e = std::exp(-2.0), d = 1.0 + 9.0 * e;
+            CHECK(z.size() == 3 && std::fabs(z[0] - 10.0 / d) < 1e-8 && std::fabs(z[1] - 10.0 * 9.0 * 2.0 * e / (d * d)) < 1e-7 && std::fabs(z[2] - (1.0 - e) / (d * d)) < 1e-8);
+            std::printf("logistic growth with generated forward sensitivities: dy/dk = %.8f, dy/dm = %.8f at t = 2\n", z[1], z[2]);
+        }
         // --- examples/sde/03_ornstein_uhlenbeck as an ensemble, and a user-defined SDE that must reproduce it bit for bit
         {
             const int n = 100000;

@@ -149,6 +149,16 @@ public:
         check(deb_define_ode(dim, (int)params.size(), diff_body.c_str(), &id), "deb_define_ode");
         return System(id, dim, std::move(params));
     }
+    // ForwardSensitivityOde::new (src/ode/sensitivity/forward.rs:43-116): the augmented system z = [y, S], S' = J_y S + J_p, generated from the
+    // bodies of `diff`, `jacobian` (J[r*dim + c] = df_r/dy_c) and `jacobian_p` (Jp[r*n_params + c] = df_r/dp_c); its dimension is dim * (1 + n_params)
+    static System sensitivity_from_source(int dim, const std::string& diff_body, const std::string& jacobian_body, const std::string& jacobian_p_body,
+                                          std::vector<double> params) {
+        int32_t id = 0;
+        check(deb_define_ode_sensitivity(dim, (int)params.size(), diff_body.c_str(), jacobian_body.c_str(), jacobian_p_body.c_str(), &id),
+              "deb_define_ode_sensitivity");
+        const int np = (int)params.size();
+        return System(id, dim * (1 + np), std::move(params));
+    }
     // one parameter set per trajectory, [n_traj][n_params] flat (a parameter sweep)
     System& sweep(std::vector<double> per_trajectory) { sweep_ = std::move(per_trajectory); return *this; }
 

@@ -36,6 +36,7 @@ int deb_solve_heat_mol(const deb_heat_problem* P) {
     if (orc_solve_heat_mol(P, 0) != 0) { g_err = "the oracle rejected the problem"; return DEB_ERR_BAD_ARG; }
     return DEB_OK;
 }
+int deb_define_ode_sensitivity(int32_t, int32_t, const char*, const char*, const char*, int32_t*) { g_err = "user-defined systems need the GPU library"; return DEB_ERR_UNSUPPORTED; }
 int deb_define_event(int32_t, const char*, int32_t*) { g_err = "user-defined events need the GPU library"; return DEB_ERR_UNSUPPORTED; }
 
 int deb_solve_ode(const deb_ode_problem* P, deb_result* R) {

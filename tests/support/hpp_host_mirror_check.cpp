@@ -112,6 +112,9 @@ int main() {
         thrown = false;
         try { System::from_source(1, "dydt[0] = y[0];", {}); } catch (const deb::CallError& e) { thrown = e.code == DEB_ERR_UNSUPPORTED; }
         CHECK(thrown);  // (this build has the oracle behind the ABI)
+        thrown = false;
+        try { System::sensitivity_from_source(1, "dydt[0] = p[0] * y[0];", "J[0] = p[0];", "Jp[0] = y[0];", {1.0}); } catch (const deb::CallError& e) { thrown = e.code == DEB_ERR_UNSUPPORTED; }
+        CHECK(thrown);
         // vector tolerances and fixed-step methods
         auto vt = EnsembleIVP::ode(System::lorenz(10.0, 28.0, 8.0 / 3.0), 0.0, 1.0, {1.0, 1.0, 1.0}).t_eval({0.5, 1.0})
                       .method(ExplicitRungeKutta::rkf45().rtol({1e-8, 1e-8, 1e-8}).atol({1e-9, 1e-9, 1e-9})).solve();
